@@ -1,0 +1,283 @@
+"""ctypes binding of the CPU ORACLE (oracle/liborb_oracle.so) and of oracle/_ref/liborb_ref.so.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liborb_oracle.so")
+REF_LIB = os.path.join(HERE, "_ref", "liborb_ref.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f32p = C.POINTER(C.c_float)
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference exists). Building is not using."""
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "orb_oracle.c")):
+        subprocess.check_call(["make", "-C", HERE, "-B", "liborb_oracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/src/ORBextractor.cc"):
+        srcs = [os.path.join(HERE, "ref_glue.cc"), os.path.join(HERE, "cvshim", "opencv2", "core", "core.hpp")]
+        if all(os.path.exists(s) for s in srcs):
+            stale = (not os.path.exists(REF_LIB)) or any(os.path.getmtime(REF_LIB) < os.path.getmtime(s) for s in srcs)
+            if force or stale:
+                subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.oc_round_f.restype = C.c_int; L.oc_round_f.argtypes = [C.c_float]
+        L.oc_fast_atan2.restype = C.c_float; L.oc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.oc_cosf.restype = C.c_float; L.oc_cosf.argtypes = [C.c_float]
+        L.oc_sinf.restype = C.c_float; L.oc_sinf.argtypes = [C.c_float]
+        L.oc_resize_linear_8u.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+        L.oc_border_reflect101.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oc_gaussian7x7_s2.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.oc_fast_score.restype = C.c_int; L.oc_fast_score.argtypes = [u8p, C.c_int]
+        L.oc_fast9_16.restype = C.c_int
+        L.oc_fast9_16.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.oc_ic_angle.restype = C.c_float; L.oc_ic_angle.argtypes = [C.c_void_p, C.c_int, i32p]
+        L.oc_orb_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_float, u8p]
+        L.oc_distribute_octtree.restype = C.c_int
+        L.oc_distribute_octtree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.oc_descriptor_distance.restype = C.c_int; L.oc_descriptor_distance.argtypes = [u8p, u8p]
+        L.oc_hamming_top2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p, C.c_int]
+        L.oc_stereo_hamming.argtypes = [C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int, C.c_int, f32p,
+                                        C.c_float, C.c_float, i32p, i32p]
+        L.oc_create.restype = C.c_void_p
+        L.oc_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.oc_destroy.argtypes = [C.c_void_p]
+        L.oc_levels.restype = C.c_int; L.oc_levels.argtypes = [C.c_void_p]
+        L.oc_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, i32p, i32p]
+        L.oc_extract.restype = C.c_int
+        L.oc_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, u8p]
+        L.oc_level_size.restype = C.c_int
+        L.oc_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p, i32p]
+        L.oc_level_ptr.restype = C.c_void_p; L.oc_level_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.oc_level_blur_ptr.restype = C.c_void_p; L.oc_level_blur_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.oc_level_candidates.restype = C.c_int
+        L.oc_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.oc_level_nkeypoints.restype = C.c_int; L.oc_level_nkeypoints.argtypes = [C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _u8(a):
+    return a.ctypes.data_as(u8p)
+
+
+def resize_linear(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().oc_resize_linear_8u(_u8(src), src.shape[1], src.shape[0], src.shape[1], _u8(dst), dw, dh, dw)
+    return dst
+
+
+def border101(img: np.ndarray, b: int = 19) -> np.ndarray:
+    h, w = img.shape
+    whole = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    whole[b:b + h, b:b + w] = img
+    lib().oc_border_reflect101(_u8(whole), w, h, w + 2 * b, b)
+    return whole
+
+
+def gaussian7(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().oc_gaussian7x7_s2(_u8(img), img.shape[1], img.shape[0], img.shape[1], _u8(out), img.shape[1])
+    return out
+
+
+def fast(roi: np.ndarray, threshold: int, nms: bool = True) -> np.ndarray:
+    roi = np.ascontiguousarray(roi, np.uint8)
+    cap = roi.size
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().oc_fast9_16(_u8(roi), roi.shape[1], roi.shape[0], roi.shape[1], threshold, int(nms), out.ctypes.data, cap)
+    return out[:n]
+
+
+def fast_atan2(y, x) -> np.ndarray:
+    y = np.asarray(y, np.float32).ravel(); x = np.asarray(x, np.float32).ravel()
+    L = lib()
+    return np.array([L.oc_fast_atan2(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+
+
+def distribute_octtree(cand: np.ndarray, minX, maxX, minY, maxY, N) -> np.ndarray:
+    cand = np.ascontiguousarray(cand, KP_DTYPE)
+    out = np.zeros(max(len(cand), 1), KP_DTYPE)
+    n = lib().oc_distribute_octtree(cand.ctypes.data, len(cand), minX, maxX, minY, maxY, N, out.ctypes.data, len(out))
+    if n < 0:
+        raise RuntimeError(f"oc_distribute_octtree status {n}")
+    return out[:n]
+
+
+def hamming_top2(q: np.ndarray, t: np.ndarray, nthreads: int = 1):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    nq, nt = len(q), len(t)
+    idx = np.empty(nq, np.int32); d1 = np.empty(nq, np.int32); d2 = np.empty(nq, np.int32)
+    lib().oc_hamming_top2(_u8(q), nq, _u8(t), nt, idx.ctypes.data_as(i32p), d1.ctypes.data_as(i32p),
+                          d2.ctypes.data_as(i32p), nthreads)
+    return idx, d1, d2
+
+
+def descriptor_distance(a: np.ndarray, b: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().oc_descriptor_distance(_u8(a), _u8(b))
+
+
+def stereo_hamming(kl, dl, kr, dr, rows, scale_factors, minD, maxD):
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    bi = np.empty(len(kl), np.int32); bd = np.empty(len(kl), np.int32)
+    lib().oc_stereo_hamming(kl.ctypes.data, _u8(dl), len(kl), kr.ctypes.data, _u8(dr), len(kr), rows,
+                            sf.ctypes.data_as(f32p), minD, maxD, bi.ctypes.data_as(i32p), bd.ctypes.data_as(i32p))
+    return bi, bd
+
+
+class Extractor:
+    """Oracle mirror of ORB_SLAM2::ORBextractor (ORBextractor.h:51-145)."""
+
+    def __init__(self, nfeatures, scale, nlevels, ini_th, min_th):
+        self.L = lib()
+        self.h = self.L.oc_create(nfeatures, scale, nlevels, ini_th, min_th)
+        if not self.h:
+            raise ValueError("oc_create failed")
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.oc_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sf = np.zeros(n, np.float32); inv = np.zeros(n, np.float32)
+        s2 = np.zeros(n, np.float32); is2 = np.zeros(n, np.float32)
+        fpl = np.zeros(n, np.int32); um = np.zeros(16, np.int32)
+        self.L.oc_tables(self.h, sf.ctypes.data_as(f32p), inv.ctypes.data_as(f32p), s2.ctypes.data_as(f32p),
+                         is2.ctypes.data_as(f32p), fpl.ctypes.data_as(i32p), um.ctypes.data_as(i32p))
+        return dict(scale_factors=sf, inv_scale_factors=inv, sigma2=s2, inv_sigma2=is2,
+                    features_per_level=fpl, umax=um)
+
+    def extract(self, img: np.ndarray):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures * 2 + 64 * self.nlevels + 4096
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.oc_extract(self.h, _u8(img), img.shape[1], img.shape[0], img.shape[1], kps.ctypes.data, cap, _u8(desc))
+        if n < 0:
+            raise RuntimeError(f"oc_extract status {n}")
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l: int, blurred: bool = False) -> np.ndarray:
+        w = C.c_int32(); h = C.c_int32(); s = C.c_int32()
+        if self.L.oc_level_size(self.h, l, C.byref(w), C.byref(h), C.byref(s)) != 0:
+            raise RuntimeError("no level")
+        if blurred:
+            p = self.L.oc_level_blur_ptr(self.h, l)
+            if not p:
+                return None
+            buf = (C.c_uint8 * (w.value * h.value)).from_address(p)
+            return np.frombuffer(buf, np.uint8).reshape(h.value, w.value).copy()
+        p = self.L.oc_level_ptr(self.h, l)
+        # view including the apron
+        base = p - 19 * s.value - 19
+        buf = (C.c_uint8 * (s.value * (h.value + 38))).from_address(base)
+        whole = np.frombuffer(buf, np.uint8).reshape(h.value + 38, s.value).copy()
+        return whole
+
+    def candidates(self, l: int) -> np.ndarray:
+        n = self.L.oc_level_candidates(self.h, l, None, 0)
+        out = np.zeros(max(n, 1), KP_DTYPE)
+        self.L.oc_level_candidates(self.h, l, out.ctypes.data, n)
+        return out[:n]
+
+    def level_counts(self):
+        return [self.L.oc_level_nkeypoints(self.h, l) for l in range(self.nlevels)]
+
+
+# ---------------------------------------------------------------- oracle/_ref (verbatim reference + cvshim)
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        build()
+        R = C.CDLL(REF_LIB)
+        R.orbref_create.restype = C.c_void_p
+        R.orbref_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        R.orbref_destroy.argtypes = [C.c_void_p]
+        R.orbref_set_deterministic.argtypes = [C.c_int]
+        R.orbref_extract.restype = C.c_int
+        R.orbref_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, u8p]
+        R.orbref_level.restype = C.c_int
+        R.orbref_level.argtypes = [C.c_void_p, C.c_int, i32p, i32p, i32p, C.POINTER(C.c_void_p)]
+        R.orbref_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p]
+        R.orbref_bench.restype = C.c_double
+        R.orbref_bench.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        _ref = R
+    return _ref
+
+
+class RefExtractor:
+    """The verbatim reference ORBextractor (compiled against oracle/cvshim)."""
+
+    def __init__(self, nfeatures, scale, nlevels, ini_th, min_th, deterministic=True):
+        self.R = ref_lib()
+        self.R.orbref_set_deterministic(int(deterministic))
+        self.h = self.R.orbref_create(nfeatures, scale, nlevels, ini_th, min_th)
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.orbref_destroy(self.h)
+            self.h = None
+
+    def extract(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures * 2 + 64 * self.nlevels + 4096
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.R.orbref_extract(self.h, _u8(img), img.shape[1], img.shape[0], img.shape[1], kps.ctypes.data, cap, _u8(desc))
+        if n < 0:
+            raise RuntimeError(f"orbref_extract status {n}")
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l):
+        w = C.c_int32(); h = C.c_int32(); s = C.c_int32(); p = C.c_void_p()
+        self.R.orbref_level(self.h, l, C.byref(w), C.byref(h), C.byref(s), C.byref(p))
+        buf = (C.c_uint8 * (s.value * (h.value + 38))).from_address(p.value - 19 * s.value - 19)
+        return np.frombuffer(buf, np.uint8).reshape(h.value + 38, s.value).copy()
+
+    def tables(self):
+        n = self.nlevels
+        a = [np.zeros(n, np.float32) for _ in range(4)]
+        self.R.orbref_tables(self.h, *[x.ctypes.data_as(f32p) for x in a])
+        return dict(scale_factors=a[0], inv_scale_factors=a[1], sigma2=a[2], inv_sigma2=a[3])

@@ -1,0 +1,816 @@
+/*
+ * orb_oracle.c — CPU ORACLE (test infrastructure, NOT product code; see orb_oracle.h).
+ *
+ * Restates, function by function, the reference hot path (file:line relative to /root/reference):
+ *   src/ORBextractor.cc  IC_Angle :77-105, computeOrbDescriptor :110-152, ctor :416-490,
+ *                        DivideNode :501-560, DistributeOctTree :562-815,
+ *                        ComputeKeyPointsOctTree :818-946, operator() :1138-1211, ComputePyramid :1215-1250
+ *   src/ORBmatcher.cc    DescriptorDistance :1844-1860, best/second-best idiom :84-126
+ *   src/Frame.cc         ComputeStereoMatches Hamming stage :554-663
+ * and the un-vendored third-party arithmetic those lines call:
+ *   OpenCV 4.13 (cv2 4.13.0 is the only OpenCV in the authoring image; reference says "2.4.3 or 3.x",
+ *   CMakeLists.txt:31-37): resize INTER_LINEAR 8U, copyMakeBorder REFLECT_101, FAST 9-16 + NMS,
+ *   GaussianBlur 7x7 sigma 2 (fixed-point path), fastAtan2, cvRound.
+ *   glibc 2.39 x86_64 cosf/sinf (FMA ifunc variant), restated from its double-precision polynomial.
+ *
+ * Deterministic choice: the reference breaks count ties in DistributeOctTree's
+ * careful pass by comparing list-node ADDRESSES (ORBextractor.cc:733 sorts pair<int,ExtractorNode*>).
+ * The oracle uses the node CREATION SEQUENCE instead; oracle/_ref reproduces exactly that by running the
+ * verbatim reference under a monotonic bump allocator.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off (the reference is built -std=c++11 => no FMA contraction).
+ */
+#include "orb_oracle.h"
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+#define PATCH_SIZE 31
+#define HALF_PATCH_SIZE 15
+#define EDGE_THRESHOLD 19
+
+static const int8_t g_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+/* ------------------------------------------------------------------ cvRound / fastAtan2 / cosf / sinf */
+
+int oc_round_f(float v) { return (int)lrintf(v); } /* SSE cvtss2si: round-half-even */
+
+static int oc_round_d(double v) { return (int)lrint(v); }
+
+/* cv::fastAtan2 scalar path (OpenCV core mathfuncs_core: atanImpl<float>) */
+float oc_fast_atan2(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * scale;
+    const float p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale;
+    const float p7 = -0.04432655554792128f * scale;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+/* glibc 2.39 sincosf tables (sysdeps/ieee754/flt-32/s_sincosf_data.c), as IEEE-754 bit patterns.
+ * Entry 1 is entry 0 with the cosine coefficients negated. */
+static double dbits(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
+typedef struct { double sign[4], hpi_inv, hpi, c0, c1, c2, c3, c4, s1, s2, s3; } sincos_tab;
+static sincos_tab g_sc[2];
+static pthread_once_t g_sc_once = PTHREAD_ONCE_INIT;
+static void sc_init(void)
+{
+    for (int t = 0; t < 2; t++) {
+        double sg = t ? -1.0 : 1.0;
+        g_sc[t].sign[0] = 1.0; g_sc[t].sign[1] = -1.0; g_sc[t].sign[2] = -1.0; g_sc[t].sign[3] = 1.0;
+        g_sc[t].hpi_inv = dbits(0x41645f306dc9c883ull); /* 2/pi * 2^24 */
+        g_sc[t].hpi = dbits(0x3ff921fb54442d18ull);     /* pi/2 */
+        g_sc[t].c0 = sg * 1.0;
+        g_sc[t].c1 = sg * dbits(0xbfdffffffd0c621cull);
+        g_sc[t].c2 = sg * dbits(0x3fa55553e1068f19ull);
+        g_sc[t].c3 = sg * dbits(0xbf56c087e89a359dull);
+        g_sc[t].c4 = sg * dbits(0x3ef99343027bf8c3ull);
+        g_sc[t].s1 = dbits(0xbfc555545995a603ull);
+        g_sc[t].s2 = dbits(0x3f81107605230bc4ull);
+        g_sc[t].s3 = dbits(0xbf2994eb3774cf24ull);
+    }
+}
+static inline double sc_cos_poly(double x2, const sincos_tab* p)
+{
+    double x4 = x2 * x2;
+    double c2 = fma(p->c4, x2, p->c3);
+    double c1 = fma(p->c1, x2, p->c0);
+    double x6 = x2 * x4;
+    double c = fma(x4, p->c2, c1);
+    return fma(c2, x6, c);
+}
+static inline double sc_sin_poly(double x, double x2, const sincos_tab* p)
+{
+    double s1 = fma(p->s3, x2, p->s2);
+    double x3 = x2 * x;
+    double x7 = x2 * x3;
+    double s = fma(x3, p->s1, x);
+    return fma(s1, x7, s);
+}
+static inline uint32_t abstop12(float x) { uint32_t u; memcpy(&u, &x, 4); return (u >> 20) & 0x7ff; }
+/* valid for |x| < 120 (the descriptor angle is in [0, 2*pi]) */
+static double sc_reduce(double x, int* np)
+{
+    double r = x * g_sc[0].hpi_inv;
+    int n = ((int32_t)r + 0x800000) >> 24;
+    *np = n;
+    return fma(-(double)n, g_sc[0].hpi, x);
+}
+float oc_cosf(float y)
+{
+    pthread_once(&g_sc_once, sc_init);
+    double x = (double)y;
+    uint32_t t = abstop12(y);
+    if (t <= 0x3f3) {
+        if (t <= 0x397) return 1.0f;
+        return (float)sc_cos_poly(x * x, &g_sc[0]);
+    }
+    int n;
+    x = sc_reduce(x, &n);
+    const sincos_tab* p = &g_sc[(n >> 1) & 1];
+    double x2 = x * x;
+    if ((n & 1) == 0) return (float)sc_cos_poly(x2, p);
+    return (float)sc_sin_poly(x * g_sc[0].sign[n & 3], x2, p);
+}
+float oc_sinf(float y)
+{
+    pthread_once(&g_sc_once, sc_init);
+    double x = (double)y;
+    uint32_t t = abstop12(y);
+    if (t <= 0x3f3) {
+        if (t <= 0x397) return y;
+        return (float)sc_sin_poly(x, x * x, &g_sc[0]);
+    }
+    int n;
+    x = sc_reduce(x, &n);
+    const sincos_tab* p = &g_sc[(n >> 1) & 1];
+    double x2 = x * x;
+    if ((n & 1) == 0) return (float)sc_sin_poly(x * g_sc[0].sign[n & 3], x2, p);
+    return (float)sc_cos_poly(x2, p);
+}
+
+/* ------------------------------------------------------------------ cv::resize INTER_LINEAR, CV_8UC1 */
+/* OpenCV imgproc/resize.cpp: coefficient tables in float from a double scale, INTER_RESIZE_COEF_BITS=11,
+ * HResizeLinear (int accumulators) + VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>. */
+static void resize_axis_tab(int ssize, int dsize, int* ofs, short* coef)
+{
+    double scale = (double)ssize / (double)dsize;
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        ofs[d] = s;
+        float c0 = 1.f - f, c1 = f;
+        coef[2 * d] = (short)oc_round_f(c0 * 2048.f);
+        coef[2 * d + 1] = (short)oc_round_f(c1 * 2048.f);
+    }
+}
+void oc_resize_linear_8u(const uint8_t* src, int sw, int sh, int sstride,
+                         uint8_t* dst, int dw, int dh, int dstride)
+{
+    int* xofs = (int*)malloc(sizeof(int) * (size_t)(dw + dh));
+    int* yofs = xofs + dw;
+    short* ca = (short*)malloc(sizeof(short) * 2 * (size_t)(dw + dh));
+    short* cb = ca + 2 * dw;
+    int* rows = (int*)malloc(sizeof(int) * 2 * (size_t)dw);
+    resize_axis_tab(sw, dw, xofs, ca);
+    resize_axis_tab(sh, dh, yofs, cb);
+    for (int dy = 0; dy < dh; dy++) {
+        int sy0 = yofs[dy], sy1 = sy0 + 1 < sh ? sy0 + 1 : sh - 1;
+        const uint8_t* r0 = src + (size_t)sy0 * sstride;
+        const uint8_t* r1 = src + (size_t)sy1 * sstride;
+        int* S0 = rows; int* S1 = rows + dw;
+        for (int dx = 0; dx < dw; dx++) {
+            int sx0 = xofs[dx], sx1 = sx0 + 1 < sw ? sx0 + 1 : sw - 1;
+            int a0 = ca[2 * dx], a1 = ca[2 * dx + 1];
+            S0[dx] = r0[sx0] * a0 + r0[sx1] * a1;
+            S1[dx] = r1[sx0] * a0 + r1[sx1] * a1;
+        }
+        int b0 = cb[2 * dy], b1 = cb[2 * dy + 1];
+        uint8_t* D = dst + (size_t)dy * dstride;
+        for (int dx = 0; dx < dw; dx++)
+            D[dx] = (uint8_t)((((b0 * (S0[dx] >> 4)) >> 16) + ((b1 * (S1[dx] >> 4)) >> 16) + 2) >> 2);
+    }
+    free(rows); free(ca); free(xofs);
+}
+
+/* cv::copyMakeBorder(..., BORDER_REFLECT_101 [+ISOLATED]) in place: `whole` is the (w+2b)x(h+2b) buffer whose
+ * payload already sits at (b,b). */
+static inline int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) { if (p < 0) p = -p; else p = 2 * (len - 1) - p; }
+    return p;
+}
+void oc_border_reflect101(uint8_t* whole, int w, int h, int stride, int b)
+{
+    for (int y = 0; y < h; y++) {
+        uint8_t* row = whole + (size_t)(y + b) * stride;
+        for (int x = 0; x < b; x++) {
+            row[x] = row[b + reflect101(x - b, w)];
+            row[b + w + x] = row[b + reflect101(w + x, w)];
+        }
+    }
+    for (int y = 0; y < b; y++) {
+        memcpy(whole + (size_t)y * stride, whole + (size_t)(b + reflect101(y - b, h)) * stride, (size_t)(w + 2 * b));
+        memcpy(whole + (size_t)(b + h + y) * stride, whole + (size_t)(b + reflect101(h + y, h)) * stride, (size_t)(w + 2 * b));
+    }
+}
+
+/* ------------------------------------------------------------------ cv::GaussianBlur(7x7, 2, 2, REFLECT_101), CV_8U */
+/* OpenCV >= 3.4.1 / 4.x takes the fixed-point path (imgproc/smooth.simd.hpp, ufixedpoint16 kernel
+ * [18,34,48,56,48,34,18]/256): horizontal sums exact in 16 bits, vertical (sum + 2^15) >> 16. */
+void oc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride)
+{
+    static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
+    uint16_t* hb = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * (size_t)h);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* s = src + (size_t)y * sstride;
+        for (int x = 0; x < w; x++) {
+            int acc = 0;
+            for (int k = -3; k <= 3; k++) acc += K[k + 3] * s[reflect101(x + k, w)];
+            hb[(size_t)y * w + x] = (uint16_t)acc;
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        const uint16_t* r[7];
+        for (int k = -3; k <= 3; k++) r[k + 3] = hb + (size_t)reflect101(y + k, h) * w;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++) {
+            uint32_t acc = 0;
+            for (int k = 0; k < 7; k++) acc += (uint32_t)K[k] * r[k][x];
+            acc = (acc + 32768u) >> 16;
+            d[x] = (uint8_t)(acc > 255 ? 255 : acc);
+        }
+    }
+    free(hb);
+}
+
+/* ------------------------------------------------------------------ cv::FAST TYPE_9_16 (features2d/fast.cpp, fast_score.cpp) */
+static const int g_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+static const int g_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+/* cornerScore<16>(ptr, pixel, threshold): max(threshold, best bright arc, best dark arc) - 1 */
+static int corner_score(const uint8_t* p, int stride, int threshold)
+{
+    int d[25], v = p[0];
+    for (int k = 0; k < 25; k++) d[k] = v - p[g_ring_dy[k & 15] * stride + g_ring_dx[k & 15]];
+    int a0 = threshold;
+    for (int k = 0; k < 16; k += 2) {
+        int a = d[k + 1] < d[k + 2] ? d[k + 1] : d[k + 2];
+        for (int m = 3; m <= 8; m++) if (d[k + m] < a) a = d[k + m];
+        int t = a < d[k] ? a : d[k]; if (t > a0) a0 = t;
+        t = a < d[k + 9] ? a : d[k + 9]; if (t > a0) a0 = t;
+    }
+    int b0 = -a0;
+    for (int k = 0; k < 16; k += 2) {
+        int b = d[k + 1] > d[k + 2] ? d[k + 1] : d[k + 2];
+        for (int m = 3; m <= 8; m++) if (d[k + m] > b) b = d[k + m];
+        int t = b > d[k] ? b : d[k]; if (t < b0) b0 = t;
+        t = b > d[k + 9] ? b : d[k + 9]; if (t < b0) b0 = t;
+    }
+    return -b0 - 1;
+}
+int oc_fast_score(const uint8_t* p, int stride) { return corner_score(p, stride, 0); }
+
+/* FAST_t<16> corner test: >= 9 contiguous ring pixels all darker than v-T or all brighter than v+T */
+static int is_corner(const uint8_t* p, int stride, int T)
+{
+    int v = p[0], lo = v - T, hi = v + T;
+    int r0 = p[3 * stride], r8 = p[-3 * stride];
+    if (!((r0 < lo) | (r0 > hi) | (r8 < lo) | (r8 > hi))) return 0; /* every 9-arc holds ring[0] or ring[8] */
+    int dark = 0, bright = 0;
+    for (int k = 0; k < 25; k++) {
+        int x = p[g_ring_dy[k & 15] * stride + g_ring_dx[k & 15]];
+        if (x < lo) { if (++dark > 8) return 1; } else dark = 0;
+        if (x > hi) { if (++bright > 8) return 1; } else bright = 0;
+    }
+    return 0;
+}
+
+int oc_fast9_16(const uint8_t* roi, int w, int h, int stride, int threshold, int nms, OcKeyPoint* out, int cap)
+{
+    if (threshold < 0) threshold = 0;
+    if (threshold > 255) threshold = 255;
+    if (w < 7 || h < 7) return 0;
+    uint8_t* sc = (uint8_t*)calloc((size_t)w * (size_t)h, 1); /* score buffer: 0 = not a corner */
+    uint8_t* isc = (uint8_t*)calloc((size_t)w * (size_t)h, 1);
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            const uint8_t* p = roi + (size_t)y * stride + x;
+            if (is_corner(p, stride, threshold)) {
+                isc[(size_t)y * w + x] = 1;
+                sc[(size_t)y * w + x] = (uint8_t)corner_score(p, stride, threshold);
+            }
+        }
+    int n = 0;
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            if (!isc[(size_t)y * w + x]) continue;
+            int s = sc[(size_t)y * w + x];
+            if (nms) {
+                const uint8_t* c = sc + (size_t)y * w + x;
+                if (!(s > c[-1] && s > c[1] && s > c[-w - 1] && s > c[-w] && s > c[-w + 1] &&
+                      s > c[w - 1] && s > c[w] && s > c[w + 1])) continue;
+            }
+            if (n < cap) {
+                OcKeyPoint k = {(float)x, (float)y, 7.f, -1.f, nms ? (float)s : 0.f, 0, -1};
+                out[n] = k;
+            }
+            n++;
+        }
+    free(sc); free(isc);
+    return n;
+}
+
+/* ------------------------------------------------------------------ IC_Angle / rBRIEF (ORBextractor.cc:77-152) */
+float oc_ic_angle(const uint8_t* center, int step, const int* umax)
+{
+    int m_01 = 0, m_10 = 0;
+    for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+    for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+        int v_sum = 0, d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            int vp = center[u + v * step], vm = center[u - v * step];
+            v_sum += (vp - vm);
+            m_10 += u * (vp + vm);
+        }
+        m_01 += v * v_sum;
+    }
+    return oc_fast_atan2((float)m_01, (float)m_10);
+}
+
+void oc_orb_descriptor(const uint8_t* center, int step, float angle_deg, uint8_t* desc)
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float angle = angle_deg * factorPI;
+    float a = oc_cosf(angle), b = oc_sinf(angle);
+    const int8_t* pat = g_pattern;
+    for (int i = 0; i < 32; ++i, pat += 32) {
+        int val = 0;
+        for (int k = 0; k < 8; k++) {
+            int x0 = pat[4 * k], y0 = pat[4 * k + 1], x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];
+            int t0 = center[oc_round_f((float)x0 * b + (float)y0 * a) * step + oc_round_f((float)x0 * a - (float)y0 * b)];
+            int t1 = center[oc_round_f((float)x1 * b + (float)y1 * a) * step + oc_round_f((float)x1 * a - (float)y1 * b)];
+            val |= (t0 < t1) << k;
+        }
+        desc[i] = (uint8_t)val;
+    }
+}
+
+/* ------------------------------------------------------------------ DistributeOctTree (ORBextractor.cc:501-815) */
+typedef struct {
+    int ULx, ULy, URx, BRy;    /* UL=(ULx,ULy) UR=(URx,ULy) BL=(ULx,BRy) BR=(URx,BRy) */
+    int* keys; int nkeys;      /* indices into the input vector, in input order */
+    int nomore, prev, next, seq;
+} QNode;
+typedef struct { QNode* n; int cnt, cap, head, tail, size, seq; } QList;
+
+static int ql_alloc(QList* L)
+{
+    if (L->cnt == L->cap) { L->cap = L->cap ? L->cap * 2 : 256; L->n = (QNode*)realloc(L->n, sizeof(QNode) * (size_t)L->cap); }
+    QNode* q = &L->n[L->cnt];
+    memset(q, 0, sizeof(*q));
+    q->prev = q->next = -1;
+    q->seq = L->seq++;
+    return L->cnt++;
+}
+static void ql_push_front(QList* L, int id)
+{
+    L->n[id].prev = -1; L->n[id].next = L->head;
+    if (L->head >= 0) L->n[L->head].prev = id; else L->tail = id;
+    L->head = id; L->size++;
+}
+static void ql_push_back(QList* L, int id)
+{
+    L->n[id].next = -1; L->n[id].prev = L->tail;
+    if (L->tail >= 0) L->n[L->tail].next = id; else L->head = id;
+    L->tail = id; L->size++;
+}
+static int ql_erase(QList* L, int id) /* returns next */
+{
+    int p = L->n[id].prev, nx = L->n[id].next;
+    if (p >= 0) L->n[p].next = nx; else L->head = nx;
+    if (nx >= 0) L->n[nx].prev = p; else L->tail = p;
+    free(L->n[id].keys); L->n[id].keys = NULL;
+    L->size--;
+    return nx;
+}
+/* ExtractorNode::DivideNode: children ids returned in c[0..3] (n1..n4), not yet linked */
+static void q_divide(QList* L, int id, const OcKeyPoint* kp, int c[4])
+{
+    for (int k = 0; k < 4; k++) c[k] = ql_alloc(L); /* may realloc: take parent pointer afterwards */
+    QNode* P = &L->n[id];
+    int halfX = (int)ceilf((float)(P->URx - P->ULx) / 2);
+    int halfY = (int)ceilf((float)(P->BRy - P->ULy) / 2);
+    int midX = P->ULx + halfX, midY = P->ULy + halfY;
+    QNode* n1 = &L->n[c[0]]; QNode* n2 = &L->n[c[1]]; QNode* n3 = &L->n[c[2]]; QNode* n4 = &L->n[c[3]];
+    n1->ULx = P->ULx; n1->URx = midX;   n1->ULy = P->ULy; n1->BRy = midY;
+    n2->ULx = midX;   n2->URx = P->URx; n2->ULy = P->ULy; n2->BRy = midY;
+    n3->ULx = P->ULx; n3->URx = midX;   n3->ULy = midY;   n3->BRy = P->BRy;
+    n4->ULx = midX;   n4->URx = P->URx; n4->ULy = midY;   n4->BRy = P->BRy;
+    for (int k = 0; k < 4; k++) L->n[c[k]].keys = (int*)malloc(sizeof(int) * (size_t)(P->nkeys ? P->nkeys : 1));
+    for (int i = 0; i < P->nkeys; i++) {
+        const OcKeyPoint* k = &kp[P->keys[i]];
+        QNode* t;
+        if (k->x < (float)midX) t = (k->y < (float)midY) ? n1 : n3;
+        else t = (k->y < (float)midY) ? n2 : n4;
+        t->keys[t->nkeys++] = P->keys[i];
+    }
+    for (int k = 0; k < 4; k++) if (L->n[c[k]].nkeys == 1) L->n[c[k]].nomore = 1;
+}
+typedef struct { int size, seq, id; } QSizeNode;
+static int qsn_cmp(const void* a, const void* b)
+{
+    const QSizeNode* x = (const QSizeNode*)a; const QSizeNode* y = (const QSizeNode*)b;
+    if (x->size != y->size) return x->size < y->size ? -1 : 1;
+    return x->seq < y->seq ? -1 : (x->seq > y->seq); /* stand-in for the reference's pointer compare */
+}
+/* push the non-empty children (n1..n4 order) to the list front; record the expandable ones */
+static void q_link_children(QList* L, const int c[4], QSizeNode* v, int* nv, int* nToExpand)
+{
+    for (int k = 0; k < 4; k++) {
+        QNode* ch = &L->n[c[k]];
+        if (ch->nkeys > 0) {
+            /* creation order of the surviving list nodes = push order: re-stamp so dropped children don't count */
+            ch->seq = L->seq++;
+            ql_push_front(L, c[k]);
+            if (ch->nkeys > 1) {
+                if (nToExpand) (*nToExpand)++;
+                v[*nv].size = ch->nkeys; v[*nv].seq = ch->seq; v[*nv].id = c[k]; (*nv)++;
+            }
+        } else { free(ch->keys); ch->keys = NULL; }
+    }
+}
+
+int oc_distribute_octtree(const OcKeyPoint* in, int n, int minX, int maxX, int minY, int maxY,
+                          int N, OcKeyPoint* out, int cap)
+{
+    const int nIni = (int)roundf((float)(maxX - minX) / (float)(maxY - minY));
+    if (nIni < 1) return -2; /* reference divides by zero here (portrait level) */
+    const float hX = (float)(maxX - minX) / (float)nIni;
+    QList L; memset(&L, 0, sizeof(L)); L.head = L.tail = -1;
+    int* ini = (int*)malloc(sizeof(int) * (size_t)nIni);
+    for (int i = 0; i < nIni; i++) {
+        int id = ql_alloc(&L);
+        QNode* q = &L.n[id];
+        q->ULx = (int)(hX * (float)i); q->URx = (int)(hX * (float)(i + 1));
+        q->ULy = 0; q->BRy = maxY - minY;
+        q->keys = (int*)malloc(sizeof(int) * (size_t)(n ? n : 1));
+        ql_push_back(&L, id);
+        ini[i] = id;
+    }
+    for (int i = 0; i < n; i++) {
+        QNode* q = &L.n[ini[(size_t)(in[i].x / hX)]];
+        q->keys[q->nkeys++] = i;
+    }
+    for (int it = L.head; it >= 0;) {
+        if (L.n[it].nkeys == 1) { L.n[it].nomore = 1; it = L.n[it].next; }
+        else if (L.n[it].nkeys == 0) it = ql_erase(&L, it);
+        else it = L.n[it].next;
+    }
+    int finish = 0;
+    QSizeNode* v = (QSizeNode*)malloc(sizeof(QSizeNode) * (size_t)(4 * (n + nIni) + 16));
+    QSizeNode* vprev = (QSizeNode*)malloc(sizeof(QSizeNode) * (size_t)(4 * (n + nIni) + 16));
+    int nv = 0;
+    while (!finish) {
+        int prevSize = L.size, nToExpand = 0;
+        nv = 0;
+        for (int it = L.head; it >= 0;) {
+            if (L.n[it].nomore) { it = L.n[it].next; continue; }
+            int c[4];
+            q_divide(&L, it, in, c);
+            q_link_children(&L, c, v, &nv, &nToExpand);
+            it = ql_erase(&L, it);
+        }
+        if (L.size >= N || L.size == prevSize) finish = 1;
+        else if (L.size + nToExpand * 3 > N) {
+            while (!finish) {
+                prevSize = L.size;
+                int nprev = nv;
+                memcpy(vprev, v, sizeof(QSizeNode) * (size_t)nv);
+                nv = 0;
+                qsort(vprev, (size_t)nprev, sizeof(QSizeNode), qsn_cmp);
+                for (int j = nprev - 1; j >= 0; j--) {
+                    int c[4];
+                    q_divide(&L, vprev[j].id, in, c);
+                    q_link_children(&L, c, v, &nv, NULL);
+                    ql_erase(&L, vprev[j].id);
+                    if (L.size >= N) break;
+                }
+                if (L.size >= N || L.size == prevSize) finish = 1;
+            }
+        }
+    }
+    int m = 0;
+    for (int it = L.head; it >= 0; it = L.n[it].next) {
+        const QNode* q = &L.n[it];
+        int best = q->keys[0];
+        float maxR = in[best].response;
+        for (int k = 1; k < q->nkeys; k++)
+            if (in[q->keys[k]].response > maxR) { best = q->keys[k]; maxR = in[best].response; }
+        if (m < cap) out[m] = in[best];
+        m++;
+    }
+    for (int i = 0; i < L.cnt; i++) free(L.n[i].keys);
+    free(L.n); free(ini); free(v); free(vprev);
+    return m;
+}
+
+/* ------------------------------------------------------------------ Hamming (ORBmatcher.cc:1844-1860, :84-126) */
+int oc_descriptor_distance(const uint8_t* a, const uint8_t* b)
+{
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t pa, pb; memcpy(&pa, a + 4 * i, 4); memcpy(&pb, b + 4 * i, 4);
+        uint32_t v = pa ^ pb;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24);
+    }
+    return dist;
+}
+static inline int dist_fast(const uint64_t* a, const uint64_t* b)
+{
+    return __builtin_popcountll(a[0] ^ b[0]) + __builtin_popcountll(a[1] ^ b[1]) +
+           __builtin_popcountll(a[2] ^ b[2]) + __builtin_popcountll(a[3] ^ b[3]);
+}
+typedef struct { const uint8_t* q; const uint8_t* t; int q0, q1, nt; int32_t *idx1, *d1, *d2; } Top2Job;
+static void* top2_worker(void* arg)
+{
+    Top2Job* J = (Top2Job*)arg;
+    for (int i = J->q0; i < J->q1; i++) {
+        uint64_t qa[4]; memcpy(qa, J->q + 32 * (size_t)i, 32);
+        int best = 256, second = 256, bi = -1;
+        for (int j = 0; j < J->nt; j++) {
+            uint64_t tb[4]; memcpy(tb, J->t + 32 * (size_t)j, 32);
+            int d = dist_fast(qa, tb); /* == oc_descriptor_distance (tests check) */
+            if (d < best) { second = best; best = d; bi = j; }
+            else if (d < second) second = d;
+        }
+        J->idx1[i] = bi; J->d1[i] = best; J->d2[i] = second;
+    }
+    return NULL;
+}
+void oc_hamming_top2(const uint8_t* q, int nq, const uint8_t* t, int nt,
+                     int32_t* idx1, int32_t* d1, int32_t* d2, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256]; Top2Job jobs[256];
+    int per = (nq + nthreads - 1) / nthreads;
+    for (int k = 0; k < nthreads; k++) {
+        int q0 = k * per, q1 = q0 + per > nq ? nq : q0 + per;
+        if (q0 > nq) q0 = nq;
+        Top2Job j = {q, t, q0, q1, nt, idx1, d1, d2};
+        jobs[k] = j;
+        if (nthreads == 1) top2_worker(&jobs[k]); else pthread_create(&th[k], NULL, top2_worker, &jobs[k]);
+    }
+    if (nthreads > 1) for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+}
+
+/* Frame::ComputeStereoMatches, Hamming stage (Frame.cc:554-663): row-band table of right keypoints,
+ * octave +-1 and disparity gates, best distance with init TH_HIGH=100, strict <. Output per left keypoint:
+ * best right index (or -1 when no candidate beat 100) and its distance; callers accept dist < 75. */
+void oc_stereo_hamming(const OcKeyPoint* kl, const uint8_t* dl, int nl,
+                       const OcKeyPoint* kr, const uint8_t* dr, int nr,
+                       int rows, const float* sf, float minD, float maxD,
+                       int32_t* best_idx_r, int32_t* best_dist)
+{
+    /* vRowIndices as CSR; filling in ascending iR keeps each row's push_back order (:564-590) */
+    int* start = (int*)calloc((size_t)rows + 1, sizeof(int));
+    for (int pass = 0; pass < 2; pass++) {
+        int* fill = pass ? (int*)calloc((size_t)rows, sizeof(int)) : NULL;
+        static int dummy;
+        int* tab = pass ? (int*)malloc(sizeof(int) * (size_t)(start[rows] ? start[rows] : 1)) : &dummy;
+        for (int iR = 0; iR < nr; iR++) {
+            float kpY = kr[iR].y;
+            float r = 2.0f * sf[kr[iR].octave];
+            int maxr = (int)ceilf(kpY + r), minr = (int)floorf(kpY - r);
+            for (int yi = minr; yi <= maxr; yi++) {
+                if (yi < 0 || yi >= rows) continue; /* the reference would index out of bounds; never happens for extractor output */
+                if (!pass) start[yi + 1]++; else tab[start[yi] + fill[yi]++] = iR;
+            }
+        }
+        if (!pass) { for (int y = 0; y < rows; y++) start[y + 1] += start[y]; continue; }
+        for (int iL = 0; iL < nl; iL++) {
+            best_idx_r[iL] = -1; best_dist[iL] = 100; /* ORBmatcher::TH_HIGH */
+            const int levelL = kl[iL].octave;
+            const float vL = kl[iL].y, uL = kl[iL].x;
+            const int row = (int)vL;
+            if (row < 0 || row >= rows || start[row + 1] == start[row]) continue;
+            const float minU = uL - maxD, maxU = uL - minD;
+            if (maxU < 0) continue;
+            int bestDist = 100, bestIdx = -1;
+            for (int c = start[row]; c < start[row + 1]; c++) {
+                const int iR = tab[c];
+                if (kr[iR].octave < levelL - 1 || kr[iR].octave > levelL + 1) continue;
+                const float uR = kr[iR].x;
+                if (uR >= minU && uR <= maxU) {
+                    int d = oc_descriptor_distance(dl + 32 * (size_t)iL, dr + 32 * (size_t)iR);
+                    if (d < bestDist) { bestDist = d; bestIdx = iR; }
+                }
+            }
+            best_idx_r[iL] = bestIdx; best_dist[iL] = bestDist;
+        }
+        free(tab); free(fill);
+    }
+    free(start);
+}
+
+/* ------------------------------------------------------------------ extractor object */
+#define OC_MAX_LEVELS 32
+struct OcExtractor {
+    int nfeatures, nlevels, iniTh, minTh;
+    double scaleFactor;                      /* ORBextractor.h: `double scaleFactor` */
+    float sf[OC_MAX_LEVELS], inv_sf[OC_MAX_LEVELS], sigma2[OC_MAX_LEVELS], inv_sigma2[OC_MAX_LEVELS];
+    int per_level[OC_MAX_LEVELS], umax[HALF_PATCH_SIZE + 1];
+    /* per-call state */
+    uint8_t* whole[OC_MAX_LEVELS]; int lw[OC_MAX_LEVELS], lh[OC_MAX_LEVELS];
+    uint8_t* blur[OC_MAX_LEVELS];
+    OcKeyPoint* cand[OC_MAX_LEVELS]; int ncand[OC_MAX_LEVELS];
+    int nkp[OC_MAX_LEVELS];
+};
+
+OcExtractor* oc_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh)
+{
+    if (nlevels < 1 || nlevels > OC_MAX_LEVELS) return NULL;
+    OcExtractor* e = (OcExtractor*)calloc(1, sizeof(*e));
+    e->nfeatures = nfeatures; e->scaleFactor = scaleFactor; e->nlevels = nlevels; e->iniTh = iniTh; e->minTh = minTh;
+    e->sf[0] = 1.0f; e->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        e->sf[i] = (float)(e->sf[i - 1] * e->scaleFactor);
+        e->sigma2[i] = e->sf[i] * e->sf[i];
+    }
+    for (int i = 0; i < nlevels; i++) { e->inv_sf[i] = 1.0f / e->sf[i]; e->inv_sigma2[i] = 1.0f / e->sigma2[i]; }
+    float factor = (float)(1.0f / e->scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        e->per_level[l] = oc_round_f(nDesired);
+        sum += e->per_level[l];
+        nDesired *= factor;
+    }
+    e->per_level[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    int v, v0, vmax = (int)floor(HALF_PATCH_SIZE * sqrtf(2.f) / 2 + 1);
+    int vmin = (int)ceil(HALF_PATCH_SIZE * sqrtf(2.f) / 2);
+    const double hp2 = HALF_PATCH_SIZE * HALF_PATCH_SIZE;
+    for (v = 0; v <= vmax; ++v) e->umax[v] = oc_round_d(sqrt(hp2 - v * v));
+    for (v = HALF_PATCH_SIZE, v0 = 0; v >= vmin; --v) {
+        while (e->umax[v0] == e->umax[v0 + 1]) ++v0;
+        e->umax[v] = v0;
+        ++v0;
+    }
+    return e;
+}
+static void oc_release_frame(OcExtractor* e)
+{
+    for (int l = 0; l < OC_MAX_LEVELS; l++) {
+        free(e->whole[l]); e->whole[l] = NULL;
+        free(e->blur[l]); e->blur[l] = NULL;
+        free(e->cand[l]); e->cand[l] = NULL;
+        e->ncand[l] = 0; e->nkp[l] = 0;
+    }
+}
+void oc_destroy(OcExtractor* e) { if (e) { oc_release_frame(e); free(e); } }
+int oc_levels(const OcExtractor* e) { return e->nlevels; }
+void oc_tables(const OcExtractor* e, float* sf, float* inv_sf, float* s2, float* inv_s2, int* fpl, int* umax16)
+{
+    for (int i = 0; i < e->nlevels; i++) {
+        if (sf) sf[i] = e->sf[i];
+        if (inv_sf) inv_sf[i] = e->inv_sf[i];
+        if (s2) s2[i] = e->sigma2[i];
+        if (inv_s2) inv_s2[i] = e->inv_sigma2[i];
+        if (fpl) fpl[i] = e->per_level[i];
+    }
+    if (umax16) for (int i = 0; i < 16; i++) umax16[i] = e->umax[i];
+}
+int oc_level_size(const OcExtractor* e, int l, int* w, int* h, int* stride)
+{
+    if (l < 0 || l >= e->nlevels || !e->whole[l]) return -1;
+    *w = e->lw[l]; *h = e->lh[l]; *stride = e->lw[l] + 2 * EDGE_THRESHOLD;
+    return 0;
+}
+const uint8_t* oc_level_ptr(const OcExtractor* e, int l)
+{
+    return e->whole[l] ? e->whole[l] + (size_t)EDGE_THRESHOLD * (e->lw[l] + 2 * EDGE_THRESHOLD) + EDGE_THRESHOLD : NULL;
+}
+const uint8_t* oc_level_blur_ptr(const OcExtractor* e, int l) { return e->blur[l]; }
+int oc_level_candidates(const OcExtractor* e, int l, OcKeyPoint* out, int cap)
+{
+    int n = e->ncand[l] < cap ? e->ncand[l] : cap;
+    if (out && n > 0) memcpy(out, e->cand[l], sizeof(OcKeyPoint) * (size_t)n);
+    return e->ncand[l];
+}
+int oc_level_nkeypoints(const OcExtractor* e, int l) { return e->nkp[l]; }
+
+int oc_extract(OcExtractor* e, const uint8_t* img, int w, int h, int stride,
+               OcKeyPoint* kps, int cap, uint8_t* desc)
+{
+    if (!img || w <= 0 || h <= 0) return 0; /* :1141 empty image -> silent return */
+    oc_release_frame(e);
+    const int B = EDGE_THRESHOLD;
+    /* ---- ComputePyramid :1215-1250 ---- */
+    for (int l = 0; l < e->nlevels; l++) {
+        float scale = e->inv_sf[l];
+        int lw = oc_round_f((float)w * scale), lh = oc_round_f((float)h * scale);
+        int ws = lw + 2 * B;
+        e->lw[l] = lw; e->lh[l] = lh;
+        e->whole[l] = (uint8_t*)malloc((size_t)ws * (size_t)(lh + 2 * B));
+        uint8_t* pay = e->whole[l] + (size_t)B * ws + B;
+        if (l != 0) {
+            const uint8_t* prev = e->whole[l - 1] + (size_t)B * (e->lw[l - 1] + 2 * B) + B;
+            oc_resize_linear_8u(prev, e->lw[l - 1], e->lh[l - 1], e->lw[l - 1] + 2 * B, pay, lw, lh, ws);
+        } else {
+            for (int y = 0; y < h; y++) memcpy(pay + (size_t)y * ws, img + (size_t)y * stride, (size_t)w);
+        }
+        oc_border_reflect101(e->whole[l], lw, lh, ws, B);
+    }
+    /* ---- ComputeKeyPointsOctTree :818-946 ---- */
+    OcKeyPoint** lvl = (OcKeyPoint**)calloc((size_t)e->nlevels, sizeof(OcKeyPoint*));
+    int status = 0;
+    const float W = 30;
+    for (int l = 0; l < e->nlevels && status == 0; l++) {
+        const int ws = e->lw[l] + 2 * B;
+        const uint8_t* pay = e->whole[l] + (size_t)B * ws + B;
+        const int minBorderX = B - 3, minBorderY = minBorderX;
+        const int maxBorderX = e->lw[l] - B + 3, maxBorderY = e->lh[l] - B + 3;
+        const float width = (float)(maxBorderX - minBorderX), height = (float)(maxBorderY - minBorderY);
+        const int nCols = (int)(width / W), nRows = (int)(height / W);
+        if (nCols < 1 || nRows < 1) { status = -2; break; } /* reference divides by zero */
+        const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+        int capc = 1024, nc = 0;
+        OcKeyPoint* cand = (OcKeyPoint*)malloc(sizeof(OcKeyPoint) * (size_t)capc);
+        OcKeyPoint* cell = (OcKeyPoint*)malloc(sizeof(OcKeyPoint) * (size_t)((wCell + 6) * (hCell + 6)));
+        for (int i = 0; i < nRows; i++) {
+            const float iniY = (float)(minBorderY + i * hCell);
+            float maxY = iniY + hCell + 6;
+            if (iniY >= maxBorderY - 3) continue;
+            if (maxY > maxBorderY) maxY = (float)maxBorderY;
+            for (int j = 0; j < nCols; j++) {
+                const float iniX = (float)(minBorderX + j * wCell);
+                float maxX = iniX + wCell + 6;
+                if (iniX >= maxBorderX - 6) continue;
+                if (maxX > maxBorderX) maxX = (float)maxBorderX;
+                const int y0 = (int)iniY, y1 = (int)maxY, x0 = (int)iniX, x1 = (int)maxX;
+                const uint8_t* roi = pay + (size_t)y0 * ws + x0;
+                int n = oc_fast9_16(roi, x1 - x0, y1 - y0, ws, e->iniTh, 1, cell, (wCell + 6) * (hCell + 6));
+                if (n == 0) n = oc_fast9_16(roi, x1 - x0, y1 - y0, ws, e->minTh, 1, cell, (wCell + 6) * (hCell + 6));
+                for (int k = 0; k < n; k++) {
+                    cell[k].x += j * wCell; cell[k].y += i * hCell;
+                    if (nc == capc) { capc *= 2; cand = (OcKeyPoint*)realloc(cand, sizeof(OcKeyPoint) * (size_t)capc); }
+                    cand[nc++] = cell[k];
+                }
+            }
+        }
+        free(cell);
+        e->cand[l] = cand; e->ncand[l] = nc;
+        int capl = nc > 0 ? nc : 1;
+        lvl[l] = (OcKeyPoint*)malloc(sizeof(OcKeyPoint) * (size_t)capl);
+        int m = oc_distribute_octtree(cand, nc, minBorderX, maxBorderX, minBorderY, maxBorderY, e->per_level[l], lvl[l], capl);
+        if (m < 0) { status = m; break; }
+        e->nkp[l] = m;
+        const int scaledPatchSize = (int)(PATCH_SIZE * e->sf[l]);
+        for (int k = 0; k < m; k++) {
+            lvl[l][k].x += minBorderX; lvl[l][k].y += minBorderY;
+            lvl[l][k].octave = l; lvl[l][k].size = (float)scaledPatchSize;
+        }
+    }
+    if (status == 0)
+        for (int l = 0; l < e->nlevels; l++) { /* computeOrientation :492-499 on the un-blurred level */
+            const int ws = e->lw[l] + 2 * B;
+            const uint8_t* pay = e->whole[l] + (size_t)B * ws + B;
+            for (int k = 0; k < e->nkp[l]; k++)
+                lvl[l][k].angle = oc_ic_angle(pay + (size_t)oc_round_f(lvl[l][k].y) * ws + oc_round_f(lvl[l][k].x), ws, e->umax);
+        }
+    /* ---- operator() :1160-1210 ---- */
+    int total = 0;
+    if (status == 0) {
+        for (int l = 0; l < e->nlevels; l++) total += e->nkp[l];
+        if (total > cap) status = -1;
+    }
+    if (status == 0) {
+        int offset = 0;
+        for (int l = 0; l < e->nlevels; l++) {
+            int n = e->nkp[l];
+            if (n == 0) continue;
+            const int ws = e->lw[l] + 2 * B;
+            const uint8_t* pay = e->whole[l] + (size_t)B * ws + B;
+            e->blur[l] = (uint8_t*)malloc((size_t)e->lw[l] * (size_t)e->lh[l]);
+            oc_gaussian7x7_s2(pay, e->lw[l], e->lh[l], ws, e->blur[l], e->lw[l]);
+            for (int k = 0; k < n; k++) {
+                OcKeyPoint* kp = &lvl[l][k];
+                const uint8_t* c = e->blur[l] + (size_t)oc_round_f(kp->y) * e->lw[l] + oc_round_f(kp->x);
+                oc_orb_descriptor(c, e->lw[l], kp->angle, desc + 32 * (size_t)(offset + k));
+            }
+            if (l != 0) {
+                float scale = e->sf[l];
+                for (int k = 0; k < n; k++) { lvl[l][k].x *= scale; lvl[l][k].y *= scale; }
+            }
+            memcpy(kps + offset, lvl[l], sizeof(OcKeyPoint) * (size_t)n);
+            offset += n;
+        }
+    }
+    for (int l = 0; l < e->nlevels; l++) free(lvl[l]);
+    free(lvl);
+    return status == 0 ? total : status;
+}

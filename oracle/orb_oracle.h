@@ -1,0 +1,71 @@
+/*
+ * orb_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the reference's ORB front-end hot path
+ * (qpc001/ORB_SLAM2_Commit: src/ORBextractor.cc, src/ORBmatcher.cc:1844-1860, src/Frame.cc:547-663)
+ * with the OpenCV primitives it calls (resize / copyMakeBorder / FAST / GaussianBlur / fastAtan2 /
+ * cvRound) restated from OpenCV 4.13's 8-bit arithmetic.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+ * Pinning: tests/golden/ (cv2 4.13 primitive outputs, tools/gen_golden.py) and oracle/_ref (the verbatim
+ * reference ORBextractor.cc compiled against oracle/cvshim).
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* identical to cv::KeyPoint (28 bytes) */
+typedef struct { float x, y, size, angle, response; int octave, class_id; } OcKeyPoint;
+
+/* ---- OpenCV primitive restatements ---- */
+int   oc_round_f(float v);                      /* cvRound: round-half-even */
+float oc_fast_atan2(float y, float x);          /* cv::fastAtan2 scalar path */
+float oc_cosf(float x);                         /* glibc 2.39 x86_64 (FMA variant) cosf, restated */
+float oc_sinf(float x);
+void  oc_resize_linear_8u(const uint8_t* src, int sw, int sh, int sstride,
+                          uint8_t* dst, int dw, int dh, int dstride);
+void  oc_border_reflect101(uint8_t* whole, int w, int h, int stride, int border);
+void  oc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+int   oc_fast_score(const uint8_t* p, int stride);           /* cornerScore<16> with threshold floor 0 */
+int   oc_fast9_16(const uint8_t* roi, int w, int h, int stride, int threshold, int nms,
+                  OcKeyPoint* out, int cap);                 /* cv::FAST(roi, kps, threshold, nms) */
+
+/* ---- reference functions ---- */
+float oc_ic_angle(const uint8_t* center, int stride, const int* umax);          /* ORBextractor.cc:77-105 */
+void  oc_orb_descriptor(const uint8_t* center, int stride, float angle_deg, uint8_t* desc32); /* :110-152 */
+int   oc_distribute_octtree(const OcKeyPoint* in, int n, int minX, int maxX, int minY, int maxY,
+                            int N, OcKeyPoint* out, int cap);                   /* :562-815 */
+int   oc_descriptor_distance(const uint8_t* a, const uint8_t* b);               /* ORBmatcher.cc:1844-1860 */
+void  oc_hamming_top2(const uint8_t* q, int nq, const uint8_t* t, int nt,
+                      int32_t* idx1, int32_t* d1, int32_t* d2, int nthreads);   /* ORBmatcher.cc:84-126 idiom */
+
+/* stereo row-band Hamming stage of Frame::ComputeStereoMatches (Frame.cc:554-663) */
+void  oc_stereo_hamming(const OcKeyPoint* kl, const uint8_t* dl, int nl,
+                        const OcKeyPoint* kr, const uint8_t* dr, int nr,
+                        int rows, const float* scale_factors, float minD, float maxD,
+                        int32_t* best_idx_r, int32_t* best_dist);
+
+/* ---- extractor object (ORBextractor.cc:416-490, 1138-1250) ---- */
+typedef struct OcExtractor OcExtractor;
+OcExtractor* oc_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+void  oc_destroy(OcExtractor*);
+int   oc_levels(const OcExtractor*);
+void  oc_tables(const OcExtractor*, float* sf, float* inv_sf, float* sigma2, float* inv_sigma2,
+                int* features_per_level, int* umax16);
+/* returns number of keypoints (<= cap) or -1 on overflow; 0 for an empty image */
+int   oc_extract(OcExtractor*, const uint8_t* img, int w, int h, int stride,
+                 OcKeyPoint* kps, int cap, uint8_t* desc);
+/* stage taps, valid after oc_extract */
+int   oc_level_size(const OcExtractor*, int level, int* w, int* h, int* stride);
+const uint8_t* oc_level_ptr(const OcExtractor*, int level);      /* payload origin (apron is around it) */
+const uint8_t* oc_level_blur_ptr(const OcExtractor*, int level); /* blurred level, stride = w ; NULL if skipped */
+int   oc_level_candidates(const OcExtractor*, int level, OcKeyPoint* out, int cap); /* pre-quadtree list */
+int   oc_level_nkeypoints(const OcExtractor*, int level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,111 @@
+"""Seeded synthetic inputs (numpy only, bit-reproducible on any host).
+
+The reference ships no images and no datasets, so every test and bench line runs on
+frames from this generator: smoothed noise stretched to 0..255 (corner-rich), random flat rectangles
+(strong FAST corners + cells that need the minThFAST retry) and one large flat region (empty cells).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# extractor settings named by BASELINE.json `configs` (the YAML files are absent from the reference tree)
+CONFIGS = {
+    "tum1": dict(width=640, height=480, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7),
+    "kitti": dict(width=1241, height=376, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
+                  fx=718.856, bf=386.1448),
+    "euroc": dict(width=752, height=480, nfeatures=1200, scale=1.2, nlevels=8, ini_th=20, min_th=7,
+                  fx=435.2047, bf=47.90639384423901),
+    "4k": dict(width=3840, height=2160, nfeatures=8000, scale=1.2, nlevels=12, ini_th=20, min_th=7),
+}
+
+
+def _smooth(a: np.ndarray, sigma: float) -> np.ndarray:
+    """Separable Gaussian with reflect-101 borders, summed in a fixed order (deterministic float64)."""
+    r = int(3 * sigma + 0.5)
+    k = np.exp(-0.5 * (np.arange(-r, r + 1) / sigma) ** 2)
+    k /= k.sum()
+    for axis in (0, 1):
+        pad = [(0, 0), (0, 0)]
+        pad[axis] = (r, r)
+        p = np.pad(a, pad, mode="reflect")
+        out = np.zeros_like(a)
+        n = a.shape[axis]
+        for i in range(2 * r + 1):
+            sl = [slice(None), slice(None)]
+            sl[axis] = slice(i, i + n)
+            out += k[i] * p[tuple(sl)]
+        a = out
+    return a
+
+
+def synth_image(width: int, height: int, seed: int, sigma: float = 1.6) -> np.ndarray:
+    """One 8-bit grayscale frame, C-contiguous (height, width)."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (height, width)).astype(np.float64)
+    s = _smooth(base, sigma)
+    lo, hi = s.min(), s.max()
+    img = np.clip((s - lo) * (255.0 / (hi - lo)), 0, 255)
+    img = np.floor(img + 0.5).astype(np.uint8)
+    nrect = max(4, (width * height) // 1500)
+    xs = rng.integers(0, width, nrect)
+    ys = rng.integers(0, height, nrect)
+    ws = rng.integers(5, 61, nrect)
+    hs = rng.integers(5, 61, nrect)
+    gs = rng.integers(0, 256, nrect)
+    keep = rng.random(nrect) < 0.35  # most of the textured background stays visible
+    for x, y, w, h, g, k in zip(xs, ys, ws, hs, gs, keep):
+        if k:
+            img[y:y + h, x:x + w] = g
+    # one large flat region -> cells with no corner at either threshold
+    fw, fh = width // 5, height // 4
+    fx = int(rng.integers(0, width - fw))
+    fy = int(rng.integers(0, height - fh))
+    img[fy:fy + fh, fx:fx + fw] = int(rng.integers(0, 256))
+    # a low-contrast patch: corners only at the min threshold
+    lw, lh = width // 6, height // 5
+    lx = int(rng.integers(0, width - lw))
+    ly = int(rng.integers(0, height - lh))
+    patch = img[ly:ly + lh, lx:lx + lw].astype(np.int32)
+    img[ly:ly + lh, lx:lx + lw] = (128 + (patch - 128) // 6).astype(np.uint8)
+    return np.ascontiguousarray(img)
+
+
+def synth_stereo_pair(width: int, height: int, seed: int, max_disp: int = 60):
+    """Left frame + a right frame = left shifted by a per-row-band disparity, plus noise (sigma 2)."""
+    left = synth_image(width, height, seed)
+    rng = np.random.default_rng(seed + 7_000_003)
+    right = np.empty_like(left)
+    band = 24
+    for y0 in range(0, height, band):
+        d = int(rng.integers(0, max_disp + 1))
+        rows = left[y0:y0 + band]
+        shifted = np.empty_like(rows)
+        if d:
+            shifted[:, :width - d] = rows[:, d:]
+            shifted[:, width - d:] = rows[:, -1:]
+        else:
+            shifted[:] = rows
+        right[y0:y0 + band] = shifted
+    noise = np.floor(rng.normal(0.0, 2.0, right.shape) + 0.5).astype(np.int32)
+    right = np.clip(right.astype(np.int32) + noise, 0, 255).astype(np.uint8)
+    return left, np.ascontiguousarray(right)
+
+
+def synth_descriptors(n_train: int, n_query: int, seed: int = 42, max_flips: int = 40, n_dup: int = 8):
+    """Config 4 inputs: random 256-bit train rows; queries = train rows with 0..max_flips bit flips.
+    A few train rows are duplicated so exact distance ties (lowest index must win) occur."""
+    rng = np.random.default_rng(seed)
+    train = rng.integers(0, 256, (n_train, 32), dtype=np.uint8)
+    rng2 = np.random.default_rng(seed + 1)
+    perm = rng2.integers(0, n_train, n_query)
+    query = train[perm].copy()
+    flips = rng2.integers(0, max_flips + 1, n_query)
+    for i in range(n_query):
+        if flips[i]:
+            bits = rng2.choice(256, int(flips[i]), replace=False)
+            np.bitwise_xor.at(query[i], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    for j in range(min(n_dup, n_query, n_train // 2)):
+        src = int(perm[j])
+        dst = (src + 1 + j * 7919) % n_train
+        train[dst] = train[src]
+    return np.ascontiguousarray(train), np.ascontiguousarray(query)

@@ -1,0 +1,98 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz — runs ONLY in the authoring container (needs cv2 4.13 and /root/reference).
+
+  prims_cv2.npz      inputs + outputs of the cv2 4.13 primitives the reference calls
+                     (resize INTER_LINEAR, copyMakeBorder REFLECT_101, GaussianBlur 7x7 s2, FAST 9-16 NMS at
+                     T=20 and T=7 on whole images and cell-sized crops, fastAtan2)
+  ref_<cfg>.npz      keypoints (28-byte cv::KeyPoint records) + descriptors + per-level pyramid CRCs produced by
+                     oracle/_ref = the UNMODIFIED /root/reference/src/ORBextractor.cc (bump-allocator build)
+  sincos.json        result of the exhaustive oc_cosf/oc_sinf == glibc cosf/sinf check
+"""
+import json, os, subprocess, sys, zlib
+import numpy as np
+import cv2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import binding as ob
+from orb_slam2_commit_b200 import synth
+
+G = os.path.join(ROOT, "tests", "golden")
+os.makedirs(G, exist_ok=True)
+assert cv2.__version__.startswith("4.13"), cv2.__version__
+
+
+def kps_to_arr(kps):
+    return np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id) for k in kps],
+                    dtype=ob.KP_DTYPE)
+
+
+def prims():
+    out = {"cv2_version": np.array(cv2.__version__)}
+    rng = np.random.default_rng(123)
+    # resize: the four BASELINE level-0 -> level-1 geometries at reduced height + odd sizes
+    for i, (w, h, dw, dh) in enumerate([(640, 96, 533, 80), (1241, 60, 1034, 50), (752, 64, 627, 53),
+                                        (97, 71, 81, 59), (214, 161, 179, 134), (63, 62, 52, 52)]):
+        src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        out[f"resize{i}_src"] = src
+        out[f"resize{i}_dst"] = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    for i, (w, h) in enumerate([(160, 120), (67, 45), (9, 8)]):
+        src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        out[f"blur{i}_src"] = src
+        out[f"blur{i}_dst"] = cv2.GaussianBlur(src, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        out[f"border{i}_dst"] = cv2.copyMakeBorder(src, 19, 19, 19, 19, cv2.BORDER_REFLECT_101) if min(w, h) > 19 else \
+            cv2.copyMakeBorder(src, 3, 3, 3, 3, cv2.BORDER_REFLECT_101)
+    img = synth.synth_image(320, 240, 5)
+    out["fast_img"] = img
+    for T in (20, 7):
+        det = cv2.FastFeatureDetector_create(T, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+        out[f"fast_full_T{T}"] = kps_to_arr(det.detect(img))
+        for j, (y0, x0, hh, ww) in enumerate([(16, 16, 36, 36), (100, 200, 37, 38), (3, 280, 24, 40), (200, 0, 40, 7)]):
+            out[f"fast_crop{j}_T{T}"] = kps_to_arr(det.detect(np.ascontiguousarray(img[y0:y0 + hh, x0:x0 + ww])))
+            out[f"fast_crop{j}_rect"] = np.array([y0, x0, hh, ww])
+    ys = rng.integers(-400000, 400000, 4096).astype(np.float32)
+    xs = rng.integers(-400000, 400000, 4096).astype(np.float32)
+    ys[:64] = 0; xs[32:96] = 0; ys[96:128] = xs[96:128]
+    out["atan2_y"] = ys; out["atan2_x"] = xs
+    out["atan2_deg"] = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in zip(ys, xs)], np.float32)
+    np.savez_compressed(os.path.join(G, "prims_cv2.npz"), **out)
+    print("prims_cv2.npz", {k: v.shape for k, v in out.items() if k.startswith("fast_full")})
+
+
+def ref_cases():
+    assert ob.ref_available() or True
+    ob.build(force=True)
+    cases = [("tum1", 1), ("kitti", 2), ("euroc", 1000), ("small", 11)]
+    for name, seed in cases:
+        if name == "small":
+            c = dict(width=200, height=150, nfeatures=150, scale=1.2, nlevels=4, ini_th=20, min_th=7)
+        else:
+            c = synth.CONFIGS[name]
+        img = synth.synth_image(c["width"], c["height"], seed)
+        r = ob.RefExtractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"], deterministic=True)
+        kps, desc = r.extract(img)
+        crcs = np.array([zlib.crc32(r.level(l).tobytes()) for l in range(c["nlevels"])], np.uint32)
+        sizes = np.array([r.level(l).shape for l in range(c["nlevels"])], np.int32)
+        t = r.tables()
+        np.savez_compressed(os.path.join(G, f"ref_{name}.npz"), seed=seed, img_crc=zlib.crc32(img.tobytes()),
+                            cfg=json.dumps(c), keypoints=kps, descriptors=desc, level_crc=crcs, level_whole_shape=sizes,
+                            **t)
+        print(f"ref_{name}.npz", len(kps), sizes[0], hex(crcs[0]))
+
+
+def sincos():
+    exe = "/tmp/check_sincos"
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-ffp-contract=off", "-mfma", "-o", exe,
+                           os.path.join(ROOT, "oracle", "check_sincos.c"), os.path.join(ROOT, "oracle", "orb_oracle.c"),
+                           "-I", os.path.join(ROOT, "oracle"), "-lm", "-lpthread"])
+    res = json.loads(subprocess.check_output([exe, "1"]).decode())
+    res["libm"] = subprocess.check_output(["ldd", "--version"]).decode().splitlines()[0]
+    json.dump(res, open(os.path.join(G, "sincos.json"), "w"), indent=1)
+    print(res)
+
+
+if __name__ == "__main__":
+    prims()
+    ref_cases()
+    if "--sincos" in sys.argv:
+        sincos()
