@@ -1,0 +1,140 @@
+/*
+ * orbx.h — C ABI of the B200-native ORB front-end (liborbx.so, hand-written sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary for ORB-SLAM2's data-parallel hot path. The reference has no FFI: its seam is the
+ * C++ class ORB_SLAM2::ORBextractor (include/ORBextractor.h:51-145) and the static function
+ * ORBmatcher::DescriptorDistance (include/ORBmatcher.h:50). The C++ shim in orb_slam2_commit_b200/host/ keeps that
+ * class surface and calls only the functions below; INTEGRATION.md shows the bindings.
+ * Every entry point cites the reference interface it replaces (file:line relative to the reference tree).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns an orbx_status (0 = ok);
+ * there is NO CPU fallback — without a CUDA device every compute call returns ORBX_ERR_CUDA.
+ * An orbx_extractor is not re-entrant (like the reference instance, which mutates mvImagePyramid); two different
+ * instances may be driven concurrently from two host threads (Frame.cc:80-84 does exactly that for stereo).
+ */
+#ifndef ORBX_H
+#define ORBX_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define ORBX_ABI_VERSION 1
+
+typedef enum {
+    ORBX_OK = 0,
+    ORBX_ERR_INVALID = 1,      /* bad argument (null pointer, non-positive size, nlevels out of range) */
+    ORBX_ERR_UNSUPPORTED = 2,  /* geometry the reference itself cannot handle (a level < 62 px, portrait level
+                                  => nIni == 0, ORBextractor.cc:567,846) or beyond this build's limits (> 4096 px) */
+    ORBX_ERR_CAPACITY = 3,     /* caller buffer too small for the keypoints produced */
+    ORBX_ERR_CUDA = 4,         /* CUDA runtime error / no device; see orbx_last_error() */
+    ORBX_ERR_STATE = 5         /* call order (e.g. pyramid requested before any extract) */
+} orbx_status;
+
+/* Bit-identical to cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct OrbxKeyPoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} OrbxKeyPoint;
+
+typedef struct orbx_extractor orbx_extractor;
+
+const char* orbx_last_error(void);          /* thread-local text of the last failure */
+int orbx_abi_version(void);
+int orbx_device_count(void);                /* 0 when no CUDA device is visible */
+
+/* ---- ORBextractor::ORBextractor(int,float,int,int,int)  (ORBextractor.h:61, ORBextractor.cc:416-490) ---- */
+int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                int device, orbx_extractor** out);
+/* ---- ~ORBextractor  (ORBextractor.h:64) ---- */
+void orbx_destroy(orbx_extractor* h);
+
+/* ---- GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ *      GetInverseScaleSigmaSquares  (ORBextractor.h:81-101); arrays hold nlevels entries, any may be NULL.
+ *      features_per_level = mnFeaturesPerLevel (ORBextractor.cc:446-457), umax16 = the IC_Angle disc table. ---- */
+int   orbx_get_levels(const orbx_extractor* h);
+float orbx_get_scale_factor(const orbx_extractor* h);
+int   orbx_get_tables(const orbx_extractor* h, float* scale_factors, float* inv_scale_factors,
+                      float* level_sigma2, float* inv_level_sigma2, int32_t* features_per_level, int32_t* umax16);
+
+/* Pre-size the HBM-resident working set for frames of width x height, up to max_batch frames per call.
+ * Optional: the extract calls do it lazily. Returns ORBX_ERR_UNSUPPORTED for geometry the reference cannot run. */
+int orbx_reserve(orbx_extractor* h, int width, int height, int max_batch);
+/* Upper bound of keypoints per frame for the reserved geometry (sum over levels of quota + slack). */
+int orbx_max_keypoints(const orbx_extractor* h);
+
+/* ---- ORBextractor::operator()(InputArray image, InputArray mask, vector<KeyPoint>&, OutputArray descriptors)
+ *      (ORBextractor.h:77, ORBextractor.cc:1138-1211). Host buffers in, host buffers out, synchronous.
+ *      image: 8-bit single channel, `stride` bytes between rows. mask is ignored by the reference (ORBextractor.h:68).
+ *      keypoints[cap], descriptors[cap*32] (row i <-> keypoint i, CV_8U 32-byte rows), *nkp = number produced.
+ *      Empty image (NULL / w<=0 / h<=0): returns ORBX_OK with *nkp = 0 and outputs untouched (ORBextractor.cc:1141). ---- */
+int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height, int stride,
+                 OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
+
+/* Frame-batched form of the same call (frames are independent; BASELINE configs 3 and 5): n images of identical
+ * size; images[i] points at frame i. keypoints[n*cap], descriptors[n*cap*32], nkp[n]. Pinned host memory makes the
+ * copies asynchronous; pageable memory works too. */
+int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height, int stride,
+                       OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
+
+/* Device-resident form: frames already in HBM (frame i at d_images + i*frame_pitch_bytes), outputs stay in HBM.
+ * Asynchronous on `cuda_stream` (a cudaStream_t passed as void*; NULL = the extractor's own stream).
+ * d_keypoints[n*cap], d_descriptors[n*cap*32], d_nkp[n] (device pointers). Keypoints beyond cap are dropped and
+ * d_nkp still reports the true count, so the caller can detect ORBX_ERR_CAPACITY after synchronising. */
+int orbx_extract_device(orbx_extractor* h, const uint8_t* d_images, int n, int width, int height, int stride,
+                        size_t frame_pitch_bytes, OrbxKeyPoint* d_keypoints, int cap, int32_t* d_nkp,
+                        uint8_t* d_descriptors, void* cuda_stream);
+int orbx_synchronize(orbx_extractor* h);
+
+/* ---- std::vector<cv::Mat> mvImagePyramid  (ORBextractor.h:104; read by Frame.cc:556,681-700) ----
+ * Level geometry of the last extract, and a copy of level `level` of frame `frame` INCLUDING its 19-px
+ * BORDER_REFLECT_101 apron into dst ((h+38) rows of (w+38) bytes, dst_stride >= w+38) — the layout of the reference's
+ * backing `temp` buffer (ORBextractor.cc:1225-1229); the payload starts at dst + 19*dst_stride + 19. */
+int orbx_level_size(const orbx_extractor* h, int level, int* width, int* height);
+int orbx_pyramid_level(orbx_extractor* h, int frame, int level, uint8_t* dst, int dst_stride);
+/* Device view of the same level: payload origin, pitch in bytes (apron lies around it in HBM). */
+int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level, const uint8_t** d_payload, int* pitch);
+
+/* Stage tap for parity tests: the pre-quadtree candidate list of (frame, level) in the reference's order
+ * (cell-row-major, then FAST's row-major; ORBextractor.cc:903-912), coordinates relative to minBorder. */
+int orbx_debug_candidates(orbx_extractor* h, int frame, int level, OrbxKeyPoint* out, int cap, int* n);
+int orbx_debug_level_counts(orbx_extractor* h, int frame, int32_t* counts /* nlevels */);
+
+/* ---- ORBmatcher::DescriptorDistance (ORBmatcher.h:50, ORBmatcher.cc:1844-1860) + the best / second-best search
+ *      idiom around it (ORBmatcher.cc:84-126): for every query row the FIRST train index attaining the minimum
+ *      distance, that distance, and the second-smallest distance counted with multiplicity; all three are 256 / -1 /
+ *      256 when no train row is closer than 256 (the reference's initial values). 32-byte rows, 4-byte aligned. ---- */
+int orbx_hamming_top2(const uint8_t* query, int nq, const uint8_t* train, int nt,
+                      int32_t* idx1, int32_t* dist1, int32_t* dist2, int device);
+/* Device-resident, asynchronous. Result per query packed as (dist1 << 48) | (dist2 << 32) | uint32(idx1);
+ * `d_packed[nq]` must be initialised with orbx_hamming_init_device (or hold a previous partial result: results
+ * are MERGED into it, which is how train shards — on one GPU or across GPUs — combine). index_base is added to
+ * the local train index. */
+int orbx_hamming_init_device(uint64_t* d_packed, int nq, void* cuda_stream);
+int orbx_hamming_top2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int64_t index_base,
+                             uint64_t* d_packed, void* cuda_stream);
+/* Merge `nparts` packed partial results (part p at d_parts + p*nq) — e.g. the all-gathered per-GPU results — and
+ * unpack into idx1/dist1/dist2 (device pointers, any may be NULL). */
+int orbx_hamming_merge_device(const uint64_t* d_parts, int nparts, int nq,
+                              int32_t* d_idx1, int32_t* d_dist1, int32_t* d_dist2, void* cuda_stream);
+
+/* ---- Frame::ComputeStereoMatches, Hamming stage (Frame.cc:554-663): for every left keypoint the best right
+ *      keypoint among the row-band candidates with octave within +-1 and uR in [uL-maxD, uL-minD], initial best
+ *      TH_HIGH = 100, strict '<' in ascending right index. Host buffers, synchronous.
+ *      best_idx_r[i] = -1 and best_dist[i] = 100 when nothing beat 100. ---- */
+int orbx_stereo_hamming(const OrbxKeyPoint* kp_left, const uint8_t* desc_left, int n_left,
+                        const OrbxKeyPoint* kp_right, const uint8_t* desc_right, int n_right,
+                        int rows, const float* scale_factors, int nlevels, float minD, float maxD,
+                        int32_t* best_idx_r, int32_t* best_dist, int device);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

@@ -1,0 +1,12 @@
+"""B200-native ORB feature front-end — drop-in for ORB-SLAM2's ORBextractor / Hamming best-second-best search.
+
+The product is `csrc/liborbx.so` (hand-written sm_100a CUDA kernels behind the C ABI of include/orbx.h).
+This package is only the thin host mirror used by the tests and bench.py: same names and argument meaning as the
+reference class (include/ORBextractor.h:51-145). There is no CPU fallback: loading fails loudly when the
+library is missing and every compute call fails when no CUDA device is visible.
+"""
+from .api import (KP_DTYPE, OrbxError, ORBextractor, ORBmatcher, build_library, hamming_top2, lib, library_path,
+                  stereo_hamming)
+
+__all__ = ["KP_DTYPE", "OrbxError", "ORBextractor", "ORBmatcher", "build_library", "hamming_top2", "lib",
+           "library_path", "stereo_hamming"]

@@ -1,0 +1,248 @@
+"""ctypes binding of liborbx.so + the host-side mirror of the reference interface."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])  # == cv::KeyPoint, 28 bytes
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f32p = C.POINTER(C.c_float)
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"orbx status {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(CSRC, "liborbx.so")
+
+
+def build_library(force: bool = False) -> str:
+    """Compile liborbx.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc"))]
+    srcs.append(os.path.join(HERE, "..", "include", "orbx.h"))
+    so = library_path()
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        args = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
+        subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    """Load liborbx.so. Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        so = library_path()
+        if not os.path.exists(so):
+            raise OrbxError(-1, f"{so} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+        L = C.CDLL(so)
+        L.orbx_last_error.restype = C.c_char_p
+        L.orbx_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.orbx_destroy.argtypes = [C.c_void_p]
+        L.orbx_get_levels.argtypes = [C.c_void_p]
+        L.orbx_get_scale_factor.argtypes = [C.c_void_p]; L.orbx_get_scale_factor.restype = C.c_float
+        L.orbx_get_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, i32p, i32p]
+        L.orbx_reserve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orbx_max_keypoints.argtypes = [C.c_void_p]
+        L.orbx_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, i32p, u8p]
+        L.orbx_extract_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int, i32p, C.c_void_p]
+        L.orbx_extract_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_synchronize.argtypes = [C.c_void_p]
+        L.orbx_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
+        L.orbx_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, C.c_int]
+        L.orbx_pyramid_level_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), i32p]
+        L.orbx_debug_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, i32p]
+        L.orbx_debug_level_counts.argtypes = [C.c_void_p, C.c_int, i32p]
+        L.orbx_hamming_top2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p, C.c_int]
+        L.orbx_hamming_init_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orbx_hamming_top2_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orbx_hamming_merge_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_stereo_hamming.argtypes = [C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int, C.c_int, f32p, C.c_int,
+                                          C.c_float, C.c_float, i32p, i32p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise OrbxError(rc, lib().orbx_last_error().decode())
+
+
+def _u8(a):
+    return a.ctypes.data_as(u8p)
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM2::ORBextractor (include/ORBextractor.h:51-145): same constructor arguments, same getters,
+    `__call__(image, mask)` -> (keypoints, descriptors) like operator(), `mvImagePyramid` like the public member."""
+
+    HARRIS_SCORE = 0
+    FAST_SCORE = 1
+
+    def __init__(self, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int, device: int = 0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        _ck(self._L.orbx_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device, C.byref(self._h)))
+        self.nfeatures, self.nlevels, self.device = nfeatures, nlevels, device
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.orbx_destroy(h)
+            self._h = None
+
+    # ---- getters (ORBextractor.h:81-101)
+    def GetLevels(self) -> int:
+        return self._L.orbx_get_levels(self._h)
+
+    def GetScaleFactor(self) -> float:
+        return self._L.orbx_get_scale_factor(self._h)
+
+    def _tables(self):
+        n = self.nlevels
+        a = [np.zeros(n, np.float32) for _ in range(4)]
+        fpl = np.zeros(n, np.int32); um = np.zeros(16, np.int32)
+        _ck(self._L.orbx_get_tables(self._h, *[x.ctypes.data_as(f32p) for x in a], fpl.ctypes.data_as(i32p), um.ctypes.data_as(i32p)))
+        return a + [fpl, um]
+
+    def GetScaleFactors(self):
+        return self._tables()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3]
+
+    def features_per_level(self):
+        return self._tables()[4]
+
+    def umax(self):
+        return self._tables()[5]
+
+    # ---- operator() (ORBextractor.h:77)
+    def __call__(self, image: np.ndarray, mask=None):
+        """image: 2-D uint8 array (any row stride). mask is ignored, as in the reference (ORBextractor.h:68).
+        Returns (keypoints[KP_DTYPE], descriptors[n,32] uint8); an empty image returns empty outputs."""
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 required (ORBextractor.cc:1146)"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        _ck(self._L.orbx_reserve(self._h, w, h, 1))
+        cap = self._L.orbx_max_keypoints(self._h)
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int32(0)
+        _ck(self._L.orbx_extract(self._h, _u8(image), w, h, image.strides[0], kps.ctypes.data, cap, C.byref(n), _u8(desc)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, max_batch: int = 64):
+        """images: sequence of equally sized 2-D uint8 arrays, or one (n,h,w) array. Returns lists."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        if n == 0:
+            return [], []
+        h, w = imgs[0].shape
+        _ck(self._L.orbx_reserve(self._h, w, h, min(n, max_batch)))
+        cap = self._L.orbx_max_keypoints(self._h)
+        kps = np.zeros((n, cap), KP_DTYPE); desc = np.zeros((n, cap, 32), np.uint8); nk = np.zeros(n, np.int32)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        _ck(self._L.orbx_extract_batch(self._h, ptrs, n, w, h, w, kps.ctypes.data, cap, nk.ctypes.data_as(i32p), desc.ctypes.data))
+        return [kps[i, :nk[i]].copy() for i in range(n)], [desc[i, :nk[i]].copy() for i in range(n)]
+
+    # ---- device-resident form used by bench.py (pointers are plain integers, e.g. torch.Tensor.data_ptr())
+    def reserve(self, width, height, max_batch):
+        _ck(self._L.orbx_reserve(self._h, width, height, max_batch))
+        return self._L.orbx_max_keypoints(self._h)
+
+    def extract_device(self, d_images, n, width, height, stride, frame_pitch, d_kps, cap, d_nkp, d_desc, stream=0):
+        _ck(self._L.orbx_extract_device(self._h, d_images, n, width, height, stride, frame_pitch, d_kps, cap, d_nkp, d_desc, stream))
+
+    def synchronize(self):
+        _ck(self._L.orbx_synchronize(self._h))
+
+    # ---- mvImagePyramid (ORBextractor.h:104)
+    def level_size(self, level):
+        w = C.c_int32(); h = C.c_int32()
+        _ck(self._L.orbx_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def pyramid_level(self, level: int, frame: int = 0, with_apron: bool = False) -> np.ndarray:
+        w, h = self.level_size(level)
+        whole = np.zeros((h + 38, w + 38), np.uint8)
+        _ck(self._L.orbx_pyramid_level(self._h, frame, level, _u8(whole), w + 38))
+        return whole if with_apron else whole[19:19 + h, 19:19 + w]
+
+    @property
+    def mvImagePyramid(self):
+        return [self.pyramid_level(l) for l in range(self.nlevels)]
+
+    # ---- stage taps for the parity tests
+    def debug_candidates(self, level: int, frame: int = 0) -> np.ndarray:
+        n = C.c_int32(0)
+        _ck(self._L.orbx_debug_candidates(self._h, frame, level, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), KP_DTYPE)
+        _ck(self._L.orbx_debug_candidates(self._h, frame, level, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
+    def debug_level_counts(self, frame: int = 0):
+        c = np.zeros(self.nlevels, np.int32)
+        _ck(self._L.orbx_debug_level_counts(self._h, frame, c.ctypes.data_as(i32p)))
+        return c
+
+
+def hamming_top2(query: np.ndarray, train: np.ndarray, device: int = 0):
+    """Best / second-best Hamming search (ORBmatcher.cc:84-126 idiom over DescriptorDistance :1844-1860).
+    Returns (idx1, dist1, dist2) int32 arrays."""
+    q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    nq, nt = len(q), len(t)
+    idx = np.full(nq, -1, np.int32); d1 = np.full(nq, 256, np.int32); d2 = np.full(nq, 256, np.int32)
+    if nq:
+        _ck(lib().orbx_hamming_top2(_u8(q), nq, _u8(t) if nt else None, nt, idx.ctypes.data_as(i32p),
+                                    d1.ctypes.data_as(i32p), d2.ctypes.data_as(i32p), device))
+    return idx, d1, d2
+
+
+def stereo_hamming(kp_left, desc_left, kp_right, desc_right, rows, scale_factors, minD, maxD, device: int = 0):
+    """Hamming stage of Frame::ComputeStereoMatches (Frame.cc:554-663). Returns (best_idx_right, best_dist)."""
+    kl = np.ascontiguousarray(kp_left, KP_DTYPE); kr = np.ascontiguousarray(kp_right, KP_DTYPE)
+    dl = np.ascontiguousarray(desc_left, np.uint8); dr = np.ascontiguousarray(desc_right, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    bi = np.full(len(kl), -1, np.int32); bd = np.full(len(kl), 100, np.int32)
+    _ck(lib().orbx_stereo_hamming(kl.ctypes.data, _u8(dl), len(kl), kr.ctypes.data, _u8(dr), len(kr), rows,
+                                  sf.ctypes.data_as(f32p), len(sf), minD, maxD, bi.ctypes.data_as(i32p),
+                                  bd.ctypes.data_as(i32p), device))
+    return bi, bd
+
+
+class ORBmatcher:
+    """The part of ORB_SLAM2::ORBmatcher that is on the hot path (include/ORBmatcher.h:50, ORBmatcher.cc:37-38)."""
+    TH_LOW = 50
+    TH_HIGH = 100
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray, device: int = 0) -> int:
+        """static int DescriptorDistance(const cv::Mat&, const cv::Mat&) — one 256-bit pair, on the GPU."""
+        _, d1, _ = hamming_top2(np.asarray(a, np.uint8).reshape(1, 32), np.asarray(b, np.uint8).reshape(1, 32), device)
+        return int(d1[0])

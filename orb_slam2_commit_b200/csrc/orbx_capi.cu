@@ -1,0 +1,567 @@
+// orbx_capi.cu — host side of liborbx.so: the C ABI of include/orbx.h, the per-instance HBM working set,
+// and the geometry tables (pyramid sizes, FAST cell grid, resize coefficients, quadtree roots, per-level quotas)
+// built with the reference's own float/double expressions (ORBextractor.cc:416-490, 829-879, 567-570, 1221-1225).
+// No OpenCV, no torch, no CPU fallback: without a CUDA device every compute entry point fails with ORBX_ERR_CUDA.
+#include "../../include/orbx.h"
+#include "orbx_internal.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ORBX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct orbx_extractor {
+    int nfeatures, nlevels, ini_th, min_th, device;
+    double scale_factor;                          // ORBextractor.h keeps it as double
+    std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    int umax[16];
+    // reserved geometry
+    int W = 0, H = 0, max_batch = 0;
+    std::vector<OrbxLevelGeom> lvl;
+    std::vector<OrbxCell> cells;
+    std::vector<OrbxResizeTap> taps;
+    int max_tile_w = 0, max_tile_h = 0;
+    OrbxFrameLayout L{};
+    // device memory
+    void* d_pool = nullptr;                       // one allocation carved into the arrays of L
+    OrbxLevelGeom* d_lvl = nullptr;
+    OrbxCell* d_cells = nullptr;
+    OrbxResizeTap* d_taps = nullptr;
+    uint8_t* d_in = nullptr;                      // [B][H][W] staging of host frames
+    OrbxKp28* d_kps = nullptr;                    // [B][kp_cap_total]
+    uint8_t* d_desc = nullptr;
+    int* d_nkp = nullptr;
+    // pinned host staging
+    uint8_t* h_in = nullptr;
+    OrbxKp28* h_kps = nullptr;
+    uint8_t* h_desc = nullptr;
+    int* h_nkp = nullptr;
+    cudaStream_t stream = nullptr;
+    int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
+    bool constants_ready = false;
+};
+
+static int round_half_even(float v) { return (int)lrintf(v); }   // cvRound
+
+extern "C" const char* orbx_last_error(void) { return g_err.c_str(); }
+extern "C" int orbx_abi_version(void) { return ORBX_ABI_VERSION; }
+extern "C" int orbx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device,
+                           orbx_extractor** out)
+{
+    if (!out) return fail(ORBX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "nlevels must be in [1,16]");
+    if (nfeatures < 0 || !(scaleFactor > 1.0f)) return fail(ORBX_ERR_INVALID, "nfeatures >= 0 and scaleFactor > 1 required");
+    orbx_extractor* h = new orbx_extractor();
+    h->nfeatures = nfeatures; h->nlevels = nlevels; h->ini_th = iniThFAST; h->min_th = minThFAST; h->device = device;
+    h->scale_factor = scaleFactor;
+    // scale tables (ORBextractor.cc:421-441)
+    h->sf.assign(nlevels, 1.0f); h->sigma2.assign(nlevels, 1.0f);
+    for (int i = 1; i < nlevels; i++) {
+        h->sf[i] = (float)(h->sf[i - 1] * h->scale_factor);
+        h->sigma2[i] = h->sf[i] * h->sf[i];
+    }
+    h->inv_sf.resize(nlevels); h->inv_sigma2.resize(nlevels);
+    for (int i = 0; i < nlevels; i++) { h->inv_sf[i] = 1.0f / h->sf[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+    // per-level quota: geometric series, remainder to the last level (ORBextractor.cc:446-457)
+    h->quota.assign(nlevels, 0);
+    const float factor = (float)(1.0f / h->scale_factor);
+    float desired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        h->quota[l] = round_half_even(desired);
+        sum += h->quota[l];
+        desired *= factor;
+    }
+    h->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // IC_Angle disc (ORBextractor.cc:473-489)
+    {
+        const int HP = 15;
+        int v, v0, vmax = (int)floor(HP * sqrtf(2.f) / 2 + 1), vmin = (int)ceil(HP * sqrtf(2.f) / 2);
+        const double hp2 = HP * HP;
+        for (v = 0; v <= vmax; ++v) h->umax[v] = (int)lrint(sqrt(hp2 - v * v));
+        for (v = HP, v0 = 0; v >= vmin; --v) {
+            while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+            h->umax[v] = v0;
+            ++v0;
+        }
+    }
+    *out = h;
+    return ORBX_OK;
+}
+
+static void release_device(orbx_extractor* h)
+{
+    if (h->device >= 0 && (h->d_pool || h->stream)) cudaSetDevice(h->device);
+    cudaFree(h->d_pool); h->d_pool = nullptr;
+    cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps);
+    h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr;
+    cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
+    h->d_in = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_nkp = nullptr;
+    cudaFreeHost(h->h_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc); cudaFreeHost(h->h_nkp);
+    h->h_in = nullptr; h->h_kps = nullptr; h->h_desc = nullptr; h->h_nkp = nullptr;
+    h->W = h->H = h->max_batch = 0;
+}
+
+extern "C" void orbx_destroy(orbx_extractor* h)
+{
+    if (!h) return;
+    release_device(h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+extern "C" int orbx_get_levels(const orbx_extractor* h) { return h ? h->nlevels : 0; }
+extern "C" float orbx_get_scale_factor(const orbx_extractor* h) { return h ? (float)h->scale_factor : 0.f; }
+extern "C" int orbx_get_tables(const orbx_extractor* h, float* sf, float* inv_sf, float* s2, float* inv_s2,
+                               int32_t* fpl, int32_t* umax16)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    for (int i = 0; i < h->nlevels; i++) {
+        if (sf) sf[i] = h->sf[i];
+        if (inv_sf) inv_sf[i] = h->inv_sf[i];
+        if (s2) s2[i] = h->sigma2[i];
+        if (inv_s2) inv_s2[i] = h->inv_sigma2[i];
+        if (fpl) fpl[i] = h->quota[i];
+    }
+    if (umax16) for (int i = 0; i < 16; i++) umax16[i] = h->umax[i];
+    return ORBX_OK;
+}
+
+// cv::resize INTER_LINEAR 8U coefficient table for one axis (OpenCV imgproc/resize.cpp)
+static void build_taps(int ssize, int dsize, OrbxResizeTap* out)
+{
+    const double scale = (double)ssize / (double)dsize;
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        out[d].ofs = (short)s;
+        out[d].c0 = (short)round_half_even((1.f - f) * 2048.f);
+        out[d].c1 = (short)round_half_even(f * 2048.f);
+        out[d].pad = 0;
+    }
+}
+
+static int build_geometry(orbx_extractor* h, int W, int H)
+{
+    if (W > ORBX_MAX_DIM || H > ORBX_MAX_DIM) return fail(ORBX_ERR_UNSUPPORTED, "image larger than 4096 px");
+    const int nl = h->nlevels;
+    h->lvl.assign(nl, OrbxLevelGeom{});
+    h->cells.clear(); h->taps.clear();
+    size_t raw = 0; int slot = 0, cand = 0, kpc = 0, qtcap = 0;
+    h->max_tile_w = h->max_tile_h = 8;
+    for (int l = 0; l < nl; l++) {
+        OrbxLevelGeom& g = h->lvl[l];
+        g.w = round_half_even((float)W * h->inv_sf[l]);          // from the ORIGINAL size (ORBextractor.cc:1223)
+        g.h = round_half_even((float)H * h->inv_sf[l]);
+        // FAST cell grid (ORBextractor.cc:829-847)
+        const int maxBX = g.w - ORBX_MINB, maxBY = g.h - ORBX_MINB;
+        const float width = (float)(maxBX - ORBX_MINB), height = (float)(maxBY - ORBX_MINB);
+        const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
+        if (nCols < 1 || nRows < 1)
+            return fail(ORBX_ERR_UNSUPPORTED, "pyramid level smaller than 62 px: the reference divides by zero here");
+        const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+        // quadtree roots (ORBextractor.cc:567-570)
+        g.nini = (int)roundf((float)(maxBX - ORBX_MINB) / (float)(maxBY - ORBX_MINB));
+        if (g.nini < 1) return fail(ORBX_ERR_UNSUPPORTED, "portrait pyramid level: nIni == 0 in the reference");
+        g.hx = (float)(maxBX - ORBX_MINB) / (float)g.nini;
+        g.quota = h->quota[l];
+        if (g.quota > ORBX_MAX_QUOTA) return fail(ORBX_ERR_UNSUPPORTED, "more than 2040 features on one level");
+        g.scale = h->sf[l];
+        g.kp_size = (float)(int)(31 * h->sf[l]);                  // scaledPatchSize (ORBextractor.cc:925)
+        g.pitch = (ORBX_XOFF + g.w + ORBX_EDGE + 3 + 31) & ~31;
+        g.raw_off = (int)raw;
+        raw += (size_t)g.pitch * (g.h + 2 * ORBX_EDGE);
+        raw = (raw + 255) & ~(size_t)255;
+        g.cell0 = (int)h->cells.size(); g.ncols = nCols; g.nrows = nRows;
+        g.cand_off = cand;
+        int lvl_slots = 0;
+        for (int i = 0; i < nRows; i++)
+            for (int j = 0; j < nCols; j++) {
+                // ROI [iniX,maxX) x [iniY,maxY); cv::FAST scores columns 3..cols-4 of it (ORBextractor.cc:855-879)
+                const int iniY = ORBX_MINB + i * hCell, iniX = ORBX_MINB + j * wCell;
+                const int maxY = std::min(iniY + hCell + 6, maxBY), maxX = std::min(iniX + wCell + 6, maxBX);
+                OrbxCell c{};
+                c.level = (short)l;
+                c.ex0 = (short)(iniX + 3); c.ex1 = (short)(maxX - 3);
+                c.ey0 = (short)(iniY + 3); c.ey1 = (short)(maxY - 3);
+                if (iniY >= maxBY - 3 || iniX >= maxBX - 6 || c.ex1 <= c.ex0 || c.ey1 <= c.ey0) { c.ex1 = c.ex0; c.ey1 = c.ey0; }
+                const int ew = c.ex1 - c.ex0, eh = c.ey1 - c.ey0;
+                c.slot_off = slot;
+                c.slot_cap = ((ew + 1) / 2) * ((eh + 1) / 2);    // strict 3x3 NMS: no two survivors are 8-adjacent
+                slot += c.slot_cap; lvl_slots += c.slot_cap;
+                h->max_tile_w = std::max(h->max_tile_w, ew + 6);
+                h->max_tile_h = std::max(h->max_tile_h, eh + 6);
+                h->cells.push_back(c);
+            }
+        g.cand_cap = std::min(lvl_slots, (1 << 23) - 1);
+        cand += g.cand_cap;
+        g.kp_cap = std::max(g.quota + 3, 4 * g.nini) + 1;
+        qtcap = std::max(qtcap, g.kp_cap);
+        h->L.lvl_kp_off[l] = kpc;
+        kpc += g.kp_cap;
+        // resize taps from level l-1
+        g.xtab_off = (int)h->taps.size();
+        if (l > 0) {
+            h->taps.resize(h->taps.size() + g.w + g.h);
+            build_taps(h->lvl[l - 1].w, g.w, h->taps.data() + g.xtab_off);
+            g.ytab_off = g.xtab_off + g.w;
+            build_taps(h->lvl[l - 1].h, g.h, h->taps.data() + g.ytab_off);
+        } else g.ytab_off = g.xtab_off;
+    }
+    OrbxFrameLayout& L = h->L;
+    L.nlevels = nl; L.ncells = (int)h->cells.size(); L.slot_total = slot; L.cand_total = cand; L.kp_cap_total = kpc;
+    L.ini_th = h->ini_th; L.min_th = h->min_th;
+    L.frame_raw_bytes = raw;
+    L.qt_cap = (qtcap + 31) & ~31;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_batch)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (width <= 0 || height <= 0 || max_batch <= 0) return fail(ORBX_ERR_INVALID, "width, height, max_batch must be positive");
+    if (width == h->W && height == h->H && max_batch <= h->max_batch) return ORBX_OK;
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(h->device));
+    if (!h->stream) CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamSynchronize(h->stream));
+    release_device(h);
+    int rc = build_geometry(h, width, height);
+    if (rc != ORBX_OK) return rc;
+    OrbxFrameLayout& L = h->L;
+    const size_t B = (size_t)max_batch;
+    // one pool for the per-frame arrays
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_raw = carve(B * L.frame_raw_bytes);
+    const size_t o_slots = carve(B * L.slot_total * sizeof(uint32_t));
+    const size_t o_cc = carve(B * L.ncells * sizeof(int));
+    const size_t o_cand = carve(B * L.cand_total * sizeof(uint32_t));
+    const size_t o_node = carve(B * L.cand_total * sizeof(uint16_t));
+    const size_t o_candc = carve(B * L.nlevels * sizeof(int));
+    const size_t o_lkp = carve(B * L.kp_cap_total * sizeof(uint32_t));
+    const size_t o_lkpc = carve(B * L.nlevels * sizeof(int));
+    CK(cudaMalloc(&h->d_pool, off));
+    uint8_t* base = (uint8_t*)h->d_pool;
+    L.raw = base + o_raw; L.slots = (uint32_t*)(base + o_slots); L.cell_count = (int*)(base + o_cc);
+    L.cand = (uint32_t*)(base + o_cand); L.cand_node = (uint16_t*)(base + o_node); L.cand_count = (int*)(base + o_candc);
+    L.lvl_kp = (uint32_t*)(base + o_lkp); L.lvl_kp_count = (int*)(base + o_lkpc);
+    CK(cudaMalloc(&h->d_lvl, h->lvl.size() * sizeof(OrbxLevelGeom)));
+    CK(cudaMalloc(&h->d_cells, h->cells.size() * sizeof(OrbxCell)));
+    CK(cudaMalloc(&h->d_taps, std::max<size_t>(h->taps.size(), 1) * sizeof(OrbxResizeTap)));
+    CK(cudaMemcpy(h->d_lvl, h->lvl.data(), h->lvl.size() * sizeof(OrbxLevelGeom), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice));
+    if (!h->taps.empty())
+        CK(cudaMemcpy(h->d_taps, h->taps.data(), h->taps.size() * sizeof(OrbxResizeTap), cudaMemcpyHostToDevice));
+    L.lvl = h->d_lvl; L.cells = h->d_cells; L.taps = h->d_taps;
+    // staging for the host entry points
+    const size_t in_bytes = B * (size_t)width * height;
+    CK(cudaMalloc(&h->d_in, in_bytes));
+    CK(cudaMalloc(&h->d_kps, B * L.kp_cap_total * sizeof(OrbxKp28)));
+    CK(cudaMalloc(&h->d_desc, B * L.kp_cap_total * 32));
+    CK(cudaMalloc(&h->d_nkp, B * sizeof(int)));
+    CK(cudaMallocHost(&h->h_in, in_bytes));
+    CK(cudaMallocHost(&h->h_kps, B * L.kp_cap_total * sizeof(OrbxKp28)));
+    CK(cudaMallocHost(&h->h_desc, B * L.kp_cap_total * 32));
+    CK(cudaMallocHost(&h->h_nkp, B * sizeof(int)));
+    if (!h->constants_ready) { orbx_upload_constants(); CK(cudaGetLastError()); h->constants_ready = true; }
+    h->W = width; h->H = height; h->max_batch = max_batch; h->last_frames = 0;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_max_keypoints(const orbx_extractor* h) { return (h && h->W) ? h->L.kp_cap_total : 0; }
+
+// the whole device pipeline for n frames that already sit in HBM
+static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stride, size_t frame_pitch,
+                        OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st)
+{
+    orbx_launch_pyramid(h->L, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st);
+    orbx_launch_fast(h->L, h->max_tile_w, h->max_tile_h, n, st);
+    orbx_launch_quadtree(h->L, n, st);
+    orbx_launch_describe(h->L, n, d_kps, d_desc, cap, d_nkp, st);
+    CK(cudaGetLastError());
+    h->last_frames = n;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extract_device(orbx_extractor* h, const uint8_t* d_images, int n, int width, int height, int stride,
+                                   size_t frame_pitch_bytes, OrbxKeyPoint* d_keypoints, int cap, int32_t* d_nkp,
+                                   uint8_t* d_descriptors, void* cuda_stream)
+{
+    if (!h || !d_images || !d_keypoints || !d_nkp || !d_descriptors) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (n <= 0 || width <= 0 || height <= 0 || stride < width || cap <= 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    if (width != h->W || height != h->H || n > h->max_batch) {
+        int rc = orbx_reserve(h, width, height, std::max(n, h->max_batch));
+        if (rc != ORBX_OK) return rc;
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    return run_pipeline(h, d_images, n, stride, frame_pitch_bytes, (OrbxKp28*)d_keypoints, d_descriptors, cap, d_nkp, st);
+}
+
+extern "C" int orbx_synchronize(orbx_extractor* h)
+{
+    if (!h || !h->stream) return ORBX_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
+                                  int stride, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (n <= 0 || !images || width <= 0 || height <= 0) return ORBX_OK;        // empty input: silent, like :1141
+    if (!keypoints || !nkp || !descriptors || cap < 0 || stride < width) return fail(ORBX_ERR_INVALID, "bad output buffers");
+    if (width != h->W || height != h->H || h->max_batch < 1) {
+        int rc = orbx_reserve(h, width, height, std::max(1, std::min(n, std::max(h->max_batch, 64))));
+        if (rc != ORBX_OK) return rc;
+    }
+    CK(cudaSetDevice(h->device));
+    const int B = h->max_batch, kc = h->L.kp_cap_total;
+    const size_t fbytes = (size_t)width * height;
+    int status = ORBX_OK;
+    for (int f0 = 0; f0 < n; f0 += B) {
+        const int m = std::min(B, n - f0);
+        for (int i = 0; i < m; i++) {
+            if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
+            // pack to contiguous pinned staging, then one H2D copy
+            uint8_t* dst = h->h_in + (size_t)i * fbytes;
+            if (stride == width) memcpy(dst, images[f0 + i], fbytes);
+            else for (int y = 0; y < height; y++) memcpy(dst + (size_t)y * width, images[f0 + i] + (size_t)y * stride, width);
+        }
+        CK(cudaMemcpyAsync(h->d_in, h->h_in, (size_t)m * fbytes, cudaMemcpyHostToDevice, h->stream));
+        int rc = run_pipeline(h, h->d_in, m, width, fbytes, h->d_kps, h->d_desc, kc, h->d_nkp, h->stream);
+        if (rc != ORBX_OK) return rc;
+        CK(cudaMemcpyAsync(h->h_nkp, h->d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)m * kc * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)m * kc * 32, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < m; i++) {
+            const int k = h->h_nkp[i];
+            nkp[f0 + i] = k;
+            const int c = std::min(k, cap);
+            if (k > cap) status = ORBX_ERR_CAPACITY;
+            memcpy(keypoints + (size_t)(f0 + i) * cap, h->h_kps + (size_t)i * kc, (size_t)c * sizeof(OrbxKp28));
+            memcpy(descriptors + (size_t)(f0 + i) * cap * 32, h->h_desc + (size_t)i * kc * 32, (size_t)c * 32);
+        }
+    }
+    if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
+    return status;
+}
+
+extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height, int stride,
+                            OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (nkp) *nkp = 0;
+    if (!image || width <= 0 || height <= 0) return ORBX_OK;   // ORBextractor.cc:1141-1142
+    const uint8_t* imgs[1] = {image};
+    return orbx_extract_batch(h, imgs, 1, width, height, stride, keypoints, cap, nkp, descriptors);
+}
+
+extern "C" int orbx_level_size(const orbx_extractor* h, int level, int* width, int* height)
+{
+    if (!h || !h->W) return fail(ORBX_ERR_STATE, "no geometry reserved yet");
+    if (level < 0 || level >= h->nlevels) return fail(ORBX_ERR_INVALID, "level out of range");
+    if (width) *width = h->lvl[level].w;
+    if (height) *height = h->lvl[level].h;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level, const uint8_t** d_payload, int* pitch)
+{
+    if (!h || !h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");
+    if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame/level out of range");
+    const OrbxLevelGeom& g = h->lvl[level];
+    if (d_payload) *d_payload = h->L.raw + (size_t)frame * h->L.frame_raw_bytes + g.raw_off + (size_t)ORBX_EDGE * g.pitch + ORBX_XOFF;
+    if (pitch) *pitch = g.pitch;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_pyramid_level(orbx_extractor* h, int frame, int level, uint8_t* dst, int dst_stride)
+{
+    const uint8_t* pay; int pitch;
+    int rc = orbx_pyramid_level_device(h, frame, level, &pay, &pitch);
+    if (rc != ORBX_OK) return rc;
+    const OrbxLevelGeom& g = h->lvl[level];
+    if (!dst || dst_stride < g.w + 2 * ORBX_EDGE) return fail(ORBX_ERR_INVALID, "dst too small");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy2D(dst, dst_stride, pay - (size_t)ORBX_EDGE * pitch - ORBX_EDGE, pitch, g.w + 2 * ORBX_EDGE,
+                    g.h + 2 * ORBX_EDGE, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_debug_level_counts(orbx_extractor* h, int frame, int32_t* counts)
+{
+    if (!h || !h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");
+    if (frame < 0 || frame >= h->last_frames || !counts) return fail(ORBX_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(counts, h->L.lvl_kp_count + (size_t)frame * h->nlevels, h->nlevels * sizeof(int), cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_debug_candidates(orbx_extractor* h, int frame, int level, OrbxKeyPoint* out, int cap, int* n)
+{
+    if (!h || !h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");
+    if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->last_frames || !n) return fail(ORBX_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int cnt = 0;
+    CK(cudaMemcpy(&cnt, h->L.cand_count + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    const int m = std::min(cnt, cap);
+    if (m > 0 && out) {
+        std::vector<uint32_t> tmp(m);
+        CK(cudaMemcpy(tmp.data(), h->L.cand + (size_t)frame * h->L.cand_total + h->lvl[level].cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) {
+            OrbxKeyPoint k;
+            k.x = (float)(tmp[i] & 0xfff); k.y = (float)((tmp[i] >> 12) & 0xfff);
+            k.size = 7.f; k.angle = -1.f; k.response = (float)(tmp[i] >> 24); k.octave = 0; k.class_id = -1;
+            out[i] = k;
+        }
+    }
+    return ORBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Hamming
+extern "C" int orbx_hamming_init_device(uint64_t* d_packed, int nq, void* cuda_stream)
+{
+    if (!d_packed || nq < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+    orbx_launch_hamming_init(d_packed, nq, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" int orbx_hamming_top2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int64_t index_base,
+                                        uint64_t* d_packed, void* cuda_stream)
+{
+    if (nq < 0 || nt < 0 || (nq > 0 && (!d_query || !d_packed)) || (nt > 0 && !d_train)) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (((uintptr_t)d_query | (uintptr_t)d_train) & 15) return fail(ORBX_ERR_INVALID, "descriptor arrays must be 16-byte aligned on the device");
+    orbx_launch_hamming_top2(d_query, nq, d_train, nt, index_base, d_packed, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" int orbx_hamming_merge_device(const uint64_t* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_dist1,
+                                         int32_t* d_dist2, void* cuda_stream)
+{
+    if (!d_parts || nparts < 1 || nq < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+    orbx_launch_hamming_merge(d_parts, nparts, nq, d_idx1, d_dist1, d_dist2, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_hamming_top2(const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* idx1, int32_t* dist1,
+                                 int32_t* dist2, int device)
+{
+    if (nq < 0 || nt < 0 || (nq > 0 && (!query || !idx1 || !dist1 || !dist2)) || (nt > 0 && !train))
+        return fail(ORBX_ERR_INVALID, "bad argument");
+    if (nq == 0) return ORBX_OK;
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    uint8_t *dq = nullptr, *dt = nullptr; uint64_t* dp = nullptr; int* dout = nullptr;
+    int rc = ORBX_OK;
+    cudaError_t e;
+    do {
+        if ((e = cudaMalloc(&dq, (size_t)nq * 32)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&dt, std::max<size_t>((size_t)nt * 32, 32))) != cudaSuccess) break;
+        if ((e = cudaMalloc(&dp, (size_t)nq * 8)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&dout, (size_t)nq * 12)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(dq, query, (size_t)nq * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (nt > 0 && (e = cudaMemcpy(dt, train, (size_t)nt * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        orbx_launch_hamming_init(dp, nq, 0);
+        orbx_launch_hamming_top2(dq, nq, dt, nt, 0, dp, 0);
+        orbx_launch_hamming_merge(dp, 1, nq, dout, dout + nq, dout + 2 * (size_t)nq, 0);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(idx1, dout, (size_t)nq * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(dist1, dout + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(dist2, dout + 2 * (size_t)nq, (size_t)nq * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) rc = fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    cudaFree(dq); cudaFree(dt); cudaFree(dp); cudaFree(dout);
+    return rc;
+}
+
+extern "C" int orbx_stereo_hamming(const OrbxKeyPoint* kl, const uint8_t* dl, int nl, const OrbxKeyPoint* kr,
+                                   const uint8_t* dr, int nr, int rows, const float* scale_factors, int nlevels,
+                                   float minD, float maxD, int32_t* best_idx_r, int32_t* best_dist, int device)
+{
+    if (nl < 0 || nr < 0 || rows <= 0 || !scale_factors || (nl > 0 && (!kl || !dl || !best_idx_r || !best_dist)) || (nr > 0 && (!kr || !dr)))
+        return fail(ORBX_ERR_INVALID, "bad argument");
+    if (nl == 0) return ORBX_OK;
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    // vRowIndices (Frame.cc:564-590) as a CSR table; filling in ascending iR keeps every row's push_back order.
+    // This is O(nr * band) host bookkeeping on a few thousand keypoints, exactly as in the reference.
+    std::vector<int> start(rows + 1, 0);
+    std::vector<int> lo(nr), hi(nr);
+    for (int i = 0; i < nr; i++) {
+        if (kr[i].octave < 0 || kr[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "right keypoint octave out of range");
+        const float r = 2.0f * scale_factors[kr[i].octave];
+        hi[i] = std::min((int)ceilf(kr[i].y + r), rows - 1);
+        lo[i] = std::max((int)floorf(kr[i].y - r), 0);
+        for (int y = lo[i]; y <= hi[i]; y++) start[y + 1]++;
+    }
+    for (int y = 0; y < rows; y++) start[y + 1] += start[y];
+    std::vector<int> tab(std::max(start[rows], 1)), fill(rows, 0);
+    for (int i = 0; i < nr; i++)
+        for (int y = lo[i]; y <= hi[i]; y++) tab[start[y] + fill[y]++] = i;
+    CK(cudaSetDevice(device));
+    void* pool = nullptr;
+    const size_t b_kl = (size_t)nl * 28, b_dl = (size_t)nl * 32, b_kr = (size_t)std::max(nr, 1) * 28, b_dr = (size_t)std::max(nr, 1) * 32;
+    const size_t b_st = (size_t)(rows + 1) * 4, b_tab = tab.size() * 4, b_out = (size_t)nl * 8;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t total = al(b_kl) + al(b_dl) + al(b_kr) + al(b_dr) + al(b_st) + al(b_tab) + al(b_out);
+    CK(cudaMalloc(&pool, total));
+    uint8_t* p = (uint8_t*)pool;
+    uint8_t *p_kl = p; p += al(b_kl);
+    uint8_t *p_dl = p; p += al(b_dl);
+    uint8_t *p_kr = p; p += al(b_kr);
+    uint8_t *p_dr = p; p += al(b_dr);
+    uint8_t *p_st = p; p += al(b_st);
+    uint8_t *p_tab = p; p += al(b_tab);
+    uint8_t *p_out = p;
+    int rc = ORBX_OK;
+    cudaError_t e;
+    do {
+        if ((e = cudaMemcpy(p_kl, kl, b_kl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_dl, dl, b_dl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (nr > 0 && (e = cudaMemcpy(p_kr, kr, (size_t)nr * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (nr > 0 && (e = cudaMemcpy(p_dr, dr, (size_t)nr * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_st, start.data(), b_st, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_tab, tab.data(), b_tab, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        orbx_launch_stereo_hamming((const OrbxKp28*)p_kl, p_dl, nl, (const OrbxKp28*)p_kr, p_dr, nr, (const int*)p_st,
+                                   (const int*)p_tab, rows, minD, maxD, (int*)p_out, (int*)p_out + nl, 0);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(best_idx_r, p_out, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(best_dist, p_out + (size_t)nl * 4, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) rc = fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    cudaFree(pool);
+    return rc;
+}

@@ -1,0 +1,217 @@
+// orbx_describe.cu — orientation + 7x7 Gaussian + steered rBRIEF, one warp per keypoint (replaces
+// computeOrientation/IC_Angle ORBextractor.cc:77-105,492-499, the per-level cv::GaussianBlur :1188-1190 and
+// computeOrbDescriptor :110-152, plus the coordinate scaling / output packing of operator() :1194-1209).
+//
+// The warp stages the 43x43 raw patch around the keypoint in shared memory (aligned 32-bit loads), then
+//   * IC_Angle: lane = column u in [-15,15], integer moments, warp-shuffle reduce, cv::fastAtan2 polynomial
+//     evaluated with un-contracted f32 mul/add (bit-equal to OpenCV's scalar path);
+//   * blur on demand: the reference blurs the whole level and then reads 512 points per keypoint; here the
+//     horizontal pass of OpenCV's fixed-point kernel [18,34,48,56,48,34,18]/256 is applied to the patch (exact in
+//     16 bits) and the vertical pass ((sum + 2^15) >> 16) only at the 16 sample points each lane needs. Border
+//     handling is the level's own REFLECT_101, which is exactly what the 19-px apron in HBM holds;
+//   * rBRIEF: lane i builds descriptor byte i (8 tests); sample = center + cvRound(x*b+y*a, x*a-y*b) with
+//     un-contracted f32 and round-half-even; cos/sin are the glibc 2.39 cosf/sinf polynomials in f64
+//     (bit-equal to the host libm the oracle was pinned against, tests/golden/sincos.json).
+// No blurred pyramid is ever written to HBM.
+#include "orbx_internal.cuh"
+
+#define DESC_WARPS 8
+#define PW 43            // patch width/height
+#define PWORDS 12        // 32-bit words per staged patch row (48 bytes)
+#define HBP 38           // pitch (u16) of the horizontally blurred patch, 37 valid columns
+
+__constant__ signed char c_pattern[1024];
+__constant__ int c_umax[16];
+
+static const signed char h_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+void orbx_upload_constants()
+{
+    // IC_Angle disc half-widths (ORBextractor.cc:473-489)
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern));
+    cudaMemcpyToSymbol(c_umax, umax, sizeof(umax));
+}
+
+__device__ __forceinline__ float dev_fast_atan2(const float y, const float x)
+{
+    const float scale = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = 2.2204460492503131e-16f;   // (float)DBL_EPSILON
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// glibc 2.39 x86_64 sincosf (sysdeps/ieee754/flt-32/s_sincosf.h, FMA build), medium-range path |x| < 120.
+__device__ __forceinline__ double sc_cos_poly(const double x2, const double sg)
+{
+    const double c0 = 1.0, c1 = __longlong_as_double(0xbfdffffffd0c621cLL), c2 = __longlong_as_double(0x3fa55553e1068f19LL);
+    const double c3 = __longlong_as_double(0xbf56c087e89a359dLL), c4 = __longlong_as_double(0x3ef99343027bf8c3LL);
+    const double x4 = __dmul_rn(x2, x2);
+    const double q2 = __fma_rn(sg * c4, x2, sg * c3);
+    const double q1 = __fma_rn(sg * c1, x2, sg * c0);
+    const double x6 = __dmul_rn(x2, x4);
+    const double q = __fma_rn(x4, sg * c2, q1);
+    return __fma_rn(q2, x6, q);
+}
+__device__ __forceinline__ double sc_sin_poly(const double x, const double x2)
+{
+    const double s1 = __longlong_as_double(0xbfc555545995a603LL), s2 = __longlong_as_double(0x3f81107605230bc4LL);
+    const double s3 = __longlong_as_double(0xbf2994eb3774cf24LL);
+    const double t1 = __fma_rn(s3, x2, s2);
+    const double x3 = __dmul_rn(x2, x);
+    const double x7 = __dmul_rn(x2, x3);
+    const double s = __fma_rn(x3, s1, x);
+    return __fma_rn(t1, x7, s);
+}
+__device__ __forceinline__ void dev_sincosf(const float y, float* sn, float* cs)
+{
+    const unsigned top = (__float_as_uint(y) >> 20) & 0x7ff;
+    double x = (double)y;
+    if (top <= 0x3f3) {
+        const double x2 = __dmul_rn(x, x);
+        if (top <= 0x397) { *cs = 1.0f; *sn = y; return; }
+        *cs = __double2float_rn(sc_cos_poly(x2, 1.0));
+        *sn = __double2float_rn(sc_sin_poly(x, x2));
+        return;
+    }
+    const double hpi_inv = __longlong_as_double(0x41645f306dc9c883LL), hpi = __longlong_as_double(0x3ff921fb54442d18LL);
+    const double r = __dmul_rn(x, hpi_inv);
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __fma_rn(-(double)n, hpi, x);
+    const double x2 = __dmul_rn(x, x);
+    const double sg = (n & 2) ? -1.0 : 1.0;                      // table 1 = negated cosine coefficients
+    const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;   // sign[n & 3] = {1,-1,-1,1}
+    const double pc = sc_cos_poly(x2, sg);
+    const double ps = sc_sin_poly(__dmul_rn(x, sign), x2);
+    // cosf: (n&1)==0 -> cosine polynomial, else sine polynomial; sinf: the other way round
+    *cs = __double2float_rn((n & 1) ? ps : pc);
+    *sn = __double2float_rn((n & 1) ? pc : ps);
+}
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayout L, OrbxKp28* __restrict__ kps,
+                                                                    uint8_t* __restrict__ desc, int cap,
+                                                                    int* __restrict__ nkp)
+{
+    __shared__ uint32_t s_raw[DESC_WARPS][PW * PWORDS];
+    __shared__ unsigned short s_hb[DESC_WARPS][PW * HBP];
+    __shared__ signed char s_pat[1024];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < 1024; i += DESC_WARPS * 32) s_pat[i] = c_pattern[i];
+    __syncthreads();
+    const int frame = blockIdx.y;
+    const int ord = blockIdx.x * DESC_WARPS + wid;      // keypoint ordinal inside the frame (level-major)
+    const int* cnt = L.lvl_kp_count + (size_t)frame * L.nlevels;
+    int level = -1, k = 0, total = 0;
+    for (int l = 0; l < L.nlevels; l++) {
+        const int c = cnt[l];
+        if (level < 0 && ord < total + c) { level = l; k = ord - total; }
+        total += c;
+    }
+    if (ord == 0 && lane == 0) nkp[frame] = total;
+    if (level < 0 || ord >= cap) return;                 // warp-uniform
+    const OrbxLevelGeom g = L.lvl[level];
+    const uint32_t pk = L.lvl_kp[(size_t)frame * L.kp_cap_total + L.lvl_kp_off[level] + k];
+    const int kx = pk & 0xfff, ky = (pk >> 12) & 0xfff, score = pk >> 24;
+
+    // ---- stage the 43x43 raw patch (rows ky-21.., columns kx-21..) with aligned 32-bit loads
+    const uint8_t* p0 = L.raw + (size_t)frame * L.frame_raw_bytes + g.raw_off +
+                        (size_t)(ky - 21 + ORBX_EDGE) * g.pitch + (kx - 21 + ORBX_XOFF);
+    const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3);
+    const uint8_t* pa = p0 - sh;
+    uint32_t* raw32 = s_raw[wid];
+    for (int i = lane; i < PW * PWORDS; i += 32) {
+        const int r = i / PWORDS, c = i - r * PWORDS;
+        raw32[i] = __ldg(reinterpret_cast<const uint32_t*>(pa + (size_t)r * g.pitch) + c);
+    }
+    __syncwarp();
+    const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32) + sh;   // raw8[r*48 + c], c in [0,43)
+
+    // ---- IC_Angle on the un-blurred level
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - 15;
+        const int au = u < 0 ? -u : u;
+#pragma unroll 1
+        for (int v = -15; v <= 15; v++) {
+            const int av = v < 0 ? -v : v;
+            if (au <= c_umax[av]) {
+                const int val = raw8[(v + 21) * (PWORDS * 4) + u + 21];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = dev_fast_atan2((float)m01, (float)m10);
+
+    // ---- horizontal pass of the fixed-point Gaussian on the patch: hb[r][c] <-> patch column c+3
+    unsigned short* hb = s_hb[wid];
+    for (int i = lane; i < PW * 37; i += 32) {
+        const int r = i / 37, c = i - r * 37;
+        const uint8_t* q = raw8 + r * (PWORDS * 4) + c;
+        hb[r * HBP + c] = (unsigned short)(18 * (q[0] + q[6]) + 34 * (q[1] + q[5]) + 48 * (q[2] + q[4]) + 56 * q[3]);
+    }
+    __syncwarp();
+
+    // ---- steered rBRIEF: lane i -> descriptor byte i
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+    float a, b;
+    dev_sincosf(__fmul_rn(angle, factorPI), &b, &a);
+    const signed char* pat = s_pat + 32 * lane;
+    int val = 0;
+#pragma unroll 2
+    for (int t = 0; t < 8; t++) {
+        int smp[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float px = (float)pat[4 * t + 2 * e], py = (float)pat[4 * t + 2 * e + 1];
+            const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const unsigned short* h = hb + (iy + 18) * HBP + (ix + 18);
+            const unsigned acc = 18u * (h[0] + h[6 * HBP]) + 34u * (h[HBP] + h[5 * HBP]) + 48u * (h[2 * HBP] + h[4 * HBP]) + 56u * h[3 * HBP];
+            smp[e] = (int)((acc + 32768u) >> 16);
+        }
+        val |= (smp[0] < smp[1]) << t;
+    }
+    const size_t o = (size_t)frame * cap + ord;
+    desc[o * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        OrbxKp28 kp;
+        kp.x = level ? __fmul_rn((float)kx, g.scale) : (float)kx;
+        kp.y = level ? __fmul_rn((float)ky, g.scale) : (float)ky;
+        kp.size = g.kp_size;
+        kp.angle = angle;
+        kp.response = (float)score;
+        kp.octave = level;
+        kp.class_id = -1;
+        kps[o] = kp;
+    }
+}
+
+void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp,
+                          cudaStream_t st)
+{
+    int total_cap = L.kp_cap_total;
+    dim3 grid((total_cap + DESC_WARPS - 1) / DESC_WARPS, nframes);
+    describe_kernel<<<grid, DESC_WARPS * 32, 0, st>>>(L, d_kps, d_desc, cap, d_nkp);
+}

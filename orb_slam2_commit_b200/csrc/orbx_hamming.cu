@@ -1,0 +1,221 @@
+// orbx_hamming.cu — 256-bit Hamming distance + best / second-best search (replaces
+// ORBmatcher::DescriptorDistance, ORBmatcher.cc:1844-1860, and the top-2 loop idiom around it, :84-126;
+// the row-band best-match stage of Frame::ComputeStereoMatches, Frame.cc:554-663).
+//
+// Brute force (BASELINE config 4): every thread keeps HT_QPT queries in registers (8 x u32 each), the CTA streams
+// its slice of the train set through shared memory with 128-bit loads that are broadcast to the whole warp, and the
+// inner loop is XOR + __popc + add with a branch-free top-2 update on packed keys (dist << 22 | local index):
+//   t = max(key, best); best = min(best, key); second = min(second, t)
+// which is exactly  if(d<best){second=best;best=d;idx=j}else if(d<second)second=d  with "first index wins" because
+// keys of equal distance order by index. Partial results of the train slices are merged with a 64-bit CAS into
+// one packed word per query; the same merge rule joins the per-GPU results after the NCCL all-gather.
+// This kernel is bound by the integer/popc pipes, not by HBM (32 B per train row are reused by every query).
+#include "orbx_internal.cuh"
+
+#define HT_THREADS 256
+#define HT_QPT 2                 // queries per thread
+#define HT_TILE 256              // train rows per shared-memory tile (8 KB)
+#define HT_SHIFT 22              // local train index bits inside a key (slice <= 4M rows)
+#define HT_SLICE_MAX (1 << HT_SHIFT)
+
+__host__ __device__ __forceinline__ unsigned long long ht_pack(int d1, int d2, unsigned idx)
+{
+    return ((unsigned long long)(unsigned)d1 << 48) | ((unsigned long long)(unsigned)d2 << 32) | idx;
+}
+// merge rule: best = smaller distance, lower index on ties; second = 2nd smallest of the multiset {d1a,d2a,d1b,d2b}
+__device__ __forceinline__ unsigned long long ht_merge(unsigned long long a, unsigned long long b)
+{
+    const int d1a = (int)(a >> 48), d2a = (int)((a >> 32) & 0xffff), d1b = (int)(b >> 48), d2b = (int)((b >> 32) & 0xffff);
+    const unsigned ia = (unsigned)a, ib = (unsigned)b;
+    const bool a_first = d1a < d1b || (d1a == d1b && ia <= ib);
+    const int d1 = a_first ? d1a : d1b;
+    const unsigned idx = a_first ? ia : ib;
+    const int d2 = min(max(d1a, d1b), min(d2a, d2b));
+    return ht_pack(d1, d2, idx);
+}
+
+__global__ void hamming_init_kernel(unsigned long long* packed, int nq)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) packed[i] = ht_pack(256, 256, 0xffffffffu);
+}
+
+__device__ __forceinline__ int ht_dist(const uint4 qa, const uint4 qb, const uint4 ta, const uint4 tb)
+{
+    return __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+           __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+}
+
+__global__ void __launch_bounds__(HT_THREADS) hamming_top2_kernel(const uint4* __restrict__ q, int nq,
+                                                                  const uint4* __restrict__ t, int nt, int slice,
+                                                                  long long index_base,
+                                                                  unsigned long long* __restrict__ packed)
+{
+    __shared__ uint4 s_t[2][HT_TILE * 2];
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * slice;                       // this CTA's train slice [t0, t1)
+    const int t1 = min(nt, t0 + slice);
+    const int qbase = blockIdx.y * (HT_THREADS * HT_QPT);
+    uint4 qa[HT_QPT], qb[HT_QPT];
+    int best[HT_QPT], second[HT_QPT];
+#pragma unroll
+    for (int k = 0; k < HT_QPT; k++) {
+        const int qi = qbase + k * HT_THREADS + tid;
+        if (qi < nq) { qa[k] = q[2 * (size_t)qi]; qb[k] = q[2 * (size_t)qi + 1]; }
+        else { qa[k] = make_uint4(0, 0, 0, 0); qb[k] = qa[k]; }
+        best[k] = 256 << HT_SHIFT;                           // reference init: bestDist = bestDist2 = 256
+        second[k] = 256 << HT_SHIFT;
+    }
+    const int ntiles = (t1 - t0 + HT_TILE - 1) / HT_TILE;
+    // prologue: tile 0
+    if (ntiles > 0) {
+        for (int i = tid; i < HT_TILE * 2; i += HT_THREADS) {
+            const int row = t0 + (i >> 1);
+            s_t[0][i] = row < t1 ? t[2 * (size_t)t0 + i] : make_uint4(0, 0, 0, 0);
+        }
+    }
+    __syncthreads();
+    for (int tile = 0; tile < ntiles; tile++) {
+        const int buf = tile & 1;
+        // prefetch the next tile into registers, store after the compute loop
+        uint4 pre[2];
+        const int nbase = t0 + (tile + 1) * HT_TILE;
+        const bool has_next = tile + 1 < ntiles;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int i = tid + r * HT_THREADS;
+            const int row = nbase + (i >> 1);
+            pre[r] = (has_next && row < t1) ? t[2 * (size_t)nbase + i] : make_uint4(0, 0, 0, 0);
+        }
+        const int rows = min(HT_TILE, t1 - (t0 + tile * HT_TILE));
+        const int jbase = tile * HT_TILE;
+#pragma unroll 4
+        for (int j = 0; j < rows; j++) {
+            const uint4 ta = s_t[buf][2 * j], tb = s_t[buf][2 * j + 1];
+#pragma unroll
+            for (int k = 0; k < HT_QPT; k++) {
+                const int key = (ht_dist(qa[k], qb[k], ta, tb) << HT_SHIFT) | (jbase + j);
+                const int hi = max(key, best[k]);
+                best[k] = min(best[k], key);
+                second[k] = min(second[k], hi);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) s_t[buf ^ 1][tid + r * HT_THREADS] = pre[r];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < HT_QPT; k++) {
+        const int qi = qbase + k * HT_THREADS + tid;
+        if (qi >= nq) continue;
+        const int d1 = best[k] >> HT_SHIFT, d2 = min(second[k] >> HT_SHIFT, 256);
+        if (d1 >= 256) continue;                              // nothing closer than 256: leave the init value
+        const unsigned idx = (unsigned)(index_base + t0 + (best[k] & (HT_SLICE_MAX - 1)));
+        const unsigned long long mine = ht_pack(d1, d2, idx);
+        unsigned long long old = packed[qi];
+        while (true) {
+            const unsigned long long want = ht_merge(old, mine);
+            if (want == old) break;
+            const unsigned long long prev = atomicCAS(&packed[qi], old, want);
+            if (prev == old) break;
+            old = prev;
+        }
+    }
+}
+
+__global__ void hamming_merge_kernel(const unsigned long long* __restrict__ parts, int nparts, int nq,
+                                     int* __restrict__ idx, int* __restrict__ d1, int* __restrict__ d2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    unsigned long long acc = ht_pack(256, 256, 0xffffffffu);
+    for (int p = 0; p < nparts; p++) acc = ht_merge(acc, parts[(size_t)p * nq + i]);
+    const int b = (int)(acc >> 48);
+    if (idx) idx[i] = b >= 256 ? -1 : (int)(unsigned)acc;
+    if (d1) d1[i] = b;
+    if (d2) d2[i] = (int)((acc >> 32) & 0xffff);
+}
+
+void orbx_launch_hamming_init(uint64_t* d_packed, int nq, cudaStream_t st)
+{
+    if (nq > 0) hamming_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(d_packed), nq);
+}
+
+void orbx_launch_hamming_top2(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, long long index_base,
+                              uint64_t* d_packed, cudaStream_t st)
+{
+    if (nq <= 0 || nt <= 0) return;
+    const int qtiles = (nq + HT_THREADS * HT_QPT - 1) / (HT_THREADS * HT_QPT);
+    // size the grid to ~4 waves of 148 SMs x 2 resident CTAs, slices a multiple of the tile
+    int want = (148 * 2 * 4 + qtiles - 1) / qtiles;
+    int slice = (nt + want - 1) / want;
+    slice = ((slice + HT_TILE - 1) / HT_TILE) * HT_TILE;
+    if (slice > HT_SLICE_MAX) slice = HT_SLICE_MAX;
+    const int nslices = (nt + slice - 1) / slice;
+    dim3 grid(nslices, qtiles);
+    hamming_top2_kernel<<<grid, HT_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(d_q), nq,
+                                                     reinterpret_cast<const uint4*>(d_t), nt, slice, index_base,
+                                                     reinterpret_cast<unsigned long long*>(d_packed));
+}
+
+void orbx_launch_hamming_merge(const uint64_t* d_parts, int nparts, int nq, int* d_idx, int* d_d1, int* d_d2,
+                               cudaStream_t st)
+{
+    if (nq > 0)
+        hamming_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_parts),
+                                                               nparts, nq, d_idx, d_d1, d_d2);
+}
+
+// ---------------------------------------------------------------- stereo row-band matching (Frame.cc:596-663)
+// One warp per left keypoint; lanes stride over the candidates of row (int)vL (CSR table built on the host in the
+// reference's push_back order = ascending right index). Warp-reduced best with (distance, candidate position) keys
+// so the first candidate attaining the minimum wins, as with the reference's strict '<'.
+__global__ void __launch_bounds__(256) stereo_hamming_kernel(const OrbxKp28* __restrict__ kl, const uint4* __restrict__ dl,
+                                                             int nl, const OrbxKp28* __restrict__ kr,
+                                                             const uint4* __restrict__ dr, const int* __restrict__ row_start,
+                                                             const int* __restrict__ row_tab, int rows, float minD,
+                                                             float maxD, int* __restrict__ best_idx,
+                                                             int* __restrict__ best_dist)
+{
+    const int lane = threadIdx.x & 31;
+    const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (iL >= nl) return;
+    const OrbxKp28 k = kl[iL];
+    const int row = (int)k.y;
+    int key = (100 << 20) | 0xfffff;                          // bestDist = TH_HIGH, no index yet
+    if (row >= 0 && row < rows) {
+        const float minU = __fsub_rn(k.x, maxD), maxU = __fsub_rn(k.x, minD);
+        if (!(maxU < 0.f)) {
+            const uint4 qa = dl[2 * (size_t)iL], qb = dl[2 * (size_t)iL + 1];
+            const int c0 = row_start[row], c1 = row_start[row + 1];
+            for (int c = c0 + lane; c < c1; c += 32) {
+                const int iR = row_tab[c];
+                const OrbxKp28 r = kr[iR];
+                if (r.octave < k.octave - 1 || r.octave > k.octave + 1) continue;
+                if (r.x >= minU && r.x <= maxU) {
+                    const int d = ht_dist(qa, qb, dr[2 * (size_t)iR], dr[2 * (size_t)iR + 1]);
+                    if (d < 100) key = min(key, (d << 20) | min(c - c0, 0xffffe));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if (lane == 0) {
+        const int pos = key & 0xfffff;
+        best_dist[iL] = key >> 20;
+        best_idx[iL] = pos == 0xfffff ? -1 : row_tab[row_start[row] + pos];
+    }
+}
+
+void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, const OrbxKp28* kr, const uint8_t* dr,
+                                int nr, const int* row_start, const int* row_tab, int rows, float minD, float maxD,
+                                int* best_idx, int* best_dist, cudaStream_t st)
+{
+    (void)nr;
+    if (nl <= 0) return;
+    const int warps_per_block = 8;
+    stereo_hamming_kernel<<<(nl + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+        kl, reinterpret_cast<const uint4*>(dl), nl, kr, reinterpret_cast<const uint4*>(dr), row_start, row_tab, rows,
+        minD, maxD, best_idx, best_dist);
+}

@@ -1,0 +1,92 @@
+// orbx_internal.cuh — shared declarations of the sm_100a ORB front-end kernels (not part of the C ABI).
+//
+// HBM layout of one extractor instance (sized by orbx_reserve for W x H frames, B frames per call):
+//   raw pyramid   [B] frames x frame_raw_bytes; level l of a frame starts at lvl[l].raw_off and is
+//                 (h+38) rows of `pitch` bytes; the payload pixel (x,y) sits at row y+19, column x+ORBX_XOFF,
+//                 so payload rows start 32-byte aligned and the 19-px REFLECT_101 apron of the reference's
+//                 `temp` buffer (ORBextractor.cc:1225-1229) physically surrounds every level.
+//   cell slots    [B][slot_total] u32  — NMS survivors of every 30-px FAST cell, packed (score<<24 | y<<12 | x),
+//                 x,y relative to minBorder (16), row-major inside the cell
+//   cell counts   [B][ncells] i32
+//   candidates    [B][cand_total] u32 + u16 node ids — per level compacted in the reference's list order
+//   level kps     [B][nlevels][kp_cap] u32 + counts — keypoints chosen by the quadtree, list order
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_EDGE 19          // EDGE_THRESHOLD (ORBextractor.cc:70)
+#define ORBX_XOFF 32          // payload column origin inside a pyramid row (apron occupies columns 13..31)
+#define ORBX_MINB 16          // minBorder = EDGE_THRESHOLD-3 (ORBextractor.cc:829)
+#define ORBX_MAX_DIM 4096     // coordinates are packed in 12 bits
+#define ORBX_QT_THREADS 1024
+#define ORBX_MAX_QUOTA 2040   // per-level quadtree target N supported by the shared-memory node table
+
+struct OrbxLevelGeom {
+    int w, h;                 // payload size of the level
+    int pitch;                // bytes per row of the level buffer
+    int raw_off;              // byte offset of the level inside a frame's raw block (row 0 of the apron)
+    int quota;                // mnFeaturesPerLevel[l]
+    int nini;                 // quadtree roots (ORBextractor.cc:567)
+    float hx;                 // root width (ORBextractor.cc:570)
+    float scale;              // mvScaleFactor[l]
+    float kp_size;            // (float)(int)(31*scale)
+    int cell0, ncols, nrows;  // first cell id of the level, cell grid
+    int cand_off;             // offset (elements) of the level's compact candidate array inside a frame
+    int cand_cap;
+    int kp_cap;               // capacity of the level's keypoint list
+    int xtab_off, ytab_off;   // offsets into the resize coefficient tables (elements)
+};
+
+struct OrbxCell {             // one FAST cell (ORBextractor.cc:849-914); emission rectangle in payload coords
+    short level;
+    short ex0, ey0, ex1, ey1; // pixels that can be emitted: [ex0,ex1) x [ey0,ey1)
+    short pad;
+    int slot_off;             // offset into the frame's slot array
+    int slot_cap;
+};
+
+struct OrbxResizeTap {        // cv::resize INTER_LINEAR 8U coefficients for one destination coordinate
+    short ofs, c0, c1, pad;
+};
+
+struct OrbxFrameLayout {      // everything the kernels need, passed by value
+    int nlevels, ncells, slot_total, cand_total, kp_cap_total;
+    int ini_th, min_th;
+    size_t frame_raw_bytes;
+    const OrbxLevelGeom* lvl;       // device
+    const OrbxCell* cells;          // device
+    const OrbxResizeTap* taps;      // device
+    uint8_t* raw;                   // [B]
+    uint32_t* slots;                // [B][slot_total]
+    int* cell_count;                // [B][ncells]
+    uint32_t* cand;                 // [B][cand_total]
+    uint16_t* cand_node;            // [B][cand_total]
+    int* cand_count;                // [B][nlevels]
+    uint32_t* lvl_kp;               // [B][kp_cap_total]   (level l at lvl_kp_off[l])
+    int* lvl_kp_count;              // [B][nlevels]
+    int lvl_kp_off[ORBX_MAX_LEVELS];
+    int qt_cap;                     // node-table capacity of the quadtree kernel
+    int status_overflow;            // unused on device
+};
+
+struct OrbxKp28 { float x, y, size, angle, response; int octave, class_id; };
+
+// kernel launchers (implemented in the .cu files; all asynchronous on `st`)
+void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
+                         int stride, size_t frame_pitch, int nframes, cudaStream_t st);
+void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
+void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, cudaStream_t st);
+void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
+                          int* d_nkp, cudaStream_t st);
+void orbx_upload_constants();  // pattern + umax tables
+
+void orbx_launch_hamming_init(uint64_t* d_packed, int nq, cudaStream_t st);
+void orbx_launch_hamming_top2(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, long long index_base,
+                              uint64_t* d_packed, cudaStream_t st);
+void orbx_launch_hamming_merge(const uint64_t* d_parts, int nparts, int nq, int* d_idx, int* d_d1, int* d_d2,
+                               cudaStream_t st);
+void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, const OrbxKp28* kr, const uint8_t* dr,
+                                int nr, const int* row_start, const int* row_tab, int rows, float minD, float maxD,
+                                int* best_idx, int* best_dist, cudaStream_t st);

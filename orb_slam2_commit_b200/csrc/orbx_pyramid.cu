@@ -1,0 +1,86 @@
+// orbx_pyramid.cu — image pyramid resident in HBM (replaces ORBextractor::ComputePyramid,
+// ORBextractor.cc:1215-1250 = cv::resize INTER_LINEAR 8U chain + cv::copyMakeBorder REFLECT_101).
+//
+// One launch per level (level l is resampled from level l-1, so levels are dependent). Each thread produces four
+// horizontally adjacent bytes of the level buffer INCLUDING the 19-px apron: an apron byte is the payload byte at
+// the reflected coordinate, recomputed instead of re-read, so every level is written exactly once and its border
+// needs no second pass. Arithmetic is OpenCV's fixed-point bilinear (11-bit coefficients, tables built on the host
+// in OpenCV's float/double sequence): bit-exact, integer only.
+#include "orbx_internal.cuh"
+
+#define PYR_TX 64
+#define PYR_TY 4
+
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    // |p| never exceeds len by more than the 19-px apron + 3 and len >= 62, so one fold per side is enough
+    p = p < 0 ? -p : p;
+    return p >= len ? 2 * (len - 1) - p : p;
+}
+
+// level 0: copy of the input frame (+apron)
+__global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_kernel(OrbxFrameLayout L, const uint8_t* __restrict__ img, int stride,
+                                                         size_t frame_pitch)
+{
+    const OrbxLevelGeom g = L.lvl[0];
+    const int t = blockIdx.x * PYR_TX + threadIdx.x;        // group of 4 buffer columns starting at column 12
+    const int rb = blockIdx.y * PYR_TY + threadIdx.y;       // buffer row
+    const int cb = 12 + 4 * t;
+    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb >= g.h + 2 * ORBX_EDGE) return;
+    const int yr = reflect101(rb - ORBX_EDGE, g.h);
+    const uint8_t* src = img + (size_t)blockIdx.z * frame_pitch + (size_t)yr * stride;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int xr = reflect101(cb + k - ORBX_XOFF, g.w);
+        out |= (uint32_t)__ldg(src + xr) << (8 * k);
+    }
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb * g.pitch + cb;
+    *reinterpret_cast<uint32_t*>(dst) = out;
+}
+
+// level l > 0 from level l-1
+__global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_kernel(OrbxFrameLayout L, int level)
+{
+    const OrbxLevelGeom g = L.lvl[level];
+    const OrbxLevelGeom s = L.lvl[level - 1];
+    const int t = blockIdx.x * PYR_TX + threadIdx.x;
+    const int rb = blockIdx.y * PYR_TY + threadIdx.y;
+    const int cb = 12 + 4 * t;
+    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb >= g.h + 2 * ORBX_EDGE) return;
+    const int yr = reflect101(rb - ORBX_EDGE, g.h);
+    const OrbxResizeTap ty = L.taps[g.ytab_off + yr];
+    const uint8_t* sbase = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + s.raw_off + ORBX_XOFF;
+    // rows sy and sy+1 of the source payload; when sy is the last row its coefficient c1 is 0 and row sy+1 is the
+    // (valid) apron row, so no clamp is needed — same for columns
+    const uint8_t* r0 = sbase + (size_t)(ty.ofs + ORBX_EDGE) * s.pitch;
+    const uint8_t* r1 = r0 + s.pitch;
+    const int b0 = ty.c0, b1 = ty.c1;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int xr = reflect101(cb + k - ORBX_XOFF, g.w);
+        const OrbxResizeTap tx = L.taps[g.xtab_off + xr];
+        const int a0 = tx.c0, a1 = tx.c1, sx = tx.ofs;
+        const int S0 = r0[sx] * a0 + r0[sx + 1] * a1;
+        const int S1 = r1[sx] * a0 + r1[sx + 1] * a1;
+        const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        out |= (uint32_t)(v & 0xff) << (8 * k);
+    }
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb * g.pitch + cb;
+    *reinterpret_cast<uint32_t*>(dst) = out;
+}
+
+void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
+                         int stride, size_t frame_pitch, int nframes, cudaStream_t st)
+{
+    (void)w; (void)h;
+    for (int l = 0; l < L.nlevels; l++) {
+        const OrbxLevelGeom& g = h_lvl[l];
+        const int groups = (ORBX_XOFF + g.w + ORBX_EDGE - 12 + 3) / 4;
+        dim3 grid((groups + PYR_TX - 1) / PYR_TX, (g.h + 2 * ORBX_EDGE + PYR_TY - 1) / PYR_TY, nframes);
+        dim3 block(PYR_TX, PYR_TY);
+        if (l == 0) pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
+        else pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
+    }
+}
