@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py — ORB front-end throughput on B200 (BASELINE.json metric: ORB frames/s, 640x480, 1000 kp, 8 levels).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (hand-written sm_100a kernels via the C ABI)
+  python bench.py --impl reference [...]                         the reference's CPU ORBextractor on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU, frames sharded by frame (weak scaling)
+
+A step = one pass of the whole hot path (pyramid -> per-cell FAST -> quadtree -> orientation + blur + rBRIEF) over
+one batch of synthetic frames. `value` = frames/s with the batch already resident in HBM; `e2e` = the same metric
+through the public C-ABI call orbx_extract_batch with pinned HOST buffers (H2D + D2H inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from orb_slam2_commit_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json metric is quoted on this one (configs[0] geometry, batched as in configs[2])
+    "tum1": dict(cfg="tum1", batch=512, distinct=32),
+    "euroc": dict(cfg="euroc", batch=512, distinct=32),
+    "kitti": dict(cfg="kitti", batch=256, distinct=16),
+    "4k": dict(cfg="4k", batch=8, distinct=4),
+}
+
+
+def level_geometry(c):
+    """Pyramid payload sizes with the reference's own formula (ORBextractor.cc:1221-1225), float32 arithmetic."""
+    sf = np.float32(1.0)
+    sizes = []
+    for l in range(c["nlevels"]):
+        inv = np.float32(1.0) / sf
+        sizes.append((int(np.rint(np.float32(c["width"]) * inv)), int(np.rint(np.float32(c["height"]) * inv))))
+        sf = np.float32(np.float64(sf) * np.float64(np.float32(c["scale"])))
+    return sizes
+
+
+def algorithmic_bytes(c, nkp_mean):
+    """per image B = P0 + 3A + N(961+60) for the reference's data flow; per stage of THIS design
+    (DESIGN.md §kernels): pyramid P0 + A, FAST A, quadtree 8 B per candidate (in+out, ~ignored), describe N*1021."""
+    P0 = c["width"] * c["height"]
+    A = sum(w * h for w, h in level_geometry(c))
+    return dict(P0=P0, A=A, B_survey=P0 + 3 * A + nkp_mean * 1021, pyramid=P0 + A, fast=A, describe=nkp_mean * 1021,
+                quadtree=0)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples in the upper half of what we saw (idle samples at the edges drop out)
+        if sm:
+            top = max(sm)
+            load = [x for x in sm if x >= 0.5 * top]
+            return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+
+def make_frames(c, distinct, seed0=1):
+    return np.stack([synth.synth_image(c["width"], c["height"], seed0 + i) for i in range(distinct)])
+
+
+def cpu_reference_bench(c, frames, target_seconds, nthreads):
+    """Times the reference's own CPU ORBextractor (oracle/_ref = verbatim ORBextractor.cc + cvshim) or, when that
+    library is absent, the oracle port, frame-parallel over `nthreads` host threads. Returns (frames/s, kind, sample)."""
+    from oracle import binding as ob
+    frames = np.ascontiguousarray(frames)
+    n_img = len(frames)
+    if ob.ref_available():
+        R = ob.ref_lib()
+        import ctypes as C
+        tot = C.c_longlong(0)
+
+        def run(iters):
+            return R.orbref_bench(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"],
+                                  frames.ctypes.data_as(ob.u8p), c["width"], c["height"], n_img, iters, nthreads, C.byref(tot))
+        t1 = run(nthreads)                         # warm-up + calibration: one frame per thread
+        iters = int(max(nthreads, min(100000, nthreads * max(1.0, target_seconds / max(t1, 1e-3)))))
+        iters = (iters // nthreads) * nthreads
+        t = run(iters)
+        return iters / t, "reference", f"{iters} frames ({n_img} distinct) over {nthreads} threads, {t:.1f} s", tot.value / iters
+    # port fallback: the oracle through ctypes (releases the GIL)
+    exs = [ob.Extractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"]) for _ in range(nthreads)]
+    counts = [0] * nthreads
+
+    def work(t, iters):
+        for i in range(t, iters, nthreads):
+            k, _ = exs[t].extract(frames[i % n_img])
+            counts[t] += len(k)
+
+    def run(iters):
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, iters)) for t in range(nthreads)]
+        [x.start() for x in th]; [x.join() for x in th]
+        return time.perf_counter() - t0
+    t1 = run(nthreads)
+    iters = int(max(nthreads, nthreads * max(1.0, target_seconds / max(t1, 1e-3))))
+    counts[:] = [0] * nthreads
+    t = run(iters)
+    return iters / t, "port", f"{iters} frames ({n_img} distinct) over {nthreads} threads, {t:.1f} s", sum(counts) / iters
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    c = synth.CONFIGS[w["cfg"]]
+    frames = make_frames(c, min(w["distinct"], 8))
+    nthreads = os.cpu_count() or 1
+    from oracle import binding as ob
+    import ctypes as C
+    per_step = max(nthreads, 2 * nthreads)
+    times = []
+    kind = "reference" if ob.ref_available() else "port"
+    if kind == "reference":
+        R = ob.ref_lib(); tot = C.c_longlong(0)
+        fr = np.ascontiguousarray(frames)
+        for s in range(args.warmup + args.steps):
+            t = R.orbref_bench(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"], fr.ctypes.data_as(ob.u8p),
+                               c["width"], c["height"], len(fr), per_step, nthreads, C.byref(tot))
+            if s >= args.warmup:
+                times.append(t)
+    else:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            fps, _, _, _ = cpu_reference_bench(c, frames, 0.0, nthreads)
+            if s >= args.warmup:
+                times.append(per_step / fps)
+    total = sum(times)
+    value = per_step * len(times) / total
+    line = {"impl": "reference", "metric": "orb_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{w['cfg']}: {c['width']}x{c['height']}, nFeatures={c['nfeatures']}, scale {c['scale']}, {c['nlevels']} levels, FAST {c['ini_th']}/{c['min_th']}",
+                       "frames_per_step": per_step, "host_threads": nthreads},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nthreads, "kind": kind,
+                             "sample": f"{per_step} frames per step, {len(times)} steps"},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def bench_hamming(torch, api_lib, dev, peaks, sm_mhz):
+    """BASELINE config 4: 2048 x 1,000,000 x 256-bit brute-force top-2, inputs resident."""
+    nq, nt = 2048, 1_000_000
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    train = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device=dev, generator=g)
+    query = train[torch.randint(0, nt, (nq,), device=dev, generator=g)].clone()
+    query[:, :4] ^= 0x5a
+    packed = torch.empty(nq, dtype=torch.int64, device=dev)
+    out = torch.empty(3, nq, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        api_lib.orbx_hamming_init_device(packed.data_ptr(), nq, st)
+        api_lib.orbx_hamming_top2_device(query.data_ptr(), nq, train.data_ptr(), nt, 0, packed.data_ptr(), st)
+        api_lib.orbx_hamming_merge_device(packed.data_ptr(), 1, nq, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), st)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg_bytes = 32 * nt + 32 * nq + 8 * nq
+    popc = 8.0 * nq * nt
+    clk = (sm_mhz or 1965.0) * 1e6
+    return {"workload": "2048 queries x 1,000,000 train rows, 256-bit, top-2", "ms": ms, "matches_per_s": nq / (ms * 1e-3),
+            "pair_distances_per_s": nq * nt / (ms * 1e-3), "algorithmic_GBps": alg_bytes / (ms * 1e-3) / 1e9,
+            "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "popc_pipe_frac": popc / (ms * 1e-3) / (148 * 16 * clk), "popc_pipe_model": "148 SMs x 16 popc/clk x measured SM clock"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tum1", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hamming", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from orb_slam2_commit_b200 import ORBextractor, api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = WORKLOADS[args.workload]
+    c = synth.CONFIGS[w["cfg"]]
+    B = args.batch or w["batch"]
+    W, H = c["width"], c["height"]
+    # every rank extracts its own shard of the frame stream (frame index -> rank); seeds differ per rank
+    frames = make_frames(c, w["distinct"], seed0=1 + 1000 * rank)
+    host_batch = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+    hb = host_batch.numpy()
+    for i in range(B):
+        hb[i] = frames[i % len(frames)]
+    d_imgs = host_batch.to(dev)
+
+    ex = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"], device=local)
+    cap = ex.reserve(W, H, B)
+    d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_nkp = torch.zeros(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ex.extract_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), cap, d_nkp.data_ptr(), d_desc.data_ptr(), stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ex.enable_timing(True)
+    sampler = ClockSampler(local); sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    stage_ms, nruns = ex.stage_ms()
+    ex.enable_timing(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    nkp = d_nkp.cpu().numpy()
+    nkp_mean = float(nkp.mean())
+    frames_per_s = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e through the public C-ABI call with pinned host buffers
+    h_kps = torch.empty((B, cap, 28), dtype=torch.uint8, pin_memory=True)
+    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True)
+    h_nkp = torch.zeros(B, dtype=torch.int32, pin_memory=True)
+    kps_np = h_kps.numpy().view(api.KP_DTYPE).reshape(B, cap)
+    desc_np = h_desc.numpy(); nkp_np = h_nkp.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ex.extract_host(hb, kps_np, desc_np, nkp_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ex.extract_host(hb, kps_np, desc_np, nkp_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_fps = world * B * e2e_steps / e2e_s
+    assert int(nkp_np.sum()) == int(nkp.sum()), "host path and device path disagree"
+
+    if rank == 0:
+        peaks = {"hbm_gbs": 6650.0, "source": "fallback"}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            try:
+                peaks = {"hbm_gbs": float(json.load(open(pk))["hbm_gbs"]), "source": "measured"}
+            except Exception:
+                pass
+        ab = algorithmic_bytes(c, nkp_mean)
+        names = ["pyramid", "fast", "quadtree", "describe"]
+        stages = {n: {"ms_per_launch_group": float(stage_ms[i]), "share": float(stage_ms[i] / max(stage_ms.sum(), 1e-9))} for i, n in enumerate(names)}
+        dom = int(np.argmax(stage_ms))
+        dom_bytes = ab[names[dom]] * B
+        achieved = dom_bytes / (float(stage_ms[dom]) * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": {"pyramid": "pyr_level0_kernel+pyr_resize_kernel (one launch per level)", "fast": "fast_cells_kernel",
+                                              "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]],
+                    "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                    "algorithmic_bytes_per_frame": ab[names[dom]], "frames_per_launch": B, "traffic": None,
+                    "stage_events_averaged_over_steps": nruns}
+        launches_per_step = c["nlevels"] + 3
+        line = {"metric": "orb_frames_per_s", "value": frames_per_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"{w['cfg']}: {W}x{H} mono frames, nFeatures={c['nfeatures']}, scale {c['scale']}, {c['nlevels']} levels, FAST {c['ini_th']}/{c['min_th']}",
+                           "frames_per_step_per_gpu": B, "distinct_frames": len(frames), "sharding": "by frame, no collective",
+                           "l2": f"batch working set {B * (W * H + ab['A'] * 1.3) / 1e6:.0f} MB per step > 126 MB L2 (inputs {B * W * H / 1e6:.0f} MB)"},
+                "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
+                        "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": "orbx_extract_batch (pinned host buffers)"},
+                "roofline": roofline, "stages": stages,
+                "pipeline": {"keypoints_per_frame": nkp_mean, "keypoints_per_s": frames_per_s * nkp_mean,
+                             "algorithmic_bytes_per_frame_survey": ab["B_survey"],
+                             "hbm_frac_of_survey_bytes": frames_per_s / world * ab["B_survey"] / 1e9 / peaks["hbm_gbs"]}}
+        if not args.no_hamming:
+            try:
+                line["hamming"] = bench_hamming(torch, api.lib(), dev, peaks, clocks.get("sm_mhz"))
+            except Exception as e:  # never lose the main line
+                line["hamming"] = {"error": str(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            nthreads = os.cpu_count() or 1
+            fps, kind, sample, kpf = cpu_reference_bench(c, frames[:8], args.cpu_seconds, nthreads)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": kind, "sample": sample,
+                                    "keypoints_per_frame": kpf}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

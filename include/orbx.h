@@ -90,6 +90,13 @@ int orbx_extract_device(orbx_extractor* h, const uint8_t* d_images, int n, int w
                         uint8_t* d_descriptors, void* cuda_stream);
 int orbx_synchronize(orbx_extractor* h);
 
+/* Measurement hook (bench.py): when enabled, CUDA events are recorded on the launching stream around the four
+ * stages of every extract (pyramid, FAST cells, quadtree, orientation+descriptor).
+ * orbx_get_stage_ms waits for the last run and returns the mean device time of each stage, in milliseconds, over
+ * the pipeline runs recorded since timing was enabled (the most recent 64 at most); *nruns = how many. */
+int orbx_enable_timing(orbx_extractor* h, int on);
+int orbx_get_stage_ms(orbx_extractor* h, float* ms4, int* nruns);
+
 /* ---- std::vector<cv::Mat> mvImagePyramid  (ORBextractor.h:104; read by Frame.cc:556,681-700) ----
  * Level geometry of the last extract, and a copy of level `level` of frame `frame` INCLUDING its 19-px
  * BORDER_REFLECT_101 apron into dst ((h+38) rows of (w+38) bytes, dst_stride >= w+38) — the layout of the reference's

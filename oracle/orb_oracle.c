@@ -225,10 +225,15 @@ void oc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* d
     uint16_t* hb = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * (size_t)h);
     for (int y = 0; y < h; y++) {
         const uint8_t* s = src + (size_t)y * sstride;
+        uint16_t* o = hb + (size_t)y * w;
         for (int x = 0; x < w; x++) {
-            int acc = 0;
-            for (int k = -3; k <= 3; k++) acc += K[k + 3] * s[reflect101(x + k, w)];
-            hb[(size_t)y * w + x] = (uint16_t)acc;
+            if (x >= 3 && x < w - 3) {
+                o[x] = (uint16_t)(18 * (s[x - 3] + s[x + 3]) + 34 * (s[x - 2] + s[x + 2]) + 48 * (s[x - 1] + s[x + 1]) + 56 * s[x]);
+            } else {
+                int acc = 0;
+                for (int k = -3; k <= 3; k++) acc += K[k + 3] * s[reflect101(x + k, w)];
+                o[x] = (uint16_t)acc;
+            }
         }
     }
     for (int y = 0; y < h; y++) {
@@ -236,8 +241,8 @@ void oc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* d
         for (int k = -3; k <= 3; k++) r[k + 3] = hb + (size_t)reflect101(y + k, h) * w;
         uint8_t* d = dst + (size_t)y * dstride;
         for (int x = 0; x < w; x++) {
-            uint32_t acc = 0;
-            for (int k = 0; k < 7; k++) acc += (uint32_t)K[k] * r[k][x];
+            uint32_t acc = 18u * ((uint32_t)r[0][x] + r[6][x]) + 34u * ((uint32_t)r[1][x] + r[5][x]) +
+                           48u * ((uint32_t)r[2][x] + r[4][x]) + 56u * r[3][x];
             acc = (acc + 32768u) >> 16;
             d[x] = (uint8_t)(acc > 255 ? 255 : acc);
         }
@@ -272,17 +277,30 @@ static int corner_score(const uint8_t* p, int stride, int threshold)
 }
 int oc_fast_score(const uint8_t* p, int stride) { return corner_score(p, stride, 0); }
 
-/* FAST_t<16> corner test: >= 9 contiguous ring pixels all darker than v-T or all brighter than v+T */
-static int is_corner(const uint8_t* p, int stride, int T)
+/* FAST_t<16> corner test: >= 9 contiguous ring pixels all darker than v-T or all brighter than v+T.
+ * Same early-outs as cv::FAST_t: every 9-arc contains one pixel of each opposite pair (k, k+8). */
+static inline int ring_class(int x, int lo, int hi) { return (x < lo ? 1 : 0) | (x > hi ? 2 : 0); }
+static int is_corner(const uint8_t* p, const int* off, int T)
 {
-    int v = p[0], lo = v - T, hi = v + T;
-    int r0 = p[3 * stride], r8 = p[-3 * stride];
-    if (!((r0 < lo) | (r0 > hi) | (r8 < lo) | (r8 > hi))) return 0; /* every 9-arc holds ring[0] or ring[8] */
-    int dark = 0, bright = 0;
-    for (int k = 0; k < 25; k++) {
-        int x = p[g_ring_dy[k & 15] * stride + g_ring_dx[k & 15]];
-        if (x < lo) { if (++dark > 8) return 1; } else dark = 0;
-        if (x > hi) { if (++bright > 8) return 1; } else bright = 0;
+    const int v = p[0], lo = v - T, hi = v + T;
+    int d = ring_class(p[off[0]], lo, hi) | ring_class(p[off[8]], lo, hi);
+    if (!d) return 0;
+    d &= ring_class(p[off[2]], lo, hi) | ring_class(p[off[10]], lo, hi);
+    d &= ring_class(p[off[4]], lo, hi) | ring_class(p[off[12]], lo, hi);
+    d &= ring_class(p[off[6]], lo, hi) | ring_class(p[off[14]], lo, hi);
+    if (!d) return 0;
+    d &= ring_class(p[off[1]], lo, hi) | ring_class(p[off[9]], lo, hi);
+    d &= ring_class(p[off[3]], lo, hi) | ring_class(p[off[11]], lo, hi);
+    d &= ring_class(p[off[5]], lo, hi) | ring_class(p[off[13]], lo, hi);
+    d &= ring_class(p[off[7]], lo, hi) | ring_class(p[off[15]], lo, hi);
+    if (!d) return 0;
+    if (d & 1) {
+        int n = 0;
+        for (int k = 0; k < 25; k++) { if (p[off[k & 15]] < lo) { if (++n > 8) return 1; } else n = 0; }
+    }
+    if (d & 2) {
+        int n = 0;
+        for (int k = 0; k < 25; k++) { if (p[off[k & 15]] > hi) { if (++n > 8) return 1; } else n = 0; }
     }
     return 0;
 }
@@ -292,25 +310,28 @@ int oc_fast9_16(const uint8_t* roi, int w, int h, int stride, int threshold, int
     if (threshold < 0) threshold = 0;
     if (threshold > 255) threshold = 255;
     if (w < 7 || h < 7) return 0;
-    uint8_t* sc = (uint8_t*)calloc((size_t)w * (size_t)h, 1); /* score buffer: 0 = not a corner */
-    uint8_t* isc = (uint8_t*)calloc((size_t)w * (size_t)h, 1);
-    for (int y = 3; y < h - 3; y++)
-        for (int x = 3; x < w - 3; x++) {
-            const uint8_t* p = roi + (size_t)y * stride + x;
-            if (is_corner(p, stride, threshold)) {
-                isc[(size_t)y * w + x] = 1;
-                sc[(size_t)y * w + x] = (uint8_t)corner_score(p, stride, threshold);
-            }
-        }
+    int off[16];
+    for (int k = 0; k < 16; k++) off[k] = g_ring_dy[k] * stride + g_ring_dx[k];
+    /* score buffer: 0 = not a corner; bit 8 marks a corner whose score is 0 (possible only when threshold == 0) */
+    uint16_t stackbuf[64 * 64];
+    const size_t npx = (size_t)w * (size_t)h;
+    uint16_t* sc = npx <= 64 * 64 ? stackbuf : (uint16_t*)malloc(npx * sizeof(uint16_t));
+    memset(sc, 0, npx * sizeof(uint16_t));
+    for (int y = 3; y < h - 3; y++) {
+        const uint8_t* row = roi + (size_t)y * stride;
+        uint16_t* srow = sc + (size_t)y * w;
+        for (int x = 3; x < w - 3; x++)
+            if (is_corner(row + x, off, threshold)) srow[x] = (uint16_t)(0x100 | corner_score(row + x, stride, threshold));
+    }
     int n = 0;
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x < w - 3; x++) {
-            if (!isc[(size_t)y * w + x]) continue;
-            int s = sc[(size_t)y * w + x];
+            const uint16_t* c = sc + (size_t)y * w + x;
+            if (!c[0]) continue;
+            const int s = c[0] & 0xff;
             if (nms) {
-                const uint8_t* c = sc + (size_t)y * w + x;
-                if (!(s > c[-1] && s > c[1] && s > c[-w - 1] && s > c[-w] && s > c[-w + 1] &&
-                      s > c[w - 1] && s > c[w] && s > c[w + 1])) continue;
+                if (!(s > (c[-1] & 0xff) && s > (c[1] & 0xff) && s > (c[-w - 1] & 0xff) && s > (c[-w] & 0xff) &&
+                      s > (c[-w + 1] & 0xff) && s > (c[w - 1] & 0xff) && s > (c[w] & 0xff) && s > (c[w + 1] & 0xff))) continue;
             }
             if (n < cap) {
                 OcKeyPoint k = {(float)x, (float)y, 7.f, -1.f, nms ? (float)s : 0.f, 0, -1};
@@ -318,7 +339,7 @@ int oc_fast9_16(const uint8_t* roi, int w, int h, int stride, int threshold, int
             }
             n++;
         }
-    free(sc); free(isc);
+    if (sc != stackbuf) free(sc);
     return n;
 }
 

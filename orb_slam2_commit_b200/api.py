@@ -66,6 +66,8 @@ def lib():
         L.orbx_extract_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_synchronize.argtypes = [C.c_void_p]
+        L.orbx_enable_timing.argtypes = [C.c_void_p, C.c_int]
+        L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
         L.orbx_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
         L.orbx_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, C.c_int]
         L.orbx_pyramid_level_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), i32p]
@@ -181,6 +183,23 @@ class ORBextractor:
 
     def synchronize(self):
         _ck(self._L.orbx_synchronize(self._h))
+
+    def enable_timing(self, on=True):
+        _ck(self._L.orbx_enable_timing(self._h, int(on)))
+
+    def stage_ms(self):
+        ms = np.zeros(4, np.float32); n = C.c_int32(0)
+        _ck(self._L.orbx_get_stage_ms(self._h, ms.ctypes.data_as(f32p), C.byref(n)))
+        return ms, n.value
+
+    def extract_host(self, images: np.ndarray, kps: np.ndarray, desc: np.ndarray, nkp: np.ndarray):
+        """orbx_extract_batch on caller-owned (ideally pinned) buffers: images (n,h,w) u8 contiguous,
+        kps (n,cap) KP_DTYPE, desc (n,cap,32) u8, nkp (n,) i32. No allocation, no copies on the Python side."""
+        n, h, w = images.shape
+        cap = kps.shape[1]
+        base = images.ctypes.data
+        ptrs = (C.c_void_p * n)(*[base + i * h * w for i in range(n)])
+        _ck(self._L.orbx_extract_batch(self._h, ptrs, n, w, h, w, kps.ctypes.data, cap, nkp.ctypes.data_as(i32p), desc.ctypes.data))
 
     # ---- mvImagePyramid (ORBextractor.h:104)
     def level_size(self, level):

@@ -44,14 +44,13 @@ struct orbx_extractor {
     OrbxKp28* d_kps = nullptr;                    // [B][kp_cap_total]
     uint8_t* d_desc = nullptr;
     int* d_nkp = nullptr;
-    // pinned host staging
-    uint8_t* h_in = nullptr;
-    OrbxKp28* h_kps = nullptr;
-    uint8_t* h_desc = nullptr;
-    int* h_nkp = nullptr;
     cudaStream_t stream = nullptr;
     int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
     bool constants_ready = false;
+    bool timing = false;
+    static const int RING = 64;
+    cudaEvent_t ev[RING][5] = {};
+    long long runs = 0;                          // pipeline runs recorded since timing was enabled
 };
 
 static int round_half_even(float v) { return (int)lrintf(v); }   // cvRound
@@ -118,8 +117,6 @@ static void release_device(orbx_extractor* h)
     h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr;
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
     h->d_in = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_nkp = nullptr;
-    cudaFreeHost(h->h_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc); cudaFreeHost(h->h_nkp);
-    h->h_in = nullptr; h->h_kps = nullptr; h->h_desc = nullptr; h->h_nkp = nullptr;
     h->W = h->H = h->max_batch = 0;
 }
 
@@ -127,6 +124,8 @@ extern "C" void orbx_destroy(orbx_extractor* h)
 {
     if (!h) return;
     release_device(h);
+    for (int r = 0; r < orbx_extractor::RING; r++)
+        for (int i = 0; i < 5; i++) if (h->ev[r][i]) cudaEventDestroy(h->ev[r][i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -285,10 +284,6 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     CK(cudaMalloc(&h->d_kps, B * L.kp_cap_total * sizeof(OrbxKp28)));
     CK(cudaMalloc(&h->d_desc, B * L.kp_cap_total * 32));
     CK(cudaMalloc(&h->d_nkp, B * sizeof(int)));
-    CK(cudaMallocHost(&h->h_in, in_bytes));
-    CK(cudaMallocHost(&h->h_kps, B * L.kp_cap_total * sizeof(OrbxKp28)));
-    CK(cudaMallocHost(&h->h_desc, B * L.kp_cap_total * 32));
-    CK(cudaMallocHost(&h->h_nkp, B * sizeof(int)));
     if (!h->constants_ready) { orbx_upload_constants(); CK(cudaGetLastError()); h->constants_ready = true; }
     h->W = width; h->H = height; h->max_batch = max_batch; h->last_frames = 0;
     return ORBX_OK;
@@ -300,10 +295,18 @@ extern "C" int orbx_max_keypoints(const orbx_extractor* h) { return (h && h->W) 
 static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stride, size_t frame_pitch,
                         OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st)
 {
+    const bool tm = h->timing;
+    cudaEvent_t* ev = h->ev[h->runs % orbx_extractor::RING];
+    if (tm) cudaEventRecord(ev[0], st);
     orbx_launch_pyramid(h->L, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st);
+    if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(h->L, h->max_tile_w, h->max_tile_h, n, st);
+    if (tm) cudaEventRecord(ev[2], st);
     orbx_launch_quadtree(h->L, n, st);
+    if (tm) cudaEventRecord(ev[3], st);
     orbx_launch_describe(h->L, n, d_kps, d_desc, cap, d_nkp, st);
+    if (tm) cudaEventRecord(ev[4], st);
+    if (tm) h->runs++;
     CK(cudaGetLastError());
     h->last_frames = n;
     return ORBX_OK;
@@ -332,6 +335,36 @@ extern "C" int orbx_synchronize(orbx_extractor* h)
     return ORBX_OK;
 }
 
+extern "C" int orbx_enable_timing(orbx_extractor* h, int on)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (on && !h->ev[0][0]) {
+        if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible");
+        CK(cudaSetDevice(h->device));
+        for (int r = 0; r < orbx_extractor::RING; r++)
+            for (int i = 0; i < 5; i++) CK(cudaEventCreate(&h->ev[r][i]));
+    }
+    h->timing = on != 0;
+    h->runs = 0;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_get_stage_ms(orbx_extractor* h, float* ms4, int* nruns)
+{
+    if (!h || !ms4 || !h->ev[0][0]) return fail(ORBX_ERR_STATE, "timing was never enabled");
+    CK(cudaSetDevice(h->device));
+    const int n = (int)std::min<long long>(h->runs, orbx_extractor::RING);
+    double acc[4] = {0, 0, 0, 0};
+    for (int k = 0; k < n; k++) {
+        cudaEvent_t* ev = h->ev[(h->runs - 1 - k) % orbx_extractor::RING];
+        CK(cudaEventSynchronize(ev[4]));
+        for (int i = 0; i < 4; i++) { float ms; CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); acc[i] += ms; }
+    }
+    for (int i = 0; i < 4; i++) ms4[i] = n ? (float)(acc[i] / n) : 0.f;
+    if (nruns) *nruns = n;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
                                   int stride, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
 {
@@ -348,28 +381,38 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* image
     int status = ORBX_OK;
     for (int f0 = 0; f0 < n; f0 += B) {
         const int m = std::min(B, n - f0);
-        for (int i = 0; i < m; i++) {
+        // frames that are contiguous in host memory go up in one copy, otherwise one (strided) copy per frame
+        bool contiguous = stride == width;
+        for (int i = 0; i < m && contiguous; i++) {
             if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
-            // pack to contiguous pinned staging, then one H2D copy
-            uint8_t* dst = h->h_in + (size_t)i * fbytes;
-            if (stride == width) memcpy(dst, images[f0 + i], fbytes);
-            else for (int y = 0; y < height; y++) memcpy(dst + (size_t)y * width, images[f0 + i] + (size_t)y * stride, width);
+            contiguous = images[f0 + i] == images[f0] + (size_t)i * fbytes;
         }
-        CK(cudaMemcpyAsync(h->d_in, h->h_in, (size_t)m * fbytes, cudaMemcpyHostToDevice, h->stream));
+        if (contiguous) CK(cudaMemcpyAsync(h->d_in, images[f0], (size_t)m * fbytes, cudaMemcpyHostToDevice, h->stream));
+        else
+            for (int i = 0; i < m; i++) {
+                if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
+                CK(cudaMemcpy2DAsync(h->d_in + (size_t)i * fbytes, width, images[f0 + i], stride, width, height,
+                                     cudaMemcpyHostToDevice, h->stream));
+            }
         int rc = run_pipeline(h, h->d_in, m, width, fbytes, h->d_kps, h->d_desc, kc, h->d_nkp, h->stream);
         if (rc != ORBX_OK) return rc;
-        CK(cudaMemcpyAsync(h->h_nkp, h->d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)m * kc * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)m * kc * 32, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        for (int i = 0; i < m; i++) {
-            const int k = h->h_nkp[i];
-            nkp[f0 + i] = k;
-            const int c = std::min(k, cap);
-            if (k > cap) status = ORBX_ERR_CAPACITY;
-            memcpy(keypoints + (size_t)(f0 + i) * cap, h->h_kps + (size_t)i * kc, (size_t)c * sizeof(OrbxKp28));
-            memcpy(descriptors + (size_t)(f0 + i) * cap * 32, h->h_desc + (size_t)i * kc * 32, (size_t)c * 32);
+        CK(cudaMemcpyAsync(nkp + f0, h->d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (cap == kc) {
+            // caller sized its buffers with orbx_max_keypoints(): results land in place with two bulk copies
+            CK(cudaMemcpyAsync(keypoints + (size_t)f0 * cap, h->d_kps, (size_t)m * kc * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(descriptors + (size_t)f0 * cap * 32, h->d_desc, (size_t)m * kc * 32, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        } else {
+            CK(cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < m; i++) {
+                const int c = std::min(nkp[f0 + i], cap);
+                if (c <= 0) continue;
+                CK(cudaMemcpyAsync(keypoints + (size_t)(f0 + i) * cap, h->d_kps + (size_t)i * kc, (size_t)c * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpyAsync(descriptors + (size_t)(f0 + i) * cap * 32, h->d_desc + (size_t)i * kc * 32, (size_t)c * 32, cudaMemcpyDeviceToHost, h->stream));
+            }
+            CK(cudaStreamSynchronize(h->stream));
         }
+        for (int i = 0; i < m; i++) if (nkp[f0 + i] > cap) status = ORBX_ERR_CAPACITY;
     }
     if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
     return status;
