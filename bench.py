@@ -268,7 +268,10 @@ def main():
     d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
     d_nkp = torch.zeros(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream: the kernels, the timing events and the torch events all live on it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def step():
         ex.extract_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), cap, d_nkp.data_ptr(), d_desc.data_ptr(), stream)

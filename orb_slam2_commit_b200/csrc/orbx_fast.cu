@@ -2,132 +2,188 @@
 // ORBextractor::ComputeKeyPointsOctTree, ORBextractor.cc:849-914, and the cv::FAST(..., nonmaxSuppression=true)
 // calls inside it).
 //
-// One CTA per 30-px cell, all levels and all frames of the batch in ONE launch (grid = cells x frames).
-// The cell tile (+3-px ring) is staged in shared memory; the corner score never touches HBM:
-//   score(p) = max over the 16 arcs of 9 contiguous ring pixels of max(min d, -max d) - 1,  d_k = I(p) - I(ring_k)
-//   p is a corner at threshold T  <=>  score(p) >= T        (cv::cornerScore<16>; independent of T)
-// so one definition serves both thresholds. NMS is cv::FAST's strict 3x3 test on a score map that is zero for
-// non-corners and zero outside the cell's own scored rectangle (NMS never crosses cell borders in the reference,
-// because every cell is a separate cv::FAST call on a sub-image). If NMS at iniThFAST leaves nothing, the cell is
-// redone at minThFAST. Survivors are written in row-major order (cv::FAST's output order) into the cell's slot.
+// ONE WARP PER 30-px CELL, all levels and all frames of the batch in one launch; no block-level barrier anywhere.
+// The warp stages the cell tile (+3-px ring) in shared memory with aligned 32-bit loads, then
+//   1. quick test (four compass pixels) on every pixel; survivors are appended, in row-major order, to a per-warp
+//      list with ballot + popc (dense work for the expensive step, no divergence waste);
+//   2. exact corner score for the listed pixels only, written to a zero-initialised u8 score map:
+//        score(p) = max over the 16 arcs of 9 contiguous ring pixels of max(min d, -max d) - 1,  d_k = I(p) - I(ring_k)
+//        p is a corner at threshold T  <=>  score(p) >= T      (cv::cornerScore<16>; independent of T)
+//   3. cv::FAST's strict 3x3 non-max suppression over the list (still row-major), survivors written to the cell's
+//      slot with ballot-prefix offsets — the reference's output order.
+// The score map is zero outside the cell's own scored rectangle: in the reference every cell is a separate
+// cv::FAST call on a sub-image, so NMS never sees a neighbouring cell. If step 3 leaves nothing at iniThFAST the
+// cell is redone at minThFAST (ORBextractor.cc:894-900). The score map never touches HBM.
 #include "orbx_internal.cuh"
 
-#define FAST_THREADS 256
+#define FAST_WARPS 4
 
-// exact corner score at threshold T (0 when the pixel is not a corner at T). `c` = centre pixel in the smem tile.
-__device__ __forceinline__ int fast_score_T(const uint8_t* __restrict__ c, const int tp, const int T)
+struct FastSmemCfg { int tpw, th, sp, srows, list_cap, tile_off, score_off, list_off, per_warp; };
+
+// exact corner score of a pixel that passed the quick test at threshold T; 0 when it is not a corner at T.
+// dark / bright say which kind of arc is possible at all (>= 2 compass pixels on that side).
+// NOTE: keep A and B as two separate accumulators. Folding them into one running `best = max(best, min3(..))`
+// chain is mis-compiled by ptxas 12.9 for sm_100a (VIMNMX3 fusion) — caught by tests/test_gpu_parity.py.
+__device__ __forceinline__ int fast_score_T(const uint8_t* __restrict__ c, const int tp, const int T,
+                                            const bool dark, const bool bright)
 {
     const int v = c[0];
-    const int d0 = v - c[3 * tp], d4 = v - c[3], d8 = v - c[-3 * tp], d12 = v - c[-3];
-    // every arc of 9 contiguous ring pixels holds at least two of the four compass pixels
-    const int nd = (d0 > T) + (d4 > T) + (d8 > T) + (d12 > T);
-    const int nb = (d0 < -T) + (d4 < -T) + (d8 < -T) + (d12 < -T);
-    if (nd < 2 && nb < 2) return 0;
     int d[16];
-    d[0] = d0; d[4] = d4; d[8] = d8; d[12] = d12;
-    d[1] = v - c[3 * tp + 1];   d[2] = v - c[2 * tp + 2];   d[3] = v - c[tp + 3];
-    d[5] = v - c[-tp + 3];      d[6] = v - c[-2 * tp + 2];  d[7] = v - c[-3 * tp + 1];
-    d[9] = v - c[-3 * tp - 1];  d[10] = v - c[-2 * tp - 2]; d[11] = v - c[-tp - 3];
-    d[13] = v - c[tp - 3];      d[14] = v - c[2 * tp - 2];  d[15] = v - c[3 * tp - 1];
+    d[0] = v - c[3 * tp];       d[1] = v - c[3 * tp + 1];   d[2] = v - c[2 * tp + 2];   d[3] = v - c[tp + 3];
+    d[4] = v - c[3];            d[5] = v - c[-tp + 3];      d[6] = v - c[-2 * tp + 2];  d[7] = v - c[-3 * tp + 1];
+    d[8] = v - c[-3 * tp];      d[9] = v - c[-3 * tp - 1];  d[10] = v - c[-2 * tp - 2]; d[11] = v - c[-tp - 3];
+    d[12] = v - c[-3];          d[13] = v - c[tp - 3];      d[14] = v - c[2 * tp - 2];  d[15] = v - c[3 * tp - 1];
     // sliding-window min / max over 9 contiguous entries of the circular array (log-step doubling)
-    int lo2[16], hi2[16], lo4[16], hi4[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
     int A = -1000, B = 1000;
+    if (dark) {     // arcs of pixels darker than the centre: A = max_k min(d[k..k+8])
+        int lo2[16], lo4[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-        A = max(A, lo9);
-        B = min(B, hi9);
+        for (int k = 0; k < 16; k++) lo2[k] = min(d[k], d[(k + 1) & 15]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) lo4[k] = min(lo2[k], lo2[(k + 2) & 15]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+            A = max(A, lo9);
+        }
+    }
+    if (bright) {   // arcs of brighter pixels: B = min_k max(d[k..k+8])
+        int hi2[16], hi4[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) hi2[k] = max(d[k], d[(k + 1) & 15]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) hi4[k] = max(hi2[k], hi2[(k + 2) & 15]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+            B = min(B, hi9);
+        }
     }
     const int s = max(A, -B) - 1;
     return s >= T ? s : 0;
 }
 
-__global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(OrbxFrameLayout L, int tile_pitch, int score_pitch,
-                                                                  int score_off)
+__global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLayout L, FastSmemCfg cfg)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_warp[FAST_THREADS / 32];
-    __shared__ int s_base;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int cell_id = blockIdx.x * FAST_WARPS + wid;
     const int frame = blockIdx.y;
-    const OrbxCell c = L.cells[blockIdx.x];
-    const OrbxLevelGeom g = L.lvl[c.level];
-    int* cell_count = L.cell_count + (size_t)frame * L.ncells + blockIdx.x;
+    if (cell_id >= L.ncells) return;                      // whole warp
+    const OrbxCell c = L.cells[cell_id];
+    int* cell_count = L.cell_count + (size_t)frame * L.ncells + cell_id;
     const int ew = c.ex1 - c.ex0, eh = c.ey1 - c.ey0;
-    if (ew <= 0 || eh <= 0) { if (tid == 0) *cell_count = 0; return; }
-    uint8_t* tile = smem;                 // (eh+6) x tile_pitch
-    uint8_t* score = smem + score_off;    // (eh+2) x score_pitch, zero frame
-    const int tw = ew + 6, th = eh + 6, tp = tile_pitch, sp = score_pitch;
-    const uint8_t* src = L.raw + (size_t)frame * L.frame_raw_bytes + g.raw_off +
-                         (size_t)(c.ey0 - 3 + ORBX_EDGE) * g.pitch + (c.ex0 - 3 + ORBX_XOFF);
-    for (int i = tid; i < tw * th; i += FAST_THREADS) {
-        const int ty = i / tw, tx = i - ty * tw;
-        tile[ty * tp + tx] = src[(size_t)ty * g.pitch + tx];
-    }
-    for (int i = tid; i < (eh + 2) * sp; i += FAST_THREADS) score[i] = 0;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
+    if (ew <= 0 || eh <= 0) { if (lane == 0) *cell_count = 0; return; }
+    const OrbxLevelGeom g = L.lvl[c.level];
+
+    uint8_t* wbase = smem + (size_t)wid * cfg.per_warp;
+    uint32_t* tile32 = reinterpret_cast<uint32_t*>(wbase + cfg.tile_off);
+    uint8_t* score = wbase + cfg.score_off;
+    unsigned short* list = reinterpret_cast<unsigned short*>(wbase + cfg.list_off);
+    const int tp = cfg.tpw * 4, sp = cfg.sp;
+
+    // ---- stage the tile rows [ey0-3, ey1+3) x [ex0-3, ex1+3) with aligned 32-bit loads
+    const int tw = ew + 6, th = eh + 6;
+    const uint8_t* p0 = L.raw + (size_t)frame * L.frame_raw_bytes + g.raw_off +
+                        (size_t)(c.ey0 - 3 + ORBX_EDGE) * g.pitch + (c.ex0 - 3 + ORBX_XOFF);
+    const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3);
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(p0 - sh);
+    const int nw = (sh + tw + 3) >> 2;                    // words per row
+    const int pitch_w = g.pitch >> 2;
+    for (int r = 0; r < th; r++)
+        for (int w = lane; w < nw; w += 32) tile32[r * cfg.tpw + w] = __ldg(pa + (size_t)r * pitch_w + w);
+    const uint8_t* tile = reinterpret_cast<const uint8_t*>(tile32) + sh;   // tile[ty*tp + tx]
+
     uint32_t* slot = L.slots + (size_t)frame * L.slot_total + c.slot_off;
-    const int npx = ew * eh;
     int total = 0;
     for (int pass = 0; pass < 2; pass++) {
         const int T = pass ? L.min_th : L.ini_th;
-        for (int i = tid; i < npx; i += FAST_THREADS) {
-            const int py = i / ew, px = i - py * ew;
-            score[(py + 1) * sp + px + 1] = (uint8_t)fast_score_T(tile + (py + 3) * tp + px + 3, tp, T);
+        // zero the score map (frame included)
+        {
+            uint32_t* s32 = reinterpret_cast<uint32_t*>(score);
+            const int nwords = ((eh + 2) * sp) >> 2;
+            for (int i = lane; i < nwords; i += 32) s32[i] = 0;
         }
-        __syncthreads();
-        // strict 3x3 NMS + ordered (row-major) compaction
-        for (int i0 = 0; i0 < npx; i0 += FAST_THREADS) {
-            const int i = i0 + tid;
+        __syncwarp();
+        // 1. quick test, row-major list of pixels worth scoring: entry = dark<<15 | bright<<14 | py<<7 | px
+        int cnt = 0;
+        for (int py = 0; py < eh; py++) {
+            const uint8_t* row = tile + (py + 3) * tp + 3;
+            for (int px0 = 0; px0 < ew; px0 += 32) {
+                const int px = px0 + lane;
+                int pass_q = 0, flags = 0;
+                if (px < ew) {
+                    const uint8_t* q = row + px;
+                    const int v = q[0];
+                    const int d0 = v - q[3 * tp], d4 = v - q[3], d8 = v - q[-3 * tp], d12 = v - q[-3];
+                    // every arc of 9 contiguous ring pixels holds at least two of the four compass pixels
+                    const int nd = (d0 > T) + (d4 > T) + (d8 > T) + (d12 > T);
+                    const int nb = (d0 < -T) + (d4 < -T) + (d8 < -T) + (d12 < -T);
+                    flags = (nd >= 2 ? 2 : 0) | (nb >= 2 ? 1 : 0);
+                    pass_q = flags != 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, pass_q);
+                if (pass_q) {
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1));
+                    if (pos < cfg.list_cap) list[pos] = (unsigned short)((flags << 14) | (py << 7) | px);
+                }
+                cnt += __popc(m);
+            }
+        }
+        cnt = min(cnt, cfg.list_cap);
+        __syncwarp();
+        // 2. exact score of the listed pixels
+        for (int k = lane; k < cnt; k += 32) {
+            const int e = list[k];
+            const int px = e & 127, py = (e >> 7) & 127;
+            const int s = fast_score_T(tile + (py + 3) * tp + px + 3, tp, T, (e >> 15) & 1, (e >> 14) & 1);
+            if (s) score[(py + 1) * sp + px + 1] = (uint8_t)s;
+        }
+        __syncwarp();
+        // 3. strict 3x3 NMS over the list (row-major) + ordered write
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int k = k0 + lane;
             int keep = 0, s = 0, px = 0, py = 0;
-            if (i < npx) {
-                py = i / ew; px = i - py * ew;
+            if (k < cnt) {
+                const int e = list[k];
+                px = e & 127; py = (e >> 7) & 127;
                 const uint8_t* q = score + (py + 1) * sp + px + 1;
                 s = q[0];
                 keep = s > 0 && s > q[-1] && s > q[1] && s > q[-sp - 1] && s > q[-sp] && s > q[-sp + 1] &&
                        s > q[sp - 1] && s > q[sp] && s > q[sp + 1];
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_warp[wid] = __popc(m);
-            __syncthreads();
-            int off = s_base;
-            for (int w = 0; w < wid; w++) off += s_warp[w];
             if (keep) {
-                off += __popc(m & ((1u << lane) - 1));
+                const int off = total + __popc(m & ((1u << lane) - 1));
                 if (off < c.slot_cap)
                     slot[off] = ((uint32_t)s << 24) | ((uint32_t)(c.ey0 + py - ORBX_MINB) << 12) | (uint32_t)(c.ex0 + px - ORBX_MINB);
             }
-            __syncthreads();
-            if (tid == 0) {
-                int t = 0;
-                for (int w = 0; w < FAST_THREADS / 32; w++) t += s_warp[w];
-                s_base += t;
-            }
-            __syncthreads();
+            total += __popc(m);
         }
-        total = s_base;
         if (total > 0) break;
+        __syncwarp();
     }
-    if (tid == 0) *cell_count = total < c.slot_cap ? total : c.slot_cap;
+    if (lane == 0) *cell_count = total < c.slot_cap ? total : c.slot_cap;
 }
 
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st)
 {
-    const int tp = (max_tile_w + 3) & ~3;
-    const int sp = (max_tile_w - 6 + 2 + 3) & ~3;
-    const int score_off = (tp * max_tile_h + 15) & ~15;
-    const size_t smem = (size_t)score_off + (size_t)sp * (max_tile_h - 6 + 2);
+    FastSmemCfg cfg;
+    cfg.tpw = (3 + max_tile_w + 3) / 4 + 1;
+    cfg.th = max_tile_h;
+    cfg.sp = (max_tile_w - 6 + 2 + 3) & ~3;
+    cfg.srows = max_tile_h - 6 + 2;
+    cfg.list_cap = (max_tile_w - 6) * (max_tile_h - 6);
+    cfg.tile_off = 0;
+    cfg.score_off = (cfg.tpw * 4 * cfg.th + 15) & ~15;
+    cfg.list_off = (cfg.score_off + cfg.sp * cfg.srows + 15) & ~15;
+    cfg.per_warp = (cfg.list_off + 2 * cfg.list_cap + 15) & ~15;
+    const size_t smem = (size_t)cfg.per_warp * FAST_WARPS;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    dim3 grid(L.ncells, nframes);
-    fast_cells_kernel<<<grid, FAST_THREADS, smem, st>>>(L, tp, sp, score_off);
+    dim3 grid((L.ncells + FAST_WARPS - 1) / FAST_WARPS, nframes);
+    fast_cells_kernel<<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
 }
