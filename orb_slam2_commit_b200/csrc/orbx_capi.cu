@@ -45,6 +45,8 @@ struct orbx_extractor {
     uint8_t* d_desc = nullptr;
     int* d_nkp = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};   // host-path double buffering (copy/compute overlap)
+    int pyr_base = 0;                             // first working-set frame of the last pipeline run
     int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
     bool constants_ready = false;
     bool timing = false;
@@ -127,6 +129,7 @@ extern "C" void orbx_destroy(orbx_extractor* h)
     for (int r = 0; r < orbx_extractor::RING; r++)
         for (int i = 0; i < 5; i++) if (h->ev[r][i]) cudaEventDestroy(h->ev[r][i]);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (int j = 0; j < 2; j++) if (h->slot_stream[j]) cudaStreamDestroy(h->slot_stream[j]);
     cudaGetLastError();
     delete h;
 }
@@ -292,23 +295,37 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
 extern "C" int orbx_max_keypoints(const orbx_extractor* h) { return (h && h->W) ? h->L.kp_cap_total : 0; }
 
 // the whole device pipeline for n frames that already sit in HBM
+// `base` = first frame of the reserved working set to use (the host path runs two chunks concurrently on two
+// streams, each in its own half of the working set)
 static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stride, size_t frame_pitch,
-                        OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st)
+                        OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st, int base = 0)
 {
+    OrbxFrameLayout Lb = h->L;
+    if (base) {
+        Lb.raw += (size_t)base * Lb.frame_raw_bytes;
+        Lb.slots += (size_t)base * Lb.slot_total;
+        Lb.cell_count += (size_t)base * Lb.ncells;
+        Lb.cand += (size_t)base * Lb.cand_total;
+        Lb.cand_node += (size_t)base * Lb.cand_total;
+        Lb.cand_count += (size_t)base * Lb.nlevels;
+        Lb.lvl_kp += (size_t)base * Lb.kp_cap_total;
+        Lb.lvl_kp_count += (size_t)base * Lb.nlevels;
+    }
     const bool tm = h->timing;
     cudaEvent_t* ev = h->ev[h->runs % orbx_extractor::RING];
     if (tm) cudaEventRecord(ev[0], st);
-    orbx_launch_pyramid(h->L, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st);
+    orbx_launch_pyramid(Lb, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st);
     if (tm) cudaEventRecord(ev[1], st);
-    orbx_launch_fast(h->L, h->max_tile_w, h->max_tile_h, n, st);
+    orbx_launch_fast(Lb, h->max_tile_w, h->max_tile_h, n, st);
     if (tm) cudaEventRecord(ev[2], st);
-    orbx_launch_quadtree(h->L, n, st);
+    orbx_launch_quadtree(Lb, n, st);
     if (tm) cudaEventRecord(ev[3], st);
-    orbx_launch_describe(h->L, n, d_kps, d_desc, cap, d_nkp, st);
+    orbx_launch_describe(Lb, n, d_kps, d_desc, cap, d_nkp, st);
     if (tm) cudaEventRecord(ev[4], st);
     if (tm) h->runs++;
     CK(cudaGetLastError());
     h->last_frames = n;
+    h->pyr_base = base;
     return ORBX_OK;
 }
 
@@ -379,41 +396,55 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* image
     const int B = h->max_batch, kc = h->L.kp_cap_total;
     const size_t fbytes = (size_t)width * height;
     int status = ORBX_OK;
-    for (int f0 = 0; f0 < n; f0 += B) {
-        const int m = std::min(B, n - f0);
+    // Two chunks in flight on two streams, each in its own half of the reserved working set: the H2D copy of chunk
+    // k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k. A slot's stream serialises its own
+    // H2D -> kernels -> D2H, so reusing a slot needs no extra event.
+    const int chunk = B >= 8 ? std::max(1, std::min(B / 2, 128)) : B;
+    const int nslots = B >= 8 ? 2 : 1;
+    for (int j = 0; j < nslots; j++)
+        if (!h->slot_stream[j]) CK(cudaStreamCreateWithFlags(&h->slot_stream[j], cudaStreamNonBlocking));
+    CK(cudaStreamSynchronize(h->stream));
+    int k = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, k++) {
+        const int m = std::min(chunk, n - f0);
+        const int slot = k % nslots, base = slot * chunk;
+        cudaStream_t st = h->slot_stream[slot];
+        uint8_t* d_in = h->d_in + (size_t)base * fbytes;
+        OrbxKp28* d_kps = h->d_kps + (size_t)base * kc;
+        uint8_t* d_desc = h->d_desc + (size_t)base * kc * 32;
+        int* d_nkp = h->d_nkp + base;
         // frames that are contiguous in host memory go up in one copy, otherwise one (strided) copy per frame
         bool contiguous = stride == width;
         for (int i = 0; i < m && contiguous; i++) {
             if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
             contiguous = images[f0 + i] == images[f0] + (size_t)i * fbytes;
         }
-        if (contiguous) CK(cudaMemcpyAsync(h->d_in, images[f0], (size_t)m * fbytes, cudaMemcpyHostToDevice, h->stream));
+        if (contiguous) CK(cudaMemcpyAsync(d_in, images[f0], (size_t)m * fbytes, cudaMemcpyHostToDevice, st));
         else
             for (int i = 0; i < m; i++) {
                 if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
-                CK(cudaMemcpy2DAsync(h->d_in + (size_t)i * fbytes, width, images[f0 + i], stride, width, height,
-                                     cudaMemcpyHostToDevice, h->stream));
+                CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, width, images[f0 + i], stride, width, height,
+                                     cudaMemcpyHostToDevice, st));
             }
-        int rc = run_pipeline(h, h->d_in, m, width, fbytes, h->d_kps, h->d_desc, kc, h->d_nkp, h->stream);
+        int rc = run_pipeline(h, d_in, m, width, fbytes, d_kps, d_desc, kc, d_nkp, st, base);
         if (rc != ORBX_OK) return rc;
-        CK(cudaMemcpyAsync(nkp + f0, h->d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(nkp + f0, d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (cap == kc) {
             // caller sized its buffers with orbx_max_keypoints(): results land in place with two bulk copies
-            CK(cudaMemcpyAsync(keypoints + (size_t)f0 * cap, h->d_kps, (size_t)m * kc * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaMemcpyAsync(descriptors + (size_t)f0 * cap * 32, h->d_desc, (size_t)m * kc * 32, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaMemcpyAsync(keypoints + (size_t)f0 * cap, d_kps, (size_t)m * kc * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(descriptors + (size_t)f0 * cap * 32, d_desc, (size_t)m * kc * 32, cudaMemcpyDeviceToHost, st));
         } else {
-            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaStreamSynchronize(st));
             for (int i = 0; i < m; i++) {
                 const int c = std::min(nkp[f0 + i], cap);
                 if (c <= 0) continue;
-                CK(cudaMemcpyAsync(keypoints + (size_t)(f0 + i) * cap, h->d_kps + (size_t)i * kc, (size_t)c * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaMemcpyAsync(descriptors + (size_t)(f0 + i) * cap * 32, h->d_desc + (size_t)i * kc * 32, (size_t)c * 32, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpyAsync(keypoints + (size_t)(f0 + i) * cap, d_kps + (size_t)i * kc, (size_t)c * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(descriptors + (size_t)(f0 + i) * cap * 32, d_desc + (size_t)i * kc * 32, (size_t)c * 32, cudaMemcpyDeviceToHost, st));
             }
-            CK(cudaStreamSynchronize(h->stream));
         }
-        for (int i = 0; i < m; i++) if (nkp[f0 + i] > cap) status = ORBX_ERR_CAPACITY;
     }
+    for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(h->slot_stream[j]));
+    for (int i = 0; i < n; i++) if (nkp[i] > cap) status = ORBX_ERR_CAPACITY;
     if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
     return status;
 }
@@ -442,7 +473,7 @@ extern "C" int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level
     if (!h || !h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");
     if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame/level out of range");
     const OrbxLevelGeom& g = h->lvl[level];
-    if (d_payload) *d_payload = h->L.raw + (size_t)frame * h->L.frame_raw_bytes + g.raw_off + (size_t)ORBX_EDGE * g.pitch + ORBX_XOFF;
+    if (d_payload) *d_payload = h->L.raw + (size_t)(h->pyr_base + frame) * h->L.frame_raw_bytes + g.raw_off + (size_t)ORBX_EDGE * g.pitch + ORBX_XOFF;
     if (pitch) *pitch = g.pitch;
     return ORBX_OK;
 }
@@ -467,7 +498,7 @@ extern "C" int orbx_debug_level_counts(orbx_extractor* h, int frame, int32_t* co
     if (frame < 0 || frame >= h->last_frames || !counts) return fail(ORBX_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(counts, h->L.lvl_kp_count + (size_t)frame * h->nlevels, h->nlevels * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(counts, h->L.lvl_kp_count + (size_t)(h->pyr_base + frame) * h->nlevels, h->nlevels * sizeof(int), cudaMemcpyDeviceToHost));
     return ORBX_OK;
 }
 
@@ -478,12 +509,12 @@ extern "C" int orbx_debug_candidates(orbx_extractor* h, int frame, int level, Or
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     int cnt = 0;
-    CK(cudaMemcpy(&cnt, h->L.cand_count + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&cnt, h->L.cand_count + (size_t)(h->pyr_base + frame) * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     *n = cnt;
     const int m = std::min(cnt, cap);
     if (m > 0 && out) {
         std::vector<uint32_t> tmp(m);
-        CK(cudaMemcpy(tmp.data(), h->L.cand + (size_t)frame * h->L.cand_total + h->lvl[level].cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(tmp.data(), h->L.cand + (size_t)(h->pyr_base + frame) * h->L.cand_total + h->lvl[level].cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
         for (int i = 0; i < m; i++) {
             OrbxKeyPoint k;
             k.x = (float)(tmp[i] & 0xfff); k.y = (float)((tmp[i] >> 12) & 0xfff);

@@ -90,8 +90,23 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
     const uint32_t* pa = reinterpret_cast<const uint32_t*>(p0 - sh);
     const int nw = (sh + tw + 3) >> 2;                    // words per row
     const int pitch_w = g.pitch >> 2;
-    for (int r = 0; r < th; r++)
-        for (int w = lane; w < nw; w += 32) tile32[r * cfg.tpw + w] = __ldg(pa + (size_t)r * pitch_w + w);
+    {
+        // flattened (row, word) index, four independent loads in flight per lane; i / nw by reciprocal multiply
+        // (exact for i < 2048, nw < 40 with a 20-bit reciprocal: checked exhaustively on the host)
+        const int nwords = th * nw, inv = (1 << 20) / nw + 1;   // th*nw < 2048
+        for (int i0 = lane; i0 < nwords; i0 += 128) {
+            uint32_t v[4]; int dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + 32 * u;
+                const int r = (int)(((unsigned)i * (unsigned)inv) >> 20), w = i - r * nw;
+                dst[u] = r * cfg.tpw + w;
+                v[u] = i < nwords ? __ldg(pa + r * pitch_w + w) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (i0 + 32 * u < nwords) tile32[dst[u]] = v[u];
+        }
+    }
     const uint8_t* tile = reinterpret_cast<const uint8_t*>(tile32) + sh;   // tile[ty*tp + tx]
 
     uint32_t* slot = L.slots + (size_t)frame * L.slot_total + c.slot_off;
