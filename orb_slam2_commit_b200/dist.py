@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): frame sharding needs no collective; brute-force
+matching shards the TRAIN set and exchanges one packed 64-bit word per query.
+
+packed = (dist1 << 48) | (dist2 << 32) | uint32(idx1)   — the layout of orbx_hamming_top2_device.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n: int, world: int, rank: int):
+    """Contiguous shard [start, stop) of n items; contiguity keeps 'first index wins' == lowest global index."""
+    per = (n + world - 1) // world
+    start = min(n, rank * per)
+    return start, min(n, start + per)
+
+
+def frames_for_rank(n_frames: int, world: int, rank: int):
+    """Frames (or stereo pairs) are independent units: frame f -> rank f mod world."""
+    return list(range(rank, n_frames, world))
+
+
+def pack_top2(idx1, dist1, dist2) -> np.ndarray:
+    idx = np.asarray(idx1).astype(np.int64) & 0xFFFFFFFF
+    return ((np.asarray(dist1).astype(np.uint64) << np.uint64(48)) | (np.asarray(dist2).astype(np.uint64) << np.uint64(32))
+            | idx.astype(np.uint64))
+
+
+def unpack_top2(packed):
+    p = np.asarray(packed).astype(np.uint64)
+    d1 = (p >> np.uint64(48)).astype(np.int32)
+    d2 = ((p >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.int32)
+    idx = (p & np.uint64(0xFFFFFFFF)).astype(np.uint32).astype(np.int64)
+    idx = np.where(d1 >= 256, -1, idx).astype(np.int32)
+    return idx, d1, d2
+
+
+def all_gather_packed(packed, group=None):
+    """All-gather one packed word per query from every rank -> tensor [world, nq] (int64 view of the u64 words).
+    Works on CUDA tensors over NCCL and on CPU tensors over gloo."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    flat = packed.contiguous().view(-1)
+    out = torch.empty(world * flat.numel(), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view(world, flat.numel())
+
+
+def hamming_top2_sharded(d_query, d_train_shard, index_base: int, group=None):
+    """Config 4: every rank holds a contiguous shard of the train set (global index of its first row = index_base) and
+    the full query set. Local top-2 on the GPU, NCCL all-gather of 8 bytes per query per rank, merge kernel.
+    Returns CUDA int32 tensors (idx1, dist1, dist2), identical on every rank."""
+    import torch
+    from . import api
+    L = api.lib()
+    nq, nt = d_query.shape[0], d_train_shard.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    packed = torch.empty(nq, dtype=torch.int64, device=d_query.device)
+    api._ck(L.orbx_hamming_init_device(packed.data_ptr(), nq, st))
+    api._ck(L.orbx_hamming_top2_device(d_query.data_ptr(), nq, d_train_shard.data_ptr() if nt else 0, nt, index_base,
+                                       packed.data_ptr(), st))
+    parts = all_gather_packed(packed, group)
+    out = torch.empty((3, nq), dtype=torch.int32, device=d_query.device)
+    api._ck(L.orbx_hamming_merge_device(parts.data_ptr(), parts.shape[0], nq, out[0].data_ptr(), out[1].data_ptr(),
+                                        out[2].data_ptr(), st))
+    return out[0], out[1], out[2]

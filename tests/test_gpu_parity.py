@@ -209,3 +209,60 @@ def test_stereo_hamming_matches_oracle():
     oi, od = ob.stereo_hamming(kl, dl, kr, dr, c["height"], sf, 0.0, float(maxD))
     assert np.array_equal(bi, oi) and np.array_equal(bd, od)
     assert np.count_nonzero(bd < 75) > 200      # the synthetic pair does produce stereo matches
+
+
+def test_hamming_shards_merge_on_device():
+    """top-2 of a union == merge of per-shard top-2s. Emulates 3 ranks on ONE GPU: (a) every shard merged
+    into the same packed buffer by the kernel's CAS epilogue, (b) separate packed parts + the merge kernel that follows
+    the NCCL all-gather. Both must equal the single-shard result and the oracle."""
+    import torch
+    from orb_slam2_commit_b200 import api, dist as od
+    L = api.lib()
+    train, query = synth.synth_descriptors(90_001, 300, seed=9)
+    dq = torch.from_numpy(query).cuda(); dt = torch.from_numpy(train).cuda()
+    nq = len(query); st = torch.cuda.current_stream().cuda_stream
+    bounds = [od.shard_range(len(train), 3, r) for r in range(3)]
+    acc = torch.empty(nq, dtype=torch.int64, device="cuda")
+    api._ck(L.orbx_hamming_init_device(acc.data_ptr(), nq, st))
+    parts = torch.empty((3, nq), dtype=torch.int64, device="cuda")
+    for r, (a, b) in enumerate(bounds):
+        shard = dt[a:b].contiguous()
+        api._ck(L.orbx_hamming_top2_device(dq.data_ptr(), nq, shard.data_ptr(), b - a, a, acc.data_ptr(), st))
+        api._ck(L.orbx_hamming_init_device(parts[r].data_ptr(), nq, st))
+        api._ck(L.orbx_hamming_top2_device(dq.data_ptr(), nq, shard.data_ptr(), b - a, a, parts[r].data_ptr(), st))
+    out = torch.empty((2, 3, nq), dtype=torch.int32, device="cuda")
+    api._ck(L.orbx_hamming_merge_device(acc.data_ptr(), 1, nq, out[0, 0].data_ptr(), out[0, 1].data_ptr(), out[0, 2].data_ptr(), st))
+    api._ck(L.orbx_hamming_merge_device(parts.data_ptr(), 3, nq, out[1, 0].data_ptr(), out[1, 1].data_ptr(), out[1, 2].data_ptr(), st))
+    torch.cuda.synchronize()
+    want = ob.hamming_top2(query, train, nthreads=8)
+    for v in range(2):
+        got = out[v].cpu().numpy()
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), v
+    # the packed words themselves decode with the host helper used by the gloo tests
+    i, d1, d2 = od.unpack_top2(acc.cpu().numpy().view(np.uint64))
+    assert np.array_equal(i, want[0]) and np.array_equal(d1, want[1]) and np.array_equal(d2, want[2])
+
+
+def test_device_resident_api_matches_host_api():
+    """orbx_extract_device (frames and results stay in HBM, caller's stream) == orbx_extract_batch."""
+    import torch
+    from orb_slam2_commit_b200 import api
+    c = _cfg("tum1")
+    imgs = np.stack([synth.synth_image(c["width"], c["height"], 40 + i) for i in range(5)])
+    ex = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    cap = ex.reserve(c["width"], c["height"], 5)
+    d_img = torch.from_numpy(imgs).cuda()
+    d_kps = torch.zeros((5, cap, 28), dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros((5, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(5, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ex.extract_device(d_img.data_ptr(), 5, c["width"], c["height"], c["width"], c["width"] * c["height"],
+                          d_kps.data_ptr(), cap, d_n.data_ptr(), d_desc.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    kb, db = ex.extract_batch(list(imgs))
+    n = d_n.cpu().numpy()
+    for i in range(5):
+        k = d_kps[i, :n[i]].cpu().numpy().view(api.KP_DTYPE).reshape(-1)
+        assert k.tobytes() == kb[i].tobytes()
+        assert np.array_equal(d_desc[i, :n[i]].cpu().numpy(), db[i])

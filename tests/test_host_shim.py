@@ -1,0 +1,51 @@
+"""CPU-only: the C++ host shim that mirrors the reference class (orb_slam2_commit_b200/host/ORBextractor.{h,cc})
+compiles against a minimal OpenCV stand-in, links to liborbx.so, and keeps the reference's getter values and its
+silent-return-on-empty-image behaviour. (Compute needs a GPU and is covered by tests/test_gpu_parity.py.)"""
+import os
+import subprocess
+import textwrap
+
+import __graft_entry__ as graft
+from orb_slam2_commit_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "orb_slam2_commit_b200", "host")
+
+MAIN = textwrap.dedent(r"""
+    #include "ORBextractor.h"
+    #include "HammingTop2.h"
+    #include <cstdio>
+    int main() {
+        ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 20, 7);
+        std::vector<float> sf = ex.GetScaleFactors(), inv = ex.GetInverseScaleFactors();
+        std::vector<float> s2 = ex.GetScaleSigmaSquares(), is2 = ex.GetInverseScaleSigmaSquares();
+        std::printf("%d %.9g %.9g %.9g %.9g %.9g %zu\n", ex.GetLevels(), ex.GetScaleFactor(), sf[7], inv[7], s2[7], is2[7],
+                    ex.mvImagePyramid.size());
+        std::vector<cv::KeyPoint> kps(3);
+        cv::Mat empty, desc;
+        ex(empty, cv::Mat(), kps, desc);                 // ORBextractor.cc:1141: silent return, outputs untouched
+        std::printf("%zu %d\n", kps.size(), (int)desc.empty());
+        return 0;
+    }
+""")
+
+
+def test_shim_compiles_links_and_matches_getters(tmp_path):
+    graft.build()
+    src = tmp_path / "main.cc"
+    src.write_text(MAIN)
+    exe = tmp_path / "shim_test"
+    libdir = os.path.dirname(api.library_path())
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", HOST, "-I", os.path.join(HOST, "cvmini"),
+                           str(src), os.path.join(HOST, "ORBextractor.cc"), "-L", libdir, "-lorbx",
+                           f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    f = out[0].split()
+    assert f[0] == "8" and f[-1] == "8"
+    import numpy as np
+    from oracle import binding as ob
+    t = ob.Extractor(1000, 1.2, 8, 20, 7).tables()
+    assert np.float32(float(f[1])) == np.float32(1.2)
+    assert np.float32(float(f[2])) == t["scale_factors"][7] and np.float32(float(f[3])) == t["inv_scale_factors"][7]
+    assert np.float32(float(f[4])) == t["sigma2"][7] and np.float32(float(f[5])) == t["inv_sigma2"][7]
+    assert out[1].split() == ["3", "1"]
