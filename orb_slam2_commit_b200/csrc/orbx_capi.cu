@@ -318,7 +318,8 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(Lb, h->max_tile_w, h->max_tile_h, n, st);
     if (tm) cudaEventRecord(ev[2], st);
-    orbx_launch_quadtree(Lb, n, st);
+    // small frames: 256-thread CTAs so that several (level, frame) trees share an SM and hide each other's barriers
+    orbx_launch_quadtree(Lb, n, (size_t)h->W * h->H <= (size_t)1 << 20 ? 256 : 1024, st);
     if (tm) cudaEventRecord(ev[3], st);
     orbx_launch_describe(Lb, n, d_kps, d_desc, cap, d_nkp, st);
     if (tm) cudaEventRecord(ev[4], st);

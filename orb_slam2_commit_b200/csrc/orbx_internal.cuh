@@ -77,7 +77,7 @@ struct OrbxKp28 { float x, y, size, angle, response; int octave, class_id; };
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
                          int stride, size_t frame_pitch, int nframes, cudaStream_t st);
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
-void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, cudaStream_t st);
+void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);
 void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
                           int* d_nkp, cudaStream_t st);
 void orbx_upload_constants();  // pattern + umax tables

@@ -17,7 +17,7 @@
 // Finally every surviving node emits its best keypoint: max response, first in list order on ties (:796-812).
 #include "orbx_internal.cuh"
 
-#define QT ORBX_QT_THREADS
+#define QT_MAX ORBX_QT_THREADS   // the kernel runs with blockDim.x = 256 (small frames) or 1024 (large frames)
 
 struct QtBounds { short x0, x1, y0, y1; };
 
@@ -32,6 +32,7 @@ __device__ __forceinline__ int qt_quadrant(const QtBounds b, const int x, const 
 __device__ int qt_scan(int* vals, const int n, int* s_w)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int QT = blockDim.x, nwarps = QT >> 5;
     int carry = 0;
     for (int base = 0; base < n; base += QT) {
         const int i = base + tid;
@@ -42,7 +43,7 @@ __device__ int qt_scan(int* vals, const int n, int* s_w)
         if (lane == 31) s_w[wid] = x;
         __syncthreads();
         if (wid == 0) {
-            const int t = s_w[lane];
+            const int t = lane < nwarps ? s_w[lane] : 0;
             int z = t;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
@@ -64,10 +65,11 @@ __device__ __forceinline__ void qt_count(int* counters, const int key, const boo
     if (active && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&counters[key], __popc(peers));
 }
 
-__global__ void __launch_bounds__(QT, 1) quadtree_kernel(OrbxFrameLayout L)
+__global__ void __launch_bounds__(QT_MAX, 1) quadtree_kernel(OrbxFrameLayout L)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x;
+    const int QT = blockDim.x, nwarps = QT >> 5;
     const int level = blockIdx.x, frame = blockIdx.y;
     const OrbxLevelGeom g = L.lvl[level];
     const int C = L.qt_cap, N = g.quota;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(QT, 1) quadtree_kernel(OrbxFrameLayout L)
             if (lane == 31) s_w[wid] = x;
             __syncthreads();
             if (wid == 0) {
-                const int t = s_w[lane];
+                const int t = lane < nwarps ? s_w[lane] : 0;
                 int z = t;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
@@ -337,7 +339,7 @@ static size_t qt_smem_bytes(int C)
     return (b + 15) & ~(size_t)15;
 }
 
-void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, cudaStream_t st)
+void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st)
 {
     const size_t smem = qt_smem_bytes(L.qt_cap);
     static size_t configured = 0;
@@ -346,5 +348,5 @@ void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, cudaStream_t st
         configured = smem;
     }
     dim3 grid(L.nlevels, nframes);
-    quadtree_kernel<<<grid, QT, smem, st>>>(L);
+    quadtree_kernel<<<grid, threads, smem, st>>>(L);
 }
