@@ -20,7 +20,7 @@
 #define PWORDS 12        // 32-bit words per staged patch row (48 bytes)
 #define HBP 40           // pitch (u16) of the horizontally blurred patch, 37 valid columns (+3 scratch)
 
-__constant__ signed char c_pattern[1024];
+__device__ uint32_t g_pattern32[256];    // the 512 (x,y) int8 sample points, four bytes per word
 __constant__ int c_umax[16];
 
 static const signed char h_pattern[1024] = {
@@ -31,7 +31,7 @@ void orbx_upload_constants()
 {
     // IC_Angle disc half-widths (ORBextractor.cc:473-489)
     static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern));
+    cudaMemcpyToSymbol(g_pattern32, h_pattern, sizeof(h_pattern));
     cudaMemcpyToSymbol(c_umax, umax, sizeof(umax));
 }
 
@@ -110,10 +110,11 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
 {
     __shared__ uint32_t s_raw[DESC_WARPS][PW * PWORDS + 4];   // +4: the last row's aligned window may over-read
     __shared__ unsigned short s_hb[DESC_WARPS][PW * HBP];
-    __shared__ signed char s_pat[1024];
+    __shared__ uint32_t s_pat32[256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < 1024; i += DESC_WARPS * 32) s_pat[i] = c_pattern[i];
+    for (int i = tid; i < 256; i += DESC_WARPS * 32) s_pat32[i] = g_pattern32[i];
     __syncthreads();
+    const signed char* s_pat = reinterpret_cast<const signed char*>(s_pat32);
     const int frame = blockIdx.y;
     const int ord = blockIdx.x * DESC_WARPS + wid;      // keypoint ordinal inside the frame (level-major)
     const int* cnt = L.lvl_kp_count + (size_t)frame * L.nlevels;
@@ -135,9 +136,25 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3);
     const uint8_t* pa = p0 - sh;
     uint32_t* raw32 = s_raw[wid];
-    for (int i = lane; i < PW * PWORDS; i += 32) {
-        const int r = i / PWORDS, c = i - r * PWORDS;
-        raw32[i] = __ldg(reinterpret_cast<const uint32_t*>(pa + (size_t)r * g.pitch) + c);
+    {
+        // 516 words, 32 per step; loads are issued in batches so that several are in flight per lane
+        const uint32_t* pa32 = reinterpret_cast<const uint32_t*>(pa);
+        const int pitch_w = g.pitch >> 2;
+#pragma unroll
+        for (int b0 = 0; b0 < PW * PWORDS; b0 += 32 * 6) {
+            uint32_t v[6];
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int i = b0 + 32 * u + lane;
+                const int r = i / PWORDS, c = i - r * PWORDS;
+                v[u] = i < PW * PWORDS ? __ldg(pa32 + r * pitch_w + c) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int i = b0 + 32 * u + lane;
+                if (i < PW * PWORDS) raw32[i] = v[u];
+            }
+        }
     }
     __syncwarp();
     const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32) + sh;   // raw8[r*48 + c], c in [0,43)

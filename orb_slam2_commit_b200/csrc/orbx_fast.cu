@@ -5,8 +5,9 @@
 // ONE WARP PER 30-px CELL, all levels and all frames of the batch in one launch; no block-level barrier anywhere.
 // The warp stages the cell tile (+3-px ring) in shared memory with aligned 32-bit loads, then
 //   1. quick test (four compass pixels) on every pixel; survivors are appended, in row-major order, to a per-warp
-//      list with ballot + popc (dense work for the expensive step, no divergence waste);
-//   2. exact corner score for the listed pixels only, written to a zero-initialised u8 score map:
+//      list with ballot + popc (dense work for the expensive steps, no divergence waste);
+//   1b. exact FAST-9 corner test (16-bit ring masks) on the listed pixels, list re-compacted to true corners;
+//   2. exact corner score for the corners only, written to a zero-initialised u8 score map:
 //        score(p) = max over the 16 arcs of 9 contiguous ring pixels of max(min d, -max d) - 1,  d_k = I(p) - I(ring_k)
 //        p is a corner at threshold T  <=>  score(p) >= T      (cv::cornerScore<16>; independent of T)
 //   3. cv::FAST's strict 3x3 non-max suppression over the list (still row-major), survivors written to the cell's
@@ -120,46 +121,75 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
             for (int i = lane; i < nwords; i += 32) s32[i] = 0;
         }
         __syncwarp();
-        // 1. quick test, row-major list of pixels worth scoring: entry = dark<<15 | bright<<14 | py<<7 | px
+        // 1. quick test on every pixel. Every arc of 9 contiguous ring pixels holds two ADJACENT compass pixels
+        //    (ring 0,4,8,12), so a dark arc needs max over adjacent pairs of min(d_a, d_b) > T and a bright arc
+        //    needs min over adjacent pairs of max(d_a, d_b) < -T. Row-major list entry = py<<7 | px.
         int cnt = 0;
         for (int py = 0; py < eh; py++) {
             const uint8_t* row = tile + (py + 3) * tp + 3;
             for (int px0 = 0; px0 < ew; px0 += 32) {
                 const int px = px0 + lane;
-                int pass_q = 0, flags = 0;
+                int pass_q = 0;
                 if (px < ew) {
                     const uint8_t* q = row + px;
                     const int v = q[0];
                     const int d0 = v - q[3 * tp], d4 = v - q[3], d8 = v - q[-3 * tp], d12 = v - q[-3];
-                    // every arc of 9 contiguous ring pixels holds at least two of the four compass pixels
-                    const int nd = (d0 > T) + (d4 > T) + (d8 > T) + (d12 > T);
-                    const int nb = (d0 < -T) + (d4 < -T) + (d8 < -T) + (d12 < -T);
-                    flags = (nd >= 2 ? 2 : 0) | (nb >= 2 ? 1 : 0);
-                    pass_q = flags != 0;
+                    const int dk = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));
+                    const int br = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));
+                    pass_q = (dk > T) | (br < -T);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, pass_q);
                 if (pass_q) {
                     const int pos = cnt + __popc(m & ((1u << lane) - 1));
-                    if (pos < cfg.list_cap) list[pos] = (unsigned short)((flags << 14) | (py << 7) | px);
+                    if (pos < cfg.list_cap) list[pos] = (unsigned short)((py << 7) | px);
                 }
                 cnt += __popc(m);
             }
         }
         cnt = min(cnt, cfg.list_cap);
         __syncwarp();
-        // 2. exact score of the listed pixels
-        for (int k = lane; k < cnt; k += 32) {
+        // 2. exact FAST-9 corner test of the listed pixels (16-bit ring masks, 9 contiguous ones in the circular
+        //    mask), re-compacted in place: entry = dark<<15 | bright<<14 | py<<7 | px. In-place is safe: a chunk of
+        //    32 entries is read before it is written and the write position never passes the read position.
+        int ncorner = 0;
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int k = k0 + lane;
+            int e = 0, fl = 0;
+            if (k < cnt) {
+                e = list[k];
+                const uint8_t* c = tile + (((e >> 7) & 127) + 3) * tp + (e & 127) + 3;
+                const int lo = (int)c[0] - T, hi = (int)c[0] + T;   // dark: ring < lo ; bright: ring > hi
+                unsigned md = 0, mb = 0;
+#define RING_BIT(kk, off) { const int r = c[off]; md |= (unsigned)(r < lo) << kk; mb |= (unsigned)(r > hi) << kk; }
+                RING_BIT(0, 3 * tp)       RING_BIT(1, 3 * tp + 1)   RING_BIT(2, 2 * tp + 2)   RING_BIT(3, tp + 3)
+                RING_BIT(4, 3)            RING_BIT(5, -tp + 3)      RING_BIT(6, -2 * tp + 2)  RING_BIT(7, -3 * tp + 1)
+                RING_BIT(8, -3 * tp)      RING_BIT(9, -3 * tp - 1)  RING_BIT(10, -2 * tp - 2) RING_BIT(11, -tp - 3)
+                RING_BIT(12, -3)          RING_BIT(13, tp - 3)      RING_BIT(14, 2 * tp - 2)  RING_BIT(15, 3 * tp - 1)
+#undef RING_BIT
+                md |= md << 16; mb |= mb << 16;
+                md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;   // bit i set <=> ring i..i+8 all dark
+                mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
+                fl = ((md & 0xffffu) ? 2 : 0) | ((mb & 0xffffu) ? 1 : 0);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, fl != 0);
+            __syncwarp();
+            if (fl) list[ncorner + __popc(m & ((1u << lane) - 1))] = (unsigned short)((fl << 14) | (e & 0x3fff));
+            ncorner += __popc(m);
+        }
+        __syncwarp();
+        // 3. exact score of the corners
+        for (int k = lane; k < ncorner; k += 32) {
             const int e = list[k];
             const int px = e & 127, py = (e >> 7) & 127;
             const int s = fast_score_T(tile + (py + 3) * tp + px + 3, tp, T, (e >> 15) & 1, (e >> 14) & 1);
             if (s) score[(py + 1) * sp + px + 1] = (uint8_t)s;
         }
         __syncwarp();
-        // 3. strict 3x3 NMS over the list (row-major) + ordered write
-        for (int k0 = 0; k0 < cnt; k0 += 32) {
+        // 4. strict 3x3 NMS over the corners (row-major) + ordered write
+        for (int k0 = 0; k0 < ncorner; k0 += 32) {
             const int k = k0 + lane;
             int keep = 0, s = 0, px = 0, py = 0;
-            if (k < cnt) {
+            if (k < ncorner) {
                 const int e = list[k];
                 px = e & 127; py = (e >> 7) & 127;
                 const uint8_t* q = score + (py + 1) * sp + px + 1;

@@ -39,36 +39,45 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_kernel(OrbxFrameLa
     *reinterpret_cast<uint32_t*>(dst) = out;
 }
 
-// level l > 0 from level l-1
+// level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows: the four
+// x-taps are fetched once and up to 16*PYR_RPT independent source-pixel loads are in flight per thread.
+#define PYR_RPT 2
 __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_kernel(OrbxFrameLayout L, int level)
 {
     const OrbxLevelGeom g = L.lvl[level];
     const OrbxLevelGeom s = L.lvl[level - 1];
     const int t = blockIdx.x * PYR_TX + threadIdx.x;
-    const int rb = blockIdx.y * PYR_TY + threadIdx.y;
+    const int rb0 = (blockIdx.y * PYR_TY + threadIdx.y) * PYR_RPT;
     const int cb = 12 + 4 * t;
-    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb >= g.h + 2 * ORBX_EDGE) return;
-    const int yr = reflect101(rb - ORBX_EDGE, g.h);
-    const OrbxResizeTap ty = L.taps[g.ytab_off + yr];
+    const int rows = g.h + 2 * ORBX_EDGE;
+    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb0 >= rows) return;
     const uint8_t* sbase = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + s.raw_off + ORBX_XOFF;
-    // rows sy and sy+1 of the source payload; when sy is the last row its coefficient c1 is 0 and row sy+1 is the
-    // (valid) apron row, so no clamp is needed — same for columns
-    const uint8_t* r0 = sbase + (size_t)(ty.ofs + ORBX_EDGE) * s.pitch;
-    const uint8_t* r1 = r0 + s.pitch;
-    const int b0 = ty.c0, b1 = ty.c1;
-    uint32_t out = 0;
+    int sx[4], a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int xr = reflect101(cb + k - ORBX_XOFF, g.w);
-        const OrbxResizeTap tx = L.taps[g.xtab_off + xr];
-        const int a0 = tx.c0, a1 = tx.c1, sx = tx.ofs;
-        const int S0 = r0[sx] * a0 + r0[sx + 1] * a1;
-        const int S1 = r1[sx] * a0 + r1[sx + 1] * a1;
-        const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-        out |= (uint32_t)(v & 0xff) << (8 * k);
+        const OrbxResizeTap tx = L.taps[g.xtab_off + reflect101(cb + k - ORBX_XOFF, g.w)];
+        sx[k] = tx.ofs; a0[k] = tx.c0; a1[k] = tx.c1;
     }
-    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb * g.pitch + cb;
-    *reinterpret_cast<uint32_t*>(dst) = out;
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
+#pragma unroll
+    for (int rr = 0; rr < PYR_RPT; rr++) {
+        if (rb0 + rr >= rows) break;
+        const OrbxResizeTap ty = L.taps[g.ytab_off + reflect101(rb0 + rr - ORBX_EDGE, g.h)];
+        // rows sy and sy+1 of the source payload; when sy is the last row its coefficient c1 is 0 and row sy+1 is
+        // the (valid) apron row, so no clamp is needed — same for columns
+        const uint8_t* r0 = sbase + (size_t)(ty.ofs + ORBX_EDGE) * s.pitch;
+        const uint8_t* r1 = r0 + s.pitch;
+        const int b0 = ty.c0, b1 = ty.c1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int S0 = r0[sx[k]] * a0[k] + r0[sx[k] + 1] * a1[k];
+            const int S1 = r1[sx[k]] * a0[k] + r1[sx[k] + 1] * a1[k];
+            const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 0xff) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)rr * g.pitch) = out;
+    }
 }
 
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
@@ -78,9 +87,14 @@ void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, c
     for (int l = 0; l < L.nlevels; l++) {
         const OrbxLevelGeom& g = h_lvl[l];
         const int groups = (ORBX_XOFF + g.w + ORBX_EDGE - 12 + 3) / 4;
-        dim3 grid((groups + PYR_TX - 1) / PYR_TX, (g.h + 2 * ORBX_EDGE + PYR_TY - 1) / PYR_TY, nframes);
+        const int rows = g.h + 2 * ORBX_EDGE;
         dim3 block(PYR_TX, PYR_TY);
-        if (l == 0) pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
-        else pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
+        if (l == 0) {
+            dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY - 1) / PYR_TY, nframes);
+            pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
+        } else {
+            dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY * PYR_RPT - 1) / (PYR_TY * PYR_RPT), nframes);
+            pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
+        }
     }
 }
