@@ -125,25 +125,39 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
         //    (ring 0,4,8,12), so a dark arc needs max over adjacent pairs of min(d_a, d_b) > T and a bright arc
         //    needs min over adjacent pairs of max(d_a, d_b) < -T. Row-major list entry = py<<7 | px.
         int cnt = 0;
-        for (int py = 0; py < eh; py++) {
-            const uint8_t* row = tile + (py + 3) * tp + 3;
+        const unsigned lt_mask = (1u << lane) - 1;
+        // two rows per iteration (independent chains, half the loop overhead) when a row fits one 32-lane chunk;
+        // wider cells go row by row so that the list stays in row-major order
+        const int rstep = ew <= 32 ? 2 : 1;
+        for (int py = 0; py < eh; py += rstep) {
+            const bool row1 = rstep == 2 && py + 1 < eh;         // warp-uniform
             for (int px0 = 0; px0 < ew; px0 += 32) {
                 const int px = px0 + lane;
-                int pass_q = 0;
-                if (px < ew) {
-                    const uint8_t* q = row + px;
-                    const int v = q[0];
-                    const int d0 = v - q[3 * tp], d4 = v - q[3], d8 = v - q[-3 * tp], d12 = v - q[-3];
+                const int pxc = min(px, ew - 1);                 // clamped: loads stay inside the tile, result masked
+                const uint8_t* q0 = tile + (py + 3) * tp + 3 + pxc;
+                const uint8_t* q1 = row1 ? q0 + tp : q0;
+                int pass0, pass1;
+                {
+                    const int v = q0[0];
+                    const int d0 = v - q0[3 * tp], d4 = v - q0[3], d8 = v - q0[-3 * tp], d12 = v - q0[-3];
                     const int dk = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));
                     const int br = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));
-                    pass_q = (dk > T) | (br < -T);
+                    pass0 = (((T - dk) | (br + T)) < 0) & (px < ew);
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, pass_q);
-                if (pass_q) {
-                    const int pos = cnt + __popc(m & ((1u << lane) - 1));
-                    if (pos < cfg.list_cap) list[pos] = (unsigned short)((py << 7) | px);
+                {
+                    const int v = q1[0];
+                    const int d0 = v - q1[3 * tp], d4 = v - q1[3], d8 = v - q1[-3 * tp], d12 = v - q1[-3];
+                    const int dk = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));
+                    const int br = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));
+                    pass1 = (((T - dk) | (br + T)) < 0) & (px < ew) & row1;
                 }
-                cnt += __popc(m);
+                const unsigned m0 = __ballot_sync(0xffffffffu, pass0);
+                const unsigned m1 = __ballot_sync(0xffffffffu, pass1);
+                // row py first, then row py+1: row-major because ew <= 32 whenever row1 is set
+                if (pass0) { const int pos = cnt + __popc(m0 & lt_mask); if (pos < cfg.list_cap) list[pos] = (unsigned short)((py << 7) | px); }
+                cnt += __popc(m0);
+                if (pass1) { const int pos = cnt + __popc(m1 & lt_mask); if (pos < cfg.list_cap) list[pos] = (unsigned short)(((py + 1) << 7) | px); }
+                cnt += __popc(m1);
             }
         }
         cnt = min(cnt, cfg.list_cap);
@@ -160,11 +174,13 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
                 const uint8_t* c = tile + (((e >> 7) & 127) + 3) * tp + (e & 127) + 3;
                 const int lo = (int)c[0] - T, hi = (int)c[0] + T;   // dark: ring < lo ; bright: ring > hi
                 unsigned md = 0, mb = 0;
-#define RING_BIT(kk, off) { const int r = c[off]; md |= (unsigned)(r < lo) << kk; mb |= (unsigned)(r > hi) << kk; }
-                RING_BIT(0, 3 * tp)       RING_BIT(1, 3 * tp + 1)   RING_BIT(2, 2 * tp + 2)   RING_BIT(3, tp + 3)
-                RING_BIT(4, 3)            RING_BIT(5, -tp + 3)      RING_BIT(6, -2 * tp + 2)  RING_BIT(7, -3 * tp + 1)
-                RING_BIT(8, -3 * tp)      RING_BIT(9, -3 * tp - 1)  RING_BIT(10, -2 * tp - 2) RING_BIT(11, -tp - 3)
-                RING_BIT(12, -3)          RING_BIT(13, tp - 3)      RING_BIT(14, 2 * tp - 2)  RING_BIT(15, 3 * tp - 1)
+                // funnel shift pulls the sign bit of (ring - lo) / (hi - ring) into the mask: 2 instructions per bit.
+                // (bit order ends up reversed, which a circular run-length test does not care about)
+#define RING_BIT(off) { const int r = c[off]; md = __funnelshift_l((unsigned)(r - lo), md, 1); mb = __funnelshift_l((unsigned)(hi - r), mb, 1); }
+                RING_BIT(3 * tp)       RING_BIT(3 * tp + 1)   RING_BIT(2 * tp + 2)   RING_BIT(tp + 3)
+                RING_BIT(3)            RING_BIT(-tp + 3)      RING_BIT(-2 * tp + 2)  RING_BIT(-3 * tp + 1)
+                RING_BIT(-3 * tp)      RING_BIT(-3 * tp - 1)  RING_BIT(-2 * tp - 2)  RING_BIT(-tp - 3)
+                RING_BIT(-3)           RING_BIT(tp - 3)       RING_BIT(2 * tp - 2)   RING_BIT(3 * tp - 1)
 #undef RING_BIT
                 md |= md << 16; mb |= mb << 16;
                 md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;   // bit i set <=> ring i..i+8 all dark
