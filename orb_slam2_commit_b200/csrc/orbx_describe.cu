@@ -162,15 +162,18 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     // ---- IC_Angle on the un-blurred level
     int m10 = 0, m01 = 0;
     if (lane < 31) {
+        // rows +v and -v together, as the reference does (ORBextractor.cc:91-102); disc half-widths are literals
+        constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         const int u = lane - 15;
         const int au = u < 0 ? -u : u;
-#pragma unroll 1
-        for (int v = -15; v <= 15; v++) {
-            const int av = v < 0 ? -v : v;
-            if (au <= c_umax[av]) {
-                const int val = raw8[(v + 21) * (PWORDS * 4) + u + 21];
-                m10 += u * val;
-                m01 += v * val;
+        const uint8_t* ctr = raw8 + 21 * (PWORDS * 4) + 21 + u;
+        m10 = u * ctr[0];
+#pragma unroll
+        for (int v = 1; v <= 15; v++) {
+            if (au <= UMAX[v]) {
+                const int vp = ctr[v * (PWORDS * 4)], vm = ctr[-v * (PWORDS * 4)];
+                m10 += u * (vp + vm);
+                m01 += v * (vp - vm);
             }
         }
     }
@@ -191,16 +194,17 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
         const int s8 = (bo & 3) * 8;
         const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2], w3 = rw[3];
         const uint32_t a0 = __funnelshift_r(w0, w1, s8), a1 = __funnelshift_r(w1, w2, s8), a2 = __funnelshift_r(w2, w3, s8);
-        int b[12];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { b[i] = (a0 >> (8 * i)) & 0xff; b[4 + i] = (a1 >> (8 * i)) & 0xff; b[8 + i] = (a2 >> (8 * i)) & 0xff; }
-        unsigned o[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            o[j] = 18 * (b[j] + b[j + 6]) + 34 * (b[j + 1] + b[j + 5]) + 48 * (b[j + 2] + b[j + 4]) + 56 * b[j + 3];
+        // P[k] = byte k | byte k+1 << 16 : two adjacent outputs ride in the two 16-bit halves of ordinary 32-bit
+        // integer ops (each sum stays below 2^16, so nothing carries from the low half into the high half)
+        uint32_t P[9];
+        P[0] = __byte_perm(a0, 0, 0x4140); P[1] = __byte_perm(a0, 0, 0x4241); P[2] = __byte_perm(a0, 0, 0x4342);
+        P[3] = __byte_perm(__funnelshift_r(a0, a1, 16), 0, 0x4241);   // bytes 3,4 straddle two words
+        P[4] = __byte_perm(a1, 0, 0x4140); P[5] = __byte_perm(a1, 0, 0x4241); P[6] = __byte_perm(a1, 0, 0x4342);
+        P[7] = __byte_perm(__funnelshift_r(a1, a2, 16), 0, 0x4241);   // bytes 7,8
+        P[8] = __byte_perm(a2, 0, 0x4140);
         uint32_t* dst = reinterpret_cast<uint32_t*>(hb + r * HBP + c0);
-        dst[0] = o[0] | (o[1] << 16);
-        dst[1] = o[2] | (o[3] << 16);
+        dst[0] = 18u * (P[0] + P[6]) + 34u * (P[1] + P[5]) + 48u * (P[2] + P[4]) + 56u * P[3];
+        dst[1] = 18u * (P[2] + P[8]) + 34u * (P[3] + P[7]) + 48u * (P[4] + P[6]) + 56u * P[5];
     }
     __syncwarp();
 
