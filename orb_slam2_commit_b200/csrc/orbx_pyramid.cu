@@ -18,30 +18,36 @@ __device__ __forceinline__ int reflect101(int p, int len)
     return p >= len ? 2 * (len - 1) - p : p;
 }
 
+#define PYR_RPT 8        // buffer rows per thread
+
 // level 0: copy of the input frame (+apron)
 __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_kernel(OrbxFrameLayout L, const uint8_t* __restrict__ img, int stride,
                                                          size_t frame_pitch)
 {
     const OrbxLevelGeom g = L.lvl[0];
     const int t = blockIdx.x * PYR_TX + threadIdx.x;        // group of 4 buffer columns starting at column 12
-    const int rb = blockIdx.y * PYR_TY + threadIdx.y;       // buffer row
+    const int rb0 = (blockIdx.y * PYR_TY + threadIdx.y) * PYR_RPT;
     const int cb = 12 + 4 * t;
-    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb >= g.h + 2 * ORBX_EDGE) return;
-    const int yr = reflect101(rb - ORBX_EDGE, g.h);
-    const uint8_t* src = img + (size_t)blockIdx.z * frame_pitch + (size_t)yr * stride;
-    uint32_t out = 0;
+    const int rows = g.h + 2 * ORBX_EDGE;
+    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb0 >= rows) return;
+    int xr[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int xr = reflect101(cb + k - ORBX_XOFF, g.w);
-        out |= (uint32_t)__ldg(src + xr) << (8 * k);
+    for (int k = 0; k < 4; k++) xr[k] = reflect101(cb + k - ORBX_XOFF, g.w);
+    const uint8_t* fimg = img + (size_t)blockIdx.z * frame_pitch;
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
+#pragma unroll
+    for (int rr = 0; rr < PYR_RPT; rr++) {
+        if (rb0 + rr >= rows) break;
+        const uint8_t* src = fimg + (size_t)reflect101(rb0 + rr - ORBX_EDGE, g.h) * stride;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) out |= (uint32_t)__ldg(src + xr[k]) << (8 * k);
+        *reinterpret_cast<uint32_t*>(dst + (size_t)rr * g.pitch) = out;
     }
-    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb * g.pitch + cb;
-    *reinterpret_cast<uint32_t*>(dst) = out;
 }
 
 // level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows: the four
 // x-taps are fetched once and up to 16*PYR_RPT independent source-pixel loads are in flight per thread.
-#define PYR_RPT 2
 __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_kernel(OrbxFrameLayout L, int level)
 {
     const OrbxLevelGeom g = L.lvl[level];
@@ -89,12 +95,8 @@ void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, c
         const int groups = (ORBX_XOFF + g.w + ORBX_EDGE - 12 + 3) / 4;
         const int rows = g.h + 2 * ORBX_EDGE;
         dim3 block(PYR_TX, PYR_TY);
-        if (l == 0) {
-            dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY - 1) / PYR_TY, nframes);
-            pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
-        } else {
-            dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY * PYR_RPT - 1) / (PYR_TY * PYR_RPT), nframes);
-            pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
-        }
+        dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY * PYR_RPT - 1) / (PYR_TY * PYR_RPT), nframes);
+        if (l == 0) pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
+        else pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
     }
 }
