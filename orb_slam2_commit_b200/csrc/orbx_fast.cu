@@ -64,6 +64,9 @@ __device__ __forceinline__ int fast_score_T(const uint8_t* __restrict__ c, const
     return s >= T ? s : 0;
 }
 
+// TPC / SPC: compile-time tile / score-map pitches in bytes (all ring and NMS offsets become immediates);
+// 0 = take them from cfg (cells wider than the common 30..46 px)
+template <int TPC, int SPC>
 __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLayout L, FastSmemCfg cfg)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
     uint32_t* tile32 = reinterpret_cast<uint32_t*>(wbase + cfg.tile_off);
     uint8_t* score = wbase + cfg.score_off;
     unsigned short* list = reinterpret_cast<unsigned short*>(wbase + cfg.list_off);
-    const int tp = cfg.tpw * 4, sp = cfg.sp;
+    const int tp = TPC ? TPC : cfg.tpw * 4, sp = SPC ? SPC : cfg.sp, tpw = tp >> 2;
 
     // ---- stage the tile rows [ey0-3, ey1+3) x [ex0-3, ex1+3) with aligned 32-bit loads
     const int tw = ew + 6, th = eh + 6;
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
             for (int u = 0; u < 4; u++) {
                 const int i = i0 + 32 * u;
                 const int r = (int)(((unsigned)i * (unsigned)inv) >> 20), w = i - r * nw;
-                dst[u] = r * cfg.tpw + w;
+                dst[u] = r * tpw + w;
                 v[u] = i < nwords ? __ldg(pa + r * pitch_w + w) : 0u;
             }
 #pragma unroll
@@ -126,38 +129,55 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
         //    needs min over adjacent pairs of max(d_a, d_b) < -T. Row-major list entry = py<<7 | px.
         int cnt = 0;
         const unsigned lt_mask = (1u << lane) - 1;
-        // two rows per iteration (independent chains, half the loop overhead) when a row fits one 32-lane chunk;
-        // wider cells go row by row so that the list stays in row-major order
-        const int rstep = ew <= 32 ? 2 : 1;
-        for (int py = 0; py < eh; py += rstep) {
-            const bool row1 = rstep == 2 && py + 1 < eh;         // warp-uniform
-            for (int px0 = 0; px0 < ew; px0 += 32) {
-                const int px = px0 + lane;
-                const int pxc = min(px, ew - 1);                 // clamped: loads stay inside the tile, result masked
-                const uint8_t* q0 = tile + (py + 3) * tp + 3 + pxc;
-                const uint8_t* q1 = row1 ? q0 + tp : q0;
-                int pass0, pass1;
-                {
-                    const int v = q0[0];
-                    const int d0 = v - q0[3 * tp], d4 = v - q0[3], d8 = v - q0[-3 * tp], d12 = v - q0[-3];
+        {
+            // lane = column, rows walked top to bottom; the pass bit of every row is shifted into a per-lane mask
+            // (funnel shift pulls the sign of x = (T-dk)|(br+T) in: one instruction, no ballot in the arithmetic loop).
+            // Up to two 32-column chunks (cells are < 60 px wide) and two 32-row halves (< 60 px tall).
+            const int nlo = min(eh, 32), nhi = eh - nlo;
+            unsigned q[2][2] = {{0u, 0u}, {0u, 0u}};            // [chunk][row half], bit (n-1-row) <-> row
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch * 32 >= ew) break;                        // warp-uniform
+                const int px = ch * 32 + lane;
+                const uint8_t* col = tile + 3 * tp + 3 + min(px, ew - 1);   // clamped: loads stay inside the tile
+                unsigned acc = 0;
+#pragma unroll 4
+                for (int py = 0; py < nlo; py++) {
+                    const uint8_t* qp = col + py * tp;
+                    const int v = qp[0];
+                    const int d0 = v - qp[3 * tp], d4 = v - qp[3], d8 = v - qp[-3 * tp], d12 = v - qp[-3];
                     const int dk = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));
                     const int br = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));
-                    pass0 = (((T - dk) | (br + T)) < 0) & (px < ew);
+                    acc = __funnelshift_l((unsigned)((T - dk) | (br + T)), acc, 1);
                 }
-                {
-                    const int v = q1[0];
-                    const int d0 = v - q1[3 * tp], d4 = v - q1[3], d8 = v - q1[-3 * tp], d12 = v - q1[-3];
+                q[ch][0] = px < ew ? acc : 0u;
+                acc = 0;
+#pragma unroll 4
+                for (int py = 32; py < eh; py++) {
+                    const uint8_t* qp = col + py * tp;
+                    const int v = qp[0];
+                    const int d0 = v - qp[3 * tp], d4 = v - qp[3], d8 = v - qp[-3 * tp], d12 = v - qp[-3];
                     const int dk = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));
                     const int br = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));
-                    pass1 = (((T - dk) | (br + T)) < 0) & (px < ew) & row1;
+                    acc = __funnelshift_l((unsigned)((T - dk) | (br + T)), acc, 1);
                 }
-                const unsigned m0 = __ballot_sync(0xffffffffu, pass0);
-                const unsigned m1 = __ballot_sync(0xffffffffu, pass1);
-                // row py first, then row py+1: row-major because ew <= 32 whenever row1 is set
-                if (pass0) { const int pos = cnt + __popc(m0 & lt_mask); if (pos < cfg.list_cap) list[pos] = (unsigned short)((py << 7) | px); }
-                cnt += __popc(m0);
-                if (pass1) { const int pos = cnt + __popc(m1 & lt_mask); if (pos < cfg.list_cap) list[pos] = (unsigned short)(((py + 1) << 7) | px); }
-                cnt += __popc(m1);
+                q[ch][1] = px < ew ? acc : 0u;
+            }
+            // row-major list of the pixels that passed: entry = py<<7 | px
+            for (int py = 0; py < eh; py++) {
+                const int half = py >> 5;
+                const int sh_bit = half ? nhi - 1 - (py - 32) : nlo - 1 - py;
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch * 32 >= ew) break;
+                    const unsigned bit = ((half ? q[ch][1] : q[ch][0]) >> sh_bit) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, bit);
+                    if (bit) {
+                        const int pos = cnt + __popc(m & lt_mask);
+                        if (pos < cfg.list_cap) list[pos] = (unsigned short)((py << 7) | (ch * 32 + lane));
+                    }
+                    cnt += __popc(m);
+                }
             }
         }
         cnt = min(cnt, cfg.list_cap);
@@ -230,9 +250,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st)
 {
     FastSmemCfg cfg;
-    cfg.tpw = (3 + max_tile_w + 3) / 4 + 1;
+    // common case (cells up to 46 px wide): compile-time pitches 56 / 48
+    const bool smallcfg = max_tile_w + 3 <= 56 && max_tile_w - 6 + 2 <= 48;
+    cfg.tpw = smallcfg ? 14 : (3 + max_tile_w + 3) / 4 + 1;
     cfg.th = max_tile_h;
-    cfg.sp = (max_tile_w - 6 + 2 + 3) & ~3;
+    cfg.sp = smallcfg ? 48 : (max_tile_w - 6 + 2 + 3) & ~3;
     cfg.srows = max_tile_h - 6 + 2;
     cfg.list_cap = (max_tile_w - 6) * (max_tile_h - 6);
     cfg.tile_off = 0;
@@ -242,9 +264,11 @@ void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, 
     const size_t smem = (size_t)cfg.per_warp * FAST_WARPS;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fast_cells_kernel<56, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fast_cells_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     dim3 grid((L.ncells + FAST_WARPS - 1) / FAST_WARPS, nframes);
-    fast_cells_kernel<<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
+    if (smallcfg) fast_cells_kernel<56, 48><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
+    else fast_cells_kernel<0, 0><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
 }
