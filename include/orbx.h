@@ -138,6 +138,17 @@ int orbx_stereo_hamming(const OrbxKeyPoint* kp_left, const uint8_t* desc_left, i
                         int rows, const float* scale_factors, int nlevels, float minD, float maxD,
                         int32_t* best_idx_r, int32_t* best_dist, int device);
 
+/* ---- Frame::ComputeStereoMatches, complete (Frame.cc:547-788): row-band Hamming as above, then the 11x11 SAD of
+ *      centre-normalised windows slid over +-5 columns on the level pyramids of BOTH extractors (left / right must
+ *      have just extracted the left / right image of the pair, same geometry, same device — their pyramids are read
+ *      where they lie in HBM), the parabola sub-pixel fit, disparity/depth, and the 1.5*1.4*median outlier cut.
+ *      mbf = Camera.bf, fx = Camera.fx (mb = mbf/fx, Frame.cc:120). Outputs: mvuRight / mvDepth, n_left floats each,
+ *      -1 where there is no stereo match. Host buffers, synchronous. ---- */
+int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right,
+                      const OrbxKeyPoint* kp_left, const uint8_t* desc_left, int n_left,
+                      const OrbxKeyPoint* kp_right, const uint8_t* desc_right, int n_right,
+                      float mbf, float fx, float* u_right, float* depth);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

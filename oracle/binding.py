@@ -76,6 +76,8 @@ def lib():
         L.oc_level_candidates.restype = C.c_int
         L.oc_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oc_level_nkeypoints.restype = C.c_int; L.oc_level_nkeypoints.argtypes = [C.c_void_p, C.c_int]
+        L.oc_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
+                                      C.c_float, C.c_float, f32p, f32p]
         _lib = L
     return _lib
 
@@ -151,6 +153,16 @@ def stereo_hamming(kl, dl, kr, dr, rows, scale_factors, minD, maxD):
     lib().oc_stereo_hamming(kl.ctypes.data, _u8(dl), len(kl), kr.ctypes.data, _u8(dr), len(kr), rows,
                             sf.ctypes.data_as(f32p), minD, maxD, bi.ctypes.data_as(i32p), bd.ctypes.data_as(i32p))
     return bi, bd
+
+
+def stereo_match(left: "Extractor", right: "Extractor", kl, dl, kr, dr, mbf, fx):
+    """Full Frame::ComputeStereoMatches on two oracle extractors that just processed the left / right image."""
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    ur = np.empty(len(kl), np.float32); dp = np.empty(len(kl), np.float32)
+    lib().oc_stereo_match(left.h, right.h, kl.ctypes.data, _u8(dl), len(kl), kr.ctypes.data, _u8(dr), len(kr),
+                          mbf, fx, ur.ctypes.data_as(f32p), dp.ctypes.data_as(f32p))
+    return ur, dp
 
 
 class Extractor:

@@ -835,3 +835,86 @@ int oc_extract(OcExtractor* e, const uint8_t* img, int w, int h, int stride,
     free(lvl);
     return status == 0 ? total : status;
 }
+
+/* ------------------------------------------------------------------ Frame::ComputeStereoMatches (Frame.cc:547-788) */
+typedef struct { int dist, idx; } DistIdx;
+static int distidx_cmp(const void* a, const void* b)
+{
+    const DistIdx* x = (const DistIdx*)a; const DistIdx* y = (const DistIdx*)b;
+    if (x->dist != y->dist) return x->dist < y->dist ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+void oc_stereo_match(const OcExtractor* EL, const OcExtractor* ER,
+                     const OcKeyPoint* kl, const uint8_t* dl, int nl,
+                     const OcKeyPoint* kr, const uint8_t* dr, int nr,
+                     float mbf, float fx, float* u_right, float* depth)
+{
+    const int B = EDGE_THRESHOLD;
+    for (int i = 0; i < nl; i++) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    const int thOrbDist = (100 + 50) / 2;                  /* (TH_HIGH+TH_LOW)/2 */
+    const int nRows = EL->lh[0];
+    const float mb = mbf / fx;                             /* Frame.cc:120 */
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    int32_t* bidx = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nl > 0 ? nl : 1));
+    int32_t* bdist = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nl > 0 ? nl : 1));
+    oc_stereo_hamming(kl, dl, nl, kr, dr, nr, nRows, EL->sf, minD, maxD, bidx, bdist);   /* :554-663 */
+    DistIdx* v = (DistIdx*)malloc(sizeof(DistIdx) * (size_t)(nl > 0 ? nl : 1));
+    int nv = 0;
+    for (int iL = 0; iL < nl; iL++) {
+        if (bidx[iL] < 0 || !(bdist[iL] < thOrbDist)) continue;
+        const OcKeyPoint* kpL = &kl[iL];
+        const float uL = kpL->x;
+        const float uR0 = kr[bidx[iL]].x;
+        const float scaleFactor = EL->inv_sf[kpL->octave];
+        const float scaleduL = roundf(kpL->x * scaleFactor);
+        const float scaledvL = roundf(kpL->y * scaleFactor);
+        const float scaleduR0 = roundf(uR0 * scaleFactor);
+        const int w = 5, L = 5;
+        const int lv = kpL->octave;
+        const int wsL = EL->lw[lv] + 2 * B, wsR = ER->lw[lv] + 2 * B;
+        const uint8_t* pL = EL->whole[lv] + (size_t)B * wsL + B;     /* payload origins; the apron makes small */
+        const uint8_t* pR = ER->whole[lv] + (size_t)B * wsR + B;     /* excursions valid memory, as in the reference */
+        const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+        const float iniu = scaleduR0 + L - w;
+        const float endu = scaleduR0 + L + w + 1;
+        if (iniu < 0 || endu >= ER->lw[lv]) continue;
+        const int cL = pL[(size_t)cv * wsL + cu];
+        int bestDist = 2147483647, bestincR = 0;
+        float vDists[11];
+        for (int incR = -L; incR <= L; incR++) {
+            const int cR = pR[(size_t)cv * wsR + cr + incR];
+            int sad = 0;
+            for (int dy = -w; dy <= w; dy++)
+                for (int dx = -w; dx <= w; dx++) {
+                    const int a = pL[(size_t)(cv + dy) * wsL + cu + dx] - cL;
+                    const int b = pR[(size_t)(cv + dy) * wsR + cr + incR + dx] - cR;
+                    sad += a > b ? a - b : b - a;
+                }
+            const float dist = (float)sad;                 /* cv::norm(IL,IR,NORM_L1) of integer-valued floats */
+            if (dist < (float)bestDist) { bestDist = (int)dist; bestincR = incR; }
+            vDists[L + incR] = dist;
+        }
+        if (bestincR == -L || bestincR == L) continue;
+        const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+        const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+        if (deltaR < -1 || deltaR > 1) continue;
+        float bestuR = EL->sf[lv] * ((float)scaleduR0 + (float)bestincR + deltaR);
+        float disparity = (uL - bestuR);
+        if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+            depth[iL] = mbf / disparity;
+            u_right[iL] = bestuR;
+            v[nv].dist = bestDist; v[nv].idx = iL; nv++;
+        }
+    }
+    if (nv > 0) {                                          /* the reference indexes an empty vector here */
+        qsort(v, (size_t)nv, sizeof(DistIdx), distidx_cmp);
+        const float median = (float)v[nv / 2].dist;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = nv - 1; i >= 0; i--) {
+            if ((float)v[i].dist < thDist) break;
+            u_right[v[i].idx] = -1; depth[v[i].idx] = -1;
+        }
+    }
+    free(v); free(bidx); free(bdist);
+}

@@ -65,6 +65,14 @@ const uint8_t* oc_level_blur_ptr(const OcExtractor*, int level); /* blurred leve
 int   oc_level_candidates(const OcExtractor*, int level, OcKeyPoint* out, int cap); /* pre-quadtree list */
 int   oc_level_nkeypoints(const OcExtractor*, int level);
 
+/* Full Frame::ComputeStereoMatches (Frame.cc:547-788) on the outputs and pyramids of two extractors that have just
+ * processed the left / right image: row-band Hamming, 11x11 SAD slide +-5 on the level pyramids, parabola
+ * sub-pixel, 1.5*1.4*median cut. mb = mbf / fx (Frame.cc:120). u_right / depth: n_left floats, -1 = no match. */
+void  oc_stereo_match(const OcExtractor* left, const OcExtractor* right,
+                      const OcKeyPoint* kl, const uint8_t* dl, int nl,
+                      const OcKeyPoint* kr, const uint8_t* dr, int nr,
+                      float mbf, float fx, float* u_right, float* depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,8 @@ def lib():
         L.orbx_hamming_merge_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_stereo_hamming.argtypes = [C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int, C.c_int, f32p, C.c_int,
                                           C.c_float, C.c_float, i32p, i32p, C.c_int]
+        L.orbx_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
+                                        C.c_float, C.c_float, f32p, f32p]
         _lib = L
     return _lib
 
@@ -253,6 +255,17 @@ def stereo_hamming(kp_left, desc_left, kp_right, desc_right, rows, scale_factors
                                   sf.ctypes.data_as(f32p), len(sf), minD, maxD, bi.ctypes.data_as(i32p),
                                   bd.ctypes.data_as(i32p), device))
     return bi, bd
+
+
+def stereo_match(left: ORBextractor, right: ORBextractor, kp_left, desc_left, kp_right, desc_right, mbf: float, fx: float):
+    """Frame::ComputeStereoMatches (Frame.cc:547-788) on the HBM-resident pyramids of two extractors that have just
+    extracted the left / right image. Returns (mvuRight, mvDepth): float32 arrays, -1 where unmatched."""
+    kl = np.ascontiguousarray(kp_left, KP_DTYPE); kr = np.ascontiguousarray(kp_right, KP_DTYPE)
+    dl = np.ascontiguousarray(desc_left, np.uint8); dr = np.ascontiguousarray(desc_right, np.uint8)
+    ur = np.full(len(kl), -1, np.float32); dp = np.full(len(kl), -1, np.float32)
+    _ck(lib().orbx_stereo_match(left._h, right._h, kl.ctypes.data, _u8(dl), len(kl), kr.ctypes.data, _u8(dr), len(kr),
+                                mbf, fx, ur.ctypes.data_as(f32p), dp.ctypes.data_as(f32p)))
+    return ur, dp
 
 
 class ORBmatcher:

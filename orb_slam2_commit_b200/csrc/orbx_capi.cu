@@ -194,6 +194,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
         g.quota = h->quota[l];
         if (g.quota > ORBX_MAX_QUOTA) return fail(ORBX_ERR_UNSUPPORTED, "more than 2040 features on one level");
         g.scale = h->sf[l];
+        g.inv_scale = h->inv_sf[l];
         g.kp_size = (float)(int)(31 * h->sf[l]);                  // scaledPatchSize (ORBextractor.cc:925)
         g.pitch = (ORBX_XOFF + g.w + ORBX_EDGE + 3 + 31) & ~31;
         g.raw_off = (int)raw;
@@ -639,4 +640,97 @@ extern "C" int orbx_stereo_hamming(const OrbxKeyPoint* kl, const uint8_t* dl, in
     if (e != cudaSuccess) rc = fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     cudaFree(pool);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ full stereo
+#include <algorithm>
+extern "C" int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, const OrbxKeyPoint* kl, const uint8_t* dl,
+                                 int nl, const OrbxKeyPoint* kr, const uint8_t* dr, int nr, float mbf, float fx,
+                                 float* u_right, float* depth)
+{
+    if (!left || !right || nl < 0 || nr < 0 || (nl > 0 && (!kl || !dl || !u_right || !depth)) || (nr > 0 && (!kr || !dr)))
+        return fail(ORBX_ERR_INVALID, "bad argument");
+    for (int i = 0; i < nl; i++) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    if (nl == 0) return ORBX_OK;
+    if (left->last_frames <= 0 || right->last_frames <= 0) return fail(ORBX_ERR_STATE, "both extractors must have extracted the pair first");
+    if (left->device != right->device || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels ||
+        left->scale_factor != right->scale_factor)
+        return fail(ORBX_ERR_INVALID, "left and right extractors must share device, image size and pyramid settings");
+    CK(cudaSetDevice(left->device));
+    CK(cudaStreamSynchronize(left->stream));
+    CK(cudaStreamSynchronize(right->stream));
+    const int rows = left->lvl[0].h, nlevels = left->nlevels;
+    const float mb = mbf / fx;                      // Frame.cc:120
+    const float minD = 0.f, maxD = mbf / mb;        // Frame.cc:592-595
+    // vRowIndices (Frame.cc:564-590) as CSR, ascending iR inside every row
+    std::vector<int> start(rows + 1, 0), lo(nr), hi(nr);
+    for (int i = 0; i < nr; i++) {
+        if (kr[i].octave < 0 || kr[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "right keypoint octave out of range");
+        const float r = 2.0f * left->sf[kr[i].octave];
+        hi[i] = std::min((int)ceilf(kr[i].y + r), rows - 1);
+        lo[i] = std::max((int)floorf(kr[i].y - r), 0);
+        for (int y = lo[i]; y <= hi[i]; y++) start[y + 1]++;
+    }
+    for (int y = 0; y < rows; y++) start[y + 1] += start[y];
+    std::vector<int> tab(std::max(start[rows], 1)), fill(rows, 0);
+    for (int i = 0; i < nr; i++)
+        for (int y = lo[i]; y <= hi[i]; y++) tab[start[y] + fill[y]++] = i;
+    for (int i = 0; i < nl; i++)
+        if (kl[i].octave < 0 || kl[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "left keypoint octave out of range");
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_kl = (size_t)nl * 28, b_dl = (size_t)nl * 32, b_kr = (size_t)std::max(nr, 1) * 28, b_dr = (size_t)std::max(nr, 1) * 32;
+    const size_t b_st = (size_t)(rows + 1) * 4, b_tab = tab.size() * 4, b_out = (size_t)nl * 12;
+    void* pool = nullptr;
+    CK(cudaMalloc(&pool, al(b_kl) + al(b_dl) + al(b_kr) + al(b_dr) + al(b_st) + al(b_tab) + al(b_out)));
+    uint8_t* p = (uint8_t*)pool;
+    uint8_t *p_kl = p; p += al(b_kl);
+    uint8_t *p_dl = p; p += al(b_dl);
+    uint8_t *p_kr = p; p += al(b_kr);
+    uint8_t *p_dr = p; p += al(b_dr);
+    uint8_t *p_st = p; p += al(b_st);
+    uint8_t *p_tab = p; p += al(b_tab);
+    uint8_t *p_out = p;
+    std::vector<float> h_u(nl), h_d(nl);
+    std::vector<int> h_sad(nl);
+    int rc = ORBX_OK;
+    cudaError_t e;
+    do {
+        if ((e = cudaMemcpy(p_kl, kl, b_kl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_dl, dl, b_dl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (nr > 0 && (e = cudaMemcpy(p_kr, kr, (size_t)nr * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (nr > 0 && (e = cudaMemcpy(p_dr, dr, (size_t)nr * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_st, start.data(), b_st, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_tab, tab.data(), b_tab, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        OrbxStereoArgs a;
+        a.kl = (const OrbxKp28*)p_kl; a.dl = p_dl; a.nl = nl; a.kr = (const OrbxKp28*)p_kr; a.dr = p_dr;
+        a.row_start = (const int*)p_st; a.row_tab = (const int*)p_tab; a.rows = rows;
+        a.raw_left = left->L.raw + (size_t)left->pyr_base * left->L.frame_raw_bytes;
+        a.raw_right = right->L.raw + (size_t)right->pyr_base * right->L.frame_raw_bytes;
+        a.lvl = left->d_lvl;
+        a.minD = minD; a.maxD = maxD; a.mbf = mbf;
+        a.u_right = (float*)p_out; a.depth = (float*)p_out + nl; a.sad = (int*)p_out + 2 * (size_t)nl;
+        orbx_launch_stereo_match(a, 0);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(h_u.data(), p_out, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(h_d.data(), p_out + (size_t)nl * 4, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(h_sad.data(), p_out + (size_t)nl * 8, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) rc = fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    cudaFree(pool);
+    if (rc != ORBX_OK) return rc;
+    // adaptive outlier cut (Frame.cc:774-787): sort (SAD, iL), threshold 1.5*1.4*median
+    std::vector<std::pair<int, int> > v;
+    for (int i = 0; i < nl; i++) {
+        if (h_sad[i] >= 0) { u_right[i] = h_u[i]; depth[i] = h_d[i]; v.push_back(std::make_pair(h_sad[i], i)); }
+    }
+    if (!v.empty()) {                               // the reference indexes an empty vector when nothing matched
+        std::sort(v.begin(), v.end());
+        const float median = (float)v[v.size() / 2].first;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = (int)v.size() - 1; i >= 0; i--) {
+            if ((float)v[i].first < thDist) break;
+            u_right[v[i].second] = -1; depth[v[i].second] = -1;
+        }
+    }
+    return ORBX_OK;
 }

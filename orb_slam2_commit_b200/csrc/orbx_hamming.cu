@@ -219,3 +219,98 @@ void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, c
         kl, reinterpret_cast<const uint4*>(dl), nl, kr, reinterpret_cast<const uint4*>(dr), row_start, row_tab, rows,
         minD, maxD, best_idx, best_dist);
 }
+
+// ---------------------------------------------------------------- full stereo matching (Frame.cc:596-764)
+// One warp per left keypoint: row-band Hamming best (as above), then — on the HBM-resident level pyramids of the two
+// extractors — the 11x11 SAD of centre-normalised windows slid over +-5 columns, the parabola fit through the three
+// SADs around the minimum and the disparity / depth of Frame.cc:733-760. All window arithmetic is integer (the
+// reference converts to float only to call cv::norm); the float steps use un-contracted IEEE operations.
+// The 1.5*1.4*median cut over all matches (Frame.cc:774-787) is a sort of <= N pairs and stays on the host.
+__global__ void __launch_bounds__(256) stereo_match_kernel(OrbxStereoArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (iL >= A.nl) return;
+    const OrbxKp28 k = A.kl[iL];
+    const int row = (int)k.y;
+    int key = (100 << 20) | 0xfffff;
+    if (row >= 0 && row < A.rows) {
+        const float minU = __fsub_rn(k.x, A.maxD), maxU = __fsub_rn(k.x, A.minD);
+        if (!(maxU < 0.f)) {
+            const uint4* dl = reinterpret_cast<const uint4*>(A.dl);
+            const uint4* dr = reinterpret_cast<const uint4*>(A.dr);
+            const uint4 qa = dl[2 * (size_t)iL], qb = dl[2 * (size_t)iL + 1];
+            const int c0 = A.row_start[row], c1 = A.row_start[row + 1];
+            for (int c = c0 + lane; c < c1; c += 32) {
+                const int iR = A.row_tab[c];
+                const OrbxKp28 r = A.kr[iR];
+                if (r.octave < k.octave - 1 || r.octave > k.octave + 1) continue;
+                if (r.x >= minU && r.x <= maxU) {
+                    const int d = ht_dist(qa, qb, dr[2 * (size_t)iR], dr[2 * (size_t)iR + 1]);
+                    if (d < 100) key = min(key, (d << 20) | min(c - c0, 0xffffe));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    float out_u = -1.f, out_d = -1.f;
+    int out_sad = -1;
+    const int pos = key & 0xfffff;
+    if (pos != 0xfffff && (key >> 20) < 75) {                 // thOrbDist = (TH_HIGH + TH_LOW) / 2  (warp-uniform)
+        const int iR = A.row_tab[A.row_start[row] + pos];
+        const OrbxLevelGeom g = A.lvl[k.octave];
+        const float uR0 = A.kr[iR].x;
+        const float scaleduL = roundf(__fmul_rn(k.x, g.inv_scale));
+        const float scaledvL = roundf(__fmul_rn(k.y, g.inv_scale));
+        const float scaleduR0 = roundf(__fmul_rn(uR0, g.inv_scale));
+        const float iniu = __fsub_rn(__fadd_rn(scaleduR0, 5.f), 5.f);          // scaleduR0 + L - w  (sic)
+        const float endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, 5.f), 5.f), 1.f);
+        if (!(iniu < 0.f || endu >= (float)g.w)) {
+            const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+            const uint8_t* pL = A.raw_left + g.raw_off + (size_t)(cv + ORBX_EDGE) * g.pitch + (cu + ORBX_XOFF);
+            const uint8_t* pR = A.raw_right + g.raw_off + (size_t)(cv + ORBX_EDGE) * g.pitch + (cr + ORBX_XOFF);
+            const int cL = pL[0];
+            int cR[11], acc[11];
+#pragma unroll
+            for (int s = 0; s < 11; s++) { cR[s] = pR[s - 5]; acc[s] = 0; }
+            for (int i = lane; i < 121; i += 32) {
+                const int dy = i / 11 - 5, dx = i - (dy + 5) * 11 - 5;
+                const int a = (int)pL[dy * g.pitch + dx] - cL;
+                const uint8_t* q = pR + dy * g.pitch + dx;
+#pragma unroll
+                for (int s = 0; s < 11; s++) acc[s] += abs(a - ((int)q[s - 5] - cR[s]));
+            }
+#pragma unroll
+            for (int s = 0; s < 11; s++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+            int bestDist = 2147483647, bestinc = 0;
+#pragma unroll
+            for (int s = 0; s < 11; s++) if ((float)acc[s] < (float)bestDist) { bestDist = acc[s]; bestinc = s - 5; }
+            if (bestinc != -5 && bestinc != 5) {
+                float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int s = 1; s < 10; s++) if (s - 5 == bestinc) { d1 = (float)acc[s - 1]; d2 = (float)acc[s]; d3 = (float)acc[s + 1]; }
+                const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+                if (!(deltaR < -1.f || deltaR > 1.f)) {
+                    float bestuR = __fmul_rn(g.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+                    float disparity = __fsub_rn(k.x, bestuR);
+                    if (disparity >= A.minD && disparity < A.maxD) {
+                        if (disparity <= 0.f) { disparity = 0.01f; bestuR = (float)((double)k.x - 0.01); }
+                        out_d = __fdiv_rn(A.mbf, disparity);
+                        out_u = bestuR;
+                        out_sad = bestDist;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { A.u_right[iL] = out_u; A.depth[iL] = out_d; A.sad[iL] = out_sad; }
+}
+
+void orbx_launch_stereo_match(const OrbxStereoArgs& a, cudaStream_t st)
+{
+    if (a.nl <= 0) return;
+    stereo_match_kernel<<<(a.nl + 7) / 8, 256, 0, st>>>(a);
+}

@@ -31,6 +31,7 @@ struct OrbxLevelGeom {
     int nini;                 // quadtree roots (ORBextractor.cc:567)
     float hx;                 // root width (ORBextractor.cc:570)
     float scale;              // mvScaleFactor[l]
+    float inv_scale;          // mvInvScaleFactor[l]
     float kp_size;            // (float)(int)(31*scale)
     int cell0, ncols, nrows;  // first cell id of the level, cell grid
     int cand_off;             // offset (elements) of the level's compact candidate array inside a frame
@@ -87,6 +88,16 @@ void orbx_launch_hamming_top2(const uint8_t* d_q, int nq, const uint8_t* d_t, in
                               uint64_t* d_packed, cudaStream_t st);
 void orbx_launch_hamming_merge(const uint64_t* d_parts, int nparts, int nq, int* d_idx, int* d_d1, int* d_d2,
                                cudaStream_t st);
+struct OrbxStereoArgs {        // full Frame::ComputeStereoMatches kernel (Frame.cc:596-764)
+    const OrbxKp28* kl; const uint8_t* dl; int nl;
+    const OrbxKp28* kr; const uint8_t* dr;
+    const int* row_start; const int* row_tab; int rows;
+    const uint8_t* raw_left; const uint8_t* raw_right;   // frame base of each extractor's HBM pyramid
+    const OrbxLevelGeom* lvl;
+    float minD, maxD, mbf;
+    float* u_right; float* depth; int* sad;               // per left keypoint; sad = -1 when unmatched
+};
+void orbx_launch_stereo_match(const OrbxStereoArgs& a, cudaStream_t st);
 void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, const OrbxKp28* kr, const uint8_t* dr,
                                 int nr, const int* row_start, const int* row_tab, int rows, float minD, float maxD,
                                 int* best_idx, int* best_dist, cudaStream_t st);

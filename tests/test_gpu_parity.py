@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import binding as ob
-from orb_slam2_commit_b200 import ORBextractor, ORBmatcher, hamming_top2, stereo_hamming, synth
+from orb_slam2_commit_b200 import ORBextractor, ORBmatcher, hamming_top2, stereo_hamming, stereo_match, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -266,3 +266,22 @@ def test_device_resident_api_matches_host_api():
         k = d_kps[i, :n[i]].cpu().numpy().view(api.KP_DTYPE).reshape(-1)
         assert k.tobytes() == kb[i].tobytes()
         assert np.array_equal(d_desc[i, :n[i]].cpu().numpy(), db[i])
+
+
+@pytest.mark.parametrize("name,seed", [("kitti", 2), ("euroc", 1001)])
+def test_full_stereo_match_matches_oracle(name, seed):
+    """Frame::ComputeStereoMatches end to end (Frame.cc:547-788): Hamming + SAD + parabola + median cut on the
+    HBM-resident pyramids of a left and a right extractor. mvuRight and mvDepth must be bit-identical floats."""
+    c = _cfg(name)
+    left, right = synth.synth_stereo_pair(c["width"], c["height"], seed)
+    args = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    exL, exR = ORBextractor(*args), ORBextractor(*args)
+    kl, dl = exL(left); kr, dr = exR(right)
+    ur, dp = stereo_match(exL, exR, kl, dl, kr, dr, c["bf"], c["fx"])
+    oL, oR = ob.Extractor(*args), ob.Extractor(*args)
+    kl_o, dl_o = oL.extract(left); kr_o, dr_o = oR.extract(right)
+    assert kl.tobytes() == kl_o.tobytes() and kr.tobytes() == kr_o.tobytes()
+    ur_o, dp_o = ob.stereo_match(oL, oR, kl_o, dl_o, kr_o, dr_o, c["bf"], c["fx"])
+    assert np.array_equal(ur.view(np.uint32), ur_o.view(np.uint32))
+    assert np.array_equal(dp.view(np.uint32), dp_o.view(np.uint32))
+    assert np.count_nonzero(ur >= 0) > 100

@@ -14,6 +14,7 @@ HOST = os.path.join(ROOT, "orb_slam2_commit_b200", "host")
 MAIN = textwrap.dedent(r"""
     #include "ORBextractor.h"
     #include "HammingTop2.h"
+    #include "StereoMatch.h"
     #include <cstdio>
     int main() {
         ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 20, 7);
