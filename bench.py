@@ -341,6 +341,22 @@ def main():
     e2e_fps = world * B * e2e_steps / e2e_s
     assert int(nkp_np.sum()) == int(nkp.sum()), "host path and device path disagree"
 
+    # ---- single-frame latency through orbx_extract (what a SLAM front-end sees: one frame in, keypoints out)
+    lat_ms = None
+    if rank == 0:
+        ex1 = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"], device=local)
+        cap1 = ex1.reserve(W, H, 1)
+        k1 = h_kps.numpy().view(api.KP_DTYPE).reshape(-1)[:cap1].reshape(1, cap1)
+        d1 = desc_np.reshape(-1, 32)[:cap1].reshape(1, cap1, 32)
+        n1 = nkp_np[:1]
+        for _ in range(20):
+            ex1.extract_host(hb[:1], k1, d1, n1)
+        t0 = time.perf_counter()
+        for i in range(200):
+            ex1.extract_host(hb[i % B:i % B + 1], k1, d1, n1)
+        lat_ms = (time.perf_counter() - t0) / 200 * 1e3
+        del ex1
+
     # ---- config 4 across ranks: train set sharded, per-query top-2 merged after an NCCL all-gather (all ranks take part)
     hamming_sharded = None
     if world > 1 and not args.no_hamming:
@@ -395,6 +411,7 @@ def main():
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
                         "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": "orbx_extract_batch (pinned host buffers)"},
+                "latency_single_frame_ms": lat_ms,
                 "roofline": roofline, "stages": stages,
                 "pipeline": {"keypoints_per_frame": nkp_mean, "keypoints_per_s": frames_per_s * nkp_mean,
                              "algorithmic_bytes_per_frame_survey": ab["B_survey"],
