@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
         }
         __syncwarp();
         // 1. quick test on every pixel. Every arc of 9 contiguous ring pixels holds two ADJACENT compass pixels
-        //    (ring 0,4,8,12), so a dark arc needs max over adjacent pairs of min(d_a, d_b) > T and a bright arc
-        //    needs min over adjacent pairs of max(d_a, d_b) < -T. Row-major list entry = py<<7 | px.
+        //    (ring 0,4,8,12), so a dark (bright) arc needs an adjacent compass pair that is dark (bright).
+        //    Row-major list entry = py<<7 | px.
         int cnt = 0;
         const unsigned lt_mask = (1u << lane) - 1;
         {
@@ -144,22 +144,26 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
 #pragma unroll 4
                 for (int py = 0; py < nlo; py++) {
                     const uint8_t* qp = col + py * tp;
-                    const int v = qp[0];
-                    const int d0 = v - qp[3 * tp], d4 = v - qp[3], d8 = v - qp[-3 * tp], d12 = v - qp[-3];
-                    const int dk = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));
-                    const int br = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));
-                    acc = __funnelshift_l((unsigned)((T - dk) | (br + T)), acc, 1);
+                    const int v = qp[0], lo = v - T, hi = v + T;
+                    const int r0 = qp[3 * tp], r4 = qp[3], r8 = qp[-3 * tp], r12 = qp[-3];
+                    // sign bit of (r - lo): ring pixel darker than v - T; of (hi - r): brighter than v + T.
+                    // (D0&D4)|(D4&D8)|(D8&D12)|(D12&D0) == (D4|D12)&(D0|D8): plain bitwise logic on the sign bits
+                    const int dk = ((r4 - lo) | (r12 - lo)) & ((r0 - lo) | (r8 - lo));
+                    const int br = ((hi - r4) | (hi - r12)) & ((hi - r0) | (hi - r8));
+                    acc = __funnelshift_l((unsigned)(dk | br), acc, 1);
                 }
                 q[ch][0] = px < ew ? acc : 0u;
                 acc = 0;
 #pragma unroll 4
                 for (int py = 32; py < eh; py++) {
                     const uint8_t* qp = col + py * tp;
-                    const int v = qp[0];
-                    const int d0 = v - qp[3 * tp], d4 = v - qp[3], d8 = v - qp[-3 * tp], d12 = v - qp[-3];
-                    const int dk = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));
-                    const int br = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));
-                    acc = __funnelshift_l((unsigned)((T - dk) | (br + T)), acc, 1);
+                    const int v = qp[0], lo = v - T, hi = v + T;
+                    const int r0 = qp[3 * tp], r4 = qp[3], r8 = qp[-3 * tp], r12 = qp[-3];
+                    // sign bit of (r - lo): ring pixel darker than v - T; of (hi - r): brighter than v + T.
+                    // (D0&D4)|(D4&D8)|(D8&D12)|(D12&D0) == (D4|D12)&(D0|D8): plain bitwise logic on the sign bits
+                    const int dk = ((r4 - lo) | (r12 - lo)) & ((r0 - lo) | (r8 - lo));
+                    const int br = ((hi - r4) | (hi - r12)) & ((hi - r0) | (hi - r8));
+                    acc = __funnelshift_l((unsigned)(dk | br), acc, 1);
                 }
                 q[ch][1] = px < ew ? acc : 0u;
             }
