@@ -167,22 +167,31 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
                 }
                 q[ch][1] = px < ew ? acc : 0u;
             }
-            // row-major list of the pixels that passed: entry = py<<7 | px
-            for (int py = 0; py < eh; py++) {
-                const int half = py >> 5;
-                const int sh_bit = half ? nhi - 1 - (py - 32) : nlo - 1 - py;
-#pragma unroll
-                for (int ch = 0; ch < 2; ch++) {
-                    if (ch * 32 >= ew) break;
-                    const unsigned bit = ((half ? q[ch][1] : q[ch][0]) >> sh_bit) & 1u;
-                    const unsigned m = __ballot_sync(0xffffffffu, bit);
-                    if (bit) {
-                        const int pos = cnt + __popc(m & lt_mask);
-                        if (pos < cfg.list_cap) list[pos] = (unsigned short)((py << 7) | (ch * 32 + lane));
+            // Row-major list of the pixels that passed (entry = py<<7 | px). The per-lane COLUMN masks are transposed
+            // into per-lane ROW masks with independent ballots (no serial dependency), row offsets come from one warp
+            // scan, then every lane writes the entries of its own row.
+            auto emit_rows = [&](const unsigned qa, const unsigned qb, const int nrows, const int rowbase) {
+                unsigned rm0 = 0, rm1 = 0;
+                for (int r = 0; r < nrows; r++) {
+                    const unsigned m0 = __ballot_sync(0xffffffffu, (qa >> (nrows - 1 - r)) & 1u);
+                    if (lane == r) rm0 = m0;
+                    if (ew > 32) {                               // warp-uniform
+                        const unsigned m1 = __ballot_sync(0xffffffffu, (qb >> (nrows - 1 - r)) & 1u);
+                        if (lane == r) rm1 = m1;
                     }
-                    cnt += __popc(m);
                 }
-            }
+                const int c = __popc(rm0) + __popc(rm1);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                int off = cnt + incl - c;
+                const int ebase = (rowbase + lane) << 7;
+                for (unsigned m = rm0; m; m &= m - 1) { if (off < cfg.list_cap) list[off] = (unsigned short)(ebase | (__ffs(m) - 1)); off++; }
+                for (unsigned m = rm1; m; m &= m - 1) { if (off < cfg.list_cap) list[off] = (unsigned short)(ebase | (32 + __ffs(m) - 1)); off++; }
+                cnt += __shfl_sync(0xffffffffu, incl, 31);
+            };
+            emit_rows(q[0][0], q[1][0], nlo, 0);
+            if (nhi > 0) emit_rows(q[0][1], q[1][1], nhi, 32);
         }
         cnt = min(cnt, cfg.list_cap);
         __syncwarp();
