@@ -110,11 +110,11 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
 {
     __shared__ uint32_t s_raw[DESC_WARPS][PW * PWORDS + 4];   // +4: the last row's aligned window may over-read
     __shared__ unsigned short s_hb[DESC_WARPS][PW * HBP];
-    __shared__ uint32_t s_pat32[256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < 256; i += DESC_WARPS * 32) s_pat32[i] = g_pattern32[i];
-    __syncthreads();
-    const signed char* s_pat = reinterpret_cast<const signed char*>(s_pat32);
+    // this lane's 16 sample points (32 int8 = two 128-bit words), fetched first so the latency hides behind staging;
+    // no block-level barrier anywhere in this kernel
+    const uint4 pat_lo = __ldg(reinterpret_cast<const uint4*>(g_pattern32) + 2 * lane);
+    const uint4 pat_hi = __ldg(reinterpret_cast<const uint4*>(g_pattern32) + 2 * lane + 1);
     const int frame = blockIdx.y;
     const int ord = blockIdx.x * DESC_WARPS + wid;      // keypoint ordinal inside the frame (level-major)
     const int* cnt = L.lvl_kp_count + (size_t)frame * L.nlevels;
@@ -212,14 +212,15 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
     float a, b;
     dev_sincosf(__fmul_rn(angle, factorPI), &b, &a);
-    const signed char* pat = s_pat + 32 * lane;
+    const uint32_t patw[8] = {pat_lo.x, pat_lo.y, pat_lo.z, pat_lo.w, pat_hi.x, pat_hi.y, pat_hi.z, pat_hi.w};
     int val = 0;
-#pragma unroll 2
+#pragma unroll
     for (int t = 0; t < 8; t++) {
+        const uint32_t w = patw[t];                    // (x0, y0, x1, y1) of test t as four int8
         int smp[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const float px = (float)pat[4 * t + 2 * e], py = (float)pat[4 * t + 2 * e + 1];
+            const float px = (float)(signed char)(w >> (16 * e)), py = (float)(signed char)(w >> (16 * e + 8));
             const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
             const unsigned short* h = hb + (iy + 18) * HBP + (ix + 18);
