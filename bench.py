@@ -379,8 +379,26 @@ def main():
         t = torch.tensor([h0.elapsed_time(h1) / reps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        hamming_sharded = {"workload": f"2048 queries x 1,000,000 train rows sharded over {world} GPUs, NCCL all-gather of 8 B/query/rank + merge",
-                           "ms": ms, "matches_per_s": nq / (ms * 1e-3), "pair_distances_per_s": nq * nt / (ms * 1e-3)}
+        # same workload with the exchange fused into the matcher (peer stores over NVLink + arrival counters, no NCCL call)
+        pm = od.PeerHammingMatcher(nq)
+        for _ in range(3):
+            pm(query, shard, a)
+        barrier()
+        h0.record()
+        for _ in range(reps):
+            pm(query, shard, a)
+        h1.record(); torch.cuda.synchronize()
+        t = torch.tensor([h0.elapsed_time(h1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_fused = float(t.item())
+        same = all(bool(torch.equal(x, y)) for x, y in zip(pm(query, shard, a), od.hamming_top2_sharded(query, shard, a)))
+        peer_ok = int(pm.status.item()) == 0 and same
+        barrier()
+        pm.close()
+        hamming_sharded = {"workload": f"2048 queries x 1,000,000 train rows sharded over {world} GPUs",
+                           "nccl_allgather_merge": {"ms": ms, "matches_per_s": nq / (ms * 1e-3), "pair_distances_per_s": nq * nt / (ms * 1e-3)},
+                           "fused_peer_stores": {"ms": ms_fused, "matches_per_s": nq / (ms_fused * 1e-3),
+                                                 "pair_distances_per_s": nq * nt / (ms_fused * 1e-3), "equal_to_nccl_path": peer_ok}}
 
     if rank == 0:
         peaks = {"hbm_gbs": 6650.0, "source": "fallback"}

@@ -138,6 +138,23 @@ int orbx_stereo_hamming(const OrbxKeyPoint* kp_left, const uint8_t* desc_left, i
                         int rows, const float* scale_factors, int nlevels, float minD, float maxD,
                         int32_t* best_idx_r, int32_t* best_dist, int device);
 
+/* ---- Train-sharded matching across GPUs with the exchange FUSED into the matcher (no NCCL call): the last CTA of
+ *      every query tile stores the rank's merged top-2 straight into every peer's landing buffer over NVLink
+ *      (CUDA IPC peer mappings) and bumps the peers' arrival counters; a one-block kernel waits for the counters
+ *      (bounded) and merges. One process per GPU; all ranks call in the same order.
+ *      Setup: orbx_peer_create on every rank -> exchange the 64-byte handles by any host channel (e.g.
+ *      torch.distributed.all_gather_object) -> orbx_peer_connect with all `world` handles in rank order.
+ *      d_status (device int, may be NULL) is set to 1 if a peer never arrived within the bounded wait. ---- */
+typedef struct orbx_peer_matcher orbx_peer_matcher;
+#define ORBX_IPC_HANDLE_BYTES 64
+int orbx_peer_create(int nq_max, int world, int rank, int device, orbx_peer_matcher** out,
+                     uint8_t handle_out[ORBX_IPC_HANDLE_BYTES]);
+int orbx_peer_connect(orbx_peer_matcher* m, const uint8_t* all_handles /* world x 64 bytes, rank order */);
+int orbx_peer_hamming_top2(orbx_peer_matcher* m, const uint8_t* d_query, int nq, const uint8_t* d_train_shard, int nt,
+                           int64_t index_base, int32_t* d_idx1, int32_t* d_dist1, int32_t* d_dist2, int32_t* d_status,
+                           void* cuda_stream);
+void orbx_peer_destroy(orbx_peer_matcher* m);
+
 /* ---- Frame::ComputeStereoMatches, complete (Frame.cc:547-788): row-band Hamming as above, then the 11x11 SAD of
  *      centre-normalised windows slid over +-5 columns on the level pyramids of BOTH extractors (left / right must
  *      have just extracted the left / right image of the pair, same geometry, same device — their pyramids are read

@@ -81,6 +81,11 @@ def lib():
                                           C.c_float, C.c_float, i32p, i32p, C.c_int]
         L.orbx_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
                                         C.c_float, C.c_float, f32p, f32p]
+        L.orbx_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
+        L.orbx_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
+        L.orbx_peer_hamming_top2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_peer_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

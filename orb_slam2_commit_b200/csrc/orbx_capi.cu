@@ -734,3 +734,98 @@ extern "C" int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, co
     }
     return ORBX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ fused peer exchange
+struct orbx_peer_matcher {
+    int nq_max = 0, world = 0, rank = 0, device = 0;
+    uint8_t* local = nullptr;                      // [2 epochs][world][nq_max] u64 landing buffer, then the arrival counter
+    size_t parts_bytes = 0;                        // bytes of ONE epoch's landing buffer
+    uint8_t* peer_base[ORBX_MAX_PEERS] = {};       // mapped bases of every rank's `local` (own entry = local)
+    bool opened[ORBX_MAX_PEERS] = {};
+    uint64_t* d_packed = nullptr;                  // local slice-merge target
+    unsigned* d_tile_done = nullptr;
+    unsigned long long epoch = 0, expected = 0;    // calls so far; arrivals expected so far (world x query tiles per call)
+    bool connected = false;
+};
+
+extern "C" int orbx_peer_create(int nq_max, int world, int rank, int device, orbx_peer_matcher** out, uint8_t* handle_out)
+{
+    if (!out || !handle_out || nq_max <= 0 || world < 1 || world > ORBX_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(ORBX_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    orbx_peer_matcher* m = new orbx_peer_matcher();
+    m->nq_max = nq_max; m->world = world; m->rank = rank; m->device = device;
+    m->parts_bytes = ((size_t)world * nq_max * 8 + 255) & ~(size_t)255;
+    const size_t total = 2 * m->parts_bytes + 256;
+    cudaError_t e = cudaMalloc(&m->local, total);           // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    if (e == cudaSuccess) e = cudaMemset(m->local, 0, total);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_packed, (size_t)nq_max * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_tile_done, 4096);
+    if (e == cudaSuccess) e = cudaMemset(m->d_tile_done, 0, 4096);
+    cudaIpcMemHandle_t hnd;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hnd, m->local);
+    if (e != cudaSuccess) { orbx_peer_destroy(m); return fail(ORBX_ERR_CUDA, cudaGetErrorString(e)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == ORBX_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle_out, &hnd, ORBX_IPC_HANDLE_BYTES);
+    CK(cudaDeviceSynchronize());
+    *out = m;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_peer_connect(orbx_peer_matcher* m, const uint8_t* all_handles)
+{
+    if (!m || !all_handles) return fail(ORBX_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(m->device));
+    for (int p = 0; p < m->world; p++) {
+        if (p == m->rank) { m->peer_base[p] = m->local; continue; }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, all_handles + (size_t)p * ORBX_IPC_HANDLE_BYTES, ORBX_IPC_HANDLE_BYTES);
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+        m->peer_base[p] = (uint8_t*)ptr; m->opened[p] = true;
+    }
+    m->connected = true;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_peer_hamming_top2(orbx_peer_matcher* m, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
+                                      int64_t index_base, int32_t* d_idx1, int32_t* d_dist1, int32_t* d_dist2,
+                                      int32_t* d_status, void* cuda_stream)
+{
+    if (!m || !m->connected) return fail(ORBX_ERR_STATE, "orbx_peer_connect has not run");
+    if (nq <= 0 || nq > m->nq_max || nt < 0 || !d_query || (nt > 0 && !d_train)) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_hamming_qtiles(nq) > 1024) return fail(ORBX_ERR_UNSUPPORTED, "too many query tiles");
+    CK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int slot = (int)(m->epoch & 1);          // landing buffers alternate per call
+    OrbxHtPeer peer{};
+    peer.world = m->world; peer.rank = m->rank; peer.nq_max = m->nq_max;
+    for (int p = 0; p < m->world; p++) {
+        peer.parts[p] = (unsigned long long*)(m->peer_base[p] + (size_t)slot * m->parts_bytes);
+        peer.arrive[p] = (unsigned*)(m->peer_base[p] + 2 * m->parts_bytes);
+    }
+    peer.tile_done = m->d_tile_done;
+    orbx_launch_hamming_init(m->d_packed, nq, st);
+    orbx_launch_hamming_top2_peer(d_query, nq, d_train, nt, index_base, m->d_packed, peer, st);
+    m->epoch++;
+    m->expected += (unsigned long long)m->world * (unsigned long long)orbx_hamming_qtiles(nq);
+    const unsigned target = (unsigned)m->expected;   // the counter is compared modulo 2^32
+    orbx_launch_hamming_wait_merge((const uint64_t*)(m->local + (size_t)slot * m->parts_bytes),
+                                   (const unsigned*)(m->local + 2 * m->parts_bytes), target, m->world, nq, m->nq_max,
+                                   d_idx1, d_dist1, d_dist2, d_status, st);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" void orbx_peer_destroy(orbx_peer_matcher* m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < m->world; p++) if (m->opened[p]) cudaIpcCloseMemHandle(m->peer_base[p]);
+    cudaFree(m->local); cudaFree(m->d_packed); cudaFree(m->d_tile_done);
+    cudaGetLastError();
+    delete m;
+}

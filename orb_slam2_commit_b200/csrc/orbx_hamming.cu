@@ -11,6 +11,7 @@
 // one packed word per query; the same merge rule joins the per-GPU results after the NCCL all-gather.
 // This kernel is bound by the integer/popc pipes, not by HBM (32 B per train row are reused by every query).
 #include "orbx_internal.cuh"
+#include <algorithm>
 
 #define HT_THREADS 256
 #define HT_QPT 2                 // queries per thread
@@ -49,9 +50,11 @@ __device__ __forceinline__ int ht_dist(const uint4 qa, const uint4 qb, const uin
 __global__ void __launch_bounds__(HT_THREADS) hamming_top2_kernel(const uint4* __restrict__ q, int nq,
                                                                   const uint4* __restrict__ t, int nt, int slice,
                                                                   long long index_base,
-                                                                  unsigned long long* __restrict__ packed)
+                                                                  unsigned long long* __restrict__ packed,
+                                                                  const OrbxHtPeer peer)
 {
     __shared__ uint4 s_t[2][HT_TILE * 2];
+    __shared__ int s_last;
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * slice;                       // this CTA's train slice [t0, t1)
     const int t1 = min(nt, t0 + slice);
@@ -121,6 +124,62 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_top2_kernel(const uint4* _
             old = prev;
         }
     }
+    // ---- fused exchange (multi-GPU): the LAST slice-CTA of a query tile pushes the tile's merged local result into
+    // every peer's landing buffer with plain 64-bit stores over NVLink and then bumps the peers' arrival counters.
+    // This replaces all-gather + a separate collective launch; peers merge after their counter reaches the target.
+    if (peer.world > 0) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&peer.tile_done[blockIdx.y], 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+#pragma unroll
+            for (int k = 0; k < HT_QPT; k++) {
+                const int qi = qbase + k * HT_THREADS + tid;
+                if (qi >= nq) continue;
+                const unsigned long long v = __ldcg(&packed[qi]);
+                for (int p = 0; p < peer.world; p++) peer.parts[p][(size_t)peer.rank * peer.nq_max + qi] = v;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                peer.tile_done[blockIdx.y] = 0;
+                for (int p = 0; p < peer.world; p++) atomicAdd_system(peer.arrive[p], 1u);
+            }
+        }
+    }
+}
+
+// Waits (bounded) until every rank's every query tile has landed, then merges the world partial results.
+__global__ void __launch_bounds__(1024) hamming_wait_merge_kernel(const unsigned long long* parts, const unsigned* arrive,
+                                                                  unsigned target, int world, int nq, int nq_max,
+                                                                  int* __restrict__ idx, int* __restrict__ d1,
+                                                                  int* __restrict__ d2, int* __restrict__ status)
+{
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        int ok = 1;
+        // wrap-safe compare; ~4 s at 2 GHz is far beyond any legitimate wait and keeps a lost peer from hanging the GPU
+        while ((int)(*reinterpret_cast<const volatile unsigned*>(arrive) - target) < 0) {
+            if (clock64() - t0 > 8000000000LL) { ok = 0; break; }
+            __nanosleep(500);
+        }
+        __threadfence_system();
+        s_ok = ok;
+        if (status) *status = ok ? 0 : 1;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+        unsigned long long acc = ht_pack(256, 256, 0xffffffffu);
+        for (int p = 0; p < world; p++) acc = ht_merge(acc, __ldcv(&parts[(size_t)p * nq_max + i]));
+        const int b = (int)(acc >> 48);
+        if (idx) idx[i] = b >= 256 ? -1 : (int)(unsigned)acc;
+        if (d1) d1[i] = b;
+        if (d2) d2[i] = (int)((acc >> 32) & 0xffff);
+    }
 }
 
 __global__ void hamming_merge_kernel(const unsigned long long* __restrict__ parts, int nparts, int nq,
@@ -141,21 +200,39 @@ void orbx_launch_hamming_init(uint64_t* d_packed, int nq, cudaStream_t st)
     if (nq > 0) hamming_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(d_packed), nq);
 }
 
+int orbx_hamming_qtiles(int nq) { return (nq + HT_THREADS * HT_QPT - 1) / (HT_THREADS * HT_QPT); }
+
+void orbx_launch_hamming_top2_peer(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, long long index_base,
+                                   uint64_t* d_packed, const OrbxHtPeer& peer, cudaStream_t st)
+{
+    if (nq <= 0) return;
+    const int qtiles = orbx_hamming_qtiles(nq);
+    // size the grid to ~4 waves of 148 SMs x 2 resident CTAs, slices a multiple of the tile
+    int want = (148 * 2 * 4 + qtiles - 1) / qtiles;
+    int slice = (std::max(nt, 1) + want - 1) / want;
+    slice = ((slice + HT_TILE - 1) / HT_TILE) * HT_TILE;
+    if (slice > HT_SLICE_MAX) slice = HT_SLICE_MAX;
+    const int nslices = std::max(1, (nt + slice - 1) / slice);      // an empty shard still has to signal its peers
+    dim3 grid(nslices, qtiles);
+    hamming_top2_kernel<<<grid, HT_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(d_q), nq,
+                                                     reinterpret_cast<const uint4*>(d_t), nt, slice, index_base,
+                                                     reinterpret_cast<unsigned long long*>(d_packed), peer);
+}
+
 void orbx_launch_hamming_top2(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, long long index_base,
                               uint64_t* d_packed, cudaStream_t st)
 {
     if (nq <= 0 || nt <= 0) return;
-    const int qtiles = (nq + HT_THREADS * HT_QPT - 1) / (HT_THREADS * HT_QPT);
-    // size the grid to ~4 waves of 148 SMs x 2 resident CTAs, slices a multiple of the tile
-    int want = (148 * 2 * 4 + qtiles - 1) / qtiles;
-    int slice = (nt + want - 1) / want;
-    slice = ((slice + HT_TILE - 1) / HT_TILE) * HT_TILE;
-    if (slice > HT_SLICE_MAX) slice = HT_SLICE_MAX;
-    const int nslices = (nt + slice - 1) / slice;
-    dim3 grid(nslices, qtiles);
-    hamming_top2_kernel<<<grid, HT_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(d_q), nq,
-                                                     reinterpret_cast<const uint4*>(d_t), nt, slice, index_base,
-                                                     reinterpret_cast<unsigned long long*>(d_packed));
+    OrbxHtPeer none{};
+    orbx_launch_hamming_top2_peer(d_q, nq, d_t, nt, index_base, d_packed, none, st);
+}
+
+void orbx_launch_hamming_wait_merge(const uint64_t* d_parts_local, const unsigned* d_arrive_local, unsigned target,
+                                    int world, int nq, int nq_max, int* d_idx, int* d_d1, int* d_d2, int* d_status,
+                                    cudaStream_t st)
+{
+    hamming_wait_merge_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_parts_local), d_arrive_local,
+                                                  target, world, nq, nq_max, d_idx, d_d1, d_d2, d_status);
 }
 
 void orbx_launch_hamming_merge(const uint64_t* d_parts, int nparts, int nq, int* d_idx, int* d_d1, int* d_d2,

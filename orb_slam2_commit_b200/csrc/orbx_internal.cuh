@@ -83,7 +83,20 @@ void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps
                           int* d_nkp, cudaStream_t st);
 void orbx_upload_constants();  // pattern + umax tables
 
+#define ORBX_MAX_PEERS 16
+struct OrbxHtPeer {            // fused exchange of the per-rank top-2 over NVLink peer memory (no NCCL call)
+    int world, rank, nq_max;
+    unsigned long long* parts[ORBX_MAX_PEERS];   // peer p's landing buffer for the current epoch: [world][nq_max]
+    unsigned* arrive[ORBX_MAX_PEERS];            // peer p's arrival counter
+    unsigned* tile_done;                         // local: one counter per query tile
+};
 void orbx_launch_hamming_init(uint64_t* d_packed, int nq, cudaStream_t st);
+void orbx_launch_hamming_top2_peer(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, long long index_base,
+                                   uint64_t* d_packed, const OrbxHtPeer& peer, cudaStream_t st);
+int orbx_hamming_qtiles(int nq);
+void orbx_launch_hamming_wait_merge(const uint64_t* d_parts_local, const unsigned* d_arrive_local, unsigned target,
+                                    int world, int nq, int nq_max, int* d_idx, int* d_d1, int* d_d2, int* d_status,
+                                    cudaStream_t st);
 void orbx_launch_hamming_top2(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, long long index_base,
                               uint64_t* d_packed, cudaStream_t st);
 void orbx_launch_hamming_merge(const uint64_t* d_parts, int nparts, int nq, int* d_idx, int* d_d1, int* d_d2,

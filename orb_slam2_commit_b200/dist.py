@@ -65,3 +65,43 @@ def hamming_top2_sharded(d_query, d_train_shard, index_base: int, group=None):
     api._ck(L.orbx_hamming_merge_device(parts.data_ptr(), parts.shape[0], nq, out[0].data_ptr(), out[1].data_ptr(),
                                         out[2].data_ptr(), st))
     return out[0], out[1], out[2]
+
+
+class PeerHammingMatcher:
+    """Config 4 with the exchange fused into the matcher kernel (orbx_peer_* in include/orbx.h): the last CTA of every
+    query tile stores the rank's top-2 into every peer's landing buffer over NVLink and bumps the peers' arrival
+    counters; a one-block kernel waits (bounded) and merges. torch.distributed is used ONCE, at construction, to
+    exchange the CUDA-IPC handles; the data path itself makes no NCCL call."""
+
+    def __init__(self, nq_max: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import api
+        self.api, self.L = api, api.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.cuda.current_device()
+        self.nq_max = nq_max
+        self.h = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        api._ck(self.L.orbx_peer_create(nq_max, self.world, self.rank, self.device, C.byref(self.h), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        api._ck(self.L.orbx_peer_connect(self.h, b"".join(handles)))
+        self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        dist.barrier(group)                      # every rank has mapped every landing buffer before the first store
+
+    def __call__(self, d_query, d_train_shard, index_base: int):
+        import torch
+        nq, nt = d_query.shape[0], d_train_shard.shape[0]
+        out = torch.empty((3, nq), dtype=torch.int32, device=d_query.device)
+        st = torch.cuda.current_stream().cuda_stream
+        self.api._ck(self.L.orbx_peer_hamming_top2(self.h, d_query.data_ptr(), nq, d_train_shard.data_ptr() if nt else 0, nt,
+                                                   index_base, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                   self.status.data_ptr(), st))
+        return out[0], out[1], out[2]
+
+    def close(self):
+        if self.h:
+            self.L.orbx_peer_destroy(self.h)
+            self.h = None
