@@ -249,10 +249,17 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
     if (width <= 0 || height <= 0 || max_batch <= 0) return fail(ORBX_ERR_INVALID, "width, height, max_batch must be positive");
     if (width == h->W && height == h->H && max_batch <= h->max_batch) return ORBX_OK;
+    // geometry is pure host arithmetic: reject what the reference cannot run before touching the device
+    {
+        orbx_extractor probe = *h;          // tables only; device members of the copy are never used or freed
+        int rc0 = build_geometry(&probe, width, height);
+        if (rc0 != ORBX_OK) return rc0;
+    }
     if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
     CK(cudaSetDevice(h->device));
     if (!h->stream) CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < 2; j++) if (h->slot_stream[j]) CK(cudaStreamSynchronize(h->slot_stream[j]));
     release_device(h);
     int rc = build_geometry(h, width, height);
     if (rc != ORBX_OK) return rc;

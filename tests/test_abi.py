@@ -83,3 +83,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp", ".hpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "orb_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_geometry_the_reference_cannot_run_is_rejected():
+    """Portrait levels (nIni == 0, ORBextractor.cc:567), levels under 62 px (nCols == 0, :846), > 4096 px and
+    > 2040 features on one level return ORBX_ERR_UNSUPPORTED from pure host arithmetic (no device needed)."""
+    L = api.lib()
+    cases = [((500, 1.2, 2), 240, 640), ((500, 1.2, 8), 120, 100), ((500, 1.2, 2), 5000, 3000), ((60000, 1.2, 8), 640, 480)]
+    for (nf, sc, nl), w, h in cases:
+        e = ORBextractor(nf, sc, nl, 20, 7)
+        rc = L.orbx_reserve(e._h, w, h, 1)
+        assert rc == 2, (w, h, rc, L.orbx_last_error())
+    e = ORBextractor(500, 1.2, 8, 20, 7)
+    assert L.orbx_reserve(e._h, 0, 480, 1) == 1 and L.orbx_reserve(e._h, 640, 480, 0) == 1

@@ -285,3 +285,21 @@ def test_full_stereo_match_matches_oracle(name, seed):
     assert np.array_equal(ur.view(np.uint32), ur_o.view(np.uint32))
     assert np.array_equal(dp.view(np.uint32), dp_o.view(np.uint32))
     assert np.count_nonzero(ur >= 0) > 100
+
+
+def test_capacity_error_and_geometry_change_on_one_instance():
+    import ctypes as C
+    from orb_slam2_commit_b200 import api
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    a = synth.synth_image(640, 480, 71); b = synth.synth_image(752, 480, 72)
+    ka, da = ex(a); kb, db = ex(b); ka2, da2 = ex(a)          # the working set is re-reserved when the size changes
+    orc = ob.Extractor(1000, 1.2, 8, 20, 7)
+    _check_against(ka, da, *orc.extract(a), "640x480")
+    _check_against(kb, db, *orc.extract(b), "752x480")
+    assert ka2.tobytes() == ka.tobytes() and np.array_equal(da2, da)
+    # a caller buffer that is too small: status 3 (ORBX_ERR_CAPACITY), *nkp still reports the required size
+    L = api.lib(); n = C.c_int32(0)
+    kps = np.zeros(100, api.KP_DTYPE); desc = np.zeros((100, 32), np.uint8)
+    rc = L.orbx_extract(ex._h, a.ctypes.data_as(api.u8p), 640, 480, 640, kps.ctypes.data, 100, C.byref(n), desc.ctypes.data_as(api.u8p))
+    assert rc == 3 and n.value == len(ka)
+    assert kps.tobytes() == ka[:100].tobytes() and np.array_equal(desc, da[:100])
