@@ -29,8 +29,8 @@ from orb_slam2_commit_b200 import synth  # noqa: E402
 
 WORKLOADS = {
     # BASELINE.json metric is quoted on this one (configs[0] geometry, batched as in configs[2])
-    "tum1": dict(cfg="tum1", batch=512, distinct=32),
-    "euroc": dict(cfg="euroc", batch=512, distinct=32),
+    "tum1": dict(cfg="tum1", batch=1024, distinct=32),
+    "euroc": dict(cfg="euroc", batch=1024, distinct=32),
     "kitti": dict(cfg="kitti", batch=256, distinct=16),
     "4k": dict(cfg="4k", batch=8, distinct=4),
 }
