@@ -417,10 +417,26 @@ def main():
         dom = int(np.argmax(stage_ms))
         dom_bytes = ab[names[dom]] * B
         achieved = dom_bytes / (float(stage_ms[dom]) * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), scaled from the
+        # captured batch (128 frames per launch) to this run's frames per launch; None when no capture is present
+        traffic = None
+        try:
+            import csv as _csv
+            prof = os.path.join(ROOT, "profiles", "r01_ncu_full_batch128.csv")
+            key = {"pyramid": "pyr_resize_kernel", "fast": "fast_cells_kernel", "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]]
+            rows_ = list(_csv.reader(open(prof)))
+            hdr_ = rows_[0]
+            ir = [i for i, c_ in enumerate(hdr_) if c_.startswith("dram__bytes_read.sum")][0]
+            iw = [i for i, c_ in enumerate(hdr_) if c_.startswith("dram__bytes_write.sum")][0]
+            mb = sum(float(r_[ir]) + float(r_[iw]) for r_ in rows_[1:] if key in r_[0])
+            traffic = mb * 1e6 / 128.0 * B
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": {"pyramid": "pyr_level0_kernel+pyr_resize_kernel (one launch per level)", "fast": "fast_cells_kernel",
                                               "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]],
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                    "algorithmic_bytes_per_frame": ab[names[dom]], "frames_per_launch": B, "traffic": None,
+                    "algorithmic_bytes_per_frame": ab[names[dom]], "frames_per_launch": B, "traffic": traffic,
+                    "traffic_source": "profiles/r01_ncu_full_batch128.csv (dram read+write per frame x frames per launch)",
                     "stage_events_averaged_over_steps": nruns}
         launches_per_step = c["nlevels"] + 3
         line = {"metric": "orb_frames_per_s", "value": frames_per_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,

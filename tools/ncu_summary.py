@@ -15,7 +15,7 @@ def launches(path):
         if d.get("Metric Name") != "gpu__time_duration.sum": continue
         v = float(d["Metric Value"].replace(",", "")); u = d["Metric Unit"]
         v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
-        agg[d["Kernel Name"].split("(")[0]].append(v)
+        agg[d["Kernel Name"].split("(")[0].replace(",", ";").replace("void ", "")].append(v)
     tot = sum(sum(v) for v in agg.values())
     print("kernel,launches,total_us,mean_us,share")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -34,7 +34,7 @@ def full(path):
     cols = [c for c in WANT if c in hdr]
     print(",".join(["kernel"] + [f"{c} [{units[hdr.index(c)]}]" for c in cols]))
     for r in rows[2:]:
-        print(",".join([r[hdr.index("Kernel Name")].split("(")[0]] + [r[hdr.index(c)].replace(",", "") for c in cols]))
+        print(",".join([r[hdr.index("Kernel Name")].split("(")[0].replace(",", ";").replace("void ", "")] + [r[hdr.index(c)].replace(",", "") for c in cols]))
 
 if __name__ == "__main__":
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
