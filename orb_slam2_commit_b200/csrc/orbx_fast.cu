@@ -206,15 +206,20 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
                 e = list[k];
                 const uint8_t* c = tile + (((e >> 7) & 127) + 3) * tp + (e & 127) + 3;
                 const int lo = (int)c[0] - T, hi = (int)c[0] + T;   // dark: ring < lo ; bright: ring > hi
-                unsigned md = 0, mb = 0;
-                // funnel shift pulls the sign bit of (ring - lo) / (hi - ring) into the mask: 2 instructions per bit.
-                // (bit order ends up reversed, which a circular run-length test does not care about)
-#define RING_BIT(off) { const int r = c[off]; md = __funnelshift_l((unsigned)(r - lo), md, 1); mb = __funnelshift_l((unsigned)(hi - r), mb, 1); }
+                // Both compares of one ring pixel in ONE multiply-add (FMA pipe): r * 0xFFFF0001 puts r in the low half
+                // and -r in the high half; adding C = (hi + 0x8000) << 16 | (0x8000 - lo) leaves r - lo + 0x8000 below and
+                // hi - r + 0x8000 above, so bit 15 is clear iff r < lo (dark) and bit 31 is clear iff r > hi (bright);
+                // neither half can carry into the other. The two bits are rotated into a packed pair of 16-bit masks.
+                const unsigned C = ((unsigned)(hi + 0x8000) << 16) + (unsigned)(0x8000 - lo);
+                unsigned M = 0;
+#define RING_BIT(off) { const unsigned X = (unsigned)c[off] * 0xFFFF0001u + C; M = (M >> 1) | (X & 0x80008000u); }
                 RING_BIT(3 * tp)       RING_BIT(3 * tp + 1)   RING_BIT(2 * tp + 2)   RING_BIT(tp + 3)
                 RING_BIT(3)            RING_BIT(-tp + 3)      RING_BIT(-2 * tp + 2)  RING_BIT(-3 * tp + 1)
                 RING_BIT(-3 * tp)      RING_BIT(-3 * tp - 1)  RING_BIT(-2 * tp - 2)  RING_BIT(-tp - 3)
                 RING_BIT(-3)           RING_BIT(tp - 3)       RING_BIT(2 * tp - 2)   RING_BIT(3 * tp - 1)
 #undef RING_BIT
+                M = ~M;                                          // bit k: ring k dark ; bit 16+k: ring k bright
+                unsigned md = M & 0xffffu, mb = M >> 16;
                 md |= md << 16; mb |= mb << 16;
                 md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;   // bit i set <=> ring i..i+8 all dark
                 mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
