@@ -165,6 +165,15 @@ int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right,
                       const OrbxKeyPoint* kp_left, const uint8_t* desc_left, int n_left,
                       const OrbxKeyPoint* kp_right, const uint8_t* desc_right, int n_right,
                       float mbf, float fx, float* u_right, float* depth);
+/* Device-resident, batched form: `pairs` stereo pairs whose left / right frames were the frames 0..pairs-1 of the last
+ * orbx_extract_device call on `left` / `right`. Keypoints, descriptors and counts are those calls' device outputs
+ * ([pairs][cap] layout). d_u_right / d_depth: [pairs][cap] floats, entries i < nl[pair] are written. Asynchronous on
+ * cuda_stream (NULL = left's stream). No host table, no host sort: the row band test runs against all right
+ * keypoints of the pair in shared memory and the median cut is a radix select on the device. */
+int orbx_stereo_match_device(orbx_extractor* left, orbx_extractor* right, int pairs,
+                             const OrbxKeyPoint* d_kp_left, const uint8_t* d_desc_left, const int32_t* d_n_left,
+                             const OrbxKeyPoint* d_kp_right, const uint8_t* d_desc_right, const int32_t* d_n_right,
+                             int cap, float mbf, float fx, float* d_u_right, float* d_depth, void* cuda_stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

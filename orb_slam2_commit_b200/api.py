@@ -81,6 +81,8 @@ def lib():
                                           C.c_float, C.c_float, i32p, i32p, C.c_int]
         L.orbx_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
                                         C.c_float, C.c_float, f32p, f32p]
+        L.orbx_stereo_match_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
         L.orbx_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
         L.orbx_peer_hamming_top2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
@@ -271,6 +273,13 @@ def stereo_match(left: ORBextractor, right: ORBextractor, kp_left, desc_left, kp
     _ck(lib().orbx_stereo_match(left._h, right._h, kl.ctypes.data, _u8(dl), len(kl), kr.ctypes.data, _u8(dr), len(kr),
                                 mbf, fx, ur.ctypes.data_as(f32p), dp.ctypes.data_as(f32p)))
     return ur, dp
+
+
+def stereo_match_device(left: ORBextractor, right: ORBextractor, pairs, d_kl, d_dl, d_nl, d_kr, d_dr, d_nr, cap, mbf, fx,
+                        d_u_right, d_depth, stream=0):
+    """Batched device-resident Frame::ComputeStereoMatches (orbx_stereo_match_device); all d_* are device pointers."""
+    _ck(lib().orbx_stereo_match_device(left._h, right._h, pairs, d_kl, d_dl, d_nl, d_kr, d_dr, d_nr, cap, mbf, fx,
+                                       d_u_right, d_depth, stream))
 
 
 class ORBmatcher:

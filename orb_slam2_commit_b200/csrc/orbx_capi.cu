@@ -47,6 +47,7 @@ struct orbx_extractor {
     cudaStream_t stream = nullptr;
     cudaStream_t slot_stream[2] = {nullptr, nullptr};   // host-path double buffering (copy/compute overlap)
     int pyr_base = 0;                             // first working-set frame of the last pipeline run
+    void* stereo_scratch = nullptr; size_t stereo_scratch_bytes = 0;   // SAD per left keypoint (stereo matcher)
     int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
     bool constants_ready = false;
     bool timing = false;
@@ -115,6 +116,7 @@ static void release_device(orbx_extractor* h)
 {
     if (h->device >= 0 && (h->d_pool || h->stream)) cudaSetDevice(h->device);
     cudaFree(h->d_pool); h->d_pool = nullptr;
+    cudaFree(h->stereo_scratch); h->stereo_scratch = nullptr; h->stereo_scratch_bytes = 0;
     cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps);
     h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr;
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
@@ -650,7 +652,50 @@ extern "C" int orbx_stereo_hamming(const OrbxKeyPoint* kl, const uint8_t* dl, in
 }
 
 // ------------------------------------------------------------------------------------------------ full stereo
-#include <algorithm>
+static int stereo_check_pair(orbx_extractor* left, orbx_extractor* right, int pairs)
+{
+    if (left->last_frames < pairs || right->last_frames < pairs)
+        return fail(ORBX_ERR_STATE, "both extractors must have extracted the pair(s) first");
+    if (left->device != right->device || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels ||
+        left->scale_factor != right->scale_factor)
+        return fail(ORBX_ERR_INVALID, "left and right extractors must share device, image size and pyramid settings");
+    return ORBX_OK;
+}
+
+extern "C" int orbx_stereo_match_device(orbx_extractor* left, orbx_extractor* right, int pairs,
+                                        const OrbxKeyPoint* d_kl, const uint8_t* d_dl, const int32_t* d_nl,
+                                        const OrbxKeyPoint* d_kr, const uint8_t* d_dr, const int32_t* d_nr, int cap,
+                                        float mbf, float fx, float* d_u_right, float* d_depth, void* cuda_stream)
+{
+    if (!left || !right || pairs <= 0 || cap <= 0 || !d_kl || !d_dl || !d_nl || !d_kr || !d_dr || !d_nr || !d_u_right || !d_depth)
+        return fail(ORBX_ERR_INVALID, "bad argument");
+    if (cap > 18000) return fail(ORBX_ERR_UNSUPPORTED, "more than 18000 keypoints per image");
+    int rc = stereo_check_pair(left, right, pairs);
+    if (rc != ORBX_OK) return rc;
+    CK(cudaSetDevice(left->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : left->stream;
+    const size_t need = (size_t)pairs * cap * sizeof(int);
+    if (need > left->stereo_scratch_bytes) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(left->stereo_scratch); left->stereo_scratch = nullptr; left->stereo_scratch_bytes = 0;
+        CK(cudaMalloc(&left->stereo_scratch, need));
+        left->stereo_scratch_bytes = need;
+    }
+    const float mb = mbf / fx;                      // Frame.cc:120
+    OrbxStereoBatch a;
+    a.kl = (const OrbxKp28*)d_kl; a.dl = d_dl; a.nl = d_nl; a.kr = (const OrbxKp28*)d_kr; a.dr = d_dr; a.nr = d_nr;
+    a.cap = cap; a.pairs = pairs; a.rows = left->lvl[0].h;
+    a.raw_left = left->L.raw + (size_t)left->pyr_base * left->L.frame_raw_bytes;
+    a.raw_right = right->L.raw + (size_t)right->pyr_base * right->L.frame_raw_bytes;
+    a.frame_raw_bytes = left->L.frame_raw_bytes;
+    a.lvl = left->d_lvl;
+    a.minD = 0.f; a.maxD = mbf / mb; a.mbf = mbf;  // Frame.cc:592-595
+    a.u_right = d_u_right; a.depth = d_depth; a.sad = (int*)left->stereo_scratch;
+    orbx_launch_stereo_batch(a, st);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
 extern "C" int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, const OrbxKeyPoint* kl, const uint8_t* dl,
                                  int nl, const OrbxKeyPoint* kr, const uint8_t* dr, int nr, float mbf, float fx,
                                  float* u_right, float* depth)
@@ -659,86 +704,40 @@ extern "C" int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, co
         return fail(ORBX_ERR_INVALID, "bad argument");
     for (int i = 0; i < nl; i++) { u_right[i] = -1.0f; depth[i] = -1.0f; }
     if (nl == 0) return ORBX_OK;
-    if (left->last_frames <= 0 || right->last_frames <= 0) return fail(ORBX_ERR_STATE, "both extractors must have extracted the pair first");
-    if (left->device != right->device || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels ||
-        left->scale_factor != right->scale_factor)
-        return fail(ORBX_ERR_INVALID, "left and right extractors must share device, image size and pyramid settings");
+    int rc = stereo_check_pair(left, right, 1);
+    if (rc != ORBX_OK) return rc;
+    for (int i = 0; i < nl; i++) if (kl[i].octave < 0 || kl[i].octave >= left->nlevels) return fail(ORBX_ERR_INVALID, "left keypoint octave out of range");
+    for (int i = 0; i < nr; i++) if (kr[i].octave < 0 || kr[i].octave >= left->nlevels) return fail(ORBX_ERR_INVALID, "right keypoint octave out of range");
     CK(cudaSetDevice(left->device));
     CK(cudaStreamSynchronize(left->stream));
     CK(cudaStreamSynchronize(right->stream));
-    const int rows = left->lvl[0].h, nlevels = left->nlevels;
-    const float mb = mbf / fx;                      // Frame.cc:120
-    const float minD = 0.f, maxD = mbf / mb;        // Frame.cc:592-595
-    // vRowIndices (Frame.cc:564-590) as CSR, ascending iR inside every row
-    std::vector<int> start(rows + 1, 0), lo(nr), hi(nr);
-    for (int i = 0; i < nr; i++) {
-        if (kr[i].octave < 0 || kr[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "right keypoint octave out of range");
-        const float r = 2.0f * left->sf[kr[i].octave];
-        hi[i] = std::min((int)ceilf(kr[i].y + r), rows - 1);
-        lo[i] = std::max((int)floorf(kr[i].y - r), 0);
-        for (int y = lo[i]; y <= hi[i]; y++) start[y + 1]++;
-    }
-    for (int y = 0; y < rows; y++) start[y + 1] += start[y];
-    std::vector<int> tab(std::max(start[rows], 1)), fill(rows, 0);
-    for (int i = 0; i < nr; i++)
-        for (int y = lo[i]; y <= hi[i]; y++) tab[start[y] + fill[y]++] = i;
-    for (int i = 0; i < nl; i++)
-        if (kl[i].octave < 0 || kl[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "left keypoint octave out of range");
+    const int cap = std::max(std::max(nl, nr), 1);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t b_kl = (size_t)nl * 28, b_dl = (size_t)nl * 32, b_kr = (size_t)std::max(nr, 1) * 28, b_dr = (size_t)std::max(nr, 1) * 32;
-    const size_t b_st = (size_t)(rows + 1) * 4, b_tab = tab.size() * 4, b_out = (size_t)nl * 12;
-    void* pool = nullptr;
-    CK(cudaMalloc(&pool, al(b_kl) + al(b_dl) + al(b_kr) + al(b_dr) + al(b_st) + al(b_tab) + al(b_out)));
-    uint8_t* p = (uint8_t*)pool;
-    uint8_t *p_kl = p; p += al(b_kl);
-    uint8_t *p_dl = p; p += al(b_dl);
-    uint8_t *p_kr = p; p += al(b_kr);
-    uint8_t *p_dr = p; p += al(b_dr);
-    uint8_t *p_st = p; p += al(b_st);
-    uint8_t *p_tab = p; p += al(b_tab);
-    uint8_t *p_out = p;
-    std::vector<float> h_u(nl), h_d(nl);
-    std::vector<int> h_sad(nl);
-    int rc = ORBX_OK;
+    const size_t b_k = al((size_t)cap * 28), b_d = al((size_t)cap * 32), b_f = al((size_t)cap * 4);
+    uint8_t* pool = nullptr;
+    CK(cudaMalloc(&pool, 2 * b_k + 2 * b_d + 2 * b_f + 256));
+    uint8_t *p_kl = pool, *p_kr = pool + b_k, *p_dl = pool + 2 * b_k, *p_dr = pool + 2 * b_k + b_d;
+    uint8_t *p_u = pool + 2 * b_k + 2 * b_d, *p_dp = p_u + b_f, *p_n = p_dp + b_f;
+    const int counts[2] = {nl, nr};
+    int out = ORBX_OK;
     cudaError_t e;
     do {
-        if ((e = cudaMemcpy(p_kl, kl, b_kl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        if ((e = cudaMemcpy(p_dl, dl, b_dl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_kl, kl, (size_t)nl * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_dl, dl, (size_t)nl * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if (nr > 0 && (e = cudaMemcpy(p_kr, kr, (size_t)nr * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if (nr > 0 && (e = cudaMemcpy(p_dr, dr, (size_t)nr * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        if ((e = cudaMemcpy(p_st, start.data(), b_st, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        if ((e = cudaMemcpy(p_tab, tab.data(), b_tab, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        OrbxStereoArgs a;
-        a.kl = (const OrbxKp28*)p_kl; a.dl = p_dl; a.nl = nl; a.kr = (const OrbxKp28*)p_kr; a.dr = p_dr;
-        a.row_start = (const int*)p_st; a.row_tab = (const int*)p_tab; a.rows = rows;
-        a.raw_left = left->L.raw + (size_t)left->pyr_base * left->L.frame_raw_bytes;
-        a.raw_right = right->L.raw + (size_t)right->pyr_base * right->L.frame_raw_bytes;
-        a.lvl = left->d_lvl;
-        a.minD = minD; a.maxD = maxD; a.mbf = mbf;
-        a.u_right = (float*)p_out; a.depth = (float*)p_out + nl; a.sad = (int*)p_out + 2 * (size_t)nl;
-        orbx_launch_stereo_match(a, 0);
-        if ((e = cudaGetLastError()) != cudaSuccess) break;
-        if ((e = cudaMemcpy(h_u.data(), p_out, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
-        if ((e = cudaMemcpy(h_d.data(), p_out + (size_t)nl * 4, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
-        if ((e = cudaMemcpy(h_sad.data(), p_out + (size_t)nl * 8, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_n, counts, sizeof(counts), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        out = orbx_stereo_match_device(left, right, 1, (const OrbxKeyPoint*)p_kl, p_dl, (const int32_t*)p_n,
+                                       (const OrbxKeyPoint*)p_kr, p_dr, (const int32_t*)p_n + 1, cap, mbf, fx,
+                                       (float*)p_u, (float*)p_dp, left->stream);
+        if (out != ORBX_OK) break;
+        if ((e = cudaStreamSynchronize(left->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(u_right, p_u, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(depth, p_dp, (size_t)nl * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
     } while (0);
-    if (e != cudaSuccess) rc = fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     cudaFree(pool);
-    if (rc != ORBX_OK) return rc;
-    // adaptive outlier cut (Frame.cc:774-787): sort (SAD, iL), threshold 1.5*1.4*median
-    std::vector<std::pair<int, int> > v;
-    for (int i = 0; i < nl; i++) {
-        if (h_sad[i] >= 0) { u_right[i] = h_u[i]; depth[i] = h_d[i]; v.push_back(std::make_pair(h_sad[i], i)); }
-    }
-    if (!v.empty()) {                               // the reference indexes an empty vector when nothing matched
-        std::sort(v.begin(), v.end());
-        const float median = (float)v[v.size() / 2].first;
-        const float thDist = 1.5f * 1.4f * median;
-        for (int i = (int)v.size() - 1; i >= 0; i--) {
-            if ((float)v[i].first < thDist) break;
-            u_right[v[i].second] = -1; depth[v[i].second] = -1;
-        }
-    }
+    if (out != ORBX_OK) return out;
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     return ORBX_OK;
 }
 

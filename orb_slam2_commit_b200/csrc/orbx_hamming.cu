@@ -297,34 +297,57 @@ void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, c
         minD, maxD, best_idx, best_dist);
 }
 
-// ---------------------------------------------------------------- full stereo matching (Frame.cc:596-764)
-// One warp per left keypoint: row-band Hamming best (as above), then — on the HBM-resident level pyramids of the two
-// extractors — the 11x11 SAD of centre-normalised windows slid over +-5 columns, the parabola fit through the three
-// SADs around the minimum and the disparity / depth of Frame.cc:733-760. All window arithmetic is integer (the
-// reference converts to float only to call cv::norm); the float steps use un-contracted IEEE operations.
-// The 1.5*1.4*median cut over all matches (Frame.cc:774-787) is a sort of <= N pairs and stays on the host.
-__global__ void __launch_bounds__(256) stereo_match_kernel(OrbxStereoArgs A)
+// ---------------------------------------------------------------- full stereo matching (Frame.cc:547-788)
+// Device-resident and batched over stereo pairs. Kernel 1: one warp per left keypoint. The reference's row table
+// (vRowIndices, Frame.cc:564-590) is not materialised: the CTA stages (band, octave, x) of every right keypoint of the
+// pair in shared memory and each warp tests "row (int)vL lies in the band" directly while striding over the right
+// keypoints in ascending index — the order the table would have given — then takes the warp-min of
+// (distance << 20 | right index): first candidate attaining the minimum, strict '<' against TH_HIGH = 100.
+// For a match below 75 the 11x11 SAD of centre-normalised windows is slid over +-5 columns on the level pyramids of
+// the two extractors, a parabola is fitted through the three SADs around the minimum and disparity / depth follow
+// Frame.cc:733-760. Window arithmetic is integer (the reference converts to float only to call cv::norm); the float
+// steps use un-contracted IEEE operations. Kernel 2: one CTA per pair finds the median SAD with a two-pass radix
+// select and applies the 1.5*1.4*median cut (Frame.cc:774-787).
+struct StereoR { float x; short minr, maxr; int octave; };   // 12 bytes per right keypoint
+
+__global__ void __launch_bounds__(256) stereo_match_batch_kernel(OrbxStereoBatch A)
 {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    StereoR* sr = reinterpret_cast<StereoR*>(s_raw);
+    const int pair = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (iL >= A.nl) return;
-    const OrbxKp28 k = A.kl[iL];
+    const int nl = min(A.nl[pair], A.cap), nr = min(A.nr[pair], A.cap);
+    if ((int)(blockIdx.x * 8) >= nl) return;                  // whole CTA
+    const OrbxKp28* kl = A.kl + (size_t)pair * A.cap;
+    const OrbxKp28* kr = A.kr + (size_t)pair * A.cap;
+    const uint4* dl = reinterpret_cast<const uint4*>(A.dl + (size_t)pair * A.cap * 32);
+    const uint4* dr = reinterpret_cast<const uint4*>(A.dr + (size_t)pair * A.cap * 32);
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+        const OrbxKp28 r = kr[i];
+        const float rad = __fmul_rn(2.0f, A.lvl[r.octave].scale);           // r = 2*mvScaleFactors[octave]
+        StereoR e;
+        e.x = r.x; e.octave = r.octave;
+        e.maxr = (short)(int)ceilf(__fadd_rn(r.y, rad));
+        e.minr = (short)(int)floorf(__fsub_rn(r.y, rad));
+        sr[i] = e;
+    }
+    __syncthreads();
+    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (iL >= nl) return;
+    const OrbxKp28 k = kl[iL];
     const int row = (int)k.y;
     int key = (100 << 20) | 0xfffff;
     if (row >= 0 && row < A.rows) {
         const float minU = __fsub_rn(k.x, A.maxD), maxU = __fsub_rn(k.x, A.minD);
         if (!(maxU < 0.f)) {
-            const uint4* dl = reinterpret_cast<const uint4*>(A.dl);
-            const uint4* dr = reinterpret_cast<const uint4*>(A.dr);
             const uint4 qa = dl[2 * (size_t)iL], qb = dl[2 * (size_t)iL + 1];
-            const int c0 = A.row_start[row], c1 = A.row_start[row + 1];
-            for (int c = c0 + lane; c < c1; c += 32) {
-                const int iR = A.row_tab[c];
-                const OrbxKp28 r = A.kr[iR];
+            for (int iR = lane; iR < nr; iR += 32) {
+                const StereoR r = sr[iR];
+                if (row < r.minr || row > r.maxr) continue;
                 if (r.octave < k.octave - 1 || r.octave > k.octave + 1) continue;
                 if (r.x >= minU && r.x <= maxU) {
                     const int d = ht_dist(qa, qb, dr[2 * (size_t)iR], dr[2 * (size_t)iR + 1]);
-                    if (d < 100) key = min(key, (d << 20) | min(c - c0, 0xffffe));
+                    if (d < 100) key = min(key, (d << 20) | iR);
                 }
             }
         }
@@ -333,11 +356,10 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(OrbxStereoArgs A)
     for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
     float out_u = -1.f, out_d = -1.f;
     int out_sad = -1;
-    const int pos = key & 0xfffff;
-    if (pos != 0xfffff && (key >> 20) < 75) {                 // thOrbDist = (TH_HIGH + TH_LOW) / 2  (warp-uniform)
-        const int iR = A.row_tab[A.row_start[row] + pos];
+    const int iR = key & 0xfffff;
+    if (iR != 0xfffff && (key >> 20) < 75) {                  // thOrbDist = (TH_HIGH + TH_LOW) / 2  (warp-uniform)
         const OrbxLevelGeom g = A.lvl[k.octave];
-        const float uR0 = A.kr[iR].x;
+        const float uR0 = sr[iR].x;
         const float scaleduL = roundf(__fmul_rn(k.x, g.inv_scale));
         const float scaledvL = roundf(__fmul_rn(k.y, g.inv_scale));
         const float scaleduR0 = roundf(__fmul_rn(uR0, g.inv_scale));
@@ -345,8 +367,8 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(OrbxStereoArgs A)
         const float endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, 5.f), 5.f), 1.f);
         if (!(iniu < 0.f || endu >= (float)g.w)) {
             const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
-            const uint8_t* pL = A.raw_left + g.raw_off + (size_t)(cv + ORBX_EDGE) * g.pitch + (cu + ORBX_XOFF);
-            const uint8_t* pR = A.raw_right + g.raw_off + (size_t)(cv + ORBX_EDGE) * g.pitch + (cr + ORBX_XOFF);
+            const uint8_t* pL = A.raw_left + (size_t)pair * A.frame_raw_bytes + g.raw_off + (size_t)(cv + ORBX_EDGE) * g.pitch + (cu + ORBX_XOFF);
+            const uint8_t* pR = A.raw_right + (size_t)pair * A.frame_raw_bytes + g.raw_off + (size_t)(cv + ORBX_EDGE) * g.pitch + (cr + ORBX_XOFF);
             const int cL = pL[0];
             int cR[11], acc[11];
 #pragma unroll
@@ -383,11 +405,65 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(OrbxStereoArgs A)
             }
         }
     }
-    if (lane == 0) { A.u_right[iL] = out_u; A.depth[iL] = out_d; A.sad[iL] = out_sad; }
+    if (lane == 0) {
+        const size_t o = (size_t)pair * A.cap + iL;
+        A.u_right[o] = out_u; A.depth[o] = out_d; A.sad[o] = out_sad;
+    }
 }
 
-void orbx_launch_stereo_match(const OrbxStereoArgs& a, cudaStream_t st)
+// median of the matched SADs (the element at index size/2 of the sorted list, Frame.cc:775) by a two-pass radix
+// select on the 16-bit values, then mvuRight = mvDepth = -1 for every match with SAD >= 1.5f*1.4f*median
+__global__ void __launch_bounds__(256) stereo_median_cut_kernel(OrbxStereoBatch A)
 {
-    if (a.nl <= 0) return;
-    stereo_match_kernel<<<(a.nl + 7) / 8, 256, 0, st>>>(a);
+    __shared__ int hist[256];
+    __shared__ int s_sel[3];
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int nl = min(A.nl[pair], A.cap);
+    const int* sad = A.sad + (size_t)pair * A.cap;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < nl; i += 256) { const int v = sad[i]; if (v >= 0) atomicAdd(&hist[min(v >> 8, 255)], 1); }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int b = 0; b < 256; b++) m += hist[b];
+        int k = m / 2, cum = 0, bin = -1;
+        for (int b = 0; b < 256 && bin < 0; b++) { if (cum + hist[b] > k) bin = b; else cum += hist[b]; }
+        s_sel[0] = m; s_sel[1] = bin; s_sel[2] = k - cum;
+    }
+    __syncthreads();
+    const int m = s_sel[0], bin = s_sel[1], k2 = s_sel[2];
+    if (m == 0) return;                                       // the reference indexes an empty vector here
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < nl; i += 256) { const int v = sad[i]; if (v >= 0 && min(v >> 8, 255) == bin) atomicAdd(&hist[v & 255], 1); }
+    __syncthreads();
+    if (tid == 0) {
+        int cum = 0, lo = 0;
+        for (int b = 0; b < 256; b++) { if (cum + hist[b] > k2) { lo = b; break; } cum += hist[b]; }
+        s_sel[1] = (bin << 8) | lo;
+    }
+    __syncthreads();
+    const float thDist = __fmul_rn(1.5f * 1.4f, (float)s_sel[1]);
+    for (int i = tid; i < nl; i += 256) {
+        const int v = sad[i];
+        if (v >= 0 && !((float)v < thDist)) {
+            A.u_right[(size_t)pair * A.cap + i] = -1.f;
+            A.depth[(size_t)pair * A.cap + i] = -1.f;
+        }
+    }
+}
+
+void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st)
+{
+    if (a.pairs <= 0 || a.cap <= 0) return;
+    const size_t smem = (size_t)a.cap * sizeof(StereoR);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(stereo_match_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    dim3 grid((a.cap + 7) / 8, a.pairs);
+    stereo_match_batch_kernel<<<grid, 256, smem, st>>>(a);
+    stereo_median_cut_kernel<<<a.pairs, 256, 0, st>>>(a);
 }

@@ -101,16 +101,17 @@ void orbx_launch_hamming_top2(const uint8_t* d_q, int nq, const uint8_t* d_t, in
                               uint64_t* d_packed, cudaStream_t st);
 void orbx_launch_hamming_merge(const uint64_t* d_parts, int nparts, int nq, int* d_idx, int* d_d1, int* d_d2,
                                cudaStream_t st);
-struct OrbxStereoArgs {        // full Frame::ComputeStereoMatches kernel (Frame.cc:596-764)
-    const OrbxKp28* kl; const uint8_t* dl; int nl;
-    const OrbxKp28* kr; const uint8_t* dr;
-    const int* row_start; const int* row_tab; int rows;
-    const uint8_t* raw_left; const uint8_t* raw_right;   // frame base of each extractor's HBM pyramid
+struct OrbxStereoBatch {       // full Frame::ComputeStereoMatches (Frame.cc:547-788) for `pairs` stereo pairs at once
+    const OrbxKp28* kl; const uint8_t* dl; const int* nl;   // left  keypoints / descriptors / counts: [pairs][cap]
+    const OrbxKp28* kr; const uint8_t* dr; const int* nr;   // right
+    int cap, pairs, rows;
+    const uint8_t* raw_left; const uint8_t* raw_right;      // HBM pyramids of the two extractors (frame p = pair p)
+    size_t frame_raw_bytes;
     const OrbxLevelGeom* lvl;
     float minD, maxD, mbf;
-    float* u_right; float* depth; int* sad;               // per left keypoint; sad = -1 when unmatched
+    float* u_right; float* depth; int* sad;                 // [pairs][cap]; sad = -1 when unmatched
 };
-void orbx_launch_stereo_match(const OrbxStereoArgs& a, cudaStream_t st);
+void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st);
 void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, const OrbxKp28* kr, const uint8_t* dr,
                                 int nr, const int* row_start, const int* row_tab, int rows, float minD, float maxD,
                                 int* best_idx, int* best_dist, cudaStream_t st);

@@ -303,3 +303,38 @@ def test_capacity_error_and_geometry_change_on_one_instance():
     rc = L.orbx_extract(ex._h, a.ctypes.data_as(api.u8p), 640, 480, 640, kps.ctypes.data, 100, C.byref(n), desc.ctypes.data_as(api.u8p))
     assert rc == 3 and n.value == len(ka)
     assert kps.tobytes() == ka[:100].tobytes() and np.array_equal(desc, da[:100])
+
+
+def test_batched_device_stereo_matches_oracle():
+    """orbx_stereo_match_device: 3 stereo pairs in one call, everything resident in HBM (frames -> two
+    orbx_extract_device calls -> matcher). Every pair must equal the oracle's Frame::ComputeStereoMatches."""
+    import torch
+    from orb_slam2_commit_b200 import api, stereo_match_device
+    c = _cfg("euroc")
+    args = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    pairs = [synth.synth_stereo_pair(c["width"], c["height"], 1010 + i) for i in range(3)]
+    W, H, P = c["width"], c["height"], len(pairs)
+    exL, exR = ORBextractor(*args), ORBextractor(*args)
+    cap = exL.reserve(W, H, P); exR.reserve(W, H, P)
+    dev = {}
+    for side, ex, imgs in (("l", exL, [p[0] for p in pairs]), ("r", exR, [p[1] for p in pairs])):
+        d_img = torch.from_numpy(np.stack(imgs)).cuda()
+        kps = torch.zeros((P, cap, 28), dtype=torch.uint8, device="cuda"); desc = torch.zeros((P, cap, 32), dtype=torch.uint8, device="cuda")
+        n = torch.zeros(P, dtype=torch.int32, device="cuda")
+        ex.extract_device(d_img.data_ptr(), P, W, H, W, W * H, kps.data_ptr(), cap, n.data_ptr(), desc.data_ptr(), 0)
+        ex.synchronize()
+        dev[side] = (kps, desc, n)
+    ur = torch.zeros((P, cap), dtype=torch.float32, device="cuda"); dp = torch.zeros((P, cap), dtype=torch.float32, device="cuda")
+    stereo_match_device(exL, exR, P, dev["l"][0].data_ptr(), dev["l"][1].data_ptr(), dev["l"][2].data_ptr(),
+                        dev["r"][0].data_ptr(), dev["r"][1].data_ptr(), dev["r"][2].data_ptr(), cap, c["bf"], c["fx"],
+                        ur.data_ptr(), dp.data_ptr(), 0)
+    exL.synchronize()
+    nl = dev["l"][2].cpu().numpy()
+    for i, (left, right) in enumerate(pairs):
+        oL, oR = ob.Extractor(*args), ob.Extractor(*args)
+        kl, dl = oL.extract(left); kr, dr = oR.extract(right)
+        assert nl[i] == len(kl)
+        ur_o, dp_o = ob.stereo_match(oL, oR, kl, dl, kr, dr, c["bf"], c["fx"])
+        assert np.array_equal(ur[i, :nl[i]].cpu().numpy().view(np.uint32), ur_o.view(np.uint32)), i
+        assert np.array_equal(dp[i, :nl[i]].cpu().numpy().view(np.uint32), dp_o.view(np.uint32)), i
+        assert np.count_nonzero(ur_o >= 0) > 50
