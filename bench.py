@@ -33,6 +33,9 @@ WORKLOADS = {
     "euroc": dict(cfg="euroc", batch=1024, distinct=32),
     "kitti": dict(cfg="kitti", batch=256, distinct=16),
     "4k": dict(cfg="4k", batch=8, distinct=4),
+    # BASELINE configs[1]: stereo pairs, left + right extraction and Frame::ComputeStereoMatches
+    "kitti_stereo": dict(cfg="kitti", batch=128, distinct=8, stereo=True),
+    "euroc_stereo": dict(cfg="euroc", batch=256, distinct=8, stereo=True),
 }
 
 
@@ -234,6 +237,103 @@ def bench_hamming(torch, api_lib, dev, peaks, sm_mhz):
             "popc_pipe_frac": popc / (ms * 1e-3) / (148 * 16 * clk), "popc_pipe_model": "148 SMs x 16 popc/clk x measured SM clock"}
 
 
+def run_stereo(args, torch, dist, rank, world, local, dev):
+    """Stereo pairs/s: two extractor instances (as the reference, Tracking.cc:120-123) + the device-resident matcher."""
+    from orb_slam2_commit_b200 import ORBextractor, api, stereo_match_device
+    w = WORKLOADS[args.workload]; c = synth.CONFIGS[w["cfg"]]
+    P = args.batch or w["batch"]; W, H = c["width"], c["height"]
+    pairs = [synth.synth_stereo_pair(W, H, 2 + i + 1000 * rank) for i in range(w["distinct"])]
+    hL = torch.empty((P, H, W), dtype=torch.uint8, pin_memory=True); hR = torch.empty((P, H, W), dtype=torch.uint8, pin_memory=True)
+    for i in range(P):
+        hL.numpy()[i] = pairs[i % len(pairs)][0]; hR.numpy()[i] = pairs[i % len(pairs)][1]
+    dL, dR = hL.to(dev), hR.to(dev)
+    cfgargs = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    exL, exR = ORBextractor(*cfgargs, device=local), ORBextractor(*cfgargs, device=local)
+    cap = exL.reserve(W, H, P); exR.reserve(W, H, P)
+    mk = lambda *shape, dt=torch.uint8: torch.empty(shape, dtype=dt, device=dev)
+    kL, kR, deL, deR = mk(P, cap, 28), mk(P, cap, 28), mk(P, cap, 32), mk(P, cap, 32)
+    nL, nR = torch.zeros(P, dtype=torch.int32, device=dev), torch.zeros(P, dtype=torch.int32, device=dev)
+    uR, dp = mk(P, cap, dt=torch.float32), mk(P, cap, dt=torch.float32)
+    ts = torch.cuda.Stream(device=dev); torch.cuda.set_stream(ts); st = ts.cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step(timed=False):
+        if timed: ev[0].record()
+        exL.extract_device(dL.data_ptr(), P, W, H, W, W * H, kL.data_ptr(), cap, nL.data_ptr(), deL.data_ptr(), st)
+        exR.extract_device(dR.data_ptr(), P, W, H, W, W * H, kR.data_ptr(), cap, nR.data_ptr(), deR.data_ptr(), st)
+        if timed: ev[1].record()
+        stereo_match_device(exL, exR, P, kL.data_ptr(), deL.data_ptr(), nL.data_ptr(), kR.data_ptr(), deR.data_ptr(), nR.data_ptr(),
+                            cap, c["bf"], c["fx"], uR.data_ptr(), dp.data_ptr(), st)
+        if timed: ev[2].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup): step()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps): step()
+    e1.record(); torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1); clocks = sampler.stop()
+    step(timed=True); torch.cuda.synchronize()
+    ms_extract, ms_match = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * P * args.steps / (ms_total * 1e-3)
+    # e2e: pinned host frames in, keypoints / descriptors / mvuRight / mvDepth out, copies inside the timed region
+    outs = [torch.empty_like(x, device="cpu").pin_memory() for x in (kL, deL, nL, kR, deR, nR, uR, dp)]
+    def e2e_step():
+        dL.copy_(hL, non_blocking=True); dR.copy_(hR, non_blocking=True)
+        step()
+        for o, x in zip(outs, (kL, deL, nL, kR, deR, nR, uR, dp)): o.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(2): e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10)); t0 = time.perf_counter()
+    for _ in range(n_e2e): e2e_step()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_v = world * P * n_e2e / float(t.item())
+    if rank != 0: return
+    matched = float((outs[6][:, :] >= 0).sum().item()) / P   # includes unwritten tail slots only if >= 0 garbage; informational
+    nl_np = outs[2].numpy()
+    matched = float(np.mean([(outs[6][i, :nl_np[i]] >= 0).sum().item() for i in range(P)]))
+    line = {"metric": "stereo_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"{w['cfg']} stereo: {W}x{H} pairs, nFeatures={c['nfeatures']} per image, left+right extraction + ComputeStereoMatches",
+                       "pairs_per_step_per_gpu": P, "distinct_pairs": len(pairs)},
+            "clocks": clocks, "gpu_launches": (2 * (c["nlevels"] + 3) + 2) * args.steps,
+            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * W * H, "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in outs)), "steps": n_e2e,
+                    "api": "orbx_extract_device x2 + orbx_stereo_match_device with pinned host buffers"},
+            "stages": {"extract_left_right_ms": ms_extract, "stereo_match_ms": ms_match},
+            "pipeline": {"keypoints_per_image": float(nl_np.mean()), "stereo_matches_per_pair": matched}}
+    if world == 1 and not args.no_cpu_baseline:
+        # CPU: the oracle port, two extractions + ComputeStereoMatches per pair, pair-parallel over the host threads
+        from oracle import binding as ob
+        nthreads = os.cpu_count() or 1
+        exs = [(ob.Extractor(*cfgargs), ob.Extractor(*cfgargs)) for _ in range(nthreads)]
+        def work(tid, iters):
+            for i in range(tid, iters, nthreads):
+                l, r = pairs[i % len(pairs)]
+                a, b = exs[tid]
+                k1, d1 = a.extract(l); k2, d2 = b.extract(r)
+                ob.stereo_match(a, b, k1, d1, k2, d2, c["bf"], c["fx"])
+        def run(iters):
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=work, args=(t_, iters)) for t_ in range(nthreads)]
+            [x.start() for x in th]; [x.join() for x in th]
+            return time.perf_counter() - t0
+        t1 = run(nthreads); iters = int(max(nthreads, nthreads * max(1.0, args.cpu_seconds / max(t1, 1e-3)))); tt = run(iters)
+        line["cpu_baseline"] = {"value": iters / tt, "unit": "pairs/s", "cores": nthreads, "kind": "port", "sample": f"{iters} pairs over {nthreads} threads, {tt:.1f} s"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,6 +368,11 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
+    if WORKLOADS[args.workload].get("stereo"):
+        run_stereo(args, torch, dist, rank, world, local, dev)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     w = WORKLOADS[args.workload]
     c = synth.CONFIGS[w["cfg"]]
     B = args.batch or w["batch"]
