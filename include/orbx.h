@@ -138,6 +138,24 @@ int orbx_stereo_hamming(const OrbxKeyPoint* kp_left, const uint8_t* desc_left, i
                         int rows, const float* scale_factors, int nlevels, float minD, float maxD,
                         int32_t* best_idx_r, int32_t* best_dist, int device);
 
+/* ---- Windowed best / second-best search: the candidate loop of ORBmatcher::SearchByProjection(Frame&,
+ *      vector<MapPoint*>&, th) (ORBmatcher.cc:46-142) over Frame::GetFeaturesInArea (Frame.cc:388-444) on the 64x48
+ *      grid of AssignFeaturesToGrid / PosInGrid (Frame.cc:254-271, 446-460). One query = one projected map point:
+ *      window centre (x, y), radius r (already scaled by mvScaleFactors[level]), level range [min_level, max_level]
+ *      (the reference passes nPredictedLevel-1, nPredictedLevel), xr = mTrackProjXR (only used when u_right is given).
+ *      occupied[i] != 0 <=> keypoint i already has an observed map point (:90-92); u_right = mvuRight (:95-100);
+ *      both may be NULL. minX/minY/invW/invH = mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv.
+ *      Outputs per query are the five values the reference loop ends with: bestIdx (-1 = none), bestDist, bestLevel,
+ *      bestDist2, bestLevel2; the caller applies `bestDist <= TH_HIGH` and the NN-ratio rule (:129-137).
+ *      Host buffers, synchronous; at most 14000 keypoints per frame. ---- */
+typedef struct OrbxWindowQuery { float x, y, r; int32_t min_level, max_level; float xr; } OrbxWindowQuery;
+int orbx_window_top2(const OrbxKeyPoint* keypoints, const uint8_t* descriptors, int n,
+                     const uint8_t* occupied, const float* u_right,
+                     float minX, float minY, float invW, float invH,
+                     const OrbxWindowQuery* queries, const uint8_t* query_descriptors, int nq,
+                     int32_t* best_idx, int32_t* best_dist, int32_t* best_level, int32_t* best_dist2, int32_t* best_level2,
+                     int device);
+
 /* ---- Train-sharded matching across GPUs with the exchange FUSED into the matcher (no NCCL call): the last CTA of
  *      every query tile stores the rank's merged top-2 straight into every peer's landing buffer over NVLink
  *      (CUDA IPC peer mappings) and bumps the peers' arrival counters; a one-block kernel waits for the counters

@@ -76,6 +76,8 @@ def lib():
         L.oc_level_candidates.restype = C.c_int
         L.oc_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oc_level_nkeypoints.restype = C.c_int; L.oc_level_nkeypoints.argtypes = [C.c_void_p, C.c_int]
+        L.oc_window_top2.argtypes = [C.c_void_p, u8p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_void_p, u8p, C.c_int, i32p, i32p, i32p, i32p, i32p]
         L.oc_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
                                       C.c_float, C.c_float, f32p, f32p]
         _lib = L
@@ -153,6 +155,22 @@ def stereo_hamming(kl, dl, kr, dr, rows, scale_factors, minD, maxD):
     lib().oc_stereo_hamming(kl.ctypes.data, _u8(dl), len(kl), kr.ctypes.data, _u8(dr), len(kr), rows,
                             sf.ctypes.data_as(f32p), minD, maxD, bi.ctypes.data_as(i32p), bd.ctypes.data_as(i32p))
     return bi, bd
+
+
+WQ_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"), ("xr", "<f4")])
+
+
+def window_top2(kps, desc, occupied, u_right, minX, minY, invW, invH, queries, qdesc):
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries, WQ_DTYPE); qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    nq = len(queries)
+    out = [np.empty(nq, np.int32) for _ in range(5)]
+    lib().oc_window_top2(kps.ctypes.data, _u8(desc), len(kps), None if occ is None else occ.ctypes.data,
+                         None if ur is None else ur.ctypes.data, minX, minY, invW, invH, queries.ctypes.data, _u8(qdesc), nq,
+                         *[o.ctypes.data_as(i32p) for o in out])
+    return out
 
 
 def stereo_match(left: "Extractor", right: "Extractor", kl, dl, kr, dr, mbf, fx):

@@ -918,3 +918,66 @@ void oc_stereo_match(const OcExtractor* EL, const OcExtractor* ER,
     }
     free(v); free(bidx); free(bdist);
 }
+
+/* ------------------------------------------------------------------ windowed top-2 (Frame.cc:254-271,388-460; ORBmatcher.cc:46-142) */
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+void oc_window_top2(const OcKeyPoint* kps, const uint8_t* desc, int n, const uint8_t* occupied, const float* u_right,
+                    float mnMinX, float mnMinY, float invW, float invH,
+                    const OcWindowQuery* q, const uint8_t* qdesc, int nq,
+                    int32_t* best_idx, int32_t* best_dist, int32_t* best_level, int32_t* best_dist2, int32_t* best_level2)
+{
+    /* AssignFeaturesToGrid: mGrid[posX][posY] holds keypoint indices in ascending order */
+    int* cnt = (int*)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, sizeof(int));
+    int* cell = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        int posX = (int)roundf((kps[i].x - mnMinX) * invW), posY = (int)roundf((kps[i].y - mnMinY) * invH);
+        cell[i] = (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) ? -1 : posX * FRAME_GRID_ROWS + posY;
+        if (cell[i] >= 0) cnt[cell[i] + 1]++;
+    }
+    for (int c = 0; c < FRAME_GRID_COLS * FRAME_GRID_ROWS; c++) cnt[c + 1] += cnt[c];
+    int* tab = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int* fill = (int*)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS, sizeof(int));
+    for (int i = 0; i < n; i++) if (cell[i] >= 0) tab[cnt[cell[i]] + fill[cell[i]]++] = i;
+    for (int k = 0; k < nq; k++) {
+        const float x = q[k].x, y = q[k].y, r = q[k].r;
+        const int minLevel = q[k].min_level, maxLevel = q[k].max_level;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        /* GetFeaturesInArea */
+        int nMinCellX = (int)floorf((x - mnMinX - r) * invW); if (nMinCellX < 0) nMinCellX = 0;
+        int nMaxCellX = (int)ceilf((x - mnMinX + r) * invW); if (nMaxCellX > FRAME_GRID_COLS - 1) nMaxCellX = FRAME_GRID_COLS - 1;
+        int nMinCellY = (int)floorf((y - mnMinY - r) * invH); if (nMinCellY < 0) nMinCellY = 0;
+        int nMaxCellY = (int)ceilf((y - mnMinY + r) * invH); if (nMaxCellY > FRAME_GRID_ROWS - 1) nMaxCellY = FRAME_GRID_ROWS - 1;
+        const int empty = nMinCellX >= FRAME_GRID_COLS || nMaxCellX < 0 || nMinCellY >= FRAME_GRID_ROWS || nMaxCellY < 0;
+        const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        if (!empty)
+            for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+                for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                    const int c = ix * FRAME_GRID_ROWS + iy;
+                    for (int j = cnt[c]; j < cnt[c + 1]; j++) {
+                        const int idx = tab[j];
+                        const OcKeyPoint* kp = &kps[idx];
+                        if (bCheckLevels) {
+                            if (kp->octave < minLevel) continue;
+                            if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                        }
+                        const float distx = kp->x - x, disty = kp->y - y;
+                        if (!(fabsf(distx) < r && fabsf(disty) < r)) continue;
+                        /* the SearchByProjection loop body (:86-126) */
+                        if (occupied && occupied[idx]) continue;
+                        if (u_right && u_right[idx] > 0) {
+                            const float er = fabsf(q[k].xr - u_right[idx]);
+                            if (er > r) continue;
+                        }
+                        const int dist = oc_descriptor_distance(qdesc + 32 * (size_t)k, desc + 32 * (size_t)idx);
+                        if (dist < bestDist) {
+                            bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kp->octave; bestIdx = idx;
+                        } else if (dist < bestDist2) {
+                            bestLevel2 = kp->octave; bestDist2 = dist;
+                        }
+                    }
+                }
+        best_idx[k] = bestIdx; best_dist[k] = bestDist; best_level[k] = bestLevel; best_dist2[k] = bestDist2; best_level2[k] = bestLevel2;
+    }
+    free(cnt); free(cell); free(tab); free(fill);
+}

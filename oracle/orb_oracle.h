@@ -73,6 +73,17 @@ void  oc_stereo_match(const OcExtractor* left, const OcExtractor* right,
                       const OcKeyPoint* kr, const uint8_t* dr, int nr,
                       float mbf, float fx, float* u_right, float* depth);
 
+/* Windowed best / second-best search of ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)
+ * (ORBmatcher.cc:46-142) over Frame::GetFeaturesInArea (Frame.cc:388-444) on the 64x48 grid built by
+ * AssignFeaturesToGrid / PosInGrid (Frame.cc:254-271, 446-460). One query = one projected map point:
+ * window centre (x,y), radius r (already multiplied by the level scale), level range, optional stereo coordinate xr
+ * (< 0 = none). occupied[i] != 0 stands for "keypoint i already has an observed map point" (:90-92). */
+typedef struct { float x, y, r; int32_t min_level, max_level; float xr; } OcWindowQuery;
+void  oc_window_top2(const OcKeyPoint* kps, const uint8_t* desc, int n, const uint8_t* occupied, const float* u_right,
+                     float minX, float minY, float invW, float invH,
+                     const OcWindowQuery* q, const uint8_t* qdesc, int nq,
+                     int32_t* best_idx, int32_t* best_dist, int32_t* best_level, int32_t* best_dist2, int32_t* best_level2);
+
 #ifdef __cplusplus
 }
 #endif

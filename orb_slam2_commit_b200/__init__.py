@@ -6,7 +6,7 @@ reference class (include/ORBextractor.h:51-145). There is no CPU fallback: loadi
 library is missing and every compute call fails when no CUDA device is visible.
 """
 from .api import (KP_DTYPE, OrbxError, ORBextractor, ORBmatcher, build_library, hamming_top2, lib, library_path,
-                  stereo_hamming, stereo_match, stereo_match_device)
+                  stereo_hamming, stereo_match, stereo_match_device, window_top2)
 
 __all__ = ["KP_DTYPE", "OrbxError", "ORBextractor", "ORBmatcher", "build_library", "hamming_top2", "lib",
-           "library_path", "stereo_hamming", "stereo_match", "stereo_match_device"]
+           "library_path", "stereo_hamming", "stereo_match", "stereo_match_device", "window_top2"]

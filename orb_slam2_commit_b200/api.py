@@ -83,6 +83,8 @@ def lib():
                                         C.c_float, C.c_float, f32p, f32p]
         L.orbx_stereo_match_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_window_top2.argtypes = [C.c_void_p, u8p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_void_p, u8p, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int]
         L.orbx_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
         L.orbx_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
         L.orbx_peer_hamming_top2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
@@ -280,6 +282,23 @@ def stereo_match_device(left: ORBextractor, right: ORBextractor, pairs, d_kl, d_
     """Batched device-resident Frame::ComputeStereoMatches (orbx_stereo_match_device); all d_* are device pointers."""
     _ck(lib().orbx_stereo_match_device(left._h, right._h, pairs, d_kl, d_dl, d_nl, d_kr, d_dr, d_nr, cap, mbf, fx,
                                        d_u_right, d_depth, stream))
+
+
+WQ_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"), ("xr", "<f4")])
+
+
+def window_top2(keypoints, descriptors, occupied, u_right, minX, minY, invW, invH, queries, query_descriptors, device: int = 0):
+    """Candidate loop of ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) over Frame::GetFeaturesInArea.
+    Returns (bestIdx, bestDist, bestLevel, bestDist2, bestLevel2) int32 arrays, one entry per query."""
+    kps = np.ascontiguousarray(keypoints, KP_DTYPE); desc = np.ascontiguousarray(descriptors, np.uint8)
+    q = np.ascontiguousarray(queries, WQ_DTYPE); qd = np.ascontiguousarray(query_descriptors, np.uint8)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    out = [np.empty(len(q), np.int32) for _ in range(5)]
+    _ck(lib().orbx_window_top2(kps.ctypes.data, _u8(desc), len(kps), None if occ is None else occ.ctypes.data,
+                               None if ur is None else ur.ctypes.data, minX, minY, invW, invH, q.ctypes.data, _u8(qd), len(q),
+                               *[o.ctypes.data_as(i32p) for o in out], device))
+    return out
 
 
 class ORBmatcher:

@@ -835,3 +835,56 @@ extern "C" void orbx_peer_destroy(orbx_peer_matcher* m)
     cudaGetLastError();
     delete m;
 }
+
+// ------------------------------------------------------------------------------------------------ windowed top-2
+extern "C" int orbx_window_top2(const OrbxKeyPoint* kps, const uint8_t* desc, int n, const uint8_t* occupied, const float* u_right,
+                                float minX, float minY, float invW, float invH, const OrbxWindowQuery* q, const uint8_t* qdesc,
+                                int nq, int32_t* best_idx, int32_t* best_dist, int32_t* best_level, int32_t* best_dist2,
+                                int32_t* best_level2, int device)
+{
+    if (n < 0 || nq < 0 || (n > 0 && (!kps || !desc)) || (nq > 0 && (!q || !qdesc || !best_idx || !best_dist || !best_level || !best_dist2 || !best_level2)))
+        return fail(ORBX_ERR_INVALID, "bad argument");
+    if (nq == 0) return ORBX_OK;
+    if (n > 14000) return fail(ORBX_ERR_UNSUPPORTED, "more than 14000 keypoints per frame");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t nn = (size_t)std::max(n, 1);
+    const size_t b_k = al(nn * 28), b_d = al(nn * 32), b_o = al(nn), b_u = al(nn * 4), b_q = al((size_t)nq * sizeof(OrbxWindowQuery)),
+                 b_qd = al((size_t)nq * 32), b_out = al((size_t)nq * 4);
+    uint8_t* pool = nullptr;
+    CK(cudaMalloc(&pool, b_k + b_d + b_o + b_u + b_q + b_qd + 5 * b_out));
+    uint8_t* p = pool;
+    uint8_t *p_k = p; p += b_k;
+    uint8_t *p_d = p; p += b_d;
+    uint8_t *p_o = p; p += b_o;
+    uint8_t *p_u = p; p += b_u;
+    uint8_t *p_q = p; p += b_q;
+    uint8_t *p_qd = p; p += b_qd;
+    uint8_t *p_out = p;
+    int32_t* outs[5] = {best_idx, best_dist, best_level, best_dist2, best_level2};
+    cudaError_t e;
+    do {
+        if (n > 0 && (e = cudaMemcpy(p_k, kps, (size_t)n * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (n > 0 && (e = cudaMemcpy(p_d, desc, (size_t)n * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (n > 0 && occupied && (e = cudaMemcpy(p_o, occupied, (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (n > 0 && u_right && (e = cudaMemcpy(p_u, u_right, (size_t)n * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_q, q, (size_t)nq * sizeof(OrbxWindowQuery), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_qd, qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        OrbxWindowArgs a;
+        a.kps = (const OrbxKp28*)p_k; a.desc = p_d; a.n = n;
+        a.occupied = (occupied && n > 0) ? p_o : nullptr; a.u_right = (u_right && n > 0) ? (const float*)p_u : nullptr;
+        a.minX = minX; a.minY = minY; a.invW = invW; a.invH = invH;
+        static_assert(sizeof(OrbxWinQuery) == sizeof(OrbxWindowQuery), "query layout");
+        a.q = (const OrbxWinQuery*)p_q; a.qdesc = p_qd; a.nq = nq;
+        a.best_idx = (int*)p_out; a.best_dist = (int*)(p_out + b_out); a.best_level = (int*)(p_out + 2 * b_out);
+        a.best_dist2 = (int*)(p_out + 3 * b_out); a.best_level2 = (int*)(p_out + 4 * b_out);
+        orbx_launch_window_top2(a, 0);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        for (int k = 0; k < 5; k++)
+            if ((e = cudaMemcpy(outs[k], p_out + (size_t)k * b_out, (size_t)nq * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(pool);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return ORBX_OK;
+}

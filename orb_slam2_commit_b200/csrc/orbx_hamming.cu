@@ -467,3 +467,93 @@ void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st)
     stereo_match_batch_kernel<<<grid, 256, smem, st>>>(a);
     stereo_median_cut_kernel<<<a.pairs, 256, 0, st>>>(a);
 }
+
+// ---------------------------------------------------------------- windowed top-2 on the Frame grid
+// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:46-142): per projected map point the
+// candidates of Frame::GetFeaturesInArea (Frame.cc:388-444) are scanned in grid order (cell column, cell row, then
+// ascending keypoint index inside a cell — the order AssignFeaturesToGrid filled the cells in) keeping best / second
+// best with strict '<'. Here: one warp per query, the CTA stages (x, y, octave, grid cell) of every keypoint of the
+// frame in shared memory, every lane tests the reference's gates directly (level range, cell range, |dx|,|dy| < r,
+// occupied, stereo) and ranks survivors by the 64-bit key  dist<<40 | cellX<<34 | cellY<<28 | index: the smallest key
+// is the first candidate attaining the minimum distance in the reference's scan order and the second smallest key is
+// exactly its (bestDist2, bestLevel2).
+struct WinKp { float x, y; int octave; int cell; };   // cell = posX << 8 | posY, or -1 when PosInGrid fails
+
+__global__ void __launch_bounds__(256) window_top2_kernel(OrbxWindowArgs A)
+{
+    extern __shared__ __align__(16) unsigned char s_raw2[];
+    WinKp* sk = reinterpret_cast<WinKp*>(s_raw2);
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
+        const OrbxKp28 k = A.kps[i];
+        WinKp e;
+        e.x = k.x; e.y = k.y; e.octave = k.octave;
+        const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, A.minX), A.invW));     // Frame::PosInGrid
+        const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, A.minY), A.invH));
+        e.cell = (posX < 0 || posX >= 64 || posY < 0 || posY >= 48) ? -1 : (posX << 8 | posY);
+        sk[i] = e;
+    }
+    __syncthreads();
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qi >= A.nq) return;
+    const OrbxWinQuery q = A.q[qi];
+    const unsigned long long NONE = (256ull << 40) | 0xffffffffffull;
+    unsigned long long b1 = NONE, b2 = NONE;
+    int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.x, A.minX), q.r), A.invW)));
+    int cx1 = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.x, A.minX), q.r), A.invW)));
+    int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.y, A.minY), q.r), A.invH)));
+    int cy1 = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.y, A.minY), q.r), A.invH)));
+    const bool empty = cx0 >= 64 || cx1 < 0 || cy0 >= 48 || cy1 < 0;
+    const bool check_levels = q.min_level > 0 || q.max_level >= 0;
+    if (!empty) {
+        const uint4* dsc = reinterpret_cast<const uint4*>(A.desc);
+        const uint4 qa = reinterpret_cast<const uint4*>(A.qdesc)[2 * (size_t)qi], qb = reinterpret_cast<const uint4*>(A.qdesc)[2 * (size_t)qi + 1];
+        for (int i = lane; i < A.n; i += 32) {
+            const WinKp k = sk[i];
+            if (k.cell < 0) continue;
+            const int px = k.cell >> 8, py = k.cell & 255;
+            if (px < cx0 || px > cx1 || py < cy0 || py > cy1) continue;
+            if (check_levels) {
+                if (k.octave < q.min_level) continue;
+                if (q.max_level >= 0 && k.octave > q.max_level) continue;
+            }
+            if (!(fabsf(__fsub_rn(k.x, q.x)) < q.r && fabsf(__fsub_rn(k.y, q.y)) < q.r)) continue;
+            if (A.occupied && A.occupied[i]) continue;
+            if (A.u_right) { const float ur = A.u_right[i]; if (ur > 0.f && fabsf(__fsub_rn(q.xr, ur)) > q.r) continue; }
+            const int d = ht_dist(qa, qb, dsc[2 * (size_t)i], dsc[2 * (size_t)i + 1]);
+            if (d >= 256) continue;                           // strict '<' against the initial 256
+            const unsigned long long key = ((unsigned long long)d << 40) | ((unsigned long long)px << 34) | ((unsigned long long)py << 28) | (unsigned)i;
+            const unsigned long long hi = key > b1 ? key : b1;
+            b1 = key < b1 ? key : b1;
+            b2 = hi < b2 ? hi : b2;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, b1, o), o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+        const unsigned long long lo = b1 < o1 ? b1 : o1, hi = b1 < o1 ? o1 : b1;
+        const unsigned long long s2 = b2 < o2 ? b2 : o2;
+        b1 = lo; b2 = hi < s2 ? hi : s2;
+    }
+    if (lane == 0) {
+        const int d1 = (int)(b1 >> 40), d2 = (int)(b2 >> 40);
+        const int i1 = (int)(b1 & 0xfffffffu), i2 = (int)(b2 & 0xfffffffu);
+        A.best_idx[qi] = d1 < 256 ? i1 : -1;
+        A.best_dist[qi] = d1 < 256 ? d1 : 256;
+        A.best_level[qi] = d1 < 256 ? sk[i1].octave : -1;
+        A.best_dist2[qi] = d2 < 256 ? d2 : 256;
+        A.best_level2[qi] = d2 < 256 ? sk[i2].octave : -1;
+    }
+}
+
+void orbx_launch_window_top2(const OrbxWindowArgs& a, cudaStream_t st)
+{
+    if (a.nq <= 0) return;
+    const size_t smem = (size_t)(a.n > 0 ? a.n : 1) * sizeof(WinKp);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(window_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    window_top2_kernel<<<(a.nq + 7) / 8, 256, smem, st>>>(a);
+}

@@ -112,6 +112,15 @@ struct OrbxStereoBatch {       // full Frame::ComputeStereoMatches (Frame.cc:547
     float* u_right; float* depth; int* sad;                 // [pairs][cap]; sad = -1 when unmatched
 };
 void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st);
+struct OrbxWinQuery { float x, y, r; int min_level, max_level; float xr; };   // == OrbxWindowQuery of include/orbx.h
+struct OrbxWindowArgs {        // windowed top-2 on the Frame grid (Frame.cc:388-444, ORBmatcher.cc:46-142)
+    const OrbxKp28* kps; const uint8_t* desc; int n;
+    const uint8_t* occupied; const float* u_right;          // optional (NULL)
+    float minX, minY, invW, invH;
+    const OrbxWinQuery* q; const uint8_t* qdesc; int nq;
+    int *best_idx, *best_dist, *best_level, *best_dist2, *best_level2;
+};
+void orbx_launch_window_top2(const OrbxWindowArgs& a, cudaStream_t st);
 void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, const OrbxKp28* kr, const uint8_t* dr,
                                 int nr, const int* row_start, const int* row_tab, int rows, float minD, float maxD,
                                 int* best_idx, int* best_dist, cudaStream_t st);

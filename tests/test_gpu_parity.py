@@ -338,3 +338,40 @@ def test_batched_device_stereo_matches_oracle():
         assert np.array_equal(ur[i, :nl[i]].cpu().numpy().view(np.uint32), ur_o.view(np.uint32)), i
         assert np.array_equal(dp[i, :nl[i]].cpu().numpy().view(np.uint32), dp_o.view(np.uint32)), i
         assert np.count_nonzero(ur_o >= 0) > 50
+
+
+def test_window_top2_matches_oracle():
+    """SearchByProjection's candidate loop over GetFeaturesInArea on the 64x48 Frame grid (Frame.cc:388-444,
+    ORBmatcher.cc:46-142): queries = keypoints of a second frame 'projected' with noise, incl. occupied keypoints,
+    stereo gating, windows leaving the image and duplicate descriptors (grid-order tie-break)."""
+    from orb_slam2_commit_b200 import window_top2
+    c = _cfg("euroc")
+    ex = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    k1, d1 = ex(synth.synth_image(c["width"], c["height"], 1200))
+    k2, d2 = ex(synth.synth_image(c["width"], c["height"], 1200)[::1, ::1])     # same frame: true matches exist
+    rng = np.random.default_rng(3)
+    sf = ex.GetScaleFactors()
+    n = len(k2)
+    q = np.zeros(n + 40, ob.WQ_DTYPE); qd = np.zeros((n + 40, 32), np.uint8)
+    q["x"][:n] = k2["x"] + rng.normal(0, 3, n).astype(np.float32); q["y"][:n] = k2["y"] + rng.normal(0, 3, n).astype(np.float32)
+    lvl = k2["octave"]
+    q["r"][:n] = (np.where(rng.random(n) < 0.5, 2.5, 4.0) * 3).astype(np.float32) * sf[lvl]
+    q["min_level"][:n] = lvl - 1; q["max_level"][:n] = lvl
+    q["xr"][:n] = q["x"][:n] - rng.uniform(0, 40, n).astype(np.float32)
+    qd[:n] = d2
+    flip = rng.integers(0, 32, n); qd[np.arange(n), flip] ^= rng.integers(0, 256, n).astype(np.uint8)
+    # 40 extra queries: windows partly / fully outside the image, no level check, huge radius
+    q["x"][n:] = rng.uniform(-200, c["width"] + 200, 40); q["y"][n:] = rng.uniform(-200, c["height"] + 200, 40)
+    q["r"][n:] = rng.uniform(5, 300, 40); q["min_level"][n:] = -1; q["max_level"][n:] = -1; q["xr"][n:] = -1
+    qd[n:] = d1[rng.integers(0, len(d1), 40)]
+    d1 = d1.copy(); d1[11] = d1[10]; d1[500] = d1[10]                    # exact ties: the grid-order first one must win
+    occ = (rng.random(len(k1)) < 0.1).astype(np.uint8)
+    ur = np.where(rng.random(len(k1)) < 0.5, k1["x"] - rng.uniform(0, 40, len(k1)), -1).astype(np.float32)
+    minX, minY = 0.0, 0.0
+    invW = np.float32(64) / np.float32(c["width"] - minX); invH = np.float32(48) / np.float32(c["height"] - minY)
+    for occupied, uright in ((None, None), (occ, ur)):
+        got = window_top2(k1, d1, occupied, uright, minX, minY, float(invW), float(invH), q, qd)
+        want = ob.window_top2(k1, d1, occupied, uright, minX, minY, float(invW), float(invH), q, qd)
+        for g, w_, name in zip(got, want, ("bestIdx", "bestDist", "bestLevel", "bestDist2", "bestLevel2")):
+            assert np.array_equal(g, w_), name
+        assert np.count_nonzero(want[0] >= 0) > n // 2
