@@ -81,6 +81,13 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height,
 int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height, int stride,
                        OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
 
+/* Colour input: Tracking::GrabImage{Stereo,RGBD,Monocular} converts 3- and 4-channel frames with cv::cvtColor
+ * (CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY, Tracking.cc:174-199, 215-237, 246-261) before the extractor
+ * sees them. Here that conversion (OpenCV 4.x 8-bit arithmetic) is fused into the level-0 kernel: `images[i]` are
+ * interleaved frames with `channels` in {1, 3, 4} and `stride` bytes per row; rgb != 0 <=> channel 0 is R (mbRGB). */
+int orbx_extract_batch_color(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height, int stride,
+                             int channels, int rgb, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
+
 /* Device-resident form: frames already in HBM (frame i at d_images + i*frame_pitch_bytes), outputs stay in HBM.
  * Asynchronous on `cuda_stream` (a cudaStream_t passed as void*; NULL = the extractor's own stream).
  * d_keypoints[n*cap], d_descriptors[n*cap*32], d_nkp[n] (device pointers). Keypoints beyond cap are dropped and

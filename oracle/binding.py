@@ -51,6 +51,7 @@ def lib():
         L.oc_resize_linear_8u.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
         L.oc_border_reflect101.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oc_gaussian7x7_s2.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.oc_cvt_gray.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
         L.oc_fast_score.restype = C.c_int; L.oc_fast_score.argtypes = [u8p, C.c_int]
         L.oc_fast9_16.restype = C.c_int
         L.oc_fast9_16.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -107,6 +108,14 @@ def gaussian7(img: np.ndarray) -> np.ndarray:
     img = np.ascontiguousarray(img, np.uint8)
     out = np.empty_like(img)
     lib().oc_gaussian7x7_s2(_u8(img), img.shape[1], img.shape[0], img.shape[1], _u8(out), img.shape[1])
+    return out
+
+
+def cvt_gray(img: np.ndarray, rgb: bool) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().oc_cvt_gray(_u8(img), w, h, w * ch, ch, int(rgb), _u8(out), w)
     return out
 
 

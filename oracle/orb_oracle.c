@@ -250,6 +250,19 @@ void oc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* d
     free(hb);
 }
 
+/* ------------------------------------------------------------------ cv::cvtColor to gray, CV_8U (Tracking.cc:174-199) */
+/* OpenCV 4.x imgproc/color_rgb: fixed point with 15 fractional bits, R 9798, G 19235, B 3735, round to nearest. */
+void oc_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb, uint8_t* dst, int dstride)
+{
+    const int c0 = rgb ? 9798 : 3735, c2 = rgb ? 3735 : 9798;
+    for (int y = 0; y < h; y++) {
+        const uint8_t* s = src + (size_t)y * sstride;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++, s += channels)
+            d[x] = (uint8_t)((s[0] * c0 + s[1] * 19235 + s[2] * c2 + (1 << 14)) >> 15);
+    }
+}
+
 /* ------------------------------------------------------------------ cv::FAST TYPE_9_16 (features2d/fast.cpp, fast_score.cpp) */
 static const int g_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
 static const int g_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};

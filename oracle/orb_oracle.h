@@ -29,6 +29,8 @@ void  oc_resize_linear_8u(const uint8_t* src, int sw, int sh, int sstride,
                           uint8_t* dst, int dw, int dh, int dstride);
 void  oc_border_reflect101(uint8_t* whole, int w, int h, int stride, int border);
 void  oc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+void  oc_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb,
+                  uint8_t* dst, int dstride);                 /* cv::cvtColor(.., CV_{RGB,BGR,RGBA,BGRA}2GRAY), 8U */
 int   oc_fast_score(const uint8_t* p, int stride);           /* cornerScore<16> with threshold floor 0 */
 int   oc_fast9_16(const uint8_t* roi, int w, int h, int stride, int threshold, int nms,
                   OcKeyPoint* out, int cap);                 /* cv::FAST(roi, kps, threshold, nms) */

@@ -63,6 +63,8 @@ def lib():
         L.orbx_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, i32p, u8p]
         L.orbx_extract_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_int, i32p, C.c_void_p]
+        L.orbx_extract_batch_color.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_int, i32p, C.c_void_p]
         L.orbx_extract_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_synchronize.argtypes = [C.c_void_p]
@@ -160,6 +162,8 @@ class ORBextractor:
         Returns (keypoints[KP_DTYPE], descriptors[n,32] uint8); an empty image returns empty outputs."""
         if image is None or image.size == 0:
             return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if image.ndim == 3:
+            return self.extract_color(image, rgb=True)
         assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 required (ORBextractor.cc:1146)"
         if image.strides[1] != 1:
             image = np.ascontiguousarray(image)
@@ -169,6 +173,19 @@ class ORBextractor:
         kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int32(0)
         _ck(self._L.orbx_extract(self._h, _u8(image), w, h, image.strides[0], kps.ctypes.data, cap, C.byref(n), _u8(desc)))
         return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_color(self, image: np.ndarray, rgb: bool):
+        """(h, w, 3|4) interleaved uint8 frame: Tracking::GrabImage*'s cvtColor (Tracking.cc:174-199) fused into level 0.
+        rgb=True <=> channel 0 is R (the reference's mbRGB)."""
+        image = np.ascontiguousarray(image, np.uint8)
+        h, w, ch = image.shape
+        _ck(self._L.orbx_reserve(self._h, w, h, 1))
+        cap = self._L.orbx_max_keypoints(self._h)
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = np.zeros(1, np.int32)
+        ptrs = (C.c_void_p * 1)(image.ctypes.data)
+        _ck(self._L.orbx_extract_batch_color(self._h, ptrs, 1, w, h, w * ch, ch, int(rgb), kps.ctypes.data, cap,
+                                             n.ctypes.data_as(i32p), desc.ctypes.data))
+        return kps[:n[0]].copy(), desc[:n[0]].copy()
 
     def extract_batch(self, images, max_batch: int = 64):
         """images: sequence of equally sized 2-D uint8 arrays, or one (n,h,w) array. Returns lists."""

@@ -40,7 +40,8 @@ struct orbx_extractor {
     OrbxLevelGeom* d_lvl = nullptr;
     OrbxCell* d_cells = nullptr;
     OrbxResizeTap* d_taps = nullptr;
-    uint8_t* d_in = nullptr;                      // [B][H][W] staging of host frames
+    uint8_t* d_in = nullptr;                      // [B][H][W(*channels)] staging of host frames
+    size_t d_in_bytes = 0;
     OrbxKp28* d_kps = nullptr;                    // [B][kp_cap_total]
     uint8_t* d_desc = nullptr;
     int* d_nkp = nullptr;
@@ -120,7 +121,7 @@ static void release_device(orbx_extractor* h)
     cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps);
     h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr;
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
-    h->d_in = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_nkp = nullptr;
+    h->d_in = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_nkp = nullptr; h->d_in_bytes = 0;
     h->W = h->H = h->max_batch = 0;
 }
 
@@ -294,6 +295,7 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     // staging for the host entry points
     const size_t in_bytes = B * (size_t)width * height;
     CK(cudaMalloc(&h->d_in, in_bytes));
+    h->d_in_bytes = in_bytes;
     CK(cudaMalloc(&h->d_kps, B * L.kp_cap_total * sizeof(OrbxKp28)));
     CK(cudaMalloc(&h->d_desc, B * L.kp_cap_total * 32));
     CK(cudaMalloc(&h->d_nkp, B * sizeof(int)));
@@ -308,7 +310,8 @@ extern "C" int orbx_max_keypoints(const orbx_extractor* h) { return (h && h->W) 
 // `base` = first frame of the reserved working set to use (the host path runs two chunks concurrently on two
 // streams, each in its own half of the working set)
 static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stride, size_t frame_pitch,
-                        OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st, int base = 0)
+                        OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st, int base = 0,
+                        int channels = 1, int rgb = 0)
 {
     OrbxFrameLayout Lb = h->L;
     if (base) {
@@ -324,7 +327,7 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     const bool tm = h->timing;
     cudaEvent_t* ev = h->ev[h->runs % orbx_extractor::RING];
     if (tm) cudaEventRecord(ev[0], st);
-    orbx_launch_pyramid(Lb, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st);
+    orbx_launch_pyramid(Lb, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st, channels, rgb);
     if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(Lb, h->max_tile_w, h->max_tile_h, n, st);
     if (tm) cudaEventRecord(ev[2], st);
@@ -393,19 +396,27 @@ extern "C" int orbx_get_stage_ms(orbx_extractor* h, float* ms4, int* nruns)
     return ORBX_OK;
 }
 
-extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
-                                  int stride, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
+static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
+                              int stride, int channels, int rgb, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
 {
     if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
     if (n <= 0 || !images || width <= 0 || height <= 0) return ORBX_OK;        // empty input: silent, like :1141
-    if (!keypoints || !nkp || !descriptors || cap < 0 || stride < width) return fail(ORBX_ERR_INVALID, "bad output buffers");
+    if (channels != 1 && channels != 3 && channels != 4) return fail(ORBX_ERR_INVALID, "channels must be 1, 3 or 4 (Tracking.cc:174-199)");
+    if (!keypoints || !nkp || !descriptors || cap < 0 || stride < width * channels) return fail(ORBX_ERR_INVALID, "bad output buffers");
     if (width != h->W || height != h->H || h->max_batch < 1) {
         int rc = orbx_reserve(h, width, height, std::max(1, std::min(n, std::max(h->max_batch, 64))));
         if (rc != ORBX_OK) return rc;
     }
     CK(cudaSetDevice(h->device));
     const int B = h->max_batch, kc = h->L.kp_cap_total;
-    const size_t fbytes = (size_t)width * height;
+    const size_t fbytes = (size_t)width * height * channels;
+    const int rowbytes = width * channels;
+    if ((size_t)B * fbytes > h->d_in_bytes) {           // colour frames need a wider staging buffer than gray ones
+        CK(cudaDeviceSynchronize());
+        cudaFree(h->d_in); h->d_in = nullptr; h->d_in_bytes = 0;
+        CK(cudaMalloc(&h->d_in, (size_t)B * fbytes));
+        h->d_in_bytes = (size_t)B * fbytes;
+    }
     int status = ORBX_OK;
     // Two chunks in flight on two streams, each in its own half of the reserved working set: the H2D copy of chunk
     // k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k. A slot's stream serialises its own
@@ -425,7 +436,7 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* image
         uint8_t* d_desc = h->d_desc + (size_t)base * kc * 32;
         int* d_nkp = h->d_nkp + base;
         // frames that are contiguous in host memory go up in one copy, otherwise one (strided) copy per frame
-        bool contiguous = stride == width;
+        bool contiguous = stride == rowbytes;
         for (int i = 0; i < m && contiguous; i++) {
             if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
             contiguous = images[f0 + i] == images[f0] + (size_t)i * fbytes;
@@ -434,10 +445,10 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* image
         else
             for (int i = 0; i < m; i++) {
                 if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
-                CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, width, images[f0 + i], stride, width, height,
+                CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, rowbytes, images[f0 + i], stride, rowbytes, height,
                                      cudaMemcpyHostToDevice, st));
             }
-        int rc = run_pipeline(h, d_in, m, width, fbytes, d_kps, d_desc, kc, d_nkp, st, base);
+        int rc = run_pipeline(h, d_in, m, rowbytes, fbytes, d_kps, d_desc, kc, d_nkp, st, base, channels, rgb);
         if (rc != ORBX_OK) return rc;
         CK(cudaMemcpyAsync(nkp + f0, d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (cap == kc) {
@@ -458,6 +469,19 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* image
     for (int i = 0; i < n; i++) if (nkp[i] > cap) status = ORBX_ERR_CAPACITY;
     if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
     return status;
+}
+
+extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
+                                  int stride, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
+{
+    return extract_batch_impl(h, images, n, width, height, stride, 1, 0, keypoints, cap, nkp, descriptors);
+}
+
+extern "C" int orbx_extract_batch_color(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
+                                        int stride, int channels, int rgb, OrbxKeyPoint* keypoints, int cap, int* nkp,
+                                        uint8_t* descriptors)
+{
+    return extract_batch_impl(h, images, n, width, height, stride, channels, rgb, keypoints, cap, nkp, descriptors);
 }
 
 extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height, int stride,

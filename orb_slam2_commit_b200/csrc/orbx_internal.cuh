@@ -76,7 +76,7 @@ struct OrbxKp28 { float x, y, size, angle, response; int octave, class_id; };
 
 // kernel launchers (implemented in the .cu files; all asynchronous on `st`)
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
-                         int stride, size_t frame_pitch, int nframes, cudaStream_t st);
+                         int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels = 1, int rgb = 0);
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);
 void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,

@@ -46,6 +46,39 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_kernel(OrbxFrameLa
     }
 }
 
+// level 0 from an interleaved colour frame (3 or 4 channels): cv::cvtColor(.., CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY /
+// CV_BGRA2GRAY) of Tracking::GrabImage* (Tracking.cc:174-199) fused into the level-0 copy. OpenCV 4.x 8-bit arithmetic:
+// (R*9798 + G*19235 + B*3735 + 2^14) >> 15.  `rgb` != 0 <=> the first channel is R (mbRGB).
+__global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_color_kernel(OrbxFrameLayout L, const uint8_t* __restrict__ img,
+                                                                            int stride, size_t frame_pitch, int channels, int rgb)
+{
+    const OrbxLevelGeom g = L.lvl[0];
+    const int t = blockIdx.x * PYR_TX + threadIdx.x;
+    const int rb0 = (blockIdx.y * PYR_TY + threadIdx.y) * PYR_RPT;
+    const int cb = 12 + 4 * t;
+    const int rows = g.h + 2 * ORBX_EDGE;
+    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb0 >= rows) return;
+    int xr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) xr[k] = reflect101(cb + k - ORBX_XOFF, g.w) * channels;
+    const int c0 = rgb ? 9798 : 3735, c2 = rgb ? 3735 : 9798;
+    const uint8_t* fimg = img + (size_t)blockIdx.z * frame_pitch;
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
+#pragma unroll
+    for (int rr = 0; rr < PYR_RPT; rr++) {
+        if (rb0 + rr >= rows) break;
+        const uint8_t* src = fimg + (size_t)reflect101(rb0 + rr - ORBX_EDGE, g.h) * stride;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint8_t* px = src + xr[k];
+            const int v = (__ldg(px) * c0 + __ldg(px + 1) * 19235 + __ldg(px + 2) * c2 + (1 << 14)) >> 15;
+            out |= (uint32_t)v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)rr * g.pitch) = out;
+    }
+}
+
 // level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows: the four
 // x-taps are fetched once and up to 16*PYR_RPT independent source-pixel loads are in flight per thread.
 __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_kernel(OrbxFrameLayout L, int level)
@@ -87,7 +120,7 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_kernel(OrbxFrameLa
 }
 
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
-                         int stride, size_t frame_pitch, int nframes, cudaStream_t st)
+                         int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels, int rgb)
 {
     (void)w; (void)h;
     for (int l = 0; l < L.nlevels; l++) {
@@ -96,7 +129,8 @@ void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, c
         const int rows = g.h + 2 * ORBX_EDGE;
         dim3 block(PYR_TX, PYR_TY);
         dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY * PYR_RPT - 1) / (PYR_TY * PYR_RPT), nframes);
-        if (l == 0) pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
+        if (l == 0 && channels > 1) pyr_level0_color_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, channels, rgb);
+        else if (l == 0) pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
         else pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
     }
 }

@@ -375,3 +375,21 @@ def test_window_top2_matches_oracle():
         for g, w_, name in zip(got, want, ("bestIdx", "bestDist", "bestLevel", "bestDist2", "bestLevel2")):
             assert np.array_equal(g, w_), name
         assert np.count_nonzero(want[0] >= 0) > n // 2
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_colour_input_fused_gray_conversion(channels, rgb):
+    """Tracking::GrabImage* converts colour frames with cv::cvtColor before extraction (Tracking.cc:174-199); the fused
+    level-0 kernel must give the result of extracting the oracle's gray image (pinned to cv2 4.13 by the golden tests)."""
+    c = _cfg("tum1")
+    rng = np.random.default_rng(channels * 2 + rgb)
+    base = synth.synth_image(c["width"], c["height"], 90 + channels)
+    col = np.stack([np.clip(base.astype(np.int32) + rng.integers(-40, 41, base.shape), 0, 255).astype(np.uint8) for _ in range(channels)], axis=2)
+    gray = ob.cvt_gray(col, rgb)
+    ex = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    kps, desc = ex.extract_color(col, rgb)
+    assert np.array_equal(ex.pyramid_level(0), gray)
+    ko, do = ob.Extractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"]).extract(gray)
+    _check_against(kps, desc, ko, do, f"colour {channels} rgb={rgb}")
+    k2, d2 = ex(gray)                                  # back to gray on the same instance
+    _check_against(k2, d2, ko, do, "gray after colour")

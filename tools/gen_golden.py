@@ -55,6 +55,12 @@ def prims():
     ys[:64] = 0; xs[32:96] = 0; ys[96:128] = xs[96:128]
     out["atan2_y"] = ys; out["atan2_x"] = xs
     out["atan2_deg"] = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in zip(ys, xs)], np.float32)
+    col = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    out["gray_src"] = col
+    out["gray_rgb"] = cv2.cvtColor(np.ascontiguousarray(col[..., :3]), cv2.COLOR_RGB2GRAY)
+    out["gray_bgr"] = cv2.cvtColor(np.ascontiguousarray(col[..., :3]), cv2.COLOR_BGR2GRAY)
+    out["gray_rgba"] = cv2.cvtColor(col, cv2.COLOR_RGBA2GRAY)
+    out["gray_bgra"] = cv2.cvtColor(col, cv2.COLOR_BGRA2GRAY)
     np.savez_compressed(os.path.join(G, "prims_cv2.npz"), **out)
     print("prims_cv2.npz", {k: v.shape for k, v in out.items() if k.startswith("fast_full")})
 
