@@ -32,7 +32,7 @@ WORKLOADS = {
     "tum1": dict(cfg="tum1", batch=1024, distinct=32),
     "euroc": dict(cfg="euroc", batch=1024, distinct=32),
     "kitti": dict(cfg="kitti", batch=256, distinct=16),
-    "4k": dict(cfg="4k", batch=8, distinct=4),
+    "4k": dict(cfg="4k", batch=32, distinct=4),
     # BASELINE configs[1]: stereo pairs, left + right extraction and Frame::ComputeStereoMatches
     "kitti_stereo": dict(cfg="kitti", batch=128, distinct=8, stereo=True),
     "euroc_stereo": dict(cfg="euroc", batch=256, distinct=8, stereo=True),
