@@ -7,6 +7,8 @@ import collections, csv, os, re, subprocess, sys, tempfile
 
 def main():
     rep, kern, obj, src, units = sys.argv[1:6]; markers = sys.argv[6:]; units = float(units)
+    kern, _, secre = kern.partition("::")       # "ncu-kernel-regex::cubin-section-regex" picks one template instance
+    secre = secre or kern
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
     cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -21,7 +23,7 @@ def main():
         if m: cur = int(m.group(2)) if os.path.basename(m.group(1)) == base_name else -1
         m = re.search(r"/\*([0-9a-f]{4,})\*/", line)
         if m and cur_sec is not None and cur is not None: secs[cur_sec][int(m.group(1), 16)] = cur
-    sec = [k for k in secs if re.search(kern, k)]
+    sec = [k for k in secs if re.search(secre, k)]
     amap = secs[sec[0]]
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
