@@ -393,3 +393,26 @@ def test_colour_input_fused_gray_conversion(channels, rgb):
     _check_against(kps, desc, ko, do, f"colour {channels} rgb={rgb}")
     k2, d2 = ex(gray)                                  # back to gray on the same instance
     _check_against(k2, d2, ko, do, "gray after colour")
+
+
+def test_random_geometries_match_oracle():
+    """Seeded sweep over image sizes / pyramid settings / thresholds (odd widths, single level, tiny levels, many levels,
+    very wide frames with several quadtree roots); settings the reference itself cannot run are skipped."""
+    from orb_slam2_commit_b200 import OrbxError
+    rng = np.random.default_rng(2026)
+    ran = 0
+    for trial in range(40):
+        w = int(rng.integers(90, 1000)); h = int(rng.integers(70, 700))
+        nl = int(rng.integers(1, 9)); sc = float(rng.choice([1.1, 1.2, 1.25, 1.5, 2.0]))
+        nf = int(rng.choice([30, 200, 1000, 3000])); ini = int(rng.integers(8, 40)); mn = int(rng.integers(1, ini + 1))
+        img = synth.synth_image(w, h, 500 + trial)
+        ex = ORBextractor(nf, sc, nl, ini, mn)
+        try:
+            kps, desc = ex(img)
+        except OrbxError as e:
+            assert e.code == 2, e          # ORBX_ERR_UNSUPPORTED: level < 62 px or portrait level
+            continue
+        ko, do = ob.Extractor(nf, sc, nl, ini, mn).extract(img)
+        _check_against(kps, desc, ko, do, f"trial {trial}: {w}x{h} nf={nf} sc={sc} nl={nl} th={ini}/{mn}")
+        ran += 1
+    assert ran >= 15
