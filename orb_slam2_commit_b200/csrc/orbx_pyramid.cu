@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_color_kernel(OrbxF
 
 // level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows: the four
 // x-taps are fetched once and up to 16*PYR_RPT independent source-pixel loads are in flight per thread.
-__global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_kernel(OrbxFrameLayout L, int level)
+__global__ void __launch_bounds__(PYR_TX * PYR_TY, 8) pyr_resize_kernel(OrbxFrameLayout L, int level)
 {
     const OrbxLevelGeom g = L.lvl[level];
     const OrbxLevelGeom s = L.lvl[level - 1];

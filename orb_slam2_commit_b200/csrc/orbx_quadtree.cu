@@ -65,7 +65,9 @@ __device__ __forceinline__ void qt_count(int* counters, const int key, const boo
     if (active && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&counters[key], __popc(peers));
 }
 
-__global__ void __launch_bounds__(QT_MAX, 1) quadtree_kernel(OrbxFrameLayout L)
+// SMALL: 256-thread CTAs, several per SM (they hide each other's barriers); otherwise one 1024-thread CTA per SM
+template <bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_kernel(OrbxFrameLayout L)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x;
@@ -344,9 +346,11 @@ void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cu
     const size_t smem = qt_smem_bytes(L.qt_cap);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(quadtree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(quadtree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     dim3 grid(L.nlevels, nframes);
-    quadtree_kernel<<<grid, threads, smem, st>>>(L);
+    if (threads == 256) quadtree_kernel<true><<<grid, 256, smem, st>>>(L);
+    else quadtree_kernel<false><<<grid, QT_MAX, smem, st>>>(L);
 }
