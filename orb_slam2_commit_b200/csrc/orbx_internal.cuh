@@ -69,7 +69,6 @@ struct OrbxFrameLayout {      // everything the kernels need, passed by value
     int* lvl_kp_count;              // [B][nlevels]
     int lvl_kp_off[ORBX_MAX_LEVELS];
     int qt_cap;                     // node-table capacity of the quadtree kernel
-    int status_overflow;            // unused on device
 };
 
 struct OrbxKp28 { float x, y, size, angle, response; int octave, class_id; };

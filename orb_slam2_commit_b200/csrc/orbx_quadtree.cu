@@ -1,7 +1,7 @@
 // orbx_quadtree.cu — level-synchronous, bit-exact parallel form of ORBextractor::DistributeOctTree
 // (ORBextractor.cc:562-815) and ExtractorNode::DivideNode (:501-560).
 //
-// One CTA of 1024 threads per (level, frame). The reference keeps a std::list of nodes, each owning a vector of
+// One CTA per (level, frame): 256 threads (several CTAs per SM) for frames up to 1 Mpx, 1024 above. The reference keeps a std::list of nodes, each owning a vector of
 // keypoints, and splits nodes one at a time; here the list is an ARRAY IN LIST ORDER held in shared memory
 // (bounds + count per node) and every candidate keypoint carries the index of the node that currently owns it
 // (u16 in HBM/L2). One "pass" = what the reference does in one sweep over its list:
