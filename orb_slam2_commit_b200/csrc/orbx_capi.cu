@@ -177,7 +177,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
     const int nl = h->nlevels;
     h->lvl.assign(nl, OrbxLevelGeom{});
     h->cells.clear(); h->taps.clear();
-    size_t raw = 0; int slot = 0, cand = 0, kpc = 0, qtcap = 0;
+    size_t raw = 0; int slot = 0, cand = 0, kpc = 0, qtcap = 0, hist_ints = 0;
     h->max_tile_w = h->max_tile_h = 8;
     for (int l = 0; l < nl; l++) {
         OrbxLevelGeom& g = h->lvl[l];
@@ -227,6 +227,17 @@ static int build_geometry(orbx_extractor* h, int W, int H)
         g.cand_cap = std::min(lvl_slots, (1 << 23) - 1);
         cand += g.cand_cap;
         g.kp_cap = std::max(g.quota + 3, 4 * g.nini) + 1;
+        // quadtree fast path: count pyramid one level deeper than a uniform spread of `quota` leaves needs; bounded by
+        // shared memory (<= 12288 ints) and the 16-bit path code the keypoints carry
+        {
+            int d = 1;
+            while ((g.nini << (2 * d)) < 4 * std::max(g.quota, 1)) d++;
+            auto ints = [&](int dd) { return (long long)g.nini * (((1ll << (2 * (dd + 1))) - 1) / 3); };
+            while (d > 0 && (ints(d) > 12288 || ((long long)g.nini << (2 * d)) > 65536)) d--;
+            if (getenv("ORBX_QT_SWEEP_ONLY")) d = 0;
+            g.qt_depth = d;
+            hist_ints = std::max(hist_ints, (int)ints(d));
+        }
         qtcap = std::max(qtcap, g.kp_cap);
         h->L.lvl_kp_off[l] = kpc;
         kpc += g.kp_cap;
@@ -244,6 +255,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
     L.ini_th = h->ini_th; L.min_th = h->min_th;
     L.frame_raw_bytes = raw;
     L.qt_cap = (qtcap + 31) & ~31;
+    L.qt_hist_ints = hist_ints;
     return ORBX_OK;
 }
 

@@ -37,6 +37,7 @@ struct OrbxLevelGeom {
     int cand_off;             // offset (elements) of the level's compact candidate array inside a frame
     int cand_cap;
     int kp_cap;               // capacity of the level's keypoint list
+    int qt_depth;             // quadtree fast path: depth of the count pyramid (0 = always use the sweep path)
     int xtab_off, ytab_off;   // offsets into the resize coefficient tables (elements)
 };
 
@@ -69,6 +70,7 @@ struct OrbxFrameLayout {      // everything the kernels need, passed by value
     int* lvl_kp_count;              // [B][nlevels]
     int lvl_kp_off[ORBX_MAX_LEVELS];
     int qt_cap;                     // node-table capacity of the quadtree kernel
+    int qt_hist_ints;               // shared-memory ints of the largest count pyramid
 };
 
 struct OrbxKp28 { float x, y, size, angle, response; int octave, class_id; };

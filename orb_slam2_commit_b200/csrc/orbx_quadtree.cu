@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(
         (reinterpret_cast<uintptr_t>(divf + C) + 7) & ~(uintptr_t)7);   // [sortn]
     int* sc = reinterpret_cast<int*>(skey + sortn);                      // [sortn] scratch for the careful pass
+    int* ndc[2];                                                         // fast path: node = depth << 24 | code
+    ndc[0] = sc + sortn;
+    ndc[1] = ndc[0] + C;
+    int* H = ndc[1] + C;                                                 // fast path: per-depth count pyramid
     __shared__ int s_w[33];
     __shared__ int s_misc[4];
 
@@ -137,35 +141,110 @@ __global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_
     }
     __syncthreads();
 
-    // ---- 1. roots (ORBextractor.cc:567-626): nIni nodes of width hX; keypoint -> root (int)(x / hX)
-    int cur = 0;
-    int S = g.nini;
-    for (int r = tid; r < S; r += QT) {
-        QtBounds b;
-        b.x0 = (short)(int)(g.hx * (float)r);
-        b.x1 = (short)(int)(g.hx * (float)(r + 1));
-        b.y0 = 0;
-        b.y1 = (short)(g.h - 2 * ORBX_MINB);
-        nb[cur][r] = b;
-        ncnt[cur][r] = 0;
-    }
-    __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += QT) {
-        const int i = i0 + tid;
-        int r = -1;
-        if (i < n) {
-            r = (int)__fdiv_rn((float)(cand[i] & 0xfffu), g.hx);
-            r = r < S ? r : S - 1;
-            node[i] = (uint16_t)r;
+    // ---- 1+2. Two ways to run the reference's passes.
+    // FAST PATH (no keypoint sweep per pass): DivideNode's geometry is a pure function of (root, quadrant path), so one
+    // sweep computes every keypoint's path code down to depth DEPTH and histograms the deepest level; the counts of
+    // all shallower nodes follow by summing children (a count pyramid in shared memory). The passes then run on the
+    // node list alone: a node is (depth, code), its children's counts are pyramid look-ups. If a node at the deepest
+    // tracked depth ever has to be split (strongly clustered keypoints) the tree falls back to the
+    // SWEEP PATH: keypoints carry their node index and every pass moves them to their child and histograms the next
+    // split (one sweep per pass).
+    const int DEPTH = g.qt_depth;
+    bool fast = DEPTH > 0;
+    int cur = 0, S = 0;
+    auto hbase = [&](int d) { return g.nini * (((1 << (2 * d)) - 1) / 3); };   // first entry of depth d in H
+    for (;;) {
+    int mode;                   // -1 root filter (sweep path only), 0 full pass, 1 careful pass
+    cur = 0;
+    if (fast) {
+        const int T = hbase(DEPTH + 1);
+        for (int i = tid; i < T; i += QT) H[i] = 0;
+        __syncthreads();
+        int* HD = H + hbase(DEPTH);
+        for (int i0 = 0; i0 < n; i0 += QT) {
+            const int i = i0 + tid;
+            int code = -1;
+            if (i < n) {
+                const uint32_t xy = cand[i];
+                const int x = xy & 0xfff, y = (xy >> 12) & 0xfff;
+                int r = (int)__fdiv_rn((float)x, g.hx);
+                r = r < g.nini ? r : g.nini - 1;
+                int x0 = (int)(g.hx * (float)r), x1 = (int)(g.hx * (float)(r + 1)), y0 = 0, y1 = g.h - 2 * ORBX_MINB;
+                code = r;
+                for (int d = 0; d < DEPTH; d++) {
+                    const int midx = x0 + ((x1 - x0 + 1) >> 1), midy = y0 + ((y1 - y0 + 1) >> 1);
+                    const int qx = x >= midx, qy = y >= midy;
+                    if (qx) x0 = midx; else x1 = midx;
+                    if (qy) y0 = midy; else y1 = midy;
+                    code = code * 4 + qx + 2 * qy;
+                }
+                node[i] = (uint16_t)code;
+            }
+            qt_count(HD, code, i < n);
         }
-        qt_count(ncnt[cur], r, i < n);
+        __syncthreads();
+        for (int d = DEPTH - 1; d >= 0; d--) {
+            int* Hd = H + hbase(d);
+            const int* Hc = H + hbase(d + 1);
+            for (int c = tid; c < (g.nini << (2 * d)); c += QT) Hd[c] = Hc[4 * c] + Hc[4 * c + 1] + Hc[4 * c + 2] + Hc[4 * c + 3];
+            __syncthreads();
+        }
+        // list = non-empty roots in root order
+        for (int r = tid; r < g.nini; r += QT) keep[r] = H[r] > 0;
+        __syncthreads();
+        S = qt_scan(keep, g.nini, s_w);
+        for (int r = tid; r < g.nini; r += QT)
+            if (H[r] > 0) { ndc[0][keep[r]] = r; ncnt[0][keep[r]] = H[r]; }
+        __syncthreads();
+        mode = 0;
+    } else {
+        // roots (ORBextractor.cc:567-626): nIni nodes of width hX; keypoint -> root (int)(x / hX)
+        S = g.nini;
+        for (int r = tid; r < S; r += QT) {
+            QtBounds b;
+            b.x0 = (short)(int)(g.hx * (float)r);
+            b.x1 = (short)(int)(g.hx * (float)(r + 1));
+            b.y0 = 0;
+            b.y1 = (short)(g.h - 2 * ORBX_MINB);
+            nb[cur][r] = b;
+            ncnt[cur][r] = 0;
+        }
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += QT) {
+            const int i = i0 + tid;
+            int r = -1;
+            if (i < n) {
+                r = (int)__fdiv_rn((float)(cand[i] & 0xfffu), g.hx);
+                r = r < S ? r : S - 1;
+                node[i] = (uint16_t)r;
+            }
+            qt_count(ncnt[cur], r, i < n);
+        }
+        __syncthreads();
+        mode = -1;              // pass -1 only drops empty roots; then the reference's while(!bFinish) loop
     }
-    __syncthreads();
 
-    // ---- 2. passes. pass -1 only drops empty roots; then the reference's while(!bFinish) loop
-    int mode = -1;              // -1 root filter, 0 full pass, 1 careful pass
-    bool finish = false;
+    bool finish = false, overflow = false;
     while (!finish) {
+        if (fast) {
+            // children's counts of every splittable node from the pyramid; a splittable node at the deepest tracked
+            // depth means the pyramid is too shallow for this tree
+            if (tid == 0) s_misc[3] = 0;
+            __syncthreads();
+            for (int i = tid; i < S; i += QT) {
+                if (ncnt[cur][i] > 1) {
+                    const int d = ndc[cur][i] >> 24, c = ndc[cur][i] & 0xffffff;
+                    if (d >= DEPTH) s_misc[3] = 1;
+                    else {
+                        const int* Hc = H + hbase(d + 1) + 4 * c;
+                        int* ch = child[cur] + 4 * i;
+                        ch[0] = Hc[0]; ch[1] = Hc[1]; ch[2] = Hc[2]; ch[3] = Hc[3];
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_misc[3]) { overflow = true; break; }
+        }
         const int nxt = cur ^ 1;
         int Ctot = 0;           // children created in this pass
         // (A) which nodes are split, and in which order they are visited
@@ -263,24 +342,27 @@ __global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_
                         QtBounds cb;
                         cb.x0 = (q & 1) ? (short)midx : b.x0;  cb.x1 = (q & 1) ? b.x1 : (short)midx;
                         cb.y0 = (q & 2) ? (short)midy : b.y0;  cb.y1 = (q & 2) ? b.y1 : (short)midy;
-                        if (ni < C) { nb[nxt][ni] = cb; ncnt[nxt][ni] = c; }
+                        if (ni < C) {
+                            nb[nxt][ni] = cb; ncnt[nxt][ni] = c;
+                            if (fast) ndc[nxt][ni] = (((ndc[cur][i] >> 24) + 1) << 24) | ((ndc[cur][i] & 0xffffff) * 4 + q);
+                        }
                         myexp += c > 1;
                         ch[q] = ni;                          // remap table for the keypoint sweep
                     }
                 }
             } else if (ncnt[cur][i] > 0) {
                 const int ni = Ctot + keep[i];
-                if (ni < C) { nb[nxt][ni] = nb[cur][i]; ncnt[nxt][ni] = ncnt[cur][i]; }
+                if (ni < C) { nb[nxt][ni] = nb[cur][i]; ncnt[nxt][ni] = ncnt[cur][i]; if (fast) ndc[nxt][ni] = ndc[cur][i]; }
                 keep[i] = ni;
             }
         }
         if (myexp) atomicAdd(&s_misc[2], myexp);
-        for (int i = tid; i < 4 * C; i += QT) child[nxt][i] = 0;
+        if (!fast) for (int i = tid; i < 4 * C; i += QT) child[nxt][i] = 0;
         __syncthreads();
         const int Enew = s_misc[2];
         const int Sn = Snew < C ? Snew : C;
-        // (C) keypoint sweep: move to the child, histogram the next split
-        for (int i0 = 0; i0 < n; i0 += QT) {
+        // (C) keypoint sweep: move to the child, histogram the next split (sweep path only)
+        for (int i0 = 0; i0 < (fast ? 0 : n); i0 += QT) {
             const int i = i0 + tid;
             int key = -1;
             bool act = false;
@@ -311,13 +393,28 @@ __global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_
         }
     }
 
+    if (overflow) { fast = false; continue; }     // pyramid too shallow: redo this tree on the sweep path
+    break;
+    }
+
     // ---- 3. best keypoint per node: max response, first in the reference's vector order on ties (:796-812)
     int* best = child[cur ^ 1];
     for (int i = tid; i < S; i += QT) best[i] = 0;
+    if (fast)                                      // leaf (depth, code) -> -(list index + 1) in the count pyramid
+        for (int i = tid; i < S; i += QT) H[hbase(ndc[cur][i] >> 24) + (ndc[cur][i] & 0xffffff)] = -(i + 1);
     __syncthreads();
     for (int i = tid; i < n; i += QT) {
         const uint32_t xy = cand[i];
-        atomicMax(&best[node[i]], (int)(((xy >> 24) << 23) | (0x7fffffu - (uint32_t)i)));
+        int idx = node[i];
+        if (fast) {                                // walk the keypoint's path down to the leaf that owns it
+            const int code = idx;
+            idx = 0;
+            for (int t = 0; t <= DEPTH; t++) {
+                const int v = H[hbase(t) + (code >> (2 * (DEPTH - t)))];
+                if (v < 0) { idx = -v - 1; break; }
+            }
+        }
+        atomicMax(&best[idx], (int)(((xy >> 24) << 23) | (0x7fffffu - (uint32_t)i)));
     }
     __syncthreads();
     uint32_t* out = L.lvl_kp + (size_t)frame * L.kp_cap_total + L.lvl_kp_off[level];
@@ -328,7 +425,7 @@ __global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_
     if (tid == 0) L.lvl_kp_count[(size_t)frame * L.nlevels + level] = S < g.kp_cap ? S : g.kp_cap;
 }
 
-static size_t qt_smem_bytes(int C)
+static size_t qt_smem_bytes(int C, int hist_ints)
 {
     int sortn = 1; while (sortn < C) sortn <<= 1;
     size_t b = 0;
@@ -338,12 +435,13 @@ static size_t qt_smem_bytes(int C)
     b += 2 * (size_t)C * sizeof(int);
     b += (size_t)C + 8;
     b += (size_t)sortn * (sizeof(unsigned long long) + sizeof(int));
+    b += 2 * (size_t)C * sizeof(int) + (size_t)hist_ints * sizeof(int);
     return (b + 15) & ~(size_t)15;
 }
 
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st)
 {
-    const size_t smem = qt_smem_bytes(L.qt_cap);
+    const size_t smem = qt_smem_bytes(L.qt_cap, L.qt_hist_ints);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(quadtree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -416,3 +416,23 @@ def test_random_geometries_match_oracle():
         _check_against(kps, desc, ko, do, f"trial {trial}: {w}x{h} nf={nf} sc={sc} nl={nl} th={ini}/{mn}")
         ran += 1
     assert ran >= 15
+
+
+def test_clustered_keypoints_deep_quadtree():
+    """All texture packed into small patches: the quadtree has to go far deeper than a uniform spread of the quota
+    would, which overflows the count pyramid of the fast path and forces the sweep-path fallback (and, with several
+    patches, mixes shallow and deep leaves)."""
+    rng = np.random.default_rng(5)
+    tex = synth._smooth(rng.integers(0, 256, (480, 640)).astype(np.float64), 1.6)
+    tex = ((tex - tex.min()) * 255 / (tex.max() - tex.min())).astype(np.uint8)
+    # one patch: a node with a single non-empty child stops the reference's loop (size == prevSize,
+    # ORBextractor.cc:650-653), so very few keypoints survive; three patches: deep, unbalanced trees.
+    for patches, floor in (([(200, 150, 110)], 8), ([(40, 60, 70), (500, 330, 90), (320, 40, 50)], 500)):
+        img = np.full((480, 640), 120, np.uint8)
+        for (x, y, s) in patches:
+            img[y:y + s, x:x + s] = tex[y:y + s, x:x + s]
+        for nf in (1000, 3000):
+            kps, desc = ORBextractor(nf, 1.2, 8, 20, 7)(img)
+            ko, do = ob.Extractor(nf, 1.2, 8, 20, 7).extract(img)
+            assert len(ko) > floor
+            _check_against(kps, desc, ko, do, f"clustered {len(patches)} patches nf={nf}")
