@@ -88,6 +88,23 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, i
 int orbx_extract_batch_color(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height, int stride,
                              int channels, int rgb, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
 
+/* Stereo rectification in front of the extractor: Examples/Stereo/stereo_euroc.cc:97-98 builds a CV_32FC1 map pair with
+ * cv::initUndistortRectifyMap once, and :136-137 runs cv::remap(im, imRect, M1, M2, cv::INTER_LINEAR) on every frame.
+ * orbx_set_rectify_maps takes that map pair (map_stride in floats; source frames are src_width x src_height) and converts
+ * it to OpenCV's fixed-point form once; orbx_extract_batch_rectified then takes UNRECTIFIED frames and fuses the remap
+ * (OpenCV 4.x 8-bit arithmetic, BORDER_CONSTANT 0) into the level-0 kernel: pyramid level 0 IS the rectified frame
+ * (map_width x map_height; read it back with orbx_pyramid_level). Passing two NULL maps clears the state.
+ * Map values must stay below 2^26 in magnitude. */
+int orbx_set_rectify_maps(orbx_extractor* h, const float* map1, const float* map2, int map_width, int map_height,
+                          int map_stride, int src_width, int src_height);
+int orbx_extract_batch_rectified(orbx_extractor* h, const uint8_t* const* images, int n, int stride,
+                                 OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
+
+/* device-resident form of the rectified call (see orbx_extract_device) */
+int orbx_extract_device_rectified(orbx_extractor* h, const uint8_t* d_images, int n, int stride, size_t frame_pitch_bytes,
+                                  OrbxKeyPoint* d_keypoints, int cap, int32_t* d_nkp, uint8_t* d_descriptors,
+                                  void* cuda_stream);
+
 /* Device-resident form: frames already in HBM (frame i at d_images + i*frame_pitch_bytes), outputs stay in HBM.
  * Asynchronous on `cuda_stream` (a cudaStream_t passed as void*; NULL = the extractor's own stream).
  * d_keypoints[n*cap], d_descriptors[n*cap*32], d_nkp[n] (device pointers). Keypoints beyond cap are dropped and
@@ -199,6 +216,18 @@ int orbx_stereo_match_device(orbx_extractor* left, orbx_extractor* right, int pa
                              const OrbxKeyPoint* d_kp_left, const uint8_t* d_desc_left, const int32_t* d_n_left,
                              const OrbxKeyPoint* d_kp_right, const uint8_t* d_desc_right, const int32_t* d_n_right,
                              int cap, float mbf, float fx, float* d_u_right, float* d_depth, void* cuda_stream);
+
+/* ---- Frame::UndistortKeyPoints (Frame.cc:471-506) and Frame::ComputeImageBounds (Frame.cc:508-538):
+ *      cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) on the keypoint coordinates. K4 = (fx, fy, cx, cy) and
+ *      dist = (k1, k2, p1, p2[, k3]) as the f32 values of mK / mDistCoef (Tracking.cc:60-84); OpenCV 4.x arithmetic
+ *      (five fixed-point iterations in f64), so `out` is bit-identical to mvKeysUn. dist[0] == 0 copies the keypoints
+ *      unchanged (:474-478). in == out is allowed. Host buffers, synchronous / device buffers, asynchronous. ---- */
+int orbx_undistort_keypoints(const OrbxKeyPoint* in, int n, const float* K4, const float* dist, int ndist,
+                             OrbxKeyPoint* out, int device);
+int orbx_undistort_keypoints_device(const OrbxKeyPoint* d_in, int n, const float* K4, const float* dist, int ndist,
+                                    OrbxKeyPoint* d_out, void* cuda_stream);
+/* bounds4 = (mnMinX, mnMaxX, mnMinY, mnMaxY) of Frame::ComputeImageBounds for a width x height frame */
+int orbx_image_bounds(int width, int height, const float* K4, const float* dist, int ndist, float* bounds4, int device);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -52,6 +52,8 @@ def lib():
         L.oc_border_reflect101.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oc_gaussian7x7_s2.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
         L.oc_cvt_gray.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.oc_remap_linear_8u.argtypes = [u8p, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.oc_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
         L.oc_fast_score.restype = C.c_int; L.oc_fast_score.argtypes = [u8p, C.c_int]
         L.oc_fast9_16.restype = C.c_int
         L.oc_fast9_16.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -116,6 +118,25 @@ def cvt_gray(img: np.ndarray, rgb: bool) -> np.ndarray:
     h, w, ch = img.shape
     out = np.empty((h, w), np.uint8)
     lib().oc_cvt_gray(_u8(img), w, h, w * ch, ch, int(rgb), _u8(out), w)
+    return out
+
+
+def remap(img: np.ndarray, map1: np.ndarray, map2: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    map1 = np.ascontiguousarray(map1, np.float32); map2 = np.ascontiguousarray(map2, np.float32)
+    dh, dw = map1.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().oc_remap_linear_8u(_u8(img), img.shape[1], img.shape[0], img.shape[1], map1.ctypes.data_as(f32p),
+                             map2.ctypes.data_as(f32p), dw, dw, dh, _u8(out), dw)
+    return out
+
+
+def undistort_points(xy: np.ndarray, K4, dist) -> np.ndarray:
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(xy)
+    lib().oc_undistort_points(xy.ctypes.data_as(f32p), len(xy), K4.ctypes.data_as(f32p), dist.ctypes.data_as(f32p),
+                              len(dist), out.ctypes.data_as(f32p))
     return out
 
 

@@ -994,3 +994,60 @@ void oc_window_top2(const OcKeyPoint* kps, const uint8_t* desc, int n, const uin
     }
     free(cnt); free(cell); free(tab); free(fill);
 }
+
+/* ------------------------------------------------------------------ cv::remap INTER_LINEAR, CV_8UC1, BORDER_CONSTANT(0)
+ * (the rectification of Examples/Stereo/stereo_euroc.cc:136-137; maps from cv::initUndistortRectifyMap(.., CV_32F, ..), :97-98).
+ * OpenCV 4.x imgproc/imgwarp.cpp: the CV_32FC1 map pair is converted to fixed point with INTER_BITS = 5,
+ *   sx = cvRound(map1 * 32), sy = cvRound(map2 * 32)      (f32 product, round half even)
+ *   (ix, iy) = saturate_cast<short>(sx >> 5, sy >> 5),   a = sx & 31, b = sy & 31
+ * and remapBilinear<FixedPtCast<int, uchar, 15>> blends with the short table w = {(32-a)(32-b), a(32-b), (32-a)b, ab} * 32
+ * (exact: the float table entries are multiples of 2^-10, so the table needs no sum correction):
+ *   dst = (p00*w00 + p01*w01 + p10*w10 + p11*w11 + 2^14) >> 15,   taps outside the source read the constant 0.
+ * Pinned bit-exact against cv2 4.13 (tests/golden/prims2_cv2.npz). */
+static int sat_short(int v) { return v < -32768 ? -32768 : v > 32767 ? 32767 : v; }
+void oc_remap_linear_8u(const uint8_t* src, int sw, int sh, int sstride, const float* map1, const float* map2,
+                        int map_stride, int dw, int dh, uint8_t* dst, int dstride)
+{
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            const int sx = oc_round_f(map1[(size_t)y * map_stride + x] * 32.0f);
+            const int sy = oc_round_f(map2[(size_t)y * map_stride + x] * 32.0f);
+            const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5), a = sx & 31, b = sy & 31;
+            int p[4];
+            for (int k = 0; k < 4; k++) {
+                const int xx = ix + (k & 1), yy = iy + (k >> 1);
+                p[k] = (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[(size_t)yy * sstride + xx] : 0;
+            }
+            const int v = p[0] * ((32 - a) * (32 - b) * 32) + p[1] * (a * (32 - b) * 32) +
+                          p[2] * ((32 - a) * b * 32) + p[3] * (a * b * 32);
+            dst[(size_t)y * dstride + x] = (uint8_t)((v + (1 << 14)) >> 15);
+        }
+}
+
+/* ------------------------------------------------------------------ cv::undistortPoints(src, dst, K, D, Mat(), K)
+ * as called by Frame::UndistortKeyPoints (Frame.cc:471-506) and Frame::ComputeImageBounds (:508-538).
+ * OpenCV 4.x calib3d/undistort: double arithmetic, 5 fixed-point iterations (default TermCriteria(MAX_ITER, 5, 0.01)),
+ * identity R, P = K, no tilt; k = (k1, k2, p1, p2, k3) with k3 = 0 when only four coefficients are given.
+ * K4 = (fx, fy, cx, cy) as f32 (mK is CV_32F, Frame.cc:91-103). Pinned bit-exact against cv2 4.13. */
+void oc_undistort_points(const float* xy, int n, const float* K4, const float* dist, int ndist, float* out_xy)
+{
+    double k[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < ndist && i < 5; i++) k[i] = (double)dist[i];
+    const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3], ifx = 1.0 / fx, ify = 1.0 / fy;
+    for (int i = 0; i < n; i++) {
+        const double u = xy[2 * i], v = xy[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        out_xy[2 * i] = (float)(fx * x + cx);
+        out_xy[2 * i + 1] = (float)(fy * y + cy);
+    }
+}

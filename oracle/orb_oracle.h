@@ -31,6 +31,10 @@ void  oc_border_reflect101(uint8_t* whole, int w, int h, int stride, int border)
 void  oc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
 void  oc_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb,
                   uint8_t* dst, int dstride);                 /* cv::cvtColor(.., CV_{RGB,BGR,RGBA,BGRA}2GRAY), 8U */
+void  oc_remap_linear_8u(const uint8_t* src, int sw, int sh, int sstride, const float* map1, const float* map2,
+                         int map_stride, int dw, int dh, uint8_t* dst, int dstride);  /* cv::remap INTER_LINEAR, BORDER_CONSTANT 0 */
+void  oc_undistort_points(const float* xy, int n, const float* K4, const float* dist, int ndist,
+                          float* out_xy);                      /* cv::undistortPoints(src,dst,K,D,Mat(),K), Frame.cc:471-538 */
 int   oc_fast_score(const uint8_t* p, int stride);           /* cornerScore<16> with threshold floor 0 */
 int   oc_fast9_16(const uint8_t* roi, int w, int h, int stride, int threshold, int nms,
                   OcKeyPoint* out, int cap);                 /* cv::FAST(roi, kps, threshold, nms) */

@@ -67,6 +67,14 @@ def lib():
                                                C.c_void_p, C.c_int, i32p, C.c_void_p]
         L.orbx_extract_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_set_rectify_maps.argtypes = [C.c_void_p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orbx_extract_batch_rectified.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int, i32p,
+                                                   C.c_void_p]
+        L.orbx_extract_device_rectified.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_undistort_keypoints.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_void_p, C.c_int]
+        L.orbx_undistort_keypoints_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbx_image_bounds.argtypes = [C.c_int, C.c_int, f32p, f32p, C.c_int, f32p, C.c_int]
         L.orbx_synchronize.argtypes = [C.c_void_p]
         L.orbx_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
@@ -201,6 +209,35 @@ class ORBextractor:
         _ck(self._L.orbx_extract_batch(self._h, ptrs, n, w, h, w, kps.ctypes.data, cap, nk.ctypes.data_as(i32p), desc.ctypes.data))
         return [kps[i, :nk[i]].copy() for i in range(n)], [desc[i, :nk[i]].copy() for i in range(n)]
 
+    # ---- stereo rectification in front of the extractor (Examples/Stereo/stereo_euroc.cc:97-98, 136-137)
+    def set_rectify_maps(self, map1, map2, src_size=None):
+        """map1 / map2: the CV_32FC1 pair of cv::initUndistortRectifyMap (None, None clears). src_size = (w, h) of the
+        unrectified frames (default: the maps' own size)."""
+        if map1 is None and map2 is None:
+            _ck(self._L.orbx_set_rectify_maps(self._h, None, None, 0, 0, 0, 0, 0)); return
+        map1 = np.ascontiguousarray(map1, np.float32); map2 = np.ascontiguousarray(map2, np.float32)
+        assert map1.shape == map2.shape and map1.ndim == 2
+        mh, mw = map1.shape
+        sw, sh = src_size if src_size is not None else (mw, mh)
+        _ck(self._L.orbx_set_rectify_maps(self._h, map1.ctypes.data_as(f32p), map2.ctypes.data_as(f32p), mw, mh, mw, sw, sh))
+        self._map_size = (mw, mh)
+
+    def extract_rectified(self, images):
+        """images: (n, h, w) or a list of UNRECTIFIED uint8 frames; cv::remap(.., INTER_LINEAR) is fused into level 0."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        mw, mh = self._map_size
+        _ck(self._L.orbx_reserve(self._h, mw, mh, min(n, 64)))
+        cap = self._L.orbx_max_keypoints(self._h)
+        kps = np.zeros((n, cap), KP_DTYPE); desc = np.zeros((n, cap, 32), np.uint8); nk = np.zeros(n, np.int32)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        _ck(self._L.orbx_extract_batch_rectified(self._h, ptrs, n, imgs[0].shape[1], kps.ctypes.data, cap,
+                                                 nk.ctypes.data_as(i32p), desc.ctypes.data))
+        return [kps[i, :nk[i]].copy() for i in range(n)], [desc[i, :nk[i]].copy() for i in range(n)]
+
+    def extract_device_rectified(self, d_images, n, stride, frame_pitch, d_kps, cap, d_nkp, d_desc, stream=0):
+        _ck(self._L.orbx_extract_device_rectified(self._h, d_images, n, stride, frame_pitch, d_kps, cap, d_nkp, d_desc, stream))
+
     # ---- device-resident form used by bench.py (pointers are plain integers, e.g. torch.Tensor.data_ptr())
     def reserve(self, width, height, max_batch):
         _ck(self._L.orbx_reserve(self._h, width, height, max_batch))
@@ -302,6 +339,25 @@ def stereo_match_device(left: ORBextractor, right: ORBextractor, pairs, d_kl, d_
 
 
 WQ_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"), ("xr", "<f4")])
+
+
+def undistort_keypoints(keypoints, K4, dist, device: int = 0):
+    """Frame::UndistortKeyPoints (Frame.cc:471-506): mvKeys -> mvKeysUn. K4 = (fx, fy, cx, cy), dist = (k1, k2, p1, p2[, k3])."""
+    kps = np.ascontiguousarray(keypoints, KP_DTYPE)
+    K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(kps)
+    _ck(lib().orbx_undistort_keypoints(kps.ctypes.data, len(kps), K4.ctypes.data_as(f32p), dist.ctypes.data_as(f32p), len(dist),
+                                       out.ctypes.data, device))
+    return out
+
+
+def image_bounds(width, height, K4, dist, device: int = 0):
+    """Frame::ComputeImageBounds (Frame.cc:508-538) -> (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+    K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    b = np.zeros(4, np.float32)
+    _ck(lib().orbx_image_bounds(width, height, K4.ctypes.data_as(f32p), dist.ctypes.data_as(f32p), len(dist),
+                                b.ctypes.data_as(f32p), device))
+    return b
 
 
 def window_top2(keypoints, descriptors, occupied, u_right, minX, minY, invW, invH, queries, query_descriptors, device: int = 0):

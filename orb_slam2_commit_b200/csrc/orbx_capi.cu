@@ -47,6 +47,8 @@ struct orbx_extractor {
     int* d_nkp = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t slot_stream[2] = {nullptr, nullptr};   // host-path double buffering (copy/compute overlap)
+    uint2* d_remap = nullptr;                     // fixed-point rectification map (orbx_set_rectify_maps)
+    int map_w = 0, map_h = 0, map_src_w = 0, map_src_h = 0;
     int pyr_base = 0;                             // first working-set frame of the last pipeline run
     void* stereo_scratch = nullptr; size_t stereo_scratch_bytes = 0;   // SAD per left keypoint (stereo matcher)
     int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
@@ -129,6 +131,7 @@ extern "C" void orbx_destroy(orbx_extractor* h)
 {
     if (!h) return;
     release_device(h);
+    cudaFree(h->d_remap);
     for (int r = 0; r < orbx_extractor::RING; r++)
         for (int i = 0; i < 5; i++) if (h->ev[r][i]) cudaEventDestroy(h->ev[r][i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -323,7 +326,7 @@ extern "C" int orbx_max_keypoints(const orbx_extractor* h) { return (h && h->W) 
 // streams, each in its own half of the working set)
 static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stride, size_t frame_pitch,
                         OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st, int base = 0,
-                        int channels = 1, int rgb = 0)
+                        int channels = 1, int rgb = 0, bool rectify = false)
 {
     OrbxFrameLayout Lb = h->L;
     if (base) {
@@ -339,7 +342,8 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     const bool tm = h->timing;
     cudaEvent_t* ev = h->ev[h->runs % orbx_extractor::RING];
     if (tm) cudaEventRecord(ev[0], st);
-    orbx_launch_pyramid(Lb, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st, channels, rgb);
+    orbx_launch_pyramid(Lb, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st, channels, rgb,
+                        rectify ? h->d_remap : nullptr, h->map_src_w, h->map_src_h);
     if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(Lb, h->max_tile_w, h->max_tile_h, n, st);
     if (tm) cudaEventRecord(ev[2], st);
@@ -368,6 +372,22 @@ extern "C" int orbx_extract_device(orbx_extractor* h, const uint8_t* d_images, i
     CK(cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     return run_pipeline(h, d_images, n, stride, frame_pitch_bytes, (OrbxKp28*)d_keypoints, d_descriptors, cap, d_nkp, st);
+}
+
+extern "C" int orbx_extract_device_rectified(orbx_extractor* h, const uint8_t* d_images, int n, int stride,
+                                             size_t frame_pitch_bytes, OrbxKeyPoint* d_keypoints, int cap, int32_t* d_nkp,
+                                             uint8_t* d_descriptors, void* cuda_stream)
+{
+    if (!h || !d_images || !d_keypoints || !d_nkp || !d_descriptors) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (!h->d_remap) return fail(ORBX_ERR_STATE, "orbx_set_rectify_maps has not been called");
+    if (n <= 0 || stride < h->map_src_w || cap <= 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    if (h->map_w != h->W || h->map_h != h->H || n > h->max_batch) {
+        int rc = orbx_reserve(h, h->map_w, h->map_h, std::max(n, h->max_batch));
+        if (rc != ORBX_OK) return rc;
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    return run_pipeline(h, d_images, n, stride, frame_pitch_bytes, (OrbxKp28*)d_keypoints, d_descriptors, cap, d_nkp, st, 0, 1, 0, true);
 }
 
 extern "C" int orbx_synchronize(orbx_extractor* h)
@@ -409,14 +429,17 @@ extern "C" int orbx_get_stage_ms(orbx_extractor* h, float* ms4, int* nruns)
 }
 
 static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
-                              int stride, int channels, int rgb, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
+                              int stride, int channels, int rgb, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors,
+                              bool rectify = false)
 {
     if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
     if (n <= 0 || !images || width <= 0 || height <= 0) return ORBX_OK;        // empty input: silent, like :1141
+    // with a rectification map the frames have the map's SOURCE size and the pyramid has the map's own size
+    const int gw = rectify ? h->map_w : width, gh = rectify ? h->map_h : height;
     if (channels != 1 && channels != 3 && channels != 4) return fail(ORBX_ERR_INVALID, "channels must be 1, 3 or 4 (Tracking.cc:174-199)");
     if (!keypoints || !nkp || !descriptors || cap < 0 || stride < width * channels) return fail(ORBX_ERR_INVALID, "bad output buffers");
-    if (width != h->W || height != h->H || h->max_batch < 1) {
-        int rc = orbx_reserve(h, width, height, std::max(1, std::min(n, std::max(h->max_batch, 64))));
+    if (gw != h->W || gh != h->H || h->max_batch < 1) {
+        int rc = orbx_reserve(h, gw, gh, std::max(1, std::min(n, std::max(h->max_batch, 64))));
         if (rc != ORBX_OK) return rc;
     }
     CK(cudaSetDevice(h->device));
@@ -460,7 +483,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
                 CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, rowbytes, images[f0 + i], stride, rowbytes, height,
                                      cudaMemcpyHostToDevice, st));
             }
-        int rc = run_pipeline(h, d_in, m, rowbytes, fbytes, d_kps, d_desc, kc, d_nkp, st, base, channels, rgb);
+        int rc = run_pipeline(h, d_in, m, rowbytes, fbytes, d_kps, d_desc, kc, d_nkp, st, base, channels, rgb, rectify);
         if (rc != ORBX_OK) return rc;
         CK(cudaMemcpyAsync(nkp + f0, d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (cap == kc) {
@@ -494,6 +517,43 @@ extern "C" int orbx_extract_batch_color(orbx_extractor* h, const uint8_t* const*
                                         uint8_t* descriptors)
 {
     return extract_batch_impl(h, images, n, width, height, stride, channels, rgb, keypoints, cap, nkp, descriptors);
+}
+
+// cv::initUndistortRectifyMap's CV_32FC1 map pair -> OpenCV's fixed-point form (imgwarp.cpp, INTER_BITS = 5), once.
+extern "C" int orbx_set_rectify_maps(orbx_extractor* h, const float* map1, const float* map2, int map_width, int map_height,
+                                     int map_stride, int src_width, int src_height)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    cudaFree(h->d_remap); h->d_remap = nullptr; h->map_w = h->map_h = h->map_src_w = h->map_src_h = 0;
+    if (!map1 && !map2) return ORBX_OK;                                        // clear
+    if (!map1 || !map2 || map_width <= 0 || map_height <= 0 || map_stride < map_width || src_width <= 0 || src_height <= 0)
+        return fail(ORBX_ERR_INVALID, "bad rectification maps");
+    if (src_width > 32766 || src_height > 32766) return fail(ORBX_ERR_UNSUPPORTED, "source frame too large for 16-bit map coordinates");
+    std::vector<uint2> fx((size_t)map_width * map_height);
+    auto sat = [](int v) { return v < -32768 ? -32768 : v > 32767 ? 32767 : v; };
+    for (int y = 0; y < map_height; y++)
+        for (int x = 0; x < map_width; x++) {
+            const int sx = round_half_even(map1[(size_t)y * map_stride + x] * 32.0f);
+            const int sy = round_half_even(map2[(size_t)y * map_stride + x] * 32.0f);
+            const int ix = sat(sx >> 5), iy = sat(sy >> 5);
+            fx[(size_t)y * map_width + x] = make_uint2(((uint32_t)ix & 0xffffu) | ((uint32_t)iy << 16),
+                                                       (uint32_t)(sx & 31) | ((uint32_t)(sy & 31) << 5));
+        }
+    CK(cudaMalloc(&h->d_remap, fx.size() * sizeof(uint2)));
+    CK(cudaMemcpy(h->d_remap, fx.data(), fx.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    h->map_w = map_width; h->map_h = map_height; h->map_src_w = src_width; h->map_src_h = src_height;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extract_batch_rectified(orbx_extractor* h, const uint8_t* const* images, int n, int stride,
+                                            OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (!h->d_remap) return fail(ORBX_ERR_STATE, "orbx_set_rectify_maps has not been called");
+    return extract_batch_impl(h, images, n, h->map_src_w, h->map_src_h, stride, 1, 0, keypoints, cap, nkp, descriptors, true);
 }
 
 extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height, int stride,
@@ -922,5 +982,74 @@ extern "C" int orbx_window_top2(const OrbxKeyPoint* kps, const uint8_t* desc, in
     } while (0);
     cudaFree(pool);
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:471-538)
+static int undistort_args(const float* K4, const float* dist, int ndist, OrbxUndistortArgs* a)
+{
+    if (!K4 || ndist < 0 || ndist > 5 || (ndist > 0 && !dist)) return fail(ORBX_ERR_INVALID, "K4 = (fx, fy, cx, cy) and up to 5 distortion coefficients required");
+    a->fx = K4[0]; a->fy = K4[1]; a->cx = K4[2]; a->cy = K4[3];
+    a->ifx = 1.0 / a->fx; a->ify = 1.0 / a->fy;
+    for (int i = 0; i < 5; i++) a->k[i] = i < ndist ? (double)dist[i] : 0.0;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_undistort_keypoints_device(const OrbxKeyPoint* d_in, int n, const float* K4, const float* dist, int ndist,
+                                               OrbxKeyPoint* d_out, void* cuda_stream)
+{
+    if (n < 0 || (n > 0 && (!d_in || !d_out))) return fail(ORBX_ERR_INVALID, "bad argument");
+    OrbxUndistortArgs a;
+    int rc = undistort_args(K4, dist, ndist, &a);
+    if (rc != ORBX_OK) return rc;
+    if (n == 0) return ORBX_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (ndist == 0 || dist[0] == 0.0f) {                                       // Frame.cc:474-478: mvKeysUn = mvKeys
+        if (d_out != d_in) CK(cudaMemcpyAsync(d_out, d_in, (size_t)n * sizeof(OrbxKp28), cudaMemcpyDeviceToDevice, st));
+        return ORBX_OK;
+    }
+    orbx_launch_undistort((const OrbxKp28*)d_in, (OrbxKp28*)d_out, n, a, st);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_undistort_keypoints(const OrbxKeyPoint* in, int n, const float* K4, const float* dist, int ndist,
+                                        OrbxKeyPoint* out, int device)
+{
+    if (n < 0 || (n > 0 && (!in || !out))) return fail(ORBX_ERR_INVALID, "bad argument");
+    OrbxUndistortArgs a;
+    int rc = undistort_args(K4, dist, ndist, &a);
+    if (rc != ORBX_OK) return rc;
+    if (n == 0) return ORBX_OK;
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    OrbxKp28* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * sizeof(OrbxKp28)));
+    cudaError_t e;
+    do {
+        if ((e = cudaMemcpy(d, in, (size_t)n * sizeof(OrbxKp28), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (ndist > 0 && dist[0] != 0.0f) orbx_launch_undistort(d, d, n, a, 0);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        e = cudaMemcpy(out, d, (size_t)n * sizeof(OrbxKp28), cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_image_bounds(int width, int height, const float* K4, const float* dist, int ndist, float* bounds4, int device)
+{
+    if (!bounds4 || width <= 0 || height <= 0) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (ndist == 0 || !dist || dist[0] == 0.0f) {                              // Frame.cc:530-536
+        bounds4[0] = 0.f; bounds4[1] = (float)width; bounds4[2] = 0.f; bounds4[3] = (float)height;
+        return ORBX_OK;
+    }
+    OrbxKeyPoint c[4] = {};
+    c[1].x = (float)width; c[2].y = (float)height; c[3].x = (float)width; c[3].y = (float)height;
+    int rc = orbx_undistort_keypoints(c, 4, K4, dist, ndist, c, device);
+    if (rc != ORBX_OK) return rc;
+    bounds4[0] = std::min(c[0].x, c[2].x); bounds4[1] = std::max(c[1].x, c[3].x);    // mnMinX, mnMaxX (Frame.cc:524-527)
+    bounds4[2] = std::min(c[0].y, c[1].y); bounds4[3] = std::max(c[2].y, c[3].y);    // mnMinY, mnMaxY
     return ORBX_OK;
 }

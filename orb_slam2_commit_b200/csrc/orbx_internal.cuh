@@ -77,7 +77,8 @@ struct OrbxKp28 { float x, y, size, angle, response; int octave, class_id; };
 
 // kernel launchers (implemented in the .cu files; all asynchronous on `st`)
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
-                         int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels = 1, int rgb = 0);
+                         int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels = 1, int rgb = 0,
+                         const uint2* d_remap = nullptr, int src_w = 0, int src_h = 0);
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);
 void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
@@ -122,6 +123,10 @@ struct OrbxWindowArgs {        // windowed top-2 on the Frame grid (Frame.cc:388
     int *best_idx, *best_dist, *best_level, *best_dist2, *best_level2;
 };
 void orbx_launch_window_top2(const OrbxWindowArgs& a, cudaStream_t st);
+
+// cv::undistortPoints(src, dst, K, D, Mat(), K): intrinsics and (k1, k2, p1, p2, k3) widened to f64 on the host
+struct OrbxUndistortArgs { double fx, fy, cx, cy, ifx, ify, k[5]; };
+void orbx_launch_undistort(const OrbxKp28* d_in, OrbxKp28* d_out, int n, const OrbxUndistortArgs& a, cudaStream_t st);
 void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, const OrbxKp28* kr, const uint8_t* dr,
                                 int nr, const int* row_start, const int* row_tab, int rows, float minD, float maxD,
                                 int* best_idx, int* best_dist, cudaStream_t st);

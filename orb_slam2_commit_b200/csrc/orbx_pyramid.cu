@@ -79,6 +79,50 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_color_kernel(OrbxF
     }
 }
 
+// level 0 through a rectification map: cv::remap(im, imRect, M1, M2, INTER_LINEAR) of Examples/Stereo/stereo_euroc.cc:136-137
+// fused into the level-0 write (the rectified frame never exists outside the pyramid). `map` holds OpenCV's fixed-point
+// form of the CV_32FC1 map pair (built once on the host in OpenCV's sequence): x = (int16 ix) | (int16 iy) << 16,
+// y = a | b << 5 with ix = sx >> 5, a = sx & 31, sx = cvRound(map1 * 32). Bilinear taps outside the source read 0
+// (BORDER_CONSTANT), dst = (sum p*w + 2^14) >> 15 with w = {(32-a)(32-b), a(32-b), (32-a)b, ab} * 32.
+__global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_remap_kernel(OrbxFrameLayout L, const uint8_t* __restrict__ img,
+                                                                            int stride, size_t frame_pitch,
+                                                                            const uint2* __restrict__ map, int sw, int sh)
+{
+    const OrbxLevelGeom g = L.lvl[0];
+    const int t = blockIdx.x * PYR_TX + threadIdx.x;
+    const int rb0 = (blockIdx.y * PYR_TY + threadIdx.y) * PYR_RPT;
+    const int cb = 12 + 4 * t;
+    const int rows = g.h + 2 * ORBX_EDGE;
+    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb0 >= rows) return;
+    int xr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) xr[k] = reflect101(cb + k - ORBX_XOFF, g.w);
+    const uint8_t* fimg = img + (size_t)blockIdx.z * frame_pitch;
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
+#pragma unroll 2
+    for (int rr = 0; rr < PYR_RPT; rr++) {
+        if (rb0 + rr >= rows) break;
+        const uint2* mrow = map + (size_t)reflect101(rb0 + rr - ORBX_EDGE, g.h) * g.w;
+        uint2 m[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) m[k] = __ldg(mrow + xr[k]);
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ix = (short)(m[k].x & 0xffffu), iy = (int)m[k].x >> 16;
+            const int a = m[k].y & 31, b = (m[k].y >> 5) & 31;
+            const bool x0 = (unsigned)ix < (unsigned)sw, x1 = (unsigned)(ix + 1) < (unsigned)sw;
+            const bool y0 = (unsigned)iy < (unsigned)sh, y1 = (unsigned)(iy + 1) < (unsigned)sh;
+            const uint8_t* p = fimg + (ptrdiff_t)iy * stride + ix;
+            const int p00 = (x0 && y0) ? __ldg(p) : 0, p01 = (x1 && y0) ? __ldg(p + 1) : 0;
+            const int p10 = (x0 && y1) ? __ldg(p + stride) : 0, p11 = (x1 && y1) ? __ldg(p + stride + 1) : 0;
+            const int v = (p00 * ((32 - a) * (32 - b)) + p01 * (a * (32 - b)) + p10 * ((32 - a) * b) + p11 * (a * b) + 512) >> 10;
+            out |= (uint32_t)v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)rr * g.pitch) = out;
+    }
+}
+
 // level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows: the four
 // x-taps are fetched once and up to 16*PYR_RPT independent source-pixel loads are in flight per thread.
 __global__ void __launch_bounds__(PYR_TX * PYR_TY, 8) pyr_resize_kernel(OrbxFrameLayout L, int level)
@@ -120,7 +164,8 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY, 8) pyr_resize_kernel(OrbxFram
 }
 
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
-                         int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels, int rgb)
+                         int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels, int rgb,
+                         const uint2* d_remap, int src_w, int src_h)
 {
     (void)w; (void)h;
     for (int l = 0; l < L.nlevels; l++) {
@@ -129,7 +174,8 @@ void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, c
         const int rows = g.h + 2 * ORBX_EDGE;
         dim3 block(PYR_TX, PYR_TY);
         dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY * PYR_RPT - 1) / (PYR_TY * PYR_RPT), nframes);
-        if (l == 0 && channels > 1) pyr_level0_color_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, channels, rgb);
+        if (l == 0 && d_remap) pyr_level0_remap_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, d_remap, src_w, src_h);
+        else if (l == 0 && channels > 1) pyr_level0_color_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, channels, rgb);
         else if (l == 0) pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
         else pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
     }

@@ -109,3 +109,37 @@ def synth_descriptors(n_train: int, n_query: int, seed: int = 42, max_flips: int
         dst = (src + 1 + j * 7919) % n_train
         train[dst] = train[src]
     return np.ascontiguousarray(train), np.ascontiguousarray(query)
+
+
+# Camera models as shipped with upstream ORB-SLAM2's example settings (the YAMLs are not in the reference snapshot):
+# EuRoC.yaml LEFT.K / LEFT.D / LEFT.R / LEFT.P (stereo rectification, Examples/Stereo/stereo_euroc.cc:70-98) and
+# TUM1.yaml Camera.* (Frame::UndistortKeyPoints, Frame.cc:471-506).
+EUROC_LEFT = dict(
+    K=np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]]),
+    D=np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0]),
+    R=np.array([[0.999966347530033, -0.001422739138722922, 0.008079580483432283],
+                [0.001365741834644127, 0.9999741760894847, 0.007055629199258132],
+                [-0.008089410156878961, -0.007044357138835809, 0.9999424675829176]]),
+    P=np.array([[435.2046959714599, 0, 367.4517211914062], [0, 435.2046959714599, 252.2008514404297], [0, 0, 1]]))
+TUM1_K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+TUM1_DIST = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+
+
+def rectify_maps(width: int, height: int, cam: dict = EUROC_LEFT, scale: float = 1.0):
+    """The CV_32FC1 map pair cv::initUndistortRectifyMap(K, D, R, P, size, CV_32F) would hand to cv::remap: for every
+    rectified pixel the source coordinate (inverse mapping through R^-1, the distortion model and K). float64 numpy,
+    rounded to float32 once — inputs for the remap parity tests, not a bit-exact copy of OpenCV's map builder."""
+    S = np.diag([scale, scale, 1.0])
+    K = S @ cam["K"]; P = S @ cam["P"]
+    k1, k2, p1, p2, k3 = cam["D"]
+    iR = np.linalg.inv(P @ cam["R"])
+    u, v = np.meshgrid(np.arange(width, dtype=np.float64), np.arange(height, dtype=np.float64))
+    X = iR[0, 0] * u + iR[0, 1] * v + iR[0, 2]
+    Y = iR[1, 0] * u + iR[1, 1] * v + iR[1, 2]
+    W = iR[2, 0] * u + iR[2, 1] * v + iR[2, 2]
+    x = X / W; y = Y / W
+    r2 = x * x + y * y
+    kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = x * kr + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * kr + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return (K[0, 0] * xd + K[0, 2]).astype(np.float32), (K[1, 1] * yd + K[1, 2]).astype(np.float32)

@@ -436,3 +436,72 @@ def test_clustered_keypoints_deep_quadtree():
             ko, do = ob.Extractor(nf, 1.2, 8, 20, 7).extract(img)
             assert len(ko) > floor
             _check_against(kps, desc, ko, do, f"clustered {len(patches)} patches nf={nf}")
+
+
+def test_rectified_extract_matches_oracle():
+    """stereo_euroc.cc:136-137: cv::remap(im, imRect, M1, M2, INTER_LINEAR) fused into level 0. Level 0 must equal the
+    oracle's remap (pinned to cv2 4.13) bit for bit and everything downstream must equal the oracle extractor run on it."""
+    c = _cfg("euroc")
+    m1, m2 = synth.rectify_maps(c["width"], c["height"])
+    ex = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    ex.set_rectify_maps(m1, m2)
+    imgs = [synth.synth_image(c["width"], c["height"], 1200 + i) for i in range(3)]
+    kps, descs = ex.extract_rectified(imgs)
+    orc = ob.Extractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    for i, im in enumerate(imgs):
+        rect = ob.remap(im, m1, m2)
+        assert np.array_equal(ex.pyramid_level(0, frame=i), rect), f"rectified level 0 of frame {i}"
+        ko, do = orc.extract(rect)
+        _check_against(kps[i], descs[i], ko, do, f"rectified frame {i}")
+    # the plain entry point still takes rectified frames as they are
+    k2, d2 = ex(ob.remap(imgs[0], m1, m2))
+    _check_against(k2, d2, kps[0], descs[0], "plain call after a rectified call")
+
+
+def test_rectified_wild_maps_and_source_size():
+    """Maps that leave the source (BORDER_CONSTANT 0), hit exact 1/64 ties and address a source of another size."""
+    rng = np.random.default_rng(9)
+    sw, sh, mw, mh = 300, 200, 320, 240
+    src = synth.synth_image(sw, sh, 31)
+    yy, xx = np.mgrid[0:mh, 0:mw].astype(np.float32)
+    m1 = (xx * (sw + 30) / mw - 15 + rng.random((mh, mw), dtype=np.float32) * 2).astype(np.float32)
+    m2 = (yy * (sh + 30) / mh - 15 + rng.random((mh, mw), dtype=np.float32) * 2).astype(np.float32)
+    m1[::7] = np.round(m1[::7] * 64) / 64; m2[::5] = np.round(m2[::5] * 64) / 64
+    m1[3, :6] = [-1, -0.5, sw - 1, sw - 0.5, sw, 1e6]; m2[3, :6] = [-1, sh - 1, sh - 0.5, sh, -0.5, -1e6]
+    ex = ORBextractor(500, 1.2, 4, 20, 7)
+    ex.set_rectify_maps(m1, m2, src_size=(sw, sh))
+    kps, descs = ex.extract_rectified([src])
+    rect = ob.remap(src, m1, m2)
+    assert np.array_equal(ex.pyramid_level(0), rect)
+    ko, do = ob.Extractor(500, 1.2, 4, 20, 7).extract(rect)
+    assert len(ko) > 100
+    _check_against(kps[0], descs[0], ko, do, "wild maps")
+
+
+def test_undistort_keypoints_bit_exact(golden_dir):
+    """Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:471-538) against cv2 4.13's undistortPoints (golden) and
+    against the oracle on real keypoints of every octave."""
+    from orb_slam2_commit_b200 import KP_DTYPE, image_bounds, undistort_keypoints
+    g = np.load(os.path.join(golden_dir, "prims2_cv2.npz"))
+    pts = g["undist_src"]
+    kin = np.zeros(len(pts), KP_DTYPE); kin["x"] = pts[:, 0]; kin["y"] = pts[:, 1]; kin["octave"] = 3; kin["angle"] = 12.5
+    for nd, key in ((5, "undist_dst5"), (4, "undist_dst4")):
+        out = undistort_keypoints(kin, g["undist_K4"], g["undist_D"][:nd])
+        assert np.array_equal(out["x"].view(np.uint32), g[key][:, 0].view(np.uint32))
+        assert np.array_equal(out["y"].view(np.uint32), g[key][:, 1].view(np.uint32))
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(out[f], kin[f])
+    kps, _ = ORBextractor(1000, 1.2, 8, 20, 7)(synth.synth_image(640, 480, 3))
+    out = undistort_keypoints(kps, synth.TUM1_K4, synth.TUM1_DIST)
+    ref = ob.undistort_points(np.stack([kps["x"], kps["y"]], 1), synth.TUM1_K4, synth.TUM1_DIST)
+    assert np.array_equal(out["x"].view(np.uint32), ref[:, 0].view(np.uint32))
+    assert np.array_equal(out["y"].view(np.uint32), ref[:, 1].view(np.uint32))
+    assert np.abs(out["x"] - kps["x"]).max() > 0.5                      # the model really moves points
+    # k1 == 0: mvKeysUn = mvKeys (Frame.cc:474-478)
+    same = undistort_keypoints(kps, synth.TUM1_K4, np.zeros(5, np.float32))
+    assert same.tobytes() == kps.tobytes()
+    # ComputeImageBounds = min / max over the four undistorted corners (first four golden points)
+    b = image_bounds(640, 480, g["undist_K4"], g["undist_D"])
+    c = g["undist_dst5"][:4]
+    assert np.array_equal(b, np.array([min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])], np.float32))
+    assert np.array_equal(image_bounds(640, 480, synth.TUM1_K4, np.zeros(4, np.float32)), np.array([0, 640, 0, 480], np.float32))

@@ -4,6 +4,7 @@
   prims_cv2.npz      inputs + outputs of the cv2 4.13 primitives the reference calls
                      (resize INTER_LINEAR, copyMakeBorder REFLECT_101, GaussianBlur 7x7 s2, FAST 9-16 NMS at
                      T=20 and T=7 on whole images and cell-sized crops, fastAtan2)
+  prims2_cv2.npz     cv2.remap INTER_LINEAR through initUndistortRectifyMap maps, cv2.undistortPoints
   ref_<cfg>.npz      keypoints (28-byte cv::KeyPoint records) + descriptors + per-level pyramid CRCs produced by
                      oracle/_ref = the UNMODIFIED /root/reference/src/ORBextractor.cc (bump-allocator build)
   sincos.json        result of the exhaustive oc_cosf/oc_sinf == glibc cosf/sinf check
@@ -65,6 +66,45 @@ def prims():
     print("prims_cv2.npz", {k: v.shape for k, v in out.items() if k.startswith("fast_full")})
 
 
+# EuRoC MH_01 cam0 calibration as shipped with upstream ORB-SLAM2's EuRoC.yaml (LEFT.K / D / R / P), scaled by 1/4 so
+# the golden maps stay small; TUM1.yaml intrinsics + distortion for undistortPoints.
+EUROC_K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+EUROC_D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0])
+EUROC_R = np.array([[0.999966347530033, -0.001422739138722922, 0.008079580483432283],
+                    [0.001365741834644127, 0.9999741760894847, 0.007055629199258132],
+                    [-0.008089410156878961, -0.007044357138835809, 0.9999424675829176]])
+EUROC_P = np.array([[435.2046959714599, 0, 367.4517211914062], [0, 435.2046959714599, 252.2008514404297], [0, 0, 1]])
+TUM1_K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+TUM1_D = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+
+
+def prims2():
+    """cv::remap (rectification, stereo_euroc.cc:136-137) and cv::undistortPoints (Frame.cc:471-538)."""
+    out = {"cv2_version": np.array(cv2.__version__)}
+    rng = np.random.default_rng(321)
+    S = np.diag([0.25, 0.25, 1.0])
+    W, H = 188, 120
+    m1, m2 = cv2.initUndistortRectifyMap(S @ EUROC_K, EUROC_D, EUROC_R, S @ EUROC_P, (W, H), cv2.CV_32F)
+    src = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    out["remap0_src"] = src; out["remap0_map1"] = m1; out["remap0_map2"] = m2
+    out["remap0_dst"] = cv2.remap(src, m1, m2, cv2.INTER_LINEAR)
+    # wild maps: out-of-range coordinates, negative values, exact .5/32 ties, source size != map size
+    src = rng.integers(0, 256, (60, 80), dtype=np.uint8)
+    m1 = (rng.random((48, 64)) * 100 - 10).astype(np.float32); m2 = (rng.random((48, 64)) * 80 - 10).astype(np.float32)
+    m1[:4] = np.round(m1[:4] * 64) / 64; m2[:4] = np.round(m2[:4] * 64) / 64
+    m1[4, :8] = [-1, -0.5, 79, 79.5, 80, -1.015625, 78.984375, 1e6]; m2[4, :8] = [-1, 59, 59.5, 60, -0.5, 3, 3, -1e6]
+    out["remap1_src"] = src; out["remap1_map1"] = m1; out["remap1_map2"] = m2
+    out["remap1_dst"] = cv2.remap(src, m1, m2, cv2.INTER_LINEAR)
+    K = np.array([[TUM1_K4[0], 0, TUM1_K4[2]], [0, TUM1_K4[1], TUM1_K4[3]], [0, 0, 1]], np.float32)
+    pts = np.stack([rng.random(2048) * 680 - 20, rng.random(2048) * 520 - 20], 1).astype(np.float32)
+    pts[:4] = [[0, 0], [640, 0], [0, 480], [640, 480]]          # ComputeImageBounds corners
+    out["undist_K4"] = TUM1_K4; out["undist_D"] = TUM1_D; out["undist_src"] = pts
+    out["undist_dst5"] = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, TUM1_D, None, K).reshape(-1, 2)
+    out["undist_dst4"] = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, TUM1_D[:4], None, K).reshape(-1, 2)
+    np.savez_compressed(os.path.join(G, "prims2_cv2.npz"), **out)
+    print("prims2_cv2.npz", os.path.getsize(os.path.join(G, "prims2_cv2.npz")))
+
+
 def ref_cases():
     assert ob.ref_available() or True
     ob.build(force=True)
@@ -98,7 +138,11 @@ def sincos():
 
 
 if __name__ == "__main__":
+    if "--prims2-only" in sys.argv:
+        prims2()
+        sys.exit(0)
     prims()
+    prims2()
     ref_cases()
     if "--sincos" in sys.argv:
         sincos()
