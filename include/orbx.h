@@ -229,6 +229,46 @@ int orbx_undistort_keypoints_device(const OrbxKeyPoint* d_in, int n, const float
 /* bounds4 = (mnMinX, mnMaxX, mnMinY, mnMaxY) of Frame::ComputeImageBounds for a width x height frame */
 int orbx_image_bounds(int width, int height, const float* K4, const float* dist, int ndist, float* bounds4, int device);
 
+/* ---- Bag of words (DBoW2 through ORBVocabulary): Frame::ComputeBoW (Frame.cc:462-469), the L1 score of
+ *      KeyFrameDatabase.cc:145,274 / LoopClosing.cc:152, and ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)
+ *      (ORBmatcher.cc:175-325) incl. the rotation-histogram check (ComputeThreeMaxima, :1797-1839).
+ *      The vocabulary is given in the order of TemplatedVocabulary::loadFromTextFile (TemplatedVocabulary.h:1338-1420):
+ *      non-root node i+1 has parent[i] (0 = root; a parent precedes its children), is_leaf[i], a 32-byte descriptor and
+ *      a weight; words are numbered in order of appearance. scoring: 0 L1_NORM .. 5 DOT_PRODUCT, weighting: 0 TF_IDF,
+ *      1 TF, 2 IDF, 3 BINARY (BowVector.h:33-54); ORBvoc.txt is "10 6 0 0". ---- */
+typedef struct orbx_vocabulary orbx_vocabulary;
+int  orbx_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,
+                       const uint8_t* descriptors, const double* weights, int device, orbx_vocabulary** out);
+void orbx_vocab_destroy(orbx_vocabulary* v);
+int  orbx_vocab_words(const orbx_vocabulary* v);
+int  orbx_vocab_nodes(const orbx_vocabulary* v);
+/* transform(features, mBowVec, mFeatVec, levelsup) for a batch: frame f has min(counts[f], cap) descriptors at
+ * descriptors + f*cap*32 — exactly the [frames][cap] layout orbx_extract_device leaves in HBM. Results stay on the
+ * device inside the vocabulary object (used by the score / SearchByBoW calls below) until the next transform;
+ * orbx_bow_get copies one frame's results out: word / node per feature, the BowVector (ascending word id, normalised
+ * value), the FeatureVector as CSR (ascending node id; fv_off has n_fv+1 entries; fv_feat lists feature indices in
+ * ascending order per node). Any output pointer may be NULL. At most 16384 features per frame. */
+int  orbx_bow_transform_device(orbx_vocabulary* v, const uint8_t* d_descriptors, const int32_t* d_counts, int frames, int cap,
+                               int levelsup, void* cuda_stream);
+int  orbx_bow_transform(orbx_vocabulary* v, const uint8_t* descriptors, const int32_t* counts, int frames, int cap, int levelsup);
+int  orbx_bow_get(orbx_vocabulary* v, int frame, int32_t* word, int32_t* node, int32_t* bow_id, double* bow_val, int32_t* n_bow,
+                  int32_t* fv_node, int32_t* fv_off, int32_t* fv_feat, int32_t* n_fv);
+/* L1Scoring::score(BowVector of frame_a[i], BowVector of frame_b[i]) for npairs pairs of frames of the last transform */
+int  orbx_bow_score(orbx_vocabulary* v, const int32_t* frame_a, const int32_t* frame_b, int npairs, double* score);
+int  orbx_bow_score_device(orbx_vocabulary* v, const int32_t* d_frame_a, const int32_t* d_frame_b, int npairs, double* d_score,
+                           void* cuda_stream);
+/* SearchByBoW for npairs (keyframe, frame) pairs taken from the last transformed batch: keypoints / descriptors are the
+ * batch the transform ran on ([frames][cap]); kf_valid[pair][cap] != 0 <=> that keyframe feature has a map point that is
+ * not bad (:212-218), NULL = all. match[pair][j] = keyframe feature matched to frame feature j or -1 (stands for
+ * vpMapPointMatches), nmatches[pair] = the return value. TH_LOW = 50. */
+int  orbx_search_by_bow_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf_frame, const int32_t* d_f_frame,
+                               const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_kf_valid,
+                               float nnratio, int check_orientation, int32_t* d_match, int32_t* d_nmatches, void* cuda_stream);
+/* one pair from host buffers (transforms both descriptor sets first) */
+int  orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoints, const uint8_t* kf_descriptors, int n_kf,
+                        const uint8_t* kf_valid, const OrbxKeyPoint* f_keypoints, const uint8_t* f_descriptors, int n_f,
+                        int levelsup, float nnratio, int check_orientation, int32_t* match_f, int32_t* nmatches);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

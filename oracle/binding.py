@@ -55,6 +55,16 @@ def lib():
         L.oc_remap_linear_8u.argtypes = [u8p, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
         L.oc_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
         L.oc_fast_score.restype = C.c_int; L.oc_fast_score.argtypes = [u8p, C.c_int]
+        L.oc_vocab_create.restype = C.c_void_p
+        L.oc_vocab_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, u8p, u8p, C.POINTER(C.c_double)]
+        L.oc_vocab_destroy.argtypes = [C.c_void_p]
+        L.oc_vocab_words.restype = C.c_int; L.oc_vocab_words.argtypes = [C.c_void_p]
+        L.oc_vocab_transform.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int] + [C.c_void_p] * 9
+        L.oc_bow_score_l1.restype = C.c_double
+        L.oc_bow_score_l1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.oc_search_by_bow.restype = C.c_int
+        L.oc_search_by_bow.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5 + \
+            [C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.oc_fast9_16.restype = C.c_int
         L.oc_fast9_16.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.oc_ic_angle.restype = C.c_float; L.oc_ic_angle.argtypes = [C.c_void_p, C.c_int, i32p]
@@ -341,3 +351,52 @@ class RefExtractor:
         a = [np.zeros(n, np.float32) for _ in range(4)]
         self.R.orbref_tables(self.h, *[x.ctypes.data_as(f32p) for x in a])
         return dict(scale_factors=a[0], inv_scale_factors=a[1], sigma2=a[2], inv_sigma2=a[3])
+
+
+class Vocabulary:
+    """DBoW2 vocabulary (restated; see orb_oracle.h). parent / is_leaf / desc / weight: one entry per non-root node in
+    text-file order."""
+
+    def __init__(self, k, L, parent, is_leaf, desc, weight, scoring=0, weighting=0):
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8); weight = np.ascontiguousarray(weight, np.float64)
+        self._h = lib().oc_vocab_create(k, L, scoring, weighting, len(parent), parent.ctypes.data_as(i32p), _u8(is_leaf), _u8(desc),
+                                        weight.ctypes.data_as(C.POINTER(C.c_double)))
+        assert self._h, "invalid vocabulary"
+        self.nwords = lib().oc_vocab_words(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oc_vocab_destroy(self._h); self._h = None
+
+    def transform(self, desc, levelsup=4):
+        """-> dict(word, node, bow_id, bow_val, fv_node, fv_off, fv_feat)"""
+        desc = np.ascontiguousarray(desc, np.uint8); n = len(desc)
+        word = np.zeros(n, np.int32); node = np.zeros(n, np.int32)
+        bow_id = np.zeros(n, np.int32); bow_val = np.zeros(n, np.float64); fv_node = np.zeros(n, np.int32)
+        fv_off = np.zeros(n + 1, np.int32); fv_feat = np.zeros(n, np.int32); nb = C.c_int32(0); nf = C.c_int32(0)
+        lib().oc_vocab_transform(self._h, _u8(desc), n, levelsup, word.ctypes.data, node.ctypes.data, bow_id.ctypes.data,
+                                 bow_val.ctypes.data, C.addressof(nb), fv_node.ctypes.data, fv_off.ctypes.data, fv_feat.ctypes.data,
+                                 C.addressof(nf))
+        return dict(word=word, node=node, bow_id=bow_id[:nb.value], bow_val=bow_val[:nb.value], fv_node=fv_node[:nf.value],
+                    fv_off=fv_off[:nf.value + 1], fv_feat=fv_feat[:fv_off[nf.value]])
+
+
+def bow_score_l1(id1, v1, id2, v2) -> float:
+    id1 = np.ascontiguousarray(id1, np.int32); id2 = np.ascontiguousarray(id2, np.int32)
+    v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
+    return lib().oc_bow_score_l1(id1.ctypes.data, v1.ctypes.data, len(id1), id2.ctypes.data, v2.ctypes.data, len(id2))
+
+
+def search_by_bow(kf, f, kf_desc, kf_angle, kf_valid, f_desc, f_angle, nnratio=0.7, check_orientation=True):
+    """kf / f: dicts from Vocabulary.transform. -> (nmatches, match_f)"""
+    kf_desc = np.ascontiguousarray(kf_desc, np.uint8); f_desc = np.ascontiguousarray(f_desc, np.uint8)
+    kf_angle = np.ascontiguousarray(kf_angle, np.float32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+    kf_valid = np.ascontiguousarray(kf_valid, np.uint8)
+    a = [np.ascontiguousarray(kf[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    b = [np.ascontiguousarray(f[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    match = np.zeros(len(f_desc), np.int32)
+    n = lib().oc_search_by_bow(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[0]), b[0].ctypes.data, b[1].ctypes.data,
+                               b[2].ctypes.data, len(b[0]), kf_desc.ctypes.data, kf_angle.ctypes.data, kf_valid.ctypes.data,
+                               f_desc.ctypes.data, f_angle.ctypes.data, len(f_desc), nnratio, int(check_orientation), match.ctypes.data)
+    return n, match

@@ -1051,3 +1051,201 @@ void oc_undistort_points(const float* xy, int n, const float* K4, const float* d
         out_xy[2 * i + 1] = (float)(fy * y + cy);
     }
 }
+
+/* ================================================================== bag of words (DBoW2)
+ * Frame::ComputeBoW (Frame.cc:462-469) = mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) with
+ * ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB> (include/ORBVocabulary.h). The reference vendors only
+ * DBoW2's HEADERS (the .h files of Thirdparty/DBoW2/DBoW2): TemplatedVocabulary.h holds transform (:1127-1196, :1216-1260) and the
+ * text loader that defines node / word numbering (:1338-1420); FORB.cpp, BowVector.cpp, FeatureVector.cpp and
+ * ScoringObject.cpp are ABSENT from the snapshot, so FORB::distance (the same 32-bit SWAR Hamming as
+ * ORBmatcher::DescriptorDistance), BowVector::addWeight / addIfNotExist / normalize, FeatureVector::addFeature and
+ * L1Scoring::score are restated from DBoW2's published algorithm (the un-versioned copy ORB-SLAM2 ships).
+ * PARITY UNPINNED for this block: no golden vectors exist and the sources cannot be compiled here. */
+struct OcVocabulary {
+    int k, L, scoring, weighting, n;      /* n = nodes incl. root (node 0) */
+    int32_t* child_off; int32_t* child;   /* CSR children lists in push_back (= ascending id) order */
+    uint8_t* desc; double* weight; int32_t* word; int nwords;
+};
+
+OcVocabulary* oc_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
+                              const uint8_t* is_leaf, const uint8_t* desc, const double* weight)
+{
+    if (n_nodes < 0 || n_nodes > (1 << 28)) return NULL;
+    OcVocabulary* v = (OcVocabulary*)calloc(1, sizeof *v);
+    v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->n = n_nodes + 1;
+    v->child_off = (int32_t*)calloc((size_t)v->n + 1, sizeof(int32_t));
+    v->child = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_nodes > 0 ? n_nodes : 1));
+    v->desc = (uint8_t*)calloc((size_t)v->n, 32);
+    v->weight = (double*)calloc((size_t)v->n, sizeof(double));
+    v->word = (int32_t*)malloc(sizeof(int32_t) * (size_t)v->n);
+    v->word[0] = -1;
+    for (int i = 0; i < n_nodes; i++) {                 /* node id = line number (TemplatedVocabulary.h:1385-1392) */
+        if (parent[i] < 0 || parent[i] > i) { oc_vocab_destroy(v); return NULL; }
+        v->child_off[parent[i] + 1]++;
+        memcpy(v->desc + 32 * (size_t)(i + 1), desc + 32 * (size_t)i, 32);
+        v->weight[i + 1] = weight[i];
+        v->word[i + 1] = is_leaf[i] ? v->nwords++ : -1; /* :1407-1414 */
+    }
+    for (int i = 0; i < v->n; i++) v->child_off[i + 1] += v->child_off[i];
+    int32_t* fill = (int32_t*)calloc((size_t)n_nodes + 1, sizeof(int32_t));
+    for (int i = 0; i < n_nodes; i++) v->child[v->child_off[parent[i]] + fill[parent[i]]++] = i + 1;
+    free(fill);
+    return v;
+}
+void oc_vocab_destroy(OcVocabulary* v)
+{
+    if (!v) return;
+    free(v->child_off); free(v->child); free(v->desc); free(v->weight); free(v->word); free(v);
+}
+int oc_vocab_words(const OcVocabulary* v) { return v->nwords; }
+
+/* transform(feature, word_id, weight, nid, levelsup), TemplatedVocabulary.h:1216-1260 */
+static void vocab_descend(const OcVocabulary* v, const uint8_t* f, int levelsup, int32_t* word, double* w, int32_t* nid)
+{
+    const int nid_level = v->L - levelsup;
+    if (nid_level <= 0) *nid = 0;
+    int final_id = 0, current_level = 0;
+    do {
+        ++current_level;
+        const int32_t* ch = v->child + v->child_off[final_id];
+        const int nch = v->child_off[final_id + 1] - v->child_off[final_id];
+        final_id = ch[0];
+        double best_d = oc_descriptor_distance(f, v->desc + 32 * (size_t)final_id);
+        for (int j = 1; j < nch; j++) {
+            const double d = oc_descriptor_distance(f, v->desc + 32 * (size_t)ch[j]);
+            if (d < best_d) { best_d = d; final_id = ch[j]; }
+        }
+        if (current_level == nid_level) *nid = final_id;
+    } while (v->child_off[final_id + 1] != v->child_off[final_id]);
+    *word = v->word[final_id]; *w = v->weight[final_id];
+}
+
+/* transform(features, v, fv, levelsup), TemplatedVocabulary.h:1127-1196. Outputs: per feature word / node (always
+ * written); the BowVector as (id ascending, value); the FeatureVector as CSR (node ascending, features in push order). */
+void oc_vocab_transform(const OcVocabulary* v, const uint8_t* desc, int n, int levelsup,
+                        int32_t* word, int32_t* node, int32_t* bow_id, double* bow_val, int32_t* n_bow,
+                        int32_t* fv_node, int32_t* fv_off, int32_t* fv_feat, int32_t* n_fv)
+{
+    *n_bow = 0; *n_fv = 0; fv_off[0] = 0;
+    if (v->n <= 1 || n <= 0) return;
+    double* acc = (double*)calloc((size_t)(v->nwords > 0 ? v->nwords : 1), sizeof(double));
+    uint8_t* present = (uint8_t*)calloc((size_t)(v->nwords > 0 ? v->nwords : 1), 1);
+    double* wts = (double*)malloc(sizeof(double) * (size_t)n);
+    int32_t* cnt = (int32_t*)calloc((size_t)v->n + 1, sizeof(int32_t));
+    const int tf = v->weighting == 0 || v->weighting == 1;            /* TF_IDF, TF: addWeight; IDF, BINARY: addIfNotExist */
+    for (int i = 0; i < n; i++) {
+        vocab_descend(v, desc + 32 * (size_t)i, levelsup, &word[i], &wts[i], &node[i]);
+        if (wts[i] > 0) {
+            if (!present[word[i]]) { present[word[i]] = 1; acc[word[i]] = wts[i]; }
+            else if (tf) acc[word[i]] += wts[i];
+            cnt[node[i] + 1]++;
+        }
+    }
+    int nb = 0;
+    for (int id = 0; id < v->nwords; id++) if (present[id]) { bow_id[nb] = id; bow_val[nb] = acc[id]; nb++; }
+    const int must = v->scoring != 5;                                  /* DOT_PRODUCT does not normalise */
+    if (tf && nb > 0 && !must) { const double nd = nb; for (int j = 0; j < nb; j++) bow_val[j] /= nd; }
+    if (must) {                                                        /* BowVector::normalize */
+        double norm = 0.0;
+        if (v->scoring != 1) { for (int j = 0; j < nb; j++) norm += fabs(bow_val[j]); }
+        else { for (int j = 0; j < nb; j++) norm += bow_val[j] * bow_val[j]; norm = sqrt(norm); }
+        if (norm > 0.0) for (int j = 0; j < nb; j++) bow_val[j] /= norm;
+    }
+    *n_bow = nb;
+    int nf = 0;
+    int32_t* start = (int32_t*)malloc(sizeof(int32_t) * ((size_t)v->n + 1));
+    int run = 0;
+    for (int id = 0; id < v->n; id++) { start[id] = run; if (cnt[id + 1]) { fv_node[nf] = id; fv_off[nf] = run; nf++; } run += cnt[id + 1]; }
+    fv_off[nf] = run;
+    for (int i = 0; i < n; i++) if (wts[i] > 0) fv_feat[start[node[i]]++] = i;
+    *n_fv = nf;
+    free(acc); free(present); free(wts); free(cnt); free(start);
+}
+
+/* L1Scoring::score (DBoW2 ScoringObject.cpp), the score of KeyFrameDatabase.cc:145,274 and LoopClosing.cc:152 */
+double oc_bow_score_l1(const int32_t* id1, const double* v1, int n1, const int32_t* id2, const double* v2, int n2)
+{
+    double score = 0;
+    int a = 0, b = 0;
+    while (a < n1 && b < n2) {
+        if (id1[a] == id2[b]) { score += fabs(v1[a] - v2[b]) - fabs(v1[a]) - fabs(v2[b]); a++; b++; }
+        else if (id1[a] < id2[b]) a++;      /* lower_bound walk == advancing the smaller side */
+        else b++;
+    }
+    return -score / 2.0;
+}
+
+/* ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:1797-1839) on bin counts */
+static void three_maxima(const int* count, int L, int* ind1, int* ind2, int* ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    *ind1 = *ind2 = *ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = count[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; *ind3 = *ind2; *ind2 = *ind1; *ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; *ind3 = *ind2; *ind2 = i; }
+        else if (s > max3) { max3 = s; *ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+#define HISTO_LENGTH 30
+static int rot_bin(float a1, float a2)      /* ORBmatcher.cc:268-277 (the 1/30 factor is the reference's) */
+{
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:175-325).
+ * kf_valid[i] != 0 <=> the keyframe's feature i has a map point that is not bad (:212-218).
+ * match_f[j] = keyframe feature matched to frame feature j, or -1 (stands for vpMapPointMatches). Returns nmatches. */
+int oc_search_by_bow(const int32_t* kf_fv_node, const int32_t* kf_fv_off, const int32_t* kf_fv_feat, int kf_nfv,
+                     const int32_t* f_fv_node, const int32_t* f_fv_off, const int32_t* f_fv_feat, int f_nfv,
+                     const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                     const uint8_t* f_desc, const float* f_angle, int f_n,
+                     float nnratio, int check_orientation, int32_t* match_f)
+{
+    int nmatches = 0;
+    int* hist_idx = (int*)malloc(sizeof(int) * (size_t)(f_n > 0 ? f_n : 1)), * hist_bin = (int*)malloc(sizeof(int) * (size_t)(f_n > 0 ? f_n : 1));
+    int nh = 0, count[HISTO_LENGTH] = {0};
+    for (int j = 0; j < f_n; j++) match_f[j] = -1;
+    int a = 0, b = 0;
+    while (a < kf_nfv && b < f_nfv) {
+        if (kf_fv_node[a] == f_fv_node[b]) {
+            for (int ik = kf_fv_off[a]; ik < kf_fv_off[a + 1]; ik++) {
+                const int realIdxKF = kf_fv_feat[ik];
+                if (!kf_valid[realIdxKF]) continue;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int jf = f_fv_off[b]; jf < f_fv_off[b + 1]; jf++) {
+                    const int realIdxF = f_fv_feat[jf];
+                    if (match_f[realIdxF] >= 0) continue;
+                    const int dist = oc_descriptor_distance(kf_desc + 32 * (size_t)realIdxKF, f_desc + 32 * (size_t)realIdxF);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= 50 && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    match_f[bestIdxF] = realIdxKF;
+                    if (check_orientation) {
+                        const int bin = rot_bin(kf_angle[realIdxKF], f_angle[bestIdxF]);
+                        hist_idx[nh] = bestIdxF; hist_bin[nh] = bin; nh++; count[bin]++;
+                    }
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (kf_fv_node[a] < f_fv_node[b]) a++;
+        else b++;
+    }
+    if (check_orientation) {
+        int i1, i2, i3;
+        three_maxima(count, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int t = 0; t < nh; t++)
+            if (hist_bin[t] != i1 && hist_bin[t] != i2 && hist_bin[t] != i3) { match_f[hist_idx[t]] = -1; nmatches--; }
+    }
+    free(hist_idx); free(hist_bin);
+    return nmatches;
+}

@@ -90,6 +90,26 @@ void  oc_window_top2(const OcKeyPoint* kps, const uint8_t* desc, int n, const ui
                      const OcWindowQuery* q, const uint8_t* qdesc, int nq,
                      int32_t* best_idx, int32_t* best_dist, int32_t* best_level, int32_t* best_dist2, int32_t* best_level2);
 
+/* ---- bag of words: DBoW2 as used through ORBVocabulary (Frame.cc:462-469, ORBmatcher.cc:175-325,
+ *      KeyFrameDatabase.cc:145). DBoW2's .cpp files are absent from the reference snapshot: PARITY UNPINNED. ----
+ * Vocabulary nodes in text-file order (TemplatedVocabulary.h:1338-1420): node i+1 has parent[i] (0 = root),
+ * is_leaf[i], a 32-byte descriptor and a weight; words are numbered in order of appearance.
+ * scoring: 0 L1_NORM 1 L2_NORM 2 CHI_SQUARE 3 KL 4 BHATTACHARYYA 5 DOT_PRODUCT; weighting: 0 TF_IDF 1 TF 2 IDF 3 BINARY. */
+typedef struct OcVocabulary OcVocabulary;
+OcVocabulary* oc_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
+                              const uint8_t* is_leaf, const uint8_t* desc, const double* weight);
+void  oc_vocab_destroy(OcVocabulary*);
+int   oc_vocab_words(const OcVocabulary*);
+void  oc_vocab_transform(const OcVocabulary* v, const uint8_t* desc, int n, int levelsup,
+                         int32_t* word, int32_t* node, int32_t* bow_id, double* bow_val, int32_t* n_bow,
+                         int32_t* fv_node, int32_t* fv_off, int32_t* fv_feat, int32_t* n_fv);
+double oc_bow_score_l1(const int32_t* id1, const double* v1, int n1, const int32_t* id2, const double* v2, int n2);
+int   oc_search_by_bow(const int32_t* kf_fv_node, const int32_t* kf_fv_off, const int32_t* kf_fv_feat, int kf_nfv,
+                       const int32_t* f_fv_node, const int32_t* f_fv_off, const int32_t* f_fv_feat, int f_nfv,
+                       const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                       const uint8_t* f_desc, const float* f_angle, int f_n,
+                       float nnratio, int check_orientation, int32_t* match_f);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,9 +5,9 @@ This package is only the thin host mirror used by the tests and bench.py: same n
 reference class (include/ORBextractor.h:51-145). There is no CPU fallback: loading fails loudly when the
 library is missing and every compute call fails when no CUDA device is visible.
 """
-from .api import (KP_DTYPE, OrbxError, ORBextractor, ORBmatcher, build_library, hamming_top2, lib, library_path,
+from .api import (KP_DTYPE, OrbxError, ORBextractor, ORBmatcher, ORBVocabulary, build_library, hamming_top2, lib, library_path,
                   image_bounds, stereo_hamming, stereo_match, stereo_match_device, undistort_keypoints, window_top2)
 
-__all__ = ["KP_DTYPE", "OrbxError", "ORBextractor", "ORBmatcher", "build_library", "hamming_top2", "lib",
+__all__ = ["KP_DTYPE", "OrbxError", "ORBextractor", "ORBmatcher", "ORBVocabulary", "build_library", "hamming_top2", "lib",
            "library_path", "image_bounds", "stereo_hamming", "stereo_match", "stereo_match_device", "undistort_keypoints",
            "window_top2"]

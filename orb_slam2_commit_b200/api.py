@@ -75,6 +75,19 @@ def lib():
         L.orbx_undistort_keypoints.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_void_p, C.c_int]
         L.orbx_undistort_keypoints_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbx_image_bounds.argtypes = [C.c_int, C.c_int, f32p, f32p, C.c_int, f32p, C.c_int]
+        L.orbx_vocab_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, u8p, u8p, C.POINTER(C.c_double), C.c_int,
+                                        C.POINTER(C.c_void_p)]
+        L.orbx_vocab_destroy.argtypes = [C.c_void_p]; L.orbx_vocab_destroy.restype = None
+        L.orbx_vocab_words.argtypes = [C.c_void_p]; L.orbx_vocab_nodes.argtypes = [C.c_void_p]
+        L.orbx_bow_transform_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orbx_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orbx_bow_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+        L.orbx_bow_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orbx_bow_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbx_search_by_bow_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_search_by_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         L.orbx_synchronize.argtypes = [C.c_void_p]
         L.orbx_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
@@ -372,6 +385,75 @@ def window_top2(keypoints, descriptors, occupied, u_right, minX, minY, invW, inv
                                None if ur is None else ur.ctypes.data, minX, minY, invW, invH, q.ctypes.data, _u8(qd), len(q),
                                *[o.ctypes.data_as(i32p) for o in out], device))
     return out
+
+
+class ORBVocabulary:
+    """DBoW2 vocabulary on the GPU (include/ORBVocabulary.h: TemplatedVocabulary<FORB::TDescriptor, FORB>).
+    parent / is_leaf / desc / weight: one entry per non-root node in ORBvoc.txt order (loadFromTextFile)."""
+
+    def __init__(self, k, L, parent, is_leaf, desc, weight, scoring=0, weighting=0, device=0):
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8); weight = np.ascontiguousarray(weight, np.float64)
+        self._L = lib(); self._h = C.c_void_p()
+        _ck(self._L.orbx_vocab_create(k, L, scoring, weighting, len(parent), parent.ctypes.data_as(i32p), _u8(is_leaf), _u8(desc),
+                                      weight.ctypes.data_as(C.POINTER(C.c_double)), device, C.byref(self._h)))
+        self.nwords = self._L.orbx_vocab_words(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orbx_vocab_destroy(self._h); self._h = None
+
+    def transform_batch(self, descs, levelsup=4):
+        """descs: list of (n_i, 32) uint8 arrays -> list of dicts (word, node, bow_id, bow_val, fv_node, fv_off, fv_feat)."""
+        frames = len(descs)
+        cap = max(1, max(len(d) for d in descs))
+        buf = np.zeros((frames, cap, 32), np.uint8); counts = np.zeros(frames, np.int32)
+        for i, d in enumerate(descs):
+            buf[i, :len(d)] = d; counts[i] = len(d)
+        _ck(self._L.orbx_bow_transform(self._h, buf.ctypes.data, counts.ctypes.data, frames, cap, levelsup))
+        return [self.get(i, int(counts[i])) for i in range(frames)]
+
+    def transform(self, desc, levelsup=4):
+        """Frame::ComputeBoW: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)."""
+        return self.transform_batch([np.ascontiguousarray(desc, np.uint8)], levelsup)[0]
+
+    def transform_device(self, d_desc, d_counts, frames, cap, levelsup=4, stream=0):
+        _ck(self._L.orbx_bow_transform_device(self._h, d_desc, d_counts, frames, cap, levelsup, stream))
+
+    def get(self, frame, n):
+        word = np.zeros(n, np.int32); node = np.zeros(n, np.int32); bow_id = np.zeros(n, np.int32); bow_val = np.zeros(n, np.float64)
+        fv_node = np.zeros(n, np.int32); fv_off = np.zeros(n + 1, np.int32); fv_feat = np.zeros(n, np.int32)
+        nb = C.c_int32(0); nf = C.c_int32(0)
+        _ck(self._L.orbx_bow_get(self._h, frame, word.ctypes.data, node.ctypes.data, bow_id.ctypes.data, bow_val.ctypes.data,
+                                 C.addressof(nb), fv_node.ctypes.data, fv_off.ctypes.data, fv_feat.ctypes.data, C.addressof(nf)))
+        return dict(word=word, node=node, bow_id=bow_id[:nb.value], bow_val=bow_val[:nb.value], fv_node=fv_node[:nf.value],
+                    fv_off=fv_off[:nf.value + 1], fv_feat=fv_feat[:fv_off[nf.value]])
+
+    def score(self, frame_a, frame_b):
+        """L1Scoring::score between frames of the last transform_batch (KeyFrameDatabase.cc:145)."""
+        a = np.ascontiguousarray(frame_a, np.int32); b = np.ascontiguousarray(frame_b, np.int32)
+        out = np.zeros(len(a), np.float64)
+        _ck(self._L.orbx_bow_score(self._h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    def score_device(self, d_a, d_b, npairs, d_score, stream=0):
+        _ck(self._L.orbx_bow_score_device(self._h, d_a, d_b, npairs, d_score, stream))
+
+    def search_by_bow(self, kf_kps, kf_desc, kf_valid, f_kps, f_desc, levelsup=4, nnratio=0.7, check_orientation=True):
+        """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches) -> (nmatches, match_f)."""
+        kf_kps = np.ascontiguousarray(kf_kps, KP_DTYPE); f_kps = np.ascontiguousarray(f_kps, KP_DTYPE)
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8); f_desc = np.ascontiguousarray(f_desc, np.uint8)
+        val = None if kf_valid is None else np.ascontiguousarray(kf_valid, np.uint8)
+        match = np.zeros(max(len(f_kps), 1), np.int32); nm = C.c_int32(0)
+        _ck(self._L.orbx_search_by_bow(self._h, kf_kps.ctypes.data, kf_desc.ctypes.data, len(kf_kps),
+                                       None if val is None else val.ctypes.data, f_kps.ctypes.data, f_desc.ctypes.data, len(f_kps),
+                                       levelsup, nnratio, int(check_orientation), match.ctypes.data, C.addressof(nm)))
+        return nm.value, match[:len(f_kps)]
+
+    def search_by_bow_device(self, npairs, d_kf_frame, d_f_frame, d_kps, d_desc, d_kf_valid, nnratio, check_orientation, d_match,
+                             d_nmatches, stream=0):
+        _ck(self._L.orbx_search_by_bow_device(self._h, npairs, d_kf_frame, d_f_frame, d_kps, d_desc, d_kf_valid, nnratio,
+                                              int(check_orientation), d_match, d_nmatches, stream))
 
 
 class ORBmatcher:

@@ -1053,3 +1053,278 @@ extern "C" int orbx_image_bounds(int width, int height, const float* K4, const f
     bounds4[2] = std::min(c[0].y, c[1].y); bounds4[3] = std::max(c[2].y, c[3].y);    // mnMinY, mnMaxY
     return ORBX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bag of words: ORBVocabulary::transform / L1 score / ORBmatcher::SearchByBoW (orbx_bow.cu)
+struct orbx_vocabulary {
+    int k = 0, L = 0, scoring = 0, weighting = 0, nodes = 0, words = 0, device = 0;
+    OrbxVocabDev V{};
+    void* d_tree = nullptr;                      // one allocation: slot arrays + node arrays
+    // workspace of the last transform
+    int frames = 0, cap = 0;
+    size_t ws_frames = 0, ws_cap = 0;
+    void* d_ws = nullptr;
+    OrbxBowOut O{};
+    const int* d_n = nullptr;                    // counts of the last transform (caller-owned or d_n_own)
+    int* d_n_own = nullptr;
+    // match workspace
+    void* d_mws = nullptr; size_t mws_pairs = 0, mws_cap = 0;
+    int *d_bin_of = nullptr, *d_hist = nullptr;
+};
+
+extern "C" int orbx_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
+                                 const uint8_t* is_leaf, const uint8_t* descriptors, const double* weights, int device,
+                                 orbx_vocabulary** out)
+{
+    if (!out) return fail(ORBX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_nodes <= 0 || !parent || !is_leaf || !descriptors || !weights) return fail(ORBX_ERR_INVALID, "empty vocabulary");
+    // the limits of TemplatedVocabulary::loadFromTextFile (TemplatedVocabulary.h:1359)
+    if (k < 1 || k > 20 || L < 1 || L > 10 || scoring < 0 || scoring > 5 || weighting < 0 || weighting > 3)
+        return fail(ORBX_ERR_INVALID, "k in [1,20], L in [1,10], scoring in [0,5], weighting in [0,3] required");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    const int n = n_nodes + 1;
+    std::vector<int> cnt(n + 1, 0), word(n, -1);
+    std::vector<double> wt(n, 0.0);
+    int words = 0;
+    for (int i = 0; i < n_nodes; i++) {
+        if (parent[i] < 0 || parent[i] > i) return fail(ORBX_ERR_INVALID, "parent id must precede the node (text-file order)");
+        cnt[parent[i] + 1]++;
+        wt[i + 1] = weights[i];
+        if (is_leaf[i]) word[i + 1] = words++;
+    }
+    for (int i = 0; i < n; i++) {
+        if (cnt[i + 1] > 32) return fail(ORBX_ERR_UNSUPPORTED, "more than 32 children per node");
+        if (i > 0 && is_leaf[i - 1] && cnt[i + 1]) return fail(ORBX_ERR_INVALID, "a leaf has children");
+        if (i > 0 && !is_leaf[i - 1] && !cnt[i + 1]) return fail(ORBX_ERR_INVALID, "an inner node has no children");
+        cnt[i + 1] += cnt[i];
+    }
+    // slot of node id = position in its parent's child list (children in push_back = ascending id order)
+    std::vector<int> fill(n, 0), slot_node(n_nodes);
+    std::vector<int2> slot_kids(n_nodes);
+    std::vector<uint8_t> slot_desc((size_t)n_nodes * 32);
+    for (int i = 0; i < n_nodes; i++) {
+        const int s = cnt[parent[i]] + fill[parent[i]]++;
+        slot_node[s] = i + 1;
+        slot_kids[s] = make_int2(cnt[i + 1], cnt[i + 2] - cnt[i + 1]);
+        memcpy(&slot_desc[(size_t)s * 32], descriptors + (size_t)i * 32, 32);
+    }
+    orbx_vocabulary* v = new orbx_vocabulary();
+    v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->nodes = n; v->words = words; v->device = device;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_desc = al((size_t)n_nodes * 32), b_kids = al((size_t)n_nodes * sizeof(int2)), b_node = al((size_t)n_nodes * 4),
+                 b_wt = al((size_t)n * 8), b_word = al((size_t)n * 4);
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaMalloc(&v->d_tree, b_desc + b_kids + b_node + b_wt + b_word)) != cudaSuccess) {
+        delete v; return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    }
+    uint8_t* p = (uint8_t*)v->d_tree;
+    cudaMemcpy(p, slot_desc.data(), (size_t)n_nodes * 32, cudaMemcpyHostToDevice); v->V.slot_desc = (const uint4*)p; p += b_desc;
+    cudaMemcpy(p, slot_kids.data(), (size_t)n_nodes * sizeof(int2), cudaMemcpyHostToDevice); v->V.slot_kids = (const int2*)p; p += b_kids;
+    cudaMemcpy(p, slot_node.data(), (size_t)n_nodes * 4, cudaMemcpyHostToDevice); v->V.slot_node = (const int*)p; p += b_node;
+    cudaMemcpy(p, wt.data(), (size_t)n * 8, cudaMemcpyHostToDevice); v->V.weight = (const double*)p; p += b_wt;
+    cudaMemcpy(p, word.data(), (size_t)n * 4, cudaMemcpyHostToDevice); v->V.word = (const int*)p;
+    if ((e = cudaGetLastError()) != cudaSuccess) { cudaFree(v->d_tree); delete v; return fail(ORBX_ERR_CUDA, cudaGetErrorString(e)); }
+    v->V.L = L; v->V.scoring = scoring; v->V.weighting = weighting; v->V.root_children = cnt[1] - cnt[0];
+    *out = v;
+    return ORBX_OK;
+}
+
+extern "C" void orbx_vocab_destroy(orbx_vocabulary* v)
+{
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaFree(v->d_tree); cudaFree(v->d_ws); cudaFree(v->d_mws); cudaFree(v->d_n_own);
+    cudaGetLastError();
+    delete v;
+}
+extern "C" int orbx_vocab_words(const orbx_vocabulary* v) { return v ? v->words : 0; }
+extern "C" int orbx_vocab_nodes(const orbx_vocabulary* v) { return v ? v->nodes : 0; }
+
+static int bow_workspace(orbx_vocabulary* v, int frames, int cap)
+{
+    if ((size_t)frames <= v->ws_frames && (size_t)cap == v->ws_cap) return ORBX_OK;
+    CK(cudaDeviceSynchronize());
+    cudaFree(v->d_ws); v->d_ws = nullptr; v->ws_frames = v->ws_cap = 0;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t fc = al((size_t)frames * cap * 4), fc1 = al((size_t)frames * (cap + 1) * 4), fd = al((size_t)frames * cap * 8), f1 = al((size_t)frames * 4);
+    CK(cudaMalloc(&v->d_ws, 6 * fc + fc1 + fd + 2 * f1));
+    uint8_t* p = (uint8_t*)v->d_ws;
+    v->O.leaf = (int*)p; p += fc; v->O.nid = (int*)p; p += fc; v->O.word = (int*)p; p += fc;
+    v->O.bow_id = (int*)p; p += fc; v->O.fv_node = (int*)p; p += fc; v->O.fv_feat = (int*)p; p += fc;
+    v->O.fv_off = (int*)p; p += fc1; v->O.bow_val = (double*)p; p += fd;
+    v->O.n_bow = (int*)p; p += f1; v->O.n_fv = (int*)p;
+    v->ws_frames = frames; v->ws_cap = cap;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_bow_transform_device(orbx_vocabulary* v, const uint8_t* d_descriptors, const int32_t* d_counts, int frames,
+                                         int cap, int levelsup, void* cuda_stream)
+{
+    if (!v || !d_descriptors || !d_counts) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (frames <= 0 || cap <= 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    if (cap > 16384) return fail(ORBX_ERR_UNSUPPORTED, "more than 16384 features per frame");
+    CK(cudaSetDevice(v->device));
+    int rc = bow_workspace(v, frames, cap);
+    if (rc != ORBX_OK) return rc;
+    orbx_launch_bow_transform(v->V, d_descriptors, d_counts, frames, cap, levelsup, v->O, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    v->frames = frames; v->cap = cap; v->d_n = d_counts;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_bow_get(orbx_vocabulary* v, int frame, int32_t* word, int32_t* node, int32_t* bow_id, double* bow_val,
+                            int32_t* n_bow, int32_t* fv_node, int32_t* fv_off, int32_t* fv_feat, int32_t* n_fv)
+{
+    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (frame < 0 || frame >= v->frames) return fail(ORBX_ERR_INVALID, "frame out of range");
+    CK(cudaSetDevice(v->device));
+    CK(cudaDeviceSynchronize());
+    const int cap = v->cap;
+    int n = 0, nb = 0, nf = 0;
+    CK(cudaMemcpy(&n, v->d_n + frame, 4, cudaMemcpyDeviceToHost));
+    n = std::min(n, cap);
+    CK(cudaMemcpy(&nb, v->O.n_bow + frame, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&nf, v->O.n_fv + frame, 4, cudaMemcpyDeviceToHost));
+    const size_t o = (size_t)frame * cap;
+    if (word && n) CK(cudaMemcpy(word, v->O.word + o, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (node && n) CK(cudaMemcpy(node, v->O.nid + o, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (bow_id && nb) CK(cudaMemcpy(bow_id, v->O.bow_id + o, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+    if (bow_val && nb) CK(cudaMemcpy(bow_val, v->O.bow_val + o, (size_t)nb * 8, cudaMemcpyDeviceToHost));
+    if (fv_node && nf) CK(cudaMemcpy(fv_node, v->O.fv_node + o, (size_t)nf * 4, cudaMemcpyDeviceToHost));
+    if (fv_off) CK(cudaMemcpy(fv_off, v->O.fv_off + (size_t)frame * (cap + 1), (size_t)(nf + 1) * 4, cudaMemcpyDeviceToHost));
+    if (fv_feat && nf) {
+        int tot = 0;
+        CK(cudaMemcpy(&tot, v->O.fv_off + (size_t)frame * (cap + 1) + nf, 4, cudaMemcpyDeviceToHost));
+        if (tot) CK(cudaMemcpy(fv_feat, v->O.fv_feat + o, (size_t)tot * 4, cudaMemcpyDeviceToHost));
+    }
+    if (n_bow) *n_bow = nb;
+    if (n_fv) *n_fv = nf;
+    return ORBX_OK;
+}
+
+// host convenience: `frames` descriptor sets of up to `cap` rows ([frames][cap][32]) -> transform; results via orbx_bow_get
+extern "C" int orbx_bow_transform(orbx_vocabulary* v, const uint8_t* descriptors, const int32_t* counts, int frames, int cap,
+                                  int levelsup)
+{
+    if (!v || !descriptors || !counts || frames <= 0 || cap <= 0) return fail(ORBX_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(v->device));
+    CK(cudaDeviceSynchronize());
+    cudaFree(v->d_n_own); v->d_n_own = nullptr;
+    uint8_t* d_desc = nullptr;
+    CK(cudaMalloc(&v->d_n_own, (size_t)frames * 4));
+    CK(cudaMalloc(&d_desc, (size_t)frames * cap * 32));
+    cudaError_t e;
+    int rc = ORBX_OK;
+    do {
+        if ((e = cudaMemcpy(v->d_n_own, counts, (size_t)frames * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_desc, descriptors, (size_t)frames * cap * 32, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        rc = orbx_bow_transform_device(v, d_desc, v->d_n_own, frames, cap, levelsup, nullptr);
+        e = cudaDeviceSynchronize();
+    } while (0);
+    cudaFree(d_desc);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int orbx_bow_score_device(orbx_vocabulary* v, const int32_t* d_frame_a, const int32_t* d_frame_b, int npairs,
+                                     double* d_score, void* cuda_stream)
+{
+    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (npairs < 0 || (npairs > 0 && (!d_frame_a || !d_frame_b || !d_score))) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (v->scoring != 0) return fail(ORBX_ERR_UNSUPPORTED, "only L1_NORM scoring (ORBvoc's) is implemented");
+    CK(cudaSetDevice(v->device));
+    orbx_launch_bow_score(v->O, v->cap, d_frame_a, d_frame_b, npairs, d_score, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_bow_score(orbx_vocabulary* v, const int32_t* frame_a, const int32_t* frame_b, int npairs, double* score)
+{
+    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (npairs <= 0) return ORBX_OK;
+    if (!frame_a || !frame_b || !score) return fail(ORBX_ERR_INVALID, "bad argument");
+    for (int i = 0; i < npairs; i++)
+        if (frame_a[i] < 0 || frame_a[i] >= v->frames || frame_b[i] < 0 || frame_b[i] >= v->frames) return fail(ORBX_ERR_INVALID, "frame out of range");
+    CK(cudaSetDevice(v->device));
+    int* d = nullptr; double* ds = nullptr;
+    CK(cudaMalloc(&d, (size_t)npairs * 8));
+    cudaError_t e = cudaMalloc(&ds, (size_t)npairs * 8);
+    int rc = ORBX_OK;
+    if (e == cudaSuccess) do {
+        if ((e = cudaMemcpy(d, frame_a, (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d + npairs, frame_b, (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        rc = orbx_bow_score_device(v, d, d + npairs, npairs, ds, nullptr);
+        e = cudaMemcpy(score, ds, (size_t)npairs * 8, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d); cudaFree(ds);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int orbx_search_by_bow_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf_frame, const int32_t* d_f_frame,
+                                         const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_kf_valid,
+                                         float nnratio, int check_orientation, int32_t* d_match, int32_t* d_nmatches,
+                                         void* cuda_stream)
+{
+    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (npairs <= 0) return ORBX_OK;
+    if (!d_kf_frame || !d_f_frame || !d_keypoints || !d_descriptors || !d_match || !d_nmatches) return fail(ORBX_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(v->device));
+    const int cap = v->cap;
+    if ((size_t)npairs > v->mws_pairs || (size_t)cap != v->mws_cap) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(v->d_mws); v->d_mws = nullptr;
+        CK(cudaMalloc(&v->d_mws, (size_t)npairs * cap * 4 + (size_t)npairs * 32 * 4));
+        v->d_bin_of = (int*)v->d_mws; v->d_hist = v->d_bin_of + (size_t)npairs * cap;
+        v->mws_pairs = npairs; v->mws_cap = cap;
+    }
+    OrbxBowMatchArgs A;
+    A.kf_frame = d_kf_frame; A.f_frame = d_f_frame; A.kps = (const OrbxKp28*)d_keypoints; A.desc = d_descriptors;
+    A.kf_valid = d_kf_valid; A.nnratio = nnratio; A.check_orientation = check_orientation; A.th_low = 50;   // ORBmatcher::TH_LOW
+    A.match = d_match; A.bin_of = v->d_bin_of; A.hist = v->d_hist; A.nmatches = d_nmatches;
+    orbx_launch_bow_match(v->O, A, v->d_n, cap, npairs, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// host convenience for one (keyframe, frame) pair: transforms both descriptor sets, then matches
+extern "C" int orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoints, const uint8_t* kf_descriptors, int n_kf,
+                                  const uint8_t* kf_valid, const OrbxKeyPoint* f_keypoints, const uint8_t* f_descriptors, int n_f,
+                                  int levelsup, float nnratio, int check_orientation, int32_t* match_f, int32_t* nmatches)
+{
+    if (!v || n_kf < 0 || n_f < 0 || !nmatches || (n_f > 0 && !match_f)) return fail(ORBX_ERR_INVALID, "bad argument");
+    *nmatches = 0;
+    for (int j = 0; j < n_f; j++) match_f[j] = -1;
+    if (n_kf == 0 || n_f == 0) return ORBX_OK;
+    if (!kf_keypoints || !kf_descriptors || !f_keypoints || !f_descriptors) return fail(ORBX_ERR_INVALID, "NULL argument");
+    const int cap = std::max(n_kf, n_f);
+    std::vector<uint8_t> desc((size_t)2 * cap * 32, 0);
+    memcpy(desc.data(), kf_descriptors, (size_t)n_kf * 32);
+    memcpy(desc.data() + (size_t)cap * 32, f_descriptors, (size_t)n_f * 32);
+    const int32_t counts[2] = {n_kf, n_f};
+    int rc = orbx_bow_transform(v, desc.data(), counts, 2, cap, levelsup);
+    if (rc != ORBX_OK) return rc;
+    uint8_t* pool = nullptr;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_kp = al((size_t)2 * cap * 28), b_d = al((size_t)2 * cap * 32), b_v = al((size_t)cap), b_m = al((size_t)cap * 4);
+    CK(cudaMalloc(&pool, b_kp + b_d + b_v + b_m + 256 + 256));
+    uint8_t *p_kp = pool, *p_d = p_kp + b_kp, *p_v = p_d + b_d, *p_m = p_v + b_v, *p_idx = p_m + b_m, *p_nm = p_idx + 256;
+    cudaError_t e;
+    do {
+        const int32_t idx[2] = {0, 1};
+        if ((e = cudaMemcpy(p_kp, kf_keypoints, (size_t)n_kf * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_kp + (size_t)cap * 28, f_keypoints, (size_t)n_f * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_d, desc.data(), desc.size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (kf_valid && (e = cudaMemcpy(p_v, kf_valid, (size_t)n_kf, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(p_idx, idx, 8, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        rc = orbx_search_by_bow_device(v, 1, (const int32_t*)p_idx, (const int32_t*)p_idx + 1, (const OrbxKeyPoint*)p_kp, p_d,
+                                       kf_valid ? p_v : nullptr, nnratio, check_orientation, (int32_t*)p_m, (int32_t*)p_nm, nullptr);
+        if (rc != ORBX_OK) { e = cudaSuccess; break; }
+        if ((e = cudaMemcpy(match_f, p_m, (size_t)n_f * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        e = cudaMemcpy(nmatches, p_nm, 4, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(pool);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}

@@ -124,6 +124,33 @@ struct OrbxWindowArgs {        // windowed top-2 on the Frame grid (Frame.cc:388
 };
 void orbx_launch_window_top2(const OrbxWindowArgs& a, cudaStream_t st);
 
+// ---- bag of words (orbx_bow.cu). Vocabulary on the device: children of a node occupy consecutive slots.
+struct OrbxVocabDev {
+    int L, scoring, weighting, root_children;
+    const uint4* slot_desc;      // [slots][2]   descriptor of the node in the slot
+    const int2* slot_kids;       // [slots]      (first slot, count) of that node's own children
+    const int* slot_node;        // [slots]      node id
+    const double* weight;        // [nodes]      WordValue (0 for inner nodes)
+    const int* word;             // [nodes]      word id, -1 for inner nodes
+};
+struct OrbxBowOut {              // per frame, `cap` entries each ([frames][cap], fv_off [frames][cap+1])
+    int *leaf, *nid, *word;      // per feature: leaf node, node at level L - levelsup, word id
+    int* bow_id; double* bow_val; int* n_bow;            // BowVector: ascending word id
+    int *fv_node, *fv_off, *fv_feat, *n_fv;              // FeatureVector as CSR: ascending node id, features in order
+};
+struct OrbxBowMatchArgs {        // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) for `pairs` (keyframe, frame) pairs
+    const int *kf_frame, *f_frame;                       // [pairs] frame indices into the transformed batch
+    const OrbxKp28* kps; const uint8_t* desc;            // the batch the transform ran on ([frames][cap])
+    const uint8_t* kf_valid;                             // [pairs][cap] or NULL (all keyframe features have a good map point)
+    float nnratio; int check_orientation, th_low;
+    int *match, *bin_of;                                 // [pairs][cap]
+    int *hist, *nmatches;                                // [pairs][32], [pairs]
+};
+void orbx_launch_bow_transform(const OrbxVocabDev& V, const uint8_t* d_desc, const int* d_n, int frames, int cap, int levelsup,
+                               const OrbxBowOut& O, cudaStream_t st);
+void orbx_launch_bow_score(const OrbxBowOut& O, int cap, const int* d_qa, const int* d_qb, int npairs, double* d_score, cudaStream_t st);
+void orbx_launch_bow_match(const OrbxBowOut& O, const OrbxBowMatchArgs& A, const int* d_n, int cap, int npairs, cudaStream_t st);
+
 // cv::undistortPoints(src, dst, K, D, Mat(), K): intrinsics and (k1, k2, p1, p2, k3) widened to f64 on the host
 struct OrbxUndistortArgs { double fx, fy, cx, cy, ifx, ify, k[5]; };
 void orbx_launch_undistort(const OrbxKp28* d_in, OrbxKp28* d_out, int n, const OrbxUndistortArgs& a, cudaStream_t st);

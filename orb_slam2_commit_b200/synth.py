@@ -143,3 +143,47 @@ def rectify_maps(width: int, height: int, cam: dict = EUROC_LEFT, scale: float =
     xd = x * kr + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
     yd = y * kr + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
     return (K[0, 0] * xd + K[0, 2]).astype(np.float32), (K[1, 1] * yd + K[1, 2]).astype(np.float32)
+
+
+def synth_vocabulary(k: int, L: int, seed: int, early_leaf: float = 0.03, stop_frac: float = 0.02):
+    """A DBoW2-style vocabulary tree in text-file order (ORBvoc.txt is not in the reference snapshot): returns
+    (parent[int32], is_leaf[uint8], desc[n,32] uint8, weight[float64]) for the non-root nodes, numbered level by level
+    so that siblings are consecutive (as DBoW2's HKmeansStep creates them). Child descriptor = parent descriptor with
+    fewer and fewer random bit flips per level; a few nodes above depth L are leaves, a few have fewer than k children,
+    and `stop_frac` of the words carry weight 0 (stopped words)."""
+    rng = np.random.default_rng(seed)
+    parents, leaves, descs, weights = [], [], [], []
+    cur_ids = np.array([0]); cur_desc = np.zeros((1, 32), np.uint8)
+    next_id = 1
+    for depth in range(1, L + 1):
+        nch = np.full(len(cur_ids), k)
+        if depth > 1:
+            nch -= (rng.random(len(cur_ids)) < 0.1) * rng.integers(1, max(2, k // 2), len(cur_ids))
+        par = np.repeat(cur_ids, nch)
+        pdesc = np.repeat(cur_desc, nch, axis=0)
+        p = 0.5 if depth == 1 else 0.5 / (1.7 ** (depth - 1))
+        flips = np.packbits(rng.random((len(par), 256)) < p, axis=1, bitorder="little")
+        d = pdesc ^ flips
+        leaf = np.ones(len(par), np.uint8) if depth == L else (rng.random(len(par)) < early_leaf).astype(np.uint8)
+        parents.append(par); leaves.append(leaf); descs.append(d)
+        w = rng.random(len(par)) * 9.5 + 0.1
+        w[rng.random(len(par)) < stop_frac] = 0.0
+        weights.append(np.where(leaf > 0, w, 0.0))
+        ids = np.arange(next_id, next_id + len(par)); next_id += len(par)
+        keep = leaf == 0
+        cur_ids = ids[keep]; cur_desc = d[keep]
+    return (np.concatenate(parents).astype(np.int32), np.concatenate(leaves), np.concatenate(descs),
+            np.concatenate(weights))
+
+
+def synth_features_near_words(voc, n: int, seed: int, max_flips: int = 30):
+    """n descriptors = random leaf descriptors of `voc` with up to max_flips random bit flips."""
+    parent, is_leaf, desc, _ = voc
+    rng = np.random.default_rng(seed)
+    leaf_idx = np.flatnonzero(is_leaf)
+    pick = leaf_idx[rng.integers(0, len(leaf_idx), n)]
+    out = desc[pick].copy()
+    for i in range(n):
+        for b in rng.integers(0, 256, rng.integers(0, max_flips + 1)):
+            out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out

@@ -505,3 +505,80 @@ def test_undistort_keypoints_bit_exact(golden_dir):
     c = g["undist_dst5"][:4]
     assert np.array_equal(b, np.array([min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])], np.float32))
     assert np.array_equal(image_bounds(640, 480, synth.TUM1_K4, np.zeros(4, np.float32)), np.array([0, 640, 0, 480], np.float32))
+
+
+def _bow_equal(got, ref, what):
+    for k in ("word", "node", "bow_id", "fv_node", "fv_off", "fv_feat"):
+        assert np.array_equal(got[k], ref[k]), f"{what}: {k} differs"
+    assert np.array_equal(got["bow_val"].view(np.uint64), ref["bow_val"].view(np.uint64)), f"{what}: BowVector values differ (bitwise)"
+
+
+@pytest.mark.parametrize("k,L,levelsup,scoring,weighting", [(10, 4, 2, 0, 0), (6, 5, 4, 0, 0), (7, 3, 4, 1, 1), (5, 4, 1, 5, 0),
+                                                             (9, 3, 2, 0, 2), (20, 2, 1, 0, 3)])
+def test_bow_transform_matches_oracle(k, L, levelsup, scoring, weighting):
+    """Frame::ComputeBoW = ORBVocabulary::transform(desc, mBowVec, mFeatVec, levelsup): words, nodes, BowVector
+    (bit-identical doubles) and FeatureVector against the DBoW2 restatement, batched with ragged counts, incl. stopped
+    words, early leaves, L - levelsup <= 0 (nodes collapse to the root) and every weighting / normalisation branch."""
+    from orb_slam2_commit_b200 import ORBVocabulary
+    voc = synth.synth_vocabulary(k, L, 100 + k)
+    V = ORBVocabulary(k, L, *voc, scoring=scoring, weighting=weighting)
+    Vo = ob.Vocabulary(k, L, *voc, scoring=scoring, weighting=weighting)
+    assert V.nwords == Vo.nwords
+    rng = np.random.default_rng(k)
+    descs = [synth.synth_features_near_words(voc, n, 7 + n) for n in (1000, 37, 1, 2048)]
+    descs.append(rng.integers(0, 256, (300, 32), dtype=np.uint8))          # far from every word
+    descs.append(np.repeat(descs[0][:5], 40, axis=0))                      # many features per word (accumulation order)
+    got = V.transform_batch(descs, levelsup)
+    for i, d in enumerate(descs):
+        _bow_equal(got[i], Vo.transform(d, levelsup), f"k={k} L={L} frame {i}")
+    assert any(len(g["bow_id"]) < (g["word"] >= 0).sum() for g in got)     # some words repeat
+    _bow_equal(V.transform(descs[1], levelsup), Vo.transform(descs[1], levelsup), "single-frame form")
+
+
+def test_bow_on_extractor_output_and_l1_score():
+    """BoW of real extractor descriptors (batched), then L1Scoring::score between all pairs of frames, bit-identical."""
+    from orb_slam2_commit_b200 import ORBVocabulary
+    voc = synth.synth_vocabulary(10, 4, 5)
+    V = ORBVocabulary(10, 4, *voc); Vo = ob.Vocabulary(10, 4, *voc)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    imgs = [synth.synth_image(640, 480, 60 + i) for i in range(3)]
+    imgs.append(np.roll(imgs[0], 3, axis=1))                               # near-duplicate of frame 0 -> many common words
+    _, descs = ex.extract_batch(imgs)
+    got = V.transform_batch(descs, 2)
+    refs = [Vo.transform(d, 2) for d in descs]
+    for i in range(len(descs)):
+        _bow_equal(got[i], refs[i], f"frame {i}")
+    a, b = np.meshgrid(np.arange(4), np.arange(4))
+    s = V.score(a.ravel(), b.ravel())
+    so = np.array([ob.bow_score_l1(refs[i]["bow_id"], refs[i]["bow_val"], refs[j]["bow_id"], refs[j]["bow_val"])
+                   for i, j in zip(a.ravel(), b.ravel())])
+    assert np.array_equal(s.view(np.uint64), so.view(np.uint64))
+    assert s.reshape(4, 4)[0, 0] > 0.99 and s.max() <= 1.0 + 1e-12
+
+
+@pytest.mark.parametrize("check_ori,nnratio", [(True, 0.7), (False, 0.9), (True, 0.95)])
+def test_search_by_bow_matches_oracle(check_ori, nnratio):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...): per-node sequential best / second-best with the already-matched
+    skip, TH_LOW, NN ratio, rotation histogram + ComputeThreeMaxima; matches and count identical to the restatement."""
+    from orb_slam2_commit_b200 import ORBVocabulary
+    voc = synth.synth_vocabulary(10, 4, 11)
+    V = ORBVocabulary(10, 4, *voc); Vo = ob.Vocabulary(10, 4, *voc)
+    ex = ORBextractor(1500, 1.2, 8, 20, 7)
+    base = synth.synth_image(640, 480, 90)
+    rng = np.random.default_rng(4)
+    moved = np.clip(np.roll(base, (2, 5), axis=(0, 1)).astype(np.int16) + rng.integers(-6, 7, base.shape), 0, 255).astype(np.uint8)
+    (kk, kf), (dk, df) = ex.extract_batch([base, moved])
+    valid = (rng.random(len(kk)) < 0.8).astype(np.uint8)
+    for kf_valid in (valid, None):
+        n, m = V.search_by_bow(kk, dk, kf_valid, kf, df, levelsup=2, nnratio=nnratio, check_orientation=check_ori)
+        to, tf = Vo.transform(dk, 2), Vo.transform(df, 2)
+        no, mo = ob.search_by_bow(to, tf, dk, kk["angle"], np.ones(len(kk), np.uint8) if kf_valid is None else kf_valid, df, kf["angle"],
+                                  nnratio, check_ori)
+        assert n == no and np.array_equal(m, mo)
+        assert n > 50 and n == np.count_nonzero(m >= 0)
+    # duplicated frame descriptors inside one node: first-in-list wins, duplicates give bestDist2 == bestDist1 (ratio fails)
+    df2 = df.copy(); df2[1::2] = df2[0::2][:len(df2[1::2])]
+    n, m = V.search_by_bow(kk, dk, None, kf, df2, levelsup=2, nnratio=nnratio, check_orientation=check_ori)
+    to, tf = Vo.transform(dk, 2), Vo.transform(df2, 2)
+    no, mo = ob.search_by_bow(to, tf, dk, kk["angle"], np.ones(len(kk), np.uint8), df2, kf["angle"], nnratio, check_ori)
+    assert n == no and np.array_equal(m, mo)
