@@ -269,6 +269,36 @@ int  orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoints, co
                         const uint8_t* kf_valid, const OrbxKeyPoint* f_keypoints, const uint8_t* f_descriptors, int n_f,
                         int levelsup, float nnratio, int check_orientation, int32_t* match_f, int32_t* nmatches);
 
+/* ---- ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646),
+ *      the matcher of Tracking::TrackWithMotionModel: projection of the last frame's map points with CurrentFrame.mTcw,
+ *      Frame::GetFeaturesInArea on the 64x48 grid, nearest descriptor <= TH_HIGH, the "already holds an observed map
+ *      point" skip in the reference's sequential order, rotation histogram + ComputeThreeMaxima.
+ *      camera9 = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY); scale_factors = mvScaleFactors.
+ *      OpenCV 4.13 f32 arithmetic for the cv::Mat expressions (see oracle/orb_oracle.c). ---- */
+typedef struct OrbxProjectionPair {
+    const OrbxKeyPoint* cur_keypoints;   /* CurrentFrame.mvKeysUn, n_cur */
+    const uint8_t* cur_descriptors;      /* CurrentFrame.mDescriptors */
+    const float* cur_u_right;            /* CurrentFrame.mvuRight, or NULL (monocular) */
+    const uint8_t* cur_occupied;         /* != 0 <=> CurrentFrame.mvpMapPoints[i] has Observations() > 0 before the call; NULL = none */
+    int32_t n_cur;
+    const OrbxKeyPoint* last_keypoints;  /* LastFrame.mvKeysUn (octave and angle are used), n_last */
+    const float* last_xyz;               /* pMP->GetWorldPos(): 3 floats per last-frame keypoint */
+    const uint8_t* last_descriptors;     /* pMP->GetDescriptor(): 32 bytes per last-frame keypoint */
+    const uint8_t* last_flags;           /* bit 0: has a map point and !mvbOutlier[i]; bit 1: pMP->Observations() > 0 */
+    int32_t n_last;
+    float Tcw[12];                       /* CurrentFrame.mTcw: Rcw row-major (9 floats), then tcw (3) */
+    int32_t mode;                        /* 0: octaves nLastOctave-1..+1, 1: bForward, 2: bBackward (:1510-1511) */
+    int32_t* match;                      /* out, n_cur: last-frame keypoint whose map point the keypoint now holds, -1 = none */
+    int32_t* nmatches;                   /* out: the return value */
+} OrbxProjectionPair;
+/* host buffers, one pair, synchronous */
+int orbx_search_by_projection(const OrbxProjectionPair* pair, const float* camera9, const float* scale_factors, int nlevels,
+                              float th, int check_orientation, int device);
+/* `pairs` is a HOST array whose pointers are DEVICE pointers; one CTA per pair, asynchronous on cuda_stream */
+int orbx_search_by_projection_device(const OrbxProjectionPair* pairs, int npairs, const float* camera9,
+                                     const float* scale_factors, int nlevels, float th, int check_orientation, int device,
+                                     void* cuda_stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

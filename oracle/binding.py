@@ -55,6 +55,10 @@ def lib():
         L.oc_remap_linear_8u.argtypes = [u8p, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
         L.oc_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
         L.oc_fast_score.restype = C.c_int; L.oc_fast_score.argtypes = [u8p, C.c_int]
+        L.oc_search_by_projection_frame.restype = C.c_int
+        L.oc_search_by_projection_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                                    C.c_int, C.c_int, C.c_void_p]
         L.oc_vocab_create.restype = C.c_void_p
         L.oc_vocab_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, u8p, u8p, C.POINTER(C.c_double)]
         L.oc_vocab_destroy.argtypes = [C.c_void_p]
@@ -400,3 +404,22 @@ def search_by_bow(kf, f, kf_desc, kf_angle, kf_valid, f_desc, f_angle, nnratio=0
                                b[2].ctypes.data, len(b[0]), kf_desc.ctypes.data, kf_angle.ctypes.data, kf_valid.ctypes.data,
                                f_desc.ctypes.data, f_angle.ctypes.data, len(f_desc), nnratio, int(check_orientation), match.ctypes.data)
     return n, match
+
+
+def search_by_projection_frame(cur_kps, cur_desc, cur_u_right, cur_occupied, Tcw12, cam9, scale_factors, last_kps, last_xyz,
+                               last_desc, last_flags, th, mode, check_orientation=True):
+    """-> (nmatches, match_cur)"""
+    cur_kps = np.ascontiguousarray(cur_kps, KP_DTYPE); last_kps = np.ascontiguousarray(last_kps, KP_DTYPE)
+    cur_desc = np.ascontiguousarray(cur_desc, np.uint8); last_desc = np.ascontiguousarray(last_desc, np.uint8)
+    ur = None if cur_u_right is None else np.ascontiguousarray(cur_u_right, np.float32)
+    occ = None if cur_occupied is None else np.ascontiguousarray(cur_occupied, np.uint8)
+    T = np.ascontiguousarray(Tcw12, np.float32); cam = np.ascontiguousarray(cam9, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    xyz = np.ascontiguousarray(last_xyz, np.float32); fl = np.ascontiguousarray(last_flags, np.uint8)
+    match = np.zeros(max(len(cur_kps), 1), np.int32)
+    n = lib().oc_search_by_projection_frame(cur_kps.ctypes.data, cur_desc.ctypes.data, len(cur_kps),
+                                            None if ur is None else ur.ctypes.data, None if occ is None else occ.ctypes.data,
+                                            T.ctypes.data, cam.ctypes.data, sf.ctypes.data, last_kps.ctypes.data, xyz.ctypes.data,
+                                            last_desc.ctypes.data, fl.ctypes.data, len(last_kps), th, mode, int(check_orientation),
+                                            match.ctypes.data)
+    return n, match[:len(cur_kps)]

@@ -1249,3 +1249,114 @@ int oc_search_by_bow(const int32_t* kf_fv_node, const int32_t* kf_fv_off, const 
     free(hist_idx); free(hist_bin);
     return nmatches;
 }
+
+/* ------------------------------------------------------------------ ORBmatcher::SearchByProjection(Frame &CurrentFrame,
+ * const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646), the matcher of Tracking::TrackWithMotionModel.
+ * cv::Mat arithmetic restated from OpenCV 4.13 (pinned with cv2.gemm): `Rcw*x3Dw+tcw` is one gemm on CV_32F 3x3 * 3x1
+ * operands evaluated in f32, left to right, the addend last. `1.0/z` is a double division rounded to float. The
+ * reference is built with -std=c++11 (CMakeLists.txt:13-26), i.e. without FMA contraction.
+ * mode: 0 = neither (levels octave-1..octave+1), 1 = bForward, 2 = bBackward (:1510-1511; decided by the caller from
+ * tlc and mb). cam = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY). last_flags bit 0: LastFrame.mvpMapPoints[i]
+ * exists and !mvbOutlier[i]; bit 1: that map point has Observations() > 0 (what :1574-1576 tests once it has been
+ * assigned to a current keypoint). cur_occupied: the same test on CurrentFrame.mvpMapPoints before the call.
+ * match_cur[k] stands for CurrentFrame.mvpMapPoints[k]: index of the last-frame keypoint whose map point it holds. */
+int oc_search_by_projection_frame(const OcKeyPoint* cur_kps, const uint8_t* cur_desc, int n_cur, const float* cur_u_right,
+                                  const uint8_t* cur_occupied, const float* Tcw12, const float* cam9,
+                                  const float* scale_factors,
+                                  const OcKeyPoint* last_kps, const float* last_xyz, const uint8_t* last_desc,
+                                  const uint8_t* last_flags, int n_last, float th, int mode, int check_orientation,
+                                  int32_t* match_cur)
+{
+    const float fx = cam9[0], fy = cam9[1], cx = cam9[2], cy = cam9[3], mbf = cam9[4];
+    const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
+    const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
+    /* AssignFeaturesToGrid */
+    int* cnt = (int*)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, sizeof(int));
+    int* cell = (int*)malloc(sizeof(int) * (size_t)(n_cur > 0 ? n_cur : 1));
+    int* tab = (int*)malloc(sizeof(int) * (size_t)(n_cur > 0 ? n_cur : 1));
+    int* fill = (int*)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS, sizeof(int));
+    uint8_t* occ = (uint8_t*)calloc((size_t)(n_cur > 0 ? n_cur : 1), 1);
+    for (int i = 0; i < n_cur; i++) {
+        int posX = (int)roundf((cur_kps[i].x - mnMinX) * invW), posY = (int)roundf((cur_kps[i].y - mnMinY) * invH);
+        cell[i] = (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) ? -1 : posX * FRAME_GRID_ROWS + posY;
+        if (cell[i] >= 0) cnt[cell[i] + 1]++;
+        match_cur[i] = -1;
+        occ[i] = cur_occupied ? (cur_occupied[i] != 0) : 0;
+    }
+    for (int c = 0; c < FRAME_GRID_COLS * FRAME_GRID_ROWS; c++) cnt[c + 1] += cnt[c];
+    for (int i = 0; i < n_cur; i++) if (cell[i] >= 0) tab[cnt[cell[i]] + fill[cell[i]]++] = i;
+    int nmatches = 0, nh = 0, count[HISTO_LENGTH] = {0};
+    int* hist_idx = (int*)malloc(sizeof(int) * (size_t)(n_last > 0 ? n_last : 1));
+    int* hist_bin = (int*)malloc(sizeof(int) * (size_t)(n_last > 0 ? n_last : 1));
+    for (int i = 0; i < n_last; i++) {
+        if (!(last_flags[i] & 1)) continue;
+        const float X = last_xyz[3 * i], Y = last_xyz[3 * i + 1], Z = last_xyz[3 * i + 2];
+        float c3[3];
+        for (int r = 0; r < 3; r++) {
+            float s = Tcw12[3 * r] * X;
+            s = s + Tcw12[3 * r + 1] * Y;
+            s = s + Tcw12[3 * r + 2] * Z;
+            c3[r] = s + Tcw12[9 + r];
+        }
+        const float xc = c3[0], yc = c3[1];
+        const float invzc = (float)(1.0 / (double)c3[2]);
+        if (invzc < 0) continue;
+        const float u = fx * xc * invzc + cx, v = fy * yc * invzc + cy;
+        if (u < mnMinX || u > mnMaxX) continue;
+        if (v < mnMinY || v > mnMaxY) continue;
+        const int nLastOctave = last_kps[i].octave;
+        const float radius = th * scale_factors[nLastOctave];
+        int minLevel, maxLevel;
+        if (mode == 1) { minLevel = nLastOctave; maxLevel = -1; }
+        else if (mode == 2) { minLevel = 0; maxLevel = nLastOctave; }
+        else { minLevel = nLastOctave - 1; maxLevel = nLastOctave + 1; }
+        int nMinCellX = (int)floorf((u - mnMinX - radius) * invW); if (nMinCellX < 0) nMinCellX = 0;
+        if (nMinCellX >= FRAME_GRID_COLS) continue;
+        int nMaxCellX = (int)ceilf((u - mnMinX + radius) * invW); if (nMaxCellX > FRAME_GRID_COLS - 1) nMaxCellX = FRAME_GRID_COLS - 1;
+        if (nMaxCellX < 0) continue;
+        int nMinCellY = (int)floorf((v - mnMinY - radius) * invH); if (nMinCellY < 0) nMinCellY = 0;
+        if (nMinCellY >= FRAME_GRID_ROWS) continue;
+        int nMaxCellY = (int)ceilf((v - mnMinY + radius) * invH); if (nMaxCellY > FRAME_GRID_ROWS - 1) nMaxCellY = FRAME_GRID_ROWS - 1;
+        if (nMaxCellY < 0) continue;
+        const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        int bestDist = 256, bestIdx2 = -1;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                const int c = ix * FRAME_GRID_ROWS + iy;
+                for (int j = cnt[c]; j < cnt[c + 1]; j++) {
+                    const int i2 = tab[j];
+                    const OcKeyPoint* kp = &cur_kps[i2];
+                    if (bCheckLevels) {
+                        if (kp->octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                    }
+                    if (!(fabsf(kp->x - u) < radius && fabsf(kp->y - v) < radius)) continue;
+                    if (occ[i2]) continue;                                   /* :1574-1576 */
+                    if (cur_u_right && cur_u_right[i2] > 0) {
+                        const float ur = u - mbf * invzc;
+                        const float er = fabsf(ur - cur_u_right[i2]);
+                        if (er > radius) continue;
+                    }
+                    const int dist = oc_descriptor_distance(last_desc + 32 * (size_t)i, cur_desc + 32 * (size_t)i2);
+                    if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+                }
+            }
+        if (bestDist <= 100) {                                               /* TH_HIGH */
+            match_cur[bestIdx2] = i;
+            occ[bestIdx2] = (last_flags[i] & 2) != 0;                        /* the new holder decides later skips */
+            nmatches++;
+            if (check_orientation) {
+                const int bin = rot_bin(last_kps[i].angle, cur_kps[bestIdx2].angle);
+                hist_idx[nh] = bestIdx2; hist_bin[nh] = bin; nh++; count[bin]++;
+            }
+        }
+    }
+    if (check_orientation) {
+        int i1, i2, i3;
+        three_maxima(count, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int t = 0; t < nh; t++)
+            if (hist_bin[t] != i1 && hist_bin[t] != i2 && hist_bin[t] != i3) { match_cur[hist_idx[t]] = -1; nmatches--; }
+    }
+    free(cnt); free(cell); free(tab); free(fill); free(occ); free(hist_idx); free(hist_bin);
+    return nmatches;
+}

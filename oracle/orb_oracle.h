@@ -110,6 +110,16 @@ int   oc_search_by_bow(const int32_t* kf_fv_node, const int32_t* kf_fv_off, cons
                        const uint8_t* f_desc, const float* f_angle, int f_n,
                        float nnratio, int check_orientation, int32_t* match_f);
 
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646);
+ * argument meaning as include/orbx.h OrbxProjectionPair. Direct restatement, cv::Mat arithmetic pinned to cv2 4.13's
+ * gemm; NOT pinned by oracle/_ref (ORBmatcher.cc needs the whole SLAM library). Returns nmatches. */
+int   oc_search_by_projection_frame(const OcKeyPoint* cur_kps, const uint8_t* cur_desc, int n_cur, const float* cur_u_right,
+                                    const uint8_t* cur_occupied, const float* Tcw12, const float* cam9,
+                                    const float* scale_factors,
+                                    const OcKeyPoint* last_kps, const float* last_xyz, const uint8_t* last_desc,
+                                    const uint8_t* last_flags, int n_last, float th, int mode, int check_orientation,
+                                    int32_t* match_cur);
+
 #ifdef __cplusplus
 }
 #endif

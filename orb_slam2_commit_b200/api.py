@@ -88,6 +88,8 @@ def lib():
                                                 C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_search_by_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbx_search_by_projection.argtypes = [C.c_void_p, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.orbx_search_by_projection_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.orbx_synchronize.argtypes = [C.c_void_p]
         L.orbx_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
@@ -385,6 +387,39 @@ def window_top2(keypoints, descriptors, occupied, u_right, minX, minY, invW, inv
                                None if ur is None else ur.ctypes.data, minX, minY, invW, invH, q.ctypes.data, _u8(qd), len(q),
                                *[o.ctypes.data_as(i32p) for o in out], device))
     return out
+
+
+class OrbxProjectionPair(C.Structure):
+    """include/orbx.h OrbxProjectionPair"""
+    _fields_ = [("cur_keypoints", C.c_void_p), ("cur_descriptors", C.c_void_p), ("cur_u_right", C.c_void_p),
+                ("cur_occupied", C.c_void_p), ("n_cur", C.c_int32),
+                ("last_keypoints", C.c_void_p), ("last_xyz", C.c_void_p), ("last_descriptors", C.c_void_p),
+                ("last_flags", C.c_void_p), ("n_last", C.c_int32),
+                ("Tcw", C.c_float * 12), ("mode", C.c_int32), ("match", C.c_void_p), ("nmatches", C.c_void_p)]
+
+
+def search_by_projection_frame(cur_kps, cur_desc, cur_u_right, cur_occupied, Tcw12, cam9, scale_factors, last_kps, last_xyz,
+                               last_desc, last_flags, th, mode, check_orientation=True, device: int = 0):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1489-1646) -> (nmatches, match_cur);
+    match_cur[k] = index of the last-frame keypoint whose map point current keypoint k now holds, -1 = none."""
+    cur_kps = np.ascontiguousarray(cur_kps, KP_DTYPE); last_kps = np.ascontiguousarray(last_kps, KP_DTYPE)
+    cur_desc = np.ascontiguousarray(cur_desc, np.uint8); last_desc = np.ascontiguousarray(last_desc, np.uint8)
+    ur = None if cur_u_right is None else np.ascontiguousarray(cur_u_right, np.float32)
+    occ = None if cur_occupied is None else np.ascontiguousarray(cur_occupied, np.uint8)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    xyz = np.ascontiguousarray(last_xyz, np.float32); fl = np.ascontiguousarray(last_flags, np.uint8)
+    match = np.zeros(max(len(cur_kps), 1), np.int32); nm = np.zeros(1, np.int32)
+    P = OrbxProjectionPair()
+    P.cur_keypoints = cur_kps.ctypes.data; P.cur_descriptors = cur_desc.ctypes.data
+    P.cur_u_right = None if ur is None else ur.ctypes.data; P.cur_occupied = None if occ is None else occ.ctypes.data
+    P.n_cur = len(cur_kps)
+    P.last_keypoints = last_kps.ctypes.data; P.last_xyz = xyz.ctypes.data; P.last_descriptors = last_desc.ctypes.data
+    P.last_flags = fl.ctypes.data; P.n_last = len(last_kps)
+    P.Tcw = (C.c_float * 12)(*np.asarray(Tcw12, np.float32).ravel().tolist()); P.mode = mode
+    P.match = match.ctypes.data; P.nmatches = nm.ctypes.data
+    _ck(lib().orbx_search_by_projection(C.byref(P), cam.ctypes.data_as(f32p), sf.ctypes.data_as(f32p), len(sf), th,
+                                        int(check_orientation), device))
+    return int(nm[0]), match[:len(cur_kps)]
 
 
 class ORBVocabulary:

@@ -1328,3 +1328,103 @@ extern "C" int orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_key
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646)
+extern "C" int orbx_search_by_projection_device(const OrbxProjectionPair* pairs, int npairs, const float* camera9,
+                                                const float* scale_factors, int nlevels, float th, int check_orientation,
+                                                int device, void* cuda_stream)
+{
+    if (npairs <= 0) return ORBX_OK;
+    if (!pairs || !camera9 || !scale_factors || nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    size_t tot_last = 0; int max_cur = 0;
+    for (int p = 0; p < npairs; p++) {
+        const OrbxProjectionPair& q = pairs[p];
+        if (q.n_cur < 0 || q.n_last < 0 || !q.match || !q.nmatches || q.mode < 0 || q.mode > 2) return fail(ORBX_ERR_INVALID, "bad pair");
+        if (q.n_cur > 10000) return fail(ORBX_ERR_UNSUPPORTED, "more than 10000 keypoints in the current frame");
+        if ((q.n_cur > 0 && (!q.cur_keypoints || !q.cur_descriptors)) ||
+            (q.n_last > 0 && (!q.last_keypoints || !q.last_xyz || !q.last_descriptors || !q.last_flags))) return fail(ORBX_ERR_INVALID, "NULL array in pair");
+        tot_last += (size_t)q.n_last; max_cur = std::max(max_cur, q.n_cur);
+    }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_pairs = al((size_t)npairs * sizeof(OrbxProjPairDev)), b_q = al(std::max<size_t>(tot_last, 1) * sizeof(OrbxProjQuery)),
+                 b_a = al(std::max<size_t>(tot_last, 1) * 4), b_sf = al((size_t)nlevels * 4);
+    uint8_t* pool = nullptr;
+    CK(cudaMallocAsync(&pool, b_pairs + b_q + b_a + b_sf, st));
+    OrbxProjQuery* d_q = (OrbxProjQuery*)(pool + b_pairs);
+    int* d_a = (int*)(pool + b_pairs + b_q);
+    float* d_sf = (float*)(pool + b_pairs + b_q + b_a);
+    std::vector<OrbxProjPairDev> hp(npairs);
+    size_t off = 0;
+    for (int p = 0; p < npairs; p++) {
+        const OrbxProjectionPair& q = pairs[p];
+        OrbxProjPairDev& d = hp[p];
+        d.cur_kps = (const OrbxKp28*)q.cur_keypoints; d.cur_desc = q.cur_descriptors; d.cur_u_right = q.cur_u_right;
+        d.cur_occupied = q.cur_occupied; d.n_cur = q.n_cur;
+        d.last_kps = (const OrbxKp28*)q.last_keypoints; d.last_xyz = q.last_xyz; d.last_desc = q.last_descriptors;
+        d.last_flags = q.last_flags; d.n_last = q.n_last;
+        memcpy(d.Tcw, q.Tcw, sizeof d.Tcw); d.mode = q.mode;
+        d.match = q.match; d.nmatches = q.nmatches;
+        d.query = d_q + off; d.assign = d_a + off; off += (size_t)q.n_last;
+    }
+    OrbxProjCam cam;
+    cam.fx = camera9[0]; cam.fy = camera9[1]; cam.cx = camera9[2]; cam.cy = camera9[3]; cam.mbf = camera9[4];
+    cam.minX = camera9[5]; cam.maxX = camera9[6]; cam.minY = camera9[7]; cam.maxY = camera9[8];
+    cudaError_t e;
+    do {
+        // pageable staging copies: cudaMemcpyAsync from pageable memory returns after the data has been staged
+        if ((e = cudaMemcpyAsync(pool, hp.data(), (size_t)npairs * sizeof(OrbxProjPairDev), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_sf, scale_factors, (size_t)nlevels * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        orbx_launch_search_projection((const OrbxProjPairDev*)pool, npairs, max_cur, cam, d_sf, th, check_orientation, st);
+        e = cudaGetLastError();
+    } while (0);
+    cudaFreeAsync(pool, st);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_search_by_projection(const OrbxProjectionPair* pair, const float* camera9, const float* scale_factors,
+                                         int nlevels, float th, int check_orientation, int device)
+{
+    if (!pair || !pair->match || !pair->nmatches) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    const int nc = pair->n_cur, nl = pair->n_last;
+    if (nc < 0 || nl < 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t c1 = std::max(nc, 1), l1 = std::max(nl, 1);
+    const size_t b[] = {al(c1 * 28), al(c1 * 32), al(c1 * 4), al(c1), al(l1 * 28), al(l1 * 12), al(l1 * 32), al(l1), al(c1 * 4), 256};
+    size_t tot = 0; for (size_t x : b) tot += x;
+    uint8_t* pool = nullptr;
+    CK(cudaMalloc(&pool, tot));
+    uint8_t* p[10]; { uint8_t* q = pool; for (int i = 0; i < 10; i++) { p[i] = q; q += b[i]; } }
+    OrbxProjectionPair d = *pair;
+    cudaError_t e = cudaSuccess;
+    int rc = ORBX_OK;
+    do {
+        auto up = [&](uint8_t* dst, const void* src, size_t n) { return (!src || !n) ? cudaSuccess : cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); };
+        if ((e = up(p[0], pair->cur_keypoints, (size_t)nc * 28)) != cudaSuccess) break;
+        if ((e = up(p[1], pair->cur_descriptors, (size_t)nc * 32)) != cudaSuccess) break;
+        if ((e = up(p[2], pair->cur_u_right, (size_t)nc * 4)) != cudaSuccess) break;
+        if ((e = up(p[3], pair->cur_occupied, (size_t)nc)) != cudaSuccess) break;
+        if ((e = up(p[4], pair->last_keypoints, (size_t)nl * 28)) != cudaSuccess) break;
+        if ((e = up(p[5], pair->last_xyz, (size_t)nl * 12)) != cudaSuccess) break;
+        if ((e = up(p[6], pair->last_descriptors, (size_t)nl * 32)) != cudaSuccess) break;
+        if ((e = up(p[7], pair->last_flags, (size_t)nl)) != cudaSuccess) break;
+        d.cur_keypoints = (const OrbxKeyPoint*)p[0]; d.cur_descriptors = p[1];
+        d.cur_u_right = pair->cur_u_right ? (const float*)p[2] : nullptr; d.cur_occupied = pair->cur_occupied ? p[3] : nullptr;
+        d.last_keypoints = (const OrbxKeyPoint*)p[4]; d.last_xyz = (const float*)p[5]; d.last_descriptors = p[6]; d.last_flags = p[7];
+        d.match = (int32_t*)p[8]; d.nmatches = (int32_t*)p[9];
+        rc = orbx_search_by_projection_device(&d, 1, camera9, scale_factors, nlevels, th, check_orientation, device, nullptr);
+        if (rc != ORBX_OK) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        if (nc > 0 && (e = cudaMemcpy(pair->match, p[8], (size_t)nc * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        e = cudaMemcpy(pair->nmatches, p[9], 4, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(pool);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}

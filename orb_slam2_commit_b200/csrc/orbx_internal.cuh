@@ -151,6 +151,19 @@ void orbx_launch_bow_transform(const OrbxVocabDev& V, const uint8_t* d_desc, con
 void orbx_launch_bow_score(const OrbxBowOut& O, int cap, const int* d_qa, const int* d_qb, int npairs, double* d_score, cudaStream_t st);
 void orbx_launch_bow_match(const OrbxBowOut& O, const OrbxBowMatchArgs& A, const int* d_n, int cap, int npairs, cudaStream_t st);
 
+// ---- ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (orbx_project.cu)
+struct OrbxProjQuery { float u, v, r, ur; int min_level, max_level; };
+struct OrbxProjCam { float fx, fy, cx, cy, mbf, minX, maxX, minY, maxY; };
+struct OrbxProjPairDev {
+    const OrbxKp28* cur_kps; const uint8_t* cur_desc; const float* cur_u_right; const uint8_t* cur_occupied; int n_cur;
+    const OrbxKp28* last_kps; const float* last_xyz; const uint8_t* last_desc; const uint8_t* last_flags; int n_last;
+    float Tcw[12]; int mode;
+    int* match; int* nmatches;
+    OrbxProjQuery* query; int* assign;            // scratch, n_last entries each
+};
+void orbx_launch_search_projection(const OrbxProjPairDev* d_pairs, int npairs, int max_n_cur, const OrbxProjCam& cam,
+                                   const float* d_scale_factors, float th, int check_orientation, cudaStream_t st);
+
 // cv::undistortPoints(src, dst, K, D, Mat(), K): intrinsics and (k1, k2, p1, p2, k3) widened to f64 on the host
 struct OrbxUndistortArgs { double fx, fy, cx, cy, ifx, ify, k[5]; };
 void orbx_launch_undistort(const OrbxKp28* d_in, OrbxKp28* d_out, int n, const OrbxUndistortArgs& a, cudaStream_t st);

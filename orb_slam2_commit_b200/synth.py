@@ -187,3 +187,69 @@ def synth_features_near_words(voc, n: int, seed: int, max_flips: int = 30):
         for b in rng.integers(0, 256, rng.integers(0, max_flips + 1)):
             out[i, b >> 3] ^= np.uint8(1 << (b & 7))
     return out
+
+
+def synth_tracking_scene(seed: int, n_last: int = 1000, n_extra: int = 400, cluster: float = 0.3, stereo: bool = True):
+    """Inputs of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1489-1646) for a TUM1-like
+    camera: map points in front of the camera, a last frame that observes them and a current frame a small motion away.
+    `cluster` of the map points are near-duplicates (same place, near-identical descriptors) so that several of them
+    compete for one current keypoint — the case where the reference's sequential "already taken" rule matters.
+    Returns a dict with the arguments of api.search_by_projection_frame / oracle.search_by_projection_frame."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, mbf = 517.306408, 516.469215, 318.643040, 255.313989, 40.0
+    W, H = 640.0, 480.0
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    kp_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                         ("octave", "<i4"), ("class_id", "<i4")])
+    n_base = max(1, int(n_last * (1 - cluster)))
+    z = rng.uniform(1.5, 12.0, n_base)
+    xyz = np.stack([(rng.uniform(20, W - 20, n_base) - cx) / fx * z, (rng.uniform(20, H - 20, n_base) - cy) / fy * z, z], 1)
+    desc = rng.integers(0, 256, (n_base, 32), dtype=np.uint8)
+    dup = rng.integers(0, n_base, n_last - n_base)
+    xyz = np.concatenate([xyz, xyz[dup] + rng.normal(0, 0.002, (len(dup), 3))]).astype(np.float32)
+    ddup = desc[dup].copy()
+    for i in range(len(dup)):
+        for b in rng.integers(0, 256, rng.integers(0, 4)):
+            ddup[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    mp_desc = np.concatenate([desc, ddup])
+    order = rng.permutation(n_last)
+    xyz, mp_desc = xyz[order], mp_desc[order]
+    last = np.zeros(n_last, kp_dtype)
+    last["x"] = fx * xyz[:, 0] / xyz[:, 2] + cx; last["y"] = fy * xyz[:, 1] / xyz[:, 2] + cy
+    last["octave"] = rng.integers(0, 8, n_last); last["angle"] = rng.uniform(0, 360, n_last).astype(np.float32)
+    flags = (rng.random(n_last) < 0.92).astype(np.uint8) | ((rng.random(n_last) < 0.7).astype(np.uint8) << 1)
+    # current pose: small rotation about y and a forward / sideways translation
+    a = 0.01
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    t = np.array([0.03, -0.01, -0.08])
+    Tcw = np.concatenate([R.ravel(), t]).astype(np.float32)
+    pc = xyz.astype(np.float64) @ R.T + t
+    u = fx * pc[:, 0] / pc[:, 2] + cx; v = fy * pc[:, 1] / pc[:, 2] + cy
+    # current keypoints: one per BASE map point (duplicates share it), jittered, plus unrelated ones
+    base_of = np.empty(n_last, np.int64); base_of[order] = np.concatenate([np.arange(n_base), dup])
+    first = {}
+    for i in range(n_last):
+        first.setdefault(base_of[i], i)
+    src = np.array(sorted(first.values()))
+    n_cur = len(src) + n_extra
+    cur = np.zeros(n_cur, kp_dtype)
+    cur["x"][:len(src)] = u[src] + rng.normal(0, 1.5, len(src)); cur["y"][:len(src)] = v[src] + rng.normal(0, 1.5, len(src))
+    cur["octave"][:len(src)] = np.clip(last["octave"][src] + rng.integers(-1, 2, len(src)), 0, 7)
+    cur["angle"][:len(src)] = (last["angle"][src] + rng.normal(4, 3, len(src)) + (rng.random(len(src)) < 0.1) * rng.uniform(0, 360, len(src))) % 360
+    cur["x"][len(src):] = rng.uniform(0, W, n_extra); cur["y"][len(src):] = rng.uniform(0, H, n_extra)
+    cur["octave"][len(src):] = rng.integers(0, 8, n_extra); cur["angle"][len(src):] = rng.uniform(0, 360, n_extra)
+    cdesc = np.concatenate([mp_desc[src], rng.integers(0, 256, (n_extra, 32), dtype=np.uint8)])
+    for i in range(len(src)):
+        for b in rng.integers(0, 256, rng.integers(0, 60)):
+            cdesc[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    perm = rng.permutation(n_cur)
+    cur, cdesc = cur[perm], cdesc[perm]
+    ur = None
+    if stereo:
+        zc = np.concatenate([pc[src, 2], rng.uniform(1.5, 12, n_extra)])[perm]
+        ur = (cur["x"] - mbf / zc + rng.normal(0, 0.7, n_cur)).astype(np.float32)
+        ur[rng.random(n_cur) < 0.25] = -1.0
+    occ = (rng.random(n_cur) < 0.03).astype(np.uint8)
+    cam9 = np.array([fx, fy, cx, cy, mbf, 0.0, W, 0.0, H], np.float32)
+    return dict(cur_kps=cur, cur_desc=cdesc, cur_u_right=ur, cur_occupied=occ, Tcw12=Tcw, cam9=cam9, scale_factors=sf,
+                last_kps=last, last_xyz=xyz, last_desc=mp_desc, last_flags=flags)

@@ -582,3 +582,30 @@ def test_search_by_bow_matches_oracle(check_ori, nnratio):
     to, tf = Vo.transform(dk, 2), Vo.transform(df2, 2)
     no, mo = ob.search_by_bow(to, tf, dk, kk["angle"], np.ones(len(kk), np.uint8), df2, kf["angle"], nnratio, check_ori)
     assert n == no and np.array_equal(m, mo)
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False), (3, True)])
+def test_search_by_projection_frame_matches_oracle(seed, stereo):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1489-1646): the assignment of
+    last-frame map points to current keypoints (incl. the sequential already-taken rule under heavy contention, the
+    overwrite by unobserved points, forward / backward / neutral level ranges, the stereo gate and the rotation check)
+    and the match count are identical to the restatement."""
+    from orb_slam2_commit_b200 import search_by_projection_frame
+    s = synth.synth_tracking_scene(seed, stereo=stereo)
+    for mode in (0, 1, 2):
+        for th, ori in ((7.0, True), (15.0, False)):
+            n, m = search_by_projection_frame(**s, th=th, mode=mode, check_orientation=ori)
+            no, mo = ob.search_by_projection_frame(**s, th=th, mode=mode, check_orientation=ori)
+            assert n == no, f"seed {seed} mode {mode} th {th}: nmatches {n} vs {no}"
+            assert np.array_equal(m, mo), f"seed {seed} mode {mode} th {th}: {np.count_nonzero(m != mo)} assignments differ"
+            assert n > 100
+    # all map points observed (every assignment blocks later ones) and none observed (free overwriting)
+    for bit in (2, 0):
+        s2 = dict(s); s2["last_flags"] = (s["last_flags"] & 1) | bit
+        n, m = search_by_projection_frame(**s2, th=15.0, mode=0, check_orientation=True)
+        no, mo = ob.search_by_projection_frame(**s2, th=15.0, mode=0, check_orientation=True)
+        assert n == no and np.array_equal(m, mo)
+    # degenerate inputs
+    e = dict(s); e["last_flags"] = np.zeros_like(s["last_flags"])
+    n, m = search_by_projection_frame(**e, th=7.0, mode=0)
+    assert n == 0 and (m == -1).all()
