@@ -36,6 +36,11 @@ WORKLOADS = {
     # BASELINE configs[1]: stereo pairs, left + right extraction and Frame::ComputeStereoMatches
     "kitti_stereo": dict(cfg="kitti", batch=128, distinct=8, stereo=True),
     "euroc_stereo": dict(cfg="euroc", batch=256, distinct=8, stereo=True),
+    # SURVEY §8(f) rows built around the extractor
+    # stereo_euroc.cc:136-137: cv::remap rectification fused into pyramid level 0
+    "euroc_rect": dict(cfg="euroc", batch=1024, distinct=32, rectify=True),
+    # per-frame front-end of Tracking: extract -> UndistortKeyPoints -> ComputeBoW -> SearchByBoW / L1 score vs previous frame
+    "tum1_frame": dict(cfg="tum1", batch=512, distinct=32, frame=True),
 }
 
 
@@ -237,6 +242,138 @@ def bench_hamming(torch, api_lib, dev, peaks, sm_mhz):
             "popc_pipe_frac": popc / (ms * 1e-3) / (148 * 16 * clk), "popc_pipe_model": "148 SMs x 16 popc/clk x measured SM clock"}
 
 
+def cpu_thread_bench(make_worker, target_seconds, nthreads):
+    """Generic CPU baseline: make_worker(tid) -> f(i) doing one unit of work through ctypes (GIL released)."""
+    workers = [make_worker(t) for t in range(nthreads)]
+
+    def run(iters):
+        def work(t):
+            for i in range(t, iters, nthreads):
+                workers[t](i)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        [x.start() for x in th]; [x.join() for x in th]
+        return time.perf_counter() - t0
+    t1 = run(nthreads)
+    iters = int(max(nthreads, nthreads * max(1.0, target_seconds / max(t1, 1e-3))))
+    tt = run(iters)
+    return iters / tt, f"{iters} units over {nthreads} threads, {tt:.1f} s"
+
+
+def run_frame(args, torch, dist, rank, world, local, dev):
+    """Frame front-end behind the extractor, chained on the device with no host round trip:
+    extract -> Frame::UndistortKeyPoints -> Frame::ComputeBoW (vocabulary k=10, L=6, levelsup 4) -> for every frame
+    ORBmatcher::SearchByBoW against the previous frame of the batch and the L1 BoW score against it."""
+    from orb_slam2_commit_b200 import ORBextractor, ORBVocabulary, api
+    w = WORKLOADS[args.workload]; c = synth.CONFIGS[w["cfg"]]
+    B = args.batch or w["batch"]; W, H = c["width"], c["height"]
+    frames = make_frames(c, w["distinct"], seed0=1 + 1000 * rank)
+    host_batch = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True); hb = host_batch.numpy()
+    for i in range(B):
+        hb[i] = frames[i % len(frames)]
+    d_imgs = host_batch.to(dev)
+    voc = synth.synth_vocabulary(10, 6, 7)
+    V = ORBVocabulary(10, 6, *voc, device=local)
+    cfgargs = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    ex = ORBextractor(*cfgargs, device=local)
+    cap = ex.reserve(W, H, B)
+    mk = lambda *shape, dt=torch.uint8: torch.zeros(shape, dtype=dt, device=dev)
+    d_kps, d_un, d_desc, d_nkp = mk(B, cap, 28), mk(B, cap, 28), mk(B, cap, 32), mk(B, dt=torch.int32)
+    # every frame is matched against the previous occurrence of the same scene in the stream (the batch cycles through
+    # `distinct` synthetic scenes), so SearchByBoW / the score see a realistic overlap instead of unrelated images
+    kf = torch.arange(0, B, dtype=torch.int32, device=dev); ff = torch.roll(kf, -len(frames))
+    d_match, d_nm, d_score = mk(B, cap, dt=torch.int32), mk(B, dt=torch.int32), mk(B, dt=torch.float64)
+    K4 = synth.TUM1_K4; D5 = synth.TUM1_DIST
+    import ctypes as C
+    f32p = C.POINTER(C.c_float)
+    L = api.lib()
+    ts = torch.cuda.Stream(device=dev); torch.cuda.set_stream(ts); st = ts.cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def step(timed=False):
+        if timed: ev[0].record()
+        ex.extract_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), cap, d_nkp.data_ptr(), d_desc.data_ptr(), st)
+        if timed: ev[1].record()
+        api._ck(L.orbx_undistort_keypoints_device(d_kps.data_ptr(), B * cap, K4.ctypes.data_as(f32p), D5.ctypes.data_as(f32p), 5,
+                                                  d_un.data_ptr(), st))
+        if timed: ev[2].record()
+        V.transform_device(d_desc.data_ptr(), d_nkp.data_ptr(), B, cap, 4, st)
+        if timed: ev[3].record()
+        V.search_by_bow_device(B, kf.data_ptr(), ff.data_ptr(), d_un.data_ptr(), d_desc.data_ptr(), None, 0.7, True,
+                               d_match.data_ptr(), d_nm.data_ptr(), st)
+        V.score_device(kf.data_ptr(), ff.data_ptr(), B, d_score.data_ptr(), st)
+        if timed: ev[4].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup): step()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps): step()
+    e1.record(); torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1); clocks = sampler.stop()
+    step(timed=True); torch.cuda.synchronize()
+    st_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+    outs_src = (d_un, d_desc, d_nkp, d_match, d_nm, d_score)
+    outs = [torch.empty_like(x, device="cpu").pin_memory() for x in outs_src]
+
+    def e2e_step():
+        d_imgs.copy_(host_batch, non_blocking=True)
+        step()
+        for o, x in zip(outs, outs_src): o.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(2): e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10)); t0 = time.perf_counter()
+    for _ in range(n_e2e): e2e_step()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_v = world * B * n_e2e / float(t.item())
+    if rank != 0: return
+    nkp = outs[2].numpy()
+    line = {"metric": "frontend_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"{w['cfg']} frame front-end: {W}x{H}, nFeatures={c['nfeatures']}: extract + UndistortKeyPoints + ComputeBoW "
+                                   f"(synthetic vocabulary k=10 L=6, {V.nwords} words) + SearchByBoW and L1 score against the previous frame",
+                       "frames_per_step_per_gpu": B, "distinct_frames": len(frames)},
+            "clocks": clocks, "gpu_launches": (c["nlevels"] + 3 + 1 + 2 + 3 + 1) * args.steps,
+            "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
+                    "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in outs)), "steps": n_e2e,
+                    "api": "orbx_extract_device + orbx_undistort_keypoints_device + orbx_bow_transform_device + orbx_search_by_bow_device + orbx_bow_score_device, pinned host buffers"},
+            "stages": {"extract_ms": st_ms[0], "undistort_ms": st_ms[1], "bow_transform_ms": st_ms[2], "search_by_bow_and_score_ms": st_ms[3]},
+            "pipeline": {"keypoints_per_frame": float(nkp.mean()), "bow_matches_per_frame": float(outs[4].numpy().mean()),
+                         "mean_l1_score_vs_previous": float(outs[5].numpy().mean())}}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        nthreads = os.cpu_count() or 1
+        Vo = ob.Vocabulary(10, 6, *voc)
+        def make_worker(tid):
+            e = ob.Extractor(*cfgargs)
+            state = {}
+            def f(i):
+                k, d = e.extract(frames[i % len(frames)])
+                ob.undistort_points(np.stack([k["x"], k["y"]], 1), K4, D5)
+                tcur = Vo.transform(d, 4)
+                if "t" in state:
+                    ob.search_by_bow(state["t"], tcur, state["d"], state["k"]["angle"], np.ones(len(state["k"]), np.uint8), d, k["angle"], 0.7, True)
+                    ob.bow_score_l1(state["t"]["bow_id"], state["t"]["bow_val"], tcur["bow_id"], tcur["bow_val"])
+                state.update(t=tcur, d=d, k=k)
+            return f
+        v, sample = cpu_thread_bench(make_worker, args.cpu_seconds, nthreads)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+
+
 def run_stereo(args, torch, dist, rank, world, local, dev):
     """Stereo pairs/s: two extractor instances (as the reference, Tracking.cc:120-123) + the device-resident matcher."""
     from orb_slam2_commit_b200 import ORBextractor, api, stereo_match_device
@@ -368,8 +505,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    if WORKLOADS[args.workload].get("stereo"):
-        run_stereo(args, torch, dist, rank, world, local, dev)
+    if WORKLOADS[args.workload].get("stereo") or WORKLOADS[args.workload].get("frame"):
+        (run_stereo if WORKLOADS[args.workload].get("stereo") else run_frame)(args, torch, dist, rank, world, local, dev)
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return
@@ -386,6 +523,10 @@ def main():
     d_imgs = host_batch.to(dev)
 
     ex = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"], device=local)
+    rectify = bool(w.get("rectify"))
+    if rectify:
+        rmaps = synth.rectify_maps(W, H)
+        ex.set_rectify_maps(*rmaps)
     cap = ex.reserve(W, H, B)
     d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
@@ -396,7 +537,11 @@ def main():
     stream = tstream.cuda_stream
 
     def step():
-        ex.extract_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), cap, d_nkp.data_ptr(), d_desc.data_ptr(), stream)
+        if rectify:
+            ex.extract_device_rectified(d_imgs.data_ptr(), B, W, W * H, d_kps.data_ptr(), cap, d_nkp.data_ptr(), d_desc.data_ptr(), stream)
+        else:
+            ex.extract_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), cap, d_nkp.data_ptr(), d_desc.data_ptr(), stream)
+    host_call = ex.extract_host_rectified if rectify else ex.extract_host
 
     def barrier():
         torch.cuda.synchronize()
@@ -435,11 +580,11 @@ def main():
     desc_np = h_desc.numpy(); nkp_np = h_nkp.numpy()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        ex.extract_host(hb, kps_np, desc_np, nkp_np)
+        host_call(hb, kps_np, desc_np, nkp_np)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ex.extract_host(hb, kps_np, desc_np, nkp_np)
+        host_call(hb, kps_np, desc_np, nkp_np)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -451,7 +596,7 @@ def main():
 
     # ---- single-frame latency through orbx_extract (what a SLAM front-end sees: one frame in, keypoints out)
     lat_ms = None
-    if rank == 0:
+    if rank == 0 and not rectify:
         ex1 = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"], device=local)
         cap1 = ex1.reserve(W, H, 1)
         k1 = h_kps.numpy().view(api.KP_DTYPE).reshape(-1)[:cap1].reshape(1, cap1)
@@ -547,12 +692,12 @@ def main():
         line = {"metric": "orb_frames_per_s", "value": frames_per_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"{w['cfg']}: {W}x{H} mono frames, nFeatures={c['nfeatures']}, scale {c['scale']}, {c['nlevels']} levels, FAST {c['ini_th']}/{c['min_th']}",
+                "config": {"workload": f"{w['cfg']}{' + fused cv::remap rectification' if rectify else ''}: {W}x{H} mono frames, nFeatures={c['nfeatures']}, scale {c['scale']}, {c['nlevels']} levels, FAST {c['ini_th']}/{c['min_th']}",
                            "frames_per_step_per_gpu": B, "distinct_frames": len(frames), "sharding": "by frame, no collective",
                            "l2": f"batch working set {B * (W * H + ab['A'] * 1.3) / 1e6:.0f} MB per step > 126 MB L2 (inputs {B * W * H / 1e6:.0f} MB)"},
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-                        "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": "orbx_extract_batch (pinned host buffers)"},
+                        "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": ("orbx_extract_batch_rectified" if rectify else "orbx_extract_batch") + " (pinned host buffers)"},
                 "latency_single_frame_ms": lat_ms,
                 "roofline": roofline, "stages": stages,
                 "pipeline": {"keypoints_per_frame": nkp_mean, "keypoints_per_s": frames_per_s * nkp_mean,
@@ -567,7 +712,17 @@ def main():
             line["hamming"] = hamming_sharded
         if world == 1 and not args.no_cpu_baseline:
             nthreads = os.cpu_count() or 1
-            fps, kind, sample, kpf = cpu_reference_bench(c, frames[:8], args.cpu_seconds, nthreads)
+            if rectify:
+                from oracle import binding as ob
+                def make_worker(tid):
+                    e = ob.RefExtractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"]) if ob.ref_available() else \
+                        ob.Extractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+                    return lambda i: e.extract(ob.remap(frames[i % 8], *rmaps))
+                fps, sample = cpu_thread_bench(make_worker, args.cpu_seconds, nthreads)
+                kind, kpf = ("reference" if ob.ref_available() else "port"), None
+                sample += " (oracle remap + extractor per frame)"
+            else:
+                fps, kind, sample, kpf = cpu_reference_bench(c, frames[:8], args.cpu_seconds, nthreads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": kind, "sample": sample,
                                     "keypoints_per_frame": kpf}
         else:

@@ -281,6 +281,14 @@ class ORBextractor:
         ptrs = (C.c_void_p * n)(*[base + i * h * w for i in range(n)])
         _ck(self._L.orbx_extract_batch(self._h, ptrs, n, w, h, w, kps.ctypes.data, cap, nkp.ctypes.data_as(i32p), desc.ctypes.data))
 
+    def extract_host_rectified(self, images: np.ndarray, kps: np.ndarray, desc: np.ndarray, nkp: np.ndarray):
+        """orbx_extract_batch_rectified on caller-owned buffers (see extract_host); images are UNRECTIFIED frames."""
+        n, h, w = images.shape
+        cap = kps.shape[1]
+        base = images.ctypes.data
+        ptrs = (C.c_void_p * n)(*[base + i * h * w for i in range(n)])
+        _ck(self._L.orbx_extract_batch_rectified(self._h, ptrs, n, w, kps.ctypes.data, cap, nkp.ctypes.data_as(i32p), desc.ctypes.data))
+
     # ---- mvImagePyramid (ORBextractor.h:104)
     def level_size(self, level):
         w = C.c_int32(); h = C.c_int32()
