@@ -15,6 +15,7 @@ MAIN = textwrap.dedent(r"""
     #include "ORBextractor.h"
     #include "HammingTop2.h"
     #include "StereoMatch.h"
+    #include "FrameOps.h"
     #include <cstdio>
     int main() {
         ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 20, 7);
@@ -26,6 +27,15 @@ MAIN = textwrap.dedent(r"""
         cv::Mat empty, desc;
         ex(empty, cv::Mat(), kps, desc);                 // ORBextractor.cc:1141: silent return, outputs untouched
         std::printf("%zu %d\n", kps.size(), (int)desc.empty());
+        // the Frame / ORBmatcher wrappers: empty inputs return without touching the GPU
+        std::vector<cv::KeyPoint> none, un; std::vector<int> match; std::vector<float> sf2(8, 1.f), xyz; std::vector<unsigned char> d8, fl;
+        const float K4[4] = {500, 500, 320, 240}, D[5] = {0, 0, 0, 0, 0}, T[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}, cam[9] = {500, 500, 320, 240, 40, 0, 640, 0, 480};
+        bool ok = ORB_SLAM2::UndistortKeyPointsGPU(none, K4, D, 5, un);
+        float a, b, c, d; ok = ok && ORB_SLAM2::ComputeImageBoundsGPU(640, 480, K4, D, 5, a, b, c, d);
+        int nm = ORB_SLAM2::SearchByProjectionGPU(none, desc, 0, 0, T, cam, sf2, none, xyz, d8, fl, 7.f, 0, true, match);
+        std::map<unsigned int, double> bow; std::map<unsigned int, std::vector<unsigned int> > fv;
+        ok = ok && ORB_SLAM2::ComputeBoWGPU(0, desc, bow, fv) && ORB_SLAM2::ExtractRectified(&ex, empty, kps, desc);
+        std::printf("%d %d %.0f %.0f %.0f %.0f\n", (int)ok, nm, a, b, c, d);
         return 0;
     }
 """)
@@ -50,3 +60,4 @@ def test_shim_compiles_links_and_matches_getters(tmp_path):
     assert np.float32(float(f[2])) == t["scale_factors"][7] and np.float32(float(f[3])) == t["inv_scale_factors"][7]
     assert np.float32(float(f[4])) == t["sigma2"][7] and np.float32(float(f[5])) == t["inv_sigma2"][7]
     assert out[1].split() == ["3", "1"]
+    assert out[2].split() == ["1", "0", "0", "640", "0", "480"]       # Frame.cc:530-536 without distortion
