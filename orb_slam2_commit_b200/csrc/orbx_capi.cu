@@ -46,12 +46,23 @@ struct orbx_extractor {
     uint8_t* d_desc = nullptr;
     int* d_nkp = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t slot_stream[2] = {nullptr, nullptr};   // host-path double buffering (copy/compute overlap)
+    static const int MAX_SLOTS = 8;
+    cudaStream_t slot_stream[MAX_SLOTS] = {};   // host-path double buffering (copy/compute overlap)
     uint2* d_remap = nullptr;                     // fixed-point rectification map (orbx_set_rectify_maps)
     int map_w = 0, map_h = 0, map_src_w = 0, map_src_h = 0;
     int pyr_base = 0;                             // first working-set frame of the last pipeline run
     void* stereo_scratch = nullptr; size_t stereo_scratch_bytes = 0;   // SAD per left keypoint (stereo matcher)
     int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
+    int map_chunk = 0, map_slots = 1;             // host batch path: frame f sits at ((f/chunk) % slots)*chunk + f%chunk
+    // working-set index of frame `frame` of the last call, or -1 when a later chunk has reused its slot
+    int ws_index(int frame) const
+    {
+        if (frame < 0 || frame >= last_frames) return -1;
+        if (!map_chunk) return pyr_base + frame;
+        const int k = frame / map_chunk, nchunks = (last_frames + map_chunk - 1) / map_chunk;
+        if (k + map_slots < nchunks) return -1;
+        return (k % map_slots) * map_chunk + frame % map_chunk;
+    }
     bool constants_ready = false;
     bool timing = false;
     static const int RING = 64;
@@ -135,7 +146,7 @@ extern "C" void orbx_destroy(orbx_extractor* h)
     for (int r = 0; r < orbx_extractor::RING; r++)
         for (int i = 0; i < 5; i++) if (h->ev[r][i]) cudaEventDestroy(h->ev[r][i]);
     if (h->stream) cudaStreamDestroy(h->stream);
-    for (int j = 0; j < 2; j++) if (h->slot_stream[j]) cudaStreamDestroy(h->slot_stream[j]);
+    for (int j = 0; j < orbx_extractor::MAX_SLOTS; j++) if (h->slot_stream[j]) cudaStreamDestroy(h->slot_stream[j]);
     cudaGetLastError();
     delete h;
 }
@@ -277,7 +288,7 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     CK(cudaSetDevice(h->device));
     if (!h->stream) CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamSynchronize(h->stream));
-    for (int j = 0; j < 2; j++) if (h->slot_stream[j]) CK(cudaStreamSynchronize(h->slot_stream[j]));
+    for (int j = 0; j < orbx_extractor::MAX_SLOTS; j++) if (h->slot_stream[j]) CK(cudaStreamSynchronize(h->slot_stream[j]));
     release_device(h);
     int rc = build_geometry(h, width, height);
     if (rc != ORBX_OK) return rc;
@@ -356,6 +367,7 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     CK(cudaGetLastError());
     h->last_frames = n;
     h->pyr_base = base;
+    h->map_chunk = 0;
     return ORBX_OK;
 }
 
@@ -453,11 +465,15 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
         h->d_in_bytes = (size_t)B * fbytes;
     }
     int status = ORBX_OK;
-    // Two chunks in flight on two streams, each in its own half of the reserved working set: the H2D copy of chunk
-    // k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k. A slot's stream serialises its own
-    // H2D -> kernels -> D2H, so reusing a slot needs no extra event.
-    const int chunk = B >= 8 ? std::max(1, std::min(B / 2, 128)) : B;
-    const int nslots = B >= 8 ? 2 : 1;
+    // Up to eight chunks in flight on as many streams, each in its own slice of the reserved working set: the H2D copy
+    // of later chunks and the D2H copy of earlier ones overlap the kernels of the current ones, and short chunks keep
+    // the pipeline's fill and drain (one chunk's copy time each) small. A slot's stream serialises its own
+    // H2D -> kernels -> D2H, so reusing a slot needs no extra event. ORBX_CHUNK / ORBX_SLOTS override the defaults
+    // (measured on B200, 1024 VGA frames per call: 2 x 128 -> 89 k frames/s, 8 x 64 -> 99 k).
+    int chunk = B >= 8 ? std::min(64, std::max(8, B / 8)) : B;
+    if (const char* e = getenv("ORBX_CHUNK")) { const int v = atoi(e); if (v > 0 && B >= 8) chunk = std::min(v, B / 2); }
+    int nslots = B >= 8 ? std::max(1, std::min(orbx_extractor::MAX_SLOTS, B / chunk)) : 1;
+    if (const char* e = getenv("ORBX_SLOTS")) { const int v = atoi(e); if (v > 0 && B >= 8) nslots = std::max(1, std::min(std::min(v, orbx_extractor::MAX_SLOTS), B / chunk)); }
     for (int j = 0; j < nslots; j++)
         if (!h->slot_stream[j]) CK(cudaStreamCreateWithFlags(&h->slot_stream[j], cudaStreamNonBlocking));
     CK(cudaStreamSynchronize(h->stream));
@@ -501,6 +517,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
         }
     }
     for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(h->slot_stream[j]));
+    h->last_frames = n; h->pyr_base = 0; h->map_chunk = chunk; h->map_slots = nslots;   // for the pyramid / debug accessors
     for (int i = 0; i < n; i++) if (nkp[i] > cap) status = ORBX_ERR_CAPACITY;
     if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
     return status;
@@ -579,8 +596,10 @@ extern "C" int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level
 {
     if (!h || !h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");
     if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame/level out of range");
+    const int wsi = h->ws_index(frame);
+    if (wsi < 0) return fail(ORBX_ERR_STATE, "the pyramid of this frame has been overwritten by a later chunk of the same call");
     const OrbxLevelGeom& g = h->lvl[level];
-    if (d_payload) *d_payload = h->L.raw + (size_t)(h->pyr_base + frame) * h->L.frame_raw_bytes + g.raw_off + (size_t)ORBX_EDGE * g.pitch + ORBX_XOFF;
+    if (d_payload) *d_payload = h->L.raw + (size_t)wsi * h->L.frame_raw_bytes + g.raw_off + (size_t)ORBX_EDGE * g.pitch + ORBX_XOFF;
     if (pitch) *pitch = g.pitch;
     return ORBX_OK;
 }
@@ -605,7 +624,8 @@ extern "C" int orbx_debug_level_counts(orbx_extractor* h, int frame, int32_t* co
     if (frame < 0 || frame >= h->last_frames || !counts) return fail(ORBX_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(counts, h->L.lvl_kp_count + (size_t)(h->pyr_base + frame) * h->nlevels, h->nlevels * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h->ws_index(frame) < 0) return fail(ORBX_ERR_STATE, "frame overwritten by a later chunk");
+    CK(cudaMemcpy(counts, h->L.lvl_kp_count + (size_t)h->ws_index(frame) * h->nlevels, h->nlevels * sizeof(int), cudaMemcpyDeviceToHost));
     return ORBX_OK;
 }
 
@@ -616,12 +636,13 @@ extern "C" int orbx_debug_candidates(orbx_extractor* h, int frame, int level, Or
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     int cnt = 0;
-    CK(cudaMemcpy(&cnt, h->L.cand_count + (size_t)(h->pyr_base + frame) * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h->ws_index(frame) < 0) return fail(ORBX_ERR_STATE, "frame overwritten by a later chunk");
+    CK(cudaMemcpy(&cnt, h->L.cand_count + (size_t)h->ws_index(frame) * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     *n = cnt;
     const int m = std::min(cnt, cap);
     if (m > 0 && out) {
         std::vector<uint32_t> tmp(m);
-        CK(cudaMemcpy(tmp.data(), h->L.cand + (size_t)(h->pyr_base + frame) * h->L.cand_total + h->lvl[level].cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(tmp.data(), h->L.cand + (size_t)h->ws_index(frame) * h->L.cand_total + h->lvl[level].cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
         for (int i = 0; i < m; i++) {
             OrbxKeyPoint k;
             k.x = (float)(tmp[i] & 0xfff); k.y = (float)((tmp[i] >> 12) & 0xfff);
@@ -752,6 +773,8 @@ static int stereo_check_pair(orbx_extractor* left, orbx_extractor* right, int pa
 {
     if (left->last_frames < pairs || right->last_frames < pairs)
         return fail(ORBX_ERR_STATE, "both extractors must have extracted the pair(s) first");
+    if ((left->map_chunk && pairs > left->map_chunk) || (right->map_chunk && pairs > right->map_chunk))
+        return fail(ORBX_ERR_STATE, "batched stereo matching needs the pyramids of orbx_extract_device (contiguous frames)");
     if (left->device != right->device || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels ||
         left->scale_factor != right->scale_factor)
         return fail(ORBX_ERR_INVALID, "left and right extractors must share device, image size and pyramid settings");

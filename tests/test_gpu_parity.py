@@ -609,3 +609,20 @@ def test_search_by_projection_frame_matches_oracle(seed, stereo):
     e = dict(s); e["last_flags"] = np.zeros_like(s["last_flags"])
     n, m = search_by_projection_frame(**e, th=7.0, mode=0)
     assert n == 0 and (m == -1).all()
+
+
+def test_pyramid_accessor_after_chunked_host_batch():
+    """The host batch path runs several chunks in flight in slices of the working set; the pyramid accessor maps a frame
+    index of the call to its slice and refuses frames whose slice a later chunk has reused."""
+    from orb_slam2_commit_b200 import OrbxError
+    imgs = [synth.synth_image(320, 240, 400 + i) for i in range(20)]
+    ex = ORBextractor(300, 1.2, 4, 20, 7)
+    kps, descs = ex.extract_batch(imgs, max_batch=20)          # working set 20 -> chunks of 8 in 2 slots: 8 + 8 + 4 frames
+    orc = ob.Extractor(300, 1.2, 4, 20, 7)
+    for i in (8, 15, 16, 19):
+        ko, do = orc.extract(imgs[i])
+        _check_against(kps[i], descs[i], ko, do, f"frame {i}")
+        assert np.array_equal(ex.pyramid_level(0, frame=i), imgs[i])
+        assert np.array_equal(ex.pyramid_level(2, frame=i, with_apron=True), orc.level(2))
+    with pytest.raises(OrbxError):
+        ex.pyramid_level(0, frame=3)                           # slot reused by frames 16..19
