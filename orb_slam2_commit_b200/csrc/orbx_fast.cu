@@ -64,6 +64,21 @@ __device__ __forceinline__ int fast_score_T(const uint8_t* __restrict__ c, const
     return s >= T ? s : 0;
 }
 
+// Quick test of one pixel, result in the SIGN BIT: set iff two adjacent compass pixels (ring 0, 4, 8, 12) are both darker
+// than v - T or both brighter than v + T. Both compares of a ring pixel r ride in one multiply-add:
+//   X = r * 0xFFFF0001 + C,  C = v * 0xFFFF + KT,  KT = (T + 0x8000) << 16 | (0x8000 + T)
+// leaves r - (v - T) + 0x8000 in the low half and (v + T) - r + 0x8000 in the high half (neither half can carry into
+// the other), so bit 15 is CLEAR iff r is dark and bit 31 is CLEAR iff r is bright. With Y = (X4 & X12) | (X0 & X8),
+// bit 15 of Y is clear iff (D4|D12)&(D0|D8) == (D0&D4)|(D4&D8)|(D8&D12)|(D12&D0), bit 31 likewise for bright.
+__device__ __forceinline__ unsigned quick_test(const uint8_t* __restrict__ qp, const int tp, const unsigned KT)
+{
+    const unsigned C = (unsigned)qp[0] * 0xFFFFu + KT;
+    const unsigned X0 = (unsigned)qp[3 * tp] * 0xFFFF0001u + C, X4 = (unsigned)qp[3] * 0xFFFF0001u + C;
+    const unsigned X8 = (unsigned)qp[-3 * tp] * 0xFFFF0001u + C, X12 = (unsigned)qp[-3] * 0xFFFF0001u + C;
+    const unsigned Y = (X4 & X12) | (X0 & X8);
+    return ~(Y & (Y << 16));
+}
+
 // TPC / SPC: compile-time tile / score-map pitches in bytes (all ring and NMS offsets become immediates);
 // 0 = take them from cfg (cells wider than the common 30..46 px)
 template <int TPC, int SPC>
@@ -131,7 +146,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
         const unsigned lt_mask = (1u << lane) - 1;
         {
             // lane = column, rows walked top to bottom; the pass bit of every row is shifted into a per-lane mask
-            // (funnel shift pulls the sign of x = (T-dk)|(br+T) in: one instruction, no ballot in the arithmetic loop).
+            // (funnel shift pulls the sign bit of quick_test() in: one instruction, no ballot in the arithmetic loop).
+            const unsigned KT = ((unsigned)(T + 0x8000) << 16) + (unsigned)(0x8000 + T);
             // Up to two 32-column chunks (cells are < 60 px wide) and two 32-row halves (< 60 px tall).
             const int nlo = min(eh, 32), nhi = eh - nlo;
             unsigned q[2][2] = {{0u, 0u}, {0u, 0u}};            // [chunk][row half], bit (n-1-row) <-> row
@@ -143,27 +159,13 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
                 unsigned acc = 0;
 #pragma unroll 4
                 for (int py = 0; py < nlo; py++) {
-                    const uint8_t* qp = col + py * tp;
-                    const int v = qp[0], lo = v - T, hi = v + T;
-                    const int r0 = qp[3 * tp], r4 = qp[3], r8 = qp[-3 * tp], r12 = qp[-3];
-                    // sign bit of (r - lo): ring pixel darker than v - T; of (hi - r): brighter than v + T.
-                    // (D0&D4)|(D4&D8)|(D8&D12)|(D12&D0) == (D4|D12)&(D0|D8): plain bitwise logic on the sign bits
-                    const int dk = ((r4 - lo) | (r12 - lo)) & ((r0 - lo) | (r8 - lo));
-                    const int br = ((hi - r4) | (hi - r12)) & ((hi - r0) | (hi - r8));
-                    acc = __funnelshift_l((unsigned)(dk | br), acc, 1);
+                    acc = __funnelshift_l(quick_test(col + py * tp, tp, KT), acc, 1);
                 }
                 q[ch][0] = px < ew ? acc : 0u;
                 acc = 0;
 #pragma unroll 4
                 for (int py = 32; py < eh; py++) {
-                    const uint8_t* qp = col + py * tp;
-                    const int v = qp[0], lo = v - T, hi = v + T;
-                    const int r0 = qp[3 * tp], r4 = qp[3], r8 = qp[-3 * tp], r12 = qp[-3];
-                    // sign bit of (r - lo): ring pixel darker than v - T; of (hi - r): brighter than v + T.
-                    // (D0&D4)|(D4&D8)|(D8&D12)|(D12&D0) == (D4|D12)&(D0|D8): plain bitwise logic on the sign bits
-                    const int dk = ((r4 - lo) | (r12 - lo)) & ((r0 - lo) | (r8 - lo));
-                    const int br = ((hi - r4) | (hi - r12)) & ((hi - r0) | (hi - r8));
-                    acc = __funnelshift_l((unsigned)(dk | br), acc, 1);
+                    acc = __funnelshift_l(quick_test(col + py * tp, tp, KT), acc, 1);
                 }
                 q[ch][1] = px < ew ? acc : 0u;
             }
