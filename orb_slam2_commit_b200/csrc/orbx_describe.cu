@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
                                                                     uint8_t* __restrict__ desc, int cap,
                                                                     int* __restrict__ nkp)
 {
-    __shared__ uint32_t s_raw[DESC_WARPS][PW * PWORDS + 4];   // +4: the last row's aligned window may over-read
-    __shared__ unsigned short s_hb[DESC_WARPS][PW * HBP];
+    __shared__ __align__(16) uint32_t s_raw[DESC_WARPS][PW * PWORDS + 4];   // +4: the last row's aligned windows over-read by up to two words
+    __shared__ __align__(16) unsigned short s_hb[DESC_WARPS][PW * HBP];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // this lane's 16 sample points (32 int8 = two 128-bit words), fetched first so the latency hides behind staging;
     // no block-level barrier anywhere in this kernel
@@ -186,25 +186,32 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
 
     // ---- horizontal pass of the fixed-point Gaussian on the patch: hb[r][c] <-> patch column c+3
     unsigned short* hb = s_hb[wid];
-    // each lane produces 4 adjacent outputs from one aligned 4-word window (10 source bytes) instead of 28 byte loads
-    for (int gi = lane; gi < PW * 10; gi += 32) {
-        const int r = gi / 10, c0 = (gi - r * 10) * 4;
+    // each lane produces 8 adjacent outputs of a row from five aligned words: the twelve 4-byte windows starting at
+    // bytes 0..11 come from funnel shifts, and every output is two 4-way byte dot products (weights 18,34,48,56 | 48,34,18,0)
+    const uint32_t WT0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), WT1 = 48u | (34u << 8) | (18u << 16);
+    for (int gi = lane; gi < PW * 5; gi += 32) {
+        const int r = gi / 5, c0 = (gi - r * 5) * 8;
         const int bo = sh + c0;
+        // bo >> 2 == c0 / 4 is even (sh < 4), so the five words are two aligned 64-bit loads and one 32-bit load
         const uint32_t* rw = raw32 + r * PWORDS + (bo >> 2);
         const int s8 = (bo & 3) * 8;
-        const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2], w3 = rw[3];
-        const uint32_t a0 = __funnelshift_r(w0, w1, s8), a1 = __funnelshift_r(w1, w2, s8), a2 = __funnelshift_r(w2, w3, s8);
-        // P[k] = byte k | byte k+1 << 16 : two adjacent outputs ride in the two 16-bit halves of ordinary 32-bit
-        // integer ops (each sum stays below 2^16, so nothing carries from the low half into the high half)
-        uint32_t P[9];
-        P[0] = __byte_perm(a0, 0, 0x4140); P[1] = __byte_perm(a0, 0, 0x4241); P[2] = __byte_perm(a0, 0, 0x4342);
-        P[3] = __byte_perm(__funnelshift_r(a0, a1, 16), 0, 0x4241);   // bytes 3,4 straddle two words
-        P[4] = __byte_perm(a1, 0, 0x4140); P[5] = __byte_perm(a1, 0, 0x4241); P[6] = __byte_perm(a1, 0, 0x4342);
-        P[7] = __byte_perm(__funnelshift_r(a1, a2, 16), 0, 0x4241);   // bytes 7,8
-        P[8] = __byte_perm(a2, 0, 0x4140);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(hb + r * HBP + c0);
-        dst[0] = 18u * (P[0] + P[6]) + 34u * (P[1] + P[5]) + 48u * (P[2] + P[4]) + 56u * P[3];
-        dst[1] = 18u * (P[2] + P[8]) + 34u * (P[3] + P[7]) + 48u * (P[4] + P[6]) + 56u * P[5];
+        const uint2 w01 = *reinterpret_cast<const uint2*>(rw), w23 = *reinterpret_cast<const uint2*>(rw + 2);
+        const uint32_t w0 = w01.x, w1 = w01.y, w2 = w23.x, w3 = w23.y, w4 = rw[4];
+        uint32_t W[12];
+        W[0] = __funnelshift_r(w0, w1, s8); W[4] = __funnelshift_r(w1, w2, s8);
+        W[8] = __funnelshift_r(w2, w3, s8);
+        const uint32_t a3 = __funnelshift_r(w3, w4, s8);
+#pragma unroll
+        for (int t = 1; t < 4; t++) {
+            W[t] = __funnelshift_r(W[0], W[4], 8 * t);
+            W[4 + t] = __funnelshift_r(W[4], W[8], 8 * t);
+            W[8 + t] = __funnelshift_r(W[8], a3, 8 * t);
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = __dp4a(W[j + 4], WT1, __dp4a(W[j], WT0, 0u));
+        // outputs are < 2^16: two per 32-bit word, one 128-bit store (rows are 80 bytes, groups 16 bytes apart)
+        *reinterpret_cast<uint4*>(hb + r * HBP + c0) = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
     }
     __syncwarp();
 
