@@ -264,6 +264,17 @@ int  orbx_bow_score_device(orbx_vocabulary* v, const int32_t* d_frame_a, const i
 int  orbx_search_by_bow_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf_frame, const int32_t* d_f_frame,
                                const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_kf_valid,
                                float nnratio, int check_orientation, int32_t* d_match, int32_t* d_nmatches, void* cuda_stream);
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (ORBmatcher.cc:589-736): both
+ * sides carry map-point flags (valid1 / valid2, NULL = all), the acceptance test is `bestDist1 < TH_LOW`, and the output
+ * is indexed by the FIRST keyframe: match12[pair][idx1] = feature of the second keyframe, -1 = none. */
+int  orbx_search_by_bow_kf_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf1_frame, const int32_t* d_kf2_frame,
+                                  const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_valid1,
+                                  const uint8_t* d_valid2, float nnratio, int check_orientation, int32_t* d_match12,
+                                  int32_t* d_nmatches, void* cuda_stream);
+int  orbx_search_by_bow_kf(orbx_vocabulary* v, const OrbxKeyPoint* kf1_keypoints, const uint8_t* kf1_descriptors, int n1,
+                           const uint8_t* valid1, const OrbxKeyPoint* kf2_keypoints, const uint8_t* kf2_descriptors, int n2,
+                           const uint8_t* valid2, int levelsup, float nnratio, int check_orientation, int32_t* match12,
+                           int32_t* nmatches);
 /* one pair from host buffers (transforms both descriptor sets first) */
 int  orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoints, const uint8_t* kf_descriptors, int n_kf,
                         const uint8_t* kf_valid, const OrbxKeyPoint* f_keypoints, const uint8_t* f_descriptors, int n_f,

@@ -55,6 +55,9 @@ def lib():
         L.oc_remap_linear_8u.argtypes = [u8p, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
         L.oc_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
         L.oc_fast_score.restype = C.c_int; L.oc_fast_score.argtypes = [u8p, C.c_int]
+        L.oc_search_by_bow_kf.restype = C.c_int
+        L.oc_search_by_bow_kf.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + \
+            [C.c_void_p] * 3 + [C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.oc_search_by_projection_frame.restype = C.c_int
         L.oc_search_by_projection_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
@@ -423,3 +426,18 @@ def search_by_projection_frame(cur_kps, cur_desc, cur_u_right, cur_occupied, Tcw
                                             last_desc.ctypes.data, fl.ctypes.data, len(last_kps), th, mode, int(check_orientation),
                                             match.ctypes.data)
     return n, match[:len(cur_kps)]
+
+
+def search_by_bow_kf(t1, t2, desc1, angle1, valid1, desc2, angle2, valid2, nnratio=0.75, check_orientation=True):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12); t1 / t2: dicts from Vocabulary.transform. -> (nmatches, match12)"""
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    angle1 = np.ascontiguousarray(angle1, np.float32); angle2 = np.ascontiguousarray(angle2, np.float32)
+    valid1 = np.ascontiguousarray(valid1, np.uint8); valid2 = np.ascontiguousarray(valid2, np.uint8)
+    a = [np.ascontiguousarray(t1[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    b = [np.ascontiguousarray(t2[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    match = np.zeros(max(len(desc1), 1), np.int32)
+    n = lib().oc_search_by_bow_kf(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[0]), b[0].ctypes.data, b[1].ctypes.data,
+                                  b[2].ctypes.data, len(b[0]), desc1.ctypes.data, angle1.ctypes.data, valid1.ctypes.data, len(desc1),
+                                  desc2.ctypes.data, angle2.ctypes.data, valid2.ctypes.data, len(desc2), nnratio,
+                                  int(check_orientation), match.ctypes.data)
+    return n, match[:len(desc1)]

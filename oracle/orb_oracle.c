@@ -1360,3 +1360,54 @@ int oc_search_by_projection_frame(const OcKeyPoint* cur_kps, const uint8_t* cur_
     free(cnt); free(cell); free(tab); free(fill); free(occ); free(hist_idx); free(hist_bin);
     return nmatches;
 }
+
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (ORBmatcher.cc:589-736).
+ * valid1 / valid2: the keyframe's feature has a map point that is not bad. match12[idx1] = feature of keyframe 2 whose
+ * map point vpMatches12[idx1] holds, -1 = none. Returns nmatches. */
+int oc_search_by_bow_kf(const int32_t* fv1_node, const int32_t* fv1_off, const int32_t* fv1_feat, int nfv1,
+                        const int32_t* fv2_node, const int32_t* fv2_off, const int32_t* fv2_feat, int nfv2,
+                        const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                        const uint8_t* desc2, const float* angle2, const uint8_t* valid2, int n2,
+                        float nnratio, int check_orientation, int32_t* match12)
+{
+    int nmatches = 0, nh = 0, count[HISTO_LENGTH] = {0};
+    int* hist_idx = (int*)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1)), * hist_bin = (int*)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1));
+    uint8_t* matched2 = (uint8_t*)calloc((size_t)(n2 > 0 ? n2 : 1), 1);
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    int a = 0, b = 0;
+    while (a < nfv1 && b < nfv2) {
+        if (fv1_node[a] == fv2_node[b]) {
+            for (int i1 = fv1_off[a]; i1 < fv1_off[a + 1]; i1++) {
+                const int idx1 = fv1_feat[i1];
+                if (!valid1[idx1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = fv2_off[b]; i2 < fv2_off[b + 1]; i2++) {
+                    const int idx2 = fv2_feat[i2];
+                    if (matched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = oc_descriptor_distance(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < 50 && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    match12[idx1] = bestIdx2;
+                    matched2[bestIdx2] = 1;
+                    if (check_orientation) {
+                        const int bin = rot_bin(angle1[idx1], angle2[bestIdx2]);
+                        hist_idx[nh] = idx1; hist_bin[nh] = bin; nh++; count[bin]++;
+                    }
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (fv1_node[a] < fv2_node[b]) a++;
+        else b++;
+    }
+    if (check_orientation) {
+        int i1, i2, i3;
+        three_maxima(count, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int t = 0; t < nh; t++)
+            if (hist_bin[t] != i1 && hist_bin[t] != i2 && hist_bin[t] != i3) { match12[hist_idx[t]] = -1; nmatches--; }
+    }
+    free(hist_idx); free(hist_bin); free(matched2);
+    return nmatches;
+}

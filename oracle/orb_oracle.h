@@ -110,6 +110,12 @@ int   oc_search_by_bow(const int32_t* kf_fv_node, const int32_t* kf_fv_off, cons
                        const uint8_t* f_desc, const float* f_angle, int f_n,
                        float nnratio, int check_orientation, int32_t* match_f);
 
+int   oc_search_by_bow_kf(const int32_t* fv1_node, const int32_t* fv1_off, const int32_t* fv1_feat, int nfv1,
+                          const int32_t* fv2_node, const int32_t* fv2_off, const int32_t* fv2_feat, int nfv2,
+                          const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                          const uint8_t* desc2, const float* angle2, const uint8_t* valid2, int n2,
+                          float nnratio, int check_orientation, int32_t* match12);   /* ORBmatcher.cc:589-736 */
+
 /* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646);
  * argument meaning as include/orbx.h OrbxProjectionPair. Direct restatement, cv::Mat arithmetic pinned to cv2 4.13's
  * gemm; NOT pinned by oracle/_ref (ORBmatcher.cc needs the whole SLAM library). Returns nmatches. */

@@ -90,6 +90,10 @@ def lib():
                                          C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         L.orbx_search_by_projection.argtypes = [C.c_void_p, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int]
         L.orbx_search_by_projection_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        L.orbx_search_by_bow_kf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbx_search_by_bow_kf_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_synchronize.argtypes = [C.c_void_p]
         L.orbx_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
@@ -492,6 +496,18 @@ class ORBVocabulary:
                                        None if val is None else val.ctypes.data, f_kps.ctypes.data, f_desc.ctypes.data, len(f_kps),
                                        levelsup, nnratio, int(check_orientation), match.ctypes.data, C.addressof(nm)))
         return nm.value, match[:len(f_kps)]
+
+    def search_by_bow_kf(self, kps1, desc1, valid1, kps2, desc2, valid2, levelsup=4, nnratio=0.75, check_orientation=True):
+        """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:589-736) -> (nmatches, match12)."""
+        kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+        desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+        v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+        match = np.zeros(max(len(kps1), 1), np.int32); nm = C.c_int32(0)
+        _ck(self._L.orbx_search_by_bow_kf(self._h, kps1.ctypes.data, desc1.ctypes.data, len(kps1), None if v1 is None else v1.ctypes.data,
+                                          kps2.ctypes.data, desc2.ctypes.data, len(kps2), None if v2 is None else v2.ctypes.data,
+                                          levelsup, nnratio, int(check_orientation), match.ctypes.data, C.addressof(nm)))
+        return nm.value, match[:len(kps1)]
 
     def search_by_bow_device(self, npairs, d_kf_frame, d_f_frame, d_kps, d_desc, d_kf_valid, nnratio, check_orientation, d_match,
                              d_nmatches, stream=0):

@@ -261,7 +261,11 @@ __global__ void __launch_bounds__(128) bow_match_kernel(OrbxBowOut O, OrbxBowMat
     const OrbxKp28* kkp = A.kps + (size_t)fk * cap;
     const OrbxKp28* fkp = A.kps + (size_t)ff * cap;
     const uint8_t* valid = A.kf_valid ? A.kf_valid + (size_t)pair * cap : nullptr;
+    const uint8_t* fvalid = A.f_valid ? A.f_valid + (size_t)pair * cap : nullptr;
+    // kf_mode (KeyFrame-KeyFrame form, ORBmatcher.cc:589-736): the output is indexed by the FIRST keyframe's feature
+    // (vpMatches12[idx1]) and the second side's "already matched" flags (vbMatched2) live in `taken`
     int* match = A.match + (size_t)pair * cap;
+    int* taken = A.kf_mode ? A.taken + (size_t)pair * cap : match;
     int* bin_of = A.bin_of + (size_t)pair * cap;
     for (int ik = k0; ik < k1; ik++) {
         const int ri = kfeat[ik];
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(128) bow_match_kernel(OrbxBowOut O, OrbxBowMat
         unsigned b1 = 0xffffffffu, b2 = 0xffffffffu;                         // per-lane best / second keys
         for (int j = j0 + lane; j < j1; j += 32) {
             const int rf = ffeat[j];
-            if (reinterpret_cast<volatile int*>(match)[rf] >= 0) continue;
+            if (reinterpret_cast<volatile int*>(taken)[rf] >= 0 || (fvalid && !fvalid[rf])) continue;
             const uint4* fd = reinterpret_cast<const uint4*>(fdesc + (size_t)rf * 32);
             const unsigned key = ((unsigned)bow_dist(q0, q1, fd[0], fd[1]) << 16) | (unsigned)(j - j0);
             const unsigned t = max(key, b1); b1 = min(b1, key); b2 = min(b2, t);
@@ -282,16 +286,18 @@ __global__ void __launch_bounds__(128) bow_match_kernel(OrbxBowOut O, OrbxBowMat
         const unsigned m2 = __reduce_min_sync(0xffffffffu, c2);
         const int bestDist1 = m1 == 0xffffffffu ? 256 : (int)(m1 >> 16);
         const int bestDist2 = m2 == 0xffffffffu ? 256 : (int)(m2 >> 16);
-        if (bestDist1 <= A.th_low && (float)bestDist1 < __fmul_rn(A.nnratio, (float)bestDist2)) {
+        // `<= TH_LOW` in the KeyFrame-Frame form (:267), `< TH_LOW` in the KeyFrame-KeyFrame form (:671)
+        if ((A.kf_mode ? bestDist1 < A.th_low : bestDist1 <= A.th_low) && (float)bestDist1 < __fmul_rn(A.nnratio, (float)bestDist2)) {
             const int bestIdxF = ffeat[j0 + (int)(m1 & 0xffffu)];
             if (lane == 0) {
-                match[bestIdxF] = ri;
+                taken[bestIdxF] = ri;
+                if (A.kf_mode) match[ri] = bestIdxF;
                 if (A.check_orientation) {
                     float rot = __fsub_rn(kkp[ri].angle, fkp[bestIdxF].angle);
                     if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                     int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
                     if (bin == 30) bin = 0;
-                    bin_of[bestIdxF] = bin;
+                    bin_of[A.kf_mode ? ri : bestIdxF] = bin;
                     atomicAdd(A.hist + pair * 32 + bin, 1);
                 }
                 atomicAdd(A.nmatches + pair, 1);
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(256) bow_rotation_kernel(OrbxBowMatchArgs A, c
         ind[0] = i1; ind[1] = i2; ind[2] = i3; removed = 0;
     }
     __syncthreads();
-    const int n = min(d_n[A.f_frame[pair]], cap);
+    const int n = min(d_n[A.kf_mode ? A.kf_frame[pair] : A.f_frame[pair]], cap);   // rotHist holds idx1 in kf_mode (:687)
     int* match = A.match + (size_t)pair * cap;
     const int* bin_of = A.bin_of + (size_t)pair * cap;
     int mine = 0;
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(256) bow_rotation_kernel(OrbxBowMatchArgs A, c
 __global__ void bow_match_init_kernel(OrbxBowMatchArgs A, int cap, int npairs)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (size_t)npairs * cap) A.match[i] = -1;
+    if (i < (size_t)npairs * cap) { A.match[i] = -1; if (A.kf_mode) A.taken[i] = -1; }
     if (i < (size_t)npairs * 32) A.hist[i] = 0;
     if (i < (size_t)npairs) A.nmatches[i] = 0;
 }

@@ -1092,7 +1092,7 @@ struct orbx_vocabulary {
     int* d_n_own = nullptr;
     // match workspace
     void* d_mws = nullptr; size_t mws_pairs = 0, mws_cap = 0;
-    int *d_bin_of = nullptr, *d_hist = nullptr;
+    int *d_bin_of = nullptr, *d_taken = nullptr, *d_hist = nullptr;
 };
 
 extern "C" int orbx_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
@@ -1285,10 +1285,10 @@ extern "C" int orbx_bow_score(orbx_vocabulary* v, const int32_t* frame_a, const 
     return rc;
 }
 
-extern "C" int orbx_search_by_bow_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf_frame, const int32_t* d_f_frame,
-                                         const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_kf_valid,
-                                         float nnratio, int check_orientation, int32_t* d_match, int32_t* d_nmatches,
-                                         void* cuda_stream)
+static int search_by_bow_device_impl(orbx_vocabulary* v, int npairs, const int32_t* d_kf_frame, const int32_t* d_f_frame,
+                                     const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_kf_valid,
+                                     const uint8_t* d_f_valid, int kf_mode, float nnratio, int check_orientation,
+                                     int32_t* d_match, int32_t* d_nmatches, void* cuda_stream)
 {
     if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
     if (npairs <= 0) return ORBX_OK;
@@ -1298,27 +1298,48 @@ extern "C" int orbx_search_by_bow_device(orbx_vocabulary* v, int npairs, const i
     if ((size_t)npairs > v->mws_pairs || (size_t)cap != v->mws_cap) {
         CK(cudaDeviceSynchronize());
         cudaFree(v->d_mws); v->d_mws = nullptr;
-        CK(cudaMalloc(&v->d_mws, (size_t)npairs * cap * 4 + (size_t)npairs * 32 * 4));
-        v->d_bin_of = (int*)v->d_mws; v->d_hist = v->d_bin_of + (size_t)npairs * cap;
+        CK(cudaMalloc(&v->d_mws, (size_t)npairs * cap * 8 + (size_t)npairs * 32 * 4));
+        v->d_bin_of = (int*)v->d_mws; v->d_taken = v->d_bin_of + (size_t)npairs * cap; v->d_hist = v->d_taken + (size_t)npairs * cap;
         v->mws_pairs = npairs; v->mws_cap = cap;
     }
     OrbxBowMatchArgs A;
     A.kf_frame = d_kf_frame; A.f_frame = d_f_frame; A.kps = (const OrbxKp28*)d_keypoints; A.desc = d_descriptors;
-    A.kf_valid = d_kf_valid; A.nnratio = nnratio; A.check_orientation = check_orientation; A.th_low = 50;   // ORBmatcher::TH_LOW
-    A.match = d_match; A.bin_of = v->d_bin_of; A.hist = v->d_hist; A.nmatches = d_nmatches;
+    A.kf_valid = d_kf_valid; A.f_valid = d_f_valid; A.kf_mode = kf_mode;
+    A.nnratio = nnratio; A.check_orientation = check_orientation; A.th_low = 50;   // ORBmatcher::TH_LOW
+    A.match = d_match; A.bin_of = v->d_bin_of; A.taken = v->d_taken; A.hist = v->d_hist; A.nmatches = d_nmatches;
     orbx_launch_bow_match(v->O, A, v->d_n, cap, npairs, (cudaStream_t)cuda_stream);
     CK(cudaGetLastError());
     return ORBX_OK;
 }
 
-// host convenience for one (keyframe, frame) pair: transforms both descriptor sets, then matches
-extern "C" int orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoints, const uint8_t* kf_descriptors, int n_kf,
-                                  const uint8_t* kf_valid, const OrbxKeyPoint* f_keypoints, const uint8_t* f_descriptors, int n_f,
-                                  int levelsup, float nnratio, int check_orientation, int32_t* match_f, int32_t* nmatches)
+extern "C" int orbx_search_by_bow_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf_frame, const int32_t* d_f_frame,
+                                         const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_kf_valid,
+                                         float nnratio, int check_orientation, int32_t* d_match, int32_t* d_nmatches,
+                                         void* cuda_stream)
 {
-    if (!v || n_kf < 0 || n_f < 0 || !nmatches || (n_f > 0 && !match_f)) return fail(ORBX_ERR_INVALID, "bad argument");
+    return search_by_bow_device_impl(v, npairs, d_kf_frame, d_f_frame, d_keypoints, d_descriptors, d_kf_valid, nullptr, 0, nnratio,
+                                     check_orientation, d_match, d_nmatches, cuda_stream);
+}
+
+extern "C" int orbx_search_by_bow_kf_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf1_frame, const int32_t* d_kf2_frame,
+                                            const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_valid1,
+                                            const uint8_t* d_valid2, float nnratio, int check_orientation, int32_t* d_match12,
+                                            int32_t* d_nmatches, void* cuda_stream)
+{
+    return search_by_bow_device_impl(v, npairs, d_kf1_frame, d_kf2_frame, d_keypoints, d_descriptors, d_valid1, d_valid2, 1, nnratio,
+                                     check_orientation, d_match12, d_nmatches, cuda_stream);
+}
+
+// host convenience for one (keyframe, frame) pair: transforms both descriptor sets, then matches
+static int search_by_bow_host(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoints, const uint8_t* kf_descriptors, int n_kf,
+                              const uint8_t* kf_valid, const OrbxKeyPoint* f_keypoints, const uint8_t* f_descriptors, int n_f,
+                              const uint8_t* f_valid, int kf_mode, int levelsup, float nnratio, int check_orientation,
+                              int32_t* match_f, int32_t* nmatches)
+{
+    const int n_out = kf_mode ? n_kf : n_f;
+    if (!v || n_kf < 0 || n_f < 0 || !nmatches || (n_out > 0 && !match_f)) return fail(ORBX_ERR_INVALID, "bad argument");
     *nmatches = 0;
-    for (int j = 0; j < n_f; j++) match_f[j] = -1;
+    for (int j = 0; j < n_out; j++) match_f[j] = -1;
     if (n_kf == 0 || n_f == 0) return ORBX_OK;
     if (!kf_keypoints || !kf_descriptors || !f_keypoints || !f_descriptors) return fail(ORBX_ERR_INVALID, "NULL argument");
     const int cap = std::max(n_kf, n_f);
@@ -1331,8 +1352,8 @@ extern "C" int orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_key
     uint8_t* pool = nullptr;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_kp = al((size_t)2 * cap * 28), b_d = al((size_t)2 * cap * 32), b_v = al((size_t)cap), b_m = al((size_t)cap * 4);
-    CK(cudaMalloc(&pool, b_kp + b_d + b_v + b_m + 256 + 256));
-    uint8_t *p_kp = pool, *p_d = p_kp + b_kp, *p_v = p_d + b_d, *p_m = p_v + b_v, *p_idx = p_m + b_m, *p_nm = p_idx + 256;
+    CK(cudaMalloc(&pool, b_kp + b_d + 2 * b_v + b_m + 256 + 256));
+    uint8_t *p_kp = pool, *p_d = p_kp + b_kp, *p_v = p_d + b_d, *p_v2 = p_v + b_v, *p_m = p_v2 + b_v, *p_idx = p_m + b_m, *p_nm = p_idx + 256;
     cudaError_t e;
     do {
         const int32_t idx[2] = {0, 1};
@@ -1340,11 +1361,13 @@ extern "C" int orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_key
         if ((e = cudaMemcpy(p_kp + (size_t)cap * 28, f_keypoints, (size_t)n_f * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((e = cudaMemcpy(p_d, desc.data(), desc.size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if (kf_valid && (e = cudaMemcpy(p_v, kf_valid, (size_t)n_kf, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (f_valid && (e = cudaMemcpy(p_v2, f_valid, (size_t)n_f, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((e = cudaMemcpy(p_idx, idx, 8, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        rc = orbx_search_by_bow_device(v, 1, (const int32_t*)p_idx, (const int32_t*)p_idx + 1, (const OrbxKeyPoint*)p_kp, p_d,
-                                       kf_valid ? p_v : nullptr, nnratio, check_orientation, (int32_t*)p_m, (int32_t*)p_nm, nullptr);
+        rc = search_by_bow_device_impl(v, 1, (const int32_t*)p_idx, (const int32_t*)p_idx + 1, (const OrbxKeyPoint*)p_kp, p_d,
+                                       kf_valid ? p_v : nullptr, f_valid ? p_v2 : nullptr, kf_mode, nnratio, check_orientation,
+                                       (int32_t*)p_m, (int32_t*)p_nm, nullptr);
         if (rc != ORBX_OK) { e = cudaSuccess; break; }
-        if ((e = cudaMemcpy(match_f, p_m, (size_t)n_f * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(match_f, p_m, (size_t)n_out * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
         e = cudaMemcpy(nmatches, p_nm, 4, cudaMemcpyDeviceToHost);
     } while (0);
     cudaFree(pool);
@@ -1450,4 +1473,21 @@ extern "C" int orbx_search_by_projection(const OrbxProjectionPair* pair, const f
     cudaFree(pool);
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     return rc;
+}
+
+extern "C" int orbx_search_by_bow(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoints, const uint8_t* kf_descriptors, int n_kf,
+                                  const uint8_t* kf_valid, const OrbxKeyPoint* f_keypoints, const uint8_t* f_descriptors, int n_f,
+                                  int levelsup, float nnratio, int check_orientation, int32_t* match_f, int32_t* nmatches)
+{
+    return search_by_bow_host(v, kf_keypoints, kf_descriptors, n_kf, kf_valid, f_keypoints, f_descriptors, n_f, nullptr, 0, levelsup,
+                              nnratio, check_orientation, match_f, nmatches);
+}
+
+extern "C" int orbx_search_by_bow_kf(orbx_vocabulary* v, const OrbxKeyPoint* kf1_keypoints, const uint8_t* kf1_descriptors, int n1,
+                                     const uint8_t* valid1, const OrbxKeyPoint* kf2_keypoints, const uint8_t* kf2_descriptors, int n2,
+                                     const uint8_t* valid2, int levelsup, float nnratio, int check_orientation, int32_t* match12,
+                                     int32_t* nmatches)
+{
+    return search_by_bow_host(v, kf1_keypoints, kf1_descriptors, n1, valid1, kf2_keypoints, kf2_descriptors, n2, valid2, 1, levelsup,
+                              nnratio, check_orientation, match12, nmatches);
 }

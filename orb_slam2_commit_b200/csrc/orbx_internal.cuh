@@ -142,8 +142,10 @@ struct OrbxBowMatchArgs {        // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, .
     const int *kf_frame, *f_frame;                       // [pairs] frame indices into the transformed batch
     const OrbxKp28* kps; const uint8_t* desc;            // the batch the transform ran on ([frames][cap])
     const uint8_t* kf_valid;                             // [pairs][cap] or NULL (all keyframe features have a good map point)
+    const uint8_t* f_valid;                              // [pairs][cap] or NULL: second side's map-point flags (KeyFrame-KeyFrame form)
     float nnratio; int check_orientation, th_low;
-    int *match, *bin_of;                                 // [pairs][cap]
+    int kf_mode;                                         // 0: SearchByBoW(KeyFrame*, Frame&) ; 1: SearchByBoW(KeyFrame*, KeyFrame*)
+    int *match, *bin_of, *taken;                         // [pairs][cap]; taken only in kf_mode
     int *hist, *nmatches;                                // [pairs][32], [pairs]
 };
 void orbx_launch_bow_transform(const OrbxVocabDev& V, const uint8_t* d_desc, const int* d_n, int frames, int cap, int levelsup,

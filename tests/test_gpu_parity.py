@@ -626,3 +626,27 @@ def test_pyramid_accessor_after_chunked_host_batch():
         assert np.array_equal(ex.pyramid_level(2, frame=i, with_apron=True), orc.level(2))
     with pytest.raises(OrbxError):
         ex.pyramid_level(0, frame=3)                           # slot reused by frames 16..19
+
+
+@pytest.mark.parametrize("check_ori,nnratio", [(True, 0.75), (False, 0.9)])
+def test_search_by_bow_keyframe_pair_matches_oracle(check_ori, nnratio):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (ORBmatcher.cc:589-736): map-point flags on both sides,
+    vbMatched2, strict `< TH_LOW`, output indexed by the first keyframe, rotation check on idx1."""
+    from orb_slam2_commit_b200 import ORBVocabulary
+    voc = synth.synth_vocabulary(10, 4, 21)
+    V = ORBVocabulary(10, 4, *voc); Vo = ob.Vocabulary(10, 4, *voc)
+    ex = ORBextractor(1500, 1.2, 8, 20, 7)
+    base = synth.synth_image(640, 480, 95)
+    rng = np.random.default_rng(6)
+    moved = np.clip(np.roll(base, (1, 4), axis=(0, 1)).astype(np.int16) + rng.integers(-5, 6, base.shape), 0, 255).astype(np.uint8)
+    (k1, k2), (d1, d2) = ex.extract_batch([base, moved])
+    d2 = d2.copy(); d2[1::3] = d2[0::3][:len(d2[1::3])]                     # duplicates: ties and ratio failures
+    v1 = (rng.random(len(k1)) < 0.8).astype(np.uint8); v2 = (rng.random(len(k2)) < 0.85).astype(np.uint8)
+    t1, t2 = Vo.transform(d1, 2), Vo.transform(d2, 2)
+    for a, b in ((v1, v2), (None, None)):
+        n, m = V.search_by_bow_kf(k1, d1, a, k2, d2, b, levelsup=2, nnratio=nnratio, check_orientation=check_ori)
+        ones1, ones2 = np.ones(len(k1), np.uint8), np.ones(len(k2), np.uint8)
+        no, mo = ob.search_by_bow_kf(t1, t2, d1, k1["angle"], ones1 if a is None else a, d2, k2["angle"], ones2 if b is None else b,
+                                     nnratio, check_ori)
+        assert n == no and np.array_equal(m, mo)
+        assert n > 50 and n == np.count_nonzero(m >= 0)
