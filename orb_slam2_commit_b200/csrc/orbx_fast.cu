@@ -6,8 +6,8 @@
 // The warp stages the cell tile (+3-px ring) in shared memory with aligned 32-bit loads, then
 //   1. quick test (four compass pixels) on every pixel; survivors are appended, in row-major order, to a per-warp
 //      list with ballot + popc (dense work for the expensive steps, no divergence waste);
-//   1b. exact FAST-9 corner test (16-bit ring masks) on the listed pixels, list re-compacted to true corners;
-//   2. exact corner score for the corners only, written to a zero-initialised u8 score map:
+//   2. exact corner score of the listed pixels (one polarity per pixel, chosen from the compass pixels), written to a
+//      zero-initialised u8 score map; the list is re-compacted to the true corners (score >= T):
 //        score(p) = max over the 16 arcs of 9 contiguous ring pixels of max(min d, -max d) - 1,  d_k = I(p) - I(ring_k)
 //        p is a corner at threshold T  <=>  score(p) >= T      (cv::cornerScore<16>; independent of T)
 //   3. cv::FAST's strict 3x3 non-max suppression over the list (still row-major), survivors written to the cell's
@@ -21,46 +21,47 @@
 
 struct FastSmemCfg { int tpw, th, sp, srows, list_cap, tile_off, score_off, list_off, per_warp; };
 
-// exact corner score of a pixel that passed the quick test at threshold T; 0 when it is not a corner at T.
-// dark / bright say which kind of arc is possible at all (>= 2 compass pixels on that side).
-// NOTE: keep A and B as two separate accumulators. Folding them into one running `best = max(best, min3(..))`
-// chain is mis-compiled by ptxas 12.9 for sm_100a (VIMNMX3 fusion) — caught by tests/test_gpu_parity.py.
-__device__ __forceinline__ int fast_score_T(const uint8_t* __restrict__ c, const int tp, const int T,
-                                            const bool dark, const bool bright)
+// max over the 16 arcs of 9 contiguous ring pixels of min(e[k..k+8]) with e_k = sg * (I(p) - I(ring_k)):
+// sg = +1 scores arcs of DARKER pixels (A = max_k min d), sg = -1 arcs of BRIGHTER pixels (-B = max_k min(-d)).
+// Sliding-window minimum by log-step doubling. NOTE: keep this as ONE plain max-chain over min3 terms; an earlier
+// version that folded the dark and the bright result into a single running accumulator was mis-compiled by ptxas 12.9
+// for sm_100a (VIMNMX3 fusion) — tests/test_gpu_parity.py::test_stages_match_oracle pins the scores.
+__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ c, const int tp, const int v, const int sg)
+{
+    const int nsg = -sg, sv = sg * v;
+    int e[16];
+    e[0] = c[3 * tp] * nsg + sv;       e[1] = c[3 * tp + 1] * nsg + sv;   e[2] = c[2 * tp + 2] * nsg + sv;   e[3] = c[tp + 3] * nsg + sv;
+    e[4] = c[3] * nsg + sv;            e[5] = c[-tp + 3] * nsg + sv;      e[6] = c[-2 * tp + 2] * nsg + sv;  e[7] = c[-3 * tp + 1] * nsg + sv;
+    e[8] = c[-3 * tp] * nsg + sv;      e[9] = c[-3 * tp - 1] * nsg + sv;  e[10] = c[-2 * tp - 2] * nsg + sv; e[11] = c[-tp - 3] * nsg + sv;
+    e[12] = c[-3] * nsg + sv;          e[13] = c[tp - 3] * nsg + sv;      e[14] = c[2 * tp - 2] * nsg + sv;  e[15] = c[3 * tp - 1] * nsg + sv;
+    int lo2[16], lo4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) lo2[k] = min(e[k], e[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) lo4[k] = min(lo2[k], lo2[(k + 2) & 15]);
+    int A = -1000;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), e[(k + 8) & 15]);
+        A = max(A, lo9);
+    }
+    return A;
+}
+
+// exact corner score of a pixel that passed the quick test at threshold T; 0 when it is not a corner at T:
+//   score(p) = max(A, -B) - 1,   p is a corner at T  <=>  score(p) >= T      (cv::cornerScore<16>; independent of T)
+// A score >= T needs an arc whose nine pixels are all beyond the threshold, hence two ADJACENT compass pixels (ring
+// 0, 4, 8, 12) beyond it on that side: only a polarity with such a pair can reach T, so one arc scan per pixel is
+// enough except for the rare pixel that has a dark and a bright compass pair.
+__device__ __forceinline__ int fast_score_T(const uint8_t* __restrict__ c, const int tp, const int T)
 {
     const int v = c[0];
-    int d[16];
-    d[0] = v - c[3 * tp];       d[1] = v - c[3 * tp + 1];   d[2] = v - c[2 * tp + 2];   d[3] = v - c[tp + 3];
-    d[4] = v - c[3];            d[5] = v - c[-tp + 3];      d[6] = v - c[-2 * tp + 2];  d[7] = v - c[-3 * tp + 1];
-    d[8] = v - c[-3 * tp];      d[9] = v - c[-3 * tp - 1];  d[10] = v - c[-2 * tp - 2]; d[11] = v - c[-tp - 3];
-    d[12] = v - c[-3];          d[13] = v - c[tp - 3];      d[14] = v - c[2 * tp - 2];  d[15] = v - c[3 * tp - 1];
-    // sliding-window min / max over 9 contiguous entries of the circular array (log-step doubling)
-    int A = -1000, B = 1000;
-    if (dark) {     // arcs of pixels darker than the centre: A = max_k min(d[k..k+8])
-        int lo2[16], lo4[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) lo2[k] = min(d[k], d[(k + 1) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; k++) lo4[k] = min(lo2[k], lo2[(k + 2) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-            A = max(A, lo9);
-        }
-    }
-    if (bright) {   // arcs of brighter pixels: B = min_k max(d[k..k+8])
-        int hi2[16], hi4[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) hi2[k] = max(d[k], d[(k + 1) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; k++) hi4[k] = max(hi2[k], hi2[(k + 2) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-            B = min(B, hi9);
-        }
-    }
-    const int s = max(A, -B) - 1;
+    const int d0 = v - c[3 * tp], d4 = v - c[3], d8 = v - c[-3 * tp], d12 = v - c[-3];
+    const int dp = ((T - d4) | (T - d12)) & ((T - d0) | (T - d8));     // sign set <=> a dark arc is possible at T
+    const int bp = ((d4 + T) | (d12 + T)) & ((d0 + T) | (d8 + T));     // sign set <=> a bright arc is possible at T
+    int best = fast_arc_score(c, tp, v, dp < 0 ? 1 : -1);
+    if ((dp & bp) < 0) best = max(best, fast_arc_score(c, tp, v, -1));
+    const int s = best - 1;
     return s >= T ? s : 0;
 }
 
@@ -197,48 +198,24 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
         }
         cnt = min(cnt, cfg.list_cap);
         __syncwarp();
-        // 2. exact FAST-9 corner test of the listed pixels (16-bit ring masks, 9 contiguous ones in the circular
-        //    mask), re-compacted in place: entry = dark<<15 | bright<<14 | py<<7 | px. In-place is safe: a chunk of
-        //    32 entries is read before it is written and the write position never passes the read position.
+        // 2. exact score of the listed pixels, written to the score map; the list is re-compacted in place to the true
+        //    corners (score >= T). In-place is safe: a chunk of 32 entries is read before it is written and the write
+        //    position never passes the read position.
         int ncorner = 0;
         for (int k0 = 0; k0 < cnt; k0 += 32) {
             const int k = k0 + lane;
-            int e = 0, fl = 0;
+            int e = 0, sc = 0;
             if (k < cnt) {
                 e = list[k];
-                const uint8_t* c = tile + (((e >> 7) & 127) + 3) * tp + (e & 127) + 3;
-                const int lo = (int)c[0] - T, hi = (int)c[0] + T;   // dark: ring < lo ; bright: ring > hi
-                // Both compares of one ring pixel in ONE multiply-add (FMA pipe): r * 0xFFFF0001 puts r in the low half
-                // and -r in the high half; adding C = (hi + 0x8000) << 16 | (0x8000 - lo) leaves r - lo + 0x8000 below and
-                // hi - r + 0x8000 above, so bit 15 is clear iff r < lo (dark) and bit 31 is clear iff r > hi (bright);
-                // neither half can carry into the other. The two bits are rotated into a packed pair of 16-bit masks.
-                const unsigned C = ((unsigned)(hi + 0x8000) << 16) + (unsigned)(0x8000 - lo);
-                unsigned M = 0;
-#define RING_BIT(off) { const unsigned X = (unsigned)c[off] * 0xFFFF0001u + C; M = (M >> 1) | (X & 0x80008000u); }
-                RING_BIT(3 * tp)       RING_BIT(3 * tp + 1)   RING_BIT(2 * tp + 2)   RING_BIT(tp + 3)
-                RING_BIT(3)            RING_BIT(-tp + 3)      RING_BIT(-2 * tp + 2)  RING_BIT(-3 * tp + 1)
-                RING_BIT(-3 * tp)      RING_BIT(-3 * tp - 1)  RING_BIT(-2 * tp - 2)  RING_BIT(-tp - 3)
-                RING_BIT(-3)           RING_BIT(tp - 3)       RING_BIT(2 * tp - 2)   RING_BIT(3 * tp - 1)
-#undef RING_BIT
-                M = ~M;                                          // bit k: ring k dark ; bit 16+k: ring k bright
-                unsigned md = M & 0xffffu, mb = M >> 16;
-                md |= md << 16; mb |= mb << 16;
-                md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;   // bit i set <=> ring i..i+8 all dark
-                mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
-                fl = ((md & 0xffffu) ? 2 : 0) | ((mb & 0xffffu) ? 1 : 0);
+                sc = fast_score_T(tile + ((e >> 7) + 3) * tp + (e & 127) + 3, tp, T);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, fl != 0);
+            const unsigned m = __ballot_sync(0xffffffffu, sc != 0);
             __syncwarp();
-            if (fl) list[ncorner + __popc(m & ((1u << lane) - 1))] = (unsigned short)((fl << 14) | (e & 0x3fff));
+            if (sc) {
+                list[ncorner + __popc(m & lt_mask)] = (unsigned short)e;
+                score[((e >> 7) + 1) * sp + (e & 127) + 1] = (uint8_t)sc;
+            }
             ncorner += __popc(m);
-        }
-        __syncwarp();
-        // 3. exact score of the corners
-        for (int k = lane; k < ncorner; k += 32) {
-            const int e = list[k];
-            const int px = e & 127, py = (e >> 7) & 127;
-            const int s = fast_score_T(tile + (py + 3) * tp + px + 3, tp, T, (e >> 15) & 1, (e >> 14) & 1);
-            if (s) score[(py + 1) * sp + px + 1] = (uint8_t)s;
         }
         __syncwarp();
         // 4. strict 3x3 NMS over the corners (row-major) + ordered write
