@@ -23,29 +23,37 @@ struct FastSmemCfg { int tpw, th, sp, srows, list_cap, tile_off, score_off, list
 
 // max over the 16 arcs of 9 contiguous ring pixels of min(e[k..k+8]) with e_k = sg * (I(p) - I(ring_k)):
 // sg = +1 scores arcs of DARKER pixels (A = max_k min d), sg = -1 arcs of BRIGHTER pixels (-B = max_k min(-d)).
-// Sliding-window minimum by log-step doubling. NOTE: keep this as ONE plain max-chain over min3 terms; an earlier
-// version that folded the dark and the bright result into a single running accumulator was mis-compiled by ptxas 12.9
-// for sm_100a (VIMNMX3 fusion) — tests/test_gpu_parity.py::test_stages_match_oracle pins the scores.
+// Two ring pixels ride in one register: P[k] = (e[k] + 1000) | (e[k+8] + 1000) << 16 (the bias keeps both halves
+// positive, so each P[k] is two exact multiply-adds and needs no packing step), and the sliding-window minimum
+// (log-step doubling: windows of 2, 4, then 4+4+4 overlapping = 9) runs on the packed 16-bit min/max instructions of
+// sm_100a (VIMNMX.S16x2 / VIMNMX3.S16x2). Index k+8 of a packed array is the same register with its halves swapped.
+// NOTE: an earlier scalar version that folded the dark and the bright result into a single running accumulator was
+// mis-compiled by ptxas 12.9 for sm_100a (VIMNMX3 fusion) — tests/test_gpu_parity.py::test_stages_match_oracle pins
+// the scores.
+__device__ __forceinline__ unsigned swap16(const unsigned x) { return __byte_perm(x, 0, 0x1032); }
 __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ c, const int tp, const int v, const int sg)
 {
-    const int nsg = -sg, sv = sg * v;
-    int e[16];
-    e[0] = c[3 * tp] * nsg + sv;       e[1] = c[3 * tp + 1] * nsg + sv;   e[2] = c[2 * tp + 2] * nsg + sv;   e[3] = c[tp + 3] * nsg + sv;
-    e[4] = c[3] * nsg + sv;            e[5] = c[-tp + 3] * nsg + sv;      e[6] = c[-2 * tp + 2] * nsg + sv;  e[7] = c[-3 * tp + 1] * nsg + sv;
-    e[8] = c[-3 * tp] * nsg + sv;      e[9] = c[-3 * tp - 1] * nsg + sv;  e[10] = c[-2 * tp - 2] * nsg + sv; e[11] = c[-tp - 3] * nsg + sv;
-    e[12] = c[-3] * nsg + sv;          e[13] = c[tp - 3] * nsg + sv;      e[14] = c[2 * tp - 2] * nsg + sv;  e[15] = c[3 * tp - 1] * nsg + sv;
-    int lo2[16], lo4[16];
+    const unsigned mlo = (unsigned)(-sg), mhi = (unsigned)(-sg) << 16;
+    const unsigned bias = (unsigned)(sg * v + 1000) * 0x10001u;
+    unsigned P[9], L2[10], L4[13];
+#define ORBX_PK(j, off) P[j] = (unsigned)c[off] * mlo + ((unsigned)c[-(off)] * mhi + bias);
+    ORBX_PK(0, 3 * tp) ORBX_PK(1, 3 * tp + 1) ORBX_PK(2, 2 * tp + 2) ORBX_PK(3, tp + 3)
+    ORBX_PK(4, 3) ORBX_PK(5, -tp + 3) ORBX_PK(6, -2 * tp + 2) ORBX_PK(7, -3 * tp + 1)
+#undef ORBX_PK
+    P[8] = swap16(P[0]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) lo2[k] = min(e[k], e[(k + 1) & 15]);
+    for (int k = 0; k < 8; k++) L2[k] = __vmins2(P[k], P[k + 1]);
+    L2[8] = swap16(L2[0]); L2[9] = swap16(L2[1]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) lo4[k] = min(lo2[k], lo2[(k + 2) & 15]);
-    int A = -1000;
+    for (int k = 0; k < 8; k++) L4[k] = __vmins2(L2[k], L2[k + 2]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), e[(k + 8) & 15]);
-        A = max(A, lo9);
-    }
-    return A;
+    for (int k = 0; k < 5; k++) L4[8 + k] = swap16(L4[k]);
+    unsigned lo9[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) lo9[k] = __vimin3_s16x2(L4[k], L4[k + 4], L4[k + 5]);   // e[k..k+3], e[k+4..k+7], e[k+5..k+8]
+    const unsigned m1 = __vimax3_s16x2(lo9[0], lo9[1], lo9[2]), m2 = __vimax3_s16x2(lo9[3], lo9[4], lo9[5]);
+    const unsigned m = __vmaxs2(__vimax3_s16x2(lo9[6], lo9[7], m1), m2);
+    return max((int)(m & 0xffffu), (int)(m >> 16)) - 1000;
 }
 
 // exact corner score of a pixel that passed the quick test at threshold T; 0 when it is not a corner at T:
