@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
                 px = e & 127; py = (e >> 7) & 127;
                 const uint8_t* q = score + (py + 1) * sp + px + 1;
                 s = q[0];
-                keep = s > 0 && s > q[-1] && s > q[1] && s > q[-sp - 1] && s > q[-sp] && s > q[-sp + 1] &&
-                       s > q[sp - 1] && s > q[sp] && s > q[sp + 1];
+                // branch-free: strictly greater than the largest of the eight neighbours (list entries have s >= T > 0)
+                const int nmax = max(max(max(max((int)q[-1], (int)q[1]), (int)q[-sp - 1]), max((int)q[-sp], (int)q[-sp + 1])),
+                                     max(max((int)q[sp - 1], (int)q[sp]), (int)q[sp + 1]));
+                keep = s > nmax;
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
