@@ -31,7 +31,9 @@ struct FastSmemCfg { int tpw, th, sp, srows, list_cap, tile_off, score_off, list
 // mis-compiled by ptxas 12.9 for sm_100a (VIMNMX3 fusion) — tests/test_gpu_parity.py::test_stages_match_oracle pins
 // the scores.
 __device__ __forceinline__ unsigned swap16(const unsigned x) { return __byte_perm(x, 0, 0x1032); }
-__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ c, const int tp, const int v, const int sg)
+// returns max_k min(e[k..k+8]); when `other` is set also the opposite polarity, max_k min(-e[k..k+8]) = -min_k max(e[k..k+8]),
+// from the same packed registers (sliding-window maximum), and the larger of the two
+__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ c, const int tp, const int v, const int sg, const bool other)
 {
     const unsigned mlo = (unsigned)(-sg), mhi = (unsigned)(-sg) << 16;
     const unsigned bias = (unsigned)(sg * v + 1000) * 0x10001u;
@@ -53,23 +55,37 @@ __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ c, con
     for (int k = 0; k < 8; k++) lo9[k] = __vimin3_s16x2(L4[k], L4[k + 4], L4[k + 5]);   // e[k..k+3], e[k+4..k+7], e[k+5..k+8]
     const unsigned m1 = __vimax3_s16x2(lo9[0], lo9[1], lo9[2]), m2 = __vimax3_s16x2(lo9[3], lo9[4], lo9[5]);
     const unsigned m = __vmaxs2(__vimax3_s16x2(lo9[6], lo9[7], m1), m2);
-    return max((int)(m & 0xffffu), (int)(m >> 16)) - 1000;
+    int best = max((int)(m & 0xffffu), (int)(m >> 16)) - 1000;
+    if (other) {
+        unsigned H2[10], H4[13], hi9[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) H2[k] = __vmaxs2(P[k], P[k + 1]);
+        H2[8] = swap16(H2[0]); H2[9] = swap16(H2[1]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) H4[k] = __vmaxs2(H2[k], H2[k + 2]);
+#pragma unroll
+        for (int k = 0; k < 5; k++) H4[8 + k] = swap16(H4[k]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) hi9[k] = __vimax3_s16x2(H4[k], H4[k + 4], H4[k + 5]);
+        const unsigned n1 = __vimin3_s16x2(hi9[0], hi9[1], hi9[2]), n2 = __vimin3_s16x2(hi9[3], hi9[4], hi9[5]);
+        const unsigned n = __vmins2(__vimin3_s16x2(hi9[6], hi9[7], n1), n2);
+        best = max(best, 1000 - min((int)(n & 0xffffu), (int)(n >> 16)));
+    }
+    return best;
 }
 
 // exact corner score of a pixel that passed the quick test at threshold T; 0 when it is not a corner at T:
 //   score(p) = max(A, -B) - 1,   p is a corner at T  <=>  score(p) >= T      (cv::cornerScore<16>; independent of T)
 // A score >= T needs an arc whose nine pixels are all beyond the threshold, hence two ADJACENT compass pixels (ring
-// 0, 4, 8, 12) beyond it on that side: only a polarity with such a pair can reach T, so one arc scan per pixel is
-// enough except for the rare pixel that has a dark and a bright compass pair.
+// 0, 4, 8, 12) beyond it on that side: only a polarity with such a pair can reach T, so the second polarity is scanned
+// only for pixels that have a dark and a bright compass pair (edge-like pixels).
 __device__ __forceinline__ int fast_score_T(const uint8_t* __restrict__ c, const int tp, const int T)
 {
     const int v = c[0];
     const int d0 = v - c[3 * tp], d4 = v - c[3], d8 = v - c[-3 * tp], d12 = v - c[-3];
     const int dp = ((T - d4) | (T - d12)) & ((T - d0) | (T - d8));     // sign set <=> a dark arc is possible at T
     const int bp = ((d4 + T) | (d12 + T)) & ((d0 + T) | (d8 + T));     // sign set <=> a bright arc is possible at T
-    int best = fast_arc_score(c, tp, v, dp < 0 ? 1 : -1);
-    if ((dp & bp) < 0) best = max(best, fast_arc_score(c, tp, v, -1));
-    const int s = best - 1;
+    const int s = fast_arc_score(c, tp, v, dp < 0 ? 1 : -1, (dp & bp) < 0) - 1;
     return s >= T ? s : 0;
 }
 
