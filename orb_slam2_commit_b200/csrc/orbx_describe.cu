@@ -6,8 +6,9 @@
 //   * IC_Angle: lane = column u in [-15,15], integer moments, warp-shuffle reduce, cv::fastAtan2 polynomial
 //     evaluated with un-contracted f32 mul/add (bit-equal to OpenCV's scalar path);
 //   * blur on demand: the reference blurs the whole level and then reads 512 points per keypoint; here the
-//     horizontal pass of OpenCV's fixed-point kernel [18,34,48,56,48,34,18]/256 is applied to the patch (exact in
-//     16 bits) and the vertical pass ((sum + 2^15) >> 16) only at the 16 sample points each lane needs. Border
+//     first pass of OpenCV's fixed-point kernel [18,34,48,56,48,34,18]/256 is applied to the patch (exact in 16 bits;
+//     taken vertically, see below) and the second pass ((sum + 2^15) >> 16) only at the 16 sample points each lane
+//     needs. Border
 //     handling is the level's own REFLECT_101, which is exactly what the 19-px apron in HBM holds;
 //   * rBRIEF: lane i builds descriptor byte i (8 tests); sample = center + cvRound(x*b+y*a, x*a-y*b) with
 //     un-contracted f32 and round-half-even; cos/sin are the glibc 2.39 cosf/sinf polynomials in f64
@@ -18,7 +19,8 @@
 #define DESC_WARPS 8
 #define PW 43            // patch width/height
 #define PWORDS 12        // 32-bit words per staged patch row (48 bytes)
-#define HBP 40           // pitch (u16) of the horizontally blurred patch, 37 valid columns (+3 scratch)
+#define VROWS 37         // rows of the vertically blurred patch (patch rows 3..39 centred)
+#define VPW 24           // its pitch in 32-bit words: 48 u16 per row, one per byte of the staged 48-byte patch row
 
 __device__ uint32_t g_pattern32[256];    // the 512 (x,y) int8 sample points, four bytes per word
 __constant__ int c_umax[16];
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
                                                                     int* __restrict__ nkp)
 {
     __shared__ __align__(16) uint32_t s_raw[DESC_WARPS][PW * PWORDS + 4];   // +4: the last row's aligned windows over-read by up to two words
-    __shared__ __align__(16) unsigned short s_hb[DESC_WARPS][PW * HBP];
+    __shared__ __align__(16) uint32_t s_vb[DESC_WARPS][VROWS * VPW];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // this lane's 16 sample points (32 int8 = two 128-bit words), fetched first so the latency hides behind staging;
     // no block-level barrier anywhere in this kernel
@@ -184,34 +186,35 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     }
     const float angle = dev_fast_atan2((float)m01, (float)m10);
 
-    // ---- horizontal pass of the fixed-point Gaussian on the patch: hb[r][c] <-> patch column c+3
-    unsigned short* hb = s_hb[wid];
-    // each lane produces 8 adjacent outputs of a row from five aligned words: the twelve 4-byte windows starting at
-    // bytes 0..11 come from funnel shifts, and every output is two 4-way byte dot products (weights 18,34,48,56 | 48,34,18,0)
-    const uint32_t WT0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), WT1 = 48u | (34u << 8) | (18u << 16);
-    for (int gi = lane; gi < PW * 5; gi += 32) {
-        const int r = gi / 5, c0 = (gi - r * 5) * 8;
-        const int bo = sh + c0;
-        // bo >> 2 == c0 / 4 is even (sh < 4), so the five words are two aligned 64-bit loads and one 32-bit load
-        const uint32_t* rw = raw32 + r * PWORDS + (bo >> 2);
-        const int s8 = (bo & 3) * 8;
-        const uint2 w01 = *reinterpret_cast<const uint2*>(rw), w23 = *reinterpret_cast<const uint2*>(rw + 2);
-        const uint32_t w0 = w01.x, w1 = w01.y, w2 = w23.x, w3 = w23.y, w4 = rw[4];
-        uint32_t W[12];
-        W[0] = __funnelshift_r(w0, w1, s8); W[4] = __funnelshift_r(w1, w2, s8);
-        W[8] = __funnelshift_r(w2, w3, s8);
-        const uint32_t a3 = __funnelshift_r(w3, w4, s8);
+    // ---- first pass of the fixed-point Gaussian on the patch, taken VERTICALLY: vb[ro][b] = sum_k w_k * row(ro+k)[b]
+    // for every byte position b of the staged 48-byte rows (exact in 16 bits). OpenCV runs the horizontal pass first,
+    // but neither pass rounds before the final (sum + 2^15) >> 16, so the order does not change the result; with the
+    // vertical pass first the seven taps a sample point needs afterwards are CONTIGUOUS in shared memory: four 32-bit
+    // loads instead of seven 16-bit ones (this kernel is bound by shared-memory wavefronts: sample reads hit random banks).
+    // Lane = (8-byte column) x (strip of 8 output rows): a 7-row window of byte pairs spread into 16-bit halves slides
+    // down the column, two outputs per 32-bit op (every sum stays below 2^16).
+    uint32_t* vb = s_vb[wid];
+    if (lane < 30) {
+        const int col = lane % 6, strip = lane / 6;
+        const int ro0 = min(strip * 8, VROWS - 8);               // strips 0,8,16,24,29 (the last two overlap)
+        const uint2* src = reinterpret_cast<const uint2*>(raw32 + ro0 * PWORDS) + col;
+        uint32_t E[7][4];
+        auto expand = [&](uint32_t (&e)[4], const uint2 w) {
+            e[0] = __byte_perm(w.x, 0, 0x4140); e[1] = __byte_perm(w.x, 0, 0x4342);
+            e[2] = __byte_perm(w.y, 0, 0x4140); e[3] = __byte_perm(w.y, 0, 0x4342);
+        };
 #pragma unroll
-        for (int t = 1; t < 4; t++) {
-            W[t] = __funnelshift_r(W[0], W[4], 8 * t);
-            W[4 + t] = __funnelshift_r(W[4], W[8], 8 * t);
-            W[8 + t] = __funnelshift_r(W[8], a3, 8 * t);
+        for (int i = 0; i < 6; i++) expand(E[i], src[i * (PWORDS / 2)]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            expand(E[(j + 6) % 7], src[(j + 6) * (PWORDS / 2)]);
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                o[q] = 18u * (E[j % 7][q] + E[(j + 6) % 7][q]) + 34u * (E[(j + 1) % 7][q] + E[(j + 5) % 7][q]) +
+                       48u * (E[(j + 2) % 7][q] + E[(j + 4) % 7][q]) + 56u * E[(j + 3) % 7][q];
+            *reinterpret_cast<uint4*>(vb + (ro0 + j) * VPW + col * 4) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        uint32_t o[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = __dp4a(W[j + 4], WT1, __dp4a(W[j], WT0, 0u));
-        // outputs are < 2^16: two per 32-bit word, one 128-bit store (rows are 80 bytes, groups 16 bytes apart)
-        *reinterpret_cast<uint4*>(hb + r * HBP + c0) = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
     }
     __syncwarp();
 
@@ -230,9 +233,16 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
             const float px = (float)(signed char)(w >> (16 * e)), py = (float)(signed char)(w >> (16 * e + 8));
             const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            const unsigned short* h = hb + (iy + 18) * HBP + (ix + 18);
-            const unsigned acc = 18u * (h[0] + h[6 * HBP]) + 34u * (h[HBP] + h[5 * HBP]) + 48u * (h[2 * HBP] + h[4 * HBP]) + 56u * h[3 * HBP];
-            smp[e] = (int)((acc + 32768u) >> 16);
+            // horizontal pass at the sample point: u16 entries idx .. idx+6 of row iy+18 (byte position sh + 18 + ix of
+            // the staged row is patch column 21 + ix - 3), fetched as four words; the weights follow the parity of idx
+            const int idx = (iy + 18) * (2 * VPW) + (sh + 18 + ix);
+            const uint32_t* h = vb + (idx >> 1);
+            const bool odd = idx & 1;
+            unsigned acc = __dp2a_lo(h[0], odd ? (18u << 8) : (18u | (34u << 8)), 32768u);
+            acc = __dp2a_lo(h[1], odd ? (34u | (48u << 8)) : (48u | (56u << 8)), acc);
+            acc = __dp2a_lo(h[2], odd ? (56u | (48u << 8)) : (48u | (34u << 8)), acc);
+            acc = __dp2a_lo(h[3], odd ? (34u | (18u << 8)) : 18u, acc);
+            smp[e] = (int)(acc >> 16);
         }
         val |= (smp[0] < smp[1]) << t;
     }
