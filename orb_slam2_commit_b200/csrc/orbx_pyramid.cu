@@ -123,8 +123,46 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_remap_kernel(OrbxF
     }
 }
 
-// level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows: the four
-// x-taps are fetched once and up to 16*PYR_RPT independent source-pixel loads are in flight per thread.
+// level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows.
+// Generic path (threads on the apron: reflected, non-monotonic x-taps): byte loads per tap. Kept out of line so that its
+// registers do not burden the fast path below.
+__device__ __noinline__ void pyr_resize_rows_generic(const OrbxResizeTap* __restrict__ xtab, const OrbxResizeTap* __restrict__ ytab,
+                                                     const int gw, const int gh, const int gpitch, const int spitch,
+                                                     const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dst,
+                                                     const int cb, const int rb0, const int rows)
+{
+    int sx[4], a0[4], a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const OrbxResizeTap tx = xtab[reflect101(cb + k - ORBX_XOFF, gw)];
+        sx[k] = tx.ofs; a0[k] = tx.c0; a1[k] = tx.c1;
+    }
+#pragma unroll 2
+    for (int rr = 0; rr < PYR_RPT; rr++) {
+        if (rb0 + rr >= rows) break;
+        const OrbxResizeTap ty = ytab[reflect101(rb0 + rr - ORBX_EDGE, gh)];
+        // rows sy and sy+1 of the source payload; when sy is the last row its coefficient c1 is 0 and row sy+1 is
+        // the (valid) apron row, so no clamp is needed — same for columns
+        const uint8_t* r0 = sbase + (size_t)(ty.ofs + ORBX_EDGE) * spitch;
+        const uint8_t* r1 = r0 + spitch;
+        const int b0 = ty.c0, b1 = ty.c1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int S0 = r0[sx[k]] * a0[k] + r0[sx[k] + 1] * a1[k];
+            const int S1 = r1[sx[k]] * a0[k] + r1[sx[k] + 1] * a1[k];
+            const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 0xff) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)rr * gpitch) = out;
+    }
+}
+
+// Fast path for threads whose four columns lie in the payload (no reflection): the eight x-taps of a source row sit
+// within 8 consecutive bytes, so each source row is three aligned 32-bit loads, two funnel shifts that bring byte
+// sx[0] to the front, two byte permutes that lay the (left, right) tap pairs of two outputs side by side, and one
+// 2-way dot product per output against the packed coefficient pair — instead of eight byte loads with 64-bit
+// address arithmetic.
 __global__ void __launch_bounds__(PYR_TX * PYR_TY, 8) pyr_resize_kernel(OrbxFrameLayout L, int level)
 {
     const OrbxLevelGeom g = L.lvl[level];
@@ -135,28 +173,50 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY, 8) pyr_resize_kernel(OrbxFram
     const int rows = g.h + 2 * ORBX_EDGE;
     if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb0 >= rows) return;
     const uint8_t* sbase = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + s.raw_off + ORBX_XOFF;
-    int sx[4], a0[4], a1[4];
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
+    // taps are stored as (ofs, c0, c1, pad) shorts: one 64-bit load each; c0 | c1 << 16 is bytes 2..5. On the apron the
+    // reflected columns give the same taps in descending order: the window starts at the smallest offset either way.
+    unsigned cf[4];
+    int x[4];
+    const uint2* tp = reinterpret_cast<const uint2*>(L.taps + g.xtab_off);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const OrbxResizeTap tx = L.taps[g.xtab_off + reflect101(cb + k - ORBX_XOFF, g.w)];
-        sx[k] = tx.ofs; a0[k] = tx.c0; a1[k] = tx.c1;
+        const uint2 tk = tp[reflect101(cb + k - ORBX_XOFF, g.w)];
+        x[k] = (short)(tk.x & 0xffff);
+        cf[k] = __byte_perm(tk.x, tk.y, 0x5432);
     }
-    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
+    const int x0 = min(min(x[0], x[1]), min(x[2], x[3]));
+    const int d0 = x[0] - x0, d1 = x[1] - x0, d2 = x[2] - x0, d3 = x[3] - x0;
+    const bool fast = max(max(d0, d1), max(d2, d3)) <= 6;
+    const int ab = x0 & ~3, s8 = (x0 & 3) * 8;
+    const unsigned sel01 = (unsigned)(d0 | ((d0 + 1) << 4) | (d1 << 8) | ((d1 + 1) << 12));
+    const unsigned sel23 = (unsigned)(d2 | ((d2 + 1) << 4) | (d3 << 8) | ((d3 + 1) << 12));
+    if (!fast) {
+        pyr_resize_rows_generic(L.taps + g.xtab_off, L.taps + g.ytab_off, g.w, g.h, g.pitch, s.pitch, sbase, dst, cb, rb0, rows);
+        return;
+    }
+    const uint8_t* sb = sbase + ab;
 #pragma unroll
     for (int rr = 0; rr < PYR_RPT; rr++) {
         if (rb0 + rr >= rows) break;
         const OrbxResizeTap ty = L.taps[g.ytab_off + reflect101(rb0 + rr - ORBX_EDGE, g.h)];
-        // rows sy and sy+1 of the source payload; when sy is the last row its coefficient c1 is 0 and row sy+1 is
-        // the (valid) apron row, so no clamp is needed — same for columns
-        const uint8_t* r0 = sbase + (size_t)(ty.ofs + ORBX_EDGE) * s.pitch;
-        const uint8_t* r1 = r0 + s.pitch;
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(sb + (size_t)(ty.ofs + ORBX_EDGE) * s.pitch);
+        const uint32_t* p1 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p0) + s.pitch);
         const int b0 = ty.c0, b1 = ty.c1;
+        const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
+        const uint32_t A0 = __funnelshift_r(u0, u1, s8), A1 = __funnelshift_r(u1, u2, s8);
+        const uint32_t B0 = __funnelshift_r(v0, v1, s8), B1 = __funnelshift_r(v1, v2, s8);
+        const uint32_t qa01 = __byte_perm(A0, A1, sel01), qa23 = __byte_perm(A0, A1, sel23);
+        const uint32_t qb01 = __byte_perm(B0, B1, sel01), qb23 = __byte_perm(B0, B1, sel23);
+        int S0[4], S1[4];
+        S0[0] = (int)__dp2a_lo(cf[0], qa01, 0u); S0[1] = (int)__dp2a_hi(cf[1], qa01, 0u);
+        S0[2] = (int)__dp2a_lo(cf[2], qa23, 0u); S0[3] = (int)__dp2a_hi(cf[3], qa23, 0u);
+        S1[0] = (int)__dp2a_lo(cf[0], qb01, 0u); S1[1] = (int)__dp2a_hi(cf[1], qb01, 0u);
+        S1[2] = (int)__dp2a_lo(cf[2], qb23, 0u); S1[3] = (int)__dp2a_hi(cf[3], qb23, 0u);
         uint32_t out = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int S0 = r0[sx[k]] * a0[k] + r0[sx[k] + 1] * a1[k];
-            const int S1 = r1[sx[k]] * a0[k] + r1[sx[k] + 1] * a1[k];
-            const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+            const int v = (((b0 * (S0[k] >> 4)) >> 16) + ((b1 * (S1[k] >> 4)) >> 16) + 2) >> 2;
             out |= (uint32_t)(v & 0xff) << (8 * k);
         }
         *reinterpret_cast<uint32_t*>(dst + (size_t)rr * g.pitch) = out;
