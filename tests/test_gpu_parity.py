@@ -71,7 +71,9 @@ def test_stages_match_oracle(name, seed):
 
 @pytest.mark.parametrize("w,h,nf,sc,nl,it,mt,seed", [
     (400, 150, 500, 1.2, 5, 20, 7, 21), (330, 300, 300, 1.5, 3, 30, 10, 22), (640, 480, 50, 1.2, 8, 20, 7, 23),
-    (640, 480, 3000, 1.1, 8, 12, 5, 24), (100, 90, 40, 1.2, 2, 20, 7, 25), (641, 479, 1000, 1.2, 8, 20, 7, 26)])
+    (640, 480, 3000, 1.1, 8, 12, 5, 24), (100, 90, 40, 1.2, 2, 20, 7, 25), (641, 479, 1000, 1.2, 8, 20, 7, 26),
+    # scale factors above ~2.3 leave the resize kernel's word-window path (taps of 4 outputs span more than 8 bytes)
+    (900, 700, 800, 2.5, 3, 20, 7, 27), (1000, 640, 500, 3.0, 3, 20, 7, 28), (640, 480, 500, 2.0, 3, 20, 7, 29)])
 def test_odd_settings_match_oracle(w, h, nf, sc, nl, it, mt, seed):
     img = synth.synth_image(w, h, seed)
     kps, desc = ORBextractor(nf, sc, nl, it, mt)(img)
