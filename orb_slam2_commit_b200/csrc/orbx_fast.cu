@@ -170,55 +170,34 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
         int cnt = 0;
         const unsigned lt_mask = (1u << lane) - 1;
         {
-            // lane = column, rows walked top to bottom; the pass bit of every row is shifted into a per-lane mask
+            // lane = ROW, pixels walked left to right; the pass bit of every pixel is shifted into the lane's row mask
             // (funnel shift pulls the sign bit of quick_test() in: one instruction, no ballot in the arithmetic loop).
+            // A lane's mask IS its row of the row-major list, so no transposition is needed: row offsets come from one
+            // warp scan, then every lane writes the entries of its own row. The tile pitch is an odd number of words, so
+            // the 32 rows a warp touches per load sit in 32 different banks.
             const unsigned KT = ((unsigned)(T + 0x8000) << 16) + (unsigned)(0x8000 + T);
-            // Up to two 32-column chunks (cells are < 60 px wide) and two 32-row halves (< 60 px tall).
-            const int nlo = min(eh, 32), nhi = eh - nlo;
-            unsigned q[2][2] = {{0u, 0u}, {0u, 0u}};            // [chunk][row half], bit (n-1-row) <-> row
-#pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch * 32 >= ew) break;                        // warp-uniform
-                const int px = ch * 32 + lane;
-                const uint8_t* col = tile + 3 * tp + 3 + min(px, ew - 1);   // clamped: loads stay inside the tile
-                unsigned acc = 0;
+            const int nlo = min(ew, 32), nhi = ew - nlo;         // up to two 32-column chunks (cells are < 60 px wide)
+            for (int rbase = 0; rbase < eh; rbase += 32) {       // and two 32-row halves (< 60 px tall)
+                const int py = rbase + lane;
+                const uint8_t* row = tile + (min(py, eh - 1) + 3) * tp + 3;   // clamped: loads stay inside the tile
+                unsigned acc0 = 0, acc1 = 0;
 #pragma unroll 4
-                for (int py = 0; py < nlo; py++) {
-                    acc = __funnelshift_l(quick_test(col + py * tp, tp, KT), acc, 1);
-                }
-                q[ch][0] = px < ew ? acc : 0u;
-                acc = 0;
+                for (int px = 0; px < nlo; px++) acc0 = __funnelshift_l(quick_test(row + px, tp, KT), acc0, 1);
 #pragma unroll 4
-                for (int py = 32; py < eh; py++) {
-                    acc = __funnelshift_l(quick_test(col + py * tp, tp, KT), acc, 1);
-                }
-                q[ch][1] = px < ew ? acc : 0u;
-            }
-            // Row-major list of the pixels that passed (entry = py<<7 | px). The per-lane COLUMN masks are transposed
-            // into per-lane ROW masks with independent ballots (no serial dependency), row offsets come from one warp
-            // scan, then every lane writes the entries of its own row.
-            auto emit_rows = [&](const unsigned qa, const unsigned qb, const int nrows, const int rowbase) {
-                unsigned rm0 = 0, rm1 = 0;
-                for (int r = 0; r < nrows; r++) {
-                    const unsigned m0 = __ballot_sync(0xffffffffu, (qa >> (nrows - 1 - r)) & 1u);
-                    if (lane == r) rm0 = m0;
-                    if (ew > 32) {                               // warp-uniform
-                        const unsigned m1 = __ballot_sync(0xffffffffu, (qb >> (nrows - 1 - r)) & 1u);
-                        if (lane == r) rm1 = m1;
-                    }
-                }
+                for (int px = 32; px < ew; px++) acc1 = __funnelshift_l(quick_test(row + px, tp, KT), acc1, 1);
+                // MSB-first accumulation: pixel px of an n-pixel chunk sits at bit n-1-px -> bit px after reversal
+                const unsigned rm0 = py < eh ? __brev(acc0) >> (32 - nlo) : 0u;
+                const unsigned rm1 = (py < eh && nhi > 0) ? __brev(acc1) >> (32 - nhi) : 0u;
                 const int c = __popc(rm0) + __popc(rm1);
                 int incl = c;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
                 int off = cnt + incl - c;
-                const int ebase = (rowbase + lane) << 7;
+                const int ebase = py << 7;
                 for (unsigned m = rm0; m; m &= m - 1) { if (off < cfg.list_cap) list[off] = (unsigned short)(ebase | (__ffs(m) - 1)); off++; }
                 for (unsigned m = rm1; m; m &= m - 1) { if (off < cfg.list_cap) list[off] = (unsigned short)(ebase | (32 + __ffs(m) - 1)); off++; }
                 cnt += __shfl_sync(0xffffffffu, incl, 31);
-            };
-            emit_rows(q[0][0], q[1][0], nlo, 0);
-            if (nhi > 0) emit_rows(q[0][1], q[1][1], nhi, 32);
+            }
         }
         cnt = min(cnt, cfg.list_cap);
         __syncwarp();
@@ -273,9 +252,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st)
 {
     FastSmemCfg cfg;
-    // common case (cells up to 46 px wide): compile-time pitches 56 / 48
-    const bool smallcfg = max_tile_w + 3 <= 56 && max_tile_w - 6 + 2 <= 48;
-    cfg.tpw = smallcfg ? 14 : (3 + max_tile_w + 3) / 4 + 1;
+    // common case (cells up to 46 px wide): compile-time pitches 60 (15 words: odd, see the quick-test loop) / 48
+    const bool smallcfg = max_tile_w + 3 <= 60 && max_tile_w - 6 + 2 <= 48;
+    cfg.tpw = smallcfg ? 15 : ((3 + max_tile_w + 3) / 4 + 1) | 1;
     cfg.th = max_tile_h;
     cfg.sp = smallcfg ? 48 : (max_tile_w - 6 + 2 + 3) & ~3;
     cfg.srows = max_tile_h - 6 + 2;
@@ -287,11 +266,11 @@ void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, 
     const size_t smem = (size_t)cfg.per_warp * FAST_WARPS;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(fast_cells_kernel<56, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fast_cells_kernel<60, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(fast_cells_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     dim3 grid((L.ncells + FAST_WARPS - 1) / FAST_WARPS, nframes);
-    if (smallcfg) fast_cells_kernel<56, 48><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
+    if (smallcfg) fast_cells_kernel<60, 48><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
     else fast_cells_kernel<0, 0><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
 }
