@@ -44,6 +44,19 @@ WORKLOADS = {
 }
 
 
+# stdout carries exactly ONE JSON line. Libraries (NCCL's "NCCL version ..." banner, a chatty driver) write to fd 1 from
+# C code, so main() points fd 1 at stderr for the whole run and the result line goes to the saved original stdout.
+_RESULT_FD = None
+
+
+def emit_json_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def level_geometry(c):
     """Pyramid payload sizes with the reference's own formula (ORBextractor.cc:1221-1225), float32 arithmetic."""
     sf = np.float32(1.0)
@@ -205,7 +218,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nthreads, "kind": kind,
                              "sample": f"{per_step} frames per step, {len(times)} steps"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def bench_hamming(torch, api_lib, dev, peaks, sm_mhz):
@@ -371,7 +384,7 @@ def run_frame(args, torch, dist, rank, world, local, dev):
             return f
         v, sample = cpu_thread_bench(make_worker, args.cpu_seconds, nthreads)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def run_stereo(args, torch, dist, rank, world, local, dev):
@@ -468,7 +481,7 @@ def run_stereo(args, torch, dist, rank, world, local, dev):
             return time.perf_counter() - t0
         t1 = run(nthreads); iters = int(max(nthreads, nthreads * max(1.0, args.cpu_seconds / max(t1, 1e-3)))); tt = run(iters)
         line["cpu_baseline"] = {"value": iters / tt, "unit": "pairs/s", "cores": nthreads, "kind": "port", "sample": f"{iters} pairs over {nthreads} threads, {tt:.1f} s"}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def main():
@@ -483,6 +496,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hamming", action="store_true")
     args = ap.parse_args()
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -727,7 +744,7 @@ def main():
                                     "keypoints_per_frame": kpf}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
