@@ -16,6 +16,7 @@
 // and histograms the NEXT split (warp-aggregated shared-memory atomics), so each pass reads the candidates once.
 // Finally every surviving node emits its best keypoint: max response, first in list order on ties (:796-812).
 #include "orbx_internal.cuh"
+#include <algorithm>
 
 #define QT_MAX ORBX_QT_THREADS   // the kernel runs with blockDim.x = 256 (small frames) or 1024 (large frames)
 
@@ -128,10 +129,22 @@ __global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_
                 if (lane == 31) s_w[32] = z;
             }
             __syncthreads();
-            int off = n + s_w[wid] + x - cnt;
-            if (cnt > 0) {
-                const uint32_t* s = slots + L.cells[g.cell0 + ci].slot_off;
-                for (int k = 0; k < cnt; k++) if (off + k < g.cand_cap) cand[off + k] = s[k];
+            // the copy itself is done warp-per-cell (coalesced reads of a cell's slot list, coalesced writes, several
+            // cells in flight per warp) instead of thread-per-cell: offsets / counts / slot addresses of this chunk of
+            // cells go through shared memory (the node arrays are not in use yet)
+            int* g_off = reinterpret_cast<int*>(smem_raw);
+            int* g_cnt = g_off + QT;
+            int* g_slot = g_cnt + QT;
+            g_off[tid] = n + s_w[wid] + x - cnt;
+            g_cnt[tid] = cnt;
+            g_slot[tid] = cnt > 0 ? L.cells[g.cell0 + ci].slot_off : 0;
+            __syncthreads();
+            const int nc = min(QT, ncl - base);
+#pragma unroll 4
+            for (int c = wid; c < nc; c += nwarps) {
+                const int k = g_cnt[c], o = g_off[c];
+                const uint32_t* sl = slots + g_slot[c];
+                for (int j = lane; j < k; j += 32) if (o + j < g.cand_cap) cand[o + j] = __ldg(sl + j);
             }
             n += s_w[32];
             __syncthreads();
@@ -436,6 +449,7 @@ static size_t qt_smem_bytes(int C, int hist_ints)
     b += (size_t)C + 8;
     b += (size_t)sortn * (sizeof(unsigned long long) + sizeof(int));
     b += 2 * (size_t)C * sizeof(int) + (size_t)hist_ints * sizeof(int);
+    b = std::max(b, (size_t)3 * QT_MAX * sizeof(int));     // the candidate gather borrows 3 ints per thread up front
     return (b + 15) & ~(size_t)15;
 }
 
