@@ -434,13 +434,18 @@ def run_stereo(args, torch, dist, rank, world, local, dev):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * P * args.steps / (ms_total * 1e-3)
-    # e2e: pinned host frames in, keypoints / descriptors / mvuRight / mvDepth out, copies inside the timed region
-    outs = [torch.empty_like(x, device="cpu").pin_memory() for x in (kL, deL, nL, kR, deR, nR, uR, dp)]
+    # e2e: the public batched host call orbx_stereo_extract_batch with pinned host frames in and pinned keypoints /
+    # descriptors / mvuRight / mvDepth out (H2D + D2H inside the timed region, chunks pipelined over several streams)
+    from orb_slam2_commit_b200 import stereo_extract_host
+    pin = lambda *shape, dt=torch.uint8: torch.zeros(shape, dtype=dt).pin_memory()
+    h_k = [pin(P, cap, 28) for _ in range(2)]; h_d = [pin(P, cap, 32) for _ in range(2)]
+    h_n = [pin(P, dt=torch.int32) for _ in range(2)]; h_f = [pin(P, cap, dt=torch.float32) for _ in range(2)]
+    hout = dict(kl=h_k[0].numpy().view(api.KP_DTYPE).reshape(P, cap), kr=h_k[1].numpy().view(api.KP_DTYPE).reshape(P, cap),
+                dl=h_d[0].numpy(), dr=h_d[1].numpy(), nl=h_n[0].numpy(), nr=h_n[1].numpy(), u_right=h_f[0].numpy(), depth=h_f[1].numpy())
+    outs = [h_k[0], h_d[0], h_n[0], h_k[1], h_d[1], h_n[1], h_f[0], h_f[1]]
+    torch.cuda.synchronize()
     def e2e_step():
-        dL.copy_(hL, non_blocking=True); dR.copy_(hR, non_blocking=True)
-        step()
-        for o, x in zip(outs, (kL, deL, nL, kR, deR, nR, uR, dp)): o.copy_(x, non_blocking=True)
-        torch.cuda.synchronize()
+        stereo_extract_host(exL, exR, hL.numpy(), hR.numpy(), c["bf"], c["fx"], hout)
     for _ in range(2): e2e_step()
     barrier()
     n_e2e = max(3, min(args.steps, 10)); t0 = time.perf_counter()
@@ -460,7 +465,7 @@ def run_stereo(args, torch, dist, rank, world, local, dev):
                        "pairs_per_step_per_gpu": P, "distinct_pairs": len(pairs)},
             "clocks": clocks, "gpu_launches": (2 * (c["nlevels"] + 3) + 2) * args.steps,
             "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * W * H, "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in outs)), "steps": n_e2e,
-                    "api": "orbx_extract_device x2 + orbx_stereo_match_device with pinned host buffers"},
+                    "api": "orbx_stereo_extract_batch (pinned host buffers)"},
             "stages": {"extract_left_right_ms": ms_extract, "stereo_match_ms": ms_match},
             "pipeline": {"keypoints_per_image": float(nl_np.mean()), "stereo_matches_per_pair": matched}}
     if world == 1 and not args.no_cpu_baseline:

@@ -207,6 +207,15 @@ int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right,
                       const OrbxKeyPoint* kp_left, const uint8_t* desc_left, int n_left,
                       const OrbxKeyPoint* kp_right, const uint8_t* desc_right, int n_right,
                       float mbf, float fx, float* u_right, float* depth);
+/* Batched host form of the stereo Frame constructor's hot part (Frame.cc:80-117): for n pairs, ExtractORB on the left and
+ * the right image and ComputeStereoMatches, pipelined in chunks over several streams (copies overlap kernels). All
+ * output arrays are [n][cap] with cap == orbx_max_keypoints() (identical for both extractors after orbx_reserve with
+ * the same geometry); entries i >= n_left[pair] of u_right / depth are unspecified. Pinned host memory recommended. */
+int orbx_stereo_extract_batch(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                              const uint8_t* const* images_right, int n, int width, int height, int stride,
+                              float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
+                              OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
+                              float* u_right, float* depth);
 /* Device-resident, batched form: `pairs` stereo pairs whose left / right frames were the frames 0..pairs-1 of the last
  * orbx_extract_device call on `left` / `right`. Keypoints, descriptors and counts are those calls' device outputs
  * ([pairs][cap] layout). d_u_right / d_depth: [pairs][cap] floats, entries i < nl[pair] are written. Asynchronous on

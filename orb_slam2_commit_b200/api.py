@@ -94,6 +94,9 @@ def lib():
                                             C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         L.orbx_search_by_bow_kf_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_stereo_extract_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                                C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbx_synchronize.argtypes = [C.c_void_p]
         L.orbx_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
@@ -385,6 +388,19 @@ def image_bounds(width, height, K4, dist, device: int = 0):
     _ck(lib().orbx_image_bounds(width, height, K4.ctypes.data_as(f32p), dist.ctypes.data_as(f32p), len(dist),
                                 b.ctypes.data_as(f32p), device))
     return b
+
+
+def stereo_extract_host(left: ORBextractor, right: ORBextractor, images_left: np.ndarray, images_right: np.ndarray, mbf: float,
+                        fx: float, out: dict):
+    """orbx_stereo_extract_batch on caller-owned (ideally pinned) buffers: images (n,h,w) u8; out = dict with kl / kr
+    (n,cap) KP_DTYPE, dl / dr (n,cap,32) u8, nl / nr (n,) i32, u_right / depth (n,cap) f32; cap = left.reserve(...)."""
+    n, h, w = images_left.shape
+    cap = out["kl"].shape[1]
+    pl = (C.c_void_p * n)(*[images_left.ctypes.data + i * h * w for i in range(n)])
+    pr = (C.c_void_p * n)(*[images_right.ctypes.data + i * h * w for i in range(n)])
+    _ck(lib().orbx_stereo_extract_batch(left._h, right._h, pl, pr, n, w, h, w, mbf, fx, out["kl"].ctypes.data, out["dl"].ctypes.data,
+                                        out["nl"].ctypes.data, out["kr"].ctypes.data, out["dr"].ctypes.data, out["nr"].ctypes.data,
+                                        cap, out["u_right"].ctypes.data, out["depth"].ctypes.data))
 
 
 def window_top2(keypoints, descriptors, occupied, u_right, minX, minY, invW, invH, queries, query_descriptors, device: int = 0):

@@ -46,12 +46,13 @@ struct orbx_extractor {
     uint8_t* d_desc = nullptr;
     int* d_nkp = nullptr;
     cudaStream_t stream = nullptr;
-    static const int MAX_SLOTS = 8;
+    static constexpr int MAX_SLOTS = 8;
     cudaStream_t slot_stream[MAX_SLOTS] = {};   // host-path double buffering (copy/compute overlap)
     uint2* d_remap = nullptr;                     // fixed-point rectification map (orbx_set_rectify_maps)
     int map_w = 0, map_h = 0, map_src_w = 0, map_src_h = 0;
     int pyr_base = 0;                             // first working-set frame of the last pipeline run
     void* stereo_scratch = nullptr; size_t stereo_scratch_bytes = 0;   // SAD per left keypoint (stereo matcher)
+    float* stereo_out = nullptr; size_t stereo_out_floats = 0;         // [2][B][kc] mvuRight / mvDepth staging (batched host path)
     int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
     int map_chunk = 0, map_slots = 1;             // host batch path: frame f sits at ((f/chunk) % slots)*chunk + f%chunk
     // working-set index of frame `frame` of the last call, or -1 when a later chunk has reused its slot
@@ -65,7 +66,7 @@ struct orbx_extractor {
     }
     bool constants_ready = false;
     bool timing = false;
-    static const int RING = 64;
+    static constexpr int RING = 64;
     cudaEvent_t ev[RING][5] = {};
     long long runs = 0;                          // pipeline runs recorded since timing was enabled
 };
@@ -131,6 +132,7 @@ static void release_device(orbx_extractor* h)
     if (h->device >= 0 && (h->d_pool || h->stream)) cudaSetDevice(h->device);
     cudaFree(h->d_pool); h->d_pool = nullptr;
     cudaFree(h->stereo_scratch); h->stereo_scratch = nullptr; h->stereo_scratch_bytes = 0;
+    cudaFree(h->stereo_out); h->stereo_out = nullptr; h->stereo_out_floats = 0;
     cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps);
     h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr;
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
@@ -812,6 +814,111 @@ extern "C" int orbx_stereo_match_device(orbx_extractor* left, orbx_extractor* ri
     a.u_right = d_u_right; a.depth = d_depth; a.sad = (int*)left->stereo_scratch;
     orbx_launch_stereo_batch(a, st);
     CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// Batched host form of Frame's stereo constructor hot part (Frame.cc:80-117): left + right ExtractORB and
+// ComputeStereoMatches for n pairs, chunks pipelined over the slot streams exactly like orbx_extract_batch (H2D of later
+// chunks and D2H of earlier ones overlap the kernels). Both extractors run on the left extractor's slot stream so that
+// the matcher can follow them without an event.
+extern "C" int orbx_stereo_extract_batch(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                                         const uint8_t* const* images_right, int n, int width, int height, int stride,
+                                         float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
+                                         OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
+                                         float* u_right, float* depth)
+{
+    if (!left || !right || left == right) return fail(ORBX_ERR_INVALID, "two extractor instances required (Tracking.cc:120-123)");
+    if (n <= 0 || !images_left || !images_right || width <= 0 || height <= 0) return ORBX_OK;
+    if (!kp_left || !desc_left || !n_left || !kp_right || !desc_right || !n_right || !u_right || !depth || stride < width)
+        return fail(ORBX_ERR_INVALID, "bad output buffers");
+    if (left->device != right->device || left->nlevels != right->nlevels || left->scale_factor != right->scale_factor)
+        return fail(ORBX_ERR_INVALID, "left and right extractors must share device and pyramid settings");
+    for (orbx_extractor* h : {left, right})
+        if (width != h->W || height != h->H || h->max_batch < 1) {
+            int rc = orbx_reserve(h, width, height, std::max(1, std::min(n, std::max(h->max_batch, 64))));
+            if (rc != ORBX_OK) return rc;
+        }
+    if (left->max_batch != right->max_batch) {
+        const int B2 = std::max(left->max_batch, right->max_batch);
+        for (orbx_extractor* h : {left, right}) { int rc = orbx_reserve(h, width, height, B2); if (rc != ORBX_OK) return rc; }
+    }
+    const int B = left->max_batch, kc = left->L.kp_cap_total;
+    if (cap != kc || right->L.kp_cap_total != kc) return fail(ORBX_ERR_INVALID, "cap must equal orbx_max_keypoints() of both extractors");
+    if (kc > 18000) return fail(ORBX_ERR_UNSUPPORTED, "more than 18000 keypoints per image");
+    CK(cudaSetDevice(left->device));
+    const size_t fbytes = (size_t)width * height;
+    for (orbx_extractor* h : {left, right})
+        if ((size_t)B * fbytes > h->d_in_bytes) {
+            CK(cudaDeviceSynchronize());
+            cudaFree(h->d_in); h->d_in = nullptr; h->d_in_bytes = 0;
+            CK(cudaMalloc(&h->d_in, (size_t)B * fbytes));
+            h->d_in_bytes = (size_t)B * fbytes;
+        }
+    if (left->stereo_out_floats < (size_t)2 * B * kc || left->stereo_scratch_bytes < (size_t)B * kc * sizeof(int)) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(left->stereo_out); left->stereo_out = nullptr; left->stereo_out_floats = 0;
+        cudaFree(left->stereo_scratch); left->stereo_scratch = nullptr; left->stereo_scratch_bytes = 0;
+        CK(cudaMalloc(&left->stereo_out, (size_t)2 * B * kc * sizeof(float)));
+        left->stereo_out_floats = (size_t)2 * B * kc;
+        CK(cudaMalloc(&left->stereo_scratch, (size_t)B * kc * sizeof(int)));
+        left->stereo_scratch_bytes = (size_t)B * kc * sizeof(int);
+    }
+    int chunk = B >= 8 ? std::min(32, std::max(4, B / 8)) : B;            // a chunk carries two frames per pair
+    int nslots = B >= 8 ? std::max(1, std::min(orbx_extractor::MAX_SLOTS, B / chunk)) : 1;
+    for (int j = 0; j < nslots; j++)
+        if (!left->slot_stream[j]) CK(cudaStreamCreateWithFlags(&left->slot_stream[j], cudaStreamNonBlocking));
+    CK(cudaStreamSynchronize(left->stream));
+    CK(cudaStreamSynchronize(right->stream));
+    const float mb = mbf / fx;
+    int k = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, k++) {
+        const int m = std::min(chunk, n - f0);
+        const int slot = k % nslots, base = slot * chunk;
+        cudaStream_t st = left->slot_stream[slot];
+        struct Side { orbx_extractor* h; const uint8_t* const* imgs; OrbxKeyPoint* kp; uint8_t* desc; int32_t* nk; };
+        const Side sides[2] = {{left, images_left, kp_left, desc_left, n_left}, {right, images_right, kp_right, desc_right, n_right}};
+        for (const Side& sd : sides) {
+            uint8_t* d_in = sd.h->d_in + (size_t)base * fbytes;
+            bool contiguous = stride == width;
+            for (int i = 0; i < m && contiguous; i++) {
+                if (!sd.imgs[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
+                contiguous = sd.imgs[f0 + i] == sd.imgs[f0] + (size_t)i * fbytes;
+            }
+            if (contiguous) CK(cudaMemcpyAsync(d_in, sd.imgs[f0], (size_t)m * fbytes, cudaMemcpyHostToDevice, st));
+            else
+                for (int i = 0; i < m; i++) {
+                    if (!sd.imgs[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
+                    CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, width, sd.imgs[f0 + i], stride, width, height, cudaMemcpyHostToDevice, st));
+                }
+            int rc = run_pipeline(sd.h, d_in, m, width, fbytes, sd.h->d_kps + (size_t)base * kc, sd.h->d_desc + (size_t)base * kc * 32, kc,
+                                  sd.h->d_nkp + base, st, base);
+            if (rc != ORBX_OK) return rc;
+        }
+        OrbxStereoBatch a;
+        a.kl = left->d_kps + (size_t)base * kc; a.dl = left->d_desc + (size_t)base * kc * 32; a.nl = left->d_nkp + base;
+        a.kr = right->d_kps + (size_t)base * kc; a.dr = right->d_desc + (size_t)base * kc * 32; a.nr = right->d_nkp + base;
+        a.cap = kc; a.pairs = m; a.rows = left->lvl[0].h;
+        a.raw_left = left->L.raw + (size_t)base * left->L.frame_raw_bytes;
+        a.raw_right = right->L.raw + (size_t)base * right->L.frame_raw_bytes;
+        a.frame_raw_bytes = left->L.frame_raw_bytes;
+        a.lvl = left->d_lvl;
+        a.minD = 0.f; a.maxD = mbf / mb; a.mbf = mbf;
+        float* d_ur = left->stereo_out + (size_t)base * kc;
+        float* d_dp = left->stereo_out + (size_t)B * kc + (size_t)base * kc;
+        a.u_right = d_ur; a.depth = d_dp; a.sad = (int*)left->stereo_scratch + (size_t)base * kc;
+        orbx_launch_stereo_batch(a, st);
+        CK(cudaGetLastError());
+        for (const Side& sd : sides) {
+            CK(cudaMemcpyAsync(sd.nk + f0, sd.h->d_nkp + base, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(sd.kp + (size_t)f0 * kc, sd.h->d_kps + (size_t)base * kc, (size_t)m * kc * sizeof(OrbxKp28), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(sd.desc + (size_t)f0 * kc * 32, sd.h->d_desc + (size_t)base * kc * 32, (size_t)m * kc * 32, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaMemcpyAsync(u_right + (size_t)f0 * kc, d_ur, (size_t)m * kc * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(depth + (size_t)f0 * kc, d_dp, (size_t)m * kc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(left->slot_stream[j]));
+    for (orbx_extractor* h : {left, right}) { h->last_frames = n; h->pyr_base = 0; h->map_chunk = chunk; h->map_slots = nslots; }
+    for (int i = 0; i < n; i++) if (n_left[i] > kc || n_right[i] > kc) return fail(ORBX_ERR_CAPACITY, "keypoint buffer too small");
     return ORBX_OK;
 }
 

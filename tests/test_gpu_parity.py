@@ -652,3 +652,32 @@ def test_search_by_bow_keyframe_pair_matches_oracle(check_ori, nnratio):
                                      nnratio, check_ori)
         assert n == no and np.array_equal(m, mo)
         assert n > 50 and n == np.count_nonzero(m >= 0)
+
+
+def test_stereo_extract_batch_host_matches_oracle():
+    """orbx_stereo_extract_batch: left + right extraction and ComputeStereoMatches for a batch of pairs from host buffers,
+    pipelined in chunks over several streams; every pair must equal the oracle (keypoints, descriptors, mvuRight, mvDepth)."""
+    from orb_slam2_commit_b200 import KP_DTYPE, stereo_extract_host
+    W, H, n = 480, 200, 11                                   # working set 11 -> chunks of 4 pairs in 2 slots
+    args = (600, 1.2, 5, 20, 7)
+    pairs = [synth.synth_stereo_pair(W, H, 300 + i, max_disp=40) for i in range(n)]
+    L = np.stack([p[0] for p in pairs]); R = np.stack([p[1] for p in pairs])
+    exL, exR = ORBextractor(*args), ORBextractor(*args)
+    cap = exL.reserve(W, H, n); assert exR.reserve(W, H, n) == cap
+    out = dict(kl=np.zeros((n, cap), KP_DTYPE), kr=np.zeros((n, cap), KP_DTYPE), dl=np.zeros((n, cap, 32), np.uint8),
+               dr=np.zeros((n, cap, 32), np.uint8), nl=np.zeros(n, np.int32), nr=np.zeros(n, np.int32),
+               u_right=np.zeros((n, cap), np.float32), depth=np.zeros((n, cap), np.float32))
+    bf, fx = 386.1448 * 0.4, 718.856 * 0.4
+    stereo_extract_host(exL, exR, L, R, bf, fx, out)
+    oL, oR = ob.Extractor(*args), ob.Extractor(*args)
+    matched = 0
+    for i in range(n):
+        kl_o, dl_o = oL.extract(L[i]); kr_o, dr_o = oR.extract(R[i])
+        nl, nr = int(out["nl"][i]), int(out["nr"][i])
+        assert out["kl"][i, :nl].tobytes() == kl_o.tobytes() and out["kr"][i, :nr].tobytes() == kr_o.tobytes(), f"pair {i}"
+        assert np.array_equal(out["dl"][i, :nl], dl_o) and np.array_equal(out["dr"][i, :nr], dr_o)
+        ur_o, dp_o = ob.stereo_match(oL, oR, kl_o, dl_o, kr_o, dr_o, bf, fx)
+        assert np.array_equal(out["u_right"][i, :nl].view(np.uint32), ur_o.view(np.uint32)), f"pair {i}: mvuRight"
+        assert np.array_equal(out["depth"][i, :nl].view(np.uint32), dp_o.view(np.uint32)), f"pair {i}: mvDepth"
+        matched += int(np.count_nonzero(ur_o >= 0))
+    assert matched > 20 * n
