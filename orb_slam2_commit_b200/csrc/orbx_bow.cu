@@ -359,11 +359,8 @@ void orbx_launch_bow_transform(const OrbxVocabDev& V, const uint8_t* d_desc, con
     bow_descend_kernel<<<g1, 256, 0, st>>>(V, d_desc, d_n, cap, levelsup, O.leaf, O.nid);
     int P = 32; while (P < cap) P <<= 1;
     const size_t smem = (size_t)P * sizeof(unsigned long long);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(bow_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static OrbxSmemMark mark[1] = {};
+    orbx_need_smem(bow_assemble_kernel, mark[0], smem);
     bow_assemble_kernel<<<frames, 512, smem, st>>>(V, O, d_n, cap, P);
 }
 

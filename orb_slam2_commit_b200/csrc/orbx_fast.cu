@@ -264,12 +264,9 @@ void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, 
     cfg.list_off = (cfg.score_off + cfg.sp * cfg.srows + 15) & ~15;
     cfg.per_warp = (cfg.list_off + 2 * cfg.list_cap + 15) & ~15;
     const size_t smem = (size_t)cfg.per_warp * FAST_WARPS;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(fast_cells_kernel<60, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(fast_cells_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static OrbxSmemMark mark[2] = {};
+    orbx_need_smem(fast_cells_kernel<60, 48>, mark[0], smem);
+    orbx_need_smem(fast_cells_kernel<0, 0>, mark[1], smem);
     dim3 grid((L.ncells + FAST_WARPS - 1) / FAST_WARPS, nframes);
     if (smallcfg) fast_cells_kernel<60, 48><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
     else fast_cells_kernel<0, 0><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);

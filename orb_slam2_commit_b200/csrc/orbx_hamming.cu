@@ -458,11 +458,8 @@ void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st)
 {
     if (a.pairs <= 0 || a.cap <= 0) return;
     const size_t smem = (size_t)a.cap * sizeof(StereoR);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(stereo_match_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static OrbxSmemMark mark[1] = {};
+    orbx_need_smem(stereo_match_batch_kernel, mark[0], smem);
     dim3 grid((a.cap + 7) / 8, a.pairs);
     stereo_match_batch_kernel<<<grid, 256, smem, st>>>(a);
     stereo_median_cut_kernel<<<a.pairs, 256, 0, st>>>(a);
@@ -550,10 +547,7 @@ void orbx_launch_window_top2(const OrbxWindowArgs& a, cudaStream_t st)
 {
     if (a.nq <= 0) return;
     const size_t smem = (size_t)(a.n > 0 ? a.n : 1) * sizeof(WinKp);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(window_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static OrbxSmemMark mark[1] = {};
+    orbx_need_smem(window_top2_kernel, mark[0], smem);
     window_top2_kernel<<<(a.nq + 7) / 8, 256, smem, st>>>(a);
 }

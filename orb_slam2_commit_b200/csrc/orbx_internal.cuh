@@ -75,6 +75,22 @@ struct OrbxFrameLayout {      // everything the kernels need, passed by value
 
 struct OrbxKp28 { float x, y, size, angle, response; int octave, class_id; };
 
+// Opt-in for more than 48 KB of dynamic shared memory. The attribute belongs to the (function, device) pair and the
+// library may serve several devices and host threads from one process, so the high-water mark is kept per device.
+struct OrbxSmemMark { size_t bytes[64]; };
+template <typename F>
+static inline void orbx_need_smem(F kernel, OrbxSmemMark& mark, size_t bytes)
+{
+    if (bytes <= 48 * 1024) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (bytes > mark.bytes[dev]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        mark.bytes[dev] = bytes;
+    }
+}
+
 // kernel launchers (implemented in the .cu files; all asynchronous on `st`)
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
                          int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels = 1, int rgb = 0,

@@ -183,10 +183,7 @@ void orbx_launch_search_projection(const OrbxProjPairDev* d_pairs, int npairs, i
 {
     if (npairs <= 0) return;
     const size_t smem = (size_t)std::max(max_n_cur, 1) * (sizeof(ProjKp) + sizeof(int));
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(search_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static OrbxSmemMark mark[1] = {};
+    orbx_need_smem(search_projection_kernel, mark[0], smem);
     search_projection_kernel<<<npairs, 512, smem, st>>>(d_pairs, cam, d_scale_factors, th, check_orientation, 100 /* TH_HIGH */);
 }

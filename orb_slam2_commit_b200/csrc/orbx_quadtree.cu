@@ -456,12 +456,9 @@ static size_t qt_smem_bytes(int C, int hist_ints)
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st)
 {
     const size_t smem = qt_smem_bytes(L.qt_cap, L.qt_hist_ints);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(quadtree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(quadtree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static OrbxSmemMark mark[2] = {};
+    orbx_need_smem(quadtree_kernel<true>, mark[0], smem);
+    orbx_need_smem(quadtree_kernel<false>, mark[1], smem);
     dim3 grid(L.nlevels, nframes);
     if (threads == 256) quadtree_kernel<true><<<grid, 256, smem, st>>>(L);
     else quadtree_kernel<false><<<grid, QT_MAX, smem, st>>>(L);
