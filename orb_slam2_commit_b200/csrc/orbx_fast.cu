@@ -193,9 +193,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
                 int off = cnt + incl - c;
-                const int ebase = py << 7;
-                for (unsigned m = rm0; m; m &= m - 1) { if (off < cfg.list_cap) list[off] = (unsigned short)(ebase | (__ffs(m) - 1)); off++; }
-                for (unsigned m = rm1; m; m &= m - 1) { if (off < cfg.list_cap) list[off] = (unsigned short)(ebase | (32 + __ffs(m) - 1)); off++; }
+                const int ebase = py * tp;                       // list entry = py * tp + px: offset into the tile AND the score map
+                // (the list holds one slot per pixel of the largest cell, so it cannot overflow)
+                for (unsigned m = rm0; m; m &= m - 1) list[off++] = (unsigned short)(ebase + (__ffs(m) - 1));
+                for (unsigned m = rm1; m; m &= m - 1) list[off++] = (unsigned short)(ebase + (32 + __ffs(m) - 1));
                 cnt += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
@@ -210,13 +211,13 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
             int e = 0, sc = 0;
             if (k < cnt) {
                 e = list[k];
-                sc = fast_score_T(tile + ((e >> 7) + 3) * tp + (e & 127) + 3, tp, T);
+                sc = fast_score_T(tile + e + (3 * tp + 3), tp, T);
             }
             const unsigned m = __ballot_sync(0xffffffffu, sc != 0);
             __syncwarp();
             if (sc) {
                 list[ncorner + __popc(m & lt_mask)] = (unsigned short)e;
-                score[((e >> 7) + 1) * sp + (e & 127) + 1] = (uint8_t)sc;
+                score[e + (sp + 1)] = (uint8_t)sc;           // sp == tp
             }
             ncorner += __popc(m);
         }
@@ -224,11 +225,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
         // 4. strict 3x3 NMS over the corners (row-major) + ordered write
         for (int k0 = 0; k0 < ncorner; k0 += 32) {
             const int k = k0 + lane;
-            int keep = 0, s = 0, px = 0, py = 0;
+            int keep = 0, s = 0, e = 0;
             if (k < ncorner) {
-                const int e = list[k];
-                px = e & 127; py = (e >> 7) & 127;
-                const uint8_t* q = score + (py + 1) * sp + px + 1;
+                e = list[k];
+                const uint8_t* q = score + e + (sp + 1);
                 s = q[0];
                 // branch-free: strictly greater than the largest of the eight neighbours (list entries have s >= T > 0)
                 const int nmax = max(max(max(max((int)q[-1], (int)q[1]), (int)q[-sp - 1]), max((int)q[-sp], (int)q[-sp + 1])),
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int off = total + __popc(m & ((1u << lane) - 1));
+                const int py = e / tp, px = e - py * tp;        // survivors only
                 if (off < c.slot_cap)
                     slot[off] = ((uint32_t)s << 24) | ((uint32_t)(c.ey0 + py - ORBX_MINB) << 12) | (uint32_t)(c.ex0 + px - ORBX_MINB);
             }
@@ -252,11 +253,12 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st)
 {
     FastSmemCfg cfg;
-    // common case (cells up to 46 px wide): compile-time pitches 60 (15 words: odd, see the quick-test loop) / 48
-    const bool smallcfg = max_tile_w + 3 <= 60 && max_tile_w - 6 + 2 <= 48;
+    // common case (cells up to 54 px wide): compile-time pitch 60 (15 words: odd, see the quick-test loop) for the tile and,
+    // so that one list entry addresses both, for the score map
+    const bool smallcfg = max_tile_w + 3 <= 60;
     cfg.tpw = smallcfg ? 15 : ((3 + max_tile_w + 3) / 4 + 1) | 1;
     cfg.th = max_tile_h;
-    cfg.sp = smallcfg ? 48 : (max_tile_w - 6 + 2 + 3) & ~3;
+    cfg.sp = cfg.tpw * 4;                               // score pitch == tile pitch
     cfg.srows = max_tile_h - 6 + 2;
     cfg.list_cap = (max_tile_w - 6) * (max_tile_h - 6);
     cfg.tile_off = 0;
@@ -265,9 +267,9 @@ void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, 
     cfg.per_warp = (cfg.list_off + 2 * cfg.list_cap + 15) & ~15;
     const size_t smem = (size_t)cfg.per_warp * FAST_WARPS;
     static OrbxSmemMark mark[2] = {};
-    orbx_need_smem(fast_cells_kernel<60, 48>, mark[0], smem);
+    orbx_need_smem(fast_cells_kernel<60, 60>, mark[0], smem);
     orbx_need_smem(fast_cells_kernel<0, 0>, mark[1], smem);
     dim3 grid((L.ncells + FAST_WARPS - 1) / FAST_WARPS, nframes);
-    if (smallcfg) fast_cells_kernel<60, 48><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
+    if (smallcfg) fast_cells_kernel<60, 60><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
     else fast_cells_kernel<0, 0><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
 }
