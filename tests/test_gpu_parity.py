@@ -681,3 +681,36 @@ def test_stereo_extract_batch_host_matches_oracle():
         assert np.array_equal(out["depth"][i, :nl].view(np.uint32), dp_o.view(np.uint32)), f"pair {i}: mvDepth"
         matched += int(np.count_nonzero(ur_o >= 0))
     assert matched > 20 * n
+
+
+def test_rows_around_the_extractor_handle_empty_and_degenerate_inputs():
+    """Empty frames inside a BoW batch, frames with one feature, empty keypoint sets for the matchers and the undistortion."""
+    from orb_slam2_commit_b200 import KP_DTYPE, ORBVocabulary, search_by_projection_frame, undistort_keypoints
+    voc = synth.synth_vocabulary(5, 3, 2)
+    V = ORBVocabulary(5, 3, *voc); Vo = ob.Vocabulary(5, 3, *voc)
+    f = synth.synth_features_near_words(voc, 40, 1)
+    got = V.transform_batch([f[:0], f, f[:1], f[:0]], 1)
+    for g, d in zip(got, (f[:0], f, f[:1], f[:0])):
+        ref = Vo.transform(d, 1)
+        for k in ("word", "node", "bow_id", "fv_node", "fv_off", "fv_feat"):
+            assert np.array_equal(g[k], ref[k]), k
+        assert np.array_equal(g["bow_val"].view(np.uint64), ref["bow_val"].view(np.uint64))
+    assert len(got[0]["bow_id"]) == 0 and list(got[0]["fv_off"]) == [0]
+    assert np.array_equal(V.score([0, 1, 1], [1, 1, 2]), np.array([ob.bow_score_l1(got[a]["bow_id"], got[a]["bow_val"], got[b]["bow_id"], got[b]["bow_val"])
+                                                                     for a, b in ((0, 1), (1, 1), (1, 2))]))
+    kp = np.zeros(40, KP_DTYPE); kp["angle"] = np.linspace(0, 359, 40, dtype=np.float32)
+    n, m = V.search_by_bow(kp[:0], f[:0], None, kp, f, levelsup=1)
+    assert n == 0 and (m == -1).all()
+    n, m = V.search_by_bow(kp, f, None, kp[:0], f[:0], levelsup=1)
+    assert n == 0 and len(m) == 0
+    n, m = V.search_by_bow(kp, f, None, kp, f, levelsup=1, nnratio=0.99, check_orientation=True)     # a frame against itself
+    no, mo = ob.search_by_bow(Vo.transform(f, 1), Vo.transform(f, 1), f, kp["angle"], np.ones(40, np.uint8), f, kp["angle"], 0.99, True)
+    assert n == no and np.array_equal(m, mo)
+    assert len(undistort_keypoints(kp[:0], synth.TUM1_K4, synth.TUM1_DIST)) == 0
+    s = synth.synth_tracking_scene(9, n_last=50, n_extra=10)
+    e = dict(s); e["cur_kps"] = s["cur_kps"][:0]; e["cur_desc"] = s["cur_desc"][:0]; e["cur_u_right"] = None; e["cur_occupied"] = None
+    n, m = search_by_projection_frame(**e, th=7.0, mode=0)
+    assert n == 0 and len(m) == 0
+    e = dict(s); e["last_kps"] = s["last_kps"][:0]; e["last_xyz"] = s["last_xyz"][:0]; e["last_desc"] = s["last_desc"][:0]; e["last_flags"] = s["last_flags"][:0]
+    n, m = search_by_projection_frame(**e, th=7.0, mode=0)
+    assert n == 0 and (m == -1).all()
