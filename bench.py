@@ -704,7 +704,20 @@ def main():
             traffic = mb * 1e6 / 128.0 * B
         except Exception:
             traffic = None
-        roofline = {"bound": "hbm", "kernel": {"pyramid": "pyr_level0_kernel+pyr_resize_kernel (one launch per level)", "fast": "fast_cells_kernel",
+        # the binding resource of this integer/byte pipeline is instruction issue, not HBM: warp-instructions per frame
+        # (committed ncu capture, TUM1 geometry) x measured frames/s against 148 SMs x 4 issue slots x the sampled SM clock
+        issue = None
+        try:
+            ii = [i for i, c_ in enumerate(hdr_) if c_.startswith("smsp__inst_executed.sum")][0]
+            inst_per_frame = sum(float(r_[ii]) for r_ in rows_[1:]) / 128.0
+            if w["cfg"] == "tum1" and not rectify:
+                peak_issue = 148 * 4 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
+                issue = {"warp_instructions_per_frame": inst_per_frame, "peak_warp_instructions_per_s": peak_issue,
+                         "frac": inst_per_frame * frames_per_s / world / peak_issue,
+                         "source": "profiles/r01_ncu_full_batch128.csv (smsp__inst_executed.sum, all kernels of a step)"}
+        except Exception:
+            issue = None
+        roofline = {"bound": "hbm", "issue": issue, "kernel": {"pyramid": "pyr_level0_kernel+pyr_resize_kernel (one launch per level)", "fast": "fast_cells_kernel",
                                               "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]],
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
                     "algorithmic_bytes_per_frame": ab[names[dom]], "frames_per_launch": B, "traffic": traffic,
