@@ -41,6 +41,9 @@ WORKLOADS = {
     "euroc_rect": dict(cfg="euroc", batch=1024, distinct=32, rectify=True),
     # per-frame front-end of Tracking: extract -> UndistortKeyPoints -> ComputeBoW -> SearchByBoW / L1 score vs previous frame
     "tum1_frame": dict(cfg="tum1", batch=512, distinct=32, frame=True),
+    # ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on synthetic tracking scenes (1000 map points,
+    # ~1100 current keypoints, 30 % near-duplicate map points): one CTA per frame pair
+    "tum1_track": dict(cfg="tum1", batch=1024, distinct=8, track=True),
 }
 
 
@@ -387,6 +390,87 @@ def run_frame(args, torch, dist, rank, world, local, dev):
     emit_json_line(line)
 
 
+def run_track(args, torch, dist, rank, world, local, dev):
+    """Frame-to-frame SearchByProjection (ORBmatcher.cc:1489-1646) for a batch of frame pairs resident in HBM."""
+    import ctypes as C
+    from orb_slam2_commit_b200 import api, search_by_projection_frame
+    w = WORKLOADS[args.workload]
+    P = args.batch or w["batch"]
+    scenes = [synth.synth_tracking_scene(11 + i + 100 * rank) for i in range(w["distinct"])]
+    L = api.lib()
+    keep = []                                   # device tensors that must outlive the pair structs
+
+    def dev_t(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev); keep.append(t); return t
+    dsc = []
+    for sc in scenes:
+        d = {k: dev_t(sc[k]) for k in ("cur_kps", "cur_desc", "cur_u_right", "cur_occupied", "last_kps", "last_xyz", "last_desc", "last_flags")}
+        dsc.append(d)
+    pairs = (api.OrbxProjectionPair * P)()
+    d_match = torch.zeros((P, max(len(s_["cur_kps"]) for s_ in scenes)), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(P, dtype=torch.int32, device=dev)
+    for i in range(P):
+        sc, d = scenes[i % len(scenes)], dsc[i % len(scenes)]
+        p = pairs[i]
+        p.cur_keypoints = d["cur_kps"].data_ptr(); p.cur_descriptors = d["cur_desc"].data_ptr()
+        p.cur_u_right = d["cur_u_right"].data_ptr(); p.cur_occupied = d["cur_occupied"].data_ptr(); p.n_cur = len(sc["cur_kps"])
+        p.last_keypoints = d["last_kps"].data_ptr(); p.last_xyz = d["last_xyz"].data_ptr()
+        p.last_descriptors = d["last_desc"].data_ptr(); p.last_flags = d["last_flags"].data_ptr(); p.n_last = len(sc["last_kps"])
+        p.Tcw = (C.c_float * 12)(*sc["Tcw12"].tolist()); p.mode = i % 3
+        p.match = d_match[i].data_ptr(); p.nmatches = d_nm[i:].data_ptr()
+    cam = scenes[0]["cam9"]; sf = scenes[0]["scale_factors"]
+    f32p = C.POINTER(C.c_float)
+    ts = torch.cuda.Stream(device=dev); torch.cuda.set_stream(ts); st = ts.cuda_stream
+
+    def step():
+        api._ck(L.orbx_search_by_projection_device(pairs, P, cam.ctypes.data_as(f32p), sf.ctypes.data_as(f32p), len(sf), 7.0, 1, local, st))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup): step()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps): step()
+    e1.record(); torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1); clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * P * args.steps / (ms_total * 1e-3)
+    # e2e: the synchronous single-pair host call (host buffers in, assignment out)
+    n_e2e = 200; t0 = time.perf_counter()
+    for i in range(n_e2e):
+        search_by_projection_frame(**scenes[i % len(scenes)], th=7.0, mode=i % 3, device=local)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_v = world * n_e2e / float(t.item())
+    if rank != 0: return
+    sc0 = scenes[0]
+    line = {"metric": "projection_search_pairs_per_s", "value": value, "unit": "frame pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"SearchByProjection(CurrentFrame, LastFrame, th=7): {len(sc0['last_kps'])} last-frame map points x "
+                                   f"{len(sc0['cur_kps'])} current keypoints per pair, rotation check on, modes cycled",
+                       "pairs_per_step_per_gpu": P, "distinct_scenes": len(scenes)},
+            "clocks": clocks, "gpu_launches": args.steps,
+            "e2e": {"value": e2e_v, "unit": "frame pairs/s", "h2d_bytes_per_step": int(sum(np.asarray(v).nbytes for v in sc0.values() if v is not None)),
+                    "d2h_bytes_per_step": 4 * len(sc0["cur_kps"]) + 4, "steps": n_e2e, "api": "orbx_search_by_projection (one pair per call, synchronous)"},
+            "pipeline": {"matches_per_pair": float(d_nm.float().mean().item())}}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        nthreads = os.cpu_count() or 1
+        def make_worker(tid):
+            return lambda i: ob.search_by_projection_frame(**scenes[i % len(scenes)], th=7.0, mode=i % 3)
+        v, sample = cpu_thread_bench(make_worker, min(args.cpu_seconds, 6.0), nthreads)
+        line["cpu_baseline"] = {"value": v, "unit": "frame pairs/s", "cores": nthreads, "kind": "port", "sample": sample}
+    emit_json_line(line)
+
+
 def run_stereo(args, torch, dist, rank, world, local, dev):
     """Stereo pairs/s: two extractor instances (as the reference, Tracking.cc:120-123) + the device-resident matcher."""
     from orb_slam2_commit_b200 import ORBextractor, api, stereo_match_device
@@ -527,8 +611,9 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    if WORKLOADS[args.workload].get("stereo") or WORKLOADS[args.workload].get("frame"):
-        (run_stereo if WORKLOADS[args.workload].get("stereo") else run_frame)(args, torch, dist, rank, world, local, dev)
+    if WORKLOADS[args.workload].get("stereo") or WORKLOADS[args.workload].get("frame") or WORKLOADS[args.workload].get("track"):
+        wl = WORKLOADS[args.workload]
+        (run_stereo if wl.get("stereo") else run_frame if wl.get("frame") else run_track)(args, torch, dist, rank, world, local, dev)
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return

@@ -1522,6 +1522,21 @@ static int search_by_bow_host(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoin
 
 // ---------------------------------------------------------------------------------------------------------------
 // ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646)
+// stream-ordered allocations are used for per-call scratch: keep freed blocks in the pool instead of returning them to
+// the driver at every synchronisation (the default release threshold is 0)
+static void keep_mempool(int device)
+{
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
 extern "C" int orbx_search_by_projection_device(const OrbxProjectionPair* pairs, int npairs, const float* camera9,
                                                 const float* scale_factors, int nlevels, float th, int check_orientation,
                                                 int device, void* cuda_stream)
@@ -1530,6 +1545,7 @@ extern "C" int orbx_search_by_projection_device(const OrbxProjectionPair* pairs,
     if (!pairs || !camera9 || !scale_factors || nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "bad argument");
     if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
     CK(cudaSetDevice(device));
+    keep_mempool(device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     size_t tot_last = 0; int max_cur = 0;
     for (int p = 0; p < npairs; p++) {
@@ -1589,14 +1605,15 @@ extern "C" int orbx_search_by_projection(const OrbxProjectionPair* pair, const f
     const size_t c1 = std::max(nc, 1), l1 = std::max(nl, 1);
     const size_t b[] = {al(c1 * 28), al(c1 * 32), al(c1 * 4), al(c1), al(l1 * 28), al(l1 * 12), al(l1 * 32), al(l1), al(c1 * 4), 256};
     size_t tot = 0; for (size_t x : b) tot += x;
+    keep_mempool(device);
     uint8_t* pool = nullptr;
-    CK(cudaMalloc(&pool, tot));
+    CK(cudaMallocAsync(&pool, tot, 0));
     uint8_t* p[10]; { uint8_t* q = pool; for (int i = 0; i < 10; i++) { p[i] = q; q += b[i]; } }
     OrbxProjectionPair d = *pair;
     cudaError_t e = cudaSuccess;
     int rc = ORBX_OK;
     do {
-        auto up = [&](uint8_t* dst, const void* src, size_t n) { return (!src || !n) ? cudaSuccess : cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); };
+        auto up = [&](uint8_t* dst, const void* src, size_t n) { return (!src || !n) ? cudaSuccess : cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, 0); };
         if ((e = up(p[0], pair->cur_keypoints, (size_t)nc * 28)) != cudaSuccess) break;
         if ((e = up(p[1], pair->cur_descriptors, (size_t)nc * 32)) != cudaSuccess) break;
         if ((e = up(p[2], pair->cur_u_right, (size_t)nc * 4)) != cudaSuccess) break;
@@ -1611,11 +1628,10 @@ extern "C" int orbx_search_by_projection(const OrbxProjectionPair* pair, const f
         d.match = (int32_t*)p[8]; d.nmatches = (int32_t*)p[9];
         rc = orbx_search_by_projection_device(&d, 1, camera9, scale_factors, nlevels, th, check_orientation, device, nullptr);
         if (rc != ORBX_OK) break;
-        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
         if (nc > 0 && (e = cudaMemcpy(pair->match, p[8], (size_t)nc * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
         e = cudaMemcpy(pair->nmatches, p[9], 4, cudaMemcpyDeviceToHost);
     } while (0);
-    cudaFree(pool);
+    cudaFreeAsync(pool, 0);
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     return rc;
 }

@@ -4,6 +4,8 @@
 // the 64x48 grid and the nearest descriptor (<= TH_HIGH) takes the map point; matches outside the three dominant
 // rotation bins are dropped (:1613-1642, ComputeThreeMaxima :1797-1839).
 //
+// The current frame's grid (Frame::mGrid) is rebuilt in shared memory as a CSR by a counting sort, so a query only
+// visits the cells of its window, in GetFeaturesInArea's own order; one thread per last-frame keypoint.
 // The reference loop is sequential in one respect: a current keypoint that already holds a map point with
 // Observations() > 0 is skipped by LATER last-frame keypoints (:1574-1576). One CTA per frame pair resolves that with a
 // fixed-point iteration: every round all queries pick their best keypoint among those not taken by an EARLIER query
@@ -15,8 +17,10 @@
 #include "orbx_internal.cuh"
 #include <algorithm>
 
-struct ProjKp { float x, y; int octave; int cell; };          // cell = posX << 8 | posY, or -1 when PosInGrid fails
+struct ProjKp { float x, y; int octave; };
 typedef OrbxProjQuery ProjQuery;                               // r < 0: this last-frame keypoint makes no query
+
+#define PROJ_CELLS (64 * 48)                                   // FRAME_GRID_COLS x FRAME_GRID_ROWS (Frame.h)
 
 __device__ __forceinline__ int proj_dist(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1)
 {
@@ -24,32 +28,90 @@ __device__ __forceinline__ int proj_dist(const uint4 a0, const uint4 a1, const u
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// One CTA per frame pair. Shared memory holds Frame::mGrid of the current frame as a CSR (cell -> keypoint indices in
+// ascending order, exactly what AssignFeaturesToGrid builds), so a query visits only the cells of its window, in
+// GetFeaturesInArea's order (cell column, cell row, index): one THREAD per query, strict '<' keeps the first minimum.
 __global__ void __launch_bounds__(512) search_projection_kernel(const OrbxProjPairDev* __restrict__ pairs, OrbxProjCam cam,
                                                                 const float* __restrict__ scale_factors, float th,
                                                                 int check_orientation, int th_high)
 {
     extern __shared__ __align__(16) unsigned char s_raw3[];
     const OrbxProjPairDev P = pairs[blockIdx.x];
-    ProjKp* sk = reinterpret_cast<ProjKp*>(s_raw3);
-    int* taker = reinterpret_cast<int*>(sk + P.n_cur);
-    __shared__ int s_changed, s_hist[32], s_ind[3], s_success, s_removed;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    ProjKp* sk = reinterpret_cast<ProjKp*>(s_raw3);                              // [n_cur]
+    int* taker = reinterpret_cast<int*>(sk + P.n_cur);                          // [n_cur]
+    unsigned short* order = reinterpret_cast<unsigned short*>(taker + P.n_cur); // [n_cur] keypoint indices sorted by cell
+    unsigned short* cstart = order + ((P.n_cur + 1) & ~1);                      // [PROJ_CELLS + 1]
+    unsigned short* cfill = cstart + PROJ_CELLS + 2;                            // [PROJ_CELLS] counts, then fill cursors
+    __shared__ int s_changed, s_hist[32], s_ind[3], s_success, s_removed, s_w[17];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float invW = __fdiv_rn(64.0f, __fsub_rn(cam.maxX, cam.minX)), invH = __fdiv_rn(48.0f, __fsub_rn(cam.maxY, cam.minY));
 
-    // ---- current frame: grid cell of every keypoint (Frame::AssignFeaturesToGrid / PosInGrid)
-    for (int i = threadIdx.x; i < P.n_cur; i += blockDim.x) {
+    // ---- current frame: Frame::AssignFeaturesToGrid / PosInGrid as a counting sort
+    for (int c = tid; c < PROJ_CELLS; c += blockDim.x) cfill[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < P.n_cur; i += blockDim.x) {
         const OrbxKp28 k = P.cur_kps[i];
-        ProjKp e;
-        e.x = k.x; e.y = k.y; e.octave = k.octave;
-        const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, cam.minX), invW));
-        const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, cam.minY), invH));
-        e.cell = (posX < 0 || posX >= 64 || posY < 0 || posY >= 48) ? -1 : (posX << 8 | posY);
+        ProjKp e; e.x = k.x; e.y = k.y; e.octave = k.octave;
         sk[i] = e;
         taker[i] = 0x7fffffff;
         P.match[i] = -1;
+        const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, cam.minX), invW));
+        const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, cam.minY), invH));
+        if (!(posX < 0 || posX >= 64 || posY < 0 || posY >= 48)) {
+            // 16-bit counters packed two per word: atomicAdd on the containing word
+            const int c = posX * 48 + posY;
+            atomicAdd(reinterpret_cast<unsigned*>(cfill) + (c >> 1), (c & 1) ? 0x10000u : 1u);
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the cell counts: 6 cells per thread, then a block scan of the per-thread sums
+        const int c0 = tid * 6;
+        int loc[6], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { loc[j] = sum; sum += cfill[c0 + j]; }
+        int x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_w[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            const int t = lane < 16 ? s_w[lane] : 0;
+            int z = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+            if (lane < 16) s_w[lane] = z - t;
+            if (lane == 15) s_w[16] = z;
+        }
+        __syncthreads();
+        const int base = s_w[wid] + x - sum;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { cstart[c0 + j] = (unsigned short)(base + loc[j]); cfill[c0 + j] = (unsigned short)(base + loc[j]); }
+        if (tid == 0) cstart[PROJ_CELLS] = (unsigned short)s_w[16];
+    }
+    __syncthreads();
+    for (int i = tid; i < P.n_cur; i += blockDim.x) {
+        const ProjKp k = sk[i];
+        const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, cam.minX), invW));
+        const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, cam.minY), invH));
+        if (!(posX < 0 || posX >= 64 || posY < 0 || posY >= 48)) {
+            const int c = posX * 48 + posY;
+            const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(cfill) + (c >> 1), (c & 1) ? 0x10000u : 1u);
+            order[(c & 1) ? (old >> 16) : (old & 0xffffu)] = (unsigned short)i;
+        }
+    }
+    __syncthreads();
+    // the atomics filled every cell in arbitrary order: the reference's cells hold ascending indices
+    for (int c = tid; c < PROJ_CELLS; c += blockDim.x) {
+        const int b0 = cstart[c], b1 = cstart[c + 1];
+        for (int i = b0 + 1; i < b1; i++) {
+            const unsigned short v = order[i];
+            int j = i - 1;
+            while (j >= b0 && order[j] > v) { order[j + 1] = order[j]; j--; }
+            order[j + 1] = v;
+        }
     }
     // ---- last frame: projection of every map point (:1524-1567)
-    for (int i = threadIdx.x; i < P.n_last; i += blockDim.x) {
+    for (int i = tid; i < P.n_last; i += blockDim.x) {
         ProjQuery q; q.r = -1.f; q.u = q.v = q.ur = 0.f; q.min_level = q.max_level = -1;
         if (P.last_flags[i] & 1) {
             const float X = P.last_xyz[3 * i], Y = P.last_xyz[3 * i + 1], Z = P.last_xyz[3 * i + 2];
@@ -78,59 +140,52 @@ __global__ void __launch_bounds__(512) search_projection_kernel(const OrbxProjPa
         P.query[i] = q;
         P.assign[i] = -1;
     }
-    if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_success = 0; s_removed = 0; }
+    if (tid < 32) s_hist[tid] = 0;
+    if (tid == 0) { s_success = 0; s_removed = 0; }
     __syncthreads();
 
     const uint4* cdesc = reinterpret_cast<const uint4*>(P.cur_desc);
     const uint4* ldesc = reinterpret_cast<const uint4*>(P.last_desc);
     for (int round = 0; round <= P.n_last; round++) {
-        if (threadIdx.x == 0) s_changed = 0;
+        if (tid == 0) s_changed = 0;
         __syncthreads();
-        for (int qi = wid; qi < P.n_last; qi += nwarps) {
+        for (int qi = tid; qi < P.n_last; qi += blockDim.x) {
             const ProjQuery q = P.query[qi];
-            if (q.r < 0.f) continue;                                         // warp-uniform
-            // after the first round only queries whose situation can have changed need a new search: skipped here for
-            // simplicity — every query is re-evaluated against the current takers
+            if (q.r < 0.f) continue;
             const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.u, cam.minX), q.r), invW)));
             const int cx1 = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.u, cam.minX), q.r), invW)));
             const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.v, cam.minY), q.r), invH)));
             const int cy1 = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.v, cam.minY), q.r), invH)));
-            unsigned long long best = ~0ull;
+            int bestDist = 256, bestIdx = -1;
             if (!(cx0 >= 64 || cx1 < 0 || cy0 >= 48 || cy1 < 0)) {
                 const bool check_levels = q.min_level > 0 || q.max_level >= 0;
                 const uint4 qa = ldesc[2 * (size_t)qi], qb = ldesc[2 * (size_t)qi + 1];
-                for (int i = lane; i < P.n_cur; i += 32) {
-                    const ProjKp k = sk[i];
-                    if (k.cell < 0) continue;
-                    const int px = k.cell >> 8, py = k.cell & 255;
-                    if (px < cx0 || px > cx1 || py < cy0 || py > cy1) continue;
-                    if (check_levels) {
-                        if (k.octave < q.min_level) continue;
-                        if (q.max_level >= 0 && k.octave > q.max_level) continue;
+                for (int ix = cx0; ix <= cx1; ix++) {
+                    // the cells of one column are adjacent in the CSR: rows cy0..cy1 form one contiguous range
+                    const int j0 = cstart[ix * 48 + cy0], j1 = cstart[ix * 48 + cy1 + 1];
+                    for (int j = j0; j < j1; j++) {
+                        const int i = order[j];
+                        const ProjKp k = sk[i];
+                        if (check_levels) {
+                            if (k.octave < q.min_level) continue;
+                            if (q.max_level >= 0 && k.octave > q.max_level) continue;
+                        }
+                        if (!(fabsf(__fsub_rn(k.x, q.u)) < q.r && fabsf(__fsub_rn(k.y, q.v)) < q.r)) continue;
+                        if ((P.cur_occupied && P.cur_occupied[i]) || taker[i] < qi) continue;
+                        if (P.cur_u_right) { const float ur = P.cur_u_right[i]; if (ur > 0.f && fabsf(__fsub_rn(q.ur, ur)) > q.r) continue; }
+                        const int d = proj_dist(qa, qb, cdesc[2 * (size_t)i], cdesc[2 * (size_t)i + 1]);
+                        if (d < bestDist) { bestDist = d; bestIdx = i; }
                     }
-                    if (!(fabsf(__fsub_rn(k.x, q.u)) < q.r && fabsf(__fsub_rn(k.y, q.v)) < q.r)) continue;
-                    if ((P.cur_occupied && P.cur_occupied[i]) || taker[i] < qi) continue;
-                    if (P.cur_u_right) { const float ur = P.cur_u_right[i]; if (ur > 0.f && fabsf(__fsub_rn(q.ur, ur)) > q.r) continue; }
-                    const int d = proj_dist(qa, qb, cdesc[2 * (size_t)i], cdesc[2 * (size_t)i + 1]);
-                    // first candidate attaining the minimum in GetFeaturesInArea's scan order: cell column, cell row, index
-                    const unsigned long long key = ((unsigned long long)d << 40) | ((unsigned long long)px << 34) | ((unsigned long long)py << 28) | (unsigned)i;
-                    best = key < best ? key : best;
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t < best ? t : best; }
-            if (lane == 0) {
-                const int d = best == ~0ull ? 256 : (int)(best >> 40);
-                const int a = (d < 256 && d <= th_high) ? (int)(best & 0xfffffffu) : -1;
-                if (a != P.assign[qi]) { P.assign[qi] = a; s_changed = 1; }
-            }
+            const int a = bestDist <= th_high ? bestIdx : -1;
+            if (a != P.assign[qi]) { P.assign[qi] = a; s_changed = 1; }
         }
         __syncthreads();
         if (!s_changed) break;
-        for (int i = threadIdx.x; i < P.n_cur; i += blockDim.x) taker[i] = 0x7fffffff;
+        for (int i = tid; i < P.n_cur; i += blockDim.x) taker[i] = 0x7fffffff;
         __syncthreads();
-        for (int qi = threadIdx.x; qi < P.n_last; qi += blockDim.x) {
+        for (int qi = tid; qi < P.n_last; qi += blockDim.x) {
             const int a = P.assign[qi];
             if (a >= 0 && (P.last_flags[qi] & 2)) atomicMin(&taker[a], qi);
         }
@@ -182,7 +237,8 @@ void orbx_launch_search_projection(const OrbxProjPairDev* d_pairs, int npairs, i
                                    const float* d_scale_factors, float th, int check_orientation, cudaStream_t st)
 {
     if (npairs <= 0) return;
-    const size_t smem = (size_t)std::max(max_n_cur, 1) * (sizeof(ProjKp) + sizeof(int));
+    const size_t n1 = (size_t)std::max(max_n_cur, 1);
+    const size_t smem = n1 * (sizeof(ProjKp) + sizeof(int)) + ((n1 + 1) & ~(size_t)1) * 2 + (size_t)(2 * PROJ_CELLS + 4) * 2 + 16;
     static OrbxSmemMark mark[1] = {};
     orbx_need_smem(search_projection_kernel, mark[0], smem);
     search_projection_kernel<<<npairs, 512, smem, st>>>(d_pairs, cam, d_scale_factors, th, check_orientation, 100 /* TH_HIGH */);
