@@ -469,85 +469,127 @@ void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st)
 // ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:46-142): per projected map point the
 // candidates of Frame::GetFeaturesInArea (Frame.cc:388-444) are scanned in grid order (cell column, cell row, then
 // ascending keypoint index inside a cell — the order AssignFeaturesToGrid filled the cells in) keeping best / second
-// best with strict '<'. Here: one warp per query, the CTA stages (x, y, octave, grid cell) of every keypoint of the
-// frame in shared memory, every lane tests the reference's gates directly (level range, cell range, |dx|,|dy| < r,
-// occupied, stereo) and ranks survivors by the 64-bit key  dist<<40 | cellX<<34 | cellY<<28 | index: the smallest key
-// is the first candidate attaining the minimum distance in the reference's scan order and the second smallest key is
-// exactly its (bestDist2, bestLevel2).
-struct WinKp { float x, y; int octave; int cell; };   // cell = posX << 8 | posY, or -1 when PosInGrid fails
+// best with strict '<'. Here every CTA rebuilds Frame::mGrid in shared memory as a CSR (counting sort + per-cell
+// insertion sort for the ascending order), then one THREAD per query walks the cells of its window in exactly that
+// order and runs the reference's update rule verbatim — no tie-break keys needed.
+struct WinKp { float x, y; int octave; };
+#define WIN_CELLS (64 * 48)
+#define WIN_THREADS 512
 
-__global__ void __launch_bounds__(256) window_top2_kernel(OrbxWindowArgs A)
+__global__ void __launch_bounds__(WIN_THREADS) window_top2_kernel(OrbxWindowArgs A, int q_per_cta)
 {
     extern __shared__ __align__(16) unsigned char s_raw2[];
-    WinKp* sk = reinterpret_cast<WinKp*>(s_raw2);
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
+    WinKp* sk = reinterpret_cast<WinKp*>(s_raw2);                                    // [n]
+    unsigned short* order = reinterpret_cast<unsigned short*>(sk + A.n);            // [n] keypoint indices sorted by cell
+    unsigned short* cstart = order + ((A.n + 1) & ~1);                              // [WIN_CELLS + 1]
+    unsigned short* cfill = cstart + WIN_CELLS + 2;                                 // [WIN_CELLS]
+    __shared__ int s_w[17];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int c = tid; c < WIN_CELLS; c += WIN_THREADS) cfill[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < A.n; i += WIN_THREADS) {
         const OrbxKp28 k = A.kps[i];
-        WinKp e;
-        e.x = k.x; e.y = k.y; e.octave = k.octave;
+        WinKp e; e.x = k.x; e.y = k.y; e.octave = k.octave;
+        sk[i] = e;
         const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, A.minX), A.invW));     // Frame::PosInGrid
         const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, A.minY), A.invH));
-        e.cell = (posX < 0 || posX >= 64 || posY < 0 || posY >= 48) ? -1 : (posX << 8 | posY);
-        sk[i] = e;
-    }
-    __syncthreads();
-    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (qi >= A.nq) return;
-    const OrbxWinQuery q = A.q[qi];
-    const unsigned long long NONE = (256ull << 40) | 0xffffffffffull;
-    unsigned long long b1 = NONE, b2 = NONE;
-    int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.x, A.minX), q.r), A.invW)));
-    int cx1 = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.x, A.minX), q.r), A.invW)));
-    int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.y, A.minY), q.r), A.invH)));
-    int cy1 = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.y, A.minY), q.r), A.invH)));
-    const bool empty = cx0 >= 64 || cx1 < 0 || cy0 >= 48 || cy1 < 0;
-    const bool check_levels = q.min_level > 0 || q.max_level >= 0;
-    if (!empty) {
-        const uint4* dsc = reinterpret_cast<const uint4*>(A.desc);
-        const uint4 qa = reinterpret_cast<const uint4*>(A.qdesc)[2 * (size_t)qi], qb = reinterpret_cast<const uint4*>(A.qdesc)[2 * (size_t)qi + 1];
-        for (int i = lane; i < A.n; i += 32) {
-            const WinKp k = sk[i];
-            if (k.cell < 0) continue;
-            const int px = k.cell >> 8, py = k.cell & 255;
-            if (px < cx0 || px > cx1 || py < cy0 || py > cy1) continue;
-            if (check_levels) {
-                if (k.octave < q.min_level) continue;
-                if (q.max_level >= 0 && k.octave > q.max_level) continue;
-            }
-            if (!(fabsf(__fsub_rn(k.x, q.x)) < q.r && fabsf(__fsub_rn(k.y, q.y)) < q.r)) continue;
-            if (A.occupied && A.occupied[i]) continue;
-            if (A.u_right) { const float ur = A.u_right[i]; if (ur > 0.f && fabsf(__fsub_rn(q.xr, ur)) > q.r) continue; }
-            const int d = ht_dist(qa, qb, dsc[2 * (size_t)i], dsc[2 * (size_t)i + 1]);
-            if (d >= 256) continue;                           // strict '<' against the initial 256
-            const unsigned long long key = ((unsigned long long)d << 40) | ((unsigned long long)px << 34) | ((unsigned long long)py << 28) | (unsigned)i;
-            const unsigned long long hi = key > b1 ? key : b1;
-            b1 = key < b1 ? key : b1;
-            b2 = hi < b2 ? hi : b2;
+        if (!(posX < 0 || posX >= 64 || posY < 0 || posY >= 48)) {
+            const int c = posX * 48 + posY;
+            atomicAdd(reinterpret_cast<unsigned*>(cfill) + (c >> 1), (c & 1) ? 0x10000u : 1u);   // two 16-bit counters per word
         }
     }
+    __syncthreads();
+    {
+        const int c0 = tid * 6;                                                      // 512 threads x 6 cells = 3072
+        int loc[6], sum = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, b1, o), o2 = __shfl_xor_sync(0xffffffffu, b2, o);
-        const unsigned long long lo = b1 < o1 ? b1 : o1, hi = b1 < o1 ? o1 : b1;
-        const unsigned long long s2 = b2 < o2 ? b2 : o2;
-        b1 = lo; b2 = hi < s2 ? hi : s2;
+        for (int j = 0; j < 6; j++) { loc[j] = sum; sum += cfill[c0 + j]; }
+        int x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_w[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            const int t = lane < 16 ? s_w[lane] : 0;
+            int z = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+            if (lane < 16) s_w[lane] = z - t;
+            if (lane == 15) s_w[16] = z;
+        }
+        __syncthreads();
+        const int base = s_w[wid] + x - sum;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { cstart[c0 + j] = (unsigned short)(base + loc[j]); cfill[c0 + j] = (unsigned short)(base + loc[j]); }
+        if (tid == 0) cstart[WIN_CELLS] = (unsigned short)s_w[16];
     }
-    if (lane == 0) {
-        const int d1 = (int)(b1 >> 40), d2 = (int)(b2 >> 40);
-        const int i1 = (int)(b1 & 0xfffffffu), i2 = (int)(b2 & 0xfffffffu);
-        A.best_idx[qi] = d1 < 256 ? i1 : -1;
-        A.best_dist[qi] = d1 < 256 ? d1 : 256;
-        A.best_level[qi] = d1 < 256 ? sk[i1].octave : -1;
-        A.best_dist2[qi] = d2 < 256 ? d2 : 256;
-        A.best_level2[qi] = d2 < 256 ? sk[i2].octave : -1;
+    __syncthreads();
+    for (int i = tid; i < A.n; i += WIN_THREADS) {
+        const WinKp k = sk[i];
+        const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, A.minX), A.invW));
+        const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, A.minY), A.invH));
+        if (!(posX < 0 || posX >= 64 || posY < 0 || posY >= 48)) {
+            const int c = posX * 48 + posY;
+            const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(cfill) + (c >> 1), (c & 1) ? 0x10000u : 1u);
+            order[(c & 1) ? (old >> 16) : (old & 0xffffu)] = (unsigned short)i;
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < WIN_CELLS; c += WIN_THREADS) {
+        const int b0 = cstart[c], b1 = cstart[c + 1];
+        for (int i = b0 + 1; i < b1; i++) {
+            const unsigned short v = order[i];
+            int j = i - 1;
+            while (j >= b0 && order[j] > v) { order[j + 1] = order[j]; j--; }
+            order[j + 1] = v;
+        }
+    }
+    __syncthreads();
+
+    const uint4* dsc = reinterpret_cast<const uint4*>(A.desc);
+    const int q_end = min(A.nq, (int)(blockIdx.x + 1) * q_per_cta);
+    for (int qi = blockIdx.x * q_per_cta + tid; qi < q_end; qi += WIN_THREADS) {
+        const OrbxWinQuery q = A.q[qi];
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.x, A.minX), q.r), A.invW)));
+        const int cx1 = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.x, A.minX), q.r), A.invW)));
+        const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.y, A.minY), q.r), A.invH)));
+        const int cy1 = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.y, A.minY), q.r), A.invH)));
+        if (!(cx0 >= 64 || cx1 < 0 || cy0 >= 48 || cy1 < 0)) {
+            const bool check_levels = q.min_level > 0 || q.max_level >= 0;
+            const uint4 qa = reinterpret_cast<const uint4*>(A.qdesc)[2 * (size_t)qi], qb = reinterpret_cast<const uint4*>(A.qdesc)[2 * (size_t)qi + 1];
+            for (int ix = cx0; ix <= cx1; ix++) {
+                // rows cy0..cy1 of one cell column are one contiguous CSR range
+                const int j0 = cstart[ix * 48 + cy0], j1 = cstart[ix * 48 + cy1 + 1];
+                for (int j = j0; j < j1; j++) {
+                    const int i = order[j];
+                    const WinKp k = sk[i];
+                    if (check_levels) {
+                        if (k.octave < q.min_level) continue;
+                        if (q.max_level >= 0 && k.octave > q.max_level) continue;
+                    }
+                    if (!(fabsf(__fsub_rn(k.x, q.x)) < q.r && fabsf(__fsub_rn(k.y, q.y)) < q.r)) continue;
+                    if (A.occupied && A.occupied[i]) continue;
+                    if (A.u_right) { const float ur = A.u_right[i]; if (ur > 0.f && fabsf(__fsub_rn(q.xr, ur)) > q.r) continue; }
+                    const int d = ht_dist(qa, qb, dsc[2 * (size_t)i], dsc[2 * (size_t)i + 1]);
+                    if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = k.octave; bestIdx = i; }
+                    else if (d < bestDist2) { bestLevel2 = k.octave; bestDist2 = d; }
+                }
+            }
+        }
+        A.best_idx[qi] = bestIdx; A.best_dist[qi] = bestDist; A.best_level[qi] = bestLevel;
+        A.best_dist2[qi] = bestDist2; A.best_level2[qi] = bestLevel2;
     }
 }
 
 void orbx_launch_window_top2(const OrbxWindowArgs& a, cudaStream_t st)
 {
     if (a.nq <= 0) return;
-    const size_t smem = (size_t)(a.n > 0 ? a.n : 1) * sizeof(WinKp);
+    const size_t n1 = (size_t)(a.n > 0 ? a.n : 1);
+    const size_t smem = n1 * sizeof(WinKp) + ((n1 + 1) & ~(size_t)1) * 2 + (size_t)(2 * WIN_CELLS + 4) * 2 + 16;
     static OrbxSmemMark mark[1] = {};
     orbx_need_smem(window_top2_kernel, mark[0], smem);
-    window_top2_kernel<<<(a.nq + 7) / 8, 256, smem, st>>>(a);
+    // every CTA rebuilds the grid, so give each one at least a full round of queries
+    const int q_per_cta = std::max(WIN_THREADS, (a.nq + 147) / 148);
+    window_top2_kernel<<<(a.nq + q_per_cta - 1) / q_per_cta, WIN_THREADS, smem, st>>>(a, q_per_cta);
 }
