@@ -848,7 +848,7 @@ extern "C" int orbx_stereo_match_device(orbx_extractor* left, orbx_extractor* ri
     a.raw_right = right->L.raw + (size_t)right->pyr_base * right->L.frame_raw_bytes;
     a.frame_raw_bytes = left->L.frame_raw_bytes;
     a.lvl = left->d_lvl;
-    a.minD = 0.f; a.maxD = mbf / mb; a.mbf = mbf;  // Frame.cc:592-595
+    a.minD = 0.f; a.maxD = mbf / mb; a.mbf = mbf; a.max_scale = left->sf.back();  // Frame.cc:592-595
     a.u_right = d_u_right; a.depth = d_depth; a.sad = (int*)left->stereo_scratch;
     orbx_launch_stereo_batch(a, st);
     CK(cudaGetLastError());
@@ -940,7 +940,7 @@ extern "C" int orbx_stereo_extract_batch(orbx_extractor* left, orbx_extractor* r
         a.raw_right = right->L.raw + (size_t)base * right->L.frame_raw_bytes;
         a.frame_raw_bytes = left->L.frame_raw_bytes;
         a.lvl = left->d_lvl;
-        a.minD = 0.f; a.maxD = mbf / mb; a.mbf = mbf;
+        a.minD = 0.f; a.maxD = mbf / mb; a.mbf = mbf; a.max_scale = left->sf.back();
         float* d_ur = left->stereo_out + (size_t)base * kc;
         float* d_dp = left->stereo_out + (size_t)B * kc + (size_t)base * kc;
         a.u_right = d_ur; a.depth = d_dp; a.sad = (int*)left->stereo_scratch + (size_t)base * kc;

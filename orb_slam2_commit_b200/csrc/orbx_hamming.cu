@@ -309,15 +309,23 @@ void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, c
 // steps use un-contracted IEEE operations. Kernel 2: one CTA per pair finds the median SAD with a two-pass radix
 // select and applies the 1.5*1.4*median cut (Frame.cc:774-787).
 struct StereoR { float x; short minr, maxr; int octave; };   // 12 bytes per right keypoint
+#define STEREO_LPC 64                                        // left keypoints per CTA
 
-__global__ void __launch_bounds__(256) stereo_match_batch_kernel(OrbxStereoBatch A)
+// BANDS: the right keypoints are additionally bucketed by 8-row bands (a keypoint enters every band its row interval
+// touches; unordered lists, built with shared-memory atomics), so a left keypoint only looks at the right keypoints
+// of its own band — the (distance << 20 | right index) key restores the ascending-index tie-break of vRowIndices.
+#define STEREO_MAXBANDS 512
+template <bool BANDS>
+__global__ void __launch_bounds__(256) stereo_match_batch_kernel(OrbxStereoBatch A, int band_cap)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     StereoR* sr = reinterpret_cast<StereoR*>(s_raw);
+    __shared__ int s_bstart[BANDS ? STEREO_MAXBANDS + 1 : 1], s_bfill[BANDS ? STEREO_MAXBANDS + 1 : 1];
+    unsigned short* bent = reinterpret_cast<unsigned short*>(sr + A.cap);      // [band_cap] right-keypoint indices by band
     const int pair = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int nl = min(A.nl[pair], A.cap), nr = min(A.nr[pair], A.cap);
-    if ((int)(blockIdx.x * 8) >= nl) return;                  // whole CTA
+    if ((int)(blockIdx.x * STEREO_LPC) >= nl) return;         // whole CTA
     const OrbxKp28* kl = A.kl + (size_t)pair * A.cap;
     const OrbxKp28* kr = A.kr + (size_t)pair * A.cap;
     const uint4* dl = reinterpret_cast<const uint4*>(A.dl + (size_t)pair * A.cap * 32);
@@ -332,8 +340,38 @@ __global__ void __launch_bounds__(256) stereo_match_batch_kernel(OrbxStereoBatch
         sr[i] = e;
     }
     __syncthreads();
-    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (iL >= nl) return;
+    if (BANDS) {
+        const int nb = (A.rows + 7) >> 3;
+        for (int b = threadIdx.x; b <= nb; b += blockDim.x) s_bfill[b] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+            const int b0 = max((int)sr[i].minr, 0) >> 3, b1 = min((int)sr[i].maxr, A.rows - 1) >> 3;
+            for (int b = b0; b <= b1; b++) atomicAdd(&s_bfill[b], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                                   // exclusive scan of up to 512 band counts by one warp
+            int carry = 0;
+            for (int b0 = 0; b0 <= nb; b0 += 32) {
+                const int b = b0 + lane;
+                const int c = b < nb ? s_bfill[b] : 0;
+                int x = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                if (b <= nb) s_bstart[b] = carry + x - c;
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b <= nb; b += blockDim.x) s_bfill[b] = s_bstart[b];
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+            const int b0 = max((int)sr[i].minr, 0) >> 3, b1 = min((int)sr[i].maxr, A.rows - 1) >> 3;
+            for (int b = b0; b <= b1; b++) { const int pos = atomicAdd(&s_bfill[b], 1); if (pos < band_cap) bent[pos] = (unsigned short)i; }
+        }
+        __syncthreads();
+    }
+    // a CTA stages the right keypoints once and serves STEREO_LPC left keypoints (8 warps, several keypoints each)
+    for (int iL = blockIdx.x * STEREO_LPC + (threadIdx.x >> 5); iL < min(nl, (int)(blockIdx.x + 1) * STEREO_LPC); iL += 8) {
     const OrbxKp28 k = kl[iL];
     const int row = (int)k.y;
     int key = (100 << 20) | 0xfffff;
@@ -341,7 +379,9 @@ __global__ void __launch_bounds__(256) stereo_match_batch_kernel(OrbxStereoBatch
         const float minU = __fsub_rn(k.x, A.maxD), maxU = __fsub_rn(k.x, A.minD);
         if (!(maxU < 0.f)) {
             const uint4 qa = dl[2 * (size_t)iL], qb = dl[2 * (size_t)iL + 1];
-            for (int iR = lane; iR < nr; iR += 32) {
+            const int j0 = BANDS ? s_bstart[row >> 3] : 0, j1 = BANDS ? min(s_bstart[(row >> 3) + 1], band_cap) : nr;
+            for (int j = j0 + lane; j < j1; j += 32) {
+                const int iR = BANDS ? (int)bent[j] : j;
                 const StereoR r = sr[iR];
                 if (row < r.minr || row > r.maxr) continue;
                 if (r.octave < k.octave - 1 || r.octave > k.octave + 1) continue;
@@ -409,6 +449,7 @@ __global__ void __launch_bounds__(256) stereo_match_batch_kernel(OrbxStereoBatch
         const size_t o = (size_t)pair * A.cap + iL;
         A.u_right[o] = out_u; A.depth[o] = out_d; A.sad[o] = out_sad;
     }
+    }
 }
 
 // median of the matched SADs (the element at index size/2 of the sorted list, Frame.cc:775) by a two-pass radix
@@ -457,11 +498,21 @@ __global__ void __launch_bounds__(256) stereo_median_cut_kernel(OrbxStereoBatch 
 void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st)
 {
     if (a.pairs <= 0 || a.cap <= 0) return;
-    const size_t smem = (size_t)a.cap * sizeof(StereoR);
-    static OrbxSmemMark mark[1] = {};
-    orbx_need_smem(stereo_match_batch_kernel, mark[0], smem);
-    dim3 grid((a.cap + 7) / 8, a.pairs);
-    stereo_match_batch_kernel<<<grid, 256, smem, st>>>(a);
+    // band lists: a right keypoint's row interval [y - 2 s, y + 2 s] touches at most (4 s + 2) / 8 + 2 bands; 8 entries
+    // per keypoint cover every pyramid this library accepts (beyond scale 10 the plain path runs)
+    const size_t smem_plain = (size_t)a.cap * sizeof(StereoR);
+    const int band_cap = a.cap * 8;
+    const size_t smem_bands = smem_plain + (size_t)band_cap * 2;
+    const bool bands = smem_bands <= 200 * 1024 && a.rows <= 8 * STEREO_MAXBANDS && a.max_scale <= 10.0f;   // interval width <= 4 s + 3 = 43 rows -> at most 7 bands
+    static OrbxSmemMark mark[2] = {};
+    dim3 grid((a.cap + STEREO_LPC - 1) / STEREO_LPC, a.pairs);
+    if (bands) {
+        orbx_need_smem(stereo_match_batch_kernel<true>, mark[0], smem_bands);
+        stereo_match_batch_kernel<true><<<grid, 256, smem_bands, st>>>(a, band_cap);
+    } else {
+        orbx_need_smem(stereo_match_batch_kernel<false>, mark[1], smem_plain);
+        stereo_match_batch_kernel<false><<<grid, 256, smem_plain, st>>>(a, 0);
+    }
     stereo_median_cut_kernel<<<a.pairs, 256, 0, st>>>(a);
 }
 

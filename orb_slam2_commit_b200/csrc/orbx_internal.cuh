@@ -127,6 +127,7 @@ struct OrbxStereoBatch {       // full Frame::ComputeStereoMatches (Frame.cc:547
     size_t frame_raw_bytes;
     const OrbxLevelGeom* lvl;
     float minD, maxD, mbf;
+    float max_scale;                                        // mvScaleFactors[nlevels - 1] (bounds the row band of a right keypoint)
     float* u_right; float* depth; int* sad;                 // [pairs][cap]; sad = -1 when unmatched
 };
 void orbx_launch_stereo_batch(const OrbxStereoBatch& a, cudaStream_t st);

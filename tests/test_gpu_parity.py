@@ -714,3 +714,20 @@ def test_rows_around_the_extractor_handle_empty_and_degenerate_inputs():
     e = dict(s); e["last_kps"] = s["last_kps"][:0]; e["last_xyz"] = s["last_xyz"][:0]; e["last_desc"] = s["last_desc"][:0]; e["last_flags"] = s["last_flags"][:0]
     n, m = search_by_projection_frame(**e, th=7.0, mode=0)
     assert n == 0 and (m == -1).all()
+
+
+def test_full_stereo_match_large_scale_factor_plain_path():
+    """Scale factors above 10 at the top octave leave the stereo matcher's 8-row band buckets (a right keypoint's row
+    interval could touch more bands than the buckets reserve): the un-bucketed scan must give the same result."""
+    W, H = 1600, 1000
+    args = (1500, 1.5, 7, 20, 7)                               # 1.5^6 = 11.4
+    left, right = synth.synth_stereo_pair(W, H, 77, max_disp=50)
+    exL, exR = ORBextractor(*args), ORBextractor(*args)
+    kl, dl = exL(left); kr, dr = exR(right)
+    ur, dp = stereo_match(exL, exR, kl, dl, kr, dr, 400.0, 700.0)
+    oL, oR = ob.Extractor(*args), ob.Extractor(*args)
+    kl_o, dl_o = oL.extract(left); kr_o, dr_o = oR.extract(right)
+    assert kl.tobytes() == kl_o.tobytes() and kr.tobytes() == kr_o.tobytes()
+    ur_o, dp_o = ob.stereo_match(oL, oR, kl_o, dl_o, kr_o, dr_o, 400.0, 700.0)
+    assert np.array_equal(ur.view(np.uint32), ur_o.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dp_o.view(np.uint32))
+    assert np.count_nonzero(ur >= 0) > 50 and kl["octave"].max() == 6
