@@ -17,7 +17,7 @@
 // cell is redone at minThFAST (ORBextractor.cc:894-900). The score map never touches HBM.
 #include "orbx_internal.cuh"
 
-#define FAST_WARPS 4
+#define FAST_MAX_WARPS 8     // warps (= cells) per CTA are chosen at launch: whatever packs most warps into an SM
 
 struct FastSmemCfg { int tpw, th, sp, srows, list_cap, tile_off, score_off, list_off, per_warp; };
 
@@ -107,11 +107,12 @@ __device__ __forceinline__ unsigned quick_test(const uint8_t* __restrict__ qp, c
 // TPC / SPC: compile-time tile / score-map pitches in bytes (all ring and NMS offsets become immediates);
 // 0 = take them from cfg (cells wider than the common 30..46 px)
 template <int TPC, int SPC>
-__global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLayout L, FastSmemCfg cfg)
+// (288 threads x 4 CTAs as the bound: at most 56 registers per thread = 7 allocation units per warp, 36 warps per SM by registers)
+__global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, FastSmemCfg cfg)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int cell_id = blockIdx.x * FAST_WARPS + wid;
+    const int cell_id = blockIdx.x * (blockDim.x >> 5) + wid;
     const int frame = blockIdx.y;
     if (cell_id >= L.ncells) return;                      // whole warp
     const OrbxCell c = L.cells[cell_id];
@@ -253,10 +254,12 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) fast_cells_kernel(OrbxFrameLa
 void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st)
 {
     FastSmemCfg cfg;
-    // common case (cells up to 54 px wide): compile-time pitch 60 (15 words: odd, see the quick-test loop) for the tile and,
-    // so that one list entry addresses both, for the score map
-    const bool smallcfg = max_tile_w + 3 <= 60;
-    cfg.tpw = smallcfg ? 15 : ((3 + max_tile_w + 3) / 4 + 1) | 1;
+    // compile-time pitches (11, 13 or 15 words: odd, see the quick-test loop) for the tile and, so that one list entry
+    // addresses both, for the score map; the narrowest that holds the widest cell (+3-px ring, +3 bytes of alignment
+    // slack) keeps shared memory per warp — and with it the number of resident warps — as good as it gets
+    const int need = max_tile_w + 3;
+    const int variant = need <= 44 ? 0 : need <= 52 ? 1 : need <= 60 ? 2 : 3;
+    cfg.tpw = variant == 0 ? 11 : variant == 1 ? 13 : variant == 2 ? 15 : ((3 + max_tile_w + 3) / 4 + 1) | 1;
     cfg.th = max_tile_h;
     cfg.sp = cfg.tpw * 4;                               // score pitch == tile pitch
     cfg.srows = max_tile_h - 6 + 2;
@@ -265,11 +268,27 @@ void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, 
     cfg.score_off = (cfg.tpw * 4 * cfg.th + 15) & ~15;
     cfg.list_off = (cfg.score_off + cfg.sp * cfg.srows + 15) & ~15;
     cfg.per_warp = (cfg.list_off + 2 * cfg.list_cap + 15) & ~15;
-    const size_t smem = (size_t)cfg.per_warp * FAST_WARPS;
-    static OrbxSmemMark mark[2] = {};
-    orbx_need_smem(fast_cells_kernel<60, 60>, mark[0], smem);
-    orbx_need_smem(fast_cells_kernel<0, 0>, mark[1], smem);
-    dim3 grid((L.ncells + FAST_WARPS - 1) / FAST_WARPS, nframes);
-    if (smallcfg) fast_cells_kernel<60, 60><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
-    else fast_cells_kernel<0, 0><<<grid, FAST_WARPS * 32, smem, st>>>(L, cfg);
+    typedef void (*kern_t)(OrbxFrameLayout, FastSmemCfg);
+    static const kern_t kerns[4] = {fast_cells_kernel<44, 44>, fast_cells_kernel<52, 52>, fast_cells_kernel<60, 60>, fast_cells_kernel<0, 0>};
+    const kern_t kern = kerns[variant];
+    // The kernel is issue-bound and gains from every extra resident warp; shared memory per warp (tile + score map + list)
+    // decides how many fit, and the CTA size decides how well they pack: ask the occupancy calculator for each size.
+    static int best_fw[64][4] = {}; static int best_pw[64][4] = {};
+    static OrbxSmemMark mk[4] = {};
+    int dev = 0; cudaGetDevice(&dev); dev &= 63;
+    if (best_pw[dev][variant] != cfg.per_warp) {
+        int bw = 0, bfw = 4;
+        for (int fw = FAST_MAX_WARPS; fw >= 2; fw--) {
+            const size_t sm = (size_t)cfg.per_warp * fw;
+            orbx_need_smem(kern, mk[variant], sm);
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, fw * 32, sm) == cudaSuccess && nb * fw > bw) { bw = nb * fw; bfw = fw; }
+        }
+        cudaGetLastError();
+        best_fw[dev][variant] = bfw; best_pw[dev][variant] = cfg.per_warp;
+    }
+    const int fwarps = best_fw[dev][variant];
+    const size_t smem = (size_t)cfg.per_warp * fwarps;
+    dim3 grid((L.ncells + fwarps - 1) / fwarps, nframes);
+    kern<<<grid, fwarps * 32, smem, st>>>(L, cfg);
 }
