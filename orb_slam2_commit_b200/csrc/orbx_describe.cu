@@ -16,7 +16,7 @@
 // No blurred pyramid is ever written to HBM.
 #include "orbx_internal.cuh"
 
-#define DESC_WARPS 8
+#define DESC_WARPS 4         // 128-thread CTAs: 9 fit by registers (54 per thread) = 36 resident warps; 8-warp CTAs only reach 32
 #define PW 43            // patch width/height
 #define PWORDS 12        // 32-bit words per staged patch row (48 bytes)
 #define VROWS 37         // rows of the vertically blurred patch (patch rows 3..39 centred)
