@@ -319,6 +319,90 @@ int orbx_search_by_projection_device(const OrbxProjectionPair* pairs, int npairs
                                      const float* scale_factors, int nlevels, float th, int check_orientation, int device,
                                      void* cuda_stream);
 
+/* ---- ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (ORBmatcher.cc:46-142),
+ *      the matcher of Tracking::SearchLocalPoints, complete: RadiusByViewingCos (:144-150), Frame::GetFeaturesInArea on the
+ *      64x48 grid with the level range [level-1, level], best / second-best with their levels, `bestDist <= TH_HIGH`, the
+ *      NN-ratio rule (:129-137) and the reference's SEQUENTIAL rule — a keypoint that holds a map point with
+ *      Observations() > 0, from before the call or assigned earlier in the loop, is skipped (:90-92).
+ *      One query per entry of vpMapPoints, carrying what Frame::isInFrustum (Frame.cc:315-384) left in the map point. ---- */
+typedef struct OrbxTrackQuery {
+    float proj_x, proj_y, proj_xr;      /* mTrackProjX, mTrackProjY, mTrackProjXR */
+    float view_cos;                     /* mTrackViewCos */
+    int32_t level;                      /* mnTrackScaleLevel */
+} OrbxTrackQuery;
+typedef struct OrbxLocalPointsFrame {
+    const OrbxKeyPoint* keypoints;      /* F.mvKeysUn, n */
+    const uint8_t* descriptors;         /* F.mDescriptors */
+    const float* u_right;               /* F.mvuRight, or NULL (monocular) */
+    const uint8_t* occupied;            /* != 0 <=> F.mvpMapPoints[i] has Observations() > 0 before the call; NULL = none */
+    int32_t n;
+    const OrbxTrackQuery* queries;      /* nq = vpMapPoints.size() */
+    const uint8_t* query_descriptors;   /* pMP->GetDescriptor(), 32 bytes each */
+    const uint8_t* query_flags;         /* bit 0: mbTrackInView && !isBad(); bit 1: Observations() > 0 */
+    int32_t nq;
+    int32_t* match;                     /* out, n: index into vpMapPoints the keypoint holds after the call, -1 = untouched */
+    int32_t* nmatches;                  /* out: the return value */
+} OrbxLocalPointsFrame;
+/* bounds4 = (mnMinX, mnMaxX, mnMinY, mnMaxY); scale_factors = F.mvScaleFactors; nnratio = mfNNratio. Host buffers, synchronous */
+int orbx_search_local_points(const OrbxLocalPointsFrame* frame, const float* bounds4, const float* scale_factors, int nlevels,
+                             float th, float nnratio, int device);
+/* `frames` is a HOST array whose pointers are DEVICE pointers; one CTA per frame, asynchronous on cuda_stream */
+int orbx_search_local_points_device(const OrbxLocalPointsFrame* frames, int nframes, const float* bounds4,
+                                    const float* scale_factors, int nlevels, float th, float nnratio, int device,
+                                    void* cuda_stream);
+
+/* ---- The search half of ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th) (ORBmatcher.cc:918-1092;
+ *      mode 0) and of Fuse(KeyFrame *pKF, cv::Mat Scw, vpPoints, th, vpReplacePoint) (:1094-1236; mode 1, with Rcw / tcw / Ow
+ *      taken out of Scw by the caller as :1101-1106 do): projection into the keyframe, KeyFrame::IsInImage, the distance-
+ *      invariance and viewing-angle gates, MapPoint::PredictScale (MapPoint.cc:407-422), KeyFrame::GetFeaturesInArea
+ *      (KeyFrame.cc:708-747), the level and chi-square gates and the nearest descriptor. best_idx[i] = keyframe feature the
+ *      point fuses with (bestDist <= TH_LOW) or -1; the Replace / AddObservation surgery that follows stays with the map. ---- */
+typedef struct OrbxFuseJob {
+    const OrbxKeyPoint* keypoints;      /* pKF->mvKeysUn, n */
+    const uint8_t* descriptors;         /* pKF->mDescriptors */
+    const float* u_right;               /* pKF->mvuRight, or NULL (all < 0) */
+    int32_t n;
+    float Tcw[12];                      /* Rcw row-major (9 floats), then tcw (3) */
+    float Ow[3];                        /* camera centre */
+    const float* pt_xyz;                /* GetWorldPos(): 3 floats per point */
+    const float* pt_normal;             /* GetNormal(): 3 floats per point */
+    const float* pt_dist;               /* 3 floats per point: GetMinDistanceInvariance(), GetMaxDistanceInvariance(), mfMaxDistance */
+    const uint8_t* pt_descriptors;      /* GetDescriptor() */
+    const uint8_t* pt_flags;            /* bit 0: non-NULL, !isBad() and not already in the keyframe (:941-945 / :1133-1136) */
+    int32_t npts;
+    float th;
+    int32_t mode;                       /* 0: Fuse(pKF, vpMapPoints, th), 1: Fuse(pKF, Scw, ...) */
+    int32_t* best_idx;                  /* out, npts */
+    int32_t* best_dist;                 /* out, npts: bestDist (256 / INT_MAX when no candidate was compared) */
+    int32_t* nfused;                    /* out: the return value */
+} OrbxFuseJob;
+/* camera9 = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY); scale_factors = mvScaleFactors, inv_level_sigma2 =
+ * mvInvLevelSigma2, log_scale_factor = mfLogScaleFactor. Host buffers, one job, synchronous. */
+int orbx_fuse_search(const OrbxFuseJob* job, const float* camera9, const float* scale_factors, const float* inv_level_sigma2,
+                     int nlevels, float log_scale_factor, int device);
+/* `jobs` is a HOST array whose pointers are DEVICE pointers; one CTA per job, asynchronous on cuda_stream */
+int orbx_fuse_search_device(const OrbxFuseJob* jobs, int njobs, const float* camera9, const float* scale_factors,
+                            const float* inv_level_sigma2, int nlevels, float log_scale_factor, int device, void* cuda_stream);
+
+/* ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (ORBmatcher.cc:738-916), the matcher
+ *      of LocalMapping::CreateNewMapPoints, for npairs keyframe pairs of the last transformed batch. has_mp[frame][cap] != 0
+ *      <=> GetMapPoint(idx) is non-NULL (NULL = none has); u_right[frame][cap] = mvuRight (NULL = monocular keyframes).
+ *      geom: 28 floats per pair — F12 row-major (9), pKF1->GetCameraCenter() (3), pKF2->GetRotation() row-major (9),
+ *      pKF2->GetTranslation() (3), pKF2's fx, fy, cx, cy. scale_factors / level_sigma2 = pKF2->mvScaleFactors / mvLevelSigma2.
+ *      match12[pair][idx1] = idx2 or -1: vMatchedPairs is the list of non-negative entries in ascending idx1.
+ *      (The reference never sets vbMatched2, so a keyframe-2 feature may appear in several pairs; reproduced.) ---- */
+int  orbx_search_for_triangulation_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf1_frame, const int32_t* d_kf2_frame,
+                                          const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_has_mp,
+                                          const float* d_u_right, const float* d_geom, const float* scale_factors,
+                                          const float* level_sigma2, int nlevels, int only_stereo, int check_orientation,
+                                          int32_t* d_match12, int32_t* d_nmatches, void* cuda_stream);
+/* one pair from host buffers (transforms both descriptor sets first) */
+int  orbx_search_for_triangulation(orbx_vocabulary* v, const OrbxKeyPoint* kf1_keypoints, const uint8_t* kf1_descriptors, int n1,
+                                   const uint8_t* has_mp1, const float* u_right1, const OrbxKeyPoint* kf2_keypoints,
+                                   const uint8_t* kf2_descriptors, int n2, const uint8_t* has_mp2, const float* u_right2,
+                                   const float* geom28, const float* scale_factors, const float* level_sigma2, int nlevels,
+                                   int levelsup, int only_stereo, int check_orientation, int32_t* match12, int32_t* nmatches);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

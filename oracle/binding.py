@@ -441,3 +441,83 @@ def search_by_bow_kf(t1, t2, desc1, angle1, valid1, desc2, angle2, valid2, nnrat
                                   desc2.ctypes.data, angle2.ctypes.data, valid2.ctypes.data, len(desc2), nnratio,
                                   int(check_orientation), match.ctypes.data)
     return n, match[:len(desc1)]
+
+
+TRACKQ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4")])
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def search_local_points(kps, desc, u_right, occupied, bounds4, scale_factors, queries, query_desc, query_flags, th, nnratio=0.8):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:46-142) -> (nmatches, match)"""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    b4 = np.ascontiguousarray(bounds4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    q = np.ascontiguousarray(queries, TRACKQ_DTYPE); qd = np.ascontiguousarray(query_desc, np.uint8)
+    qf = np.ascontiguousarray(query_flags, np.uint8)
+    match = np.zeros(max(len(kps), 1), np.int32)
+    f = lib().oc_search_local_points
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    n = f(kps.ctypes.data, desc.ctypes.data, len(kps), _p(ur), _p(occ), b4.ctypes.data, sf.ctypes.data, len(sf), q.ctypes.data,
+          qd.ctypes.data, qf.ctypes.data, len(q), th, nnratio, match.ctypes.data)
+    return n, match[:len(kps)]
+
+
+def predict_scale(max_distance, current_dist, log_scale_factor, nlevels):
+    f = lib().oc_predict_scale
+    f.restype = C.c_int; f.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+    return f(max_distance, current_dist, log_scale_factor, nlevels)
+
+
+def fuse_search(kps, desc, u_right, Tcw12, Ow3, cam9, scale_factors, inv_level_sigma2, log_scale_factor, pt_xyz, pt_normal,
+                pt_dist, pt_desc, pt_flags, th, mode=0):
+    """Search half of ORBmatcher::Fuse (ORBmatcher.cc:918-1092 / 1094-1236) -> (nFused, best_idx, best_dist)"""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    T = np.ascontiguousarray(Tcw12, np.float32); Ow = np.ascontiguousarray(Ow3, np.float32)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = np.ascontiguousarray(pt_normal, np.float32)
+    dst = np.ascontiguousarray(pt_dist, np.float32); pd = np.ascontiguousarray(pt_desc, np.uint8)
+    pf = np.ascontiguousarray(pt_flags, np.uint8)
+    npts = len(pf)
+    bi = np.zeros(max(npts, 1), np.int32); bd = np.zeros(max(npts, 1), np.int32)
+    f = lib().oc_fuse_search
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_float] + [C.c_void_p] * 5 + \
+        [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    n = f(kps.ctypes.data, desc.ctypes.data, len(kps), _p(ur), T.ctypes.data, Ow.ctypes.data, cam.ctypes.data, sf.ctypes.data,
+          s2.ctypes.data, len(sf), float(log_scale_factor), xyz.ctypes.data, nrm.ctypes.data, dst.ctypes.data, pd.ctypes.data,
+          pf.ctypes.data, npts, th, mode, bi.ctypes.data, bd.ctypes.data)
+    return n, bi[:npts], bd[:npts]
+
+
+def search_for_triangulation(t1, t2, kps1, desc1, has_mp1, u_right1, kps2, desc2, has_mp2, u_right2, geom28, scale_factors,
+                             level_sigma2, only_stereo=False, check_orientation=True):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:738-916); t1 / t2: dicts from Vocabulary.transform. geom28 = F12 (9),
+    Cw1 (3), R2w (9), t2w (3), K2 (4). -> (nmatches, match12)"""
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    m1 = None if has_mp1 is None else np.ascontiguousarray(has_mp1, np.uint8)
+    m2 = None if has_mp2 is None else np.ascontiguousarray(has_mp2, np.uint8)
+    r1 = None if u_right1 is None else np.ascontiguousarray(u_right1, np.float32)
+    r2 = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+    g = np.ascontiguousarray(geom28, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    s2 = np.ascontiguousarray(level_sigma2, np.float32)
+    a = [np.ascontiguousarray(t1[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    b = [np.ascontiguousarray(t2[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    match = np.zeros(max(len(kps1), 1), np.int32)
+    f = lib().oc_search_for_triangulation
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + \
+        [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]
+    n = f(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, len(b[0]),
+          kps1.ctypes.data, desc1.ctypes.data, _p(m1), _p(r1), len(kps1), kps2.ctypes.data, desc2.ctypes.data, _p(m2), _p(r2), len(kps2),
+          g[0:9].ctypes.data, g[9:12].ctypes.data, g[12:24].ctypes.data, g[24:28].ctypes.data, sf.ctypes.data, s2.ctypes.data,
+          int(only_stereo), int(check_orientation), match.ctypes.data)
+    return n, match[:len(kps1)]

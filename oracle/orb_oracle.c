@@ -22,6 +22,7 @@
  */
 #include "orb_oracle.h"
 #include <float.h>
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1409,5 +1410,273 @@ int oc_search_by_bow_kf(const int32_t* fv1_node, const int32_t* fv1_off, const i
             if (hist_bin[t] != i1 && hist_bin[t] != i2 && hist_bin[t] != i3) { match12[hist_idx[t]] = -1; nmatches--; }
     }
     free(hist_idx); free(hist_bin); free(matched2);
+    return nmatches;
+}
+
+/* ------------------------------------------------------------------ Frame grid helper shared by the matchers below */
+typedef struct { int* cnt; int* tab; } OcGrid;
+static OcGrid oc_grid_build(const OcKeyPoint* kps, int n, float mnMinX, float mnMinY, float invW, float invH)
+{
+    OcGrid g;
+    g.cnt = (int*)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, sizeof(int));
+    g.tab = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int* cell = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int* fill = (int*)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS, sizeof(int));
+    for (int i = 0; i < n; i++) {
+        int posX = (int)roundf((kps[i].x - mnMinX) * invW), posY = (int)roundf((kps[i].y - mnMinY) * invH);
+        cell[i] = (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) ? -1 : posX * FRAME_GRID_ROWS + posY;
+        if (cell[i] >= 0) g.cnt[cell[i] + 1]++;
+    }
+    for (int c = 0; c < FRAME_GRID_COLS * FRAME_GRID_ROWS; c++) g.cnt[c + 1] += g.cnt[c];
+    for (int i = 0; i < n; i++) if (cell[i] >= 0) g.tab[g.cnt[cell[i]] + fill[cell[i]]++] = i;
+    free(cell); free(fill);
+    return g;
+}
+static void oc_grid_free(OcGrid* g) { free(g->cnt); free(g->tab); }
+/* cell rectangle of GetFeaturesInArea (Frame.cc:394-408, KeyFrame.cc:713-727); 0 = empty result */
+static int oc_grid_window(float x, float y, float r, float mnMinX, float mnMinY, float invW, float invH, int* x0, int* x1, int* y0, int* y1)
+{
+    *x0 = (int)floorf((x - mnMinX - r) * invW); if (*x0 < 0) *x0 = 0;
+    if (*x0 >= FRAME_GRID_COLS) return 0;
+    *x1 = (int)ceilf((x - mnMinX + r) * invW); if (*x1 > FRAME_GRID_COLS - 1) *x1 = FRAME_GRID_COLS - 1;
+    if (*x1 < 0) return 0;
+    *y0 = (int)floorf((y - mnMinY - r) * invH); if (*y0 < 0) *y0 = 0;
+    if (*y0 >= FRAME_GRID_ROWS) return 0;
+    *y1 = (int)ceilf((y - mnMinY + r) * invH); if (*y1 > FRAME_GRID_ROWS - 1) *y1 = FRAME_GRID_ROWS - 1;
+    if (*y1 < 0) return 0;
+    return 1;
+}
+
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (ORBmatcher.cc:46-142),
+ * called by Tracking::SearchLocalPoints. q[i] carries what Frame::isInFrustum left in the map point (mTrackProjX,
+ * mTrackProjY, mTrackProjXR, mTrackViewCos, mnTrackScaleLevel); qflags bit 0: mbTrackInView && !isBad(), bit 1:
+ * Observations() > 0. occupied[k]: F.mvpMapPoints[k] exists with Observations() > 0 before the call.
+ * match[k] = index into vpMapPoints that keypoint k holds after the call, -1 = untouched. Returns nmatches. */
+int oc_search_local_points(const OcKeyPoint* kps, const uint8_t* desc, int n, const float* u_right, const uint8_t* occupied,
+                           const float* bounds4, const float* scale_factors, int nlevels,
+                           const OcTrackQuery* q, const uint8_t* qdesc, const uint8_t* qflags, int nq,
+                           float th, float nnratio, int32_t* match)
+{
+    const float mnMinX = bounds4[0], mnMaxX = bounds4[1], mnMinY = bounds4[2], mnMaxY = bounds4[3];
+    const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
+    OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);
+    uint8_t* occ = (uint8_t*)calloc((size_t)(n > 0 ? n : 1), 1);
+    for (int i = 0; i < n; i++) { match[i] = -1; occ[i] = occupied ? (occupied[i] != 0) : 0; }
+    int nmatches = 0;
+    const int bFactor = th != 1.0;
+    (void)nlevels;
+    for (int iMP = 0; iMP < nq; iMP++) {
+        if (!(qflags[iMP] & 1)) continue;
+        const int nPredictedLevel = q[iMP].level;
+        float r = q[iMP].view_cos > 0.998 ? 2.5 : 4.0;                          /* RadiusByViewingCos (:144-150) */
+        if (bFactor) r *= th;
+        const float rad = r * scale_factors[nPredictedLevel];
+        const int minLevel = nPredictedLevel - 1, maxLevel = nPredictedLevel;
+        int x0, x1, y0, y1;
+        if (!oc_grid_window(q[iMP].x, q[iMP].y, rad, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int ix = x0; ix <= x1; ix++)
+            for (int iy = y0; iy <= y1; iy++) {
+                const int c = ix * FRAME_GRID_ROWS + iy;
+                for (int j = g.cnt[c]; j < g.cnt[c + 1]; j++) {
+                    const int idx = g.tab[j];
+                    const OcKeyPoint* kp = &kps[idx];
+                    if (bCheckLevels) {
+                        if (kp->octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                    }
+                    if (!(fabsf(kp->x - q[iMP].x) < rad && fabsf(kp->y - q[iMP].y) < rad)) continue;
+                    if (occ[idx]) continue;                                       /* :90-92 */
+                    if (u_right && u_right[idx] > 0) {
+                        const float er = fabsf(q[iMP].xr - u_right[idx]);
+                        if (er > r * scale_factors[nPredictedLevel]) continue;
+                    }
+                    const int dist = oc_descriptor_distance(qdesc + 32 * (size_t)iMP, desc + 32 * (size_t)idx);
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kp->octave; bestIdx = idx; }
+                    else if (dist < bestDist2) { bestLevel2 = kp->octave; bestDist2 = dist; }
+                }
+            }
+        if (bestDist <= 100) {                                                    /* TH_HIGH */
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            match[bestIdx] = iMP;                                                 /* F.mvpMapPoints[bestIdx] = pMP */
+            occ[bestIdx] = (qflags[iMP] & 2) != 0;
+            nmatches++;
+        }
+    }
+    oc_grid_free(&g); free(occ);
+    return nmatches;
+}
+
+/* MapPoint::PredictScale (MapPoint.cc:407-422); `log` resolves to std::log(float) because KeyFrame.h pulls in DBoW2's
+ * global `using namespace std` (TemplatedVocabulary.h:36), so the expression is evaluated in f32. */
+int oc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int nlevels)
+{
+    const float ratio = max_distance / current_dist;
+    int nScale = (int)ceilf(logf(ratio) / log_scale_factor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= nlevels) nScale = nlevels - 1;
+    return nScale;
+}
+
+/* The search half of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (ORBmatcher.cc:918-1092; mode 0) and of
+ * Fuse(KeyFrame*, cv::Mat Scw, ...) (:1094-1236; mode 1, Rcw / tcw / Ow already taken out of Scw by the caller as
+ * :1101-1106 do). cv::Mat arithmetic restated from OpenCV 4.13: `Rcw*p3Dw + tcw` is one f32 gemm (products summed left
+ * to right, addend last), cv::norm / Mat::dot of 3-vectors accumulate in f64 in element order.
+ * cam = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY). pt_dist[i] = (GetMinDistanceInvariance,
+ * GetMaxDistanceInvariance, mfMaxDistance). pt_flags bit 0: the point is non-NULL, not bad and not already in the keyframe.
+ * best_idx[i] = keyframe feature to fuse with (bestDist <= TH_LOW) or -1; best_dist[i] = bestDist. Returns nFused. */
+int oc_fuse_search(const OcKeyPoint* kps, const uint8_t* desc, int n, const float* u_right,
+                   const float* Tcw12, const float* Ow3, const float* cam9, const float* scale_factors,
+                   const float* inv_level_sigma2, int nlevels, float log_scale_factor,
+                   const float* pt_xyz, const float* pt_normal, const float* pt_dist, const uint8_t* pt_desc,
+                   const uint8_t* pt_flags, int npts, float th, int mode, int32_t* best_idx, int32_t* best_dist)
+{
+    const float fx = cam9[0], fy = cam9[1], cx = cam9[2], cy = cam9[3], bf = cam9[4];
+    const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
+    const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
+    OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);
+    int nFused = 0;
+    for (int i = 0; i < npts; i++) {
+        int bestDist = mode == 0 ? 256 : INT_MAX, bestIdx = -1;
+        best_idx[i] = -1; best_dist[i] = bestDist;
+        if (!(pt_flags[i] & 1)) continue;
+        const float X = pt_xyz[3 * i], Y = pt_xyz[3 * i + 1], Z = pt_xyz[3 * i + 2];
+        float c3[3];
+        for (int r = 0; r < 3; r++) {
+            float s = Tcw12[3 * r] * X;
+            s = s + Tcw12[3 * r + 1] * Y;
+            s = s + Tcw12[3 * r + 2] * Z;
+            c3[r] = s + Tcw12[9 + r];
+        }
+        if (c3[2] < 0.0f) continue;
+        const float invz = mode == 0 ? 1 / c3[2] : (float)(1.0 / c3[2]);          /* :954 / :1146 */
+        const float x = c3[0] * invz, y = c3[1] * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!(u >= mnMinX && u < mnMaxX && v >= mnMinY && v < mnMaxY)) continue;  /* KeyFrame::IsInImage */
+        const float ur = u - bf * invz;
+        const float maxDistance = pt_dist[3 * i + 1], minDistance = pt_dist[3 * i];
+        const float PO[3] = {X - Ow3[0], Y - Ow3[1], Z - Ow3[2]};
+        double s2 = 0.0;
+        for (int k = 0; k < 3; k++) s2 += (double)PO[k] * (double)PO[k];
+        const float dist3D = (float)sqrt(s2);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        double dot = 0.0;
+        for (int k = 0; k < 3; k++) dot += (double)PO[k] * (double)pt_normal[3 * i + k];
+        if (dot < 0.5 * dist3D) continue;
+        const int nPredictedLevel = oc_predict_scale(pt_dist[3 * i + 2], dist3D, log_scale_factor, nlevels);
+        const float radius = th * scale_factors[nPredictedLevel];
+        int x0, x1, y0, y1;
+        if (!oc_grid_window(u, v, radius, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        for (int ix = x0; ix <= x1; ix++)
+            for (int iy = y0; iy <= y1; iy++) {
+                const int c = ix * FRAME_GRID_ROWS + iy;
+                for (int j = g.cnt[c]; j < g.cnt[c + 1]; j++) {
+                    const int idx = g.tab[j];
+                    const OcKeyPoint* kp = &kps[idx];
+                    if (!(fabsf(kp->x - u) < radius && fabsf(kp->y - v) < radius)) continue;   /* KeyFrame::GetFeaturesInArea */
+                    const int kpLevel = kp->octave;
+                    if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+                    if (mode == 0) {
+                        if (u_right && u_right[idx] >= 0) {
+                            const float ex = u - kp->x, ey = v - kp->y, er = ur - u_right[idx];
+                            const float e2 = ex * ex + ey * ey + er * er;
+                            if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+                        } else {
+                            const float ex = u - kp->x, ey = v - kp->y;
+                            const float e2 = ex * ex + ey * ey;
+                            if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+                        }
+                    }
+                    const int dist = oc_descriptor_distance(pt_desc + 32 * (size_t)i, desc + 32 * (size_t)idx);
+                    if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+                }
+            }
+        best_dist[i] = bestDist;
+        if (bestDist <= 50) { best_idx[i] = bestIdx; nFused++; }                   /* TH_LOW */
+    }
+    oc_grid_free(&g);
+    return nFused;
+}
+
+/* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:738-916). skip1 / skip2: the feature already has a map point
+ * (GetMapPoint != NULL). u_right1 / u_right2: mvuRight (NULL = monocular keyframes, i.e. all -1). F12 row-major 3x3.
+ * pose2 = (R2w row-major 9, t2w 3), Cw1 = pKF1->GetCameraCenter(), K2 = (fx, fy, cx, cy) of pKF2.
+ * Note that the reference never sets vbMatched2, so several features of keyframe 1 may share one of keyframe 2.
+ * match12[idx1] = idx2 or -1 (vMatchedPairs = the non-negative entries in ascending idx1). Returns nmatches. */
+int oc_search_for_triangulation(const int32_t* fv1_node, const int32_t* fv1_off, const int32_t* fv1_feat, int nfv1,
+                                const int32_t* fv2_node, const int32_t* fv2_off, const int32_t* fv2_feat, int nfv2,
+                                const OcKeyPoint* kps1, const uint8_t* desc1, const uint8_t* skip1, const float* u_right1, int n1,
+                                const OcKeyPoint* kps2, const uint8_t* desc2, const uint8_t* skip2, const float* u_right2, int n2,
+                                const float* F12, const float* Cw1, const float* pose2, const float* K2,
+                                const float* scale_factors2, const float* level_sigma2_2,
+                                int only_stereo, int check_orientation, int32_t* match12)
+{
+    (void)n2;
+    float C2[3];
+    for (int r = 0; r < 3; r++) {
+        float s = pose2[3 * r] * Cw1[0];
+        s = s + pose2[3 * r + 1] * Cw1[1];
+        s = s + pose2[3 * r + 2] * Cw1[2];
+        C2[r] = s + pose2[9 + r];
+    }
+    const float invz = 1.0f / C2[2];
+    const float ex = K2[0] * C2[0] * invz + K2[2];
+    const float ey = K2[1] * C2[1] * invz + K2[3];
+    int nmatches = 0, nh = 0, count[HISTO_LENGTH] = {0};
+    int* hist_idx = (int*)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1)), * hist_bin = (int*)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1));
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    int a = 0, b = 0;
+    while (a < nfv1 && b < nfv2) {
+        if (fv1_node[a] == fv2_node[b]) {
+            for (int i1 = fv1_off[a]; i1 < fv1_off[a + 1]; i1++) {
+                const int idx1 = fv1_feat[i1];
+                if (skip1 && skip1[idx1]) continue;
+                const int bStereo1 = u_right1 ? u_right1[idx1] >= 0 : 0;
+                if (only_stereo && !bStereo1) continue;
+                const OcKeyPoint* kp1 = &kps1[idx1];
+                int bestDist = 50, bestIdx2 = -1;                                 /* TH_LOW */
+                for (int i2 = fv2_off[b]; i2 < fv2_off[b + 1]; i2++) {
+                    const int idx2 = fv2_feat[i2];
+                    if (skip2 && skip2[idx2]) continue;
+                    const int bStereo2 = u_right2 ? u_right2[idx2] >= 0 : 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = oc_descriptor_distance(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (dist > 50 || dist > bestDist) continue;
+                    const OcKeyPoint* kp2 = &kps2[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2->x, distey = ey - kp2->y;
+                        if (distex * distex + distey * distey < 100 * scale_factors2[kp2->octave]) continue;
+                    }
+                    /* CheckDistEpipolarLine (:153-173) */
+                    const float fa = kp1->x * F12[0] + kp1->y * F12[3] + F12[6];
+                    const float fb = kp1->x * F12[1] + kp1->y * F12[4] + F12[7];
+                    const float fc = kp1->x * F12[2] + kp1->y * F12[5] + F12[8];
+                    const float num = fa * kp2->x + fb * kp2->y + fc;
+                    const float den = fa * fa + fb * fb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * level_sigma2_2[kp2->octave]) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (check_orientation) {
+                        const int bin = rot_bin(kp1->angle, kps2[bestIdx2].angle);
+                        hist_idx[nh] = idx1; hist_bin[nh] = bin; nh++; count[bin]++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (fv1_node[a] < fv2_node[b]) a++;
+        else b++;
+    }
+    if (check_orientation) {
+        int i1, i2, i3;
+        three_maxima(count, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int t = 0; t < nh; t++)
+            if (hist_bin[t] != i1 && hist_bin[t] != i2 && hist_bin[t] != i3) { match12[hist_idx[t]] = -1; nmatches--; }
+    }
+    free(hist_idx); free(hist_bin);
     return nmatches;
 }

@@ -126,6 +126,29 @@ int   oc_search_by_projection_frame(const OcKeyPoint* cur_kps, const uint8_t* cu
                                     const uint8_t* last_flags, int n_last, float th, int mode, int check_orientation,
                                     int32_t* match_cur);
 
+/* ---- the remaining window / BoW matchers of ORBmatcher; see the definitions in orb_oracle.c for argument meaning.
+ *      Direct restatements, cv::Mat arithmetic as pinned for oc_search_by_projection_frame; NOT pinned by oracle/_ref
+ *      (ORBmatcher.cc needs the whole SLAM library). ---- */
+typedef struct { float x, y, xr, view_cos; int32_t level; } OcTrackQuery;
+int   oc_search_local_points(const OcKeyPoint* kps, const uint8_t* desc, int n, const float* u_right, const uint8_t* occupied,
+                             const float* bounds4, const float* scale_factors, int nlevels,
+                             const OcTrackQuery* q, const uint8_t* qdesc, const uint8_t* qflags, int nq,
+                             float th, float nnratio, int32_t* match);          /* ORBmatcher.cc:46-142 */
+int   oc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int nlevels);   /* MapPoint.cc:407-422 */
+int   oc_fuse_search(const OcKeyPoint* kps, const uint8_t* desc, int n, const float* u_right,
+                     const float* Tcw12, const float* Ow3, const float* cam9, const float* scale_factors,
+                     const float* inv_level_sigma2, int nlevels, float log_scale_factor,
+                     const float* pt_xyz, const float* pt_normal, const float* pt_dist, const uint8_t* pt_desc,
+                     const uint8_t* pt_flags, int npts, float th, int mode, int32_t* best_idx, int32_t* best_dist);
+                                                                                /* ORBmatcher.cc:918-1092, 1094-1236 */
+int   oc_search_for_triangulation(const int32_t* fv1_node, const int32_t* fv1_off, const int32_t* fv1_feat, int nfv1,
+                                  const int32_t* fv2_node, const int32_t* fv2_off, const int32_t* fv2_feat, int nfv2,
+                                  const OcKeyPoint* kps1, const uint8_t* desc1, const uint8_t* skip1, const float* u_right1, int n1,
+                                  const OcKeyPoint* kps2, const uint8_t* desc2, const uint8_t* skip2, const float* u_right2, int n2,
+                                  const float* F12, const float* Cw1, const float* pose2, const float* K2,
+                                  const float* scale_factors2, const float* level_sigma2_2,
+                                  int only_stereo, int check_orientation, int32_t* match12);   /* ORBmatcher.cc:738-916 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,15 @@ def lib():
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_window_top2.argtypes = [C.c_void_p, u8p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                        C.c_void_p, u8p, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int]
+        L.orbx_search_local_points.argtypes = [C.c_void_p, f32p, f32p, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.orbx_search_local_points_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
+        L.orbx_fuse_search.argtypes = [C.c_void_p, f32p, f32p, f32p, C.c_int, C.c_float, C.c_int]
+        L.orbx_fuse_search_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.orbx_search_for_triangulation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, f32p, f32p, f32p, C.c_int, C.c_int,
+                                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbx_search_for_triangulation_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [f32p, f32p, C.c_int, C.c_int,
+                                                                                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbx_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
         L.orbx_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
         L.orbx_peer_hamming_top2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
@@ -450,6 +459,69 @@ def search_by_projection_frame(cur_kps, cur_desc, cur_u_right, cur_occupied, Tcw
     return int(nm[0]), match[:len(cur_kps)]
 
 
+TRACKQ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4")])
+
+
+class OrbxLocalPointsFrame(C.Structure):
+    """include/orbx.h OrbxLocalPointsFrame"""
+    _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("u_right", C.c_void_p), ("occupied", C.c_void_p),
+                ("n", C.c_int32), ("queries", C.c_void_p), ("query_descriptors", C.c_void_p), ("query_flags", C.c_void_p),
+                ("nq", C.c_int32), ("match", C.c_void_p), ("nmatches", C.c_void_p)]
+
+
+def search_local_points(kps, desc, u_right, occupied, bounds4, scale_factors, queries, query_desc, query_flags, th, nnratio=0.8,
+                        device: int = 0):
+    """ORBmatcher(nnratio).SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:46-142) -> (nmatches, match);
+    match[k] = index into vpMapPoints that keypoint k holds after the call, -1 = untouched."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    b4 = np.ascontiguousarray(bounds4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    q = np.ascontiguousarray(queries, TRACKQ_DTYPE); qd = np.ascontiguousarray(query_desc, np.uint8)
+    qf = np.ascontiguousarray(query_flags, np.uint8)
+    match = np.zeros(max(len(kps), 1), np.int32); nm = np.zeros(1, np.int32)
+    F = OrbxLocalPointsFrame()
+    F.keypoints = kps.ctypes.data; F.descriptors = desc.ctypes.data
+    F.u_right = None if ur is None else ur.ctypes.data; F.occupied = None if occ is None else occ.ctypes.data; F.n = len(kps)
+    F.queries = q.ctypes.data; F.query_descriptors = qd.ctypes.data; F.query_flags = qf.ctypes.data; F.nq = len(q)
+    F.match = match.ctypes.data; F.nmatches = nm.ctypes.data
+    _ck(lib().orbx_search_local_points(C.byref(F), b4.ctypes.data_as(f32p), sf.ctypes.data_as(f32p), len(sf), th, nnratio, device))
+    return int(nm[0]), match[:len(kps)]
+
+
+class OrbxFuseJob(C.Structure):
+    """include/orbx.h OrbxFuseJob"""
+    _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("u_right", C.c_void_p), ("n", C.c_int32),
+                ("Tcw", C.c_float * 12), ("Ow", C.c_float * 3),
+                ("pt_xyz", C.c_void_p), ("pt_normal", C.c_void_p), ("pt_dist", C.c_void_p), ("pt_descriptors", C.c_void_p),
+                ("pt_flags", C.c_void_p), ("npts", C.c_int32), ("th", C.c_float), ("mode", C.c_int32),
+                ("best_idx", C.c_void_p), ("best_dist", C.c_void_p), ("nfused", C.c_void_p)]
+
+
+def fuse_search(kps, desc, u_right, Tcw12, Ow3, cam9, scale_factors, inv_level_sigma2, log_scale_factor, pt_xyz, pt_normal,
+                pt_dist, pt_desc, pt_flags, th, mode=0, device: int = 0):
+    """Search half of ORBmatcher::Fuse (ORBmatcher.cc:918-1092 mode 0, :1094-1236 mode 1) -> (nFused, best_idx, best_dist)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = np.ascontiguousarray(pt_normal, np.float32)
+    dst = np.ascontiguousarray(pt_dist, np.float32); pd = np.ascontiguousarray(pt_desc, np.uint8)
+    pf = np.ascontiguousarray(pt_flags, np.uint8)
+    npts = len(pf)
+    bi = np.zeros(max(npts, 1), np.int32); bd = np.zeros(max(npts, 1), np.int32); nf = np.zeros(1, np.int32)
+    J = OrbxFuseJob()
+    J.keypoints = kps.ctypes.data; J.descriptors = desc.ctypes.data; J.u_right = None if ur is None else ur.ctypes.data; J.n = len(kps)
+    J.Tcw = (C.c_float * 12)(*np.asarray(Tcw12, np.float32).ravel().tolist())
+    J.Ow = (C.c_float * 3)(*np.asarray(Ow3, np.float32).ravel().tolist())
+    J.pt_xyz = xyz.ctypes.data; J.pt_normal = nrm.ctypes.data; J.pt_dist = dst.ctypes.data; J.pt_descriptors = pd.ctypes.data
+    J.pt_flags = pf.ctypes.data; J.npts = npts; J.th = th; J.mode = mode
+    J.best_idx = bi.ctypes.data; J.best_dist = bd.ctypes.data; J.nfused = nf.ctypes.data
+    _ck(lib().orbx_fuse_search(C.byref(J), cam.ctypes.data_as(f32p), sf.ctypes.data_as(f32p), s2.ctypes.data_as(f32p), len(sf),
+                               float(log_scale_factor), device))
+    return int(nf[0]), bi[:npts], bd[:npts]
+
+
 class ORBVocabulary:
     """DBoW2 vocabulary on the GPU (include/ORBVocabulary.h: TemplatedVocabulary<FORB::TDescriptor, FORB>).
     parent / is_leaf / desc / weight: one entry per non-root node in ORBvoc.txt order (loadFromTextFile)."""
@@ -523,6 +595,26 @@ class ORBVocabulary:
         _ck(self._L.orbx_search_by_bow_kf(self._h, kps1.ctypes.data, desc1.ctypes.data, len(kps1), None if v1 is None else v1.ctypes.data,
                                           kps2.ctypes.data, desc2.ctypes.data, len(kps2), None if v2 is None else v2.ctypes.data,
                                           levelsup, nnratio, int(check_orientation), match.ctypes.data, C.addressof(nm)))
+        return nm.value, match[:len(kps1)]
+
+    def search_for_triangulation(self, kps1, desc1, has_mp1, u_right1, kps2, desc2, has_mp2, u_right2, geom28, scale_factors,
+                                 level_sigma2, levelsup=4, only_stereo=False, check_orientation=True):
+        """ORBmatcher(0.6, checkOri).SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (ORBmatcher.cc:738-916)
+        -> (nmatches, match12); vMatchedPairs = [(i, match12[i]) for i where match12[i] >= 0]."""
+        kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+        desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        m1 = None if has_mp1 is None else np.ascontiguousarray(has_mp1, np.uint8)
+        m2 = None if has_mp2 is None else np.ascontiguousarray(has_mp2, np.uint8)
+        r1 = None if u_right1 is None else np.ascontiguousarray(u_right1, np.float32)
+        r2 = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+        g = np.ascontiguousarray(geom28, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        s2 = np.ascontiguousarray(level_sigma2, np.float32)
+        match = np.zeros(max(len(kps1), 1), np.int32); nm = C.c_int32(0)
+        p = lambda a: None if a is None else a.ctypes.data
+        _ck(self._L.orbx_search_for_triangulation(self._h, kps1.ctypes.data, desc1.ctypes.data, len(kps1), p(m1), p(r1), kps2.ctypes.data,
+                                                  desc2.ctypes.data, len(kps2), p(m2), p(r2), g.ctypes.data_as(f32p),
+                                                  sf.ctypes.data_as(f32p), s2.ctypes.data_as(f32p), len(sf), levelsup, int(only_stereo),
+                                                  int(check_orientation), match.ctypes.data, C.addressof(nm)))
         return nm.value, match[:len(kps1)]
 
     def search_by_bow_device(self, npairs, d_kf_frame, d_f_frame, d_kps, d_desc, d_kf_valid, nnratio, check_orientation, d_match,

@@ -308,6 +308,103 @@ __global__ void __launch_bounds__(128) bow_match_kernel(OrbxBowOut O, OrbxBowMat
     }
 }
 
+// ------------------------------------------------------------------------------------------- SearchForTriangulation
+// ORBmatcher::SearchForTriangulation (ORBmatcher.cc:738-916): features WITHOUT a map point of two keyframes, matched inside
+// common FeatureVector nodes under the epipolar constraint of F12. The reference never sets vbMatched2, so a keyframe-1
+// feature's result depends on nothing but the candidates themselves: the winner is the candidate with the smallest
+// distance <= TH_LOW among those that pass the stateless gates (map-point / stereo flags, distance to the epipole,
+// CheckDistEpipolarLine :153-173), and the LAST such candidate in list order on ties (`dist > bestDist` skips, an equal
+// distance replaces). One warp per node of keyframe 1, candidates over the lanes, key = dist << 16 | (0xffff - position).
+__global__ void __launch_bounds__(128) bow_triangulation_kernel(OrbxBowOut O, OrbxBowTriArgs T, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int pair = blockIdx.y;
+    const int f1 = T.kf1_frame[pair], f2 = T.kf2_frame[pair];
+    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (a >= O.n_fv[f1]) return;
+    const int node = O.fv_node[(size_t)f1 * cap + a];
+    const int* node2 = O.fv_node + (size_t)f2 * cap;
+    int lo = 0, hi = O.n_fv[f2];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (node2[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= O.n_fv[f2] || node2[lo] != node) return;
+    const int* off1 = O.fv_off + (size_t)f1 * (cap + 1);
+    const int* off2 = O.fv_off + (size_t)f2 * (cap + 1);
+    const int* feat1 = O.fv_feat + (size_t)f1 * cap;
+    const int* feat2 = O.fv_feat + (size_t)f2 * cap;
+    const int k0 = off1[a], k1 = off1[a + 1], j0 = off2[lo], j1 = off2[lo + 1];
+    const uint8_t* desc1 = T.desc + (size_t)f1 * cap * 32;
+    const uint8_t* desc2 = T.desc + (size_t)f2 * cap * 32;
+    const OrbxKp28* kp1s = T.kps + (size_t)f1 * cap;
+    const OrbxKp28* kp2s = T.kps + (size_t)f2 * cap;
+    const uint8_t* mp1 = T.has_mp ? T.has_mp + (size_t)f1 * cap : nullptr;
+    const uint8_t* mp2 = T.has_mp ? T.has_mp + (size_t)f2 * cap : nullptr;
+    const float* ur1 = T.u_right ? T.u_right + (size_t)f1 * cap : nullptr;
+    const float* ur2 = T.u_right ? T.u_right + (size_t)f2 * cap : nullptr;
+    const float* g = T.geom + (size_t)pair * 28;                             // F12 (9), Cw1 (3), R2w (9), t2w (3), K2 (4)
+    // epipole of camera 1 in image 2 (:744-754): C2 = R2w*Cw + t2w as one f32 gemm, invz = 1.0f / C2.z
+    float C2[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float s = __fmul_rn(g[12 + 3 * r], g[9]);
+        s = __fadd_rn(s, __fmul_rn(g[12 + 3 * r + 1], g[10]));
+        s = __fadd_rn(s, __fmul_rn(g[12 + 3 * r + 2], g[11]));
+        C2[r] = __fadd_rn(s, g[21 + r]);
+    }
+    const float invz = __fdiv_rn(1.0f, C2[2]);
+    const float ex = __fadd_rn(__fmul_rn(__fmul_rn(g[24], C2[0]), invz), g[26]);
+    const float ey = __fadd_rn(__fmul_rn(__fmul_rn(g[25], C2[1]), invz), g[27]);
+    int* match = T.match + (size_t)pair * cap;
+    int* bin_of = T.bin_of + (size_t)pair * cap;
+    for (int ik = k0; ik < k1; ik++) {
+        const int idx1 = feat1[ik];
+        if (mp1 && mp1[idx1]) continue;                                       // warp-uniform
+        const bool stereo1 = ur1 ? ur1[idx1] >= 0.f : false;
+        if (T.only_stereo && !stereo1) continue;
+        const OrbxKp28 kp1 = kp1s[idx1];
+        // the epipolar line of kp1 in image 2
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g[0]), __fmul_rn(kp1.y, g[3])), g[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g[1]), __fmul_rn(kp1.y, g[4])), g[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g[2]), __fmul_rn(kp1.y, g[5])), g[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        const uint4* d1 = reinterpret_cast<const uint4*>(desc1 + (size_t)idx1 * 32);
+        const uint4 q0 = __ldg(d1), q1 = __ldg(d1 + 1);
+        unsigned best = 0xffffffffu;
+        for (int j = j0 + lane; j < j1; j += 32) {
+            const int idx2 = feat2[j];
+            if (mp2 && mp2[idx2]) continue;
+            const bool stereo2 = ur2 ? ur2[idx2] >= 0.f : false;
+            if (T.only_stereo && !stereo2) continue;
+            const uint4* d2 = reinterpret_cast<const uint4*>(desc2 + (size_t)idx2 * 32);
+            const int dist = bow_dist(q0, q1, d2[0], d2[1]);
+            if (dist > T.th_low) continue;
+            const OrbxKp28 kp2 = kp2s[idx2];
+            if (!stereo1 && !stereo2) {
+                const float dx = __fsub_rn(ex, kp2.x), dy = __fsub_rn(ey, kp2.y);
+                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, T.scale_factors[kp2.octave])) continue;
+            }
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+            if (den == 0.f) continue;
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            if (!((double)dsqr < __dmul_rn(3.84, (double)T.level_sigma2[kp2.octave]))) continue;
+            best = min(best, ((unsigned)dist << 16) | (unsigned)(0xffff - (j - j0)));
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != 0xffffffffu && lane == 0) {
+            const int idx2 = feat2[j0 + (0xffff - (int)(best & 0xffffu))];
+            match[idx1] = idx2;
+            if (T.check_orientation) {
+                float rot = __fsub_rn(kp1.angle, kp2s[idx2].angle);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+                if (bin == 30) bin = 0;
+                bin_of[idx1] = bin;
+                atomicAdd(T.hist + pair * 32 + bin, 1);
+            }
+            atomicAdd(T.nmatches + pair, 1);
+        }
+    }
+}
+
 // ComputeThreeMaxima + rejection of the matches outside the three dominant rotation bins (ORBmatcher.cc:296-322, 1797-1839)
 __global__ void __launch_bounds__(256) bow_rotation_kernel(OrbxBowMatchArgs A, const int* __restrict__ d_n, int cap)
 {
@@ -368,6 +465,20 @@ void orbx_launch_bow_score(const OrbxBowOut& O, int cap, const int* d_qa, const 
 {
     if (npairs <= 0) return;
     bow_score_l1_kernel<<<(npairs + 3) / 4, 128, 0, st>>>(O, cap, d_qa, d_qb, npairs, d_score);
+}
+
+void orbx_launch_bow_triangulation(const OrbxBowOut& O, const OrbxBowTriArgs& T, int* d_taken, const int* d_n, int cap, int npairs,
+                                   cudaStream_t st)
+{
+    if (npairs <= 0 || cap <= 0) return;
+    OrbxBowMatchArgs A = {};                                                 // init / rotation kernels of the KeyFrame-KeyFrame form
+    A.kf_frame = T.kf1_frame; A.f_frame = T.kf2_frame; A.kf_mode = 1; A.check_orientation = T.check_orientation;
+    A.match = T.match; A.bin_of = T.bin_of; A.taken = d_taken; A.hist = T.hist; A.nmatches = T.nmatches;
+    const size_t tot = (size_t)npairs * std::max(cap, 32);
+    bow_match_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, cap, npairs);
+    dim3 g((cap + 3) / 4, npairs);
+    bow_triangulation_kernel<<<g, 128, 0, st>>>(O, T, cap);
+    if (T.check_orientation) bow_rotation_kernel<<<npairs, 256, 0, st>>>(A, d_n, cap);
 }
 
 void orbx_launch_bow_match(const OrbxBowOut& O, const OrbxBowMatchArgs& A, const int* d_n, int cap, int npairs, cudaStream_t st)

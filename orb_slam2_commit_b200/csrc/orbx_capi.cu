@@ -1652,3 +1652,288 @@ extern "C" int orbx_search_by_bow_kf(orbx_vocabulary* v, const OrbxKeyPoint* kf1
     return search_by_bow_host(v, kf1_keypoints, kf1_descriptors, n1, valid1, kf2_keypoints, kf2_descriptors, n2, valid2, 1, levelsup,
                               nnratio, check_orientation, match12, nmatches);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th) (ORBmatcher.cc:46-142) — orbx_match.cu
+extern "C" int orbx_search_local_points_device(const OrbxLocalPointsFrame* frames, int nframes, const float* bounds4,
+                                               const float* scale_factors, int nlevels, float th, float nnratio, int device,
+                                               void* cuda_stream)
+{
+    if (nframes <= 0) return ORBX_OK;
+    if (!frames || !bounds4 || !scale_factors || nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    keep_mempool(device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    size_t tot_q = 0; int max_n = 0;
+    for (int p = 0; p < nframes; p++) {
+        const OrbxLocalPointsFrame& f = frames[p];
+        if (f.n < 0 || f.nq < 0 || !f.match || !f.nmatches) return fail(ORBX_ERR_INVALID, "bad frame");
+        if (f.n > 10000) return fail(ORBX_ERR_UNSUPPORTED, "more than 10000 keypoints in the frame");
+        if ((f.n > 0 && (!f.keypoints || !f.descriptors)) || (f.nq > 0 && (!f.queries || !f.query_descriptors || !f.query_flags)))
+            return fail(ORBX_ERR_INVALID, "NULL array in frame");
+        tot_q += (size_t)f.nq; max_n = std::max(max_n, f.n);
+    }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_f = al((size_t)nframes * sizeof(OrbxLocalFrameDev)), b_a = al(std::max<size_t>(tot_q, 1) * 4), b_sf = al((size_t)nlevels * 4);
+    uint8_t* pool = nullptr;
+    CK(cudaMallocAsync(&pool, b_f + b_a + b_sf, st));
+    int* d_a = (int*)(pool + b_f);
+    float* d_sf = (float*)(pool + b_f + b_a);
+    std::vector<OrbxLocalFrameDev> hf(nframes);
+    size_t off = 0;
+    for (int p = 0; p < nframes; p++) {
+        const OrbxLocalPointsFrame& f = frames[p];
+        OrbxLocalFrameDev& d = hf[p];
+        d.kps = (const OrbxKp28*)f.keypoints; d.desc = f.descriptors; d.u_right = f.u_right; d.occupied = f.occupied; d.n = f.n;
+        d.q = (const OrbxTrackQueryDev*)f.queries; d.qdesc = f.query_descriptors; d.qflags = f.query_flags; d.nq = f.nq;
+        d.match = f.match; d.nmatches = f.nmatches; d.assign = d_a + off; off += (size_t)f.nq;
+    }
+    cudaError_t e;
+    do {
+        if ((e = cudaMemcpyAsync(pool, hf.data(), (size_t)nframes * sizeof(OrbxLocalFrameDev), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_sf, scale_factors, (size_t)nlevels * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        orbx_launch_local_points((const OrbxLocalFrameDev*)pool, nframes, max_n, bounds4, d_sf, nlevels, th, nnratio, st);
+        e = cudaGetLastError();
+    } while (0);
+    cudaFreeAsync(pool, st);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+// upload helper of the one-shot host forms below: arrays are packed into one stream-ordered allocation
+namespace {
+struct HostPack {
+    std::vector<size_t> off; size_t tot = 0; uint8_t* pool = nullptr;
+    size_t add(size_t bytes) { off.push_back(tot); tot += (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; return off.size() - 1; }
+    uint8_t* at(size_t i) const { return pool + off[i]; }
+};
+}
+
+extern "C" int orbx_search_local_points(const OrbxLocalPointsFrame* frame, const float* bounds4, const float* scale_factors,
+                                        int nlevels, float th, float nnratio, int device)
+{
+    if (!frame || !frame->match || !frame->nmatches) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    const int n = frame->n, nq = frame->nq;
+    if (n < 0 || nq < 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    keep_mempool(device);
+    HostPack P;
+    const size_t i_kp = P.add((size_t)n * 28), i_d = P.add((size_t)n * 32), i_ur = P.add((size_t)n * 4), i_oc = P.add(n),
+                 i_q = P.add((size_t)nq * sizeof(OrbxTrackQuery)), i_qd = P.add((size_t)nq * 32), i_qf = P.add(nq),
+                 i_m = P.add((size_t)n * 4), i_nm = P.add(4);
+    CK(cudaMallocAsync(&P.pool, P.tot, 0));
+    OrbxLocalPointsFrame d = *frame;
+    cudaError_t e = cudaSuccess;
+    int rc = ORBX_OK;
+    do {
+        auto up = [&](size_t i, const void* src, size_t bytes) { return (!src || !bytes) ? cudaSuccess : cudaMemcpyAsync(P.at(i), src, bytes, cudaMemcpyHostToDevice, 0); };
+        if ((e = up(i_kp, frame->keypoints, (size_t)n * 28)) != cudaSuccess) break;
+        if ((e = up(i_d, frame->descriptors, (size_t)n * 32)) != cudaSuccess) break;
+        if ((e = up(i_ur, frame->u_right, (size_t)n * 4)) != cudaSuccess) break;
+        if ((e = up(i_oc, frame->occupied, (size_t)n)) != cudaSuccess) break;
+        if ((e = up(i_q, frame->queries, (size_t)nq * sizeof(OrbxTrackQuery))) != cudaSuccess) break;
+        if ((e = up(i_qd, frame->query_descriptors, (size_t)nq * 32)) != cudaSuccess) break;
+        if ((e = up(i_qf, frame->query_flags, (size_t)nq)) != cudaSuccess) break;
+        d.keypoints = (const OrbxKeyPoint*)P.at(i_kp); d.descriptors = P.at(i_d);
+        d.u_right = frame->u_right ? (const float*)P.at(i_ur) : nullptr; d.occupied = frame->occupied ? P.at(i_oc) : nullptr;
+        d.queries = (const OrbxTrackQuery*)P.at(i_q); d.query_descriptors = P.at(i_qd); d.query_flags = P.at(i_qf);
+        d.match = (int32_t*)P.at(i_m); d.nmatches = (int32_t*)P.at(i_nm);
+        rc = orbx_search_local_points_device(&d, 1, bounds4, scale_factors, nlevels, th, nnratio, device, nullptr);
+        if (rc != ORBX_OK) break;
+        if (n > 0 && (e = cudaMemcpy(frame->match, P.at(i_m), (size_t)n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        e = cudaMemcpy(frame->nmatches, P.at(i_nm), 4, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFreeAsync(P.pool, 0);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ORBmatcher::Fuse, search half (ORBmatcher.cc:918-1092, 1094-1236) — orbx_match.cu
+// MapPoint::PredictScale (MapPoint.cc:407-422) is `ceil(logf(ratio) / mfLogScaleFactor)` clamped to [0, nlevels-1]. The
+// device takes it from a threshold table instead of its own logf: level_ratio[n] = the smallest positive float whose
+// predicted level exceeds n, found by bisection over the float bit patterns with the HOST's logf (monotonic), so the
+// device level is the host libm's level for every ratio.
+static void predict_scale_thresholds(float log_scale_factor, int nlevels, float* level_ratio)
+{
+    for (int n = 0; n < ORBX_MAX_LEVELS; n++) level_ratio[n] = INFINITY;
+    auto exceeds = [&](uint32_t bits, int n) { float r; memcpy(&r, &bits, 4); return logf(r) / log_scale_factor > (float)n; };
+    for (int n = 0; n + 1 < nlevels; n++) {
+        uint32_t lo = 1u, hi = 0x7f7fffffu;                   // smallest denormal .. FLT_MAX
+        if (!exceeds(hi, n)) continue;
+        while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (exceeds(mid, n)) hi = mid; else lo = mid + 1; }
+        memcpy(&level_ratio[n], &lo, 4);
+    }
+}
+
+extern "C" int orbx_fuse_search_device(const OrbxFuseJob* jobs, int njobs, const float* camera9, const float* scale_factors,
+                                       const float* inv_level_sigma2, int nlevels, float log_scale_factor, int device,
+                                       void* cuda_stream)
+{
+    if (njobs <= 0) return ORBX_OK;
+    if (!jobs || !camera9 || !scale_factors || !inv_level_sigma2 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !(log_scale_factor > 0.f))
+        return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    keep_mempool(device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int max_n = 0;
+    std::vector<OrbxFuseDev> hj(njobs);
+    for (int p = 0; p < njobs; p++) {
+        const OrbxFuseJob& j = jobs[p];
+        if (j.n < 0 || j.npts < 0 || !j.nfused || (j.npts > 0 && (!j.best_idx || !j.best_dist)) || j.mode < 0 || j.mode > 1)
+            return fail(ORBX_ERR_INVALID, "bad job");
+        if (j.n > 10000) return fail(ORBX_ERR_UNSUPPORTED, "more than 10000 keypoints in the keyframe");
+        if ((j.n > 0 && (!j.keypoints || !j.descriptors)) ||
+            (j.npts > 0 && (!j.pt_xyz || !j.pt_normal || !j.pt_dist || !j.pt_descriptors || !j.pt_flags))) return fail(ORBX_ERR_INVALID, "NULL array in job");
+        OrbxFuseDev& d = hj[p];
+        d.kps = (const OrbxKp28*)j.keypoints; d.desc = j.descriptors; d.u_right = j.u_right; d.n = j.n;
+        memcpy(d.Tcw, j.Tcw, sizeof d.Tcw); memcpy(d.Ow, j.Ow, sizeof d.Ow); d.th = j.th; d.mode = j.mode;
+        d.pt_xyz = j.pt_xyz; d.pt_normal = j.pt_normal; d.pt_dist = j.pt_dist; d.pt_desc = j.pt_descriptors; d.pt_flags = j.pt_flags;
+        d.npts = j.npts; d.best_idx = j.best_idx; d.best_dist = j.best_dist; d.nfound = j.nfused;
+        max_n = std::max(max_n, j.n);
+    }
+    OrbxFuseCam cam = {};
+    cam.fx = camera9[0]; cam.fy = camera9[1]; cam.cx = camera9[2]; cam.cy = camera9[3]; cam.bf = camera9[4];
+    cam.minX = camera9[5]; cam.maxX = camera9[6]; cam.minY = camera9[7]; cam.maxY = camera9[8]; cam.nlevels = nlevels;
+    for (int l = 0; l < nlevels; l++) { cam.scale_factors[l] = scale_factors[l]; cam.inv_level_sigma2[l] = inv_level_sigma2[l]; }
+    predict_scale_thresholds(log_scale_factor, nlevels, cam.level_ratio);
+    uint8_t* pool = nullptr;
+    CK(cudaMallocAsync(&pool, (size_t)njobs * sizeof(OrbxFuseDev), st));
+    cudaError_t e;
+    do {
+        if ((e = cudaMemcpyAsync(pool, hj.data(), (size_t)njobs * sizeof(OrbxFuseDev), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        orbx_launch_fuse_search((const OrbxFuseDev*)pool, njobs, max_n, cam, st);
+        e = cudaGetLastError();
+    } while (0);
+    cudaFreeAsync(pool, st);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_fuse_search(const OrbxFuseJob* job, const float* camera9, const float* scale_factors,
+                                const float* inv_level_sigma2, int nlevels, float log_scale_factor, int device)
+{
+    if (!job || !job->nfused) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    const int n = job->n, np = job->npts;
+    if (n < 0 || np < 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    keep_mempool(device);
+    HostPack P;
+    const size_t i_kp = P.add((size_t)n * 28), i_d = P.add((size_t)n * 32), i_ur = P.add((size_t)n * 4),
+                 i_x = P.add((size_t)np * 12), i_nr = P.add((size_t)np * 12), i_ds = P.add((size_t)np * 12), i_pd = P.add((size_t)np * 32),
+                 i_pf = P.add(np), i_bi = P.add((size_t)np * 4), i_bd = P.add((size_t)np * 4), i_nf = P.add(4);
+    CK(cudaMallocAsync(&P.pool, P.tot, 0));
+    OrbxFuseJob d = *job;
+    cudaError_t e = cudaSuccess;
+    int rc = ORBX_OK;
+    do {
+        auto up = [&](size_t i, const void* src, size_t bytes) { return (!src || !bytes) ? cudaSuccess : cudaMemcpyAsync(P.at(i), src, bytes, cudaMemcpyHostToDevice, 0); };
+        if ((e = up(i_kp, job->keypoints, (size_t)n * 28)) != cudaSuccess) break;
+        if ((e = up(i_d, job->descriptors, (size_t)n * 32)) != cudaSuccess) break;
+        if ((e = up(i_ur, job->u_right, (size_t)n * 4)) != cudaSuccess) break;
+        if ((e = up(i_x, job->pt_xyz, (size_t)np * 12)) != cudaSuccess) break;
+        if ((e = up(i_nr, job->pt_normal, (size_t)np * 12)) != cudaSuccess) break;
+        if ((e = up(i_ds, job->pt_dist, (size_t)np * 12)) != cudaSuccess) break;
+        if ((e = up(i_pd, job->pt_descriptors, (size_t)np * 32)) != cudaSuccess) break;
+        if ((e = up(i_pf, job->pt_flags, (size_t)np)) != cudaSuccess) break;
+        d.keypoints = (const OrbxKeyPoint*)P.at(i_kp); d.descriptors = P.at(i_d); d.u_right = job->u_right ? (const float*)P.at(i_ur) : nullptr;
+        d.pt_xyz = (const float*)P.at(i_x); d.pt_normal = (const float*)P.at(i_nr); d.pt_dist = (const float*)P.at(i_ds);
+        d.pt_descriptors = P.at(i_pd); d.pt_flags = P.at(i_pf);
+        d.best_idx = (int32_t*)P.at(i_bi); d.best_dist = (int32_t*)P.at(i_bd); d.nfused = (int32_t*)P.at(i_nf);
+        rc = orbx_fuse_search_device(&d, 1, camera9, scale_factors, inv_level_sigma2, nlevels, log_scale_factor, device, nullptr);
+        if (rc != ORBX_OK) break;
+        if (np > 0 && (e = cudaMemcpy(job->best_idx, P.at(i_bi), (size_t)np * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if (np > 0 && (e = cudaMemcpy(job->best_dist, P.at(i_bd), (size_t)np * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        e = cudaMemcpy(job->nfused, P.at(i_nf), 4, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFreeAsync(P.pool, 0);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchForTriangulation (ORBmatcher.cc:738-916) — orbx_bow.cu
+extern "C" int orbx_search_for_triangulation_device(orbx_vocabulary* v, int npairs, const int32_t* d_kf1_frame, const int32_t* d_kf2_frame,
+                                                    const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, const uint8_t* d_has_mp,
+                                                    const float* d_u_right, const float* d_geom, const float* scale_factors,
+                                                    const float* level_sigma2, int nlevels, int only_stereo, int check_orientation,
+                                                    int32_t* d_match12, int32_t* d_nmatches, void* cuda_stream)
+{
+    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (npairs <= 0) return ORBX_OK;
+    if (!d_kf1_frame || !d_kf2_frame || !d_keypoints || !d_descriptors || !d_geom || !scale_factors || !level_sigma2 || !d_match12 ||
+        !d_nmatches || nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(v->device));
+    const int cap = v->cap;
+    if ((size_t)npairs > v->mws_pairs || (size_t)cap != v->mws_cap) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(v->d_mws); v->d_mws = nullptr;
+        CK(cudaMalloc(&v->d_mws, (size_t)npairs * cap * 8 + (size_t)npairs * 32 * 4));
+        v->d_bin_of = (int*)v->d_mws; v->d_taken = v->d_bin_of + (size_t)npairs * cap; v->d_hist = v->d_taken + (size_t)npairs * cap;
+        v->mws_pairs = npairs; v->mws_cap = cap;
+    }
+    OrbxBowTriArgs T = {};
+    T.kf1_frame = d_kf1_frame; T.kf2_frame = d_kf2_frame; T.kps = (const OrbxKp28*)d_keypoints; T.desc = d_descriptors;
+    T.has_mp = d_has_mp; T.u_right = d_u_right; T.geom = d_geom;
+    for (int l = 0; l < nlevels; l++) { T.scale_factors[l] = scale_factors[l]; T.level_sigma2[l] = level_sigma2[l]; }
+    T.only_stereo = only_stereo; T.check_orientation = check_orientation; T.th_low = 50;   // ORBmatcher::TH_LOW
+    T.match = d_match12; T.bin_of = v->d_bin_of; T.hist = v->d_hist; T.nmatches = d_nmatches;
+    orbx_launch_bow_triangulation(v->O, T, v->d_taken, v->d_n, cap, npairs, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_search_for_triangulation(orbx_vocabulary* v, const OrbxKeyPoint* kf1_keypoints, const uint8_t* kf1_descriptors, int n1,
+                                             const uint8_t* has_mp1, const float* u_right1, const OrbxKeyPoint* kf2_keypoints,
+                                             const uint8_t* kf2_descriptors, int n2, const uint8_t* has_mp2, const float* u_right2,
+                                             const float* geom28, const float* scale_factors, const float* level_sigma2, int nlevels,
+                                             int levelsup, int only_stereo, int check_orientation, int32_t* match12, int32_t* nmatches)
+{
+    if (!v || n1 < 0 || n2 < 0 || !nmatches || (n1 > 0 && !match12) || !geom28) return fail(ORBX_ERR_INVALID, "bad argument");
+    if ((u_right1 == nullptr) != (u_right2 == nullptr) || (has_mp1 == nullptr) != (has_mp2 == nullptr))
+        return fail(ORBX_ERR_INVALID, "u_right / has_mp must be given for both keyframes or for neither");
+    *nmatches = 0;
+    for (int j = 0; j < n1; j++) match12[j] = -1;
+    if (n1 == 0 || n2 == 0) return ORBX_OK;
+    if (!kf1_keypoints || !kf1_descriptors || !kf2_keypoints || !kf2_descriptors) return fail(ORBX_ERR_INVALID, "NULL argument");
+    const int cap = std::max(n1, n2);
+    std::vector<uint8_t> desc((size_t)2 * cap * 32, 0);
+    memcpy(desc.data(), kf1_descriptors, (size_t)n1 * 32);
+    memcpy(desc.data() + (size_t)cap * 32, kf2_descriptors, (size_t)n2 * 32);
+    const int32_t counts[2] = {n1, n2};
+    int rc = orbx_bow_transform(v, desc.data(), counts, 2, cap, levelsup);
+    if (rc != ORBX_OK) return rc;
+    HostPack P;
+    const size_t i_kp = P.add((size_t)2 * cap * 28), i_d = P.add((size_t)2 * cap * 32), i_mp = P.add((size_t)2 * cap), i_ur = P.add((size_t)2 * cap * 4),
+                 i_g = P.add(28 * 4), i_m = P.add((size_t)cap * 4), i_idx = P.add(8), i_nm = P.add(4);
+    CK(cudaMalloc(&P.pool, P.tot));
+    cudaError_t e;
+    do {
+        const int32_t idx[2] = {0, 1};
+        if ((e = cudaMemset(P.pool, 0, P.tot)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(P.at(i_kp), kf1_keypoints, (size_t)n1 * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(P.at(i_kp) + (size_t)cap * 28, kf2_keypoints, (size_t)n2 * 28, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(P.at(i_d), desc.data(), desc.size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (has_mp1 && (e = cudaMemcpy(P.at(i_mp), has_mp1, (size_t)n1, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (has_mp2 && (e = cudaMemcpy(P.at(i_mp) + cap, has_mp2, (size_t)n2, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (u_right1 && (e = cudaMemcpy(P.at(i_ur), u_right1, (size_t)n1 * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (u_right2 && (e = cudaMemcpy(P.at(i_ur) + (size_t)cap * 4, u_right2, (size_t)n2 * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(P.at(i_g), geom28, 28 * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(P.at(i_idx), idx, 8, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        rc = orbx_search_for_triangulation_device(v, 1, (const int32_t*)P.at(i_idx), (const int32_t*)P.at(i_idx) + 1,
+                                                  (const OrbxKeyPoint*)P.at(i_kp), P.at(i_d), has_mp1 ? P.at(i_mp) : nullptr,
+                                                  u_right1 ? (const float*)P.at(i_ur) : nullptr, (const float*)P.at(i_g), scale_factors,
+                                                  level_sigma2, nlevels, only_stereo, check_orientation, (int32_t*)P.at(i_m),
+                                                  (int32_t*)P.at(i_nm), nullptr);
+        if (rc != ORBX_OK) { e = cudaSuccess; break; }
+        if ((e = cudaMemcpy(match12, P.at(i_m), (size_t)n1 * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        e = cudaMemcpy(nmatches, P.at(i_nm), 4, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(P.pool);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}

@@ -165,6 +165,18 @@ struct OrbxBowMatchArgs {        // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, .
     int *match, *bin_of, *taken;                         // [pairs][cap]; taken only in kf_mode
     int *hist, *nmatches;                                // [pairs][32], [pairs]
 };
+struct OrbxBowTriArgs {          // ORBmatcher::SearchForTriangulation for `pairs` (keyframe 1, keyframe 2) pairs
+    const int *kf1_frame, *kf2_frame;                    // [pairs] frame indices into the transformed batch
+    const OrbxKp28* kps; const uint8_t* desc;            // [frames][cap]
+    const uint8_t* has_mp;                               // [frames][cap] or NULL: the feature already has a map point
+    const float* u_right;                                // [frames][cap] or NULL (monocular keyframes)
+    const float* geom;                                   // [pairs][28]: F12 (9), Cw1 (3), R2w (9), t2w (3), K2 = fx fy cx cy
+    float scale_factors[ORBX_MAX_LEVELS], level_sigma2[ORBX_MAX_LEVELS];
+    int only_stereo, check_orientation, th_low;
+    int *match, *bin_of, *hist, *nmatches;               // [pairs][cap] x2, [pairs][32], [pairs]
+};
+void orbx_launch_bow_triangulation(const OrbxBowOut& O, const OrbxBowTriArgs& T, int* d_taken, const int* d_n, int cap, int npairs,
+                                   cudaStream_t st);
 void orbx_launch_bow_transform(const OrbxVocabDev& V, const uint8_t* d_desc, const int* d_n, int frames, int cap, int levelsup,
                                const OrbxBowOut& O, cudaStream_t st);
 void orbx_launch_bow_score(const OrbxBowOut& O, int cap, const int* d_qa, const int* d_qb, int npairs, double* d_score, cudaStream_t st);
@@ -182,6 +194,30 @@ struct OrbxProjPairDev {
 };
 void orbx_launch_search_projection(const OrbxProjPairDev* d_pairs, int npairs, int max_n_cur, const OrbxProjCam& cam,
                                    const float* d_scale_factors, float th, int check_orientation, cudaStream_t st);
+
+// ---- ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) and ORBmatcher::Fuse (orbx_match.cu)
+struct OrbxTrackQueryDev { float x, y, xr, view_cos; int level; };   // == OrbxTrackQuery of include/orbx.h
+struct OrbxLocalFrameDev {
+    const OrbxKp28* kps; const uint8_t* desc; const float* u_right; const uint8_t* occupied; int n;
+    const OrbxTrackQueryDev* q; const uint8_t* qdesc; const uint8_t* qflags; int nq;
+    int* match; int* nmatches;
+    int* assign;                                  // scratch, nq entries
+};
+void orbx_launch_local_points(const OrbxLocalFrameDev* d_frames, int nframes, int max_n, const float* bounds4,
+                              const float* d_scale_factors, int nlevels, float th, float nnratio, cudaStream_t st);
+struct OrbxFuseCam {
+    float fx, fy, cx, cy, bf, minX, maxX, minY, maxY;
+    int nlevels;
+    float scale_factors[ORBX_MAX_LEVELS], inv_level_sigma2[ORBX_MAX_LEVELS];
+    float level_ratio[ORBX_MAX_LEVELS];           // PredictScale thresholds: level = #{n < nlevels-1 : ratio >= level_ratio[n]}
+};
+struct OrbxFuseDev {
+    const OrbxKp28* kps; const uint8_t* desc; const float* u_right; int n;
+    float Tcw[12], Ow[3], th; int mode;
+    const float* pt_xyz; const float* pt_normal; const float* pt_dist; const uint8_t* pt_desc; const uint8_t* pt_flags; int npts;
+    int* best_idx; int* best_dist; int* nfound;
+};
+void orbx_launch_fuse_search(const OrbxFuseDev* d_jobs, int njobs, int max_n, const OrbxFuseCam& cam, cudaStream_t st);
 
 // cv::undistortPoints(src, dst, K, D, Mat(), K): intrinsics and (k1, k2, p1, p2, k3) widened to f64 on the host
 struct OrbxUndistortArgs { double fx, fy, cx, cy, ifx, ify, k[5]; };

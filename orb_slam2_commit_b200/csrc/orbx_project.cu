@@ -14,19 +14,11 @@
 // round i at the latest; on real frames two or three rounds suffice.
 // Projection arithmetic: OpenCV 4.13's small-matrix gemm for `Rcw*x3Dw+tcw` (f32, left to right, addend last), a
 // double division for 1.0/z, un-contracted f32 everywhere else (the reference is built without FMA contraction).
-#include "orbx_internal.cuh"
+#include "orbx_grid.cuh"
 #include <algorithm>
 
-struct ProjKp { float x, y; int octave; };
+typedef GridKp ProjKp;
 typedef OrbxProjQuery ProjQuery;                               // r < 0: this last-frame keypoint makes no query
-
-#define PROJ_CELLS (64 * 48)                                   // FRAME_GRID_COLS x FRAME_GRID_ROWS (Frame.h)
-
-__device__ __forceinline__ int proj_dist(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1)
-{
-    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-}
 
 // One CTA per frame pair. Shared memory holds Frame::mGrid of the current frame as a CSR (cell -> keypoint indices in
 // ascending order, exactly what AssignFeaturesToGrid builds), so a query visits only the cells of its window, in
@@ -37,79 +29,18 @@ __global__ void __launch_bounds__(512) search_projection_kernel(const OrbxProjPa
 {
     extern __shared__ __align__(16) unsigned char s_raw3[];
     const OrbxProjPairDev P = pairs[blockIdx.x];
-    ProjKp* sk = reinterpret_cast<ProjKp*>(s_raw3);                              // [n_cur]
-    int* taker = reinterpret_cast<int*>(sk + P.n_cur);                          // [n_cur]
-    unsigned short* order = reinterpret_cast<unsigned short*>(taker + P.n_cur); // [n_cur] keypoint indices sorted by cell
-    unsigned short* cstart = order + ((P.n_cur + 1) & ~1);                      // [PROJ_CELLS + 1]
-    unsigned short* cfill = cstart + PROJ_CELLS + 2;                            // [PROJ_CELLS] counts, then fill cursors
+    GridSmem G;
+    int* taker = reinterpret_cast<int*>(grid_carve(s_raw3, P.n_cur, G));        // [n_cur]
+    const ProjKp* sk = G.kp;
+    const unsigned short* order = G.order;
+    const unsigned short* cstart = G.cstart;
     __shared__ int s_changed, s_hist[32], s_ind[3], s_success, s_removed, s_w[17];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     const float invW = __fdiv_rn(64.0f, __fsub_rn(cam.maxX, cam.minX)), invH = __fdiv_rn(48.0f, __fsub_rn(cam.maxY, cam.minY));
 
     // ---- current frame: Frame::AssignFeaturesToGrid / PosInGrid as a counting sort
-    for (int c = tid; c < PROJ_CELLS; c += blockDim.x) cfill[c] = 0;
-    __syncthreads();
-    for (int i = tid; i < P.n_cur; i += blockDim.x) {
-        const OrbxKp28 k = P.cur_kps[i];
-        ProjKp e; e.x = k.x; e.y = k.y; e.octave = k.octave;
-        sk[i] = e;
-        taker[i] = 0x7fffffff;
-        P.match[i] = -1;
-        const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, cam.minX), invW));
-        const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, cam.minY), invH));
-        if (!(posX < 0 || posX >= 64 || posY < 0 || posY >= 48)) {
-            // 16-bit counters packed two per word: atomicAdd on the containing word
-            const int c = posX * 48 + posY;
-            atomicAdd(reinterpret_cast<unsigned*>(cfill) + (c >> 1), (c & 1) ? 0x10000u : 1u);
-        }
-    }
-    __syncthreads();
-    {   // exclusive scan of the cell counts: 6 cells per thread, then a block scan of the per-thread sums
-        const int c0 = tid * 6;
-        int loc[6], sum = 0;
-#pragma unroll
-        for (int j = 0; j < 6; j++) { loc[j] = sum; sum += cfill[c0 + j]; }
-        int x = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_w[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            const int t = lane < 16 ? s_w[lane] : 0;
-            int z = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
-            if (lane < 16) s_w[lane] = z - t;
-            if (lane == 15) s_w[16] = z;
-        }
-        __syncthreads();
-        const int base = s_w[wid] + x - sum;
-#pragma unroll
-        for (int j = 0; j < 6; j++) { cstart[c0 + j] = (unsigned short)(base + loc[j]); cfill[c0 + j] = (unsigned short)(base + loc[j]); }
-        if (tid == 0) cstart[PROJ_CELLS] = (unsigned short)s_w[16];
-    }
-    __syncthreads();
-    for (int i = tid; i < P.n_cur; i += blockDim.x) {
-        const ProjKp k = sk[i];
-        const int posX = (int)roundf(__fmul_rn(__fsub_rn(k.x, cam.minX), invW));
-        const int posY = (int)roundf(__fmul_rn(__fsub_rn(k.y, cam.minY), invH));
-        if (!(posX < 0 || posX >= 64 || posY < 0 || posY >= 48)) {
-            const int c = posX * 48 + posY;
-            const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(cfill) + (c >> 1), (c & 1) ? 0x10000u : 1u);
-            order[(c & 1) ? (old >> 16) : (old & 0xffffu)] = (unsigned short)i;
-        }
-    }
-    __syncthreads();
-    // the atomics filled every cell in arbitrary order: the reference's cells hold ascending indices
-    for (int c = tid; c < PROJ_CELLS; c += blockDim.x) {
-        const int b0 = cstart[c], b1 = cstart[c + 1];
-        for (int i = b0 + 1; i < b1; i++) {
-            const unsigned short v = order[i];
-            int j = i - 1;
-            while (j >= b0 && order[j] > v) { order[j + 1] = order[j]; j--; }
-            order[j + 1] = v;
-        }
-    }
+    for (int i = tid; i < P.n_cur; i += blockDim.x) { taker[i] = 0x7fffffff; P.match[i] = -1; }
+    grid_build(P.cur_kps, P.n_cur, cam.minX, cam.minY, invW, invH, G, s_w);
     // ---- last frame: projection of every map point (:1524-1567)
     for (int i = tid; i < P.n_last; i += blockDim.x) {
         ProjQuery q; q.r = -1.f; q.u = q.v = q.ur = 0.f; q.min_level = q.max_level = -1;
@@ -173,7 +104,7 @@ __global__ void __launch_bounds__(512) search_projection_kernel(const OrbxProjPa
                         if (!(fabsf(__fsub_rn(k.x, q.u)) < q.r && fabsf(__fsub_rn(k.y, q.v)) < q.r)) continue;
                         if ((P.cur_occupied && P.cur_occupied[i]) || taker[i] < qi) continue;
                         if (P.cur_u_right) { const float ur = P.cur_u_right[i]; if (ur > 0.f && fabsf(__fsub_rn(q.ur, ur)) > q.r) continue; }
-                        const int d = proj_dist(qa, qb, cdesc[2 * (size_t)i], cdesc[2 * (size_t)i + 1]);
+                        const int d = grid_hamming(qa, qb, cdesc[2 * (size_t)i], cdesc[2 * (size_t)i + 1]);
                         if (d < bestDist) { bestDist = d; bestIdx = i; }
                     }
                 }
@@ -238,7 +169,7 @@ void orbx_launch_search_projection(const OrbxProjPairDev* d_pairs, int npairs, i
 {
     if (npairs <= 0) return;
     const size_t n1 = (size_t)std::max(max_n_cur, 1);
-    const size_t smem = n1 * (sizeof(ProjKp) + sizeof(int)) + ((n1 + 1) & ~(size_t)1) * 2 + (size_t)(2 * PROJ_CELLS + 4) * 2 + 16;
+    const size_t smem = grid_smem_bytes(n1) + n1 * sizeof(int) + 16;
     static OrbxSmemMark mark[1] = {};
     orbx_need_smem(search_projection_kernel, mark[0], smem);
     search_projection_kernel<<<npairs, 512, smem, st>>>(d_pairs, cam, d_scale_factors, th, check_orientation, 100 /* TH_HIGH */);

@@ -253,3 +253,175 @@ def synth_tracking_scene(seed: int, n_last: int = 1000, n_extra: int = 400, clus
     cam9 = np.array([fx, fy, cx, cy, mbf, 0.0, W, 0.0, H], np.float32)
     return dict(cur_kps=cur, cur_desc=cdesc, cur_u_right=ur, cur_occupied=occ, Tcw12=Tcw, cam9=cam9, scale_factors=sf,
                 last_kps=last, last_xyz=xyz, last_desc=mp_desc, last_flags=flags)
+
+
+TRACKQ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4")])
+
+
+def synth_local_points_scene(seed: int, n_points: int = 1500, n_extra: int = 400, cluster: float = 0.3, stereo: bool = True):
+    """Inputs of ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:46-142) as Tracking::SearchLocalPoints
+    calls it: local map points with the fields Frame::isInFrustum leaves in them, and a frame whose keypoints observe most
+    of them. `cluster` of the points are near-duplicates competing for one keypoint (the sequential rule), some keypoints
+    carry a second near-identical neighbour on the same level (the NN-ratio rule).
+    Returns the keyword arguments of api.search_local_points / oracle.search_local_points (without th / nnratio)."""
+    sc = synth_tracking_scene(seed, n_last=n_points, n_extra=n_extra, cluster=cluster, stereo=stereo)
+    rng = np.random.default_rng(seed + 7919)
+    fx, fy, cx, cy, mbf = [float(v) for v in sc["cam9"][:5]]
+    T = sc["Tcw12"].astype(np.float64); R = T[:9].reshape(3, 3); t = T[9:]
+    pc = sc["last_xyz"].astype(np.float64) @ R.T + t
+    q = np.zeros(n_points, TRACKQ_DTYPE)
+    q["proj_x"] = fx * pc[:, 0] / pc[:, 2] + cx; q["proj_y"] = fy * pc[:, 1] / pc[:, 2] + cy
+    q["proj_xr"] = q["proj_x"] - mbf / pc[:, 2]
+    q["view_cos"] = np.where(rng.random(n_points) < 0.5, rng.uniform(0.9985, 1.0, n_points), rng.uniform(0.5, 0.9975, n_points))
+    q["level"] = sc["last_kps"]["octave"]
+    flags = (rng.random(n_points) < 0.9).astype(np.uint8) | ((rng.random(n_points) < 0.8).astype(np.uint8) << 1)
+    kps, desc = sc["cur_kps"].copy(), sc["cur_desc"].copy()
+    # second-best competitors: clone some keypoints (same level, 1-2 px away, a few bits flipped)
+    n_twin = len(kps) // 8
+    src = rng.choice(len(kps), n_twin, replace=False)
+    twin = kps[src].copy(); twin["x"] += rng.normal(0, 1.5, n_twin).astype(np.float32); twin["y"] += rng.normal(0, 1.5, n_twin).astype(np.float32)
+    twin["octave"] = np.where(rng.random(n_twin) < 0.7, twin["octave"], np.clip(twin["octave"] - 1, 0, 7))
+    tdesc = desc[src].copy()
+    for i in range(n_twin):
+        for b in rng.integers(0, 256, rng.integers(0, 12)):
+            tdesc[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    kps = np.concatenate([kps, twin]); desc = np.concatenate([desc, tdesc])
+    ur = None
+    if stereo:
+        ur = np.concatenate([sc["cur_u_right"], sc["cur_u_right"][src]]).astype(np.float32)
+    occ = np.concatenate([sc["cur_occupied"], np.zeros(n_twin, np.uint8)])
+    perm = rng.permutation(len(kps))
+    kps, desc, occ = kps[perm], desc[perm], occ[perm]
+    if ur is not None:
+        ur = ur[perm]
+    bounds4 = np.array([sc["cam9"][5], sc["cam9"][6], sc["cam9"][7], sc["cam9"][8]], np.float32)
+    return dict(kps=kps, desc=desc, u_right=ur, occupied=occ, bounds4=bounds4, scale_factors=sc["scale_factors"], queries=q,
+                query_desc=sc["last_desc"], query_flags=flags)
+
+
+def synth_fuse_scene(seed: int, n_points: int = 1200, n_extra: int = 500, stereo: bool = True):
+    """Inputs of the search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:918-1092): a keyframe (pose, camera,
+    undistorted keypoints, mvuRight) and map points of its neighbours — most seen by the keyframe at a plausible scale,
+    some behind the camera, outside the image, outside their distance-invariance range or seen from a wrong angle.
+    Returns the keyword arguments of api.fuse_search / oracle.fuse_search (without th / mode)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, mbf = 517.306408, 516.469215, 318.643040, 255.313989, 40.0
+    W, H = 640.0, 480.0
+    nlevels = 8
+    sf = (np.float32(1.2) ** np.arange(nlevels)).astype(np.float32)
+    inv_s2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+    log_sf = np.float32(np.log(np.float32(1.2)))
+    a, b = 0.05, -0.03
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    R = (Ry @ Rx).astype(np.float32); t = np.array([0.2, -0.1, 0.3], np.float32)
+    Ow = (-R.T.astype(np.float64) @ t.astype(np.float64)).astype(np.float32)
+    Tcw = np.concatenate([R.ravel(), t]).astype(np.float32)
+    z = rng.uniform(1.0, 15.0, n_points)
+    pc = np.stack([(rng.uniform(-40, W + 40, n_points) - cx) / fx * z, (rng.uniform(-40, H + 40, n_points) - cy) / fy * z, z], 1)
+    pc[rng.random(n_points) < 0.04, 2] *= -1                                       # behind the camera
+    xyz = ((pc - t.astype(np.float64)) @ R.astype(np.float64)).astype(np.float32)   # Rcw^T (pc - tcw)
+    PO = xyz.astype(np.float64) - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    normal = PO / dist[:, None] + rng.normal(0, 0.25, (n_points, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    flip = rng.random(n_points) < 0.08
+    normal[flip] *= -1                                                              # seen from behind
+    lvl = rng.integers(0, nlevels, n_points)
+    max_d = (dist * sf[lvl] * rng.uniform(0.85, 1.15, n_points)).astype(np.float32)  # mfMaxDistance = dist * scale of the reference octave
+    min_d = (max_d / sf[nlevels - 1]).astype(np.float32)
+    pt_dist = np.stack([np.float32(0.8) * min_d, np.float32(1.2) * max_d, max_d], 1).astype(np.float32)
+    far = rng.random(n_points) < 0.06
+    pt_dist[far, 1] = (dist[far] * 0.7).astype(np.float32)                          # outside the invariance range
+    pt_desc = rng.integers(0, 256, (n_points, 32), dtype=np.uint8)
+    flags = (rng.random(n_points) < 0.9).astype(np.uint8)
+    # keyframe keypoints: one near the projection of most points, at the predicted level or one below
+    u = fx * pc[:, 0] / pc[:, 2] + cx; v = fy * pc[:, 1] / pc[:, 2] + cy
+    ok = (pc[:, 2] > 0) & (u > 0) & (u < W) & (v > 0) & (v < H)
+    src = np.flatnonzero(ok & (rng.random(n_points) < 0.85))
+    n = len(src) + n_extra
+    kp_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                         ("octave", "<i4"), ("class_id", "<i4")])
+    kps = np.zeros(n, kp_dtype)
+    ratio = max_d[src] / dist[src].astype(np.float32)
+    pred = np.clip(np.ceil(np.log(ratio) / log_sf), 0, nlevels - 1).astype(np.int64)
+    kps["octave"][:len(src)] = np.clip(pred - rng.integers(0, 3, len(src)) + (rng.random(len(src)) < 0.1), 0, nlevels - 1)
+    jit = sf[kps["octave"][:len(src)]] * 1.2
+    kps["x"][:len(src)] = u[src] + rng.normal(0, 1, len(src)) * jit; kps["y"][:len(src)] = v[src] + rng.normal(0, 1, len(src)) * jit
+    kps["x"][len(src):] = rng.uniform(0, W, n_extra); kps["y"][len(src):] = rng.uniform(0, H, n_extra)
+    kps["octave"][len(src):] = rng.integers(0, nlevels, n_extra)
+    kps["angle"] = rng.uniform(0, 360, n)
+    desc = np.concatenate([pt_desc[src], rng.integers(0, 256, (n_extra, 32), dtype=np.uint8)])
+    for i in range(len(src)):
+        for bb in rng.integers(0, 256, rng.integers(0, 70)):
+            desc[i, bb >> 3] ^= np.uint8(1 << (bb & 7))
+    ur = None
+    if stereo:
+        zc = np.concatenate([pc[src, 2], rng.uniform(1, 15, n_extra)])
+        ur = (kps["x"] - mbf / zc + rng.normal(0, 0.8, n)).astype(np.float32)
+        ur[rng.random(n) < 0.3] = -1.0
+    perm = rng.permutation(n)
+    kps, desc = kps[perm], desc[perm]
+    if ur is not None:
+        ur = ur[perm]
+    cam9 = np.array([fx, fy, cx, cy, mbf, 0.0, W, 0.0, H], np.float32)
+    return dict(kps=kps, desc=desc, u_right=ur, Tcw12=Tcw, Ow3=Ow, cam9=cam9, scale_factors=sf, inv_level_sigma2=inv_s2,
+                log_scale_factor=float(log_sf), pt_xyz=xyz, pt_normal=normal.astype(np.float32), pt_dist=pt_dist, pt_desc=pt_desc,
+                pt_flags=flags)
+
+
+def synth_triangulation_scene(voc, seed: int, n_points: int = 1200, n_extra: int = 300, stereo: bool = False):
+    """Inputs of ORBmatcher::SearchForTriangulation (ORBmatcher.cc:738-916): two keyframes seeing the same 3-D points from
+    two poses (descriptors near vocabulary words so that matching features share FeatureVector nodes), F12 from the poses,
+    some features already holding map points, some epipolar outliers. `voc` = (parent, is_leaf, desc, weight) of
+    synth_vocabulary. Returns the keyword arguments of ORBVocabulary.search_for_triangulation (without flags)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, mbf = 517.306408, 516.469215, 318.643040, 255.313989, 40.0
+    W, H = 640.0, 480.0
+    nlevels = 8
+    sf = (np.float32(1.2) ** np.arange(nlevels)).astype(np.float32)
+    s2 = (sf * sf).astype(np.float32)
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    a = 0.06
+    R1 = np.eye(3); t1 = np.zeros(3)
+    R2 = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]); t2 = np.array([-0.35, 0.02, 0.05])
+    # F12 as LocalMapping::ComputeF12 builds it: K1^-T * [t12]x * R12 * K2^-1 with R12 = R1w R2w^T, t12 = -R12 t2w + t1w
+    R12 = R1 @ R2.T; t12 = -R12 @ t2 + t1
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    F12 = (np.linalg.inv(K).T @ tx @ R12 @ np.linalg.inv(K)).astype(np.float32)
+    Cw1 = (-R1.T @ t1).astype(np.float32)
+    z = rng.uniform(1.5, 10.0, n_points)
+    Xw = np.stack([(rng.uniform(10, W - 10, n_points) - cx) / fx * z, (rng.uniform(10, H - 10, n_points) - cy) / fy * z, z], 1)
+    kp_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                         ("octave", "<i4"), ("class_id", "<i4")])
+    base_desc = synth_features_near_words(voc, n_points, seed + 1, max_flips=6)
+    out = {}
+    for tag, R, t in (("1", R1, t1), ("2", R2, t2)):
+        pc = Xw @ R.T + t
+        u = fx * pc[:, 0] / pc[:, 2] + cx; v = fy * pc[:, 1] / pc[:, 2] + cy
+        vis = np.flatnonzero((pc[:, 2] > 0.2) & (u > 2) & (u < W - 2) & (v > 2) & (v < H - 2))
+        n = len(vis) + n_extra
+        kps = np.zeros(n, kp_dtype)
+        oct_ = rng.integers(0, nlevels, n)
+        noise = rng.normal(0, 0.6, (len(vis), 2)) * sf[oct_[:len(vis)], None]
+        outl = rng.random(len(vis)) < 0.1
+        noise[outl] += rng.normal(0, 25, (int(outl.sum()), 2))                     # epipolar outliers
+        kps["x"][:len(vis)] = u[vis] + noise[:, 0]; kps["y"][:len(vis)] = v[vis] + noise[:, 1]
+        kps["x"][len(vis):] = rng.uniform(0, W, n_extra); kps["y"][len(vis):] = rng.uniform(0, H, n_extra)
+        kps["octave"] = oct_
+        kps["angle"] = np.concatenate([(37.0 * vis + rng.normal(3 if tag == "2" else 0, 3, len(vis))) % 360, rng.uniform(0, 360, n_extra)])
+        d = np.concatenate([base_desc[vis], synth_features_near_words(voc, n_extra, seed + 10 + int(tag), max_flips=6)])
+        for i in range(len(vis)):
+            for b in rng.integers(0, 256, rng.integers(0, 14)):
+                d[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        ur = None
+        if stereo:
+            zc = np.concatenate([pc[vis, 2], rng.uniform(1.5, 10, n_extra)])
+            ur = (kps["x"] - mbf / zc).astype(np.float32); ur[rng.random(n) < 0.5] = -1.0
+        perm = rng.permutation(n)
+        out["kps" + tag] = kps[perm]; out["desc" + tag] = d[perm]
+        out["has_mp" + tag] = (rng.random(n) < 0.35).astype(np.uint8)
+        out["u_right" + tag] = None if ur is None else ur[perm]
+    geom = np.concatenate([F12.ravel(), Cw1, R2.astype(np.float32).ravel(), t2.astype(np.float32), np.array([fx, fy, cx, cy], np.float32)])
+    out.update(geom28=geom.astype(np.float32), scale_factors=sf, level_sigma2=s2)
+    return out

@@ -1,0 +1,141 @@
+"""GPU parity tests (-m gpu) of the remaining ORBmatcher rows — SearchByProjection(F, vpMapPoints) for
+Tracking::SearchLocalPoints, the search half of Fuse, SearchForTriangulation — through the C ABI against the CPU oracle on
+the same seeded scenes. Bar: assignments, distances and match counts bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from orb_slam2_commit_b200 import ORBVocabulary, fuse_search, search_local_points, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False), (3, True)])
+def test_search_local_points_matches_oracle(seed, stereo):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:46-142): RadiusByViewingCos, the level range
+    [level-1, level], best / second-best with levels, TH_HIGH, the NN-ratio rule, the stereo gate and the sequential
+    "keypoint already holds an observed map point" rule under contention; last writer wins."""
+    s = synth.synth_local_points_scene(seed, stereo=stereo)
+    for th, nnratio in ((1.0, 0.8), (3.0, 0.8), (5.0, 0.6)):
+        n, m = search_local_points(**s, th=th, nnratio=nnratio)
+        no, mo = ob.search_local_points(**s, th=th, nnratio=nnratio)
+        assert n == no, f"seed {seed} th {th}: nmatches {n} vs {no}"
+        assert np.array_equal(m, mo), f"seed {seed} th {th}: {np.count_nonzero(m != mo)} assignments differ"
+        assert n > 200
+    # every map point observed (each assignment blocks later ones) / none observed (free overwriting)
+    for bit in (2, 0):
+        s2 = dict(s); s2["query_flags"] = (s["query_flags"] & 1) | bit
+        n, m = search_local_points(**s2, th=5.0, nnratio=0.8)
+        no, mo = ob.search_local_points(**s2, th=5.0, nnratio=0.8)
+        assert n == no and np.array_equal(m, mo)
+    # heavy contention: every point projects onto one of 40 places with one of 40 descriptors
+    rng = np.random.default_rng(seed)
+    s3 = dict(s); q = s["queries"].copy(); pick = rng.integers(0, 40, len(q))
+    q["proj_x"] = q["proj_x"][pick]; q["proj_y"] = q["proj_y"][pick]; q["proj_xr"] = q["proj_xr"][pick]; q["level"] = q["level"][pick]
+    s3["queries"] = q; s3["query_desc"] = s["query_desc"][pick]
+    n, m = search_local_points(**s3, th=5.0, nnratio=0.9)
+    no, mo = ob.search_local_points(**s3, th=5.0, nnratio=0.9)
+    assert n == no and np.array_equal(m, mo) and n > 40
+
+
+def test_search_local_points_degenerate_inputs():
+    s = synth.synth_local_points_scene(5, n_points=60, n_extra=20)
+    e = dict(s); e["query_flags"] = np.zeros_like(s["query_flags"])
+    n, m = search_local_points(**e, th=1.0)
+    assert n == 0 and (m == -1).all()
+    e = dict(s); e["kps"] = s["kps"][:0]; e["desc"] = s["desc"][:0]; e["u_right"] = None; e["occupied"] = None
+    n, m = search_local_points(**e, th=1.0)
+    assert n == 0 and len(m) == 0
+    e = dict(s); e["queries"] = s["queries"][:0]; e["query_desc"] = s["query_desc"][:0]; e["query_flags"] = s["query_flags"][:0]
+    n, m = search_local_points(**e, th=1.0)
+    assert n == 0 and (m == -1).all()
+    # windows that miss the grid entirely
+    e = dict(s); q = s["queries"].copy(); q["proj_x"] += 5000; e["queries"] = q
+    n, m = search_local_points(**e, th=1.0)
+    no, mo = ob.search_local_points(**e, th=1.0)
+    assert n == no == 0 and np.array_equal(m, mo)
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False), (3, True)])
+def test_fuse_search_matches_oracle(seed, stereo):
+    """Search half of ORBmatcher::Fuse (ORBmatcher.cc:918-1092 and the Sim3 form :1094-1236): projection, IsInImage, the
+    distance / viewing-angle gates, PredictScale, GetFeaturesInArea, level + chi-square gates, nearest descriptor."""
+    s = synth.synth_fuse_scene(seed, stereo=stereo)
+    for mode in (0, 1):
+        for th in (3.0, 4.0, 10.0):
+            n, bi, bd = fuse_search(**s, th=th, mode=mode)
+            no, bio, bdo = ob.fuse_search(**s, th=th, mode=mode)
+            assert n == no, f"seed {seed} mode {mode} th {th}: nFused {n} vs {no}"
+            assert np.array_equal(bi, bio), f"seed {seed} mode {mode} th {th}: {np.count_nonzero(bi != bio)} picks differ"
+            assert np.array_equal(bd, bdo)
+            assert n > 100 and n == np.count_nonzero(bi >= 0)
+
+
+def test_predict_scale_thresholds_match_libm_logf():
+    """MapPoint::PredictScale (MapPoint.cc:407-422) on the device goes through a threshold table built from the host's logf;
+    a fuse job whose points sit at distances swept finely across every level boundary must predict the oracle's level.
+    The level decides the window radius and the admissible octaves, so any off-by-one shows up in the picks."""
+    s = synth.synth_fuse_scene(7, n_points=4000, n_extra=100)
+    Ow = s["Ow3"].astype(np.float64)
+    PO = s["pt_xyz"].astype(np.float64) - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    k = np.arange(len(dist))
+    # mfMaxDistance = dist * 1.2^(k / 500): ratios sweep 1.2^0 .. 1.2^8 in 4000 steps, plus exact powers
+    md = (dist * np.float64(np.float32(1.2)) ** (k / 500.0)).astype(np.float32)
+    s["pt_dist"] = np.stack([np.zeros_like(md), md * 100, md], 1).astype(np.float32)
+    for mode in (0, 1):
+        n, bi, bd = fuse_search(**s, th=3.0, mode=mode)
+        no, bio, bdo = ob.fuse_search(**s, th=3.0, mode=mode)
+        assert n == no and np.array_equal(bi, bio) and np.array_equal(bd, bdo)
+    lv = [ob.predict_scale(float(m), float(np.float32(d)), s["log_scale_factor"], 8) for m, d in zip(md[::97], dist[::97])]
+    assert min(lv) == 0 and max(lv) == 7
+
+
+def test_fuse_search_degenerate_inputs():
+    s = synth.synth_fuse_scene(9, n_points=50, n_extra=10)
+    e = dict(s); e["pt_flags"] = np.zeros_like(s["pt_flags"])
+    n, bi, bd = fuse_search(**e, th=3.0)
+    assert n == 0 and (bi == -1).all() and (bd == 256).all()
+    e = dict(s); e["kps"] = s["kps"][:0]; e["desc"] = s["desc"][:0]; e["u_right"] = None
+    n, bi, bd = fuse_search(**e, th=3.0, mode=1)
+    no, bio, bdo = ob.fuse_search(**e, th=3.0, mode=1)
+    assert n == no == 0 and np.array_equal(bi, bio) and np.array_equal(bd, bdo)
+    e = dict(s)
+    for k in ("pt_xyz", "pt_normal", "pt_dist", "pt_desc", "pt_flags"):
+        e[k] = s[k][:0]
+    n, bi, bd = fuse_search(**e, th=3.0)
+    assert n == 0 and len(bi) == 0
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, False), (2, True), (3, False)])
+def test_search_for_triangulation_matches_oracle(seed, stereo):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:738-916): node-aligned candidates, map-point / stereo flags, the
+    epipole distance gate, CheckDistEpipolarLine, last-minimum-wins under `dist > bestDist`, rotation histogram."""
+    voc = synth.synth_vocabulary(10, 4, 5)
+    V = ORBVocabulary(10, 4, *voc); Vo = ob.Vocabulary(10, 4, *voc)
+    s = synth.synth_triangulation_scene(voc, seed, stereo=stereo)
+    t1, t2 = Vo.transform(s["desc1"], 2), Vo.transform(s["desc2"], 2)
+    for only_stereo, ori in ((False, True), (False, False), (True, True)):
+        n, m = V.search_for_triangulation(**s, levelsup=2, only_stereo=only_stereo, check_orientation=ori)
+        no, mo = ob.search_for_triangulation(t1, t2, **s, only_stereo=only_stereo, check_orientation=ori)
+        assert n == no, f"seed {seed} only_stereo {only_stereo} ori {ori}: {n} vs {no}"
+        assert np.array_equal(m, mo), f"{np.count_nonzero(m != mo)} pairs differ"
+        assert n == np.count_nonzero(m >= 0)
+        if not only_stereo:
+            assert n > 100
+    # equal distances inside a node: duplicate keyframe-2 descriptors so that the LAST of the equal candidates must win
+    s2 = dict(s); d2 = s["desc2"].copy(); d2[1::2] = d2[0::2][:len(d2[1::2])]; s2["desc2"] = d2
+    k2 = s["kps2"].copy(); k2["x"][1::2] = k2["x"][0::2][:len(k2["x"][1::2])]; k2["y"][1::2] = k2["y"][0::2][:len(k2["y"][1::2])]
+    k2["octave"][1::2] = k2["octave"][0::2][:len(k2["octave"][1::2])]; s2["kps2"] = k2
+    n, m = V.search_for_triangulation(**s2, levelsup=2)
+    no, mo = ob.search_for_triangulation(Vo.transform(s2["desc1"], 2), Vo.transform(s2["desc2"], 2), **s2)
+    assert n == no and np.array_equal(m, mo)
+    # no map-point flags at all / empty sides
+    s3 = dict(s); s3["has_mp1"] = None; s3["has_mp2"] = None
+    n, m = V.search_for_triangulation(**s3, levelsup=2)
+    no, mo = ob.search_for_triangulation(t1, t2, **s3)
+    assert n == no and np.array_equal(m, mo)
+    s4 = dict(s); s4["kps2"] = s["kps2"][:0]; s4["desc2"] = s["desc2"][:0]; s4["has_mp2"] = s["has_mp2"][:0]
+    s4["u_right2"] = None if s["u_right2"] is None else s["u_right2"][:0]
+    n, m = V.search_for_triangulation(**s4, levelsup=2)
+    assert n == 0 and (m == -1).all()
