@@ -403,6 +403,76 @@ int  orbx_search_for_triangulation(orbx_vocabulary* v, const OrbxKeyPoint* kf1_k
                                    const float* geom28, const float* scale_factors, const float* level_sigma2, int nlevels,
                                    int levelsup, int only_stereo, int check_orientation, int32_t* match12, int32_t* nmatches);
 
+/* ---- ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+ *      (ORBmatcher.cc:1648-1795; mode 0, Tracking::Relocalization) and ORBmatcher::SearchByProjection(KeyFrame *pKF, cv::Mat Scw,
+ *      vpPoints, vpMatched, int th) (:327-440; mode 1, LoopClosing — Rcw / tcw / Ow taken out of Scw by the caller as :333-339
+ *      do, max_dist = TH_LOW = 50). Map points are projected, gated (distance invariance, viewing angle in mode 1,
+ *      MapPoint::PredictScale) and each takes the nearest FREE feature of its window in the reference's sequential order:
+ *      a feature that holds a map point before the call (`occupied`) or received one earlier in the loop is skipped. ---- */
+typedef struct OrbxProjectionJob {
+    const OrbxKeyPoint* keypoints;      /* mvKeysUn of the frame (mode 0) / keyframe (mode 1), n */
+    const uint8_t* descriptors;
+    const uint8_t* occupied;            /* != 0 <=> CurrentFrame.mvpMapPoints[i] / vpMatched[i] is non-NULL before the call; NULL = none */
+    int32_t n;
+    float Tcw[12];                      /* Rcw row-major (9 floats), then tcw (3) */
+    float Ow[3];                        /* -Rcw^T * tcw */
+    const float* pt_xyz;                /* GetWorldPos(), 3 floats per point */
+    const float* pt_normal;             /* GetNormal() (mode 1 only; may be NULL in mode 0) */
+    const float* pt_dist;               /* 3 floats per point: GetMinDistanceInvariance(), GetMaxDistanceInvariance(), mfMaxDistance */
+    const uint8_t* pt_descriptors;      /* GetDescriptor() */
+    const uint8_t* pt_flags;            /* bit 0: non-NULL, !isBad(), not in sAlreadyFound / spAlreadyFound */
+    const float* pt_angle;              /* mode 0 with check_orientation: pKF->mvKeysUn[i].angle */
+    int32_t npts;
+    float th;
+    int32_t max_dist;                   /* ORBdist (mode 0) / TH_LOW (mode 1) */
+    int32_t mode;
+    int32_t* match;                     /* out, n: point index the feature holds after the call, -1 = untouched */
+    int32_t* nmatches;                  /* out: the return value */
+} OrbxProjectionJob;
+int orbx_search_by_projection_kf(const OrbxProjectionJob* job, const float* camera9, const float* scale_factors, int nlevels,
+                                 float log_scale_factor, int check_orientation, int device);
+/* `jobs` is a HOST array whose pointers are DEVICE pointers; one CTA per job, asynchronous on cuda_stream */
+int orbx_search_by_projection_kf_device(const OrbxProjectionJob* jobs, int njobs, const float* camera9, const float* scale_factors,
+                                        int nlevels, float log_scale_factor, int check_orientation, int device, void* cuda_stream);
+
+/* ---- ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (ORBmatcher.cc:1238-1487): the map points of each
+ *      keyframe are carried into the other camera through the Sim3 and matched in a window (TH_HIGH); pairs found in both
+ *      directions survive. Per keyframe: its features and, per feature, the map point it holds (mp_flags bit 0: the point
+ *      exists, is not bad and the feature is not in vbAlreadyMatched). S12 = (sR12 row-major, t12), S21 = (sR21, t21) as
+ *      :1253-1255 build them. match12[i1] = feature of keyframe 2 or -1. ---- */
+typedef struct OrbxSim3KeyFrame {
+    const OrbxKeyPoint* keypoints; const uint8_t* descriptors; int32_t n;
+    const float* mp_xyz;                /* 3 floats per feature */
+    const float* mp_dist;               /* 3 floats per feature (see OrbxProjectionJob.pt_dist) */
+    const uint8_t* mp_descriptors;      /* 32 bytes per feature */
+    const uint8_t* mp_flags;
+    float Tcw[12];                      /* GetRotation() row-major, GetTranslation() */
+} OrbxSim3KeyFrame;
+int orbx_search_by_sim3(const OrbxSim3KeyFrame* kf1, const OrbxSim3KeyFrame* kf2, const float* S12, const float* S21,
+                        const float* camera9, const float* scale_factors, int nlevels, float log_scale_factor, float th,
+                        int32_t* match12, int32_t* nfound, int device);
+/* device pointers inside kf1 / kf2, d_match12 (kf1->n ints) and d_nfound; d_scratch: (kf1->n + kf2->n + 2) ints */
+int orbx_search_by_sim3_device(const OrbxSim3KeyFrame* kf1, const OrbxSim3KeyFrame* kf2, const float* S12, const float* S21,
+                               const float* camera9, const float* scale_factors, int nlevels, float log_scale_factor, float th,
+                               int32_t* d_match12, int32_t* d_nfound, int32_t* d_scratch, int device, void* cuda_stream);
+
+/* ---- ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:442-587), the matcher
+ *      of Tracking::MonocularInitialization: level-0 keypoints only, the sequential vMatchedDistance / vnMatches21 rule, NN
+ *      ratio, rotation histogram. prev_matched = vbPrevMatched (2 floats per F1 keypoint), updated like :582-584. ---- */
+typedef struct OrbxInitPair {
+    const OrbxKeyPoint* keypoints1; const uint8_t* descriptors1; int32_t n1;   /* F1.mvKeysUn / mDescriptors */
+    const OrbxKeyPoint* keypoints2; const uint8_t* descriptors2; int32_t n2;   /* F2 */
+    const float* prev_matched;          /* in, 2 * n1 */
+    float* prev_matched_out;            /* out, 2 * n1 (may alias prev_matched) */
+    int32_t window_size;
+    int32_t* match12;                   /* out, n1: vnMatches12 */
+    int32_t* nmatches;                  /* out */
+} OrbxInitPair;
+int orbx_search_for_initialization(const OrbxInitPair* pair, const float* bounds4, float nnratio, int check_orientation, int device);
+/* `pairs` is a HOST array whose pointers are DEVICE pointers; one CTA per pair, asynchronous on cuda_stream */
+int orbx_search_for_initialization_device(const OrbxInitPair* pairs, int npairs, const float* bounds4, float nnratio,
+                                          int check_orientation, int device, void* cuda_stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -521,3 +521,61 @@ def search_for_triangulation(t1, t2, kps1, desc1, has_mp1, u_right1, kps2, desc2
           g[0:9].ctypes.data, g[9:12].ctypes.data, g[12:24].ctypes.data, g[24:28].ctypes.data, sf.ctypes.data, s2.ctypes.data,
           int(only_stereo), int(check_orientation), match.ctypes.data)
     return n, match[:len(kps1)]
+
+
+def search_by_projection_kf(kps, desc, occupied, Tcw12, Ow3, cam9, scale_factors, log_scale_factor, pt_xyz, pt_normal, pt_dist,
+                            pt_desc, pt_flags, pt_angle, th, max_dist, mode, check_orientation=True):
+    """ORBmatcher.cc:1648-1795 (mode 0) / :327-440 (mode 1) -> (nmatches, match)"""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    T = np.ascontiguousarray(Tcw12, np.float32); Ow = np.ascontiguousarray(Ow3, np.float32)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = None if pt_normal is None else np.ascontiguousarray(pt_normal, np.float32)
+    dst = np.ascontiguousarray(pt_dist, np.float32); pd = np.ascontiguousarray(pt_desc, np.uint8)
+    pf = np.ascontiguousarray(pt_flags, np.uint8); pa = None if pt_angle is None else np.ascontiguousarray(pt_angle, np.float32)
+    match = np.zeros(max(len(kps), 1), np.int32)
+    f = lib().oc_search_by_projection_seq
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_float] + [C.c_void_p] * 6 + \
+        [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    n = f(kps.ctypes.data, desc.ctypes.data, len(kps), _p(occ), T.ctypes.data, Ow.ctypes.data, cam.ctypes.data, sf.ctypes.data, len(sf),
+          float(log_scale_factor), xyz.ctypes.data, _p(nrm), dst.ctypes.data, pd.ctypes.data, pf.ctypes.data, _p(pa), len(pf), th,
+          max_dist, mode, int(check_orientation), match.ctypes.data)
+    return n, match[:len(kps)]
+
+
+def search_by_sim3(kf1, kf2, S12, S21, cam9, scale_factors, log_scale_factor, th):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1238-1487) -> (nFound, match12)"""
+    def arrs(k):
+        return [np.ascontiguousarray(k["kps"], KP_DTYPE), np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["mp_xyz"], np.float32),
+                np.ascontiguousarray(k["mp_dist"], np.float32), np.ascontiguousarray(k["mp_desc"], np.uint8), np.ascontiguousarray(k["mp_flags"], np.uint8)]
+    a, b = arrs(kf1), arrs(kf2)
+    T1 = np.ascontiguousarray(kf1["Tcw12"], np.float32); T2 = np.ascontiguousarray(kf2["Tcw12"], np.float32)
+    s12 = np.ascontiguousarray(S12, np.float32); s21 = np.ascontiguousarray(S21, np.float32)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    match = np.zeros(max(len(a[0]), 1), np.int32)
+    f = lib().oc_search_by_sim3
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+        [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_float, C.c_void_p]
+    n = f(a[0].ctypes.data, a[1].ctypes.data, len(a[0]), a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data, a[5].ctypes.data,
+          b[0].ctypes.data, b[1].ctypes.data, len(b[0]), b[2].ctypes.data, b[3].ctypes.data, b[4].ctypes.data, b[5].ctypes.data,
+          T1.ctypes.data, T2.ctypes.data, s12.ctypes.data, s21.ctypes.data, cam.ctypes.data, sf.ctypes.data, len(sf),
+          float(log_scale_factor), th, match.ctypes.data)
+    return n, match[:len(a[0])]
+
+
+def search_for_initialization(kps1, desc1, kps2, desc2, bounds4, prev_matched, window_size=100, nnratio=0.9, check_orientation=True):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:442-587) -> (nmatches, vnMatches12, updated vbPrevMatched)"""
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    b4 = np.ascontiguousarray(bounds4, np.float32)
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    match = np.zeros(max(len(kps1), 1), np.int32)
+    f = lib().oc_search_for_initialization
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
+                  C.c_void_p]
+    n = f(kps1.ctypes.data, desc1.ctypes.data, len(kps1), kps2.ctypes.data, desc2.ctypes.data, len(kps2), b4.ctypes.data,
+          prev.ctypes.data, window_size, nnratio, int(check_orientation), match.ctypes.data)
+    return n, match[:len(kps1)], prev

@@ -1680,3 +1680,252 @@ int oc_search_for_triangulation(const int32_t* fv1_node, const int32_t* fv1_off,
     free(hist_idx); free(hist_bin);
     return nmatches;
 }
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+ * (ORBmatcher.cc:1648-1795; mode 0, the relocalisation matcher) and
+ * ORBmatcher::SearchByProjection(KeyFrame *pKF, cv::Mat Scw, vpPoints, vpMatched, int th) (:327-440; mode 1, loop closing,
+ * Rcw / tcw / Ow taken out of Scw by the caller as :333-339 do; th_dist = TH_LOW).
+ * occupied[k]: the frame / keyframe feature already holds a map point before the call (CurrentFrame.mvpMapPoints[k] /
+ * vpMatched[k] non-NULL). pt_flags bit 0: the point is non-NULL, not bad and not in sAlreadyFound / spAlreadyFound.
+ * pt_angle[i] = pKF->mvKeysUn[i].angle (mode 0 with check_orientation). match[k] = point index the feature now holds,
+ * -1 = untouched. Returns nmatches. */
+int oc_search_by_projection_seq(const OcKeyPoint* kps, const uint8_t* desc, int n, const uint8_t* occupied,
+                                const float* Tcw12, const float* Ow3, const float* cam9, const float* scale_factors,
+                                int nlevels, float log_scale_factor,
+                                const float* pt_xyz, const float* pt_normal, const float* pt_dist, const uint8_t* pt_desc,
+                                const uint8_t* pt_flags, const float* pt_angle, int npts,
+                                float th, int th_dist, int mode, int check_orientation, int32_t* match)
+{
+    const float fx = cam9[0], fy = cam9[1], cx = cam9[2], cy = cam9[3];
+    const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
+    const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
+    OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);
+    uint8_t* occ = (uint8_t*)calloc((size_t)(n > 0 ? n : 1), 1);
+    for (int i = 0; i < n; i++) { match[i] = -1; occ[i] = occupied ? (occupied[i] != 0) : 0; }
+    int nmatches = 0, nh = 0, count[HISTO_LENGTH] = {0};
+    int* hist_idx = (int*)malloc(sizeof(int) * (size_t)(npts > 0 ? npts : 1)), * hist_bin = (int*)malloc(sizeof(int) * (size_t)(npts > 0 ? npts : 1));
+    for (int i = 0; i < npts; i++) {
+        if (!(pt_flags[i] & 1)) continue;
+        const float X = pt_xyz[3 * i], Y = pt_xyz[3 * i + 1], Z = pt_xyz[3 * i + 2];
+        float c3[3];
+        for (int r = 0; r < 3; r++) {
+            float s = Tcw12[3 * r] * X;
+            s = s + Tcw12[3 * r + 1] * Y;
+            s = s + Tcw12[3 * r + 2] * Z;
+            c3[r] = s + Tcw12[9 + r];
+        }
+        float u, v;
+        if (mode == 0) {
+            const float xc = c3[0], yc = c3[1];
+            const float invzc = (float)(1.0 / c3[2]);
+            u = fx * xc * invzc + cx; v = fy * yc * invzc + cy;
+            if (u < mnMinX || u > mnMaxX) continue;
+            if (v < mnMinY || v > mnMaxY) continue;
+        } else {
+            if (c3[2] < 0.0) continue;
+            const float invz = 1 / c3[2];
+            const float x = c3[0] * invz, y = c3[1] * invz;
+            u = fx * x + cx; v = fy * y + cy;
+            if (!(u >= mnMinX && u < mnMaxX && v >= mnMinY && v < mnMaxY)) continue;
+        }
+        const float PO[3] = {X - Ow3[0], Y - Ow3[1], Z - Ow3[2]};
+        double s2 = 0.0;
+        for (int k = 0; k < 3; k++) s2 += (double)PO[k] * (double)PO[k];
+        const float dist3D = (float)sqrt(s2);
+        if (dist3D < pt_dist[3 * i] || dist3D > pt_dist[3 * i + 1]) continue;
+        if (mode == 1) {
+            double dot = 0.0;
+            for (int k = 0; k < 3; k++) dot += (double)PO[k] * (double)pt_normal[3 * i + k];
+            if (dot < 0.5 * dist3D) continue;
+        }
+        const int nPredictedLevel = oc_predict_scale(pt_dist[3 * i + 2], dist3D, log_scale_factor, nlevels);
+        const float radius = th * scale_factors[nPredictedLevel];
+        const int minLevel = nPredictedLevel - 1, maxLevel = mode == 0 ? nPredictedLevel + 1 : nPredictedLevel;
+        int x0, x1, y0, y1;
+        if (!oc_grid_window(u, v, radius, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int ix = x0; ix <= x1; ix++)
+            for (int iy = y0; iy <= y1; iy++) {
+                const int c = ix * FRAME_GRID_ROWS + iy;
+                for (int j = g.cnt[c]; j < g.cnt[c + 1]; j++) {
+                    const int idx = g.tab[j];
+                    const OcKeyPoint* kp = &kps[idx];
+                    /* mode 0: Frame::GetFeaturesInArea(.., level-1, level+1): maxLevel >= 0 always, so both bounds are checked;
+                       mode 1: KeyFrame::GetFeaturesInArea + the explicit level test (:415-418) */
+                    if (kp->octave < minLevel || kp->octave > maxLevel) continue;
+                    if (!(fabsf(kp->x - u) < radius && fabsf(kp->y - v) < radius)) continue;
+                    if (occ[idx]) continue;
+                    const int dist = oc_descriptor_distance(pt_desc + 32 * (size_t)i, desc + 32 * (size_t)idx);
+                    if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+                }
+            }
+        if (bestDist <= th_dist) {
+            match[bestIdx] = i; occ[bestIdx] = 1;
+            nmatches++;
+            if (mode == 0 && check_orientation) {
+                const int bin = rot_bin(pt_angle[i], kps[bestIdx].angle);
+                hist_idx[nh] = bestIdx; hist_bin[nh] = bin; nh++; count[bin]++;
+            }
+        }
+    }
+    if (mode == 0 && check_orientation) {
+        int i1, i2, i3;
+        three_maxima(count, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int t = 0; t < nh; t++)
+            if (hist_bin[t] != i1 && hist_bin[t] != i2 && hist_bin[t] != i3) { match[hist_idx[t]] = -1; nmatches--; }
+    }
+    oc_grid_free(&g); free(occ); free(hist_idx); free(hist_bin);
+    return nmatches;
+}
+
+/* One direction of ORBmatcher::SearchBySim3 (ORBmatcher.cc:1281-1359 / :1362-1440): points of the source keyframe go
+ * through T1 = (R1w, t1w) and T2 = (sR21, t21) into the target camera; vnMatch[i] = target feature or -1. */
+static void sim3_direction(const OcKeyPoint* kps, const uint8_t* desc, int n, const float* T1, const float* T2,
+                           const float* cam9, const float* scale_factors, int nlevels, float log_scale_factor,
+                           const float* pt_xyz, const float* pt_dist, const uint8_t* pt_desc, const uint8_t* pt_flags, int npts,
+                           float th, int32_t* vnMatch)
+{
+    const float fx = cam9[0], fy = cam9[1], cx = cam9[2], cy = cam9[3];
+    const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
+    const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
+    OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);
+    for (int i = 0; i < npts; i++) {
+        vnMatch[i] = -1;
+        if (!(pt_flags[i] & 1)) continue;                         /* NULL, already matched or bad */
+        const float X = pt_xyz[3 * i], Y = pt_xyz[3 * i + 1], Z = pt_xyz[3 * i + 2];
+        float a3[3], c3[3];
+        for (int r = 0; r < 3; r++) {
+            float s = T1[3 * r] * X;
+            s = s + T1[3 * r + 1] * Y;
+            s = s + T1[3 * r + 2] * Z;
+            a3[r] = s + T1[9 + r];
+        }
+        for (int r = 0; r < 3; r++) {
+            float s = T2[3 * r] * a3[0];
+            s = s + T2[3 * r + 1] * a3[1];
+            s = s + T2[3 * r + 2] * a3[2];
+            c3[r] = s + T2[9 + r];
+        }
+        if (c3[2] < 0.0) continue;
+        const float invz = (float)(1.0 / c3[2]);
+        const float x = c3[0] * invz, y = c3[1] * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!(u >= mnMinX && u < mnMaxX && v >= mnMinY && v < mnMaxY)) continue;
+        double s2 = 0.0;
+        for (int k = 0; k < 3; k++) s2 += (double)c3[k] * (double)c3[k];
+        const float dist3D = (float)sqrt(s2);
+        if (dist3D < pt_dist[3 * i] || dist3D > pt_dist[3 * i + 1]) continue;
+        const int nPredictedLevel = oc_predict_scale(pt_dist[3 * i + 2], dist3D, log_scale_factor, nlevels);
+        const float radius = th * scale_factors[nPredictedLevel];
+        int x0, x1, y0, y1;
+        if (!oc_grid_window(u, v, radius, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int ix = x0; ix <= x1; ix++)
+            for (int iy = y0; iy <= y1; iy++) {
+                const int c = ix * FRAME_GRID_ROWS + iy;
+                for (int j = g.cnt[c]; j < g.cnt[c + 1]; j++) {
+                    const int idx = g.tab[j];
+                    const OcKeyPoint* kp = &kps[idx];
+                    if (!(fabsf(kp->x - u) < radius && fabsf(kp->y - v) < radius)) continue;
+                    if (kp->octave < nPredictedLevel - 1 || kp->octave > nPredictedLevel) continue;
+                    const int dist = oc_descriptor_distance(pt_desc + 32 * (size_t)i, desc + 32 * (size_t)idx);
+                    if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+                }
+            }
+        if (bestDist <= 100) vnMatch[i] = bestIdx;                 /* TH_HIGH */
+    }
+    oc_grid_free(&g);
+}
+
+/* ORBmatcher::SearchBySim3 (ORBmatcher.cc:1238-1487). Per keyframe: undistorted keypoints, descriptors, and for every
+ * feature its map point (xyz, (min, max distance invariance, mfMaxDistance), descriptor) with flags bit 0 = the feature has
+ * a map point that is not bad and is not already matched (vbAlreadyMatched). T1w / T2w = (R, t) of the keyframes,
+ * S12 = (sR12, t12), S21 = (sR21, t21) as :1253-1255 build them. match12[i1] = feature of keyframe 2 whose map point
+ * vpMatches12[i1] receives, -1 = none. Returns nFound. */
+int oc_search_by_sim3(const OcKeyPoint* kps1, const uint8_t* desc1, int n1, const float* xyz1, const float* dist1,
+                      const uint8_t* mpdesc1, const uint8_t* flags1,
+                      const OcKeyPoint* kps2, const uint8_t* desc2, int n2, const float* xyz2, const float* dist2,
+                      const uint8_t* mpdesc2, const uint8_t* flags2,
+                      const float* T1w, const float* T2w, const float* S12, const float* S21,
+                      const float* cam9, const float* scale_factors, int nlevels, float log_scale_factor, float th,
+                      int32_t* match12)
+{
+    int32_t* m1 = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n1 > 0 ? n1 : 1));
+    int32_t* m2 = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
+    sim3_direction(kps2, desc2, n2, T1w, S21, cam9, scale_factors, nlevels, log_scale_factor, xyz1, dist1, mpdesc1, flags1, n1, th, m1);
+    sim3_direction(kps1, desc1, n1, T2w, S12, cam9, scale_factors, nlevels, log_scale_factor, xyz2, dist2, mpdesc2, flags2, n2, th, m2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        match12[i1] = -1;
+        const int idx2 = m1[i1];
+        if (idx2 >= 0 && m2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+    }
+    free(m1); free(m2);
+    return nFound;
+}
+
+/* ORBmatcher::SearchForInitialization (ORBmatcher.cc:442-587). prev = vbPrevMatched (2 floats per F1 keypoint, updated in
+ * place like :582-584); match12 = vnMatches12. Returns nmatches. */
+int oc_search_for_initialization(const OcKeyPoint* kps1, const uint8_t* desc1, int n1,
+                                 const OcKeyPoint* kps2, const uint8_t* desc2, int n2, const float* bounds4,
+                                 float* prev, int window, float nnratio, int check_orientation, int32_t* match12)
+{
+    const float mnMinX = bounds4[0], mnMaxX = bounds4[1], mnMinY = bounds4[2], mnMaxY = bounds4[3];
+    const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
+    OcGrid g = oc_grid_build(kps2, n2, mnMinX, mnMinY, invW, invH);
+    int nmatches = 0, nh = 0, count[HISTO_LENGTH] = {0};
+    int* hist_idx = (int*)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1)), * hist_bin = (int*)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1));
+    int* vMatchedDistance = (int*)malloc(sizeof(int) * (size_t)(n2 > 0 ? n2 : 1));
+    int* vnMatches21 = (int*)malloc(sizeof(int) * (size_t)(n2 > 0 ? n2 : 1));
+    for (int i = 0; i < n2; i++) { vMatchedDistance[i] = INT_MAX; vnMatches21[i] = -1; }
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    const float r = (float)window;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = kps1[i1].octave;
+        if (level1 > 0) continue;
+        const float x = prev[2 * i1], y = prev[2 * i1 + 1];
+        int x0, x1, y0, y1;
+        if (!oc_grid_window(x, y, r, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        const int minLevel = level1, maxLevel = level1;
+        const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int ix = x0; ix <= x1; ix++)
+            for (int iy = y0; iy <= y1; iy++) {
+                const int c = ix * FRAME_GRID_ROWS + iy;
+                for (int j = g.cnt[c]; j < g.cnt[c + 1]; j++) {
+                    const int i2 = g.tab[j];
+                    const OcKeyPoint* kp = &kps2[i2];
+                    if (bCheckLevels) {
+                        if (kp->octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                    }
+                    if (!(fabsf(kp->x - x) < r && fabsf(kp->y - y) < r)) continue;
+                    const int dist = oc_descriptor_distance(desc1 + 32 * (size_t)i1, desc2 + 32 * (size_t)i2);
+                    if (vMatchedDistance[i2] <= dist) continue;
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+            }
+        if (bestDist <= 50) {                                                     /* TH_LOW */
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { match12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                match12[i1] = bestIdx2; vnMatches21[bestIdx2] = i1; vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_orientation) {
+                    const int bin = rot_bin(kps1[i1].angle, kps2[bestIdx2].angle);
+                    hist_idx[nh] = i1; hist_bin[nh] = bin; nh++; count[bin]++;
+                }
+            }
+        }
+    }
+    if (check_orientation) {
+        int i1, i2, i3;
+        three_maxima(count, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int t = 0; t < nh; t++)
+            if (hist_bin[t] != i1 && hist_bin[t] != i2 && hist_bin[t] != i3 && match12[hist_idx[t]] >= 0) { match12[hist_idx[t]] = -1; nmatches--; }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (match12[i1] >= 0) { prev[2 * i1] = kps2[match12[i1]].x; prev[2 * i1 + 1] = kps2[match12[i1]].y; }
+    oc_grid_free(&g); free(hist_idx); free(hist_bin); free(vMatchedDistance); free(vnMatches21);
+    return nmatches;
+}

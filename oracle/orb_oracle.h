@@ -149,6 +149,25 @@ int   oc_search_for_triangulation(const int32_t* fv1_node, const int32_t* fv1_of
                                   const float* scale_factors2, const float* level_sigma2_2,
                                   int only_stereo, int check_orientation, int32_t* match12);   /* ORBmatcher.cc:738-916 */
 
+int   oc_search_by_projection_seq(const OcKeyPoint* kps, const uint8_t* desc, int n, const uint8_t* occupied,
+                                  const float* Tcw12, const float* Ow3, const float* cam9, const float* scale_factors,
+                                  int nlevels, float log_scale_factor,
+                                  const float* pt_xyz, const float* pt_normal, const float* pt_dist, const uint8_t* pt_desc,
+                                  const uint8_t* pt_flags, const float* pt_angle, int npts,
+                                  float th, int th_dist, int mode, int check_orientation, int32_t* match);
+                                                                                /* ORBmatcher.cc:1648-1795 (mode 0), 327-440 (mode 1) */
+int   oc_search_by_sim3(const OcKeyPoint* kps1, const uint8_t* desc1, int n1, const float* xyz1, const float* dist1,
+                        const uint8_t* mpdesc1, const uint8_t* flags1,
+                        const OcKeyPoint* kps2, const uint8_t* desc2, int n2, const float* xyz2, const float* dist2,
+                        const uint8_t* mpdesc2, const uint8_t* flags2,
+                        const float* T1w, const float* T2w, const float* S12, const float* S21,
+                        const float* cam9, const float* scale_factors, int nlevels, float log_scale_factor, float th,
+                        int32_t* match12);                                      /* ORBmatcher.cc:1238-1487 */
+int   oc_search_for_initialization(const OcKeyPoint* kps1, const uint8_t* desc1, int n1,
+                                   const OcKeyPoint* kps2, const uint8_t* desc2, int n2, const float* bounds4,
+                                   float* prev, int window, float nnratio, int check_orientation, int32_t* match12);
+                                                                                /* ORBmatcher.cc:442-587 */
+
 #ifdef __cplusplus
 }
 #endif

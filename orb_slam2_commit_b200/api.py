@@ -126,6 +126,12 @@ def lib():
                                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orbx_search_for_triangulation_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [f32p, f32p, C.c_int, C.c_int,
                                                                                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orbx_search_by_projection_kf.argtypes = [C.c_void_p, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.orbx_search_by_projection_kf_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        L.orbx_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, f32p, f32p, f32p, f32p, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                          C.c_void_p, C.c_int]
+        L.orbx_search_for_initialization.argtypes = [C.c_void_p, f32p, C.c_float, C.c_int, C.c_int]
+        L.orbx_search_for_initialization_device.argtypes = [C.c_void_p, C.c_int, f32p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.orbx_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
         L.orbx_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
         L.orbx_peer_hamming_top2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
@@ -520,6 +526,93 @@ def fuse_search(kps, desc, u_right, Tcw12, Ow3, cam9, scale_factors, inv_level_s
     _ck(lib().orbx_fuse_search(C.byref(J), cam.ctypes.data_as(f32p), sf.ctypes.data_as(f32p), s2.ctypes.data_as(f32p), len(sf),
                                float(log_scale_factor), device))
     return int(nf[0]), bi[:npts], bd[:npts]
+
+
+class OrbxProjectionJob(C.Structure):
+    """include/orbx.h OrbxProjectionJob"""
+    _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("occupied", C.c_void_p), ("n", C.c_int32),
+                ("Tcw", C.c_float * 12), ("Ow", C.c_float * 3),
+                ("pt_xyz", C.c_void_p), ("pt_normal", C.c_void_p), ("pt_dist", C.c_void_p), ("pt_descriptors", C.c_void_p),
+                ("pt_flags", C.c_void_p), ("pt_angle", C.c_void_p), ("npts", C.c_int32), ("th", C.c_float),
+                ("max_dist", C.c_int32), ("mode", C.c_int32), ("match", C.c_void_p), ("nmatches", C.c_void_p)]
+
+
+def search_by_projection_kf(kps, desc, occupied, Tcw12, Ow3, cam9, scale_factors, log_scale_factor, pt_xyz, pt_normal, pt_dist,
+                            pt_desc, pt_flags, pt_angle, th, max_dist, mode, check_orientation=True, device: int = 0):
+    """mode 0: ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1648-1795);
+    mode 1: ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (:327-440). -> (nmatches, match)"""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = None if pt_normal is None else np.ascontiguousarray(pt_normal, np.float32)
+    dst = np.ascontiguousarray(pt_dist, np.float32); pd = np.ascontiguousarray(pt_desc, np.uint8)
+    pf = np.ascontiguousarray(pt_flags, np.uint8); pa = None if pt_angle is None else np.ascontiguousarray(pt_angle, np.float32)
+    match = np.zeros(max(len(kps), 1), np.int32); nm = np.zeros(1, np.int32)
+    J = OrbxProjectionJob()
+    J.keypoints = kps.ctypes.data; J.descriptors = desc.ctypes.data; J.occupied = None if occ is None else occ.ctypes.data; J.n = len(kps)
+    J.Tcw = (C.c_float * 12)(*np.asarray(Tcw12, np.float32).ravel().tolist())
+    J.Ow = (C.c_float * 3)(*np.asarray(Ow3, np.float32).ravel().tolist())
+    J.pt_xyz = xyz.ctypes.data; J.pt_normal = None if nrm is None else nrm.ctypes.data; J.pt_dist = dst.ctypes.data
+    J.pt_descriptors = pd.ctypes.data; J.pt_flags = pf.ctypes.data; J.pt_angle = None if pa is None else pa.ctypes.data
+    J.npts = len(pf); J.th = th; J.max_dist = max_dist; J.mode = mode
+    J.match = match.ctypes.data; J.nmatches = nm.ctypes.data
+    _ck(lib().orbx_search_by_projection_kf(C.byref(J), cam.ctypes.data_as(f32p), sf.ctypes.data_as(f32p), len(sf),
+                                           float(log_scale_factor), int(check_orientation), device))
+    return int(nm[0]), match[:len(kps)]
+
+
+class OrbxSim3KeyFrame(C.Structure):
+    """include/orbx.h OrbxSim3KeyFrame"""
+    _fields_ = [("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("n", C.c_int32), ("mp_xyz", C.c_void_p),
+                ("mp_dist", C.c_void_p), ("mp_descriptors", C.c_void_p), ("mp_flags", C.c_void_p), ("Tcw", C.c_float * 12)]
+
+
+def search_by_sim3(kf1, kf2, S12, S21, cam9, scale_factors, log_scale_factor, th, device: int = 0):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1238-1487). kf1 / kf2: dicts with kps, desc, mp_xyz, mp_dist, mp_desc, mp_flags,
+    Tcw12. S12 = (sR12, t12), S21 = (sR21, t21): 12 floats each. -> (nFound, match12)"""
+    keep = []
+
+    def pack(k):
+        K = OrbxSim3KeyFrame()
+        a = [np.ascontiguousarray(k["kps"], KP_DTYPE), np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["mp_xyz"], np.float32),
+             np.ascontiguousarray(k["mp_dist"], np.float32), np.ascontiguousarray(k["mp_desc"], np.uint8), np.ascontiguousarray(k["mp_flags"], np.uint8)]
+        keep.append(a)
+        K.keypoints, K.descriptors, K.mp_xyz, K.mp_dist, K.mp_descriptors, K.mp_flags = [x.ctypes.data for x in a]
+        K.n = len(a[0]); K.Tcw = (C.c_float * 12)(*np.asarray(k["Tcw12"], np.float32).ravel().tolist())
+        return K
+    K1, K2 = pack(kf1), pack(kf2)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    s12 = np.ascontiguousarray(S12, np.float32); s21 = np.ascontiguousarray(S21, np.float32)
+    match = np.zeros(max(K1.n, 1), np.int32); nf = np.zeros(1, np.int32)
+    _ck(lib().orbx_search_by_sim3(C.byref(K1), C.byref(K2), s12.ctypes.data_as(f32p), s21.ctypes.data_as(f32p), cam.ctypes.data_as(f32p),
+                                  sf.ctypes.data_as(f32p), len(sf), float(log_scale_factor), th, match.ctypes.data, nf.ctypes.data, device))
+    return int(nf[0]), match[:K1.n]
+
+
+class OrbxInitPair(C.Structure):
+    """include/orbx.h OrbxInitPair"""
+    _fields_ = [("keypoints1", C.c_void_p), ("descriptors1", C.c_void_p), ("n1", C.c_int32),
+                ("keypoints2", C.c_void_p), ("descriptors2", C.c_void_p), ("n2", C.c_int32),
+                ("prev_matched", C.c_void_p), ("prev_matched_out", C.c_void_p), ("window_size", C.c_int32),
+                ("match12", C.c_void_p), ("nmatches", C.c_void_p)]
+
+
+def search_for_initialization(kps1, desc1, kps2, desc2, bounds4, prev_matched, window_size=100, nnratio=0.9, check_orientation=True,
+                              device: int = 0):
+    """ORBmatcher(nnratio, checkOri).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+    (ORBmatcher.cc:442-587) -> (nmatches, vnMatches12, updated vbPrevMatched)."""
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    b4 = np.ascontiguousarray(bounds4, np.float32)
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    match = np.zeros(max(len(kps1), 1), np.int32); nm = np.zeros(1, np.int32)
+    Q = OrbxInitPair()
+    Q.keypoints1 = kps1.ctypes.data; Q.descriptors1 = desc1.ctypes.data; Q.n1 = len(kps1)
+    Q.keypoints2 = kps2.ctypes.data; Q.descriptors2 = desc2.ctypes.data; Q.n2 = len(kps2)
+    Q.prev_matched = prev.ctypes.data; Q.prev_matched_out = prev.ctypes.data; Q.window_size = window_size
+    Q.match12 = match.ctypes.data; Q.nmatches = nm.ctypes.data
+    _ck(lib().orbx_search_for_initialization(C.byref(Q), b4.ctypes.data_as(f32p), nnratio, int(check_orientation), device))
+    return int(nm[0]), match[:len(kps1)], prev
 
 
 class ORBVocabulary:

@@ -213,11 +213,32 @@ struct OrbxFuseCam {
 };
 struct OrbxFuseDev {
     const OrbxKp28* kps; const uint8_t* desc; const float* u_right; int n;
-    float Tcw[12], Ow[3], th; int mode;
+    float Tcw[12], T2[12], Ow[3], th; int mode;
     const float* pt_xyz; const float* pt_normal; const float* pt_dist; const uint8_t* pt_desc; const uint8_t* pt_flags; int npts;
     int* best_idx; int* best_dist; int* nfound;
 };
 void orbx_launch_fuse_search(const OrbxFuseDev* d_jobs, int njobs, int max_n, const OrbxFuseCam& cam, cudaStream_t st);
+
+void orbx_launch_sim3_mutual(const int* d_match1, int n1, const int* d_match2, int n2, int* d_match12, int* d_nfound, cudaStream_t st);
+struct OrbxSeqProjDev {        // SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (mode 0) / (pKF, Scw, vpPoints, vpMatched, th) (mode 1)
+    const OrbxKp28* kps; const uint8_t* desc; const uint8_t* occupied; int n;
+    float Tcw[12], Ow[3], th; int mode, th_dist, check_orientation;
+    const float* pt_xyz; const float* pt_normal; const float* pt_dist; const uint8_t* pt_desc; const uint8_t* pt_flags;
+    const float* pt_angle; int npts;
+    int* match; int* nmatches;
+    OrbxProjQuery* query; int* assign;            // scratch, npts entries each
+};
+void orbx_launch_seq_projection(const OrbxSeqProjDev* d_jobs, int njobs, int max_n, const OrbxFuseCam& cam, cudaStream_t st);
+struct OrbxInitPairDev {       // ORBmatcher::SearchForInitialization
+    const OrbxKp28* kps1; const uint8_t* desc1; int n1;
+    const OrbxKp28* kps2; const uint8_t* desc2; int n2;
+    const float* prev; float* prev_out;           // vbPrevMatched in / out: 2 floats per F1 keypoint
+    int window;
+    int* match12; int* nmatches;
+    int* bin_of;                                  // scratch, n1 entries
+};
+void orbx_launch_init_match(const OrbxInitPairDev* d_pairs, int npairs, int max_n2, const float* bounds4, float nnratio,
+                            int check_orientation, cudaStream_t st);
 
 // cv::undistortPoints(src, dst, K, D, Mat(), K): intrinsics and (k1, k2, p1, p2, k3) widened to f64 on the host
 struct OrbxUndistortArgs { double fx, fy, cx, cy, ifx, ify, k[5]; };

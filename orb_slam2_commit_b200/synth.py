@@ -425,3 +425,134 @@ def synth_triangulation_scene(voc, seed: int, n_points: int = 1200, n_extra: int
     geom = np.concatenate([F12.ravel(), Cw1, R2.astype(np.float32).ravel(), t2.astype(np.float32), np.array([fx, fy, cx, cy], np.float32)])
     out.update(geom28=geom.astype(np.float32), scale_factors=sf, level_sigma2=s2)
     return out
+
+
+def synth_kf_projection_scene(seed: int, n_points: int = 1200, n_extra: int = 500, cluster: float = 0.3):
+    """Inputs of ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1648-1795) and
+    of SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (:327-440): the scene of synth_fuse_scene plus near-duplicate
+    points that compete for one feature (the sequential occupancy rule), features that are occupied beforehand and the
+    keyframe-side angles for the rotation check. Returns the keyword arguments of api.search_by_projection_kf (without th,
+    max_dist, mode, check_orientation)."""
+    s = synth_fuse_scene(seed, n_points=n_points, n_extra=n_extra, stereo=False)
+    rng = np.random.default_rng(seed + 104729)
+    n_dup = int(n_points * cluster)
+    src = rng.integers(0, n_points, n_dup)
+    xyz = np.concatenate([s["pt_xyz"], s["pt_xyz"][src] + rng.normal(0, 0.002, (n_dup, 3)).astype(np.float32)])
+    d = s["pt_desc"][src].copy()
+    for i in range(n_dup):
+        for b in rng.integers(0, 256, rng.integers(0, 5)):
+            d[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    order = rng.permutation(n_points + n_dup)
+    cat = lambda a, b: np.concatenate([a, b])[order]
+    out = dict(kps=s["kps"], desc=s["desc"], occupied=(rng.random(len(s["kps"])) < 0.08).astype(np.uint8), Tcw12=s["Tcw12"], Ow3=s["Ow3"],
+               cam9=s["cam9"], scale_factors=s["scale_factors"], log_scale_factor=s["log_scale_factor"],
+               pt_xyz=xyz[order], pt_normal=cat(s["pt_normal"], s["pt_normal"][src]), pt_dist=cat(s["pt_dist"], s["pt_dist"][src]),
+               pt_desc=cat(s["pt_desc"], d), pt_flags=cat(s["pt_flags"], s["pt_flags"][src]),
+               pt_angle=None)
+    # angles: features around 10 deg, keyframe side around 45 deg (10 % anywhere), so that the rotation histogram has dominant bins
+    kps = out["kps"].copy(); kps["angle"] = rng.normal(10, 8, len(kps)) % 360; out["kps"] = kps
+    npt = n_points + n_dup
+    out["pt_angle"] = np.where(rng.random(npt) < 0.1, rng.uniform(0, 360, npt), rng.normal(45, 12, npt) % 360).astype(np.float32)
+    return out
+
+
+def synth_sim3_scene(seed: int, n_points: int = 1500, n_extra: int = 300):
+    """Inputs of ORBmatcher::SearchBySim3 (ORBmatcher.cc:1238-1487): two keyframes of one camera that see the same map points
+    from two poses related by a similarity (scale drift 3 %). Every feature of a keyframe may hold a map point (mp_*).
+    Returns (kf1, kf2, S12, S21, cam9, scale_factors, log_scale_factor)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, mbf = 517.306408, 516.469215, 318.643040, 255.313989, 40.0
+    W, H = 640.0, 480.0
+    nlevels = 8
+    sf = (np.float32(1.2) ** np.arange(nlevels)).astype(np.float32)
+    log_sf = np.float32(np.log(np.float32(1.2)))
+    kp_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                         ("octave", "<i4"), ("class_id", "<i4")])
+    a = 0.08
+    R1 = np.eye(3); t1 = np.array([0.05, 0.0, 0.1])
+    R2 = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]); t2 = np.array([-0.4, 0.03, 0.2])
+    z = rng.uniform(2.0, 12.0, n_points)
+    Xw = np.stack([(rng.uniform(-60, W + 60, n_points) - cx) / fx * z, (rng.uniform(-60, H + 60, n_points) - cy) / fy * z, z], 1)
+    pdesc = rng.integers(0, 256, (n_points, 32), dtype=np.uint8)
+    lvl = rng.integers(0, nlevels, n_points)
+    kfs = []
+    for R, t in ((R1, t1), (R2, t2)):
+        pc = Xw @ R.T + t
+        dist = np.linalg.norm(pc, axis=1)
+        u = fx * pc[:, 0] / pc[:, 2] + cx; v = fy * pc[:, 1] / pc[:, 2] + cy
+        vis = np.flatnonzero((pc[:, 2] > 0.3) & (u > 1) & (u < W - 1) & (v > 1) & (v < H - 1) & (rng.random(n_points) < 0.85))
+        n = len(vis) + n_extra
+        kps = np.zeros(n, kp_dtype)
+        max_d = (dist * sf[lvl] * rng.uniform(0.9, 1.1, n_points)).astype(np.float32)
+        ratio = max_d[vis] / dist[vis].astype(np.float32)
+        pred = np.clip(np.ceil(np.log(ratio) / log_sf), 0, nlevels - 1).astype(np.int64)
+        kps["octave"][:len(vis)] = np.clip(pred - rng.integers(0, 3, len(vis)), 0, nlevels - 1)
+        jit = sf[kps["octave"][:len(vis)]]
+        kps["x"][:len(vis)] = u[vis] + rng.normal(0, 1.0, len(vis)) * jit; kps["y"][:len(vis)] = v[vis] + rng.normal(0, 1.0, len(vis)) * jit
+        kps["x"][len(vis):] = rng.uniform(0, W, n_extra); kps["y"][len(vis):] = rng.uniform(0, H, n_extra)
+        kps["octave"][len(vis):] = rng.integers(0, nlevels, n_extra)
+        desc = np.concatenate([pdesc[vis], rng.integers(0, 256, (n_extra, 32), dtype=np.uint8)])
+        for i in range(len(vis)):
+            for b in rng.integers(0, 256, rng.integers(0, 80)):
+                desc[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        # the map point each feature holds: its own point for most, a random other point or none for the rest
+        own = np.concatenate([vis, rng.integers(0, n_points, n_extra)])
+        wrong = rng.random(n) < 0.1
+        own[wrong] = rng.integers(0, n_points, int(wrong.sum()))
+        min_d = (max_d / sf[nlevels - 1]).astype(np.float32)
+        mp_dist = np.stack([np.float32(0.8) * min_d[own], np.float32(1.2) * max_d[own], max_d[own]], 1).astype(np.float32)
+        flags = (rng.random(n) < 0.8).astype(np.uint8)
+        perm = rng.permutation(n)
+        kfs.append(dict(kps=kps[perm], desc=desc[perm], mp_xyz=Xw[own].astype(np.float32)[perm], mp_dist=mp_dist[perm],
+                        mp_desc=pdesc[own][perm], mp_flags=flags[perm], Tcw12=np.concatenate([R.ravel(), t]).astype(np.float32)))
+    s12 = np.float32(1.03)
+    R12 = (R1 @ R2.T).astype(np.float32); t12 = (t1 - (R1 @ R2.T) @ t2).astype(np.float32)
+    sR12 = (s12 * R12).astype(np.float32)
+    sR21 = ((np.float64(1.0) / np.float64(s12)) * R12.T.astype(np.float64)).astype(np.float32)
+    t21 = (-(sR21.astype(np.float64) @ t12.astype(np.float64))).astype(np.float32)
+    S12 = np.concatenate([sR12.ravel(), t12]).astype(np.float32); S21 = np.concatenate([sR21.ravel(), t21]).astype(np.float32)
+    cam9 = np.array([fx, fy, cx, cy, mbf, 0.0, W, 0.0, H], np.float32)
+    return kfs[0], kfs[1], S12, S21, cam9, sf, float(log_sf)
+
+
+def synth_initialization_scene(seed: int, n: int = 1500, cluster: float = 0.25):
+    """Inputs of ORBmatcher::SearchForInitialization (ORBmatcher.cc:442-587): an initial frame and a current frame a small
+    image motion away; half of the keypoints on level 0; `cluster` of the F1 keypoints are near-duplicates of another one
+    (close by, near-identical descriptor), so that F2 keypoints change hands during the loop.
+    Returns the keyword arguments of api.search_for_initialization (without window_size / nnratio / check_orientation)."""
+    rng = np.random.default_rng(seed)
+    W, H = 640.0, 480.0
+    kp_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                         ("octave", "<i4"), ("class_id", "<i4")])
+    n_base = int(n * (1 - cluster))
+    x = rng.uniform(20, W - 20, n_base); y = rng.uniform(20, H - 20, n_base)
+    d = rng.integers(0, 256, (n_base, 32), dtype=np.uint8)
+    octv = np.where(rng.random(n_base) < 0.55, 0, rng.integers(1, 8, n_base))
+    ang = rng.uniform(0, 360, n_base)
+    dup = rng.integers(0, n_base, n - n_base)
+    x1 = np.concatenate([x, x[dup] + rng.normal(0, 3, len(dup))]); y1 = np.concatenate([y, y[dup] + rng.normal(0, 3, len(dup))])
+    d1 = np.concatenate([d, d[dup]])
+    for i in range(n_base, n):
+        for b in rng.integers(0, 256, rng.integers(0, 6)):
+            d1[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    o1 = np.concatenate([octv, octv[dup]]); a1 = np.concatenate([ang, ang[dup]])
+    p1 = rng.permutation(n)
+    k1 = np.zeros(n, kp_dtype); k1["x"] = x1[p1]; k1["y"] = y1[p1]; k1["octave"] = o1[p1]; k1["angle"] = a1[p1]; d1 = d1[p1]
+    # F2: the base keypoints moved by a smooth flow, descriptors with noise, some dropped, some new
+    keep = rng.random(n_base) < 0.85
+    n_new = 300
+    k2 = np.zeros(int(keep.sum()) + n_new, kp_dtype)
+    m = int(keep.sum())
+    k2["x"][:m] = x[keep] + 12 + 0.02 * (y[keep] - H / 2) + rng.normal(0, 1, m); k2["y"][:m] = y[keep] - 6 + rng.normal(0, 1, m)
+    k2["octave"][:m] = octv[keep]
+    k2["angle"][:m] = (ang[keep] + rng.normal(5, 3, m) + (rng.random(m) < 0.1) * rng.uniform(0, 360, m)) % 360
+    k2["x"][m:] = rng.uniform(0, W, n_new); k2["y"][m:] = rng.uniform(0, H, n_new)
+    k2["octave"][m:] = np.where(rng.random(n_new) < 0.55, 0, rng.integers(1, 8, n_new)); k2["angle"][m:] = rng.uniform(0, 360, n_new)
+    d2 = np.concatenate([d[keep], rng.integers(0, 256, (n_new, 32), dtype=np.uint8)])
+    for i in range(m):
+        for b in rng.integers(0, 256, rng.integers(0, 50)):
+            d2[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    p2 = rng.permutation(len(k2))
+    k2, d2 = k2[p2], d2[p2]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)                      # Tracking.cc: mvbPrevMatched[i] = mInitialFrame.mvKeysUn[i].pt
+    return dict(kps1=k1, desc1=d1, kps2=k2, desc2=d2, bounds4=np.array([0.0, W, 0.0, H], np.float32), prev_matched=prev)

@@ -139,3 +139,83 @@ def test_search_for_triangulation_matches_oracle(seed, stereo):
     s4["u_right2"] = None if s["u_right2"] is None else s["u_right2"][:0]
     n, m = V.search_for_triangulation(**s4, levelsup=2)
     assert n == 0 and (m == -1).all()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_search_by_projection_kf_matches_oracle(seed):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1648-1795, mode 0) and
+    SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (:327-440, mode 1): gates, PredictScale, level ranges, the
+    sequential "feature already holds a map point" rule under contention, the rotation check of mode 0."""
+    from orb_slam2_commit_b200 import search_by_projection_kf
+    s = synth.synth_kf_projection_scene(seed)
+    for mode, th, md, ori in ((0, 10.0, 100, True), (0, 3.0, 64, False), (0, 10.0, 100, False), (1, 10.0, 50, True), (1, 4.0, 50, True)):
+        n, m = search_by_projection_kf(**s, th=th, max_dist=md, mode=mode, check_orientation=ori)
+        no, mo = ob.search_by_projection_kf(**s, th=th, max_dist=md, mode=mode, check_orientation=ori)
+        assert n == no, f"seed {seed} mode {mode} th {th}: {n} vs {no}"
+        assert np.array_equal(m, mo), f"seed {seed} mode {mode} th {th}: {np.count_nonzero(m != mo)} assignments differ"
+        assert n > 100 and n == np.count_nonzero(m >= 0)
+    # heavy contention: all points are copies of 30 points
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, 30, len(s["pt_flags"]))
+    s2 = dict(s)
+    for k in ("pt_xyz", "pt_normal", "pt_dist", "pt_desc", "pt_flags", "pt_angle"):
+        s2[k] = s[k][pick]
+    s2["pt_flags"] = np.ones_like(s2["pt_flags"])
+    for mode, md in ((0, 100), (1, 50)):
+        n, m = search_by_projection_kf(**s2, th=15.0, max_dist=md, mode=mode)
+        no, mo = ob.search_by_projection_kf(**s2, th=15.0, max_dist=md, mode=mode)
+        assert n == no and np.array_equal(m, mo)
+    # degenerate
+    e = dict(s); e["pt_flags"] = np.zeros_like(s["pt_flags"])
+    n, m = search_by_projection_kf(**e, th=10.0, max_dist=100, mode=0)
+    assert n == 0 and (m == -1).all()
+    e = dict(s); e["kps"] = s["kps"][:0]; e["desc"] = s["desc"][:0]; e["occupied"] = None
+    n, m = search_by_projection_kf(**e, th=10.0, max_dist=50, mode=1)
+    assert n == 0 and len(m) == 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_search_by_sim3_matches_oracle(seed):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1238-1487): both projection directions through the similarity and the
+    mutual-consistency check."""
+    from orb_slam2_commit_b200 import search_by_sim3
+    k1, k2, S12, S21, cam, sf, lsf = synth.synth_sim3_scene(seed)
+    for th in (7.5, 3.0, 15.0):
+        n, m = search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, th)
+        no, mo = ob.search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, th)
+        assert n == no and np.array_equal(m, mo), f"seed {seed} th {th}: {n} vs {no}, {np.count_nonzero(m != mo)} differ"
+        assert n == np.count_nonzero(m >= 0)
+    assert n > 50
+    e1 = {k: (v[:0] if k != "Tcw12" else v) for k, v in k1.items()}
+    n, m = search_by_sim3(e1, k2, S12, S21, cam, sf, lsf, 7.5)
+    assert n == 0 and len(m) == 0
+    e2 = {k: (v[:0] if k != "Tcw12" else v) for k, v in k2.items()}
+    n, m = search_by_sim3(k1, e2, S12, S21, cam, sf, lsf, 7.5)
+    assert n == 0 and (m == -1).all()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_search_for_initialization_matches_oracle(seed):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:442-587): level-0 keypoints only, the sequential vMatchedDistance /
+    vnMatches21 rule (matches change hands), NN ratio, rotation histogram over every push, vbPrevMatched update."""
+    from orb_slam2_commit_b200 import search_for_initialization
+    s = synth.synth_initialization_scene(seed)
+    for win, nnr, ori in ((100, 0.9, True), (100, 0.9, False), (30, 0.7, True), (1000, 0.99, True)):
+        n, m, p = search_for_initialization(**s, window_size=win, nnratio=nnr, check_orientation=ori)
+        no, mo, po = ob.search_for_initialization(**s, window_size=win, nnratio=nnr, check_orientation=ori)
+        assert n == no, f"seed {seed} window {win}: {n} vs {no}"
+        assert np.array_equal(m, mo), f"seed {seed} window {win}: {np.count_nonzero(m != mo)} differ"
+        assert np.array_equal(p.view(np.uint32), po.view(np.uint32))
+        assert n == np.count_nonzero(m >= 0) and n > 100
+    # second call with the updated vbPrevMatched, as Tracking::MonocularInitialization does on the next frame
+    s2 = dict(s); s2["prev_matched"] = p
+    n, m, p2 = search_for_initialization(**s2, window_size=100)
+    no, mo, po2 = ob.search_for_initialization(**s2, window_size=100)
+    assert n == no and np.array_equal(m, mo) and np.array_equal(p2, po2)
+    # degenerate: no level-0 keypoints in F1 / empty F2
+    e = dict(s); k = s["kps1"].copy(); k["octave"] = 1; e["kps1"] = k
+    n, m, _ = search_for_initialization(**e)
+    assert n == 0 and (m == -1).all()
+    e = dict(s); e["kps2"] = s["kps2"][:0]; e["desc2"] = s["desc2"][:0]
+    n, m, _ = search_for_initialization(**e)
+    assert n == 0 and (m == -1).all()
