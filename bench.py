@@ -44,6 +44,9 @@ WORKLOADS = {
     # ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on synthetic tracking scenes (1000 map points,
     # ~1100 current keypoints, 30 % near-duplicate map points): one CTA per frame pair
     "tum1_track": dict(cfg="tum1", batch=1024, distinct=8, track=True),
+    # the other ORBmatcher functions, each batched one CTA per call: SearchByProjection(F, vpMapPoints) [SearchLocalPoints],
+    # Fuse (search half), SearchByProjection(CurrentFrame, pKF, ..) [relocalisation], SearchForInitialization
+    "tum1_matchers": dict(cfg="tum1", batch=1024, distinct=8, matchers=True),
 }
 
 
@@ -471,6 +474,142 @@ def run_track(args, torch, dist, rank, world, local, dev):
     emit_json_line(line)
 
 
+def run_matchers(args, torch, dist, rank, world, local, dev):
+    """The window matchers of ORBmatcher beyond the frame-to-frame one, device-resident and batched (one CTA per call):
+    headline = SearchByProjection(F, vpMapPoints, th) as Tracking::SearchLocalPoints calls it; the others in `others`."""
+    import ctypes as C
+    from orb_slam2_commit_b200 import api, search_local_points
+    w = WORKLOADS[args.workload]
+    P = args.batch or w["batch"]
+    L = api.lib()
+    keep = []
+    f32p = C.POINTER(C.c_float)
+
+    def dev_t(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev); keep.append(t); return t.data_ptr()
+
+    def fp(a):
+        a = np.ascontiguousarray(a, np.float32); keep.append(a); return a.ctypes.data_as(f32p)
+    ts = torch.cuda.Stream(device=dev); torch.cuda.set_stream(ts); st = ts.cuda_stream
+    nd = w["distinct"]
+    # ---- SearchLocalPoints
+    lp = [synth.synth_local_points_scene(21 + i + 100 * rank) for i in range(nd)]
+    lpd = [{k: (None if v is None else dev_t(v)) for k, v in sc.items() if k not in ("bounds4", "scale_factors")} for sc in lp]
+    frames = (api.OrbxLocalPointsFrame * P)()
+    d_match = torch.zeros((P, max(len(s_["kps"]) for s_ in lp)), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(P, dtype=torch.int32, device=dev)
+    for i in range(P):
+        sc, d = lp[i % nd], lpd[i % nd]; f = frames[i]
+        f.keypoints = d["kps"]; f.descriptors = d["desc"]; f.u_right = d["u_right"]; f.occupied = d["occupied"]; f.n = len(sc["kps"])
+        f.queries = d["queries"]; f.query_descriptors = d["query_desc"]; f.query_flags = d["query_flags"]; f.nq = len(sc["queries"])
+        f.match = d_match[i].data_ptr(); f.nmatches = d_nm[i:].data_ptr()
+    b4, sf = fp(lp[0]["bounds4"]), fp(lp[0]["scale_factors"])
+
+    def step_local():
+        api._ck(L.orbx_search_local_points_device(frames, P, b4, sf, 8, 1.0, 0.8, local, st))
+    # ---- Fuse (search half) and the relocalisation matcher share one scene family
+    fs = [synth.synth_kf_projection_scene(31 + i + 100 * rank) for i in range(nd)]
+    fsd = [{k: dev_t(v) for k, v in sc.items() if k in ("kps", "desc", "occupied", "pt_xyz", "pt_normal", "pt_dist", "pt_desc", "pt_flags", "pt_angle")} for sc in fs]
+    fj = (api.OrbxFuseJob * P)(); pj = (api.OrbxProjectionJob * P)()
+    npt = max(len(s_["pt_flags"]) for s_ in fs)
+    d_bi = torch.zeros((P, npt), dtype=torch.int32, device=dev); d_bd = torch.zeros((P, npt), dtype=torch.int32, device=dev)
+    d_nf = torch.zeros(P, dtype=torch.int32, device=dev)
+    d_m2 = torch.zeros((P, max(len(s_["kps"]) for s_ in fs)), dtype=torch.int32, device=dev); d_nm2 = torch.zeros(P, dtype=torch.int32, device=dev)
+    for i in range(P):
+        sc, d = fs[i % nd], fsd[i % nd]
+        for j in (fj[i], pj[i]):
+            j.keypoints = d["kps"]; j.descriptors = d["desc"]; j.n = len(sc["kps"])
+            j.Tcw = (C.c_float * 12)(*sc["Tcw12"].tolist()); j.Ow = (C.c_float * 3)(*sc["Ow3"].tolist())
+            j.pt_xyz = d["pt_xyz"]; j.pt_normal = d["pt_normal"]; j.pt_dist = d["pt_dist"]; j.pt_descriptors = d["pt_desc"]
+            j.pt_flags = d["pt_flags"]; j.npts = len(sc["pt_flags"]); j.mode = 0
+        fj[i].u_right = None; fj[i].th = 3.0
+        fj[i].best_idx = d_bi[i].data_ptr(); fj[i].best_dist = d_bd[i].data_ptr(); fj[i].nfused = d_nf[i:].data_ptr()
+        pj[i].occupied = d["occupied"]; pj[i].pt_angle = d["pt_angle"]; pj[i].th = 10.0; pj[i].max_dist = 100
+        pj[i].match = d_m2[i].data_ptr(); pj[i].nmatches = d_nm2[i:].data_ptr()
+    cam9, sff, is2 = fp(fs[0]["cam9"]), fp(fs[0]["scale_factors"]), fp(1.0 / (fs[0]["scale_factors"] ** 2))
+    lsf = fs[0]["log_scale_factor"]
+
+    def step_fuse():
+        api._ck(L.orbx_fuse_search_device(fj, P, cam9, sff, is2, 8, lsf, local, st))
+
+    def step_reloc():
+        api._ck(L.orbx_search_by_projection_kf_device(pj, P, cam9, sff, 8, lsf, 1, local, st))
+    # ---- SearchForInitialization
+    ini = [synth.synth_initialization_scene(41 + i + 100 * rank) for i in range(nd)]
+    inid = [{k: dev_t(v) for k, v in sc.items() if k != "bounds4"} for sc in ini]
+    ip = (api.OrbxInitPair * P)()
+    d_m3 = torch.zeros((P, max(len(s_["kps1"]) for s_ in ini)), dtype=torch.int32, device=dev); d_nm3 = torch.zeros(P, dtype=torch.int32, device=dev)
+    d_prev = torch.zeros((P, max(len(s_["kps1"]) for s_ in ini), 2), dtype=torch.float32, device=dev)
+    for i in range(P):
+        sc, d = ini[i % nd], inid[i % nd]; q = ip[i]
+        q.keypoints1 = d["kps1"]; q.descriptors1 = d["desc1"]; q.n1 = len(sc["kps1"]); q.keypoints2 = d["kps2"]; q.descriptors2 = d["desc2"]
+        q.n2 = len(sc["kps2"]); q.prev_matched = d["prev_matched"]; q.prev_matched_out = d_prev[i].data_ptr(); q.window_size = 100
+        q.match12 = d_m3[i].data_ptr(); q.nmatches = d_nm3[i:].data_ptr()
+    ib4 = fp(ini[0]["bounds4"])
+
+    def step_init():
+        api._ck(L.orbx_search_for_initialization_device(ip, P, ib4, 0.9, 1, local, st))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps):
+        for _ in range(args.warmup): step()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps): step()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    sampler = ClockSampler(local); sampler.start()
+    ms_total = timed(step_local, args.steps)
+    clocks = sampler.stop()
+    value = world * P * args.steps / (ms_total * 1e-3)
+    others = {}
+    for name, step in (("fuse_search", step_fuse), ("search_by_projection_kf_relocalisation", step_reloc), ("search_for_initialization", step_init)):
+        ms = timed(step, max(5, args.steps // 5))
+        others[name] = {"calls_per_s": world * P * max(5, args.steps // 5) / (ms * 1e-3), "ms_per_launch": ms / max(5, args.steps // 5), "calls_per_launch": P}
+    others["fuse_search"]["fused_per_call"] = float(d_nf.float().mean().item())
+    others["search_by_projection_kf_relocalisation"]["matches_per_call"] = float(d_nm2.float().mean().item())
+    others["search_for_initialization"]["matches_per_call"] = float(d_nm3.float().mean().item())
+    n_e2e = 200; t0 = time.perf_counter()
+    for i in range(n_e2e):
+        search_local_points(**lp[i % nd], th=1.0, nnratio=0.8, device=local)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_v = world * n_e2e / float(t.item())
+    if rank != 0: return
+    sc0 = lp[0]
+    line = {"metric": "search_local_points_calls_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"SearchByProjection(F, vpMapPoints, th=1): {len(sc0['queries'])} local map points x {len(sc0['kps'])} keypoints "
+                                   f"per frame (Tracking::SearchLocalPoints), 30 % near-duplicate points, stereo gate on",
+                       "frames_per_step_per_gpu": P, "distinct_scenes": nd},
+            "clocks": clocks, "gpu_launches": args.steps,
+            "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(sum(np.asarray(v).nbytes for v in sc0.values() if v is not None)),
+                    "d2h_bytes_per_step": 4 * len(sc0["kps"]) + 4, "steps": n_e2e, "api": "orbx_search_local_points (one frame per call, synchronous)"},
+            "pipeline": {"matches_per_frame": float(d_nm.float().mean().item())}, "others": others}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        nthreads = os.cpu_count() or 1
+        secs = min(args.cpu_seconds, 4.0)
+        v, sample = cpu_thread_bench(lambda tid: (lambda i: ob.search_local_points(**lp[i % nd], th=1.0, nnratio=0.8)), secs, nthreads)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
+        v, _ = cpu_thread_bench(lambda tid: (lambda i: ob.fuse_search(**{k: x for k, x in fs[i % nd].items() if k not in ("occupied", "pt_angle")}, u_right=None, inv_level_sigma2=1.0 / (fs[0]["scale_factors"] ** 2), th=3.0, mode=0)), 2.0, nthreads)
+        others["fuse_search"]["cpu_calls_per_s"] = v
+        v, _ = cpu_thread_bench(lambda tid: (lambda i: ob.search_by_projection_kf(**fs[i % nd], th=10.0, max_dist=100, mode=0)), 2.0, nthreads)
+        others["search_by_projection_kf_relocalisation"]["cpu_calls_per_s"] = v
+        v, _ = cpu_thread_bench(lambda tid: (lambda i: ob.search_for_initialization(**ini[i % nd])), 2.0, nthreads)
+        others["search_for_initialization"]["cpu_calls_per_s"] = v
+    emit_json_line(line)
+
+
 def run_stereo(args, torch, dist, rank, world, local, dev):
     """Stereo pairs/s: two extractor instances (as the reference, Tracking.cc:120-123) + the device-resident matcher."""
     from orb_slam2_commit_b200 import ORBextractor, api, stereo_match_device
@@ -611,9 +750,10 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    if WORKLOADS[args.workload].get("stereo") or WORKLOADS[args.workload].get("frame") or WORKLOADS[args.workload].get("track"):
+    if any(WORKLOADS[args.workload].get(k) for k in ("stereo", "frame", "track", "matchers")):
         wl = WORKLOADS[args.workload]
-        (run_stereo if wl.get("stereo") else run_frame if wl.get("frame") else run_track)(args, torch, dist, rank, world, local, dev)
+        (run_stereo if wl.get("stereo") else run_frame if wl.get("frame") else run_track if wl.get("track") else run_matchers)(
+            args, torch, dist, rank, world, local, dev)
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return

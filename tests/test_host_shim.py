@@ -16,6 +16,7 @@ MAIN = textwrap.dedent(r"""
     #include "HammingTop2.h"
     #include "StereoMatch.h"
     #include "FrameOps.h"
+    #include "MatcherOps.h"
     #include <cstdio>
     int main() {
         ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 20, 7);
@@ -36,6 +37,18 @@ MAIN = textwrap.dedent(r"""
         std::map<unsigned int, double> bow; std::map<unsigned int, std::vector<unsigned int> > fv;
         ok = ok && ORB_SLAM2::ComputeBoWGPU(0, desc, bow, fv) && ORB_SLAM2::ExtractRectified(&ex, empty, kps, desc);
         std::printf("%d %d %.0f %.0f %.0f %.0f\n", (int)ok, nm, a, b, c, d);
+        // the ORBmatcher wrappers (MatcherOps.h): empty inputs return 0 without touching the GPU
+        ORB_SLAM2::MapPointTable pts; ORB_SLAM2::KeyFrameCamera kc; std::memcpy(kc.camera9, cam, sizeof cam);
+        kc.mvScaleFactors = sf2; kc.mvLevelSigma2 = sf2; kc.mvInvLevelSigma2 = sf2; kc.mfLogScaleFactor = 0.18f;
+        std::vector<OrbxTrackQuery> tq; std::vector<unsigned char> hm; std::vector<std::pair<size_t, size_t> > vp; std::vector<cv::Point2f> prev;
+        const float b4[4] = {0, 640, 0, 480}, ow[3] = {0, 0, 0}, g28[28] = {0};
+        int r = ORB_SLAM2::SearchByProjectionGPU(none, desc, 0, 0, b4, sf2, tq, d8, fl, 1.f, 0.8f, match);
+        r += ORB_SLAM2::FuseSearchGPU(none, desc, 0, T, ow, kc, pts, 3.f, false, match);
+        r += ORB_SLAM2::SearchByProjectionGPU(none, desc, 0, T, ow, kc, pts, 0, 10.f, 100, false, true, match);
+        r += ORB_SLAM2::SearchForTriangulationGPU(0, none, desc, hm, 0, none, desc, hm, 0, g28, kc, false, true, vp);
+        r += ORB_SLAM2::SearchForInitializationGPU(none, desc, none, desc, b4, prev, match, 100, 0.9f, true);
+        std::printf("%d %zu\n", r, sizeof(cv::Point2f));
+        (void)&ORB_SLAM2::SearchBySim3GPU;
         return 0;
     }
 """)
@@ -61,3 +74,4 @@ def test_shim_compiles_links_and_matches_getters(tmp_path):
     assert np.float32(float(f[4])) == t["sigma2"][7] and np.float32(float(f[5])) == t["inv_sigma2"][7]
     assert out[1].split() == ["3", "1"]
     assert out[2].split() == ["1", "0", "0", "640", "0", "480"]       # Frame.cc:530-536 without distortion
+    assert out[3].split() == ["0", "8"]                               # five matcher wrappers on empty inputs; Point2f = 2 packed floats

@@ -4,7 +4,7 @@
 # gpurun_out/<tag>_*; tools/ncu_summary.py / tools/ncu_phases.py condense it into profiles/ afterwards.
 # ncu runs only after the same command has exited 0 without it; numbers printed under ncu are never bench values.
 T=${1:-r01}; O=gpurun_out; mkdir -p $O
-for w in tum1 euroc kitti 4k kitti_stereo euroc_stereo euroc_rect tum1_frame tum1_track; do
+for w in tum1 euroc kitti 4k kitti_stereo euroc_stereo euroc_rect tum1_frame tum1_track tum1_matchers; do
   extra=""; [ "$w" != tum1 ] && extra="--no-hamming"
   python bench.py --workload $w $extra > $O/${T}_bench_$w.json 2> $O/${T}_bench_$w.err || echo "bench $w FAILED"
 done
