@@ -14,6 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liborb_oracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "liborb_ref.so")
+MATCHER_REF_LIB = os.path.join(HERE, "_ref", "libmatcher_ref.so")
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
@@ -34,6 +35,12 @@ def build(force: bool = False) -> None:
             stale = (not os.path.exists(REF_LIB)) or any(os.path.getmtime(REF_LIB) < os.path.getmtime(s) for s in srcs)
             if force or stale:
                 subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/src/ORBmatcher.cc"):
+        srcs = [os.path.join(HERE, "matcher_glue.cc")] + [os.path.join(HERE, "slamshim", f) for f in
+                                                          ("Frame.h", "KeyFrame.h", "MapPoint.h", "opencv2/core/core.hpp")]
+        stale = (not os.path.exists(MATCHER_REF_LIB)) or any(os.path.getmtime(MATCHER_REF_LIB) < os.path.getmtime(s) for s in srcs)
+        if force or stale:
+            subprocess.check_call(["make", "-C", HERE, "ref_matcher"], stdout=subprocess.DEVNULL)
 
 
 _lib = None
@@ -579,3 +586,186 @@ def search_for_initialization(kps1, desc1, kps2, desc2, bounds4, prev_matched, w
     n = f(kps1.ctypes.data, desc1.ctypes.data, len(kps1), kps2.ctypes.data, desc2.ctypes.data, len(kps2), b4.ctypes.data,
           prev.ctypes.data, window_size, nnratio, int(check_orientation), match.ctypes.data)
     return n, match[:len(kps1)], prev
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref/libmatcher_ref.so: the UNMODIFIED reference ORBmatcher.cc behind oracle/matcher_glue.cc (see its header).
+_mref = None
+
+
+def matcher_ref():
+    """ctypes handle of the verbatim-reference matcher build, or None when it has not been built (no reference tree)."""
+    global _mref
+    if _mref is None:
+        build()
+        if not os.path.exists(MATCHER_REF_LIB):
+            return None
+        _mref = C.CDLL(MATCHER_REF_LIB)
+    return _mref
+
+
+def _dist4(pt_dist_raw):
+    """(mfMinDistance, mfMaxDistance) per point -> rows (0.8f*min, 1.2f*max, max, min) as MapPoint.cc:395-405 return them"""
+    raw = np.ascontiguousarray(pt_dist_raw, np.float32).reshape(-1, 2)
+    return np.stack([np.float32(0.8) * raw[:, 0], np.float32(1.2) * raw[:, 1], raw[:, 1], raw[:, 0]], 1).astype(np.float32)
+
+
+def ref_search_local_points(kps, desc, u_right, occupied, bounds4, scale_factors, queries, query_desc, query_flags, th, nnratio=0.8):
+    R = matcher_ref()
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    b4 = np.ascontiguousarray(bounds4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    q = np.ascontiguousarray(queries, TRACKQ_DTYPE); qd = np.ascontiguousarray(query_desc, np.uint8); qf = np.ascontiguousarray(query_flags, np.uint8)
+    q4 = np.ascontiguousarray(np.stack([q["proj_x"], q["proj_y"], q["proj_xr"], q["view_cos"]], 1), np.float32)
+    ql = np.ascontiguousarray(q["level"], np.int32)
+    match = np.zeros(max(len(kps), 1), np.int32)
+    f = R.mref_search_local_points
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_float, C.c_float, C.c_void_p]
+    n = f(kps.ctypes.data, desc.ctypes.data, len(kps), _p(ur), _p(occ), b4.ctypes.data, sf.ctypes.data, len(sf), q4.ctypes.data, ql.ctypes.data,
+          qd.ctypes.data, qf.ctypes.data, len(q), th, nnratio, match.ctypes.data)
+    return n, match[:len(kps)]
+
+
+def ref_search_by_projection_frame(cur_kps, cur_desc, cur_u_right, cur_occupied, Tcw12, cam9, scale_factors, last_kps, last_xyz,
+                                   last_desc, last_flags, th, mono, tlw_z, check_orientation=True):
+    """-> (nmatches, match_cur, mode the reference derived from tlc)"""
+    R = matcher_ref()
+    cur_kps = np.ascontiguousarray(cur_kps, KP_DTYPE); last_kps = np.ascontiguousarray(last_kps, KP_DTYPE)
+    cur_desc = np.ascontiguousarray(cur_desc, np.uint8); last_desc = np.ascontiguousarray(last_desc, np.uint8)
+    ur = None if cur_u_right is None else np.ascontiguousarray(cur_u_right, np.float32)
+    occ = None if cur_occupied is None else np.ascontiguousarray(cur_occupied, np.uint8)
+    T = np.ascontiguousarray(Tcw12, np.float32); cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    xyz = np.ascontiguousarray(last_xyz, np.float32); fl = np.ascontiguousarray(last_flags, np.uint8)
+    match = np.zeros(max(len(cur_kps), 1), np.int32); mode = C.c_int32(0)
+    f = R.mref_search_by_projection_frame
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_float, C.c_int, C.c_float,
+                                                                                                    C.c_int, C.c_void_p, C.c_void_p]
+    n = f(cur_kps.ctypes.data, cur_desc.ctypes.data, len(cur_kps), _p(ur), _p(occ), T.ctypes.data, cam.ctypes.data, sf.ctypes.data, len(sf),
+          last_kps.ctypes.data, xyz.ctypes.data, last_desc.ctypes.data, fl.ctypes.data, len(last_kps), th, int(mono), tlw_z,
+          int(check_orientation), match.ctypes.data, C.addressof(mode))
+    return n, match[:len(cur_kps)], mode.value
+
+
+def ref_fuse(kps, desc, u_right, T12, Ow3, cam9, scale_factors, inv_level_sigma2, log_scale_factor, pt_xyz, pt_normal, pt_dist_raw,
+             pt_desc, pt_flags, th, mode):
+    """T12: the keyframe pose (mode 0) or the 3x4 top of Scw (mode 1). pt_dist_raw: (mfMinDistance, mfMaxDistance) per point.
+    -> (nFused, best_idx, Tcw12 and Ow3 as the reference derived them, pt_dist rows for the restatement)"""
+    R = matcher_ref()
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    T = np.ascontiguousarray(T12, np.float32); Ow = np.zeros(3, np.float32) if Ow3 is None else np.ascontiguousarray(Ow3, np.float32)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = np.ascontiguousarray(pt_normal, np.float32)
+    d4 = _dist4(pt_dist_raw); pd = np.ascontiguousarray(pt_desc, np.uint8); pf = np.ascontiguousarray(pt_flags, np.uint8)
+    bi = np.zeros(max(len(pf), 1), np.int32); To = np.zeros(12, np.float32); Oo = np.zeros(3, np.float32)
+    f = R.mref_fuse
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_float] + [C.c_void_p] * 5 + [C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 3
+    n = f(kps.ctypes.data, desc.ctypes.data, len(kps), _p(ur), T.ctypes.data, Ow.ctypes.data, cam.ctypes.data, sf.ctypes.data, s2.ctypes.data,
+          len(sf), float(log_scale_factor), xyz.ctypes.data, nrm.ctypes.data, d4.ctypes.data, pd.ctypes.data, pf.ctypes.data, len(pf), th, mode,
+          bi.ctypes.data, To.ctypes.data, Oo.ctypes.data)
+    return n, bi[:len(pf)], To, Oo, np.ascontiguousarray(d4[:, :3])
+
+
+def ref_search_by_projection_kf(kps, desc, occupied, T12, cam9, scale_factors, log_scale_factor, pt_xyz, pt_normal, pt_dist_raw, pt_desc,
+                                pt_flags, pt_angle, th, max_dist, mode, check_orientation=True):
+    """-> (nmatches, match, Tcw12, Ow3 as derived by the reference, pt_dist rows for the restatement)"""
+    R = matcher_ref()
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    T = np.ascontiguousarray(T12, np.float32); cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = None if pt_normal is None else np.ascontiguousarray(pt_normal, np.float32)
+    d4 = _dist4(pt_dist_raw); pd = np.ascontiguousarray(pt_desc, np.uint8); pf = np.ascontiguousarray(pt_flags, np.uint8)
+    pa = None if pt_angle is None else np.ascontiguousarray(pt_angle, np.float32)
+    match = np.zeros(max(len(kps), 1), np.int32); To = np.zeros(12, np.float32); Oo = np.zeros(3, np.float32)
+    f = R.mref_search_by_projection_seq
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_float] + [C.c_void_p] * 6 + \
+        [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3
+    n = f(kps.ctypes.data, desc.ctypes.data, len(kps), _p(occ), T.ctypes.data, cam.ctypes.data, sf.ctypes.data, len(sf), float(log_scale_factor),
+          xyz.ctypes.data, _p(nrm), d4.ctypes.data, pd.ctypes.data, pf.ctypes.data, _p(pa), len(pf), th, max_dist, mode, int(check_orientation),
+          match.ctypes.data, To.ctypes.data, Oo.ctypes.data)
+    return n, match[:len(kps)], To, Oo, np.ascontiguousarray(d4[:, :3])
+
+
+def ref_search_by_sim3(kf1, kf2, s12, R12, t12, cam9, scale_factors, log_scale_factor, th):
+    """kf dicts as for search_by_sim3 but with mp_dist_raw = (mfMinDistance, mfMaxDistance). -> (nFound, match12, S12, S21, dist rows 1, 2)"""
+    R = matcher_ref()
+
+    def arrs(k):
+        return [np.ascontiguousarray(k["kps"], KP_DTYPE), np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["mp_xyz"], np.float32),
+                _dist4(k["mp_dist_raw"]), np.ascontiguousarray(k["mp_desc"], np.uint8), np.ascontiguousarray(k["mp_flags"], np.uint8)]
+    a, b = arrs(kf1), arrs(kf2)
+    T1 = np.ascontiguousarray(kf1["Tcw12"], np.float32); T2 = np.ascontiguousarray(kf2["Tcw12"], np.float32)
+    R12 = np.ascontiguousarray(R12, np.float32); t12 = np.ascontiguousarray(t12, np.float32)
+    cam = np.ascontiguousarray(cam9, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    match = np.zeros(max(len(a[0]), 1), np.int32); S12 = np.zeros(12, np.float32); S21 = np.zeros(12, np.float32)
+    f = R.mref_search_by_sim3
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+        [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float] + [C.c_void_p] * 3
+    n = f(a[0].ctypes.data, a[1].ctypes.data, len(a[0]), a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data, a[5].ctypes.data,
+          b[0].ctypes.data, b[1].ctypes.data, len(b[0]), b[2].ctypes.data, b[3].ctypes.data, b[4].ctypes.data, b[5].ctypes.data,
+          T1.ctypes.data, T2.ctypes.data, float(s12), R12.ctypes.data, t12.ctypes.data, cam.ctypes.data, sf.ctypes.data, len(sf),
+          float(log_scale_factor), th, match.ctypes.data, S12.ctypes.data, S21.ctypes.data)
+    return n, match[:len(a[0])], S12, S21, np.ascontiguousarray(a[3][:, :3]), np.ascontiguousarray(b[3][:, :3])
+
+
+def ref_search_for_triangulation(t1, t2, kps1, desc1, has_mp1, u_right1, kps2, desc2, has_mp2, u_right2, geom28, scale_factors,
+                                 level_sigma2, only_stereo=False, check_orientation=True):
+    R = matcher_ref()
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    m1 = None if has_mp1 is None else np.ascontiguousarray(has_mp1, np.uint8); m2 = None if has_mp2 is None else np.ascontiguousarray(has_mp2, np.uint8)
+    r1 = None if u_right1 is None else np.ascontiguousarray(u_right1, np.float32); r2 = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+    g = np.ascontiguousarray(geom28, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32); s2 = np.ascontiguousarray(level_sigma2, np.float32)
+    a = [np.ascontiguousarray(t1[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    b = [np.ascontiguousarray(t2[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    match = np.zeros(max(len(kps1), 1), np.int32)
+    f = R.mref_search_for_triangulation
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + \
+        [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    n = f(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, len(b[0]),
+          kps1.ctypes.data, desc1.ctypes.data, _p(m1), _p(r1), len(kps1), kps2.ctypes.data, desc2.ctypes.data, _p(m2), _p(r2), len(kps2),
+          g.ctypes.data, sf.ctypes.data, s2.ctypes.data, len(sf), int(only_stereo), int(check_orientation), match.ctypes.data)
+    return n, match[:len(kps1)]
+
+
+def ref_search_for_initialization(kps1, desc1, kps2, desc2, bounds4, prev_matched, window_size=100, nnratio=0.9, check_orientation=True):
+    R = matcher_ref()
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    b4 = np.ascontiguousarray(bounds4, np.float32)
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    match = np.zeros(max(len(kps1), 1), np.int32)
+    f = R.mref_search_for_initialization
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = f(kps1.ctypes.data, desc1.ctypes.data, len(kps1), kps2.ctypes.data, desc2.ctypes.data, len(kps2), b4.ctypes.data, prev.ctypes.data,
+          window_size, nnratio, int(check_orientation), match.ctypes.data)
+    return n, match[:len(kps1)], prev
+
+
+def ref_search_by_bow(t1, t2, kps1, desc1, valid1, kps2, desc2, valid2, nnratio, check_orientation, kf_mode):
+    """kf_mode 0: SearchByBoW(pKF, F, ..) -> match indexed by F's features; 1: SearchByBoW(pKF1, pKF2, ..) -> indexed by pKF1's"""
+    R = matcher_ref()
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8); v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+    a = [np.ascontiguousarray(t1[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    b = [np.ascontiguousarray(t2[k], np.int32) for k in ("fv_node", "fv_off", "fv_feat")]
+    nout = len(kps1) if kf_mode else len(kps2)
+    match = np.zeros(max(nout, 1), np.int32)
+    f = R.mref_search_by_bow
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + \
+        [C.c_float, C.c_int, C.c_int, C.c_void_p]
+    n = f(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, len(b[0]),
+          kps1.ctypes.data, desc1.ctypes.data, _p(v1), len(kps1), kps2.ctypes.data, desc2.ctypes.data, _p(v2), len(kps2), nnratio,
+          int(check_orientation), kf_mode, match.ctypes.data)
+    return n, match[:nout]

@@ -1535,7 +1535,9 @@ int oc_fuse_search(const OcKeyPoint* kps, const uint8_t* desc, int n, const floa
     const float fx = cam9[0], fy = cam9[1], cx = cam9[2], cy = cam9[3], bf = cam9[4];
     const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
     const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
-    OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);
+    OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);      /* the Frame's grid, copied by KeyFrame.cc:52-57 */
+    /* KeyFrame.h:236-239 keeps the bounds as const int: IsInImage and GetFeaturesInArea see the truncated values */
+    const int kMinX = (int)mnMinX, kMaxX = (int)mnMaxX, kMinY = (int)mnMinY, kMaxY = (int)mnMaxY;
     int nFused = 0;
     for (int i = 0; i < npts; i++) {
         int bestDist = mode == 0 ? 256 : INT_MAX, bestIdx = -1;
@@ -1553,7 +1555,7 @@ int oc_fuse_search(const OcKeyPoint* kps, const uint8_t* desc, int n, const floa
         const float invz = mode == 0 ? 1 / c3[2] : (float)(1.0 / c3[2]);          /* :954 / :1146 */
         const float x = c3[0] * invz, y = c3[1] * invz;
         const float u = fx * x + cx, v = fy * y + cy;
-        if (!(u >= mnMinX && u < mnMaxX && v >= mnMinY && v < mnMaxY)) continue;  /* KeyFrame::IsInImage */
+        if (!(u >= kMinX && u < kMaxX && v >= kMinY && v < kMaxY)) continue;      /* KeyFrame::IsInImage */
         const float ur = u - bf * invz;
         const float maxDistance = pt_dist[3 * i + 1], minDistance = pt_dist[3 * i];
         const float PO[3] = {X - Ow3[0], Y - Ow3[1], Z - Ow3[2]};
@@ -1567,7 +1569,7 @@ int oc_fuse_search(const OcKeyPoint* kps, const uint8_t* desc, int n, const floa
         const int nPredictedLevel = oc_predict_scale(pt_dist[3 * i + 2], dist3D, log_scale_factor, nlevels);
         const float radius = th * scale_factors[nPredictedLevel];
         int x0, x1, y0, y1;
-        if (!oc_grid_window(u, v, radius, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        if (!oc_grid_window(u, v, radius, (float)kMinX, (float)kMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
         for (int ix = x0; ix <= x1; ix++)
             for (int iy = y0; iy <= y1; iy++) {
                 const int c = ix * FRAME_GRID_ROWS + iy;
@@ -1700,6 +1702,7 @@ int oc_search_by_projection_seq(const OcKeyPoint* kps, const uint8_t* desc, int 
     const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
     const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
     OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);
+    const int kMinX = (int)mnMinX, kMaxX = (int)mnMaxX, kMinY = (int)mnMinY, kMaxY = (int)mnMaxY;   /* KeyFrame bounds (mode 1) */
     uint8_t* occ = (uint8_t*)calloc((size_t)(n > 0 ? n : 1), 1);
     for (int i = 0; i < n; i++) { match[i] = -1; occ[i] = occupied ? (occupied[i] != 0) : 0; }
     int nmatches = 0, nh = 0, count[HISTO_LENGTH] = {0};
@@ -1726,7 +1729,7 @@ int oc_search_by_projection_seq(const OcKeyPoint* kps, const uint8_t* desc, int 
             const float invz = 1 / c3[2];
             const float x = c3[0] * invz, y = c3[1] * invz;
             u = fx * x + cx; v = fy * y + cy;
-            if (!(u >= mnMinX && u < mnMaxX && v >= mnMinY && v < mnMaxY)) continue;
+            if (!(u >= kMinX && u < kMaxX && v >= kMinY && v < kMaxY)) continue;
         }
         const float PO[3] = {X - Ow3[0], Y - Ow3[1], Z - Ow3[2]};
         double s2 = 0.0;
@@ -1742,7 +1745,7 @@ int oc_search_by_projection_seq(const OcKeyPoint* kps, const uint8_t* desc, int 
         const float radius = th * scale_factors[nPredictedLevel];
         const int minLevel = nPredictedLevel - 1, maxLevel = mode == 0 ? nPredictedLevel + 1 : nPredictedLevel;
         int x0, x1, y0, y1;
-        if (!oc_grid_window(u, v, radius, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        if (!oc_grid_window(u, v, radius, mode == 0 ? mnMinX : (float)kMinX, mode == 0 ? mnMinY : (float)kMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
         int bestDist = 256, bestIdx = -1;
         for (int ix = x0; ix <= x1; ix++)
             for (int iy = y0; iy <= y1; iy++) {
@@ -1789,6 +1792,7 @@ static void sim3_direction(const OcKeyPoint* kps, const uint8_t* desc, int n, co
     const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
     const float invW = (float)FRAME_GRID_COLS / (mnMaxX - mnMinX), invH = (float)FRAME_GRID_ROWS / (mnMaxY - mnMinY);
     OcGrid g = oc_grid_build(kps, n, mnMinX, mnMinY, invW, invH);
+    const int kMinX = (int)mnMinX, kMaxX = (int)mnMaxX, kMinY = (int)mnMinY, kMaxY = (int)mnMaxY;   /* KeyFrame bounds */
     for (int i = 0; i < npts; i++) {
         vnMatch[i] = -1;
         if (!(pt_flags[i] & 1)) continue;                         /* NULL, already matched or bad */
@@ -1810,7 +1814,7 @@ static void sim3_direction(const OcKeyPoint* kps, const uint8_t* desc, int n, co
         const float invz = (float)(1.0 / c3[2]);
         const float x = c3[0] * invz, y = c3[1] * invz;
         const float u = fx * x + cx, v = fy * y + cy;
-        if (!(u >= mnMinX && u < mnMaxX && v >= mnMinY && v < mnMaxY)) continue;
+        if (!(u >= kMinX && u < kMaxX && v >= kMinY && v < kMaxY)) continue;
         double s2 = 0.0;
         for (int k = 0; k < 3; k++) s2 += (double)c3[k] * (double)c3[k];
         const float dist3D = (float)sqrt(s2);
@@ -1818,7 +1822,7 @@ static void sim3_direction(const OcKeyPoint* kps, const uint8_t* desc, int n, co
         const int nPredictedLevel = oc_predict_scale(pt_dist[3 * i + 2], dist3D, log_scale_factor, nlevels);
         const float radius = th * scale_factors[nPredictedLevel];
         int x0, x1, y0, y1;
-        if (!oc_grid_window(u, v, radius, mnMinX, mnMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
+        if (!oc_grid_window(u, v, radius, (float)kMinX, (float)kMinY, invW, invH, &x0, &x1, &y0, &y1)) continue;
         int bestDist = INT_MAX, bestIdx = -1;
         for (int ix = x0; ix <= x1; ix++)
             for (int iy = y0; iy <= y1; iy++) {

@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(512) fuse_search_kernel(const OrbxFuseDev* __r
     const float invW = __fdiv_rn(64.0f, __fsub_rn(cam.maxX, cam.minX)), invH = __fdiv_rn(48.0f, __fsub_rn(cam.maxY, cam.minY));
     if (tid == 0) s_found = 0;
     grid_build(P.kps, P.n, cam.minX, cam.minY, invW, invH, G, s_w);
+    // KeyFrame keeps the image bounds as `const int` (KeyFrame.h:236-239, initialised from the Frame's floats): its grid is
+    // the Frame's (float bounds, above), but IsInImage and GetFeaturesInArea compare against the truncated values
+    const float kminX = (float)(int)cam.minX, kmaxX = (float)(int)cam.maxX, kminY = (float)(int)cam.minY, kmaxY = (float)(int)cam.maxY;
     const uint4* kdesc = reinterpret_cast<const uint4*>(P.desc);
     const uint4* pdesc = reinterpret_cast<const uint4*>(P.pt_desc);
     int mine = 0;
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(512) fuse_search_kernel(const OrbxFuseDev* __r
             const float invz = P.mode == 0 ? __fdiv_rn(1.0f, c3[2]) : __double2float_rn(__ddiv_rn(1.0, (double)c3[2]));
             const float x = __fmul_rn(c3[0], invz), y = __fmul_rn(c3[1], invz);
             const float u = __fadd_rn(__fmul_rn(cam.fx, x), cam.cx), v = __fadd_rn(__fmul_rn(cam.fy, y), cam.cy);
-            if (!(u >= cam.minX && u < cam.maxX && v >= cam.minY && v < cam.maxY)) break;      // KeyFrame::IsInImage
+            if (!(u >= kminX && u < kmaxX && v >= kminY && v < kmaxY)) break;                  // KeyFrame::IsInImage
             const float ur = __fsub_rn(u, __fmul_rn(cam.bf, invz));
             // PO = p3Dw - Ow; SearchBySim3 measures the point in the target camera instead: cv::norm(p3Dc2) (:1318)
             const float po0 = P.mode == 2 ? c3[0] : __fsub_rn(X, P.Ow[0]), po1 = P.mode == 2 ? c3[1] : __fsub_rn(Y, P.Ow[1]),
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(512) fuse_search_kernel(const OrbxFuseDev* __r
             for (int n = 0; n < cam.nlevels - 1; n++) level += (ratio >= cam.level_ratio[n]) ? 1 : 0;
             const float radius = __fmul_rn(P.th, cam.scale_factors[level]);
             int cx0, cx1, cy0, cy1;
-            if (!grid_window(u, v, radius, cam.minX, cam.minY, invW, invH, cx0, cx1, cy0, cy1)) break;
+            if (!grid_window(u, v, radius, kminX, kminY, invW, invH, cx0, cx1, cy0, cy1)) break;
             const uint4 qa = pdesc[2 * (size_t)pi], qb = pdesc[2 * (size_t)pi + 1];
             for (int ix = cx0; ix <= cx1; ix++) {
                 const int j0 = G.cstart[ix * GRID_ROWS + cy0], j1 = G.cstart[ix * GRID_ROWS + cy1 + 1];
@@ -272,6 +275,10 @@ __global__ void __launch_bounds__(512) seq_projection_kernel(const OrbxSeqProjDe
     if (tid < 32) s_hist[tid] = 0;
     if (tid == 0) { s_success = 0; s_removed = 0; }
     grid_build(P.kps, P.n, cam.minX, cam.minY, invW, invH, G, s_w);
+    // mode 1 searches a KeyFrame, whose bounds are the Frame's truncated to int (see fuse_search_kernel)
+    const bool kf = P.mode == 1;
+    const float wminX = kf ? (float)(int)cam.minX : cam.minX, wmaxX = kf ? (float)(int)cam.maxX : cam.maxX,
+                wminY = kf ? (float)(int)cam.minY : cam.minY, wmaxY = kf ? (float)(int)cam.maxY : cam.maxY;
     // ---- projection and gates of every map point
     for (int pi = tid; pi < P.npts; pi += blockDim.x) {
         OrbxProjQuery q; q.r = -1.f; q.u = q.v = q.ur = 0.f; q.min_level = q.max_level = -1;
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(512) seq_projection_kernel(const OrbxSeqProjDe
                 const float invz = __fdiv_rn(1.0f, c3[2]);
                 const float x = __fmul_rn(c3[0], invz), y = __fmul_rn(c3[1], invz);
                 u = __fadd_rn(__fmul_rn(cam.fx, x), cam.cx); v = __fadd_rn(__fmul_rn(cam.fy, y), cam.cy);
-                if (!(u >= cam.minX && u < cam.maxX && v >= cam.minY && v < cam.maxY)) break;
+                if (!(u >= wminX && u < wmaxX && v >= wminY && v < wmaxY)) break;
             }
             const float po0 = __fsub_rn(X, P.Ow[0]), po1 = __fsub_rn(Y, P.Ow[1]), po2 = __fsub_rn(Z, P.Ow[2]);
             double s2 = __dmul_rn((double)po0, (double)po0);
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(512) seq_projection_kernel(const OrbxSeqProjDe
             if (q.r < 0.f) continue;
             int cx0, cx1, cy0, cy1;
             int bestDist = 256, bestIdx = -1;
-            if (grid_window(q.u, q.v, q.r, cam.minX, cam.minY, invW, invH, cx0, cx1, cy0, cy1)) {
+            if (grid_window(q.u, q.v, q.r, wminX, wminY, invW, invH, cx0, cx1, cy0, cy1)) {
                 const uint4 qa = pdesc[2 * (size_t)qi], qb = pdesc[2 * (size_t)qi + 1];
                 for (int ix = cx0; ix <= cx1; ix++) {
                     const int j0 = G.cstart[ix * GRID_ROWS + cy0], j1 = G.cstart[ix * GRID_ROWS + cy1 + 1];

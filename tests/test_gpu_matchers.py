@@ -219,3 +219,34 @@ def test_search_for_initialization_matches_oracle(seed):
     e = dict(s); e["kps2"] = s["kps2"][:0]; e["desc2"] = s["desc2"][:0]
     n, m, _ = search_for_initialization(**e)
     assert n == 0 and (m == -1).all()
+
+
+def test_keyframe_side_matchers_with_non_integer_image_bounds():
+    """A distorted camera has non-integer undistorted bounds. KeyFrame keeps them as `const int` (KeyFrame.h:236-239) while
+    its grid is the Frame's (float bounds): Fuse, the loop-closing SearchByProjection and SearchBySim3 must build the grid
+    with the floats and test IsInImage / the window cells with the truncated values; the Frame-side matchers use the floats
+    throughout. (tests/test_matcher_ref.py pins the oracle's handling to the reference itself.)"""
+    from orb_slam2_commit_b200 import search_by_projection_kf, search_by_sim3
+    bounds = np.array([-3.6, 643.2, -2.7, 482.9], np.float32)
+    s = synth.synth_fuse_scene(11)
+    s["cam9"] = s["cam9"].copy(); s["cam9"][5:9] = bounds
+    for mode in (0, 1):
+        n, bi, bd = fuse_search(**s, th=4.0, mode=mode)
+        no, bio, bdo = ob.fuse_search(**s, th=4.0, mode=mode)
+        assert n == no and np.array_equal(bi, bio) and np.array_equal(bd, bdo) and n > 100
+    p = synth.synth_kf_projection_scene(12)
+    p["cam9"] = p["cam9"].copy(); p["cam9"][5:9] = bounds
+    for mode, md in ((0, 100), (1, 50)):
+        n, m = search_by_projection_kf(**p, th=10.0, max_dist=md, mode=mode)
+        no, mo = ob.search_by_projection_kf(**p, th=10.0, max_dist=md, mode=mode)
+        assert n == no and np.array_equal(m, mo) and n > 100
+    k1, k2, S12, S21, cam, sf, lsf = synth.synth_sim3_scene(13)
+    cam = cam.copy(); cam[5:9] = bounds
+    n, m = search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, 7.5)
+    no, mo = ob.search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, 7.5)
+    assert n == no and np.array_equal(m, mo) and n > 30
+    lp = synth.synth_local_points_scene(14)
+    lp["bounds4"] = bounds
+    n, m = search_local_points(**lp, th=3.0)
+    no, mo = ob.search_local_points(**lp, th=3.0)
+    assert n == no and np.array_equal(m, mo) and n > 200

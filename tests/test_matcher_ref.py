@@ -1,0 +1,190 @@
+"""CPU-only: the oracle's matcher restatements (oracle/orb_oracle.c) against the UNMODIFIED reference ORBmatcher.cc, compiled
+here from /root/reference by oracle/Makefile (target ref_matcher) against the stub classes of oracle/slamshim — every public
+function of ORBmatcher, on the same seeded scenes the GPU parity tests use. This is what pins the control flow of the
+restatements (and through them the CUDA kernels) to the reference itself. Skipped where oracle/_ref/libmatcher_ref.so is
+absent and cannot be built (no reference tree)."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from orb_slam2_commit_b200 import synth
+
+pytestmark = pytest.mark.skipif(ob.matcher_ref() is None, reason="oracle/_ref/libmatcher_ref.so not built (reference tree absent)")
+
+ODD_BOUNDS = (-3.6, 643.2, -2.7, 482.9)     # undistorted-image bounds are not integers for a distorted camera (Frame.cc:508-538)
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False)])
+def test_search_local_points_restatement_equals_reference(seed, stereo):
+    s = synth.synth_local_points_scene(seed, stereo=stereo)
+    for bounds in (None, ODD_BOUNDS):
+        if bounds:
+            s = dict(s); s["bounds4"] = np.array(bounds, np.float32)
+        for th, nnratio in ((1.0, 0.8), (3.0, 0.8), (5.0, 0.6)):
+            n, m = ob.search_local_points(**s, th=th, nnratio=nnratio)
+            nr, mr = ob.ref_search_local_points(**s, th=th, nnratio=nnratio)
+            assert n == nr and np.array_equal(m, mr), (seed, th, n, nr)
+            assert n > 200
+    for bit in (2, 0):
+        s2 = dict(s); s2["query_flags"] = (s["query_flags"] & 1) | bit
+        assert ob.search_local_points(**s2, th=5.0)[0] == ob.ref_search_local_points(**s2, th=5.0)[0]
+        assert np.array_equal(ob.search_local_points(**s2, th=5.0)[1], ob.ref_search_local_points(**s2, th=5.0)[1])
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False)])
+def test_search_by_projection_frame_restatement_equals_reference(seed, stereo):
+    s = synth.synth_tracking_scene(seed, stereo=stereo)
+    seen = set()
+    for mono, tlw_z in ((1, 0.0), (0, 0.0), (0, 5.0), (0, -5.0)):
+        for th, ori in ((7.0, True), (15.0, False)):
+            nr, mr, mode = ob.ref_search_by_projection_frame(**s, th=th, mono=mono, tlw_z=tlw_z, check_orientation=ori)
+            n, m = ob.search_by_projection_frame(**s, th=th, mode=mode, check_orientation=ori)
+            assert n == nr and np.array_equal(m, mr), (seed, mono, tlw_z, th, n, nr)
+            seen.add(mode)
+    assert seen == {0, 1, 2}
+
+
+def _raw_dist(s, rng):
+    """(mfMinDistance, mfMaxDistance) per point for a fuse-type scene; a few points get a range that excludes them"""
+    mx = s["pt_dist"][:, 2].copy()
+    mn = (mx / s["scale_factors"][-1]).astype(np.float32)
+    far = rng.random(len(mx)) < 0.06
+    mx[far] *= np.float32(0.4)
+    return np.stack([mn, mx], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False)])
+def test_fuse_restatement_equals_reference(seed, stereo):
+    s = synth.synth_fuse_scene(seed, stereo=stereo)
+    raw = _raw_dist(s, np.random.default_rng(seed))
+    for bounds in (None, ODD_BOUNDS):
+        cam = s["cam9"].copy()
+        if bounds:
+            cam[5:9] = bounds
+        for th in (3.0, 10.0):
+            # Fuse(pKF, vpMapPoints, th)
+            nr, bir, T, Ow, d3 = ob.ref_fuse(s["kps"], s["desc"], s["u_right"], s["Tcw12"], s["Ow3"], cam, s["scale_factors"], s["inv_level_sigma2"],
+                                             s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], raw, s["pt_desc"], s["pt_flags"], th, 0)
+            n, bi, _ = ob.fuse_search(s["kps"], s["desc"], s["u_right"], T, Ow, cam, s["scale_factors"], s["inv_level_sigma2"],
+                                      s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], d3, s["pt_desc"], s["pt_flags"], th, 0)
+            assert n == nr and np.array_equal(bi, bir), (seed, th, n, nr, np.count_nonzero(bi != bir))
+            assert n > 100
+            # Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) with Scw = 1.7 * [R | t]
+            Scw = (np.float32(1.7) * s["Tcw12"]).astype(np.float32)
+            nr, bir, T, Ow, d3 = ob.ref_fuse(s["kps"], s["desc"], s["u_right"], Scw, None, cam, s["scale_factors"], s["inv_level_sigma2"],
+                                             s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], raw, s["pt_desc"], s["pt_flags"], th, 1)
+            n, bi, _ = ob.fuse_search(s["kps"], s["desc"], s["u_right"], T, Ow, cam, s["scale_factors"], s["inv_level_sigma2"],
+                                      s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], d3, s["pt_desc"], s["pt_flags"], th, 1)
+            assert n == nr and np.array_equal(bi, bir), (seed, th, n, nr, np.count_nonzero(bi != bir))
+            assert n > 100
+
+
+def test_predict_scale_restatement_equals_reference_across_level_boundaries():
+    """ratios swept finely across every level boundary: the level decides radius and admissible octaves, so an off-by-one in
+    ceil(logf(ratio)/mfLogScaleFactor) changes the picks"""
+    s = synth.synth_fuse_scene(7, n_points=4000, n_extra=100)
+    dist = np.linalg.norm(s["pt_xyz"].astype(np.float64) - s["Ow3"].astype(np.float64), axis=1)
+    md = (dist * np.float64(np.float32(1.2)) ** (np.arange(len(dist)) / 500.0)).astype(np.float32)
+    raw = np.stack([np.zeros_like(md), md], 1)
+    nr, bir, T, Ow, d3 = ob.ref_fuse(s["kps"], s["desc"], s["u_right"], s["Tcw12"], s["Ow3"], s["cam9"], s["scale_factors"], s["inv_level_sigma2"],
+                                     s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], raw, s["pt_desc"], s["pt_flags"], 3.0, 0)
+    d3[:, 1] = md * 100                        # the restatement takes the invariance bounds as given: open the upper one as the sweep needs
+    raw2 = np.stack([np.zeros_like(md), md], 1)
+    n, bi, _ = ob.fuse_search(s["kps"], s["desc"], s["u_right"], T, Ow, s["cam9"], s["scale_factors"], s["inv_level_sigma2"], s["log_scale_factor"],
+                              s["pt_xyz"], s["pt_normal"], np.stack([d3[:, 0], np.float32(1.2) * raw2[:, 1], d3[:, 2]], 1), s["pt_desc"], s["pt_flags"], 3.0, 0)
+    assert n == nr and np.array_equal(bi, bir)
+    assert n > 300
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_search_by_projection_kf_restatement_equals_reference(seed):
+    s = synth.synth_kf_projection_scene(seed)
+    raw = _raw_dist(s, np.random.default_rng(seed))
+    for bounds in (None, ODD_BOUNDS):
+        cam = s["cam9"].copy()
+        if bounds:
+            cam[5:9] = bounds
+        for mode, th, md, ori in ((0, 10.0, 100, True), (0, 3.0, 64, False), (1, 10.0, 50, True), (1, 4.0, 50, True)):
+            T12 = s["Tcw12"] if mode == 0 else (np.float32(0.8) * s["Tcw12"]).astype(np.float32)
+            nr, mr, T, Ow, d3 = ob.ref_search_by_projection_kf(s["kps"], s["desc"], s["occupied"], T12, cam, s["scale_factors"], s["log_scale_factor"],
+                                                               s["pt_xyz"], s["pt_normal"], raw, s["pt_desc"], s["pt_flags"], s["pt_angle"], th, md, mode, ori)
+            n, m = ob.search_by_projection_kf(s["kps"], s["desc"], s["occupied"], T, Ow, cam, s["scale_factors"], s["log_scale_factor"], s["pt_xyz"],
+                                              s["pt_normal"], d3, s["pt_desc"], s["pt_flags"], s["pt_angle"], th, md, mode, ori)
+            assert n == nr and np.array_equal(m, mr), (seed, mode, th, n, nr, np.count_nonzero(m != mr))
+            assert n > 80
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_search_by_sim3_restatement_equals_reference(seed):
+    k1, k2, S12, S21, cam, sf, lsf = synth.synth_sim3_scene(seed)
+    for k in (k1, k2):
+        k["mp_dist_raw"] = np.stack([k["mp_dist"][:, 2] / sf[-1], k["mp_dist"][:, 2]], 1).astype(np.float32)
+    R12 = (S12[:9] / np.float32(1.03)).astype(np.float32); t12 = S12[9:]
+    for bounds in (None, ODD_BOUNDS):
+        c = cam.copy()
+        if bounds:
+            c[5:9] = bounds
+        for th in (7.5, 3.0):
+            nr, mr, S12r, S21r, d1, d2 = ob.ref_search_by_sim3(k1, k2, 1.03, R12, t12, c, sf, lsf, th)
+            a = dict(k1); a["mp_dist"] = d1
+            b = dict(k2); b["mp_dist"] = d2
+            n, m = ob.search_by_sim3(a, b, S12r, S21r, c, sf, lsf, th)
+            assert n == nr and np.array_equal(m, mr), (seed, th, n, nr)
+    assert n > 30
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, False), (2, True)])
+def test_search_for_triangulation_restatement_equals_reference(seed, stereo):
+    voc = synth.synth_vocabulary(10, 4, 5)
+    Vo = ob.Vocabulary(10, 4, *voc)
+    s = synth.synth_triangulation_scene(voc, seed, stereo=stereo)
+    t1, t2 = Vo.transform(s["desc1"], 2), Vo.transform(s["desc2"], 2)
+    for only_stereo, ori in ((False, True), (False, False), (True, True)):
+        n, m = ob.search_for_triangulation(t1, t2, **s, only_stereo=only_stereo, check_orientation=ori)
+        nr, mr = ob.ref_search_for_triangulation(t1, t2, **s, only_stereo=only_stereo, check_orientation=ori)
+        assert n == nr and np.array_equal(m, mr), (seed, only_stereo, ori, n, nr)
+    # equal distances inside a node (the LAST equal candidate wins in the reference)
+    s2 = dict(s); d2 = s["desc2"].copy(); d2[1::2] = d2[0::2][:len(d2[1::2])]; s2["desc2"] = d2
+    k2 = s["kps2"].copy()
+    for f in ("x", "y", "octave"):
+        k2[f][1::2] = k2[f][0::2][:len(k2[f][1::2])]
+    s2["kps2"] = k2
+    t2b = Vo.transform(d2, 2)
+    n, m = ob.search_for_triangulation(t1, t2b, **s2)
+    nr, mr = ob.ref_search_for_triangulation(t1, t2b, **s2)
+    assert n == nr and np.array_equal(m, mr) and n > 50
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_search_for_initialization_restatement_equals_reference(seed):
+    s = synth.synth_initialization_scene(seed)
+    for win, nnr, ori in ((100, 0.9, True), (100, 0.9, False), (30, 0.7, True), (1000, 0.99, True)):
+        n, m, p = ob.search_for_initialization(**s, window_size=win, nnratio=nnr, check_orientation=ori)
+        nr, mr, pr = ob.ref_search_for_initialization(**s, window_size=win, nnratio=nnr, check_orientation=ori)
+        assert n == nr and np.array_equal(m, mr) and np.array_equal(p.view(np.uint32), pr.view(np.uint32)), (seed, win, n, nr)
+        assert n > 100
+
+
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_by_bow_restatements_equal_reference(check_ori):
+    voc = synth.synth_vocabulary(10, 4, 11)
+    Vo = ob.Vocabulary(10, 4, *voc)
+    rng = np.random.default_rng(3)
+    n = 1200
+    d1 = synth.synth_features_near_words(voc, n, 1, max_flips=10)
+    d2 = d1[rng.permutation(n)].copy()
+    for i in range(n):
+        for b in rng.integers(0, 256, rng.integers(0, 20)):
+            d2[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    k1 = np.zeros(n, ob.KP_DTYPE); k2 = np.zeros(n, ob.KP_DTYPE)
+    k1["angle"] = rng.uniform(0, 360, n); k2["angle"] = (k1["angle"] + rng.normal(8, 6, n)) % 360
+    v1 = (rng.random(n) < 0.8).astype(np.uint8); v2 = (rng.random(n) < 0.8).astype(np.uint8)
+    t1, t2 = Vo.transform(d1, 2), Vo.transform(d2, 2)
+    for nnr in (0.7, 0.9):
+        no, mo = ob.search_by_bow(t1, t2, d1, k1["angle"], v1, d2, k2["angle"], nnr, check_ori)
+        nr, mr = ob.ref_search_by_bow(t1, t2, k1, d1, v1, k2, d2, None, nnr, check_ori, 0)
+        assert no == nr and np.array_equal(mo, mr), (nnr, no, nr)
+        no, mo = ob.search_by_bow_kf(t1, t2, d1, k1["angle"], v1, d2, k2["angle"], v2, nnr, check_ori)
+        nr, mr = ob.ref_search_by_bow(t1, t2, k1, d1, v1, k2, d2, v2, nnr, check_ori, 1)
+        assert no == nr and np.array_equal(mo, mr), (nnr, no, nr)
+    assert no > 50
