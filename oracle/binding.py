@@ -769,3 +769,30 @@ def ref_search_by_bow(t1, t2, kps1, desc1, valid1, kps2, desc2, valid2, nnratio,
           kps1.ctypes.data, desc1.ctypes.data, _p(v1), len(kps1), kps2.ctypes.data, desc2.ctypes.data, _p(v2), len(kps2), nnratio,
           int(check_orientation), kf_mode, match.ctypes.data)
     return n, match[:nout]
+
+
+def ref_stereo_match(left: "Extractor", right: "Extractor", kl, dl, kr, dr, mbf, fx):
+    """The verbatim Frame::ComputeStereoMatches (Frame.cc:547-788) on the pyramids of two ORACLE extractors -> (mvuRight, mvDepth)"""
+    R = matcher_ref()
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    n = left.nlevels
+    lv = [(left.level(l), right.level(l)) for l in range(n)]                 # copies incl. the 19-px apron
+    whs = np.zeros((n, 3), np.int32)
+    pl = (C.c_void_p * n)(); pr = (C.c_void_p * n)()
+    for l, (a, b) in enumerate(lv):
+        h, s = a.shape[0] - 38, a.shape[1]
+        w = C.c_int32(); hh = C.c_int32(); ss = C.c_int32()
+        left.L.oc_level_size(left.h, l, C.byref(w), C.byref(hh), C.byref(ss))
+        whs[l] = (w.value, h, s)
+        pl[l] = a.ctypes.data + 19 * s + 19; pr[l] = b.ctypes.data + 19 * s + 19
+    t = left.tables()
+    sf = np.ascontiguousarray(t["scale_factors"], np.float32); isf = np.ascontiguousarray(t["inv_scale_factors"], np.float32)
+    ur = np.empty(max(len(kl), 1), np.float32); dp = np.empty(max(len(kl), 1), np.float32)
+    f = R.mref_stereo_match
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    f(kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data, dr.ctypes.data, len(kr), pl, pr, whs.ctypes.data, n, sf.ctypes.data,
+      isf.ctypes.data, mbf, fx, ur.ctypes.data, dp.ctypes.data)
+    return ur[:len(kl)], dp[:len(kl)]

@@ -2,7 +2,7 @@
  * oracle/matcher_glue.cc — C entry points around the UNMODIFIED /root/reference/src/ORBmatcher.cc (oracle/_ref build,
  * TEST INFRASTRUCTURE ONLY). The build recipe (oracle/Makefile, target ref_matcher) compiles ORBmatcher.cc where it lies
  * against oracle/slamshim (a small cv::Mat and stub Frame / KeyFrame / MapPoint classes) and takes the few member
- * functions the matcher calls — Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid, KeyFrame::GetFeaturesInArea /
+ * functions the matcher calls — Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid (and Frame::ComputeStereoMatches), KeyFrame::GetFeaturesInArea /
  * IsInImage, MapPoint::PredictScale / Get{Min,Max}DistanceInvariance — verbatim from the reference sources by line range
  * into oracle/_ref/gen/*.inc. Each mref_* function takes the same flattened arrays as the oc_* restatement in
  * orb_oracle.c, builds the object graph the reference function expects, runs it, and flattens the result back, so that
@@ -11,6 +11,8 @@
  * sR21 / t21 from s12, R12, t12) the glue derives it with the same shim operators and hands it back, and the test feeds
  * exactly those values to the restatement.
  */
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -34,6 +36,7 @@ float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 #include "gen/frame_assign.inc"
 #include "gen/frame_area.inc"
 #include "gen/frame_posingrid.inc"
+#include "gen/frame_stereo.inc"
 #include "gen/keyframe_area.inc"
 #include "gen/mappoint_dist.inc"
 void KeyFrame::AddMapPoint(MapPoint* pMP, const size_t& idx) { pMP->fused = (int)idx; }   /* records Fuse's pick, performs nothing */
@@ -380,5 +383,25 @@ int mref_search_by_bow(const int32_t* fv1_node, const int32_t* fv1_off, const in
         for (int i = 0; i < n1; i++) match[i] = out[i] ? out[i]->index : -1;
     }
     return r;
+}
+
+/* Frame::ComputeStereoMatches (Frame.cc:547-788) on two pyramids: lv_ptr[l] = payload origin of level l, lv_whs = (w, h, stride) */
+void mref_stereo_match(const KP28* kl, const uint8_t* dl, int nl, const KP28* kr, const uint8_t* dr, int nr,
+                       const uint8_t* const* lvL, const uint8_t* const* lvR, const int32_t* lv_whs, int nlevels,
+                       const float* scale_factors, const float* inv_scale_factors, float mbf, float fx, float* u_right, float* depth)
+{
+    Frame F;
+    F.N = nl; keys(kl, nl, F.mvKeys); keys(kr, nr, F.mvKeysRight);
+    F.mDescriptors = desc_rows(dl, nl); F.mDescriptorsRight = desc_rows(dr, nr);
+    F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels); F.mvInvScaleFactors.assign(inv_scale_factors, inv_scale_factors + nlevels);
+    F.mbf = mbf; F.mb = mbf / fx;                                           /* Frame.cc:120 */
+    ORBextractor L, R;
+    for (int l = 0; l < nlevels; l++) {
+        L.mvImagePyramid.push_back(cv::Mat(lv_whs[3 * l + 1], lv_whs[3 * l], CV_8U, const_cast<uint8_t*>(lvL[l]), (size_t)lv_whs[3 * l + 2]));
+        R.mvImagePyramid.push_back(cv::Mat(lv_whs[3 * l + 1], lv_whs[3 * l], CV_8U, const_cast<uint8_t*>(lvR[l]), (size_t)lv_whs[3 * l + 2]));
+    }
+    F.mpORBextractorLeft = &L; F.mpORBextractorRight = &R;
+    F.ComputeStereoMatches();
+    for (int i = 0; i < nl; i++) { u_right[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
 }
 }

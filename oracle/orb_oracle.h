@@ -118,7 +118,7 @@ int   oc_search_by_bow_kf(const int32_t* fv1_node, const int32_t* fv1_off, const
 
 /* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646);
  * argument meaning as include/orbx.h OrbxProjectionPair. Direct restatement, cv::Mat arithmetic pinned to cv2 4.13's
- * gemm; NOT pinned by oracle/_ref (ORBmatcher.cc needs the whole SLAM library). Returns nmatches. */
+ * gemm; pinned to the unmodified ORBmatcher.cc by oracle/_ref/libmatcher_ref.so (tests/test_matcher_ref.py). Returns nmatches. */
 int   oc_search_by_projection_frame(const OcKeyPoint* cur_kps, const uint8_t* cur_desc, int n_cur, const float* cur_u_right,
                                     const uint8_t* cur_occupied, const float* Tcw12, const float* cam9,
                                     const float* scale_factors,
@@ -127,8 +127,8 @@ int   oc_search_by_projection_frame(const OcKeyPoint* cur_kps, const uint8_t* cu
                                     int32_t* match_cur);
 
 /* ---- the remaining window / BoW matchers of ORBmatcher; see the definitions in orb_oracle.c for argument meaning.
- *      Direct restatements, cv::Mat arithmetic as pinned for oc_search_by_projection_frame; NOT pinned by oracle/_ref
- *      (ORBmatcher.cc needs the whole SLAM library). ---- */
+ *      Direct restatements, cv::Mat arithmetic as pinned for oc_search_by_projection_frame; pinned to the UNMODIFIED
+ *      ORBmatcher.cc by oracle/_ref/libmatcher_ref.so (oracle/matcher_glue.cc, tests/test_matcher_ref.py). ---- */
 typedef struct { float x, y, xr, view_cos; int32_t level; } OcTrackQuery;
 int   oc_search_local_points(const OcKeyPoint* kps, const uint8_t* desc, int n, const float* u_right, const uint8_t* occupied,
                              const float* bounds4, const float* scale_factors, int nlevels,

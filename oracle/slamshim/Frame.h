@@ -13,10 +13,16 @@ namespace ORB_SLAM2
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
 class MapPoint;
+class ORBextractor { public: std::vector<cv::Mat> mvImagePyramid; };   /* ORBextractor.h:104, all ComputeStereoMatches reads of it */
 class Frame
 {
 public:
-    Frame() : N(0), mb(0), mbf(0), mnScaleLevels(0), mfLogScaleFactor(0) {}
+    Frame() : N(0), mb(0), mbf(0), mnScaleLevels(0), mfLogScaleFactor(0), mpORBextractorLeft(0), mpORBextractorRight(0) {}
+    void ComputeStereoMatches();                  /* verbatim from Frame.cc:547-788 through the build recipe */
+    std::vector<cv::KeyPoint> mvKeysRight;
+    cv::Mat mDescriptorsRight;
+    std::vector<float> mvDepth, mvInvScaleFactors;
+    ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const;
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
     void AssignFeaturesToGrid();

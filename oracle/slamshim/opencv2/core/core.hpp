@@ -34,6 +34,15 @@ public:
     Mat() : rows(0), cols(0), type_(CV_32F), step_(0), data_(0) {}
     Mat(int r, int c, int t) : rows(r), cols(c), type_(t), step_((size_t)c * (t == CV_32F ? 4 : 1)),
         buf_(new std::vector<uchar>((size_t)r * c * (t == CV_32F ? 4 : 1) + 1, 0)), data_(buf_->data()) {}
+    Mat(int r, int c, int t, void* ext, size_t step) : rows(r), cols(c), type_(t), step_(step), data_(static_cast<uchar*>(ext)) {}   /* external data */
+    static Mat ones(int r, int c, int t) { Mat m(r, c, t); for (int y = 0; y < r; y++) for (int x = 0; x < c; x++) m.at<float>(y, x) = 1.f; return m; }
+    void convertTo(Mat& dst, int t) const                 /* CV_8U -> CV_32F only; dst may be *this */
+    {
+        assert(type_ == CV_8U && t == CV_32F);
+        Mat m(rows, cols, CV_32F);
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) m.at<float>(y, x) = (float)at<uchar>(y, x);
+        dst = m;
+    }
     bool empty() const { return rows == 0 || cols == 0; }
     int type() const { return type_; }
     template <typename T> T& at(int r, int c) { return *reinterpret_cast<T*>(data_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
@@ -95,5 +104,13 @@ inline Mat operator*(double s, const Mat& a) { return scaled(a, s); }
 inline Mat operator*(const Mat& a, double s) { return scaled(a, s); }
 inline Mat operator/(const Mat& a, double s) { return scaled(a, 1.0 / s); }
 inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
+enum { NORM_L1 = 2 };
+inline double norm(const Mat& a, const Mat& b, int t)     /* normDiffL1_32f: |a - b| accumulated in f64 */
+{
+    assert(t == NORM_L1);
+    double s = 0.0;
+    for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) s += std::fabs((double)a.at<float>(r, c) - (double)b.at<float>(r, c));
+    return s;
+}
 } // namespace cv
 #endif

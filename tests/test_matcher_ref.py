@@ -188,3 +188,19 @@ def test_search_by_bow_restatements_equal_reference(check_ori):
         nr, mr = ob.ref_search_by_bow(t1, t2, k1, d1, v1, k2, d2, v2, nnr, check_ori, 1)
         assert no == nr and np.array_equal(mo, mr), (nnr, no, nr)
     assert no > 50
+
+
+@pytest.mark.parametrize("name,seed,mbf,fx", [("kitti", 2, 386.1448, 718.856), ("euroc", 1000, 47.9064, 435.2047), ("small", 5, 40.0, 200.0)])
+def test_compute_stereo_matches_restatement_equals_reference(name, seed, mbf, fx):
+    """oc_stereo_match against the verbatim Frame::ComputeStereoMatches (Frame.cc:547-788) on the oracle's own pyramids:
+    row bands, Hamming stage, 11x11 SAD slide, parabola, disparity / depth, median cut — mvuRight / mvDepth bit for bit."""
+    c = dict(width=320, height=240, nfeatures=500, scale=1.2, nlevels=6, ini_th=20, min_th=7) if name == "small" else synth.CONFIGS[name]
+    left, right = synth.synth_stereo_pair(c["width"], c["height"], seed)
+    args = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    oL, oR = ob.Extractor(*args), ob.Extractor(*args)
+    kl, dl = oL.extract(left); kr, dr = oR.extract(right)
+    ur, dp = ob.stereo_match(oL, oR, kl, dl, kr, dr, mbf, fx)
+    urr, dpr = ob.ref_stereo_match(oL, oR, kl, dl, kr, dr, mbf, fx)
+    assert np.array_equal(ur.view(np.uint32), urr.view(np.uint32)), np.count_nonzero(ur != urr)
+    assert np.array_equal(dp.view(np.uint32), dpr.view(np.uint32))
+    assert np.count_nonzero(ur >= 0) > 50
