@@ -330,6 +330,18 @@ typedef struct OrbxTrackQuery {
     float view_cos;                     /* mTrackViewCos */
     int32_t level;                      /* mnTrackScaleLevel */
 } OrbxTrackQuery;
+/* Frame::isInFrustum(MapPoint *pMP, float viewingCosLimit) (Frame.cc:315-378) for npts map points at once — what
+ * Tracking::SearchLocalPoints (Tracking.cc:1409-1470) runs on every local map point before the matcher: Tcw12 = (mRcw
+ * row-major, mtcw), Ow3 = mOw, camera9 = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY), pt_dist = 3 floats per
+ * point (GetMinDistanceInvariance(), GetMaxDistanceInvariance(), mfMaxDistance). in_view[i] = the return value
+ * (= mbTrackInView); queries[i] is written only where in_view[i] != 0 and feeds orbx_search_local_points directly. */
+int orbx_is_in_frustum(const float* Tcw12, const float* Ow3, const float* camera9, int nlevels, float log_scale_factor,
+                       const float* pt_xyz, const float* pt_normal, const float* pt_dist, int npts, float viewing_cos_limit,
+                       OrbxTrackQuery* queries, uint8_t* in_view, int device);
+/* device pointers for the point arrays and outputs; asynchronous on cuda_stream */
+int orbx_is_in_frustum_device(const float* Tcw12, const float* Ow3, const float* camera9, int nlevels, float log_scale_factor,
+                              const float* d_pt_xyz, const float* d_pt_normal, const float* d_pt_dist, int npts,
+                              float viewing_cos_limit, OrbxTrackQuery* d_queries, uint8_t* d_in_view, int device, void* cuda_stream);
 typedef struct OrbxLocalPointsFrame {
     const OrbxKeyPoint* keypoints;      /* F.mvKeysUn, n */
     const uint8_t* descriptors;         /* F.mDescriptors */

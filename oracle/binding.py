@@ -796,3 +796,35 @@ def ref_stereo_match(left: "Extractor", right: "Extractor", kl, dl, kr, dr, mbf,
     f(kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data, dr.ctypes.data, len(kr), pl, pr, whs.ctypes.data, n, sf.ctypes.data,
       isf.ctypes.data, mbf, fx, ur.ctypes.data, dp.ctypes.data)
     return ur[:len(kl)], dp[:len(kl)]
+
+
+def is_in_frustum(Tcw12, Ow3, cam9, nlevels, log_scale_factor, pt_xyz, pt_normal, pt_dist, viewing_cos_limit=0.5):
+    """Frame::isInFrustum (Frame.cc:315-378) -> (queries, in_view)"""
+    T = np.ascontiguousarray(Tcw12, np.float32); Ow = np.ascontiguousarray(Ow3, np.float32); cam = np.ascontiguousarray(cam9, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = np.ascontiguousarray(pt_normal, np.float32); dst = np.ascontiguousarray(pt_dist, np.float32)
+    n = len(xyz)
+    q = np.zeros(max(n, 1), TRACKQ_DTYPE); v = np.zeros(max(n, 1), np.uint8)
+    f = lib().oc_is_in_frustum
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    f(T.ctypes.data, Ow.ctypes.data, cam.ctypes.data, nlevels, float(log_scale_factor), xyz.ctypes.data, nrm.ctypes.data, dst.ctypes.data, n,
+      viewing_cos_limit, q.ctypes.data, v.ctypes.data)
+    return q[:n], v[:n]
+
+
+def ref_is_in_frustum(Tcw12, Ow3, cam9, nlevels, log_scale_factor, pt_xyz, pt_normal, pt_dist_raw, viewing_cos_limit=0.5):
+    """the verbatim Frame::isInFrustum -> (queries, in_view, pt_dist rows for the restatement)"""
+    R = matcher_ref()
+    T = np.ascontiguousarray(Tcw12, np.float32); Ow = np.ascontiguousarray(Ow3, np.float32); cam = np.ascontiguousarray(cam9, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = np.ascontiguousarray(pt_normal, np.float32); d4 = _dist4(pt_dist_raw)
+    n = len(xyz)
+    q4 = np.zeros((max(n, 1), 4), np.float32); lv = np.zeros(max(n, 1), np.int32); v = np.zeros(max(n, 1), np.uint8)
+    f = R.mref_is_in_frustum
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                  C.c_void_p, C.c_void_p]
+    f(T.ctypes.data, Ow.ctypes.data, cam.ctypes.data, nlevels, float(log_scale_factor), xyz.ctypes.data, nrm.ctypes.data, d4.ctypes.data, n,
+      viewing_cos_limit, q4.ctypes.data, lv.ctypes.data, v.ctypes.data)
+    q = np.zeros(n, TRACKQ_DTYPE)
+    q["proj_x"] = q4[:n, 0]; q["proj_y"] = q4[:n, 1]; q["proj_xr"] = q4[:n, 2]; q["view_cos"] = q4[:n, 3]; q["level"] = lv[:n]
+    return q, v[:n], np.ascontiguousarray(d4[:, :3])

@@ -36,6 +36,7 @@ float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 #include "gen/frame_assign.inc"
 #include "gen/frame_area.inc"
 #include "gen/frame_posingrid.inc"
+#include "gen/frame_frustum.inc"
 #include "gen/frame_stereo.inc"
 #include "gen/keyframe_area.inc"
 #include "gen/mappoint_dist.inc"
@@ -403,5 +404,22 @@ void mref_stereo_match(const KP28* kl, const uint8_t* dl, int nl, const KP28* kr
     F.mpORBextractorLeft = &L; F.mpORBextractorRight = &R;
     F.ComputeStereoMatches();
     for (int i = 0; i < nl; i++) { u_right[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+}
+
+/* Frame::isInFrustum (Frame.cc:315-378) per point; q5 rows = (mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos), level */
+void mref_is_in_frustum(const float* Tcw12, const float* Ow3, const float* cam9, int nlevels, float log_sf, const float* pt_xyz,
+                        const float* pt_normal, const float* pt_dist4, int npts, float limit, float* q4, int32_t* level, uint8_t* in_view)
+{
+    set_frame_statics(cam9);
+    Frame F;
+    F.mRcw = mat33(Tcw12); F.mtcw = vec3(Tcw12 + 9); F.mOw = vec3(Ow3); F.mbf = cam9[4];
+    F.mnScaleLevels = nlevels; F.mfLogScaleFactor = log_sf;
+    for (int i = 0; i < npts; i++) {
+        MapPoint p;
+        fill_point(&p, pt_xyz + 3 * (size_t)i, pt_normal + 3 * (size_t)i, pt_dist4 + 4 * (size_t)i, 0);
+        in_view[i] = F.isInFrustum(&p, limit) ? 1 : 0;
+        q4[4 * i] = p.mTrackProjX; q4[4 * i + 1] = p.mTrackProjY; q4[4 * i + 2] = p.mTrackProjXR; q4[4 * i + 3] = p.mTrackViewCos;
+        level[i] = p.mnTrackScaleLevel;
+    }
 }
 }

@@ -18,7 +18,7 @@
  * The oracle uses the node CREATION SEQUENCE instead; oracle/_ref reproduces exactly that by running the
  * verbatim reference under a monotonic bump allocator.
  *
- * Build: gcc -O2 -std=c11 -ffp-contract=off (the reference is built -std=c++11 => no FMA contraction).
+ * Build: gcc -O2 -std=c11 -ffp-contract=off: the pinned semantics are the uncontracted ones (contraction note).
  */
 #include "orb_oracle.h"
 #include <float.h>
@@ -1255,7 +1255,7 @@ int oc_search_by_bow(const int32_t* kf_fv_node, const int32_t* kf_fv_off, const 
  * const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1489-1646), the matcher of Tracking::TrackWithMotionModel.
  * cv::Mat arithmetic restated from OpenCV 4.13 (pinned with cv2.gemm): `Rcw*x3Dw+tcw` is one gemm on CV_32F 3x3 * 3x1
  * operands evaluated in f32, left to right, the addend last. `1.0/z` is a double division rounded to float. The
- * reference is built with -std=c++11 (CMakeLists.txt:13-26), i.e. without FMA contraction.
+ * reference arithmetic is taken uncontracted (contraction note).
  * mode: 0 = neither (levels octave-1..octave+1), 1 = bForward, 2 = bBackward (:1510-1511; decided by the caller from
  * tlc and mb). cam = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY). last_flags bit 0: LastFrame.mvpMapPoints[i]
  * exists and !mvbOutlier[i]; bit 1: that map point has Observations() > 0 (what :1574-1576 tests once it has been
@@ -1932,4 +1932,43 @@ int oc_search_for_initialization(const OcKeyPoint* kps1, const uint8_t* desc1, i
         if (match12[i1] >= 0) { prev[2 * i1] = kps2[match12[i1]].x; prev[2 * i1 + 1] = kps2[match12[i1]].y; }
     oc_grid_free(&g); free(hist_idx); free(hist_bin); free(vMatchedDistance); free(vnMatches21);
     return nmatches;
+}
+
+
+/* Frame::isInFrustum (Frame.cc:315-378) for npts map points: q[i] (the five mTrack* fields) is written where the function
+ * returns true, in_view[i] = its return value. cam9 = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY). */
+void oc_is_in_frustum(const float* Tcw12, const float* Ow3, const float* cam9, int nlevels, float log_scale_factor,
+                      const float* pt_xyz, const float* pt_normal, const float* pt_dist, int npts, float viewingCosLimit,
+                      OcTrackQuery* q, uint8_t* in_view)
+{
+    const float fx = cam9[0], fy = cam9[1], cx = cam9[2], cy = cam9[3], mbf = cam9[4];
+    const float mnMinX = cam9[5], mnMaxX = cam9[6], mnMinY = cam9[7], mnMaxY = cam9[8];
+    for (int i = 0; i < npts; i++) {
+        in_view[i] = 0;
+        const float X = pt_xyz[3 * i], Y = pt_xyz[3 * i + 1], Z = pt_xyz[3 * i + 2];
+        float Pc[3];
+        for (int r = 0; r < 3; r++) {
+            float s = Tcw12[3 * r] * X;
+            s = s + Tcw12[3 * r + 1] * Y;
+            s = s + Tcw12[3 * r + 2] * Z;
+            Pc[r] = s + Tcw12[9 + r];
+        }
+        if (Pc[2] < 0.0f) continue;
+        const float invz = 1.0f / Pc[2];
+        const float u = fx * Pc[0] * invz + cx, v = fy * Pc[1] * invz + cy;
+        if (u < mnMinX || u > mnMaxX) continue;
+        if (v < mnMinY || v > mnMaxY) continue;
+        const float PO[3] = {X - Ow3[0], Y - Ow3[1], Z - Ow3[2]};
+        double s2 = 0.0, dot = 0.0;
+        for (int k = 0; k < 3; k++) s2 += (double)PO[k] * (double)PO[k];
+        const float dist = (float)sqrt(s2);
+        if (dist < pt_dist[3 * i] || dist > pt_dist[3 * i + 1]) continue;
+        for (int k = 0; k < 3; k++) dot += (double)PO[k] * (double)pt_normal[3 * i + k];
+        const float viewCos = dot / dist;
+        if (viewCos < viewingCosLimit) continue;
+        if (u != u || v != v || viewCos != viewCos) continue;       /* NaN (a point at the camera centre): outside the domain */
+        q[i].level = oc_predict_scale(pt_dist[3 * i + 2], dist, log_scale_factor, nlevels);
+        q[i].x = u; q[i].xr = u - mbf * invz; q[i].y = v; q[i].view_cos = viewCos;
+        in_view[i] = 1;
+    }
 }

@@ -168,6 +168,10 @@ int   oc_search_for_initialization(const OcKeyPoint* kps1, const uint8_t* desc1,
                                    float* prev, int window, float nnratio, int check_orientation, int32_t* match12);
                                                                                 /* ORBmatcher.cc:442-587 */
 
+void  oc_is_in_frustum(const float* Tcw12, const float* Ow3, const float* cam9, int nlevels, float log_scale_factor,
+                       const float* pt_xyz, const float* pt_normal, const float* pt_dist, int npts, float viewingCosLimit,
+                       OcTrackQuery* q, uint8_t* in_view);                      /* Frame.cc:315-378 */
+
 #ifdef __cplusplus
 }
 #endif

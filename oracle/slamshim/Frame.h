@@ -18,6 +18,8 @@ class Frame
 {
 public:
     Frame() : N(0), mb(0), mbf(0), mnScaleLevels(0), mfLogScaleFactor(0), mpORBextractorLeft(0), mpORBextractorRight(0) {}
+    bool isInFrustum(MapPoint* pMP, float viewingCosLimit);   /* verbatim from Frame.cc:315-378 */
+    cv::Mat mRcw, mtcw, mOw;
     void ComputeStereoMatches();                  /* verbatim from Frame.cc:547-788 through the build recipe */
     std::vector<cv::KeyPoint> mvKeysRight;
     cv::Mat mDescriptorsRight;

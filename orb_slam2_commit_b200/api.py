@@ -132,6 +132,10 @@ def lib():
                                           C.c_void_p, C.c_int]
         L.orbx_search_for_initialization.argtypes = [C.c_void_p, f32p, C.c_float, C.c_int, C.c_int]
         L.orbx_search_for_initialization_device.argtypes = [C.c_void_p, C.c_int, f32p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        L.orbx_is_in_frustum.argtypes = [f32p, f32p, f32p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                         C.c_void_p, C.c_void_p, C.c_int]
+        L.orbx_is_in_frustum_device.argtypes = [f32p, f32p, f32p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orbx_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
         L.orbx_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
         L.orbx_peer_hamming_top2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
@@ -466,6 +470,18 @@ def search_by_projection_frame(cur_kps, cur_desc, cur_u_right, cur_occupied, Tcw
 
 
 TRACKQ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4")])
+
+
+def is_in_frustum(Tcw12, Ow3, cam9, nlevels, log_scale_factor, pt_xyz, pt_normal, pt_dist, viewing_cos_limit=0.5, device: int = 0):
+    """Frame::isInFrustum (Frame.cc:315-378) for every map point -> (queries TRACKQ_DTYPE, in_view uint8); queries[i] is
+    meaningful where in_view[i] != 0 (the reference leaves the mTrack* fields untouched otherwise)."""
+    T = np.ascontiguousarray(Tcw12, np.float32); Ow = np.ascontiguousarray(Ow3, np.float32); cam = np.ascontiguousarray(cam9, np.float32)
+    xyz = np.ascontiguousarray(pt_xyz, np.float32); nrm = np.ascontiguousarray(pt_normal, np.float32); dst = np.ascontiguousarray(pt_dist, np.float32)
+    n = len(xyz)
+    q = np.zeros(max(n, 1), TRACKQ_DTYPE); v = np.zeros(max(n, 1), np.uint8)
+    _ck(lib().orbx_is_in_frustum(T.ctypes.data_as(f32p), Ow.ctypes.data_as(f32p), cam.ctypes.data_as(f32p), nlevels, float(log_scale_factor),
+                                 xyz.ctypes.data, nrm.ctypes.data, dst.ctypes.data, n, viewing_cos_limit, q.ctypes.data, v.ctypes.data, device))
+    return q[:n], v[:n]
 
 
 class OrbxLocalPointsFrame(C.Structure):

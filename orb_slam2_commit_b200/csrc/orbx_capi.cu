@@ -2218,3 +2218,58 @@ extern "C" int orbx_search_for_initialization(const OrbxInitPair* pair, const fl
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     return rc;
 }
+
+
+// Frame::isInFrustum (Frame.cc:315-378) — orbx_match.cu
+extern "C" int orbx_is_in_frustum_device(const float* Tcw12, const float* Ow3, const float* camera9, int nlevels, float log_scale_factor,
+                                         const float* d_pt_xyz, const float* d_pt_normal, const float* d_pt_dist, int npts,
+                                         float viewing_cos_limit, OrbxTrackQuery* d_queries, uint8_t* d_in_view, int device,
+                                         void* cuda_stream)
+{
+    if (npts <= 0) return ORBX_OK;
+    if (!Tcw12 || !Ow3 || !d_pt_xyz || !d_pt_normal || !d_pt_dist || !d_queries || !d_in_view) return fail(ORBX_ERR_INVALID, "bad argument");
+    std::vector<float> sf1((size_t)std::max(nlevels, 1), 1.f);
+    OrbxFuseCam cam;
+    int rc = make_fuse_cam(camera9, sf1.data(), nullptr, nlevels, log_scale_factor, cam);
+    if (rc != ORBX_OK) return rc;
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    OrbxFrustumArgs a;
+    memcpy(a.Tcw, Tcw12, sizeof a.Tcw); memcpy(a.Ow, Ow3, sizeof a.Ow); a.view_cos_limit = viewing_cos_limit;
+    a.pt_xyz = d_pt_xyz; a.pt_normal = d_pt_normal; a.pt_dist = d_pt_dist; a.npts = npts;
+    a.q = (OrbxTrackQueryDev*)d_queries; a.in_view = d_in_view;
+    orbx_launch_in_frustum(a, cam, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_is_in_frustum(const float* Tcw12, const float* Ow3, const float* camera9, int nlevels, float log_scale_factor,
+                                  const float* pt_xyz, const float* pt_normal, const float* pt_dist, int npts, float viewing_cos_limit,
+                                  OrbxTrackQuery* queries, uint8_t* in_view, int device)
+{
+    if (npts <= 0) return ORBX_OK;
+    if (!pt_xyz || !pt_normal || !pt_dist || !queries || !in_view) return fail(ORBX_ERR_INVALID, "bad argument");
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    keep_mempool(device);
+    HostPack P;
+    const size_t i_x = P.add((size_t)npts * 12), i_n = P.add((size_t)npts * 12), i_d = P.add((size_t)npts * 12),
+                 i_q = P.add((size_t)npts * sizeof(OrbxTrackQuery)), i_v = P.add(npts);
+    CK(cudaMallocAsync(&P.pool, P.tot, 0));
+    cudaError_t e = cudaSuccess;
+    int rc = ORBX_OK;
+    do {
+        if ((e = cudaMemcpyAsync(P.at(i_x), pt_xyz, (size_t)npts * 12, cudaMemcpyHostToDevice, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(P.at(i_n), pt_normal, (size_t)npts * 12, cudaMemcpyHostToDevice, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(P.at(i_d), pt_dist, (size_t)npts * 12, cudaMemcpyHostToDevice, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(P.at(i_q), queries, (size_t)npts * sizeof(OrbxTrackQuery), cudaMemcpyHostToDevice, 0)) != cudaSuccess) break;
+        rc = orbx_is_in_frustum_device(Tcw12, Ow3, camera9, nlevels, log_scale_factor, (const float*)P.at(i_x), (const float*)P.at(i_n),
+                                       (const float*)P.at(i_d), npts, viewing_cos_limit, (OrbxTrackQuery*)P.at(i_q), P.at(i_v), device, nullptr);
+        if (rc != ORBX_OK) break;
+        if ((e = cudaMemcpy(queries, P.at(i_q), (size_t)npts * sizeof(OrbxTrackQuery), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        e = cudaMemcpy(in_view, P.at(i_v), (size_t)npts, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFreeAsync(P.pool, 0);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}

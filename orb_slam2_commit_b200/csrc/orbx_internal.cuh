@@ -219,6 +219,12 @@ struct OrbxFuseDev {
 };
 void orbx_launch_fuse_search(const OrbxFuseDev* d_jobs, int njobs, int max_n, const OrbxFuseCam& cam, cudaStream_t st);
 
+struct OrbxFrustumArgs {       // Frame::isInFrustum for npts map points
+    float Tcw[12], Ow[3], view_cos_limit;
+    const float* pt_xyz; const float* pt_normal; const float* pt_dist; int npts;
+    OrbxTrackQueryDev* q; uint8_t* in_view;
+};
+void orbx_launch_in_frustum(const OrbxFrustumArgs& a, const OrbxFuseCam& cam, cudaStream_t st);
 void orbx_launch_sim3_mutual(const int* d_match1, int n1, const int* d_match2, int n2, int* d_match12, int* d_nfound, cudaStream_t st);
 struct OrbxSeqProjDev {        // SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (mode 0) / (pKF, Scw, vpPoints, vpMatched, th) (mode 1)
     const OrbxKp28* kps; const uint8_t* desc; const uint8_t* occupied; int n;

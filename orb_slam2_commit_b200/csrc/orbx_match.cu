@@ -108,11 +108,66 @@ void orbx_launch_local_points(const OrbxLocalFrameDev* d_frames, int nframes, in
                                                     nlevels, th, nnratio, 100 /* TH_HIGH */);
 }
 
+// ------------------------------------------------------------------------------------------------------ isInFrustum
+// Frame::isInFrustum (Frame.cc:315-378), the per-map-point prologue of Tracking::SearchLocalPoints: projection with
+// mRcw / mtcw, image-bounds, distance-invariance and viewing-angle tests, MapPoint::PredictScale; writes the five mTrack*
+// fields the matcher above reads. Thread per map point, arithmetic as in fuse_search_kernel below.
+__global__ void __launch_bounds__(256) in_frustum_kernel(OrbxFrustumArgs A, OrbxFuseCam cam)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.npts) return;
+    bool ok = false;
+    do {
+        const float X = A.pt_xyz[3 * i], Y = A.pt_xyz[3 * i + 1], Z = A.pt_xyz[3 * i + 2];
+        float c3[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            float s = __fmul_rn(A.Tcw[3 * r], X);
+            s = __fadd_rn(s, __fmul_rn(A.Tcw[3 * r + 1], Y));
+            s = __fadd_rn(s, __fmul_rn(A.Tcw[3 * r + 2], Z));
+            c3[r] = __fadd_rn(s, A.Tcw[9 + r]);
+        }
+        if (c3[2] < 0.0f) break;
+        const float invz = __fdiv_rn(1.0f, c3[2]);
+        const float u = __fadd_rn(__fmul_rn(__fmul_rn(cam.fx, c3[0]), invz), cam.cx);
+        const float v = __fadd_rn(__fmul_rn(__fmul_rn(cam.fy, c3[1]), invz), cam.cy);
+        if (u < cam.minX || u > cam.maxX) break;
+        if (v < cam.minY || v > cam.maxY) break;
+        const float po0 = __fsub_rn(X, A.Ow[0]), po1 = __fsub_rn(Y, A.Ow[1]), po2 = __fsub_rn(Z, A.Ow[2]);
+        double s2 = __dmul_rn((double)po0, (double)po0);
+        s2 = __dadd_rn(s2, __dmul_rn((double)po1, (double)po1));
+        s2 = __dadd_rn(s2, __dmul_rn((double)po2, (double)po2));
+        const float dist = __double2float_rn(__dsqrt_rn(s2));
+        if (dist < A.pt_dist[3 * i] || dist > A.pt_dist[3 * i + 1]) break;
+        const float* nrm = A.pt_normal + 3 * i;
+        double dot = __dmul_rn((double)po0, (double)nrm[0]);
+        dot = __dadd_rn(dot, __dmul_rn((double)po1, (double)nrm[1]));
+        dot = __dadd_rn(dot, __dmul_rn((double)po2, (double)nrm[2]));
+        const float viewCos = __double2float_rn(__ddiv_rn(dot, (double)dist));
+        if (viewCos < A.view_cos_limit) break;
+        if (!(u == u) || !(v == v) || !(viewCos == viewCos)) break;          // NaN: out of the function's domain (a point at the camera centre)
+        const float ratio = __fdiv_rn(A.pt_dist[3 * i + 2], dist);
+        int level = 0;
+        for (int n = 0; n < cam.nlevels - 1; n++) level += (ratio >= cam.level_ratio[n]) ? 1 : 0;
+        OrbxTrackQueryDev q;
+        q.x = u; q.y = v; q.xr = __fsub_rn(u, __fmul_rn(cam.bf, invz)); q.view_cos = viewCos; q.level = level;
+        A.q[i] = q;
+        ok = true;
+    } while (0);
+    A.in_view[i] = ok ? 1 : 0;
+}
+
+void orbx_launch_in_frustum(const OrbxFrustumArgs& a, const OrbxFuseCam& cam, cudaStream_t st)
+{
+    if (a.npts <= 0) return;
+    in_frustum_kernel<<<(a.npts + 255) / 256, 256, 0, st>>>(a, cam);
+}
+
 // ------------------------------------------------------------------------------------------------------------- Fuse
 // One CTA per (keyframe, map-point list). Thread per map point: projection with OpenCV's small-matrix gemm order
 // (`Rcw*p3Dw + tcw`: f32 products summed left to right, the addend last), `1/z` as an f32 division, cv::norm and
-// Mat::dot accumulated in f64 in element order, un-contracted f32 elsewhere (the reference is built without FMA
-// contraction). MapPoint::PredictScale's `ceil(logf(ratio) / mfLogScaleFactor)` is evaluated through a threshold table
+// Mat::dot accumulated in f64 in element order, un-contracted f32 elsewhere (the pinned reference semantics,
+// DESIGN.md §3). MapPoint::PredictScale's `ceil(logf(ratio) / mfLogScaleFactor)` is evaluated through a threshold table
 // built on the host with the host's own logf (level_ratio[n] = smallest ratio whose predicted level exceeds n), so the
 // level equals the host libm's bit for bit.
 __global__ void __launch_bounds__(512) fuse_search_kernel(const OrbxFuseDev* __restrict__ jobs, OrbxFuseCam cam, int th_low, int th_high)

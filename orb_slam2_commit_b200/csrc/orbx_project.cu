@@ -13,7 +13,7 @@
 // round that changes nothing is the sequential result (induction over the query index), and query i is final after
 // round i at the latest; on real frames two or three rounds suffice.
 // Projection arithmetic: OpenCV 4.13's small-matrix gemm for `Rcw*x3Dw+tcw` (f32, left to right, addend last), a
-// double division for 1.0/z, un-contracted f32 everywhere else (the reference is built without FMA contraction).
+// double division for 1.0/z, un-contracted f32 everywhere else (the pinned reference semantics).
 #include "orbx_grid.cuh"
 #include <algorithm>
 

@@ -250,3 +250,25 @@ def test_keyframe_side_matchers_with_non_integer_image_bounds():
     n, m = search_local_points(**lp, th=3.0)
     no, mo = ob.search_local_points(**lp, th=3.0)
     assert n == no and np.array_equal(m, mo) and n > 200
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_is_in_frustum_matches_oracle_and_feeds_search_local_points(seed):
+    """Frame::isInFrustum (Frame.cc:315-378) on the GPU: return value and the five mTrack* fields bit-identical to the
+    restatement; its output drives SearchByProjection(F, vpMapPoints) exactly as Tracking::SearchLocalPoints chains them."""
+    from orb_slam2_commit_b200 import is_in_frustum
+    s = synth.synth_fuse_scene(seed, n_points=3000)
+    for limit in (0.5, 0.9):
+        q, v = is_in_frustum(s["Tcw12"], s["Ow3"], s["cam9"], 8, s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], s["pt_dist"], limit)
+        qo, vo = ob.is_in_frustum(s["Tcw12"], s["Ow3"], s["cam9"], 8, s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], s["pt_dist"], limit)
+        assert np.array_equal(v, vo) and q[v != 0].tobytes() == qo[vo != 0].tobytes()
+        assert 300 < np.count_nonzero(v) < len(v)
+    rng = np.random.default_rng(seed)
+    flags = v | ((rng.random(len(v)) < 0.8).astype(np.uint8) << 1)
+    args = dict(kps=s["kps"], desc=s["desc"], u_right=s["u_right"], occupied=None, bounds4=s["cam9"][5:9], scale_factors=s["scale_factors"],
+                queries=q, query_desc=s["pt_desc"], query_flags=flags)
+    n, m = search_local_points(**args, th=3.0)
+    no, mo = ob.search_local_points(**args, th=3.0)
+    assert n == no and np.array_equal(m, mo) and n > 100
+    qe, ve = is_in_frustum(s["Tcw12"], s["Ow3"], s["cam9"], 8, s["log_scale_factor"], s["pt_xyz"][:0], s["pt_normal"][:0], s["pt_dist"][:0])
+    assert len(qe) == 0 and len(ve) == 0

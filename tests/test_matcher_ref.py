@@ -204,3 +204,19 @@ def test_compute_stereo_matches_restatement_equals_reference(name, seed, mbf, fx
     assert np.array_equal(ur.view(np.uint32), urr.view(np.uint32)), np.count_nonzero(ur != urr)
     assert np.array_equal(dp.view(np.uint32), dpr.view(np.uint32))
     assert np.count_nonzero(ur >= 0) > 50
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_is_in_frustum_restatement_equals_reference(seed):
+    """oc_is_in_frustum against the verbatim Frame::isInFrustum (Frame.cc:315-378): return value and the five mTrack* fields"""
+    s = synth.synth_fuse_scene(seed, n_points=3000)
+    raw = _raw_dist(s, np.random.default_rng(seed))
+    for bounds, limit in ((None, 0.5), (ODD_BOUNDS, 0.5), (None, 0.9)):
+        cam = s["cam9"].copy()
+        if bounds:
+            cam[5:9] = bounds
+        qr, vr, d3 = ob.ref_is_in_frustum(s["Tcw12"], s["Ow3"], cam, 8, s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], raw, limit)
+        q, v = ob.is_in_frustum(s["Tcw12"], s["Ow3"], cam, 8, s["log_scale_factor"], s["pt_xyz"], s["pt_normal"], d3, limit)
+        assert np.array_equal(v, vr)
+        assert q[v != 0].tobytes() == qr[vr != 0].tobytes()
+        assert 300 < np.count_nonzero(v) < len(v)
