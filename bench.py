@@ -55,7 +55,48 @@ WORKLOADS = {
 _RESULT_FD = None
 
 
+# Host placement: a rank's pinned frame buffers should live on the NUMA node its GPU hangs off, otherwise every H2D copy
+# crosses the socket interconnect and the end-to-end path of 4-8 ranks becomes host-memory bound. The rank binds itself to
+# that node's cores before it allocates (first touch then lands locally) and restores the full mask before any CPU baseline.
+_ORIG_AFFINITY = None
+_NUMA_INFO = None
+
+
+def bind_to_gpu_numa_node(torch, local):
+    global _ORIG_AFFINITY, _NUMA_INFO
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            _NUMA_INFO = {"gpu_pci": bdf, "node": node, "bound": False}
+            return
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        _ORIG_AFFINITY = os.sched_getaffinity(0)
+        cpus &= _ORIG_AFFINITY
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        _NUMA_INFO = {"gpu_pci": bdf, "node": node, "cpus": len(cpus), "bound": bool(cpus)}
+    except Exception as e:                                  # placement is an optimisation, never a requirement
+        _NUMA_INFO = {"bound": False, "error": str(e)[:80]}
+
+
+def restore_affinity():
+    if _ORIG_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _ORIG_AFFINITY)
+        except OSError:
+            pass
+
+
 def emit_json_line(line):
+    if _NUMA_INFO is not None and isinstance(line.get("config"), dict):
+        line["config"]["host_placement"] = _NUMA_INFO
     data = (json.dumps(line) + "\n").encode()
     if _RESULT_FD is None:
         sys.stdout.write(data.decode()); sys.stdout.flush()
@@ -151,6 +192,7 @@ def make_frames(c, distinct, seed0=1):
 def cpu_reference_bench(c, frames, target_seconds, nthreads):
     """Times the reference's own CPU ORBextractor (oracle/_ref = verbatim ORBextractor.cc + cvshim) or, when that
     library is absent, the oracle port, frame-parallel over `nthreads` host threads. Returns (frames/s, kind, sample)."""
+    restore_affinity()
     from oracle import binding as ob
     frames = np.ascontiguousarray(frames)
     n_img = len(frames)
@@ -263,6 +305,7 @@ def bench_hamming(torch, api_lib, dev, peaks, sm_mhz):
 
 def cpu_thread_bench(make_worker, target_seconds, nthreads):
     """Generic CPU baseline: make_worker(tid) -> f(i) doing one unit of work through ctypes (GIL released)."""
+    restore_affinity()
     workers = [make_worker(t) for t in range(nthreads)]
 
     def run(iters):
@@ -550,6 +593,49 @@ def run_matchers(args, torch, dist, rank, world, local, dev):
     def step_init():
         api._ck(L.orbx_search_for_initialization_device(ip, P, ib4, 0.9, 1, local, st))
 
+    # ---- SearchForTriangulation: nd keyframe pairs transformed once (ComputeBoW), then P pair matches per launch
+    from orb_slam2_commit_b200 import ORBVocabulary
+    voc = synth.synth_vocabulary(10, 4, 5)
+    V = ORBVocabulary(10, 4, *voc, device=local)
+    tri = [synth.synth_triangulation_scene(voc, 51 + i + 100 * rank) for i in range(nd)]
+    tcap = max(max(len(t["kps1"]), len(t["kps2"])) for t in tri)
+    t_desc = np.zeros((2 * nd, tcap, 32), np.uint8); t_kps = np.zeros((2 * nd, tcap), api.KP_DTYPE); t_cnt = np.zeros(2 * nd, np.int32)
+    t_mp = np.zeros((2 * nd, tcap), np.uint8); t_geom = np.zeros((P, 28), np.float32)
+    for i, t in enumerate(tri):
+        for j, tag in enumerate(("1", "2")):
+            n_ = len(t["kps" + tag]); t_cnt[2 * i + j] = n_
+            t_desc[2 * i + j, :n_] = t["desc" + tag]; t_kps[2 * i + j, :n_] = t["kps" + tag]; t_mp[2 * i + j, :n_] = t["has_mp" + tag]
+    for i in range(P):
+        t_geom[i] = tri[i % nd]["geom28"]
+    d_tdesc = dev_t(t_desc); d_tkps = dev_t(t_kps); d_tmp = dev_t(t_mp); d_tgeom = dev_t(t_geom)
+    d_tcnt = torch.from_numpy(t_cnt).to(dev)
+    d_f1 = torch.tensor([2 * (i % nd) for i in range(P)], dtype=torch.int32, device=dev)
+    d_f2 = torch.tensor([2 * (i % nd) + 1 for i in range(P)], dtype=torch.int32, device=dev)
+    d_m4 = torch.zeros((P, tcap), dtype=torch.int32, device=dev); d_nm4 = torch.zeros(P, dtype=torch.int32, device=dev)
+    V.transform_device(d_tdesc, d_tcnt.data_ptr(), 2 * nd, tcap, 2, st)
+    tsf, ts2 = fp(tri[0]["scale_factors"]), fp(tri[0]["level_sigma2"])
+
+    def step_tri():
+        api._ck(L.orbx_search_for_triangulation_device(V._h, P, d_f1.data_ptr(), d_f2.data_ptr(), d_tkps, d_tdesc, d_tmp, None, d_tgeom,
+                                                       tsf, ts2, 8, 0, 1, d_m4.data_ptr(), d_nm4.data_ptr(), st))
+    # ---- SearchBySim3: one keyframe pair per call (two projection jobs + the mutual check in two launches)
+    s3 = synth.synth_sim3_scene(61 + 100 * rank)
+    ks = []
+    for k in s3[:2]:
+        K = api.OrbxSim3KeyFrame()
+        K.keypoints = dev_t(k["kps"]); K.descriptors = dev_t(k["desc"]); K.n = len(k["kps"]); K.mp_xyz = dev_t(k["mp_xyz"])
+        K.mp_dist = dev_t(k["mp_dist"]); K.mp_descriptors = dev_t(k["mp_desc"]); K.mp_flags = dev_t(k["mp_flags"])
+        K.Tcw = (C.c_float * 12)(*k["Tcw12"].tolist()); ks.append(K)
+    d_m5 = torch.zeros(ks[0].n, dtype=torch.int32, device=dev); d_nf5 = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_scr = torch.zeros(ks[0].n + ks[1].n + 2, dtype=torch.int32, device=dev)
+    s12, s21, scam, ssf = fp(s3[2]), fp(s3[3]), fp(s3[4]), fp(s3[5])
+    n_sim3 = 64
+
+    def step_sim3():
+        for _ in range(n_sim3):
+            api._ck(L.orbx_search_by_sim3_device(C.byref(ks[0]), C.byref(ks[1]), s12, s21, scam, ssf, 8, s3[6], 7.5, d_m5.data_ptr(),
+                                                 d_nf5.data_ptr(), d_scr.data_ptr(), local, st))
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1: dist.barrier()
@@ -573,6 +659,12 @@ def run_matchers(args, torch, dist, rank, world, local, dev):
     for name, step in (("fuse_search", step_fuse), ("search_by_projection_kf_relocalisation", step_reloc), ("search_for_initialization", step_init)):
         ms = timed(step, max(5, args.steps // 5))
         others[name] = {"calls_per_s": world * P * max(5, args.steps // 5) / (ms * 1e-3), "ms_per_launch": ms / max(5, args.steps // 5), "calls_per_launch": P}
+    ms = timed(step_tri, max(5, args.steps // 5))
+    others["search_for_triangulation"] = {"calls_per_s": world * P * max(5, args.steps // 5) / (ms * 1e-3), "ms_per_launch": ms / max(5, args.steps // 5),
+                                          "calls_per_launch": P, "matches_per_call": float(d_nm4.float().mean().item())}
+    ms = timed(step_sim3, 5)
+    others["search_by_sim3"] = {"calls_per_s": world * n_sim3 * 5 / (ms * 1e-3), "ms_per_call": ms / (5 * n_sim3), "found_per_call": int(d_nf5.item()),
+                                "note": "one keyframe pair per call, stream-ordered, no synchronisation between calls"}
     others["fuse_search"]["fused_per_call"] = float(d_nf.float().mean().item())
     others["search_by_projection_kf_relocalisation"]["matches_per_call"] = float(d_nm2.float().mean().item())
     others["search_for_initialization"]["matches_per_call"] = float(d_nm3.float().mean().item())
@@ -743,6 +835,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if not os.environ.get("ORBX_NO_NUMA_BIND"):
+        bind_to_gpu_numa_node(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly ONE JSON line: keep NCCL's own banner ("NCCL version ...") off it

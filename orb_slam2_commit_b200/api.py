@@ -130,6 +130,8 @@ def lib():
         L.orbx_search_by_projection_kf_device.argtypes = [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.orbx_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, f32p, f32p, f32p, f32p, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                           C.c_void_p, C.c_int]
+        L.orbx_search_by_sim3_device.argtypes = [C.c_void_p, C.c_void_p, f32p, f32p, f32p, f32p, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orbx_search_for_initialization.argtypes = [C.c_void_p, f32p, C.c_float, C.c_int, C.c_int]
         L.orbx_search_for_initialization_device.argtypes = [C.c_void_p, C.c_int, f32p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.orbx_is_in_frustum.argtypes = [f32p, f32p, f32p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
