@@ -2159,8 +2159,9 @@ extern "C" int orbx_search_for_initialization_device(const OrbxInitPair* pairs, 
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_p = al((size_t)npairs * sizeof(OrbxInitPairDev));
     uint8_t* pool = nullptr;
-    CK(cudaMallocAsync(&pool, b_p + al(std::max<size_t>(tot, 1) * 4), st));
-    int* d_bin = (int*)(pool + b_p);
+    CK(cudaMallocAsync(&pool, b_p + al(std::max<size_t>(tot, 1) * 4 * 10), st));
+    int* d_bin = (int*)(pool + b_p);                                          // per F1 keypoint: bin, count, 4 keys, 4 indices
+    int* d_cnt = d_bin + std::max<size_t>(tot, 1); int* d_key = d_cnt + std::max<size_t>(tot, 1); int* d_idx = d_key + 4 * std::max<size_t>(tot, 1);
     std::vector<OrbxInitPairDev> hp(npairs);
     size_t off = 0;
     for (int p = 0; p < npairs; p++) {
@@ -2169,7 +2170,8 @@ extern "C" int orbx_search_for_initialization_device(const OrbxInitPair* pairs, 
         d.kps1 = (const OrbxKp28*)q.keypoints1; d.desc1 = q.descriptors1; d.n1 = q.n1;
         d.kps2 = (const OrbxKp28*)q.keypoints2; d.desc2 = q.descriptors2; d.n2 = q.n2;
         d.prev = q.prev_matched; d.prev_out = q.prev_matched_out; d.window = q.window_size;
-        d.match12 = q.match12; d.nmatches = q.nmatches; d.bin_of = d_bin + off; off += (size_t)q.n1;
+        d.match12 = q.match12; d.nmatches = q.nmatches; d.bin_of = d_bin + off;
+        d.ncand = d_cnt + off; d.top_key = (unsigned*)d_key + 4 * off; d.top_idx = d_idx + 4 * off; off += (size_t)q.n1;
     }
     cudaError_t e;
     do {

@@ -242,6 +242,7 @@ struct OrbxInitPairDev {       // ORBmatcher::SearchForInitialization
     int window;
     int* match12; int* nmatches;
     int* bin_of;                                  // scratch, n1 entries
+    unsigned* top_key; int* top_idx; int* ncand;  // scratch: 4, 4 and 1 entries per F1 keypoint
 };
 void orbx_launch_init_match(const OrbxInitPairDev* d_pairs, int npairs, int max_n2, const float* bounds4, float nnratio,
                             int check_orientation, cudaStream_t st);

@@ -479,8 +479,10 @@ void orbx_launch_seq_projection(const OrbxSeqProjDev* d_jobs, int njobs, int max
 // ORBmatcher::SearchForInitialization (ORBmatcher.cc:442-587), the matcher of the monocular initialiser: level-0 keypoints
 // of F1 against the level-0 keypoints of F2 inside a square window around vbPrevMatched[i1]. The loop is sequential
 // through vMatchedDistance / vnMatches21 (a later F1 keypoint may take an F2 keypoint away from an earlier one if it is
-// strictly closer), so one warp walks the F1 keypoints in order; inside a query the lanes share the window's candidates,
-// key = dist << 16 | candidate ordinal reproduces `dist < bestDist` (first minimum) and the multiset second best.
+// strictly closer). All warps first collect, per F1 keypoint, the four nearest window candidates in the reference's order
+// (key = dist << 16 | candidate ordinal reproduces `dist < bestDist`: first minimum, multiset second best); one warp then
+// walks the F1 keypoints in order and decides from those four, rescanning the window only when fewer than two of them are
+// still open and more candidates exist.
 __global__ void __launch_bounds__(512) init_match_kernel(const OrbxInitPairDev* __restrict__ pairs, float minX, float maxX,
                                                          float minY, float maxY, float nnratio, int check_orientation, int th_low)
 {
@@ -500,16 +502,19 @@ __global__ void __launch_bounds__(512) init_match_kernel(const OrbxInitPairDev* 
     const uint4* d1 = reinterpret_cast<const uint4*>(P.desc1);
     const uint4* d2 = reinterpret_cast<const uint4*>(P.desc2);
     const float r = (float)P.window;
-    if (tid < 32) {
-        int nmatches = 0;
-        for (int i1 = 0; i1 < P.n1; i1++) {
-            const OrbxKp28 kp1 = P.kps1[i1];
-            if (kp1.octave > 0) continue;                                        // :469-470
-            const float x = P.prev[2 * i1], y = P.prev[2 * i1 + 1];
-            int cx0, cx1, cy0, cy1;
-            if (!grid_window(x, y, r, minX, minY, invW, invH, cx0, cx1, cy0, cy1)) continue;
+    // ---- phase 1, all warps, one F1 keypoint per warp at a time: the FOUR nearest window candidates in the reference's
+    //      order (key = dist << 16 | candidate ordinal) without the vMatchedDistance filter, and the candidate count.
+    //      The sequential phase below decides from these four whenever they suffice, which is exact: any candidate
+    //      beyond them has a larger key than all four.
+    const int wid = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int i1 = wid; i1 < P.n1; i1 += nwarps) {
+        unsigned k0 = 0xffffffffu, k1 = 0xffffffffu, k2 = 0xffffffffu, k3 = 0xffffffffu;
+        int x0 = -1, x1 = -1, x2 = -1, x3 = -1, ncand = 0;
+        const OrbxKp28 kp1 = P.kps1[i1];
+        int cx0, cx1, cy0, cy1;
+        const float x = P.prev[2 * i1], y = P.prev[2 * i1 + 1];
+        if (kp1.octave <= 0 && grid_window(x, y, r, minX, minY, invW, invH, cx0, cx1, cy0, cy1)) {
             const uint4 qa = d1[2 * (size_t)i1], qb = d1[2 * (size_t)i1 + 1];
-            unsigned b1 = 0xffffffffu, b2 = 0xffffffffu;
             int base = 0;
             for (int ix = cx0; ix <= cx1; ix++) {
                 const int j0 = G.cstart[ix * GRID_ROWS + cy0], j1 = G.cstart[ix * GRID_ROWS + cy1 + 1];
@@ -518,33 +523,93 @@ __global__ void __launch_bounds__(512) init_match_kernel(const OrbxInitPairDev* 
                     const GridKp k = G.kp[i2];
                     if (k.octave > 0) continue;                                  // GetFeaturesInArea(.., level1, level1) with level1 == 0
                     if (!(fabsf(__fsub_rn(k.x, x)) < r && fabsf(__fsub_rn(k.y, y)) < r)) continue;
-                    const int dist = grid_hamming(qa, qb, d2[2 * (size_t)i2], d2[2 * (size_t)i2 + 1]);
-                    if (mdist[i2] <= dist) continue;                             // :494-495
-                    const unsigned key = ((unsigned)dist << 16) | (unsigned)(base + j - j0);
-                    const unsigned t = max(key, b1); b1 = min(b1, key); b2 = min(b2, t);
+                    const unsigned key = ((unsigned)grid_hamming(qa, qb, d2[2 * (size_t)i2], d2[2 * (size_t)i2 + 1]) << 16) | (unsigned)(base + j - j0);
+                    ncand++;
+                    if (key < k3) {                                              // insertion into the lane's sorted four
+                        k3 = key; x3 = i2;
+                        if (k3 < k2) { const unsigned t = k2; k2 = k3; k3 = t; const int u = x2; x2 = x3; x3 = u; }
+                        if (k2 < k1) { const unsigned t = k1; k1 = k2; k2 = t; const int u = x1; x1 = x2; x2 = u; }
+                        if (k1 < k0) { const unsigned t = k0; k0 = k1; k1 = t; const int u = x0; x0 = x1; x1 = u; }
+                    }
                 }
                 base += j1 - j0;
             }
-            const unsigned m1 = __reduce_min_sync(0xffffffffu, b1);
-            const unsigned c2 = b1 == m1 ? b2 : b1;
-            const unsigned m2 = __reduce_min_sync(0xffffffffu, c2);
-            if (m1 == 0xffffffffu) continue;
-            const int bestDist = (int)(m1 >> 16);
-            const float bestDist2 = m2 == 0xffffffffu ? 2147483648.0f /* (float)INT_MAX */ : (float)(int)(m2 >> 16);
-            if (bestDist <= th_low && (float)bestDist < __fmul_rn(bestDist2, nnratio)) {
-                // the ordinal back to the keypoint index: walk the columns again (warp-uniform)
-                int ord = (int)(m1 & 0xffffu), bestIdx2 = -1;
+        }
+        ncand = __reduce_add_sync(0xffffffffu, ncand);
+        unsigned outk = 0xffffffffu; int outx = -1;                              // lane e (< 4) ends up with the e-th smallest
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const unsigned m = __reduce_min_sync(0xffffffffu, k0);
+            const unsigned own = __ballot_sync(0xffffffffu, k0 == m && m != 0xffffffffu);
+            const int src = own ? __ffs(own) - 1 : 0;
+            const int xi = __shfl_sync(0xffffffffu, x0, src);
+            if (lane == e) { outk = m; outx = m != 0xffffffffu ? xi : -1; }
+            if (own && lane == src) { k0 = k1; x0 = x1; k1 = k2; x1 = x2; k2 = k3; x2 = x3; k3 = 0xffffffffu; }
+        }
+        if (lane < 4) { P.top_key[4 * (size_t)i1 + lane] = outk; P.top_idx[4 * (size_t)i1 + lane] = outx; }
+        if (lane == 0) P.ncand[i1] = ncand;
+    }
+    __syncthreads();
+    // ---- phase 2, one warp: the reference loop in order (:463-546)
+    if (tid < 32) {
+        int nmatches = 0;
+        for (int i1 = 0; i1 < P.n1; i1++) {
+            const int ncand = P.ncand[i1];
+            if (ncand == 0) continue;                                            // level > 0, window off the grid, or no candidate
+            const unsigned key = lane < 4 ? P.top_key[4 * (size_t)i1 + lane] : 0xffffffffu;
+            const int idx = lane < 4 ? P.top_idx[4 * (size_t)i1 + lane] : -1;
+            const bool valid = key != 0xffffffffu;
+            const bool open = valid && !(mdist[idx] <= (int)(key >> 16));        // :494-495
+            const unsigned U = __ballot_sync(0xffffffffu, open);
+            unsigned m1, m2; int bestIdx2;
+            if (__popc(U) >= 2 || ncand <= 4) {
+                if (!U) continue;
+                const int l1 = __ffs(U) - 1, l2 = __ffs(U & (U - 1)) - 1;
+                m1 = __shfl_sync(0xffffffffu, key, l1); bestIdx2 = __shfl_sync(0xffffffffu, idx, l1);
+                m2 = l2 >= 0 ? __shfl_sync(0xffffffffu, key, l2) : 0xffffffffu;
+            } else {
+                // fewer than two of the four are still open and there are more candidates: rescan the window with the filter
+                const float x = P.prev[2 * i1], y = P.prev[2 * i1 + 1];
+                int cx0, cx1, cy0, cy1;
+                grid_window(x, y, r, minX, minY, invW, invH, cx0, cx1, cy0, cy1);
+                const uint4 qa = d1[2 * (size_t)i1], qb = d1[2 * (size_t)i1 + 1];
+                unsigned b1 = 0xffffffffu, b2 = 0xffffffffu;
+                int base = 0;
+                for (int ix = cx0; ix <= cx1; ix++) {
+                    const int j0 = G.cstart[ix * GRID_ROWS + cy0], j1 = G.cstart[ix * GRID_ROWS + cy1 + 1];
+                    for (int j = j0 + lane; j < j1; j += 32) {
+                        const int i2 = G.order[j];
+                        const GridKp k = G.kp[i2];
+                        if (k.octave > 0) continue;
+                        if (!(fabsf(__fsub_rn(k.x, x)) < r && fabsf(__fsub_rn(k.y, y)) < r)) continue;
+                        const int dist = grid_hamming(qa, qb, d2[2 * (size_t)i2], d2[2 * (size_t)i2 + 1]);
+                        if (mdist[i2] <= dist) continue;
+                        const unsigned kk = ((unsigned)dist << 16) | (unsigned)(base + j - j0);
+                        const unsigned t = max(kk, b1); b1 = min(b1, kk); b2 = min(b2, t);
+                    }
+                    base += j1 - j0;
+                }
+                m1 = __reduce_min_sync(0xffffffffu, b1);
+                const unsigned c2 = b1 == m1 ? b2 : b1;
+                m2 = __reduce_min_sync(0xffffffffu, c2);
+                if (m1 == 0xffffffffu) continue;
+                int ord = (int)(m1 & 0xffffu);                                   // the ordinal back to the keypoint index
+                bestIdx2 = -1;
                 for (int ix = cx0; ix <= cx1; ix++) {
                     const int j0 = G.cstart[ix * GRID_ROWS + cy0], j1 = G.cstart[ix * GRID_ROWS + cy1 + 1];
                     if (ord < j1 - j0) { bestIdx2 = G.order[j0 + ord]; break; }
                     ord -= j1 - j0;
                 }
+            }
+            const int bestDist = (int)(m1 >> 16);
+            const float bestDist2 = m2 == 0xffffffffu ? 2147483648.0f /* (float)INT_MAX */ : (float)(int)(m2 >> 16);
+            if (bestDist <= th_low && (float)bestDist < __fmul_rn(bestDist2, nnratio)) {
                 if (lane == 0) {
                     if (m21[bestIdx2] >= 0) { P.match12[m21[bestIdx2]] = -1; nmatches--; }
                     P.match12[i1] = bestIdx2; m21[bestIdx2] = i1; mdist[bestIdx2] = bestDist;
                     nmatches++;
                     if (check_orientation) {
-                        float rot = __fsub_rn(kp1.angle, P.kps2[bestIdx2].angle);
+                        float rot = __fsub_rn(P.kps1[i1].angle, P.kps2[bestIdx2].angle);
                         if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                         int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
                         if (bin == 30) bin = 0;
