@@ -828,3 +828,68 @@ def ref_is_in_frustum(Tcw12, Ow3, cam9, nlevels, log_scale_factor, pt_xyz, pt_no
     q = np.zeros(n, TRACKQ_DTYPE)
     q["proj_x"] = q4[:n, 0]; q["proj_y"] = q4[:n, 1]; q["proj_xr"] = q4[:n, 2]; q["view_cos"] = q4[:n, 3]; q["level"] = lv[:n]
     return q, v[:n], np.ascontiguousarray(d4[:, :3])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref/libbow_ref.so: the reference's own DBoW2 TemplatedVocabulary.h (verbatim header template) behind oracle/bow_glue.cc
+BOW_REF_LIB = os.path.join(HERE, "_ref", "libbow_ref.so")
+_bref = None
+
+
+def bow_ref():
+    global _bref
+    if _bref is None:
+        if os.path.exists("/root/reference/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"):
+            srcs = [os.path.join(HERE, "bow_glue.cc"), os.path.join(HERE, "slamshim", "opencv2", "core", "core.hpp")]
+            if (not os.path.exists(BOW_REF_LIB)) or any(os.path.getmtime(BOW_REF_LIB) < os.path.getmtime(s) for s in srcs):
+                subprocess.check_call(["make", "-C", HERE, "ref_bow"], stdout=subprocess.DEVNULL)
+        if not os.path.exists(BOW_REF_LIB):
+            return None
+        R = C.CDLL(BOW_REF_LIB)
+        R.bref_vocab_load.restype = C.c_void_p; R.bref_vocab_load.argtypes = [C.c_char_p]
+        R.bref_vocab_destroy.argtypes = [C.c_void_p]
+        R.bref_vocab_words.argtypes = [C.c_void_p]
+        R.bref_vocab_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        R.bref_vocab_score.restype = C.c_double
+        R.bref_vocab_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _bref = R
+    return _bref
+
+
+def write_vocabulary_text(path, k, L, parent, is_leaf, desc, weight, scoring=0, weighting=0):
+    """ORBvoc.txt format (TemplatedVocabulary.h:1338-1420): header `k L scoring weighting`, then one line per non-root node:
+    parent id, leaf flag, 32 descriptor bytes, weight. No trailing newline: the loader's `while(!f.eof())` would read an
+    empty last line into a phantom node."""
+    lines = [f"{k} {L} {scoring} {weighting}"]
+    for p, l, d, w in zip(parent, is_leaf, desc, weight):
+        lines.append(f"{int(p)} {int(l)} " + " ".join(str(int(b)) for b in d) + f" {float(w)!r}")
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+class RefVocabulary:
+    """The reference's ORBVocabulary (TemplatedVocabulary<FORB::TDescriptor, FORB>) loaded through its own text loader."""
+
+    def __init__(self, path):
+        self.R = bow_ref()
+        self._h = self.R.bref_vocab_load(path.encode())
+        assert self._h, "loadFromTextFile failed"
+        self.nwords = self.R.bref_vocab_words(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.R.bref_vocab_destroy(self._h); self._h = None
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8); n = len(desc)
+        bow_id = np.zeros(max(n, 1), np.int32); bow_val = np.zeros(max(n, 1), np.float64); fv_node = np.zeros(max(n, 1), np.int32)
+        fv_off = np.zeros(n + 1, np.int32); fv_feat = np.zeros(max(n, 1), np.int32); nb = C.c_int32(0); nf = C.c_int32(0)
+        self.R.bref_vocab_transform(self._h, desc.ctypes.data, n, levelsup, bow_id.ctypes.data, bow_val.ctypes.data, C.addressof(nb),
+                                    fv_node.ctypes.data, fv_off.ctypes.data, fv_feat.ctypes.data, C.addressof(nf))
+        return dict(bow_id=bow_id[:nb.value], bow_val=bow_val[:nb.value], fv_node=fv_node[:nf.value], fv_off=fv_off[:nf.value + 1],
+                    fv_feat=fv_feat[:fv_off[nf.value]])
+
+    def score(self, a, b):
+        i1 = np.ascontiguousarray(a["bow_id"], np.int32); v1 = np.ascontiguousarray(a["bow_val"], np.float64)
+        i2 = np.ascontiguousarray(b["bow_id"], np.int32); v2 = np.ascontiguousarray(b["bow_val"], np.float64)
+        return self.R.bref_vocab_score(self._h, i1.ctypes.data, v1.ctypes.data, len(i1), i2.ctypes.data, v2.ctypes.data, len(i2))

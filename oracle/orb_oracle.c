@@ -1061,7 +1061,8 @@ void oc_undistort_points(const float* xy, int n, const float* K4, const float* d
  * ScoringObject.cpp are ABSENT from the snapshot, so FORB::distance (the same 32-bit SWAR Hamming as
  * ORBmatcher::DescriptorDistance), BowVector::addWeight / addIfNotExist / normalize, FeatureVector::addFeature and
  * L1Scoring::score are restated from DBoW2's published algorithm (the un-versioned copy ORB-SLAM2 ships).
- * PARITY UNPINNED for this block: no golden vectors exist and the sources cannot be compiled here. */
+ * Pinned to the reference's verbatim TemplatedVocabulary.h header (oracle/bow_glue.cc); the leaf functions of DBoW2's absent
+ * .cpp files follow DBoW2's published algorithm. */
 struct OcVocabulary {
     int k, L, scoring, weighting, n;      /* n = nodes incl. root (node 0) */
     int32_t* child_off; int32_t* child;   /* CSR children lists in push_back (= ascending id) order */

@@ -91,7 +91,8 @@ void  oc_window_top2(const OcKeyPoint* kps, const uint8_t* desc, int n, const ui
                      int32_t* best_idx, int32_t* best_dist, int32_t* best_level, int32_t* best_dist2, int32_t* best_level2);
 
 /* ---- bag of words: DBoW2 as used through ORBVocabulary (Frame.cc:462-469, ORBmatcher.cc:175-325,
- *      KeyFrameDatabase.cc:145). DBoW2's .cpp files are absent from the reference snapshot: PARITY UNPINNED. ----
+ *      KeyFrameDatabase.cc:145). DBoW2's .cpp files are absent from the reference snapshot; transform / score are pinned to the
+ *      verbatim TemplatedVocabulary.h header by oracle/_ref/libbow_ref.so (oracle/bow_glue.cc, tests/test_matcher_ref.py). ----
  * Vocabulary nodes in text-file order (TemplatedVocabulary.h:1338-1420): node i+1 has parent[i] (0 = root),
  * is_leaf[i], a 32-byte descriptor and a weight; words are numbered in order of appearance.
  * scoring: 0 L1_NORM 1 L2_NORM 2 CHI_SQUARE 3 KL 4 BHATTACHARYYA 5 DOT_PRODUCT; weighting: 0 TF_IDF 1 TF 2 IDF 3 BINARY. */

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
 
 #define CV_8U 0
@@ -112,5 +113,30 @@ inline double norm(const Mat& a, const Mat& b, int t)     /* normDiffL1_32f: |a 
     for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) s += std::fabs((double)a.at<float>(r, c) - (double)b.at<float>(r, c));
     return s;
 }
+/* cv::FileStorage / cv::FileNode: only so that the virtual save / load members of DBoW2's TemplatedVocabulary compile
+ * (bow_glue.cc loads the vocabulary through the reference's own text loader, never through these). */
+class FileNode {
+public:
+    enum { SEQ = 5 };
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    int type() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const char*, int) {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+};
+template <typename T> inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 } // namespace cv
 #endif

@@ -220,3 +220,37 @@ def test_is_in_frustum_restatement_equals_reference(seed):
         assert np.array_equal(v, vr)
         assert q[v != 0].tobytes() == qr[vr != 0].tobytes()
         assert 300 < np.count_nonzero(v) < len(v)
+
+
+@pytest.mark.skipif(ob.bow_ref() is None, reason="oracle/_ref/libbow_ref.so not built (reference tree absent)")
+@pytest.mark.parametrize("k,L,seed,early", [(10, 4, 11, 0.03), (10, 4, 12, 0.0), (6, 5, 13, 0.0), (3, 6, 14, 0.02)])
+def test_bow_restatement_equals_the_reference_dbow2_header(tmp_path, k, L, seed, early):
+    """oc_vocab_transform / oc_bow_score_l1 against the reference's own DBoW2 code: TemplatedVocabulary.h (a header template,
+    compiled verbatim as ORBVocabulary.h instantiates it) loads the vocabulary with its own text loader and runs transform()
+    and score(); only the leaf functions of DBoW2's absent .cpp files are restated (oracle/bow_glue.cc).
+    A leaf above level L - levelsup leaves `nid` uninitialised in the reference (TemplatedVocabulary.h:1151-1156, :1226-1258),
+    so the FeatureVector is compared where every leaf lies at or below that level; the BowVector always."""
+    voc = synth.synth_vocabulary(k, L, seed, early_leaf=early)
+    path = str(tmp_path / "voc.txt")
+    ob.write_vocabulary_text(path, k, L, *voc)
+    R = ob.RefVocabulary(path); O = ob.Vocabulary(k, L, *voc)
+    assert R.nwords == O.nwords > 100
+    parent = np.asarray(voc[0]); is_leaf = np.asarray(voc[1])
+    depth = np.zeros(len(parent) + 1, np.int64)
+    for i, p in enumerate(parent):
+        depth[i + 1] = depth[p] + 1
+    min_leaf_depth = int(depth[1:][is_leaf != 0].min())
+    f = synth.synth_features_near_words(voc, 1500, seed + 1, max_flips=12)
+    g = synth.synth_features_near_words(voc, 1300, seed + 2, max_flips=12)
+    checked_fv = 0
+    for levelsup in range(0, L + 1):
+        a, b = R.transform(f, levelsup), O.transform(f, levelsup)
+        assert np.array_equal(a["bow_id"], b["bow_id"]) and np.array_equal(a["bow_val"].view(np.uint64), b["bow_val"].view(np.uint64))
+        if L - levelsup <= min_leaf_depth:
+            for key in ("fv_node", "fv_off", "fv_feat"):
+                assert np.array_equal(a[key], b[key]), (levelsup, key)
+            checked_fv += 1
+    assert checked_fv >= 2
+    ta, tb = O.transform(f, 4), O.transform(g, 4)
+    assert R.score(ta, tb) == ob.bow_score_l1(ta["bow_id"], ta["bow_val"], tb["bow_id"], tb["bow_val"])
+    assert R.score(ta, ta) == ob.bow_score_l1(ta["bow_id"], ta["bow_val"], ta["bow_id"], ta["bow_val"])
