@@ -272,3 +272,51 @@ def test_is_in_frustum_matches_oracle_and_feeds_search_local_points(seed):
     assert n == no and np.array_equal(m, mo) and n > 100
     qe, ve = is_in_frustum(s["Tcw12"], s["Ow3"], s["cam9"], 8, s["log_scale_factor"], s["pt_xyz"][:0], s["pt_normal"][:0], s["pt_dist"][:0])
     assert len(qe) == 0 and len(ve) == 0
+
+
+@pytest.mark.parametrize("seed", list(range(100, 124)))
+def test_small_random_scenes_match_oracle(seed):
+    """The GPU twin of tests/test_matcher_ref.py::test_small_random_scenes_restatements_equal_reference: many small scenes
+    with random thresholds (sparse grids, empty windows, single candidates, heavy contention) through every matcher."""
+    from orb_slam2_commit_b200 import (is_in_frustum, search_by_projection_frame, search_by_projection_kf, search_by_sim3,
+                                       search_for_initialization)
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(8, 260)); extra = int(rng.integers(0, 60))
+    bounds = None if seed % 3 else np.array([-3.6, 643.2, -2.7, 482.9], np.float32)
+    s = synth.synth_local_points_scene(seed, n_points=n, n_extra=extra, cluster=float(rng.uniform(0, 0.8)), stereo=bool(seed & 1))
+    if bounds is not None:
+        s["bounds4"] = bounds
+    th, nnr = float(rng.choice([1.0, 3.0, 5.0, 20.0])), float(rng.choice([0.6, 0.8, 0.99]))
+    a, b = search_local_points(**s, th=th, nnratio=nnr), ob.search_local_points(**s, th=th, nnratio=nnr)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    t = synth.synth_tracking_scene(seed, n_last=n, n_extra=extra, cluster=float(rng.uniform(0, 0.8)), stereo=bool(seed & 2))
+    th = float(rng.choice([3.0, 7.0, 15.0, 40.0]))
+    for mode in (0, 1, 2):
+        a = search_by_projection_frame(**t, th=th, mode=mode, check_orientation=bool(seed & 4))
+        b = ob.search_by_projection_frame(**t, th=th, mode=mode, check_orientation=bool(seed & 4))
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    f = synth.synth_kf_projection_scene(seed, n_points=n, n_extra=extra, cluster=float(rng.uniform(0, 0.8)))
+    if bounds is not None:
+        f["cam9"] = f["cam9"].copy(); f["cam9"][5:9] = bounds
+    inv_s2 = (np.float32(1.0) / (f["scale_factors"] * f["scale_factors"])).astype(np.float32)
+    th = float(rng.choice([3.0, 4.0, 10.0, 30.0]))
+    fa = {k: v for k, v in f.items() if k not in ("occupied", "pt_angle")}
+    for mode in (0, 1):
+        a = fuse_search(**fa, u_right=None, inv_level_sigma2=inv_s2, th=th, mode=mode)
+        b = ob.fuse_search(**fa, u_right=None, inv_level_sigma2=inv_s2, th=th, mode=mode)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        md = int(rng.choice([50, 64, 100]))
+        a = search_by_projection_kf(**f, th=float(int(th)), max_dist=md, mode=mode, check_orientation=bool(seed & 1))
+        b = ob.search_by_projection_kf(**f, th=float(int(th)), max_dist=md, mode=mode, check_orientation=bool(seed & 1))
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    q, v = is_in_frustum(f["Tcw12"], f["Ow3"], f["cam9"], 8, f["log_scale_factor"], f["pt_xyz"], f["pt_normal"], f["pt_dist"], 0.5)
+    qo, vo = ob.is_in_frustum(f["Tcw12"], f["Ow3"], f["cam9"], 8, f["log_scale_factor"], f["pt_xyz"], f["pt_normal"], f["pt_dist"], 0.5)
+    assert np.array_equal(v, vo) and q[v != 0].tobytes() == qo[vo != 0].tobytes()
+    i = synth.synth_initialization_scene(seed, n=max(n, 20), cluster=float(rng.uniform(0, 0.8)))
+    win, nnr = int(rng.choice([10, 50, 100, 400])), float(rng.choice([0.7, 0.9, 0.99]))
+    a = search_for_initialization(**i, window_size=win, nnratio=nnr, check_orientation=bool(seed & 1))
+    b = ob.search_for_initialization(**i, window_size=win, nnratio=nnr, check_orientation=bool(seed & 1))
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    k1, k2, S12, S21, cam, sf, lsf = synth.synth_sim3_scene(seed, n_points=max(n, 30), n_extra=extra)
+    a, b = search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, th), ob.search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, th)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])

@@ -254,3 +254,55 @@ def test_bow_restatement_equals_the_reference_dbow2_header(tmp_path, k, L, seed,
     ta, tb = O.transform(f, 4), O.transform(g, 4)
     assert R.score(ta, tb) == ob.bow_score_l1(ta["bow_id"], ta["bow_val"], tb["bow_id"], tb["bow_val"])
     assert R.score(ta, ta) == ob.bow_score_l1(ta["bow_id"], ta["bow_val"], ta["bow_id"], ta["bow_val"])
+
+
+@pytest.mark.parametrize("seed", list(range(100, 124)))
+def test_small_random_scenes_restatements_equal_reference(seed):
+    """Many small scenes (tens to a few hundred features, random thresholds): sparse grids, empty windows, single candidates
+    and heavy contention hit the corner cases of every matcher loop."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(8, 260)); extra = int(rng.integers(0, 60))
+    bounds = None if seed % 3 else np.array(ODD_BOUNDS, np.float32)
+    # SearchByProjection(F, vpMapPoints)
+    s = synth.synth_local_points_scene(seed, n_points=n, n_extra=extra, cluster=float(rng.uniform(0, 0.8)), stereo=bool(seed & 1))
+    if bounds is not None:
+        s["bounds4"] = bounds
+    th, nnr = float(rng.choice([1.0, 3.0, 5.0, 20.0])), float(rng.choice([0.6, 0.8, 0.99]))
+    a, b = ob.search_local_points(**s, th=th, nnratio=nnr), ob.ref_search_local_points(**s, th=th, nnratio=nnr)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    # SearchByProjection(CurrentFrame, LastFrame)
+    t = synth.synth_tracking_scene(seed, n_last=n, n_extra=extra, cluster=float(rng.uniform(0, 0.8)), stereo=bool(seed & 2))
+    th = float(rng.choice([3.0, 7.0, 15.0, 40.0]))
+    nr, mr, mode = ob.ref_search_by_projection_frame(**t, th=th, mono=int(seed % 4 == 0), tlw_z=float(rng.choice([-5.0, 0.0, 5.0])), check_orientation=bool(seed & 4))
+    a = ob.search_by_projection_frame(**t, th=th, mode=mode, check_orientation=bool(seed & 4))
+    assert a[0] == nr and np.array_equal(a[1], mr)
+    # Fuse, both forms, and the two sequential KeyFrame / Frame projections
+    f = synth.synth_kf_projection_scene(seed, n_points=n, n_extra=extra, cluster=float(rng.uniform(0, 0.8)))
+    cam = f["cam9"].copy()
+    if bounds is not None:
+        cam[5:9] = bounds
+    raw = _raw_dist(f, rng)
+    inv_s2 = (np.float32(1.0) / (f["scale_factors"] * f["scale_factors"])).astype(np.float32)
+    th = float(rng.choice([3.0, 4.0, 10.0, 30.0]))
+    for mode in (0, 1):
+        T12 = f["Tcw12"] if mode == 0 else (np.float32(rng.uniform(0.5, 2.0)) * f["Tcw12"]).astype(np.float32)
+        nr, bir, T, Ow, d3 = ob.ref_fuse(f["kps"], f["desc"], None, T12, f["Ow3"], cam, f["scale_factors"], inv_s2, f["log_scale_factor"],
+                                         f["pt_xyz"], f["pt_normal"], raw, f["pt_desc"], f["pt_flags"], th, mode)
+        n_, bi, _ = ob.fuse_search(f["kps"], f["desc"], None, T, Ow, cam, f["scale_factors"], inv_s2, f["log_scale_factor"], f["pt_xyz"],
+                                   f["pt_normal"], d3, f["pt_desc"], f["pt_flags"], th, mode)
+        assert n_ == nr and np.array_equal(bi, bir)
+        md = int(rng.choice([50, 64, 100])) if mode == 0 else 50          # the loop-closing form always uses TH_LOW (:435)
+        nr, mr, T, Ow, d3 = ob.ref_search_by_projection_kf(f["kps"], f["desc"], f["occupied"], T12, cam, f["scale_factors"], f["log_scale_factor"],
+                                                           f["pt_xyz"], f["pt_normal"], raw, f["pt_desc"], f["pt_flags"], f["pt_angle"], float(int(th)), md, mode, bool(seed & 1))
+        n_, m = ob.search_by_projection_kf(f["kps"], f["desc"], f["occupied"], T, Ow, cam, f["scale_factors"], f["log_scale_factor"], f["pt_xyz"],
+                                           f["pt_normal"], d3, f["pt_desc"], f["pt_flags"], f["pt_angle"], float(int(th)), md, mode, bool(seed & 1))
+        assert n_ == nr and np.array_equal(m, mr)
+    qr, vr, d3 = ob.ref_is_in_frustum(f["Tcw12"], f["Ow3"], cam, 8, f["log_scale_factor"], f["pt_xyz"], f["pt_normal"], raw, 0.5)
+    q, v = ob.is_in_frustum(f["Tcw12"], f["Ow3"], cam, 8, f["log_scale_factor"], f["pt_xyz"], f["pt_normal"], d3, 0.5)
+    assert np.array_equal(v, vr) and q[v != 0].tobytes() == qr[vr != 0].tobytes()
+    # SearchForInitialization
+    i = synth.synth_initialization_scene(seed, n=max(n, 20), cluster=float(rng.uniform(0, 0.8)))
+    win, nnr = int(rng.choice([10, 50, 100, 400])), float(rng.choice([0.7, 0.9, 0.99]))
+    a, b = ob.search_for_initialization(**i, window_size=win, nnratio=nnr, check_orientation=bool(seed & 1)), \
+        ob.ref_search_for_initialization(**i, window_size=win, nnratio=nnr, check_orientation=bool(seed & 1))
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
