@@ -239,7 +239,7 @@ def run_reference_arm(args, rank, world):
     nthreads = os.cpu_count() or 1
     from oracle import binding as ob
     import ctypes as C
-    per_step = max(nthreads, 2 * nthreads)
+    per_step = 8 * nthreads                      # a bounded sample per step (~0.2 s on 16 threads), long enough that thread start-up does not weigh
     times = []
     kind = "reference" if ob.ref_available() else "port"
     if kind == "reference":
