@@ -38,6 +38,19 @@ inline void PackDescriptors(const cv::Mat& m, std::vector<unsigned char>& out)
     for (int i = 0; i < m.rows; i++) std::memcpy(&out[(size_t)i * 32], m.ptr(i), 32);
 }
 
+// Frame::isInFrustum(pMP, viewingCosLimit) (Frame.cc:315-378) for all local map points at once, as the loop of
+// Tracking::SearchLocalPoints (Tracking.cc:1409-1470) needs it. Tcw12 = (mRcw row-major, mtcw), Ow3 = mOw. queries[i] receives
+// the five mTrack* fields where inView[i] != 0 (= the return value = mbTrackInView) and feeds SearchByProjectionGPU below.
+inline bool IsInFrustumGPU(const float Tcw12[12], const float Ow3[3], const KeyFrameCamera& cam, const MapPointTable& pts,
+                           float viewingCosLimit, std::vector<OrbxTrackQuery>& queries, std::vector<unsigned char>& inView, int device = 0)
+{
+    queries.resize(pts.size()); inView.assign(pts.size(), 0);
+    if (pts.size() == 0) return true;
+    return orbx_is_in_frustum(Tcw12, Ow3, cam.camera9, (int)cam.mvScaleFactors.size(), cam.mfLogScaleFactor, pts.xyz.data(),
+                              pts.normal.data(), pts.dist.data(), (int)pts.size(), viewingCosLimit, queries.data(), inView.data(),
+                              device) == ORBX_OK;
+}
+
 // ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (ORBmatcher.cc:46-142).
 // queries[i] = (mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mnTrackScaleLevel) of vpMapPoints[i];
 // flags bit 0: mbTrackInView && !isBad(), bit 1: Observations() > 0. occupied[k]: F.mvpMapPoints[k] has observations.

@@ -43,6 +43,7 @@ MAIN = textwrap.dedent(r"""
         std::vector<OrbxTrackQuery> tq; std::vector<unsigned char> hm; std::vector<std::pair<size_t, size_t> > vp; std::vector<cv::Point2f> prev;
         const float b4[4] = {0, 640, 0, 480}, ow[3] = {0, 0, 0}, g28[28] = {0};
         int r = ORB_SLAM2::SearchByProjectionGPU(none, desc, 0, 0, b4, sf2, tq, d8, fl, 1.f, 0.8f, match);
+        std::vector<unsigned char> inview; r += ORB_SLAM2::IsInFrustumGPU(T, ow, kc, pts, 0.5f, tq, inview) ? 0 : 100;
         r += ORB_SLAM2::FuseSearchGPU(none, desc, 0, T, ow, kc, pts, 3.f, false, match);
         r += ORB_SLAM2::SearchByProjectionGPU(none, desc, 0, T, ow, kc, pts, 0, 10.f, 100, false, true, match);
         r += ORB_SLAM2::SearchForTriangulationGPU(0, none, desc, hm, 0, none, desc, hm, 0, g28, kc, false, true, vp);
