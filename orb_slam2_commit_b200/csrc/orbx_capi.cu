@@ -48,6 +48,8 @@ struct orbx_extractor {
     cudaStream_t stream = nullptr;
     static constexpr int MAX_SLOTS = 8;
     cudaStream_t slot_stream[MAX_SLOTS] = {};   // host-path double buffering (copy/compute overlap)
+    cudaStream_t copy_stream = nullptr;          // host batch path: all uploads of a call, in order, ahead of the kernels
+    std::vector<cudaEvent_t> in_ready, in_free;  // per input buffer: upload finished / kernels that read it finished
     // single-frame host calls are launch-bound (11 small kernels): after the first call with a given input form the
     // kernel sequence is replayed from a CUDA graph (one launch instead of eleven)
     cudaGraphExec_t g1 = nullptr;
@@ -156,6 +158,9 @@ extern "C" void orbx_destroy(orbx_extractor* h)
         for (int i = 0; i < 5; i++) if (h->ev[r][i]) cudaEventDestroy(h->ev[r][i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int j = 0; j < orbx_extractor::MAX_SLOTS; j++) if (h->slot_stream[j]) cudaStreamDestroy(h->slot_stream[j]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t e : h->in_ready) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->in_free) cudaEventDestroy(e);
     cudaGetLastError();
     delete h;
 }
@@ -481,20 +486,41 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
     // of later chunks and the D2H copy of earlier ones overlap the kernels of the current ones, and short chunks keep
     // the pipeline's fill and drain (one chunk's copy time each) small. A slot's stream serialises its own
     // H2D -> kernels -> D2H, so reusing a slot needs no extra event. ORBX_CHUNK / ORBX_SLOTS override the defaults
-    // (measured on B200, 1024 VGA frames per call: 2 x 128 -> 89 k frames/s, 8 x 64 -> 99 k).
-    int chunk = B >= 8 ? std::min(64, std::max(8, B / 8)) : B;
+    // (measured on B200, 1024 VGA frames per call, tools/exp_chunks.py: 8 x 128 -> 125.8 k frames/s, 8 x 64 -> 132.2 k,
+    // 8 x 32 -> 133.7 k, 8 x 16 -> 111.8 k).
+    int chunk = B >= 8 ? std::min(32, std::max(8, B / 8)) : B;
     if (const char* e = getenv("ORBX_CHUNK")) { const int v = atoi(e); if (v > 0 && B >= 8) chunk = std::min(v, B / 2); }
     int nslots = B >= 8 ? std::max(1, std::min(orbx_extractor::MAX_SLOTS, B / chunk)) : 1;
     if (const char* e = getenv("ORBX_SLOTS")) { const int v = atoi(e); if (v > 0 && B >= 8) nslots = std::max(1, std::min(std::min(v, orbx_extractor::MAX_SLOTS), B / chunk)); }
     for (int j = 0; j < nslots; j++)
         if (!h->slot_stream[j]) CK(cudaStreamCreateWithFlags(&h->slot_stream[j], cudaStreamNonBlocking));
     CK(cudaStreamSynchronize(h->stream));
+    // Uploads run ahead of the kernels: the staging buffer holds B frames, i.e. more chunks than there are compute slots,
+    // so every upload of a call goes onto ONE copy stream in order and a slot's stream only waits for its own chunk's
+    // event. (With the upload on the slot's stream, chunk k + nslots could not start its copy before chunk k had left the
+    // slot; the slots tend to finish together, and their uploads then queued up behind each other while the SMs idled:
+    // 7.89 -> 7.74 ms per 1024 VGA frames.) An input buffer is reused once the kernels that read it are done.
+    // What remains above the 6.7 ms of the kernels: uploads arrive about as fast as the kernels consume them, so few chunks
+    // are runnable at once and a chunk running alone fills the GPU less well than eight do (tools/exp_streams2.py).
+    const bool ahead = n > chunk && !getenv("ORBX_NO_COPY_STREAM");
+    const int nin = std::max(nslots, B / chunk);
+    if (ahead) {
+        if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        while ((int)h->in_ready.size() < nin) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            h->in_ready.push_back(a); h->in_free.push_back(b);
+        }
+    }
     int k = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, k++) {
         const int m = std::min(chunk, n - f0);
         const int slot = k % nslots, base = slot * chunk;
         cudaStream_t st = h->slot_stream[slot];
-        uint8_t* d_in = h->d_in + (size_t)base * fbytes;
+        const int in_slot = ahead ? k % nin : slot;
+        cudaStream_t cst = ahead ? h->copy_stream : st;
+        uint8_t* d_in = h->d_in + (size_t)in_slot * chunk * fbytes;
+        if (ahead && k >= nin) CK(cudaStreamWaitEvent(cst, h->in_free[in_slot], 0));
         OrbxKp28* d_kps = h->d_kps + (size_t)base * kc;
         uint8_t* d_desc = h->d_desc + (size_t)base * kc * 32;
         int* d_nkp = h->d_nkp + base;
@@ -504,13 +530,14 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
             if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
             contiguous = images[f0 + i] == images[f0] + (size_t)i * fbytes;
         }
-        if (contiguous) CK(cudaMemcpyAsync(d_in, images[f0], (size_t)m * fbytes, cudaMemcpyHostToDevice, st));
+        if (contiguous) CK(cudaMemcpyAsync(d_in, images[f0], (size_t)m * fbytes, cudaMemcpyHostToDevice, cst));
         else
             for (int i = 0; i < m; i++) {
                 if (!images[f0 + i]) return fail(ORBX_ERR_INVALID, "images[i] is NULL");
                 CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, rowbytes, images[f0 + i], stride, rowbytes, height,
-                                     cudaMemcpyHostToDevice, st));
+                                     cudaMemcpyHostToDevice, cst));
             }
+        if (ahead) { CK(cudaEventRecord(h->in_ready[in_slot], cst)); CK(cudaStreamWaitEvent(st, h->in_ready[in_slot], 0)); }
         int rc = ORBX_OK;
         const bool single = n == 1 && base == 0 && !h->timing && !getenv("ORBX_NO_GRAPH");
         const bool same_form = h->g1_channels == channels && h->g1_rgb == rgb && h->g1_rect == (int)rectify &&
@@ -539,6 +566,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
             if (single) h->g1_seen++;
         }
         if (rc != ORBX_OK) return rc;
+        if (ahead) CK(cudaEventRecord(h->in_free[in_slot], st));
         CK(cudaMemcpyAsync(nkp + f0, d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (cap == kc) {
             // caller sized its buffers with orbx_max_keypoints(): results land in place with two bulk copies
@@ -554,6 +582,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
             }
         }
     }
+    if (ahead) CK(cudaStreamSynchronize(h->copy_stream));
     for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(h->slot_stream[j]));
     h->last_frames = n; h->pyr_base = 0; h->map_chunk = chunk; h->map_slots = nslots;   // for the pyramid / debug accessors
     for (int i = 0; i < n; i++) if (nkp[i] > cap) status = ORBX_ERR_CAPACITY;
