@@ -932,8 +932,34 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    e2e_fps = world * B * e2e_steps / e2e_s
+    e2e_sync_fps = world * B * e2e_steps / e2e_s
     assert int(nkp_np.sum()) == int(nkp.sum()), "host path and device path disagree"
+    # the same step as a stream of batches: orbx_extract_batch_begin / _end with two batches in flight (two sets of pinned
+    # result buffers), so the upload of step i+1 overlaps the kernels of step i; every step's H2D and D2H stay in the timed region
+    e2e_fps, e2e_api = e2e_sync_fps, ("orbx_extract_batch_rectified" if rectify else "orbx_extract_batch") + " (pinned host buffers)"
+    if not rectify:
+        h_kps2 = torch.empty((B, cap, 28), dtype=torch.uint8, pin_memory=True)
+        h_desc2 = torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True)
+        h_nkp2 = torch.zeros(B, dtype=torch.int32, pin_memory=True)
+        sets = [(kps_np, desc_np, nkp_np), (h_kps2.numpy().view(api.KP_DTYPE).reshape(B, cap), h_desc2.numpy(), h_nkp2.numpy())]
+
+        def stream_of_batches(steps):
+            ex.extract_host_begin(hb, *sets[0])
+            for s_ in range(1, steps):
+                ex.extract_host_begin(hb, *sets[s_ % 2])
+                ex.extract_host_end()
+            ex.extract_host_end()
+        stream_of_batches(2)
+        barrier()
+        t0 = time.perf_counter()
+        stream_of_batches(e2e_steps)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_fps = world * B * e2e_steps / float(t.item())
+        e2e_api = "orbx_extract_batch_begin / _end (pinned host buffers, two batches in flight)"
+        assert int(sets[0][2].sum()) == int(nkp.sum()) and int(sets[1][2].sum()) == int(nkp.sum()), "batches in flight disagree with the device path"
 
     # ---- single-frame latency through orbx_extract (what a SLAM front-end sees: one frame in, keypoints out)
     lat_ms = None
@@ -1051,7 +1077,8 @@ def main():
                            "l2": f"batch working set {B * (W * H + ab['A'] * 1.3) / 1e6:.0f} MB per step > 126 MB L2 (inputs {B * W * H / 1e6:.0f} MB)"},
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-                        "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": ("orbx_extract_batch_rectified" if rectify else "orbx_extract_batch") + " (pinned host buffers)"},
+                        "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": e2e_api,
+                        "synchronous_call": {"value": e2e_sync_fps, "api": ("orbx_extract_batch_rectified" if rectify else "orbx_extract_batch") + ", one blocking call per step"}},
                 "latency_single_frame_ms": lat_ms,
                 "roofline": roofline, "stages": stages,
                 "pipeline": {"keypoints_per_frame": nkp_mean, "keypoints_per_s": frames_per_s * nkp_mean,

@@ -81,6 +81,15 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height,
 int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height, int stride,
                        OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
 
+/* The same call for a STREAM of batches (a video, a dataset): begin() enqueues the uploads, kernels and downloads of one batch
+ * and returns; end() waits for the OLDEST batch begun and returns its status (ORBX_ERR_CAPACITY as above). Two batches may be
+ * in flight, so that the uploads of batch i+1 overlap the kernels of batch i (a third begin(), a batch of another shape or any
+ * synchronous extract call first completes what is in flight). Host buffers must be distinct per batch in flight, stay valid
+ * until its end(), and cap must equal orbx_max_keypoints() after orbx_reserve(). Results are those of orbx_extract_batch. */
+int orbx_extract_batch_begin(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height, int stride,
+                             OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
+int orbx_extract_batch_end(orbx_extractor* h);
+
 /* Colour input: Tracking::GrabImage{Stereo,RGBD,Monocular} converts 3- and 4-channel frames with cv::cvtColor
  * (CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY, Tracking.cc:174-199, 215-237, 246-261) before the extractor
  * sees them. Here that conversion (OpenCV 4.x 8-bit arithmetic) is fused into the level-0 kernel: `images[i]` are

@@ -138,6 +138,8 @@ def lib():
                                          C.c_void_p, C.c_void_p, C.c_int]
         L.orbx_is_in_frustum_device.argtypes = [f32p, f32p, f32p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orbx_extract_batch_begin.argtypes = L.orbx_extract_batch.argtypes
+        L.orbx_extract_batch_end.argtypes = [C.c_void_p]
         L.orbx_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
         L.orbx_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
         L.orbx_peer_hamming_top2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
@@ -308,6 +310,19 @@ class ORBextractor:
         base = images.ctypes.data
         ptrs = (C.c_void_p * n)(*[base + i * h * w for i in range(n)])
         _ck(self._L.orbx_extract_batch(self._h, ptrs, n, w, h, w, kps.ctypes.data, cap, nkp.ctypes.data_as(i32p), desc.ctypes.data))
+
+    def extract_host_begin(self, images: np.ndarray, kps: np.ndarray, desc: np.ndarray, nkp: np.ndarray):
+        """orbx_extract_batch_begin: enqueue one batch (buffers as for extract_host, cap = reserve()) and return; up to two
+        batches in flight. The buffers belong to the batch until the matching extract_host_end()."""
+        n, h, w = images.shape
+        cap = kps.shape[1]
+        base = images.ctypes.data
+        ptrs = (C.c_void_p * n)(*[base + i * h * w for i in range(n)])
+        _ck(self._L.orbx_extract_batch_begin(self._h, ptrs, n, w, h, w, kps.ctypes.data, cap, nkp.ctypes.data_as(i32p), desc.ctypes.data))
+
+    def extract_host_end(self):
+        """orbx_extract_batch_end: wait for the oldest batch begun."""
+        _ck(self._L.orbx_extract_batch_end(self._h))
 
     def extract_host_rectified(self, images: np.ndarray, kps: np.ndarray, desc: np.ndarray, nkp: np.ndarray):
         """orbx_extract_batch_rectified on caller-owned buffers (see extract_host); images are UNRECTIFIED frames."""

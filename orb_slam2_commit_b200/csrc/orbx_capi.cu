@@ -49,6 +49,8 @@ struct orbx_extractor {
     static constexpr int MAX_SLOTS = 8;
     cudaStream_t slot_stream[MAX_SLOTS] = {};   // host-path double buffering (copy/compute overlap)
     cudaStream_t copy_stream = nullptr;          // host batch path: all uploads of a call, in order, ahead of the kernels
+    struct Pending { int n = 0, cap = 0, nslots = 0; size_t fbytes = 0; const int* nkp = nullptr; cudaEvent_t done[MAX_SLOTS] = {}; };
+    Pending pending[2]; int npending = 0;        // orbx_extract_batch_begin / _end: batches in flight, oldest first
     std::vector<cudaEvent_t> in_ready, in_free;  // per input buffer: upload finished / kernels that read it finished
     // single-frame host calls are launch-bound (11 small kernels): after the first call with a given input form the
     // kernel sequence is replayed from a CUDA graph (one launch instead of eleven)
@@ -152,6 +154,7 @@ static void release_device(orbx_extractor* h)
 extern "C" void orbx_destroy(orbx_extractor* h)
 {
     if (!h) return;
+    if (h->npending > 0) { cudaSetDevice(h->device); cudaDeviceSynchronize(); h->npending = 0; }   // batches begun and never ended
     release_device(h);
     cudaFree(h->d_remap);
     for (int r = 0; r < orbx_extractor::RING; r++)
@@ -159,6 +162,7 @@ extern "C" void orbx_destroy(orbx_extractor* h)
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int j = 0; j < orbx_extractor::MAX_SLOTS; j++) if (h->slot_stream[j]) cudaStreamDestroy(h->slot_stream[j]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto& pd : h->pending) for (cudaEvent_t e : pd.done) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->in_ready) cudaEventDestroy(e);
     for (cudaEvent_t e : h->in_free) cudaEventDestroy(e);
     cudaGetLastError();
@@ -457,9 +461,23 @@ extern "C" int orbx_get_stage_ms(orbx_extractor* h, float* ms4, int* nruns)
     return ORBX_OK;
 }
 
+// completes the oldest batch begun with orbx_extract_batch_begin: waits for its last operation on every slot stream
+static int finish_oldest_pending(orbx_extractor* h)
+{
+    if (h->npending <= 0) return ORBX_OK;
+    orbx_extractor::Pending& pd = h->pending[0];
+    for (int j = 0; j < pd.nslots; j++) CK(cudaEventSynchronize(pd.done[j]));
+    int status = ORBX_OK;
+    for (int i = 0; i < pd.n; i++) if (pd.nkp[i] > pd.cap) status = ORBX_ERR_CAPACITY;
+    std::swap(h->pending[0], h->pending[1]);                   // keeps both event sets alive
+    h->npending--;
+    if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
+    return status;
+}
+
 static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
                               int stride, int channels, int rgb, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors,
-                              bool rectify = false)
+                              bool rectify = false, bool begin_only = false)
 {
     if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
     if (n <= 0 || !images || width <= 0 || height <= 0) return ORBX_OK;        // empty input: silent, like :1141
@@ -467,6 +485,8 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
     const int gw = rectify ? h->map_w : width, gh = rectify ? h->map_h : height;
     if (channels != 1 && channels != 3 && channels != 4) return fail(ORBX_ERR_INVALID, "channels must be 1, 3 or 4 (Tracking.cc:174-199)");
     if (!keypoints || !nkp || !descriptors || cap < 0 || stride < width * channels) return fail(ORBX_ERR_INVALID, "bad output buffers");
+    if (gw != h->W || gh != h->H || h->max_batch < 1)
+        while (h->npending > 0) { const int rc = finish_oldest_pending(h); if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc; }
     if (gw != h->W || gh != h->H || h->max_batch < 1) {
         int rc = orbx_reserve(h, gw, gh, std::max(1, std::min(n, std::max(h->max_batch, 64))));
         if (rc != ORBX_OK) return rc;
@@ -475,6 +495,12 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
     const int B = h->max_batch, kc = h->L.kp_cap_total;
     const size_t fbytes = (size_t)width * height * channels;
     const int rowbytes = width * channels;
+    // batches still in flight: a synchronous call, a batch of another shape or a third batch first completes them
+    while (h->npending > 0 && (!begin_only || h->npending >= 2 || h->pending[0].n != n || h->pending[0].fbytes != fbytes ||
+                               h->pending[0].cap != cap)) {
+        const int rc = finish_oldest_pending(h);
+        if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc;
+    }
     if ((size_t)B * fbytes > h->d_in_bytes) {           // colour frames need a wider staging buffer than gray ones
         CK(cudaDeviceSynchronize());
         cudaFree(h->d_in); h->d_in = nullptr; h->d_in_bytes = 0;
@@ -520,7 +546,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
         const int in_slot = ahead ? k % nin : slot;
         cudaStream_t cst = ahead ? h->copy_stream : st;
         uint8_t* d_in = h->d_in + (size_t)in_slot * chunk * fbytes;
-        if (ahead && k >= nin) CK(cudaStreamWaitEvent(cst, h->in_free[in_slot], 0));
+        if (ahead) CK(cudaStreamWaitEvent(cst, h->in_free[in_slot], 0));   // no-op until the buffer has had a reader (also across begun batches)
         OrbxKp28* d_kps = h->d_kps + (size_t)base * kc;
         uint8_t* d_desc = h->d_desc + (size_t)base * kc * 32;
         int* d_nkp = h->d_nkp + base;
@@ -582,9 +608,19 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
             }
         }
     }
+    h->last_frames = n; h->pyr_base = 0; h->map_chunk = chunk; h->map_slots = nslots;   // for the pyramid / debug accessors
+    if (begin_only) {
+        orbx_extractor::Pending& pd = h->pending[h->npending];
+        pd.n = n; pd.cap = cap; pd.nslots = nslots; pd.fbytes = fbytes; pd.nkp = nkp;
+        for (int j = 0; j < nslots; j++) {
+            if (!pd.done[j]) CK(cudaEventCreateWithFlags(&pd.done[j], cudaEventDisableTiming));
+            CK(cudaEventRecord(pd.done[j], h->slot_stream[j]));
+        }
+        h->npending++;
+        return ORBX_OK;
+    }
     if (ahead) CK(cudaStreamSynchronize(h->copy_stream));
     for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(h->slot_stream[j]));
-    h->last_frames = n; h->pyr_base = 0; h->map_chunk = chunk; h->map_slots = nslots;   // for the pyramid / debug accessors
     for (int i = 0; i < n; i++) if (nkp[i] > cap) status = ORBX_ERR_CAPACITY;
     if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
     return status;
@@ -594,6 +630,22 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* image
                                   int stride, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
 {
     return extract_batch_impl(h, images, n, width, height, stride, 1, 0, keypoints, cap, nkp, descriptors);
+}
+
+extern "C" int orbx_extract_batch_begin(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,
+                                        int stride, OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors)
+{
+    if (h && cap != orbx_max_keypoints(h) && h->W == width && h->H == height)
+        return fail(ORBX_ERR_INVALID, "orbx_extract_batch_begin needs cap == orbx_max_keypoints() (results are downloaded in bulk)");
+    return extract_batch_impl(h, images, n, width, height, stride, 1, 0, keypoints, cap, nkp, descriptors, false, true);
+}
+
+extern "C" int orbx_extract_batch_end(orbx_extractor* h)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (h->npending <= 0) return fail(ORBX_ERR_STATE, "no batch in flight");
+    CK(cudaSetDevice(h->device));
+    return finish_oldest_pending(h);
 }
 
 extern "C" int orbx_extract_batch_color(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height,

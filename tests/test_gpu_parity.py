@@ -731,3 +731,40 @@ def test_full_stereo_match_large_scale_factor_plain_path():
     ur_o, dp_o = ob.stereo_match(oL, oR, kl_o, dl_o, kr_o, dr_o, 400.0, 700.0)
     assert np.array_equal(ur.view(np.uint32), ur_o.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dp_o.view(np.uint32))
     assert np.count_nonzero(ur >= 0) > 50 and kl["octave"].max() == 6
+
+
+def test_batches_in_flight_give_the_results_of_the_synchronous_call():
+    """orbx_extract_batch_begin / _end: two batches in flight (uploads of one overlapping the kernels of the other, shared
+    working-set slices and staging buffers) return exactly what orbx_extract_batch returns for each batch; a synchronous
+    call or a batch of another shape completes what is in flight first."""
+    from orb_slam2_commit_b200 import KP_DTYPE, OrbxError
+    W, H, B = 320, 240, 96
+    imgs = [np.stack([synth.synth_image(W, H, 700 + 10 * s + (i % 7)) for i in range(B)]) for s in range(3)]
+    ex = ORBextractor(300, 1.2, 4, 20, 7)
+    cap = ex.reserve(W, H, B)
+    ref = []
+    for s in range(3):
+        k = np.zeros((B, cap), KP_DTYPE); d = np.zeros((B, cap, 32), np.uint8); n = np.zeros(B, np.int32)
+        ex.extract_host(imgs[s], k, d, n); ref.append((k, d, n))
+    out = [(np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32)) for _ in range(3)]
+    ex.extract_host_begin(imgs[0], *out[0])
+    ex.extract_host_begin(imgs[1], *out[1])
+    ex.extract_host_end()                                        # batch 0
+    ex.extract_host_begin(imgs[2], *out[2])                      # batch 1 still in flight
+    ex.extract_host_end(); ex.extract_host_end()
+    for s in range(3):
+        assert np.array_equal(out[s][2], ref[s][2]) and int(ref[s][2].min()) > 50
+        for i in range(B):
+            c = ref[s][2][i]
+            assert out[s][0][i, :c].tobytes() == ref[s][0][i, :c].tobytes() and np.array_equal(out[s][1][i, :c], ref[s][1][i, :c])
+    with pytest.raises(OrbxError):
+        ex.extract_host_end()                                    # nothing in flight
+    # a third begin completes the oldest; a synchronous call completes everything
+    for s in range(3):
+        for a in out[s]: a[...] = 0
+        ex.extract_host_begin(imgs[s], *out[s])
+    k = np.zeros((B, cap), KP_DTYPE); d = np.zeros((B, cap, 32), np.uint8); n = np.zeros(B, np.int32)
+    ex.extract_host(imgs[0], k, d, n)
+    for s in range(3):
+        assert np.array_equal(out[s][2], ref[s][2])
+    assert np.array_equal(n, ref[0][2])
