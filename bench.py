@@ -768,7 +768,29 @@ def run_stereo(args, torch, dist, rank, world, local, dev):
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_sync_v = world * P * n_e2e / float(t.item())
+    # the same step as a stream of batches (two batches of pairs in flight, two sets of pinned result buffers)
+    from orb_slam2_commit_b200 import stereo_extract_host_begin, stereo_extract_host_end
+    h_k2 = [pin(P, cap, 28) for _ in range(2)]; h_d2 = [pin(P, cap, 32) for _ in range(2)]
+    h_n2 = [pin(P, dt=torch.int32) for _ in range(2)]; h_f2 = [pin(P, cap, dt=torch.float32) for _ in range(2)]
+    hout2 = dict(kl=h_k2[0].numpy().view(api.KP_DTYPE).reshape(P, cap), kr=h_k2[1].numpy().view(api.KP_DTYPE).reshape(P, cap),
+                 dl=h_d2[0].numpy(), dr=h_d2[1].numpy(), nl=h_n2[0].numpy(), nr=h_n2[1].numpy(), u_right=h_f2[0].numpy(), depth=h_f2[1].numpy())
+    houts = [hout, hout2]
+
+    def stream_of_batches(steps):
+        stereo_extract_host_begin(exL, exR, hL.numpy(), hR.numpy(), c["bf"], c["fx"], houts[0])
+        for s_ in range(1, steps):
+            stereo_extract_host_begin(exL, exR, hL.numpy(), hR.numpy(), c["bf"], c["fx"], houts[s_ % 2])
+            stereo_extract_host_end(exL)
+        stereo_extract_host_end(exL)
+    stream_of_batches(2)
+    barrier()
+    t0 = time.perf_counter()
+    stream_of_batches(n_e2e)
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_v = world * P * n_e2e / float(t.item())
+    assert np.array_equal(hout["nl"], hout2["nl"]) and np.array_equal(hout["u_right"].view(np.uint32)[0, :hout["nl"][0]], hout2["u_right"].view(np.uint32)[0, :hout["nl"][0]])
     if rank != 0: return
     matched = float((outs[6][:, :] >= 0).sum().item()) / P   # includes unwritten tail slots only if >= 0 garbage; informational
     nl_np = outs[2].numpy()
@@ -780,7 +802,8 @@ def run_stereo(args, torch, dist, rank, world, local, dev):
                        "pairs_per_step_per_gpu": P, "distinct_pairs": len(pairs)},
             "clocks": clocks, "gpu_launches": (2 * (c["nlevels"] + 3) + 2) * args.steps,
             "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * W * H, "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in outs)), "steps": n_e2e,
-                    "api": "orbx_stereo_extract_batch (pinned host buffers)"},
+                    "api": "orbx_stereo_extract_batch_begin / _end (pinned host buffers, two batches in flight)",
+                    "synchronous_call": {"value": e2e_sync_v, "api": "orbx_stereo_extract_batch, one blocking call per step"}},
             "stages": {"extract_left_right_ms": ms_extract, "stereo_match_ms": ms_match},
             "pipeline": {"keypoints_per_image": float(nl_np.mean()), "stereo_matches_per_pair": matched}}
     if world == 1 and not args.no_cpu_baseline:

@@ -225,6 +225,14 @@ int orbx_stereo_extract_batch(orbx_extractor* left, orbx_extractor* right, const
                               float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
                               OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
                               float* u_right, float* depth);
+/* begin / end form of the same call for streams of batches (see orbx_extract_batch_begin): up to two batches of pairs in
+ * flight, end() completes the oldest and returns its status. The batches in flight are tracked in `left`. */
+int orbx_stereo_extract_batch_begin(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                                    const uint8_t* const* images_right, int n, int width, int height, int stride,
+                                    float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
+                                    OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
+                                    float* u_right, float* depth);
+int orbx_stereo_extract_batch_end(orbx_extractor* left);
 /* Device-resident, batched form: `pairs` stereo pairs whose left / right frames were the frames 0..pairs-1 of the last
  * orbx_extract_device call on `left` / `right`. Keypoints, descriptors and counts are those calls' device outputs
  * ([pairs][cap] layout). d_u_right / d_depth: [pairs][cap] floats, entries i < nl[pair] are written. Asynchronous on

@@ -97,6 +97,8 @@ def lib():
         L.orbx_stereo_extract_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                                 C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbx_stereo_extract_batch_begin.argtypes = L.orbx_stereo_extract_batch.argtypes
+        L.orbx_stereo_extract_batch_end.argtypes = [C.c_void_p]
         L.orbx_synchronize.argtypes = [C.c_void_p]
         L.orbx_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
@@ -424,6 +426,23 @@ def image_bounds(width, height, K4, dist, device: int = 0):
     _ck(lib().orbx_image_bounds(width, height, K4.ctypes.data_as(f32p), dist.ctypes.data_as(f32p), len(dist),
                                 b.ctypes.data_as(f32p), device))
     return b
+
+
+def stereo_extract_host_begin(left: ORBextractor, right: ORBextractor, images_left: np.ndarray, images_right: np.ndarray, mbf: float,
+                              fx: float, out: dict):
+    """orbx_stereo_extract_batch_begin (buffers as for stereo_extract_host); up to two batches in flight, each owning its `out`."""
+    n, h, w = images_left.shape
+    cap = out["kl"].shape[1]
+    pl = (C.c_void_p * n)(*[images_left.ctypes.data + i * h * w for i in range(n)])
+    pr = (C.c_void_p * n)(*[images_right.ctypes.data + i * h * w for i in range(n)])
+    _ck(lib().orbx_stereo_extract_batch_begin(left._h, right._h, pl, pr, n, w, h, w, mbf, fx, out["kl"].ctypes.data, out["dl"].ctypes.data,
+                                              out["nl"].ctypes.data, out["kr"].ctypes.data, out["dr"].ctypes.data, out["nr"].ctypes.data,
+                                              cap, out["u_right"].ctypes.data, out["depth"].ctypes.data))
+
+
+def stereo_extract_host_end(left: ORBextractor):
+    """orbx_stereo_extract_batch_end: wait for the oldest batch of pairs begun."""
+    _ck(lib().orbx_stereo_extract_batch_end(left._h))
 
 
 def stereo_extract_host(left: ORBextractor, right: ORBextractor, images_left: np.ndarray, images_right: np.ndarray, mbf: float,

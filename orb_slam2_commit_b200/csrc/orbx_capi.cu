@@ -49,7 +49,7 @@ struct orbx_extractor {
     static constexpr int MAX_SLOTS = 8;
     cudaStream_t slot_stream[MAX_SLOTS] = {};   // host-path double buffering (copy/compute overlap)
     cudaStream_t copy_stream = nullptr;          // host batch path: all uploads of a call, in order, ahead of the kernels
-    struct Pending { int n = 0, cap = 0, nslots = 0; size_t fbytes = 0; const int* nkp = nullptr; cudaEvent_t done[MAX_SLOTS] = {}; };
+    struct Pending { int n = 0, cap = 0, nslots = 0; size_t fbytes = 0; const int* nkp = nullptr; const int* nkp2 = nullptr; cudaEvent_t done[MAX_SLOTS] = {}; };
     Pending pending[2]; int npending = 0;        // orbx_extract_batch_begin / _end: batches in flight, oldest first
     std::vector<cudaEvent_t> in_ready, in_free;  // per input buffer: upload finished / kernels that read it finished
     // single-frame host calls are launch-bound (11 small kernels): after the first call with a given input form the
@@ -468,7 +468,7 @@ static int finish_oldest_pending(orbx_extractor* h)
     orbx_extractor::Pending& pd = h->pending[0];
     for (int j = 0; j < pd.nslots; j++) CK(cudaEventSynchronize(pd.done[j]));
     int status = ORBX_OK;
-    for (int i = 0; i < pd.n; i++) if (pd.nkp[i] > pd.cap) status = ORBX_ERR_CAPACITY;
+    for (int i = 0; i < pd.n; i++) if (pd.nkp[i] > pd.cap || (pd.nkp2 && pd.nkp2[i] > pd.cap)) status = ORBX_ERR_CAPACITY;
     std::swap(h->pending[0], h->pending[1]);                   // keeps both event sets alive
     h->npending--;
     if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
@@ -611,7 +611,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
     h->last_frames = n; h->pyr_base = 0; h->map_chunk = chunk; h->map_slots = nslots;   // for the pyramid / debug accessors
     if (begin_only) {
         orbx_extractor::Pending& pd = h->pending[h->npending];
-        pd.n = n; pd.cap = cap; pd.nslots = nslots; pd.fbytes = fbytes; pd.nkp = nkp;
+        pd.n = n; pd.cap = cap; pd.nslots = nslots; pd.fbytes = fbytes; pd.nkp = nkp; pd.nkp2 = nullptr;
         for (int j = 0; j < nslots; j++) {
             if (!pd.done[j]) CK(cudaEventCreateWithFlags(&pd.done[j], cudaEventDisableTiming));
             CK(cudaEventRecord(pd.done[j], h->slot_stream[j]));
@@ -940,14 +940,20 @@ extern "C" int orbx_stereo_match_device(orbx_extractor* left, orbx_extractor* ri
 // ComputeStereoMatches for n pairs, chunks pipelined over the slot streams exactly like orbx_extract_batch (H2D of later
 // chunks and D2H of earlier ones overlap the kernels). Both extractors run on the left extractor's slot stream so that
 // the matcher can follow them without an event.
-extern "C" int orbx_stereo_extract_batch(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
-                                         const uint8_t* const* images_right, int n, int width, int height, int stride,
-                                         float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
-                                         OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
-                                         float* u_right, float* depth)
+static int stereo_extract_batch_impl(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                                     const uint8_t* const* images_right, int n, int width, int height, int stride,
+                                     float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
+                                     OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
+                                     float* u_right, float* depth, bool begin_only)
 {
     if (!left || !right || left == right) return fail(ORBX_ERR_INVALID, "two extractor instances required (Tracking.cc:120-123)");
     if (n <= 0 || !images_left || !images_right || width <= 0 || height <= 0) return ORBX_OK;
+    // batches in flight live in `left`: a blocking call, another shape or a third batch first completes them
+    while (left->npending > 0 && (!begin_only || left->npending >= 2 || left->pending[0].n != n || left->pending[0].cap != cap ||
+                                  left->pending[0].fbytes != (size_t)width * height || width != left->W || height != left->H)) {
+        const int rc = finish_oldest_pending(left);
+        if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc;
+    }
     if (!kp_left || !desc_left || !n_left || !kp_right || !desc_right || !n_right || !u_right || !depth || stride < width)
         return fail(ORBX_ERR_INVALID, "bad output buffers");
     if (left->device != right->device || left->nlevels != right->nlevels || left->scale_factor != right->scale_factor)
@@ -1035,10 +1041,45 @@ extern "C" int orbx_stereo_extract_batch(orbx_extractor* left, orbx_extractor* r
         CK(cudaMemcpyAsync(u_right + (size_t)f0 * kc, d_ur, (size_t)m * kc * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(depth + (size_t)f0 * kc, d_dp, (size_t)m * kc * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(left->slot_stream[j]));
     for (orbx_extractor* h : {left, right}) { h->last_frames = n; h->pyr_base = 0; h->map_chunk = chunk; h->map_slots = nslots; }
+    if (begin_only) {
+        orbx_extractor::Pending& pd = left->pending[left->npending];
+        pd.n = n; pd.cap = cap; pd.nslots = nslots; pd.fbytes = fbytes; pd.nkp = n_left; pd.nkp2 = n_right;
+        for (int j = 0; j < nslots; j++) {
+            if (!pd.done[j]) CK(cudaEventCreateWithFlags(&pd.done[j], cudaEventDisableTiming));
+            CK(cudaEventRecord(pd.done[j], left->slot_stream[j]));
+        }
+        left->npending++;
+        return ORBX_OK;
+    }
+    for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(left->slot_stream[j]));
     for (int i = 0; i < n; i++) if (n_left[i] > kc || n_right[i] > kc) return fail(ORBX_ERR_CAPACITY, "keypoint buffer too small");
     return ORBX_OK;
+}
+
+extern "C" int orbx_stereo_extract_batch(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                                         const uint8_t* const* images_right, int n, int width, int height, int stride,
+                                         float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
+                                         OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
+                                         float* u_right, float* depth)
+{
+    return stereo_extract_batch_impl(left, right, images_left, images_right, n, width, height, stride, mbf, fx, kp_left, desc_left, n_left,
+                                     kp_right, desc_right, n_right, cap, u_right, depth, false);
+}
+
+extern "C" int orbx_stereo_extract_batch_begin(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                                               const uint8_t* const* images_right, int n, int width, int height, int stride,
+                                               float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
+                                               OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
+                                               float* u_right, float* depth)
+{
+    return stereo_extract_batch_impl(left, right, images_left, images_right, n, width, height, stride, mbf, fx, kp_left, desc_left, n_left,
+                                     kp_right, desc_right, n_right, cap, u_right, depth, true);
+}
+
+extern "C" int orbx_stereo_extract_batch_end(orbx_extractor* left)
+{
+    return orbx_extract_batch_end(left);
 }
 
 extern "C" int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, const OrbxKeyPoint* kl, const uint8_t* dl,

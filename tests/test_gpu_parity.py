@@ -768,3 +768,39 @@ def test_batches_in_flight_give_the_results_of_the_synchronous_call():
     for s in range(3):
         assert np.array_equal(out[s][2], ref[s][2])
     assert np.array_equal(n, ref[0][2])
+
+
+def test_stereo_batches_in_flight_give_the_results_of_the_synchronous_call():
+    """orbx_stereo_extract_batch_begin / _end: two batches of pairs in flight return what the blocking call returns."""
+    from orb_slam2_commit_b200 import KP_DTYPE, stereo_extract_host, stereo_extract_host_begin, stereo_extract_host_end
+    W, H, n = 480, 200, 24
+    args = (600, 1.2, 5, 20, 7)
+    exL, exR = ORBextractor(*args), ORBextractor(*args)
+    cap = exL.reserve(W, H, n); assert exR.reserve(W, H, n) == cap
+    bf, fx = 386.1448 * 0.4, 718.856 * 0.4
+
+    def bufs():
+        return dict(kl=np.zeros((n, cap), KP_DTYPE), kr=np.zeros((n, cap), KP_DTYPE), dl=np.zeros((n, cap, 32), np.uint8),
+                    dr=np.zeros((n, cap, 32), np.uint8), nl=np.zeros(n, np.int32), nr=np.zeros(n, np.int32),
+                    u_right=np.zeros((n, cap), np.float32), depth=np.zeros((n, cap), np.float32))
+    batches = []
+    for s in range(3):
+        pairs = [synth.synth_stereo_pair(W, H, 900 + 30 * s + (i % 5), max_disp=40) for i in range(n)]
+        batches.append((np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])))
+    ref = []
+    for L, R in batches:
+        o = bufs(); stereo_extract_host(exL, exR, L, R, bf, fx, o); ref.append(o)
+    out = [bufs() for _ in range(3)]
+    stereo_extract_host_begin(exL, exR, *batches[0], bf, fx, out[0])
+    stereo_extract_host_begin(exL, exR, *batches[1], bf, fx, out[1])
+    stereo_extract_host_end(exL)
+    stereo_extract_host_begin(exL, exR, *batches[2], bf, fx, out[2])
+    stereo_extract_host_end(exL); stereo_extract_host_end(exL)
+    for s in range(3):
+        assert np.array_equal(out[s]["nl"], ref[s]["nl"]) and np.array_equal(out[s]["nr"], ref[s]["nr"])
+        for i in range(n):
+            nl = int(ref[s]["nl"][i])
+            assert out[s]["kl"][i, :nl].tobytes() == ref[s]["kl"][i, :nl].tobytes()
+            assert np.array_equal(out[s]["u_right"][i, :nl].view(np.uint32), ref[s]["u_right"][i, :nl].view(np.uint32))
+            assert np.array_equal(out[s]["depth"][i, :nl].view(np.uint32), ref[s]["depth"][i, :nl].view(np.uint32))
+        assert int(np.count_nonzero(ref[s]["u_right"] > 0)) > 20 * n
