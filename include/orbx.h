@@ -84,7 +84,8 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* const* images, int n, i
 /* The same call for a STREAM of batches (a video, a dataset): begin() enqueues the uploads, kernels and downloads of one batch
  * and returns; end() waits for the OLDEST batch begun and returns its status (ORBX_ERR_CAPACITY as above). Two batches may be
  * in flight, so that the uploads of batch i+1 overlap the kernels of batch i (a third begin(), a batch of another shape or any
- * synchronous extract call first completes what is in flight). Host buffers must be distinct per batch in flight, stay valid
+ * other extract / stereo / pyramid call on the handle first completes what is in flight; a capacity overflow of a batch that
+ * was completed that way is still visible in its nkp). Host buffers must be distinct per batch in flight, stay valid
  * until its end(), and cap must equal orbx_max_keypoints() after orbx_reserve(). Results are those of orbx_extract_batch. */
 int orbx_extract_batch_begin(orbx_extractor* h, const uint8_t* const* images, int n, int width, int height, int stride,
                              OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);

@@ -378,12 +378,21 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     return ORBX_OK;
 }
 
+// batches begun with orbx_extract_batch_begin share the working set with every other call on the handle: complete them first
+static int finish_oldest_pending(orbx_extractor* h);
+static int finish_all_pending(orbx_extractor* h)
+{
+    while (h && h->npending > 0) { const int rc = finish_oldest_pending(h); if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc; }
+    return ORBX_OK;
+}
+
 extern "C" int orbx_extract_device(orbx_extractor* h, const uint8_t* d_images, int n, int width, int height, int stride,
                                    size_t frame_pitch_bytes, OrbxKeyPoint* d_keypoints, int cap, int32_t* d_nkp,
                                    uint8_t* d_descriptors, void* cuda_stream)
 {
     if (!h || !d_images || !d_keypoints || !d_nkp || !d_descriptors) return fail(ORBX_ERR_INVALID, "NULL argument");
     if (n <= 0 || width <= 0 || height <= 0 || stride < width || cap <= 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    { const int rc = finish_all_pending(h); if (rc != ORBX_OK) return rc; }
     if (width != h->W || height != h->H || n > h->max_batch) {
         int rc = orbx_reserve(h, width, height, std::max(n, h->max_batch));
         if (rc != ORBX_OK) return rc;
@@ -400,6 +409,7 @@ extern "C" int orbx_extract_device_rectified(orbx_extractor* h, const uint8_t* d
     if (!h || !d_images || !d_keypoints || !d_nkp || !d_descriptors) return fail(ORBX_ERR_INVALID, "NULL argument");
     if (!h->d_remap) return fail(ORBX_ERR_STATE, "orbx_set_rectify_maps has not been called");
     if (n <= 0 || stride < h->map_src_w || cap <= 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    { const int rc = finish_all_pending(h); if (rc != ORBX_OK) return rc; }
     if (h->map_w != h->W || h->map_h != h->H || n > h->max_batch) {
         int rc = orbx_reserve(h, h->map_w, h->map_h, std::max(n, h->max_batch));
         if (rc != ORBX_OK) return rc;
@@ -714,7 +724,9 @@ extern "C" int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level
 extern "C" int orbx_pyramid_level(orbx_extractor* h, int frame, int level, uint8_t* dst, int dst_stride)
 {
     const uint8_t* pay; int pitch;
-    int rc = orbx_pyramid_level_device(h, frame, level, &pay, &pitch);
+    int rc = finish_all_pending(h);                      // the pyramid of a batch still in flight is not there yet
+    if (rc != ORBX_OK) return rc;
+    rc = orbx_pyramid_level_device(h, frame, level, &pay, &pitch);
     if (rc != ORBX_OK) return rc;
     const OrbxLevelGeom& g = h->lvl[level];
     if (!dst || dst_stride < g.w + 2 * ORBX_EDGE) return fail(ORBX_ERR_INVALID, "dst too small");
@@ -896,7 +908,10 @@ extern "C" int orbx_stereo_match_device(orbx_extractor* left, orbx_extractor* ri
     if (!left || !right || pairs <= 0 || cap <= 0 || !d_kl || !d_dl || !d_nl || !d_kr || !d_dr || !d_nr || !d_u_right || !d_depth)
         return fail(ORBX_ERR_INVALID, "bad argument");
     if (cap > 18000) return fail(ORBX_ERR_UNSUPPORTED, "more than 18000 keypoints per image");
-    int rc = stereo_check_pair(left, right, pairs);
+    int rc = finish_all_pending(left);
+    if (rc == ORBX_OK) rc = finish_all_pending(right);
+    if (rc != ORBX_OK) return rc;
+    rc = stereo_check_pair(left, right, pairs);
     if (rc != ORBX_OK) return rc;
     CK(cudaSetDevice(left->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : left->stream;
