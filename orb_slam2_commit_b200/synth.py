@@ -556,3 +556,19 @@ def synth_initialization_scene(seed: int, n: int = 1500, cluster: float = 0.25):
     k2, d2 = k2[p2], d2[p2]
     prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)                      # Tracking.cc: mvbPrevMatched[i] = mInitialFrame.mvKeysUn[i].pt
     return dict(kps1=k1, desc1=d1, kps2=k2, desc2=d2, bounds4=np.array([0.0, W, 0.0, H], np.float32), prev_matched=prev)
+
+
+def golden_matcher_scenes():
+    """The scene set behind tests/golden/ref_matchers.npz, shared by tools/gen_golden_matchers.py and the tests so that generator
+    and checks cannot drift apart."""
+    s = {}
+    s["local"] = synth_local_points_scene(41, n_points=600, n_extra=150)
+    s["track"] = synth_tracking_scene(42, n_last=500, n_extra=150)
+    s["kf"] = synth_kf_projection_scene(43, n_points=500, n_extra=200)
+    mx = s["kf"]["pt_dist"][:, 2].copy(); mn = (mx / s["kf"]["scale_factors"][-1]).astype(np.float32)
+    s["kf_raw"] = np.stack([mn, mx], 1).astype(np.float32)
+    s["voc"] = synth_vocabulary(10, 4, 5)
+    s["tri"] = synth_triangulation_scene(s["voc"], 44, n_points=600, n_extra=150)
+    s["init"] = synth_initialization_scene(45, n=700)
+    s["sim3"] = synth_sim3_scene(46, n_points=700, n_extra=150)
+    return s

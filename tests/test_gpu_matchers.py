@@ -320,3 +320,16 @@ def test_small_random_scenes_match_oracle(seed):
     k1, k2, S12, S21, cam, sf, lsf = synth.synth_sim3_scene(seed, n_points=max(n, 30), n_extra=extra)
     a, b = search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, th), ob.search_by_sim3(k1, k2, S12, S21, cam, sf, lsf, th)
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+def test_matchers_reproduce_the_reference_fixtures():
+    """The CUDA matchers through the C ABI against tests/golden/ref_matchers.npz: outputs of the UNMODIFIED reference code
+    (ORBmatcher.cc, Frame::isInFrustum, DBoW2's TemplatedVocabulary.h) on seeded scenes, generated by tools/gen_golden_matchers.py."""
+    import orb_slam2_commit_b200 as impl
+    import golden_matchers
+    S = golden_matchers.scenes()
+    V = ORBVocabulary(10, 4, *S["voc"])
+
+    def tri(t):
+        return V.search_for_triangulation(**t, levelsup=2)
+    golden_matchers.check(impl, V.transform, tri)
