@@ -41,6 +41,11 @@ def build(force: bool = False) -> None:
         stale = (not os.path.exists(MATCHER_REF_LIB)) or any(os.path.getmtime(MATCHER_REF_LIB) < os.path.getmtime(s) for s in srcs)
         if force or stale:
             subprocess.check_call(["make", "-C", HERE, "ref_matcher"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"):
+        bow_lib = os.path.join(HERE, "_ref", "libbow_ref.so")
+        srcs = [os.path.join(HERE, "bow_glue.cc"), os.path.join(HERE, "slamshim", "opencv2", "core", "core.hpp")]
+        if force or (not os.path.exists(bow_lib)) or any(os.path.getmtime(bow_lib) < os.path.getmtime(s) for s in srcs):
+            subprocess.check_call(["make", "-C", HERE, "ref_bow"], stdout=subprocess.DEVNULL)
 
 
 _lib = None
