@@ -306,3 +306,19 @@ def test_small_random_scenes_restatements_equal_reference(seed):
     a, b = ob.search_for_initialization(**i, window_size=win, nnratio=nnr, check_orientation=bool(seed & 1)), \
         ob.ref_search_for_initialization(**i, window_size=win, nnratio=nnr, check_orientation=bool(seed & 1))
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_committed_matcher_fixtures_are_what_the_reference_produces_now(tmp_path, monkeypatch):
+    """tests/golden/ref_matchers.npz must be reproducible: regenerating it from the reference sources gives the same arrays."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_golden_matchers", os.path.join(root, "tools", "gen_golden_matchers.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    (tmp_path / "tests" / "golden").mkdir(parents=True)
+    monkeypatch.setattr(gen, "ROOT", str(tmp_path))
+    gen.main()
+    new = np.load(tmp_path / "tests" / "golden" / "ref_matchers.npz"); old = np.load(os.path.join(root, "tests", "golden", "ref_matchers.npz"))
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert np.asarray(old[k]).tobytes() == np.asarray(new[k]).tobytes(), k
