@@ -107,6 +107,9 @@ int orbx_extract_batch_color(orbx_extractor* h, const uint8_t* const* images, in
  * Map values must stay below 2^26 in magnitude. */
 int orbx_set_rectify_maps(orbx_extractor* h, const float* map1, const float* map2, int map_width, int map_height,
                           int map_stride, int src_width, int src_height);
+/* size of the rectified frame (= the map's own size, which may differ from the source size): what orbx_reserve and the
+ * keypoint capacity of the rectified calls are based on */
+int orbx_rectify_map_size(const orbx_extractor* h, int* map_width, int* map_height);
 int orbx_extract_batch_rectified(orbx_extractor* h, const uint8_t* const* images, int n, int stride,
                                  OrbxKeyPoint* keypoints, int cap, int* nkp, uint8_t* descriptors);
 
@@ -267,6 +270,14 @@ typedef struct orbx_vocabulary orbx_vocabulary;
 int  orbx_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,
                        const uint8_t* descriptors, const double* weights, int device, orbx_vocabulary** out);
 void orbx_vocab_destroy(orbx_vocabulary* v);
+/* Thread safety: ORB-SLAM2 shares one ORBVocabulary between Tracking (Frame::ComputeBoW, Frame.cc:462-469), LocalMapping
+ * (KeyFrame::ComputeBoW, SearchForTriangulation) and LoopClosing (score / SearchByBoW), and DBoW2's transform() is const.
+ * Here the tree is immutable but the handle keeps the results of the LAST transform, so every entry point that takes an
+ * orbx_vocabulary* holds the handle's (recursive) mutex for its duration, the host one-shot forms (orbx_search_by_bow*,
+ * orbx_search_for_triangulation) across their whole transform + match sequence. A caller that issues a multi-call
+ * sequence itself (orbx_bow_transform followed by orbx_bow_get / orbx_bow_score) brackets it with these two. */
+int  orbx_vocab_lock(orbx_vocabulary* v);
+int  orbx_vocab_unlock(orbx_vocabulary* v);
 int  orbx_vocab_words(const orbx_vocabulary* v);
 int  orbx_vocab_nodes(const orbx_vocabulary* v);
 /* transform(features, mBowVec, mFeatVec, levelsup) for a batch: frame f has min(counts[f], cap) descriptors at

@@ -79,6 +79,7 @@ def lib():
                                         C.POINTER(C.c_void_p)]
         L.orbx_vocab_destroy.argtypes = [C.c_void_p]; L.orbx_vocab_destroy.restype = None
         L.orbx_vocab_words.argtypes = [C.c_void_p]; L.orbx_vocab_nodes.argtypes = [C.c_void_p]
+        L.orbx_vocab_lock.argtypes = [C.c_void_p]; L.orbx_vocab_unlock.argtypes = [C.c_void_p]
         L.orbx_bow_transform_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orbx_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orbx_bow_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
@@ -690,8 +691,13 @@ class ORBVocabulary:
         buf = np.zeros((frames, cap, 32), np.uint8); counts = np.zeros(frames, np.int32)
         for i, d in enumerate(descs):
             buf[i, :len(d)] = d; counts[i] = len(d)
-        _ck(self._L.orbx_bow_transform(self._h, buf.ctypes.data, counts.ctypes.data, frames, cap, levelsup))
-        return [self.get(i, int(counts[i])) for i in range(frames)]
+        # transform -> get is one critical section on the handle (it keeps the results of the LAST transform)
+        _ck(self._L.orbx_vocab_lock(self._h))
+        try:
+            _ck(self._L.orbx_bow_transform(self._h, buf.ctypes.data, counts.ctypes.data, frames, cap, levelsup))
+            return [self.get(i, int(counts[i])) for i in range(frames)]
+        finally:
+            self._L.orbx_vocab_unlock(self._h)
 
     def transform(self, desc, levelsup=4):
         """Frame::ComputeBoW: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)."""

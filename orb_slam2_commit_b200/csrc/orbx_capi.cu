@@ -37,6 +37,10 @@ struct orbx_extractor {
     cudaStream_t copy_stream = nullptr;          // host batch path: all uploads of a call, in order, ahead of the kernels
     struct Pending { int n = 0, cap = 0, nslots = 0; size_t fbytes = 0; const int* nkp = nullptr; const int* nkp2 = nullptr; cudaEvent_t done[MAX_SLOTS] = {}; };
     Pending pending[2]; int npending = 0;        // orbx_extract_batch_begin / _end: batches in flight, oldest first
+    // a stereo batch in flight is recorded on the LEFT handle but runs on the right handle's working set too: the right
+    // handle points at the left one while that is so, and every entry point on either handle completes the batch first
+    orbx_extractor* stereo_owner = nullptr;      // set on the right handle
+    orbx_extractor* stereo_partner = nullptr;    // set on the left handle
     std::vector<cudaEvent_t> in_ready, in_free;  // per input buffer: upload finished / kernels that read it finished
     // single-frame host calls are launch-bound (11 small kernels): after the first call with a given input form the
     // kernel sequence is replayed from a CUDA graph (one launch instead of eleven)
@@ -67,6 +71,7 @@ struct orbx_extractor {
 };
 
 static int round_half_even(float v) { return (int)lrintf(v); }   // cvRound
+static int finish_all_pending(orbx_extractor* h);                // batches begun with orbx_*_batch_begin (defined below)
 
 extern "C" const char* orbx_last_error(void) { return g_orbx_err.c_str(); }
 extern "C" int orbx_abi_version(void) { return ORBX_ABI_VERSION; }
@@ -140,7 +145,9 @@ static void release_device(orbx_extractor* h)
 extern "C" void orbx_destroy(orbx_extractor* h)
 {
     if (!h) return;
+    if (h->stereo_owner) { finish_all_pending(h); }
     if (h->npending > 0) { cudaSetDevice(h->device); cudaDeviceSynchronize(); h->npending = 0; }   // batches begun and never ended
+    if (h->stereo_partner) { h->stereo_partner->stereo_owner = nullptr; h->stereo_partner = nullptr; }
     release_device(h);
     cudaFree(h->d_remap);
     for (int r = 0; r < orbx_extractor::RING; r++)
@@ -282,6 +289,7 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
     if (width <= 0 || height <= 0 || max_batch <= 0) return fail(ORBX_ERR_INVALID, "width, height, max_batch must be positive");
     if (width == h->W && height == h->H && max_batch <= h->max_batch) return ORBX_OK;
+    { const int rc = finish_all_pending(h); if (rc != ORBX_OK) return rc; }   // also a stereo batch begun on the partner handle
     // geometry is pure host arithmetic: reject what the reference cannot run before touching the device
     {
         orbx_extractor probe = *h;          // tables only; device members of the copy are never used or freed
@@ -382,6 +390,10 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
 static int finish_oldest_pending(orbx_extractor* h);
 static int finish_all_pending(orbx_extractor* h)
 {
+    if (h && h->stereo_owner && h->stereo_owner != h) {          // right handle of a stereo batch in flight
+        const int rc = finish_all_pending(h->stereo_owner);
+        if (rc != ORBX_OK) return rc;
+    }
     while (h && h->npending > 0) { const int rc = finish_oldest_pending(h); if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc; }
     return ORBX_OK;
 }
@@ -467,6 +479,7 @@ static int finish_oldest_pending(orbx_extractor* h)
     for (int i = 0; i < pd.n; i++) if (pd.nkp[i] > pd.cap || (pd.nkp2 && pd.nkp2[i] > pd.cap)) status = ORBX_ERR_CAPACITY;
     std::swap(h->pending[0], h->pending[1]);                   // keeps both event sets alive
     h->npending--;
+    if (h->npending == 0 && h->stereo_partner) { h->stereo_partner->stereo_owner = nullptr; h->stereo_partner = nullptr; }
     if (status == ORBX_ERR_CAPACITY) return fail(status, "keypoint buffer too small (see nkp for the required size)");
     return status;
 }
@@ -481,6 +494,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
     const int gw = rectify ? h->map_w : width, gh = rectify ? h->map_h : height;
     if (channels != 1 && channels != 3 && channels != 4) return fail(ORBX_ERR_INVALID, "channels must be 1, 3 or 4 (Tracking.cc:174-199)");
     if (!keypoints || !nkp || !descriptors || cap < 0 || stride < width * channels) return fail(ORBX_ERR_INVALID, "bad output buffers");
+    if (h->stereo_owner) { const int rc = finish_all_pending(h); if (rc != ORBX_OK) return rc; }   // right handle of a stereo batch in flight
     if (gw != h->W || gh != h->H || h->max_batch < 1)
         while (h->npending > 0) { const int rc = finish_oldest_pending(h); if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc; }
     if (gw != h->W || gh != h->H || h->max_batch < 1) {
@@ -657,6 +671,7 @@ extern "C" int orbx_set_rectify_maps(orbx_extractor* h, const float* map1, const
 {
     if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
     if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible");
+    { const int rc = finish_all_pending(h); if (rc != ORBX_OK) return rc; }
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
     cudaFree(h->d_remap); h->d_remap = nullptr; h->map_w = h->map_h = h->map_src_w = h->map_src_h = 0;
@@ -679,6 +694,15 @@ extern "C" int orbx_set_rectify_maps(orbx_extractor* h, const float* map1, const
     CK(cudaMalloc(&h->d_remap, fx.size() * sizeof(uint2)));
     CK(cudaMemcpy(h->d_remap, fx.data(), fx.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     h->map_w = map_width; h->map_h = map_height; h->map_src_w = src_width; h->map_src_h = src_height;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_rectify_map_size(const orbx_extractor* h, int* map_width, int* map_height)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (!h->d_remap) return fail(ORBX_ERR_STATE, "orbx_set_rectify_maps has not been called");
+    if (map_width) *map_width = h->map_w;
+    if (map_height) *map_height = h->map_h;
     return ORBX_OK;
 }
 
@@ -949,6 +973,9 @@ static int stereo_extract_batch_impl(orbx_extractor* left, orbx_extractor* right
 {
     if (!left || !right || left == right) return fail(ORBX_ERR_INVALID, "two extractor instances required (Tracking.cc:120-123)");
     if (n <= 0 || !images_left || !images_right || width <= 0 || height <= 0) return ORBX_OK;
+    // the right handle may still serve another left handle's batch, or hold a mono batch of its own
+    if (right->stereo_owner && right->stereo_owner != left) { const int rc = finish_all_pending(right); if (rc != ORBX_OK) return rc; }
+    while (right->npending > 0) { const int rc = finish_oldest_pending(right); if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc; }
     // batches in flight live in `left`: a blocking call, another shape or a third batch first completes them
     while (left->npending > 0 && (!begin_only || left->npending >= 2 || left->pending[0].n != n || left->pending[0].cap != cap ||
                                   left->pending[0].fbytes != (size_t)width * height || width != left->W || height != left->H)) {
@@ -1051,6 +1078,7 @@ static int stereo_extract_batch_impl(orbx_extractor* left, orbx_extractor* right
             CK(cudaEventRecord(pd.done[j], left->slot_stream[j]));
         }
         left->npending++;
+        left->stereo_partner = right; right->stereo_owner = left;
         return ORBX_OK;
     }
     for (int j = 0; j < nslots; j++) CK(cudaStreamSynchronize(left->slot_stream[j]));
@@ -1361,7 +1389,13 @@ struct orbx_vocabulary {
     // match workspace
     void* d_mws = nullptr; size_t mws_pairs = 0, mws_cap = 0;
     int *d_bin_of = nullptr, *d_taken = nullptr, *d_hist = nullptr;
+    // The tree is immutable, but the workspace of the last transform (O, d_n, frames / cap) and the match workspace are
+    // per-handle mutable state, and ORB-SLAM2 shares ONE ORBVocabulary between Tracking, LocalMapping and LoopClosing:
+    // every entry point holds this (recursive) mutex, the host one-shot forms across their whole transform + match
+    // sequence, and orbx_vocab_lock / _unlock let a caller hold it across transform -> get (host/FrameOps.h).
+    std::recursive_mutex mu;
 };
+#define VLOCK(v) std::lock_guard<std::recursive_mutex> vlock_((v)->mu)
 
 extern "C" int orbx_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
                                  const uint8_t* is_leaf, const uint8_t* descriptors, const double* weights, int device,
@@ -1429,6 +1463,8 @@ extern "C" void orbx_vocab_destroy(orbx_vocabulary* v)
     cudaGetLastError();
     delete v;
 }
+extern "C" int orbx_vocab_lock(orbx_vocabulary* v) { if (!v) return fail(ORBX_ERR_INVALID, "vocabulary is NULL"); v->mu.lock(); return ORBX_OK; }
+extern "C" int orbx_vocab_unlock(orbx_vocabulary* v) { if (!v) return fail(ORBX_ERR_INVALID, "vocabulary is NULL"); v->mu.unlock(); return ORBX_OK; }
 extern "C" int orbx_vocab_words(const orbx_vocabulary* v) { return v ? v->words : 0; }
 extern "C" int orbx_vocab_nodes(const orbx_vocabulary* v) { return v ? v->nodes : 0; }
 
@@ -1453,6 +1489,7 @@ extern "C" int orbx_bow_transform_device(orbx_vocabulary* v, const uint8_t* d_de
                                          int cap, int levelsup, void* cuda_stream)
 {
     if (!v || !d_descriptors || !d_counts) return fail(ORBX_ERR_INVALID, "NULL argument");
+    VLOCK(v);
     if (frames <= 0 || cap <= 0) return fail(ORBX_ERR_INVALID, "bad sizes");
     if (cap > 16384) return fail(ORBX_ERR_UNSUPPORTED, "more than 16384 features per frame");
     CK(cudaSetDevice(v->device));
@@ -1467,7 +1504,9 @@ extern "C" int orbx_bow_transform_device(orbx_vocabulary* v, const uint8_t* d_de
 extern "C" int orbx_bow_get(orbx_vocabulary* v, int frame, int32_t* word, int32_t* node, int32_t* bow_id, double* bow_val,
                             int32_t* n_bow, int32_t* fv_node, int32_t* fv_off, int32_t* fv_feat, int32_t* n_fv)
 {
-    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (!v) return fail(ORBX_ERR_INVALID, "vocabulary is NULL");
+    VLOCK(v);
+    if (v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
     if (frame < 0 || frame >= v->frames) return fail(ORBX_ERR_INVALID, "frame out of range");
     CK(cudaSetDevice(v->device));
     CK(cudaDeviceSynchronize());
@@ -1499,6 +1538,7 @@ extern "C" int orbx_bow_transform(orbx_vocabulary* v, const uint8_t* descriptors
                                   int levelsup)
 {
     if (!v || !descriptors || !counts || frames <= 0 || cap <= 0) return fail(ORBX_ERR_INVALID, "bad argument");
+    VLOCK(v);
     CK(cudaSetDevice(v->device));
     CK(cudaDeviceSynchronize());
     cudaFree(v->d_n_own); v->d_n_own = nullptr;
@@ -1521,7 +1561,9 @@ extern "C" int orbx_bow_transform(orbx_vocabulary* v, const uint8_t* descriptors
 extern "C" int orbx_bow_score_device(orbx_vocabulary* v, const int32_t* d_frame_a, const int32_t* d_frame_b, int npairs,
                                      double* d_score, void* cuda_stream)
 {
-    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (!v) return fail(ORBX_ERR_INVALID, "vocabulary is NULL");
+    VLOCK(v);
+    if (v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
     if (npairs < 0 || (npairs > 0 && (!d_frame_a || !d_frame_b || !d_score))) return fail(ORBX_ERR_INVALID, "bad argument");
     if (v->scoring != 0) return fail(ORBX_ERR_UNSUPPORTED, "only L1_NORM scoring (ORBvoc's) is implemented");
     CK(cudaSetDevice(v->device));
@@ -1532,7 +1574,9 @@ extern "C" int orbx_bow_score_device(orbx_vocabulary* v, const int32_t* d_frame_
 
 extern "C" int orbx_bow_score(orbx_vocabulary* v, const int32_t* frame_a, const int32_t* frame_b, int npairs, double* score)
 {
-    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (!v) return fail(ORBX_ERR_INVALID, "vocabulary is NULL");
+    VLOCK(v);
+    if (v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
     if (npairs <= 0) return ORBX_OK;
     if (!frame_a || !frame_b || !score) return fail(ORBX_ERR_INVALID, "bad argument");
     for (int i = 0; i < npairs; i++)
@@ -1558,7 +1602,9 @@ static int search_by_bow_device_impl(orbx_vocabulary* v, int npairs, const int32
                                      const uint8_t* d_f_valid, int kf_mode, float nnratio, int check_orientation,
                                      int32_t* d_match, int32_t* d_nmatches, void* cuda_stream)
 {
-    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (!v) return fail(ORBX_ERR_INVALID, "vocabulary is NULL");
+    VLOCK(v);
+    if (v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
     if (npairs <= 0) return ORBX_OK;
     if (!d_kf_frame || !d_f_frame || !d_keypoints || !d_descriptors || !d_match || !d_nmatches) return fail(ORBX_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(v->device));
@@ -1606,6 +1652,7 @@ static int search_by_bow_host(orbx_vocabulary* v, const OrbxKeyPoint* kf_keypoin
 {
     const int n_out = kf_mode ? n_kf : n_f;
     if (!v || n_kf < 0 || n_f < 0 || !nmatches || (n_out > 0 && !match_f)) return fail(ORBX_ERR_INVALID, "bad argument");
+    VLOCK(v);                                    // transform + match are one critical section
     *nmatches = 0;
     for (int j = 0; j < n_out; j++) match_f[j] = -1;
     if (n_kf == 0 || n_f == 0) return ORBX_OK;
@@ -1784,7 +1831,9 @@ extern "C" int orbx_search_for_triangulation_device(orbx_vocabulary* v, int npai
                                                     const float* level_sigma2, int nlevels, int only_stereo, int check_orientation,
                                                     int32_t* d_match12, int32_t* d_nmatches, void* cuda_stream)
 {
-    if (!v || v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
+    if (!v) return fail(ORBX_ERR_INVALID, "vocabulary is NULL");
+    VLOCK(v);
+    if (v->frames <= 0) return fail(ORBX_ERR_STATE, "no transform has run yet");
     if (npairs <= 0) return ORBX_OK;
     if (!d_kf1_frame || !d_kf2_frame || !d_keypoints || !d_descriptors || !d_geom || !scale_factors || !level_sigma2 || !d_match12 ||
         !d_nmatches || nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "bad argument");
@@ -1815,6 +1864,7 @@ extern "C" int orbx_search_for_triangulation(orbx_vocabulary* v, const OrbxKeyPo
                                              int levelsup, int only_stereo, int check_orientation, int32_t* match12, int32_t* nmatches)
 {
     if (!v || n1 < 0 || n2 < 0 || !nmatches || (n1 > 0 && !match12) || !geom28) return fail(ORBX_ERR_INVALID, "bad argument");
+    VLOCK(v);                                    // transform + match are one critical section
     if ((u_right1 == nullptr) != (u_right2 == nullptr) || (has_mp1 == nullptr) != (has_mp2 == nullptr))
         return fail(ORBX_ERR_INVALID, "u_right / has_mp must be given for both keyframes or for neither");
     *nmatches = 0;

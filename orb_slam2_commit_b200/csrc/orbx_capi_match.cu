@@ -411,7 +411,9 @@ extern "C" int orbx_search_for_initialization_device(const OrbxInitPair* pairs, 
     for (int p = 0; p < npairs; p++) {
         const OrbxInitPair& q = pairs[p];
         if (q.n1 < 0 || q.n2 < 0 || !q.nmatches || (q.n1 > 0 && (!q.match12 || !q.prev_matched || !q.prev_matched_out))) return fail(ORBX_ERR_INVALID, "bad pair");
-        if (q.n2 > 10000) return fail(ORBX_ERR_UNSUPPORTED, "more than 10000 keypoints in F2");
+        // init_match_kernel keeps F2's grid CSR + vMatchedDistance / vnMatches21 in shared memory: 22 B per F2 keypoint + 12.5 KB,
+        // which passes the 227 KB opt-in limit just below 10000 keypoints
+        if (q.n2 > 9900) return fail(ORBX_ERR_UNSUPPORTED, "more than 9900 keypoints in F2");
         if ((q.n1 > 0 && (!q.keypoints1 || !q.descriptors1)) || (q.n2 > 0 && (!q.keypoints2 || !q.descriptors2))) return fail(ORBX_ERR_INVALID, "NULL array in pair");
         tot += (size_t)q.n1; max_n2 = std::max(max_n2, q.n2);
     }

@@ -171,7 +171,16 @@ __global__ void __launch_bounds__(1024) hamming_wait_merge_kernel(const unsigned
         if (status) *status = ok ? 0 : 1;
     }
     __syncthreads();
-    if (!s_ok) return;
+    if (!s_ok) {
+        // a peer never arrived: the landing buffer may be partly written, so report "no match" for every query instead of
+        // leaving the caller's buffers uninitialised; *status = 1 tells the host that this matcher must be recreated
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+            if (idx) idx[i] = -1;
+            if (d1) d1[i] = 256;
+            if (d2) d2[i] = 256;
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < nq; i += blockDim.x) {
         unsigned long long acc = ht_pack(256, 256, 0xffffffffu);
         for (int p = 0; p < world; p++) acc = ht_merge(acc, __ldcv(&parts[(size_t)p * nq_max + i]));

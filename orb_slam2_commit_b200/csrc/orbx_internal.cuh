@@ -86,8 +86,9 @@ static inline void orbx_need_smem(F kernel, OrbxSmemMark& mark, size_t bytes)
     cudaGetDevice(&dev);
     dev &= 63;
     if (bytes > mark.bytes[dev]) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        mark.bytes[dev] = bytes;
+        // on failure the mark stays where it was: the launch that follows fails with a launch error that the caller's
+        // cudaGetLastError() check turns into ORBX_ERR_CUDA, and the next call tries again
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess) mark.bytes[dev] = bytes;
     }
 }
 

@@ -67,6 +67,22 @@ def hamming_top2_sharded(d_query, d_train_shard, index_base: int, group=None):
     return out[0], out[1], out[2]
 
 
+def hamming_top2_single(d_query, d_train):
+    """The same search over a train set that lives on ONE GPU (orbx_hamming_top2_device + the merge kernel with a single
+    part): the result the sharded paths must reproduce bit for bit. Returns CUDA int32 tensors (idx1, dist1, dist2)."""
+    import torch
+    from . import api
+    L = api.lib()
+    nq, nt = d_query.shape[0], d_train.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    packed = torch.empty(nq, dtype=torch.int64, device=d_query.device)
+    api._ck(L.orbx_hamming_init_device(packed.data_ptr(), nq, st))
+    api._ck(L.orbx_hamming_top2_device(d_query.data_ptr(), nq, d_train.data_ptr() if nt else 0, nt, 0, packed.data_ptr(), st))
+    out = torch.empty((3, nq), dtype=torch.int32, device=d_query.device)
+    api._ck(L.orbx_hamming_merge_device(packed.data_ptr(), 1, nq, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), st))
+    return out[0], out[1], out[2]
+
+
 class PeerHammingMatcher:
     """Config 4 with the exchange fused into the matcher kernel (orbx_peer_* in include/orbx.h): the last CTA of every
     query tile stores the rank's top-2 into every peer's landing buffer over NVLink and bumps the peers' arrival
@@ -91,15 +107,29 @@ class PeerHammingMatcher:
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
         dist.barrier(group)                      # every rank has mapped every landing buffer before the first store
 
-    def __call__(self, d_query, d_train_shard, index_base: int):
+    def __call__(self, d_query, d_train_shard, index_base: int, check: bool = True):
+        """check=True reads the status word back (one 4-byte D2H, synchronises the stream) and raises when a peer did not
+        arrive within the kernel's bounded wait; the outputs then hold -1 / 256 ("no match") and the matcher is closed,
+        because its arrival counters are out of step with the peers' — build a new one behind a barrier. A caller that
+        pipelines calls passes check=False and calls raise_if_failed() once it synchronises anyway."""
         import torch
+        if self.h is None:
+            raise RuntimeError("PeerHammingMatcher is closed (a previous call timed out or close() was called)")
         nq, nt = d_query.shape[0], d_train_shard.shape[0]
         out = torch.empty((3, nq), dtype=torch.int32, device=d_query.device)
         st = torch.cuda.current_stream().cuda_stream
         self.api._ck(self.L.orbx_peer_hamming_top2(self.h, d_query.data_ptr(), nq, d_train_shard.data_ptr() if nt else 0, nt,
                                                    index_base, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                                    self.status.data_ptr(), st))
+        if check:
+            self.raise_if_failed()
         return out[0], out[1], out[2]
+
+    def raise_if_failed(self):
+        if self.h is not None and int(self.status.item()) != 0:
+            self.close()
+            raise RuntimeError("PeerHammingMatcher: a peer's top-2 did not arrive within the bounded wait; results are "
+                               "'no match' (-1 / 256) and the matcher was closed — recreate it on every rank behind a barrier")
 
     def close(self):
         if self.h:

@@ -5,6 +5,7 @@
 #ifndef ORB_SLAM2_FRAME_OPS_H
 #define ORB_SLAM2_FRAME_OPS_H
 
+#include <cstring>
 #include <map>
 #include <vector>
 #include <opencv2/core/core.hpp>
@@ -46,7 +47,10 @@ inline bool ExtractRectified(ORBextractor* extractor, const cv::Mat& imUnrectifi
 {
     orbx_extractor* h = extractor->Handle();
     if (imUnrectified.empty()) return true;
-    const int cap = [&] { orbx_reserve(h, imUnrectified.cols, imUnrectified.rows, 1); return orbx_max_keypoints(h); }();
+    // the pyramid (and with it the keypoint capacity) has the MAP's size, which may differ from the source frame's
+    int mw = 0, mh = 0;
+    if (orbx_rectify_map_size(h, &mw, &mh) != ORBX_OK || orbx_reserve(h, mw, mh, 1) != ORBX_OK) return false;
+    const int cap = orbx_max_keypoints(h);
     std::vector<OrbxKeyPoint> kp((size_t)cap);
     std::vector<unsigned char> desc((size_t)cap * 32);
     int n = 0;
@@ -71,6 +75,9 @@ inline bool ComputeBoWGPU(orbx_vocabulary* voc, const cv::Mat& mDescriptors, std
     std::vector<unsigned char> d((size_t)n * 32);
     for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], mDescriptors.ptr(i), 32);
     const int32_t counts[1] = {n};
+    // transform -> get is one critical section on the shared vocabulary handle (Tracking, LocalMapping and LoopClosing
+    // all call ComputeBoW on the same ORBVocabulary)
+    struct VocLock { orbx_vocabulary* v; explicit VocLock(orbx_vocabulary* v_) : v(v_) { orbx_vocab_lock(v); } ~VocLock() { orbx_vocab_unlock(v); } } lock(voc);
     if (orbx_bow_transform(voc, d.data(), counts, 1, n, levelsup) != ORBX_OK) return false;
     std::vector<int32_t> bow_id(n), fv_node(n), fv_off(n + 1), fv_feat(n);
     std::vector<double> bow_val(n);
