@@ -3,6 +3,7 @@
 // built with the reference's own float/double expressions (ORBextractor.cc:416-490, 829-879, 567-570, 1221-1225).
 // No OpenCV, no torch, no CPU fallback: without a CUDA device every compute entry point fails with ORBX_ERR_CUDA.
 #include "orbx_capi_common.cuh"
+#include "orbx_tma.cuh"
 
 #include <mutex>
 
@@ -21,6 +22,7 @@ struct orbx_extractor {
     std::vector<OrbxResizeTap> taps;
     int max_tile_w = 0, max_tile_h = 0;
     OrbxFrameLayout L{};
+    OrbxTmaps tm_fast{}, tm_desc{};               // per-level tensor maps of the raw pyramid (TMA staging of FAST tiles / describe patches)
     // device memory
     void* d_pool = nullptr;                       // one allocation carved into the arrays of L
     OrbxLevelGeom* d_lvl = nullptr;
@@ -69,6 +71,40 @@ struct orbx_extractor {
     cudaEvent_t ev[RING][5] = {};
     long long runs = 0;                          // pipeline runs recorded since timing was enabled
 };
+
+// ---- TMA descriptors (orbx_tma.cuh). cuTensorMapEncodeTiled is a driver-API symbol: fetched through the runtime so that
+// the library does not link libcuda and still loads on a machine without a driver (tests/test_abi.py).
+bool orbx_encode_level_maps(OrbxTmaps* out, const OrbxLevelGeom* lvl, int nlevels, uint8_t* raw, size_t frame_raw_bytes,
+                            int frames, int box_w, const int* box_h, const char** err)
+{
+    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            if (err) *err = "cuTensorMapEncodeTiled is not available from this driver";
+            return false;
+        }
+        encode = (encode_t)fn;
+    }
+    for (int l = 0; l < nlevels; l++) {
+        const OrbxLevelGeom& g = lvl[l];
+        // x = byte column of the level buffer, y = buffer row (apron included), z = frame of the working set
+        const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)(g.h + 2 * ORBX_EDGE), (cuuint64_t)frames};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)frame_raw_bytes};     // bytes, dims 1 and 2 (multiples of 16)
+        const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h[l], 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = encode(&out->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, raw + g.raw_off, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled rejected a pyramid level descriptor"; return false; }
+    }
+    return true;
+}
 
 static int round_half_even(float v) { return (int)lrintf(v); }   // cvRound
 static int finish_all_pending(orbx_extractor* h);                // batches begun with orbx_*_batch_begin (defined below)
@@ -249,6 +285,11 @@ static int build_geometry(orbx_extractor* h, int W, int H)
                 h->max_tile_h = std::max(h->max_tile_h, eh + 6);
                 h->cells.push_back(c);
             }
+        {
+            int bh = 8;
+            for (size_t ci = (size_t)g.cell0; ci < h->cells.size(); ci++) bh = std::max(bh, h->cells[ci].ey1 - h->cells[ci].ey0 + 6);
+            for (size_t ci = (size_t)g.cell0; ci < h->cells.size(); ci++) h->cells[ci].box_h = (short)bh;
+        }
         g.cand_cap = std::min(lvl_slots, (1 << 23) - 1);
         cand += g.cand_cap;
         g.kp_cap = std::max(g.quota + 3, 4 * g.nini) + 1;
@@ -330,6 +371,15 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     if (!h->taps.empty())
         CK(cudaMemcpy(h->d_taps, h->taps.data(), h->taps.size() * sizeof(OrbxResizeTap), cudaMemcpyHostToDevice));
     L.lvl = h->d_lvl; L.cells = h->d_cells; L.taps = h->d_taps;
+    {
+        int box_h[ORBX_MAX_LEVELS], box_d[ORBX_MAX_LEVELS];
+        for (int l = 0; l < h->nlevels; l++) { box_h[l] = h->cells[h->lvl[l].cell0].box_h; box_d[l] = 43; }
+        const char* why = nullptr;
+        if (!orbx_encode_level_maps(&h->tm_fast, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch,
+                                    orbx_fast_tile_pitch(h->max_tile_w), box_h, &why) ||
+            !orbx_encode_level_maps(&h->tm_desc, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch, 64, box_d, &why))
+            return fail(ORBX_ERR_CUDA, why ? why : "cuTensorMapEncodeTiled failed");
+    }
     // staging for the host entry points
     const size_t in_bytes = B * (size_t)width * height;
     CK(cudaMalloc(&h->d_in, in_bytes));
@@ -352,6 +402,7 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
                         int channels = 1, int rgb = 0, bool rectify = false)
 {
     OrbxFrameLayout Lb = h->L;
+    Lb.frame0 = base;
     if (base) {
         Lb.raw += (size_t)base * Lb.frame_raw_bytes;
         Lb.slots += (size_t)base * Lb.slot_total;
@@ -368,7 +419,7 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     orbx_launch_pyramid(Lb, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st, channels, rgb,
                         rectify ? h->d_remap : nullptr, h->map_src_w, h->map_src_h);
     if (tm) cudaEventRecord(ev[1], st);
-    orbx_launch_fast(Lb, h->max_tile_w, h->max_tile_h, n, st);
+    orbx_launch_fast(Lb, h->tm_fast, h->max_tile_w, h->max_tile_h, n, st);
     if (tm) cudaEventRecord(ev[2], st);
     // small frames: 256-thread CTAs so that several (level, frame) trees share an SM and hide each other's barriers
     // ... unless there are so few trees that every one gets an SM to itself anyway (single frames): then the wide CTA
@@ -376,7 +427,7 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     const bool few = n * h->nlevels <= 148;
     orbx_launch_quadtree(Lb, n, ((size_t)h->W * h->H <= (size_t)1 << 20 && !few) ? 256 : 1024, st);
     if (tm) cudaEventRecord(ev[3], st);
-    orbx_launch_describe(Lb, n, d_kps, d_desc, cap, d_nkp, st);
+    orbx_launch_describe(Lb, h->tm_desc, n, d_kps, d_desc, cap, d_nkp, st);
     if (tm) cudaEventRecord(ev[4], st);
     if (tm) h->runs++;
     CK(cudaGetLastError());

@@ -2,7 +2,8 @@
 // computeOrientation/IC_Angle ORBextractor.cc:77-105,492-499, the per-level cv::GaussianBlur :1188-1190 and
 // computeOrbDescriptor :110-152, plus the coordinate scaling / output packing of operator() :1194-1209).
 //
-// The warp stages the 43x43 raw patch around the keypoint in shared memory (aligned 32-bit loads), then
+// One elected lane has the TMA unit copy the 64x43-byte box around the keypoint from the HBM pyramid into the warp's
+// shared-memory slot (cp.async.bulk.tensor through the level's tensor map, completion on the warp's mbarrier); then
 //   * IC_Angle: lane = column u in [-15,15], integer moments, warp-shuffle reduce, cv::fastAtan2 polynomial
 //     evaluated with un-contracted f32 mul/add (bit-equal to OpenCV's scalar path);
 //   * blur on demand: the reference blurs the whole level and then reads 512 points per keypoint; here the
@@ -15,10 +16,14 @@
 //     (bit-equal to the host libm the oracle was pinned against, tests/golden/sincos.json).
 // No blurred pyramid is ever written to HBM.
 #include "orbx_internal.cuh"
+#include "orbx_tma.cuh"
 
-#define DESC_WARPS 4         // 128-thread CTAs: 9 fit by registers (54 per thread) = 36 resident warps; 8-warp CTAs only reach 32
+#ifndef DESC_WARPS
+#define DESC_WARPS 4         // warps (= keypoints) per CTA
+#endif
 #define PW 43            // patch width/height
-#define PWORDS 12        // 32-bit words per staged patch row (48 bytes)
+#define PWORDS 12        // 32-bit words of a staged patch row that the kernel works on (48 bytes: 43 + up to 3 of alignment)
+#define RPW 16           // pitch of the staged rows in words: the 64-byte TMA box (its origin must be 16-byte aligned)
 #define VROWS 37         // rows of the vertically blurred patch (patch rows 3..39 centred)
 #define VPW 24           // its pitch in 32-bit words: 48 u16 per row, one per byte of the staged 48-byte patch row
 
@@ -106,12 +111,14 @@ __device__ __forceinline__ void dev_sincosf(const float y, float* sn, float* cs)
     *sn = __double2float_rn((n & 1) ? pc : ps);
 }
 
-__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayout L, OrbxKp28* __restrict__ kps,
-                                                                    uint8_t* __restrict__ desc, int cap,
+#define RAW_SLOT_WORDS 704   // 64 x 43 bytes = 688 words, padded to a multiple of 128 bytes (TMA destination alignment)
+__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayout L, const __grid_constant__ OrbxTmaps maps,
+                                                                    OrbxKp28* __restrict__ kps, uint8_t* __restrict__ desc, int cap,
                                                                     int* __restrict__ nkp)
 {
-    __shared__ __align__(16) uint32_t s_raw[DESC_WARPS][PW * PWORDS + 4];   // +4: the last row's aligned windows over-read by up to two words
+    __shared__ __align__(128) uint32_t s_raw[DESC_WARPS][RAW_SLOT_WORDS];
     __shared__ __align__(16) uint32_t s_vb[DESC_WARPS][VROWS * VPW];
+    __shared__ __align__(8) unsigned long long s_bar[DESC_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // this lane's 16 sample points (32 int8 = two 128-bit words), fetched first so the latency hides behind staging;
     // no block-level barrier anywhere in this kernel
@@ -132,34 +139,23 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     const uint32_t pk = L.lvl_kp[(size_t)frame * L.kp_cap_total + L.lvl_kp_off[level] + k];
     const int kx = pk & 0xfff, ky = (pk >> 12) & 0xfff, score = pk >> 24;
 
-    // ---- stage the 43x43 raw patch (rows ky-21.., columns kx-21..) with aligned 32-bit loads
-    const uint8_t* p0 = L.raw + (size_t)frame * L.frame_raw_bytes + g.raw_off +
-                        (size_t)(ky - 21 + ORBX_EDGE) * g.pitch + (kx - 21 + ORBX_XOFF);
-    const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3);
-    const uint8_t* pa = p0 - sh;
-    uint32_t* raw32 = s_raw[wid];
+    // ---- stage the raw patch: rows ky-21 .. ky+21 of the 64-byte box that starts at the 16-byte aligned column at or left
+    // of kx-21; the kernel then works on the 48-byte window that starts at the WORD holding column kx-21 (byte `sh` of it)
+    uint32_t* slot32 = s_raw[wid];
+    const int x0 = kx - 21 + ORBX_XOFF;
     {
-        // 516 words, 32 per step; loads are issued in batches so that several are in flight per lane
-        const uint32_t* pa32 = reinterpret_cast<const uint32_t*>(pa);
-        const int pitch_w = g.pitch >> 2;
-#pragma unroll
-        for (int b0 = 0; b0 < PW * PWORDS; b0 += 32 * 6) {
-            uint32_t v[6];
-#pragma unroll
-            for (int u = 0; u < 6; u++) {
-                const int i = b0 + 32 * u + lane;
-                const int r = i / PWORDS, c = i - r * PWORDS;
-                v[u] = i < PW * PWORDS ? __ldg(pa32 + r * pitch_w + c) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 6; u++) {
-                const int i = b0 + 32 * u + lane;
-                if (i < PW * PWORDS) raw32[i] = v[u];
-            }
+        const uint32_t bar = orbx_smem_addr(&s_bar[wid]);
+        if (lane == 0) {
+            orbx_mbar_init(bar, 1);
+            orbx_mbar_expect_tx(bar, PW * RPW * 4);
+            orbx_tma_load_3d(orbx_smem_addr(slot32), &maps.m[level], x0 & ~15, ky - 21 + ORBX_EDGE, L.frame0 + frame, bar);
         }
+        __syncwarp();                                    // the barrier is initialised before anyone waits on it
+        orbx_mbar_wait(bar, 0);
     }
-    __syncwarp();
-    const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32) + sh;   // raw8[r*48 + c], c in [0,43)
+    const uint32_t* raw32 = slot32 + ((x0 & 15) >> 2);   // row r of the window = raw32 + r * RPW, 12 words
+    const int sh = x0 & 3;
+    const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32) + sh;   // raw8[r*64 + c], c in [0,43)
 
     // ---- IC_Angle on the un-blurred level
     int m10 = 0, m01 = 0;
@@ -168,12 +164,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
         constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         const int u = lane - 15;
         const int au = u < 0 ? -u : u;
-        const uint8_t* ctr = raw8 + 21 * (PWORDS * 4) + 21 + u;
+        const uint8_t* ctr = raw8 + 21 * (RPW * 4) + 21 + u;
         m10 = u * ctr[0];
 #pragma unroll
         for (int v = 1; v <= 15; v++) {
             if (au <= UMAX[v]) {
-                const int vp = ctr[v * (PWORDS * 4)], vm = ctr[-v * (PWORDS * 4)];
+                const int vp = ctr[v * (RPW * 4)], vm = ctr[-v * (RPW * 4)];
                 m10 += u * (vp + vm);
                 m01 += v * (vp - vm);
             }
@@ -197,17 +193,18 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     if (lane < 30) {
         const int col = lane % 6, strip = lane / 6;
         const int ro0 = min(strip * 8, VROWS - 8);               // strips 0,8,16,24,29 (the last two overlap)
-        const uint2* src = reinterpret_cast<const uint2*>(raw32 + ro0 * PWORDS) + col;
+        // (the window starts at a word, not at an 8-byte boundary of the box: two 32-bit loads per row)
+        const uint32_t* src = raw32 + ro0 * RPW + 2 * col;
         uint32_t E[7][4];
-        auto expand = [&](uint32_t (&e)[4], const uint2 w) {
-            e[0] = __byte_perm(w.x, 0, 0x4140); e[1] = __byte_perm(w.x, 0, 0x4342);
-            e[2] = __byte_perm(w.y, 0, 0x4140); e[3] = __byte_perm(w.y, 0, 0x4342);
+        auto expand = [&](uint32_t (&e)[4], const uint32_t wx, const uint32_t wy) {
+            e[0] = __byte_perm(wx, 0, 0x4140); e[1] = __byte_perm(wx, 0, 0x4342);
+            e[2] = __byte_perm(wy, 0, 0x4140); e[3] = __byte_perm(wy, 0, 0x4342);
         };
 #pragma unroll
-        for (int i = 0; i < 6; i++) expand(E[i], src[i * (PWORDS / 2)]);
+        for (int i = 0; i < 6; i++) expand(E[i], src[i * RPW], src[i * RPW + 1]);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            expand(E[(j + 6) % 7], src[(j + 6) * (PWORDS / 2)]);
+            expand(E[(j + 6) % 7], src[(j + 6) * RPW], src[(j + 6) * RPW + 1]);
             uint32_t o[4];
 #pragma unroll
             for (int q = 0; q < 4; q++)
@@ -261,10 +258,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     }
 }
 
-void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp,
-                          cudaStream_t st)
+void orbx_launch_describe(const OrbxFrameLayout& L, const OrbxTmaps& maps, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
+                          int* d_nkp, cudaStream_t st)
 {
     int total_cap = L.kp_cap_total;
     dim3 grid((total_cap + DESC_WARPS - 1) / DESC_WARPS, nframes);
-    describe_kernel<<<grid, DESC_WARPS * 32, 0, st>>>(L, d_kps, d_desc, cap, d_nkp);
+    describe_kernel<<<grid, DESC_WARPS * 32, 0, st>>>(L, maps, d_kps, d_desc, cap, d_nkp);
 }

@@ -44,7 +44,7 @@ struct OrbxLevelGeom {
 struct OrbxCell {             // one FAST cell (ORBextractor.cc:849-914); emission rectangle in payload coords
     short level;
     short ex0, ey0, ex1, ey1; // pixels that can be emitted: [ex0,ex1) x [ey0,ey1)
-    short pad;
+    short box_h;              // rows of the level's TMA box (tallest cell tile of the level = eh + 6)
     int slot_off;             // offset into the frame's slot array
     int slot_cap;
 };
@@ -56,6 +56,7 @@ struct OrbxResizeTap {        // cv::resize INTER_LINEAR 8U coefficients for one
 struct OrbxFrameLayout {      // everything the kernels need, passed by value
     int nlevels, ncells, slot_total, cand_total, kp_cap_total;
     int ini_th, min_th;
+    int frame0;                     // working-set index of frame 0 of this launch (z coordinate of the tensor maps; `raw` etc. are already offset)
     size_t frame_raw_bytes;
     const OrbxLevelGeom* lvl;       // device
     const OrbxCell* cells;          // device
@@ -96,9 +97,11 @@ static inline void orbx_need_smem(F kernel, OrbxSmemMark& mark, size_t bytes)
 void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
                          int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels = 1, int rgb = 0,
                          const uint2* d_remap = nullptr, int src_w = 0, int src_h = 0);
-void orbx_launch_fast(const OrbxFrameLayout& L, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
+struct OrbxTmaps;               // orbx_tma.cuh: one tensor map per pyramid level
+void orbx_launch_fast(const OrbxFrameLayout& L, const OrbxTmaps& maps, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
+int orbx_fast_tile_pitch(int max_tile_w);
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);
-void orbx_launch_describe(const OrbxFrameLayout& L, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
+void orbx_launch_describe(const OrbxFrameLayout& L, const OrbxTmaps& maps, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
                           int* d_nkp, cudaStream_t st);
 void orbx_upload_constants();  // pattern + umax tables
 
