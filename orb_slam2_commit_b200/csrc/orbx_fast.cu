@@ -82,23 +82,25 @@ __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ c, con
 }
 
 // Quick test of one pixel: both compares of a ring pixel r ride in one multiply-add,
-//   X = r * 0xFFFF0001 + C,  C = v * 0xFFFF + KT,  KT = (T + 0x8000) << 16 | (0x8000 + T)
-// leaves r - (v - T) + 0x8000 in the low half and (v + T) - r + 0x8000 in the high half (neither half can carry into
-// the other), so bit 15 is CLEAR iff r is dark and bit 31 is CLEAR iff r is bright. With Y = (X4 & X12) | (X0 & X8),
-// bit 15 of Y is clear iff (D4|D12)&(D0|D8) == (D0&D4)|(D4&D8)|(D8&D12)|(D12&D0): two ADJACENT compass pixels (ring 0, 4,
-// 8, 12) are darker than v - T — every arc of 9 contiguous ring pixels holds such a pair; bit 31 likewise for bright.
-// Returns ~Y: bit 15 SET <=> a dark arc is possible at T, bit 31 SET <=> a bright arc is possible at T.
-template <int TP>
-__device__ __forceinline__ unsigned quick_test(const uint8_t* __restrict__ qp, const unsigned KT)
+//   X = r * 0xFFFF0001 + C,  C = v * 0xFFFF + KT,  KT = (T + 0x4000) << 16 | (0x4000 + T)
+// leaves r - (v - T) + 0x4000 in the low half and (v + T) - r + 0x4000 in the high half (neither half can carry into
+// the other), so bit 14 is CLEAR iff r is dark and bit 30 is CLEAR iff r is bright. With Y = (X4 & X12) | (X0 & X8),
+// bit 14 of Y is clear iff (D4|D12)&(D0|D8) == (D0&D4)|(D4&D8)|(D8&D12)|(D12&D0): two ADJACENT compass pixels (ring 0, 4,
+// 8, 12) are darker than v - T — every arc of 9 contiguous ring pixels holds such a pair; bit 30 likewise for bright.
+// Returns ~Y: bit 14 SET <=> a dark arc is possible at T, bit 30 SET <=> a bright arc is possible at T.
+// (v, up, down) are the lane's own column at rows y, y-3, y+3 and come from the caller's register window.
+__device__ __forceinline__ unsigned quick_test(const unsigned v, const unsigned up, const unsigned down, const unsigned left,
+                                               const unsigned right, const unsigned KT)
 {
-    const unsigned C = (unsigned)qp[0] * 0xFFFFu + KT;
-    const unsigned X0 = (unsigned)qp[3 * TP] * 0xFFFF0001u + C, X4 = (unsigned)qp[3] * 0xFFFF0001u + C;
-    const unsigned X8 = (unsigned)qp[-3 * TP] * 0xFFFF0001u + C, X12 = (unsigned)qp[-3] * 0xFFFF0001u + C;
+    const unsigned C = v * 0xFFFFu + KT;
+    const unsigned X0 = down * 0xFFFF0001u + C, X4 = right * 0xFFFF0001u + C;
+    const unsigned X8 = up * 0xFFFF0001u + C, X12 = left * 0xFFFF0001u + C;
     return ~((X4 & X12) | (X0 & X8));
 }
 
-#define FAST_DARK 0x8000u      // list entry flags (bits 15 / 14); bits 0..13 = py * TP + px
-#define FAST_BRIGHT 0x4000u
+#define FAST_DARK 0x4000u      // list entry flags (bits 14 / 15); bits 0..13 = py * TP + px
+#define FAST_BRIGHT 0x8000u
+#define FAST_QMASK 0x40004000u // the two result bits of quick_test()
 
 // TP: tile pitch = TMA box width in bytes (64 or 80). The TMA unit wants the box to start at a 16-byte aligned byte
 // column of the level buffer (measured: any other origin raises an illegal-instruction fault, tools/probe/), so the box
@@ -149,34 +151,49 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
     int total = 0;
     for (int pass = 0; pass < 2; pass++) {
         const int T = pass ? L.min_th : L.ini_th;
-        // 1. quick test on every pixel, lane = column: the 32 lanes read 32 consecutive bytes of a tile row per load.
-        //    Row-major list entry = py * TP + px | polarity flags.
+        // 1. quick test on every pixel, lane = column: the 32 lanes read 32 consecutive bytes of a tile row per load, and
+        //    a lane keeps its own column in a six-row register window (row y+3 is loaded once and serves as "down", three
+        //    rows later as centre, six rows later as "up"). Row-major list entry = py * TP + px | polarity flags; lanes
+        //    that do not pass store to a dummy slot behind the list, so the append is branch-free.
         int cnt = 0;
         {
-            const unsigned KT = ((unsigned)(T + 0x8000) << 16) + (unsigned)(0x8000 + T);
-            const bool in0 = lane < ew;
-            const uint8_t* q0 = tile + 3 * TP + 3 + min(lane, ew - 1);      // clamped: loads stay inside the tile
+            const unsigned KT = ((unsigned)(T + 0x4000) << 16) + (unsigned)(0x4000 + T);
+            unsigned short* const dummy = list + cfg.list_cap;
             if (ew <= 32) {
-#pragma unroll 4
+                const unsigned lanemask = lane < ew ? FAST_QMASK : 0u;
+                const uint8_t* q = tile + 3 + min(lane, ew - 1);           // clamped: loads stay inside the tile; q[ty * TP] = own column
+                unsigned w0 = q[0], w1 = q[TP], w2 = q[2 * TP], w3 = q[3 * TP], w4 = q[4 * TP], w5 = q[5 * TP];   // tile rows py .. py+5
+                q += 3 * TP;                                                // q[0] = centre pixel of row py
+                int e = lane;
+#pragma unroll 6
                 for (int py = 0; py < eh; py++) {
-                    const unsigned nY = quick_test<TP>(q0 + py * TP, KT);
-                    const bool p = in0 && (nY & 0x80008000u);
-                    const unsigned m = __ballot_sync(0xffffffffu, p);
-                    if (p) list[cnt + __popc(m & lt_mask)] = (unsigned short)((py * TP + lane) | (nY & FAST_DARK) | ((nY >> 17) & FAST_BRIGHT));
+                    const unsigned w6 = q[3 * TP];
+                    const unsigned nY = quick_test(w3, w0, w6, q[-3], q[3], KT) & lanemask;
+                    const unsigned m = __ballot_sync(0xffffffffu, nY != 0);
+                    const unsigned val = (unsigned)e + ((nY | (nY >> 15)) & (FAST_DARK | FAST_BRIGHT));
+                    unsigned short* dst = list + cnt + __popc(m & lt_mask);
+                    *(nY ? dst : dummy) = (unsigned short)val;
                     cnt += __popc(m);
+                    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+                    q += TP; e += TP;
                 }
-            } else {                                                       // cells wider than 32 px (< 64): two column chunks per row
-                const bool in1 = lane + 32 < ew;
+            } else {                                                        // cells wider than 32 px (< 64): two column chunks per row
+                const unsigned lanemask1 = lane + 32 < ew ? FAST_QMASK : 0u;
+                const uint8_t* q0 = tile + 3 * TP + 3 + lane;
                 const uint8_t* q1 = tile + 3 * TP + 3 + min(lane + 32, ew - 1);
+                int e = lane;
 #pragma unroll 2
                 for (int py = 0; py < eh; py++) {
-                    const unsigned nY0 = quick_test<TP>(q0 + py * TP, KT), nY1 = quick_test<TP>(q1 + py * TP, KT);
-                    const bool p0 = nY0 & 0x80008000u, p1 = in1 && (nY1 & 0x80008000u);
-                    const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
-                    if (p0) list[cnt + __popc(m0 & lt_mask)] = (unsigned short)((py * TP + lane) | (nY0 & FAST_DARK) | ((nY0 >> 17) & FAST_BRIGHT));
+                    const unsigned nY0 = quick_test(q0[0], q0[-3 * TP], q0[3 * TP], q0[-3], q0[3], KT) & FAST_QMASK;
+                    const unsigned nY1 = quick_test(q1[0], q1[-3 * TP], q1[3 * TP], q1[-3], q1[3], KT) & lanemask1;
+                    const unsigned m0 = __ballot_sync(0xffffffffu, nY0 != 0), m1 = __ballot_sync(0xffffffffu, nY1 != 0);
+                    unsigned short* d0 = list + cnt + __popc(m0 & lt_mask);
+                    *(nY0 ? d0 : dummy) = (unsigned short)((unsigned)e + ((nY0 | (nY0 >> 15)) & (FAST_DARK | FAST_BRIGHT)));
                     cnt += __popc(m0);
-                    if (p1) list[cnt + __popc(m1 & lt_mask)] = (unsigned short)((py * TP + lane + 32) | (nY1 & FAST_DARK) | ((nY1 >> 17) & FAST_BRIGHT));
+                    unsigned short* d1 = list + cnt + __popc(m1 & lt_mask);
+                    *(nY1 ? d1 : dummy) = (unsigned short)((unsigned)(e + 32) + ((nY1 | (nY1 >> 15)) & (FAST_DARK | FAST_BRIGHT)));
                     cnt += __popc(m1);
+                    q0 += TP; q1 += TP; e += TP;
                 }
             }
         }
@@ -197,10 +214,9 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
             const bool is_corner = k < cnt && s >= T;
             const unsigned m = __ballot_sync(0xffffffffu, is_corner);
             __syncwarp();
-            if (is_corner) {
-                list[ncorner + __popc(m & lt_mask)] = (unsigned short)e;
-                score[e - (e / TP) * (TP - SP) + (SP + 1)] = (uint8_t)s;    // (py, px) -> py * SP + px
-            }
+            // branch-free: lanes without a corner write the dummy list slot / the spare byte behind the score map
+            *(is_corner ? list + ncorner + __popc(m & lt_mask) : list + cfg.list_cap) = (unsigned short)e;
+            score[is_corner ? e - (e / TP) * (TP - SP) + (SP + 1) : cfg.score_bytes - 1] = (uint8_t)s;    // (py, px) -> py * SP + px
             ncorner += __popc(m);
         }
         __syncwarp();
@@ -244,9 +260,9 @@ void orbx_launch_fast(const OrbxFrameLayout& L, const OrbxTmaps& maps, int max_t
     const int variant = TP == 80 ? 3 : SP == 40 ? 0 : SP == 48 ? 1 : 2;
     cfg.list_cap = ew * eh;
     cfg.score_off = (TP * max_tile_h + 127) & ~127;                         // tile: TP x (tallest box), 128-byte aligned for the TMA unit
-    cfg.score_bytes = (SP * (eh + 2) + 16 + 15) & ~15;                      // (eh + 2) rows + the (SP + 1) origin shift
+    cfg.score_bytes = (SP * (eh + 2) + 16 + 15) & ~15;                      // (eh + 2) rows + the (SP + 1) origin shift + a spare byte
     cfg.list_off = cfg.score_off + cfg.score_bytes;
-    cfg.bar_off = (cfg.list_off + 2 * cfg.list_cap + 15) & ~15;
+    cfg.bar_off = (cfg.list_off + 2 * (cfg.list_cap + 1) + 15) & ~15;    // + the dummy slot of the branch-free appends
     cfg.per_warp = (cfg.bar_off + 16 + 127) & ~127;
     typedef void (*kern_t)(OrbxFrameLayout, FastSmemCfg, const OrbxTmaps);
     static const kern_t kerns[4] = {fast_cells_kernel<64, 40>, fast_cells_kernel<64, 48>, fast_cells_kernel<64, 64>, fast_cells_kernel<80, 80>};

@@ -35,17 +35,21 @@ __device__ __forceinline__ void orbx_mbar_expect_tx(uint32_t bar, uint32_t bytes
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Waits for the phase with the given parity. try_wait suspends the thread for a hardware-defined time slice per call; a
+// copy that never completes (a broken descriptor, a lost arm) ends in a trap after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void orbx_mbar_wait(uint32_t bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "ORBX_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra ORBX_DONE_%=;\n"
-        "bra ORBX_WAIT_%=;\n"
-        "ORBX_DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+    for (int spins = 0;; spins++) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1 << 22)) __trap();                 // every try_wait sleeps for a time slice: seconds, not a busy loop
+    }
 }
 // box origin (x, y, z) in elements of the map's three dimensions
 __device__ __forceinline__ void orbx_tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar)
