@@ -140,6 +140,17 @@ int orbx_get_stage_ms(orbx_extractor* h, float* ms4, int* nruns);
  * backing `temp` buffer (ORBextractor.cc:1225-1229); the payload starts at dst + 19*dst_stride + 19. */
 int orbx_level_size(const orbx_extractor* h, int level, int* width, int* height);
 int orbx_pyramid_level(orbx_extractor* h, int frame, int level, uint8_t* dst, int dst_stride);
+/* The whole pyramid of one frame in ONE copy: the frame's raw block (all levels, each (h+38) rows of `pitch` bytes with
+ * the apron physically around the payload) lands in a pinned host mirror owned by the handle; level `level`'s payload
+ * pixel (0,0) sits at host_block + payload_offset and rows are `pitch` bytes apart, so
+ *   cv::Mat(h, w, CV_8UC1, (void*)(host_block + payload_offset), pitch)
+ * IS the reference's mvImagePyramid[level] (a view at (19,19) of `temp`, ORBextractor.cc:1225-1229): the pointer
+ * arithmetic of Frame.cc:681-700 finds the 19-px apron on every side. After orbx_set_pyramid_mirror(h, 1) a single-frame
+ * orbx_extract downloads the block itself, asynchronously in the stream of its kernels (no extra synchronisation);
+ * orbx_pyramid_mirror then just returns the pointer. The mirror stays valid until the next call on the handle. */
+int orbx_set_pyramid_mirror(orbx_extractor* h, int on);
+int orbx_pyramid_level_layout(const orbx_extractor* h, int level, size_t* payload_offset, int* pitch, size_t* block_bytes);
+int orbx_pyramid_mirror(orbx_extractor* h, int frame, const uint8_t** host_block);
 /* Device view of the same level: payload origin, pitch in bytes (apron lies around it in HBM). */
 int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level, const uint8_t** d_payload, int* pitch);
 

@@ -55,6 +55,9 @@ struct orbx_extractor {
     void* stereo_scratch = nullptr; size_t stereo_scratch_bytes = 0;   // SAD per left keypoint (stereo matcher)
     float* stereo_out = nullptr; size_t stereo_out_floats = 0;         // [2][B][kc] mvuRight / mvDepth staging (batched host path)
     int last_frames = 0;                          // frames of the last extract (for the pyramid accessors)
+    // host mirror of ONE frame's raw pyramid block (pinned): what the C++ shim's mvImagePyramid views. With mirror_on a
+    // single-frame host call downloads the block in the same stream as its kernels (one asynchronous copy, no extra sync)
+    uint8_t* mirror = nullptr; size_t mirror_bytes = 0; bool mirror_on = false; int mirror_frame = -1;
     int map_chunk = 0, map_slots = 1;             // host batch path: frame f sits at ((f/chunk) % slots)*chunk + f%chunk
     // working-set index of frame `frame` of the last call, or -1 when a later chunk has reused its slot
     int ws_index(int frame) const
@@ -169,6 +172,7 @@ static void release_device(orbx_extractor* h)
     if (h->g1) { cudaGraphExecDestroy(h->g1); h->g1 = nullptr; }
     h->g1_seen = 0;
     cudaFree(h->d_pool); h->d_pool = nullptr;
+    if (h->mirror) { cudaFreeHost(h->mirror); h->mirror = nullptr; h->mirror_bytes = 0; } h->mirror_frame = -1;
     cudaFree(h->stereo_scratch); h->stereo_scratch = nullptr; h->stereo_scratch_bytes = 0;
     cudaFree(h->stereo_out); h->stereo_out = nullptr; h->stereo_out_floats = 0;
     cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps);
@@ -653,6 +657,12 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
             if (single) h->g1_seen++;
         }
         if (rc != ORBX_OK) return rc;
+        h->mirror_frame = -1;
+        if (n == 1 && h->mirror_on) {
+            if (!h->mirror) { CK(cudaMallocHost(&h->mirror, h->L.frame_raw_bytes)); h->mirror_bytes = h->L.frame_raw_bytes; }
+            CK(cudaMemcpyAsync(h->mirror, h->L.raw + (size_t)base * h->L.frame_raw_bytes, h->L.frame_raw_bytes, cudaMemcpyDeviceToHost, st));
+            h->mirror_frame = 0;
+        }
         if (ahead) CK(cudaEventRecord(h->in_free[in_slot], st));
         CK(cudaMemcpyAsync(nkp + f0, d_nkp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (cap == kc) {
@@ -793,6 +803,45 @@ extern "C" int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level
     const OrbxLevelGeom& g = h->lvl[level];
     if (d_payload) *d_payload = h->L.raw + (size_t)wsi * h->L.frame_raw_bytes + g.raw_off + (size_t)ORBX_EDGE * g.pitch + ORBX_XOFF;
     if (pitch) *pitch = g.pitch;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_set_pyramid_mirror(orbx_extractor* h, int on)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    h->mirror_on = on != 0;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_pyramid_level_layout(const orbx_extractor* h, int level, size_t* payload_offset, int* pitch, size_t* block_bytes)
+{
+    if (!h || !h->W) return fail(ORBX_ERR_STATE, "no geometry reserved yet");
+    if (level < 0 || level >= h->nlevels) return fail(ORBX_ERR_INVALID, "level out of range");
+    const OrbxLevelGeom& g = h->lvl[level];
+    if (payload_offset) *payload_offset = (size_t)g.raw_off + (size_t)ORBX_EDGE * g.pitch + ORBX_XOFF;
+    if (pitch) *pitch = g.pitch;
+    if (block_bytes) *block_bytes = h->L.frame_raw_bytes;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_pyramid_mirror(orbx_extractor* h, int frame, const uint8_t** host_block)
+{
+    if (!h || !host_block) return fail(ORBX_ERR_INVALID, "NULL argument");
+    *host_block = nullptr;
+    int rc = finish_all_pending(h);
+    if (rc != ORBX_OK) return rc;
+    if (!h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");
+    if (frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame out of range");
+    if (h->mirror && h->mirror_frame == frame) { *host_block = h->mirror; return ORBX_OK; }   // downloaded by the extract call itself
+    const int wsi = h->ws_index(frame);
+    if (wsi < 0) return fail(ORBX_ERR_STATE, "the pyramid of this frame has been overwritten by a later chunk of the same call");
+    CK(cudaSetDevice(h->device));
+    if (!h->mirror) { CK(cudaMallocHost(&h->mirror, h->L.frame_raw_bytes)); h->mirror_bytes = h->L.frame_raw_bytes; }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(h->mirror, h->L.raw + (size_t)wsi * h->L.frame_raw_bytes, h->L.frame_raw_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->mirror_frame = frame;
+    *host_block = h->mirror;
     return ORBX_OK;
 }
 

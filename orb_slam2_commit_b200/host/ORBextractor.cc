@@ -29,7 +29,6 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     if (orbx_get_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
                         mvInvLevelSigma2.data(), mnFeaturesPerLevel.data(), 0) != ORBX_OK) die("orbx_get_tables");
     mvImagePyramid.resize(nlevels);
-    mvWhole.resize(nlevels);
 }
 
 ORBextractor::~ORBextractor() { orbx_destroy(mpHandle); }
@@ -44,6 +43,7 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray /*_mask*/, 
     assert(image.type() == CV_8UC1 );
 
     if (orbx_reserve(mpHandle, image.cols, image.rows, 1) != ORBX_OK) die("orbx_reserve");
+    if (orbx_set_pyramid_mirror(mpHandle, mbDownloadPyramid ? 1 : 0) != ORBX_OK) die("orbx_set_pyramid_mirror");
     const int cap = orbx_max_keypoints(mpHandle);
     static_assert(sizeof(cv::KeyPoint) == sizeof(OrbxKeyPoint), "cv::KeyPoint must be the 28-byte POD of OpenCV 2.4/3.x/4.x");
     _keypoints.resize(cap);
@@ -62,14 +62,20 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray /*_mask*/, 
     }
 
     if (mbDownloadPyramid)
+    {
+        // ONE asynchronous copy (issued by orbx_extract itself, in the stream of its kernels) brought the frame's whole
+        // raw pyramid block into the handle's pinned mirror; every level is a cv::Mat header over it with the device
+        // pitch as step, so the 19-px apron lies around the payload exactly as around the reference's ROI of `temp`
+        const unsigned char* block = 0;
+        if (orbx_pyramid_mirror(mpHandle, 0, &block) != ORBX_OK) die("orbx_pyramid_mirror");
         for (int level = 0; level < nlevels; ++level)
         {
-            int w = 0, h = 0;
-            if (orbx_level_size(mpHandle, level, &w, &h) != ORBX_OK) die("orbx_level_size");
-            mvWhole[level].create(h + 38, w + 38, CV_8UC1);
-            if (orbx_pyramid_level(mpHandle, 0, level, mvWhole[level].data, (int)mvWhole[level].step) != ORBX_OK) die("orbx_pyramid_level");
-            mvImagePyramid[level] = mvWhole[level](cv::Rect(19, 19, w, h));
+            int w = 0, h = 0, pitch = 0; size_t off = 0;
+            if (orbx_level_size(mpHandle, level, &w, &h) != ORBX_OK ||
+                orbx_pyramid_level_layout(mpHandle, level, &off, &pitch, 0) != ORBX_OK) die("orbx_pyramid_level_layout");
+            mvImagePyramid[level] = cv::Mat(h, w, CV_8UC1, const_cast<unsigned char*>(block + off), (size_t)pitch);
         }
+    }
 }
 
 } //namespace ORB_SLAM

@@ -40,8 +40,10 @@ public:
     std::vector<float> inline GetInverseScaleSigmaSquares(){ return mvInvLevelSigma2; }
 
     // reference: ORBextractor.h:104. Filled after every operator() call when mbDownloadPyramid is true (default):
-    // each level is a view at (19,19) into a (w+38)x(h+38) buffer holding the BORDER_REFLECT_101 apron, exactly the
-    // reference's memory layout. Monocular / RGB-D users can switch the download off (nothing reads the pyramid there).
+    // each level is a cv::Mat header over the handle's pinned mirror of the frame's raw pyramid block (one asynchronous
+    // device-to-host copy per frame); its step is the device pitch and the BORDER_REFLECT_101 apron lies around the
+    // payload, exactly as around the reference's view at (19,19) of `temp`. Valid until the next operator() call.
+    // Monocular / RGB-D users can switch the download off (nothing reads the pyramid there).
     std::vector<cv::Mat> mvImagePyramid;
     bool mbDownloadPyramid;
 
@@ -59,7 +61,6 @@ protected:
     std::vector<float> mvLevelSigma2;
     std::vector<float> mvInvLevelSigma2;
     std::vector<int> mnFeaturesPerLevel;
-    std::vector<cv::Mat> mvWhole;      // backing (w+38)x(h+38) buffers of mvImagePyramid
     orbx_extractor* mpHandle;
 };
 
