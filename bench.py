@@ -702,12 +702,36 @@ def run_matchers(args, torch, dist, rank, world, local, dev):
     emit_json_line(line)
 
 
-def run_stereo(args, torch, dist, rank, world, local, dev):
-    """Stereo pairs/s: two extractor instances (as the reference, Tracking.cc:120-123) + the device-resident matcher."""
+def h2d_ceiling_gbs(torch, dist, host_batch, dev, world, reps=8):
+    """What the box can feed: every rank copies its own pinned batch to its GPU at the same time, no kernels running
+    (cudaMemcpyAsync on one stream, `reps` copies back to back); aggregate GB/s = world x bytes x reps / max-over-ranks time."""
+    dst = torch.empty_like(host_batch, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        dst.copy_(host_batch, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(st):
+        for _ in range(reps):
+            dst.copy_(host_batch, non_blocking=True)
+    st.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return world * host_batch.numel() * reps / float(t.item()) / 1e9
+
+
+def stereo_measure(wname, P, steps, warmup, torch, dist, rank, world, local, dev, distinct=None):
+    """Stereo pairs/s: two extractor instances (as the reference, Tracking.cc:120-123) + the device-resident matcher
+    (Frame.cc:80-84, 547-788); pairs shard by frame over the ranks, no collective. Returns the bench line (without a CPU
+    baseline) on rank 0 and None elsewhere; every rank takes part in the barriers / reductions."""
     from orb_slam2_commit_b200 import ORBextractor, api, stereo_match_device
-    w = WORKLOADS[args.workload]; c = synth.CONFIGS[w["cfg"]]
-    P = args.batch or w["batch"]; W, H = c["width"], c["height"]
-    pairs = [synth.synth_stereo_pair(W, H, 2 + i + 1000 * rank) for i in range(w["distinct"])]
+    w = WORKLOADS[wname]; c = synth.CONFIGS[w["cfg"]]
+    W, H = c["width"], c["height"]
+    pairs = [synth.synth_stereo_pair(W, H, 2 + i + 1000 * rank) for i in range(distinct or w["distinct"])]
+    args = argparse.Namespace(steps=steps, warmup=warmup)
     hL = torch.empty((P, H, W), dtype=torch.uint8, pin_memory=True); hR = torch.empty((P, H, W), dtype=torch.uint8, pin_memory=True)
     for i in range(P):
         hL.numpy()[i] = pairs[i % len(pairs)][0]; hR.numpy()[i] = pairs[i % len(pairs)][1]
@@ -791,7 +815,8 @@ def run_stereo(args, torch, dist, rank, world, local, dev):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_v = world * P * n_e2e / float(t.item())
     assert np.array_equal(hout["nl"], hout2["nl"]) and np.array_equal(hout["u_right"].view(np.uint32)[0, :hout["nl"][0]], hout2["u_right"].view(np.uint32)[0, :hout["nl"][0]])
-    if rank != 0: return
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    if rank != 0: return None
     matched = float((outs[6][:, :] >= 0).sum().item()) / P   # includes unwritten tail slots only if >= 0 garbage; informational
     nl_np = outs[2].numpy()
     matched = float(np.mean([(outs[6][i, :nl_np[i]] >= 0).sum().item() for i in range(P)]))
@@ -806,6 +831,15 @@ def run_stereo(args, torch, dist, rank, world, local, dev):
                     "synchronous_call": {"value": e2e_sync_v, "api": "orbx_stereo_extract_batch, one blocking call per step"}},
             "stages": {"extract_left_right_ms": ms_extract, "stereo_match_ms": ms_match},
             "pipeline": {"keypoints_per_image": float(nl_np.mean()), "stereo_matches_per_pair": matched}}
+    return line
+
+
+def run_stereo(args, torch, dist, rank, world, local, dev):
+    w = WORKLOADS[args.workload]; c = synth.CONFIGS[w["cfg"]]
+    cfgargs = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    line = stereo_measure(args.workload, args.batch or w["batch"], args.steps, args.warmup, torch, dist, rank, world, local, dev)
+    if rank != 0: return
+    pairs = [synth.synth_stereo_pair(c["width"], c["height"], 2 + i) for i in range(w["distinct"])]
     if world == 1 and not args.no_cpu_baseline:
         # CPU: the oracle port, two extractions + ComputeStereoMatches per pair, pair-parallel over the host threads
         from oracle import binding as ob
@@ -838,6 +872,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-stereo", action="store_true", help="skip the EuRoC / KITTI stereo legs of the default line")
     args = ap.parse_args()
     global _RESULT_FD
     sys.stdout.flush()
@@ -984,7 +1019,7 @@ def main():
         assert int(sets[0][2].sum()) == int(nkp.sum()) and int(sets[1][2].sum()) == int(nkp.sum()), "batches in flight disagree with the device path"
 
     # ---- single-frame latency through orbx_extract (what a SLAM front-end sees: one frame in, keypoints out)
-    lat_ms = None
+    lat_ms = lat_pyr_ms = None
     if rank == 0 and not rectify:
         ex1 = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"], device=local)
         cap1 = ex1.reserve(W, H, 1)
@@ -997,7 +1032,32 @@ def main():
         for i in range(200):
             ex1.extract_host(hb[i % B:i % B + 1], k1, d1, n1)
         lat_ms = (time.perf_counter() - t0) / 200 * 1e3
+        # the same call when the caller also wants mvImagePyramid on the host (stereo: Frame.cc:556,681-700): the frame's raw
+        # pyramid block comes back in ONE asynchronous copy in the stream of the kernels (orbx_set_pyramid_mirror)
+        ex1.set_pyramid_mirror(True)
+        for _ in range(20):
+            ex1.extract_host(hb[:1], k1, d1, n1)
+        t0 = time.perf_counter()
+        for i in range(200):
+            ex1.extract_host(hb[i % B:i % B + 1], k1, d1, n1)
+            ex1.pyramid_mirror(0)
+        lat_pyr_ms = (time.perf_counter() - t0) / 200 * 1e3
         del ex1
+
+    # ---- what the box can feed: all ranks upload their pinned batch at once, no kernels (the e2e number is read against this)
+    ceiling_gbs = h2d_ceiling_gbs(torch, dist, host_batch, dev, world)
+
+    # ---- configs 2 and 3 ride along on the default line: KITTI and EuRoC stereo pairs (two extractors + ComputeStereoMatches,
+    # Frame.cc:80-84, 547-788), pairs sharded by frame over the ranks, short runs
+    stereo_legs = {}
+    if args.workload == "tum1" and not args.no_stereo:
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
+        for leg, P_leg in (("euroc_stereo", 128), ("kitti_stereo", 64)):
+            ln = stereo_measure(leg, P_leg, max(3, min(args.steps, 8)), 3, torch, dist, rank, world, local, dev, distinct=4)
+            if ln is not None:
+                stereo_legs[leg] = {"pairs_per_s": ln["value"], "unit": "pairs/s", "ms_per_step": ln["ms_per_step"], "e2e": ln["e2e"],
+                                    "config": ln["config"], "stages": ln["stages"], "pipeline": ln["pipeline"]}
+        torch.cuda.set_stream(tstream)
 
     # ---- config 4 across ranks: train set sharded, per-query top-2 merged after an NCCL all-gather (all ranks take part)
     hamming_sharded = None
@@ -1082,16 +1142,19 @@ def main():
         traffic = None
         try:
             import csv as _csv
-            prof = os.path.join(ROOT, "profiles", "r01_ncu_full_batch128.csv")
+            import glob as _glob
+            prof = sorted(_glob.glob(os.path.join(ROOT, "profiles", "r0*_ncu_full_batch128.csv")))[-1]     # the newest committed capture
+            prof_name = os.path.relpath(prof, ROOT)
             key = {"pyramid": "pyr_resize_kernel", "fast": "fast_cells_kernel", "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]]
             rows_ = list(_csv.reader(open(prof)))
             hdr_ = rows_[0]
             ir = [i for i, c_ in enumerate(hdr_) if c_.startswith("dram__bytes_read.sum")][0]
             iw = [i for i, c_ in enumerate(hdr_) if c_.startswith("dram__bytes_write.sum")][0]
             mb = sum(float(r_[ir]) + float(r_[iw]) for r_ in rows_[1:] if key in r_[0])
-            traffic = mb * 1e6 / 128.0 * B
+            # a capture of the TUM1 geometry says nothing about another workload's traffic
+            traffic = mb * 1e6 / 128.0 * B if (w["cfg"] == "tum1" and not rectify) else None
         except Exception:
-            traffic = None
+            traffic = None; prof_name = None
         # the binding resource of this integer/byte pipeline is instruction issue, not HBM: warp-instructions per frame
         # (committed ncu capture, TUM1 geometry) x measured frames/s against 148 SMs x 4 issue slots x the sampled SM clock
         issue = None
@@ -1102,14 +1165,18 @@ def main():
                 peak_issue = 148 * 4 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
                 issue = {"warp_instructions_per_frame": inst_per_frame, "peak_warp_instructions_per_s": peak_issue,
                          "frac": inst_per_frame * frames_per_s / world / peak_issue,
-                         "source": "profiles/r01_ncu_full_batch128.csv (smsp__inst_executed.sum, all kernels of a step)"}
+                         "source": f"{prof_name} (smsp__inst_executed.sum, all kernels of a step)"}
         except Exception:
             issue = None
-        roofline = {"bound": "hbm", "issue": issue, "kernel": {"pyramid": "pyr_level0_kernel+pyr_resize_kernel (one launch per level)", "fast": "fast_cells_kernel",
+        # what binds: the pixel kernels of this integer / byte path saturate instruction issue (ALU pipe) or, for describe,
+        # shared-memory wavefronts long before HBM (ncu: issue 73-80 %, DRAM 4-7 %); `achieved` / `peak` / `frac` keep the HBM
+        # roofline of the contract beside it
+        roofline = {"bound": "issue", "bound_detail": "instruction issue / ALU pipe (ncu smsp__issue_active ~78 %, dram throughput ~5 %); achieved, peak and frac are the HBM roofline of the same kernel",
+                    "issue": issue, "kernel": {"pyramid": "pyr_level0_kernel+pyr_resize_kernel (one launch per level)", "fast": "fast_cells_kernel",
                                               "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]],
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
                     "algorithmic_bytes_per_frame": ab[names[dom]], "frames_per_launch": B, "traffic": traffic,
-                    "traffic_source": "profiles/r01_ncu_full_batch128.csv (dram read+write per frame x frames per launch)",
+                    "traffic_source": (f"{prof_name} (dram read+write per frame x frames per launch)" if traffic is not None else None),
                     "stage_events_averaged_over_steps": nruns}
         launches_per_step = c["nlevels"] + 3
         line = {"metric": "orb_frames_per_s", "value": frames_per_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -1121,8 +1188,10 @@ def main():
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
                         "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": e2e_api,
-                        "synchronous_call": {"value": e2e_sync_fps, "api": ("orbx_extract_batch_rectified" if rectify else "orbx_extract_batch") + ", one blocking call per step"}},
-                "latency_single_frame_ms": lat_ms,
+                        "synchronous_call": {"value": e2e_sync_fps, "api": ("orbx_extract_batch_rectified" if rectify else "orbx_extract_batch") + ", one blocking call per step"},
+                        "h2d_ceiling_gbs": ceiling_gbs, "h2d_gbs": e2e_fps * W * H / 1e9, "frac_of_h2d_ceiling": e2e_fps * W * H / 1e9 / ceiling_gbs,
+                        "h2d_ceiling_how": "all ranks copy their pinned input batch to their GPU concurrently, no kernels running (aggregate GB/s, max time over ranks)"},
+                "latency_single_frame_ms": lat_ms, "latency_single_frame_with_pyramid_ms": lat_pyr_ms,
                 "roofline": roofline, "stages": stages,
                 "pipeline": {"keypoints_per_frame": nkp_mean, "keypoints_per_s": frames_per_s * nkp_mean,
                              "algorithmic_bytes_per_frame_survey": ab["B_survey"],
@@ -1134,6 +1203,7 @@ def main():
                 line["hamming"] = {"error": str(e)}
         if hamming_sharded is not None:
             line["hamming"] = hamming_sharded
+        line.update(stereo_legs)
         if world == 1 and not args.no_cpu_baseline:
             nthreads = os.cpu_count() or 1
             if rectify:

@@ -60,6 +60,9 @@ def lib():
         L.orbx_get_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, i32p, i32p]
         L.orbx_reserve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orbx_max_keypoints.argtypes = [C.c_void_p]
+        L.orbx_set_pyramid_mirror.argtypes = [C.c_void_p, C.c_int]
+        L.orbx_pyramid_mirror.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_uint8))]
+        L.orbx_pyramid_level_layout.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.orbx_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, i32p, u8p]
         L.orbx_extract_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_int, i32p, C.c_void_p]
@@ -358,6 +361,24 @@ class ORBextractor:
         out = np.zeros(max(n.value, 1), KP_DTYPE)
         _ck(self._L.orbx_debug_candidates(self._h, frame, level, out.ctypes.data, n.value, C.byref(n)))
         return out[:n.value]
+
+    def set_pyramid_mirror(self, on: bool):
+        """Single-frame host calls also bring the frame's raw pyramid block to a pinned host mirror (one asynchronous copy)."""
+        _ck(self._L.orbx_set_pyramid_mirror(self._h, int(bool(on))))
+
+    def pyramid_mirror(self, frame: int = 0):
+        """-> list of per-level uint8 views (h x w, strides (pitch, 1)) into the handle's pinned mirror of `frame`'s pyramid;
+        the 19-px apron lies around every view in memory. Valid until the next call on the extractor."""
+        blk = C.POINTER(C.c_uint8)()
+        _ck(self._L.orbx_pyramid_mirror(self._h, frame, C.byref(blk)))
+        out = []
+        for l in range(self.nlevels):
+            w = C.c_int(0); h = C.c_int(0); pitch = C.c_int(0); off = C.c_size_t(0); tot = C.c_size_t(0)
+            _ck(self._L.orbx_level_size(self._h, l, C.byref(w), C.byref(h)))
+            _ck(self._L.orbx_pyramid_level_layout(self._h, l, C.byref(off), C.byref(pitch), C.byref(tot)))
+            whole = np.ctypeslib.as_array(blk, shape=(tot.value,))
+            out.append(np.lib.stride_tricks.as_strided(whole[off.value:], shape=(h.value, w.value), strides=(pitch.value, 1), writeable=False))
+        return out
 
     def debug_level_counts(self, frame: int = 0):
         c = np.zeros(self.nlevels, np.int32)

@@ -804,3 +804,28 @@ def test_stereo_batches_in_flight_give_the_results_of_the_synchronous_call():
             assert np.array_equal(out[s]["u_right"][i, :nl].view(np.uint32), ref[s]["u_right"][i, :nl].view(np.uint32))
             assert np.array_equal(out[s]["depth"][i, :nl].view(np.uint32), ref[s]["depth"][i, :nl].view(np.uint32))
         assert int(np.count_nonzero(ref[s]["u_right"] > 0)) > 20 * n
+
+
+def test_pyramid_mirror_is_the_pyramid_with_its_apron():
+    """orbx_pyramid_mirror: ONE copy of the frame's raw block; every level's header (payload pointer, device pitch as step)
+    sees the payload and, by pointer arithmetic as in Frame.cc:681-700, the 19-px BORDER_REFLECT_101 apron around it."""
+    import ctypes
+    c = _cfg("tum1")
+    img = synth.synth_image(c["width"], c["height"], 21)
+    orc = ob.Extractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    orc.extract(img)
+    for mirror_in_call in (True, False):
+        ex = ORBextractor(c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+        ex.set_pyramid_mirror(mirror_in_call)
+        for _ in range(3):                                    # the third call replays the recorded CUDA graph
+            ex(img)
+        for l, v in enumerate(ex.pyramid_mirror(0)):
+            want = orc.level(l)                               # (h+38) x (w+38), apron included
+            h, w = v.shape
+            assert want.shape == (h + 38, w + 38)
+            assert np.array_equal(np.asarray(v), want[19:-19, 19:-19]), f"level {l}: payload"
+            pitch = v.strides[0]
+            addr = v.__array_interface__["data"][0] - 19 * pitch - 19
+            flat = np.frombuffer((ctypes.c_uint8 * ((h + 38) * pitch)).from_address(addr), np.uint8)
+            around = np.lib.stride_tricks.as_strided(flat, shape=(h + 38, w + 38), strides=(pitch, 1))
+            assert np.array_equal(around, want), f"level {l}: apron around the mirrored payload"
