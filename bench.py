@@ -675,6 +675,44 @@ def run_matchers(args, torch, dist, rank, world, local, dev):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_v = world * n_e2e / float(t.item())
+    # ---- the same call against a device-resident Frame handle (orbx_frame_*): keypoints / descriptors / mvuRight stay in HBM,
+    # only the projected map points go up (one packed copy from pinned staging) and the assignments come down. One handle per
+    # host thread (own stream): (a) one thread, call after call = the latency a tracking thread sees; (b) all host threads at
+    # once, each on its own handle = what the machine sustains — the form the 16-thread CPU baseline is measured in.
+    from orb_slam2_commit_b200 import Frame
+    nthreads_h = os.cpu_count() or 1
+    handles = []
+    for t_ in range(nthreads_h):
+        sc = lp[t_ % nd]
+        fr = Frame(len(sc["kps"]), len(sc["queries"]), device=local)
+        fr.from_device(lpd[t_ % nd]["kps"], lpd[t_ % nd]["desc"], len(sc["kps"]), stream=st)
+        fr.set_stereo(sc["u_right"])
+        handles.append((fr, sc, np.empty(len(sc["kps"]), np.int32)))
+    torch.cuda.synchronize()
+
+    def frame_call(h):
+        fr, sc, out = h
+        return fr.search_local_points(sc["queries"], sc["query_desc"], sc["query_flags"], sc["occupied"], sc["bounds4"], sc["scale_factors"], 1.0, 0.8, out=out)
+    want_nm = [search_local_points(**lp[i], th=1.0, nnratio=0.8, device=local)[0] for i in range(nd)]
+    for t_, h in enumerate(handles):
+        assert frame_call(h)[0] == want_nm[t_ % nd], "frame-handle result differs from the one-shot host call"
+    t0 = time.perf_counter()
+    for i in range(400):
+        frame_call(handles[0])
+    frame_lat_ms = (time.perf_counter() - t0) / 400 * 1e3
+    per_thread = 300
+
+    def worker(h):
+        for _ in range(per_thread):
+            frame_call(h)
+    barrier()
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(h,)) for h in handles]
+    [x.start() for x in th]; [x.join() for x in th]
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    frame_mt_v = world * nthreads_h * per_thread / float(t.item())
+    del handles
     if rank != 0: return
     sc0 = lp[0]
     line = {"metric": "search_local_points_calls_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -685,7 +723,12 @@ def run_matchers(args, torch, dist, rank, world, local, dev):
                        "frames_per_step_per_gpu": P, "distinct_scenes": nd},
             "clocks": clocks, "gpu_launches": args.steps,
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(sum(np.asarray(v).nbytes for v in sc0.values() if v is not None)),
-                    "d2h_bytes_per_step": 4 * len(sc0["kps"]) + 4, "steps": n_e2e, "api": "orbx_search_local_points (one frame per call, synchronous)"},
+                    "d2h_bytes_per_step": 4 * len(sc0["kps"]) + 4, "steps": n_e2e, "api": "orbx_search_local_points (one frame per call, synchronous)",
+                    "frame_handle": {"api": "orbx_frame_search_local_points (device-resident Frame, one frame per call, synchronous)",
+                                     "h2d_bytes_per_call": int(sc0["queries"].nbytes + np.asarray(sc0["query_desc"]).nbytes + len(sc0["query_flags"]) + len(sc0["kps"]) + 256),
+                                     "one_host_thread": {"frames_per_s": 1e3 / frame_lat_ms, "ms_per_call": frame_lat_ms},
+                                     "all_host_threads": {"frames_per_s": frame_mt_v, "threads": nthreads_h, "handles": nthreads_h,
+                                                          "note": "every thread calls on its own handle / stream; the kernels of different handles overlap on the GPU"}}},
             "pipeline": {"matches_per_frame": float(d_nm.float().mean().item())}, "others": others}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import binding as ob

@@ -403,6 +403,37 @@ int orbx_search_local_points_device(const OrbxLocalPointsFrame* frames, int nfra
                                     const float* scale_factors, int nlevels, float th, float nnratio, int device,
                                     void* cuda_stream);
 
+/* ---- A device-resident Frame (Frame::Frame, Frame.cc:62-123: ExtractORB -> UndistortKeyPoints -> ComputeStereoMatches ->
+ *      AssignFeaturesToGrid all work on the SAME keypoints). An orbx_frame keeps mvKeys, mDescriptors, mvKeysUn and mvuRight
+ *      of one frame in HBM, taken straight from the extractor's device results, together with the scratch of the matchers:
+ *      a matcher call uploads only the projected map points (one packed copy from a pinned staging buffer) and downloads
+ *      the assignments (one copy); nothing is allocated on the call path. Every handle owns a CUDA stream, so calls on
+ *      different handles — host threads, frames in flight — overlap on the GPU. A handle is not re-entrant. ---- */
+typedef struct orbx_frame orbx_frame;
+int  orbx_frame_create(int device, int max_keypoints, int max_queries, orbx_frame** out);
+void orbx_frame_destroy(orbx_frame* f);
+/* Frame `frame_index` (n keypoints, as reported in nkp) of the extractor's last HOST call (orbx_extract / orbx_extract_batch*):
+ * device-to-device copy of keypoints + descriptors, then Frame::UndistortKeyPoints (Frame.cc:471-506) with K4 = (fx, fy, cx,
+ * cy) and `ndist` distortion coefficients (0 = mvKeysUn = mvKeys). Ordered behind the extractor's stream, asynchronous. */
+int  orbx_frame_from_extract(orbx_frame* f, orbx_extractor* ex, int frame_index, int n, const float* K4, const float* dist, int ndist);
+/* the same from device arrays (e.g. the outputs of orbx_extract_device); producer_stream = the stream that wrote them */
+int  orbx_frame_from_device(orbx_frame* f, const OrbxKeyPoint* d_keypoints, const uint8_t* d_descriptors, int n, const float* K4,
+                            const float* dist, int ndist, void* producer_stream);
+/* mvuRight (n floats; host array, or a device array when on_device != 0, e.g. the output of orbx_stereo_match_device); NULL = monocular */
+int  orbx_frame_set_stereo(orbx_frame* f, const float* u_right, int on_device);
+int  orbx_frame_size(const orbx_frame* f);
+/* mvKeysUn / mDescriptors back on the host (either may be NULL) */
+int  orbx_frame_keypoints(orbx_frame* f, OrbxKeyPoint* keypoints_un, uint8_t* descriptors, int cap, int* n);
+/* the resident arrays and the handle's stream, for chaining the *_device matcher forms */
+int  orbx_frame_device_arrays(orbx_frame* f, const OrbxKeyPoint** d_keypoints, const OrbxKeyPoint** d_keypoints_un,
+                              const uint8_t** d_descriptors, const float** d_u_right, void** cuda_stream);
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th) (ORBmatcher.cc:46-142) against the resident frame:
+ * arguments as orbx_search_local_points, host arrays; occupied (n bytes) may be NULL. Synchronous. */
+int  orbx_frame_search_local_points(orbx_frame* f, const OrbxTrackQuery* queries, const uint8_t* query_descriptors,
+                                    const uint8_t* query_flags, int nq, const uint8_t* occupied, const float* bounds4,
+                                    const float* scale_factors, int nlevels, float th, float nnratio, int32_t* match,
+                                    int32_t* nmatches);
+
 /* ---- The search half of ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th) (ORBmatcher.cc:918-1092;
  *      mode 0) and of Fuse(KeyFrame *pKF, cv::Mat Scw, vpPoints, th, vpReplacePoint) (:1094-1236; mode 1, with Rcw / tcw / Ow
  *      taken out of Scw by the caller as :1101-1106 do): projection into the keyframe, KeyFrame::IsInImage, the distance-

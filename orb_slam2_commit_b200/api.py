@@ -386,6 +386,74 @@ class ORBextractor:
         return c
 
 
+class Frame:
+    """Device-resident Frame (include/orbx.h orbx_frame_*; Frame.cc:62-123): keypoints, descriptors, undistorted keypoints and
+    mvuRight stay in HBM; matcher calls upload only the projected map points."""
+
+    def __init__(self, max_keypoints: int, max_queries: int, device: int = 0):
+        self._L = lib(); self._h = C.c_void_p()
+        L = self._L
+        L.orbx_frame_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.orbx_frame_destroy.argtypes = [C.c_void_p]; L.orbx_frame_destroy.restype = None
+        L.orbx_frame_from_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, f32p, f32p, C.c_int]
+        L.orbx_frame_from_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.c_void_p]
+        L.orbx_frame_set_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orbx_frame_size.argtypes = [C.c_void_p]
+        L.orbx_frame_keypoints.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, i32p]
+        L.orbx_frame_search_local_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, f32p, f32p, C.c_int,
+                                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        _ck(L.orbx_frame_create(device, max_keypoints, max_queries, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orbx_frame_destroy(self._h); self._h = None
+
+    @staticmethod
+    def _kd(K4, dist):
+        K = None if K4 is None else np.ascontiguousarray(K4, np.float32)
+        D = None if dist is None else np.ascontiguousarray(dist, np.float32)
+        return K, D, (0 if D is None else len(D))
+
+    def from_extract(self, ex: "ORBextractor", frame_index: int, n: int, K4=None, dist=None):
+        K, D, nd = self._kd(K4, dist)
+        _ck(self._L.orbx_frame_from_extract(self._h, ex._h, frame_index, n, None if K is None else K.ctypes.data_as(f32p),
+                                            None if D is None else D.ctypes.data_as(f32p), nd))
+
+    def from_device(self, d_kps: int, d_desc: int, n: int, K4=None, dist=None, stream: int = 0):
+        K, D, nd = self._kd(K4, dist)
+        _ck(self._L.orbx_frame_from_device(self._h, d_kps, d_desc, n, None if K is None else K.ctypes.data_as(f32p),
+                                           None if D is None else D.ctypes.data_as(f32p), nd, stream))
+
+    def set_stereo(self, u_right):
+        if u_right is None:
+            _ck(self._L.orbx_frame_set_stereo(self._h, None, 0)); return
+        u = np.ascontiguousarray(u_right, np.float32)
+        _ck(self._L.orbx_frame_set_stereo(self._h, u.ctypes.data, 0))
+
+    def __len__(self):
+        return self._L.orbx_frame_size(self._h)
+
+    def keypoints(self):
+        n = len(self)
+        k = np.zeros(max(n, 1), KP_DTYPE); d = np.zeros((max(n, 1), 32), np.uint8); m = C.c_int32(0)
+        _ck(self._L.orbx_frame_keypoints(self._h, k.ctypes.data, d.ctypes.data, max(n, 1), C.byref(m)))
+        return k[:n], d[:n]
+
+    def search_local_points(self, queries, query_descriptors, query_flags, occupied, bounds4, scale_factors, th, nnratio=0.8,
+                            out=None):
+        """ORBmatcher(nnratio).SearchByProjection(F, vpMapPoints, th) -> (nmatches, match). `out` (int32, >= n) avoids an allocation."""
+        q = np.ascontiguousarray(queries); qd = np.ascontiguousarray(query_descriptors, np.uint8); qf = np.ascontiguousarray(query_flags, np.uint8)
+        oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        b4 = np.ascontiguousarray(bounds4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        n = len(self)
+        match = out if out is not None else np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        _ck(self._L.orbx_frame_search_local_points(self._h, q.ctypes.data, qd.ctypes.data, qf.ctypes.data, len(q),
+                                                   None if oc is None else oc.ctypes.data, b4.ctypes.data_as(f32p), sf.ctypes.data_as(f32p),
+                                                   len(sf), th, nnratio, match.ctypes.data, C.addressof(nm)))
+        return nm.value, match[:n]
+
+
 def hamming_top2(query: np.ndarray, train: np.ndarray, device: int = 0):
     """Best / second-best Hamming search (ORBmatcher.cc:84-126 idiom over DescriptorDistance :1844-1860).
     Returns (idx1, dist1, dist2) int32 arrays."""

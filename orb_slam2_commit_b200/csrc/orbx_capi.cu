@@ -785,6 +785,20 @@ extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, 
     return orbx_extract_batch(h, imgs, 1, width, height, stride, keypoints, cap, nkp, descriptors);
 }
 
+int orbx_internal_results(orbx_extractor* h, int frame_index, const OrbxKp28** d_kps, const uint8_t** d_desc, cudaStream_t* st, int* device)
+{
+    if (!h || !h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");
+    const int rc = finish_all_pending(h);
+    if (rc != ORBX_OK) return rc;
+    if (!h->map_chunk) return fail(ORBX_ERR_STATE, "the last call was orbx_extract_device: its results live in the caller's buffers (use orbx_frame_from_device)");
+    const int wsi = h->ws_index(frame_index);
+    if (wsi < 0) return fail(ORBX_ERR_STATE, "frame out of range, or its working-set slot was reused by a later chunk of the same call");
+    const int kc = h->L.kp_cap_total;
+    *d_kps = h->d_kps + (size_t)wsi * kc; *d_desc = h->d_desc + (size_t)wsi * kc * 32;
+    *st = h->slot_stream[(frame_index / h->map_chunk) % h->map_slots]; *device = h->device;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_level_size(const orbx_extractor* h, int level, int* width, int* height)
 {
     if (!h || !h->W) return fail(ORBX_ERR_STATE, "no geometry reserved yet");

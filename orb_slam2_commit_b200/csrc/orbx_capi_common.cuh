@@ -31,3 +31,7 @@ struct HostPack {
     size_t add(size_t bytes) { off.push_back(tot); tot += (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; return off.size() - 1; }
     uint8_t* at(size_t i) const { return pool + off[i]; }
 };
+
+// where the device results of an extractor's last HOST call live (orbx_capi.cu): frame `frame_index` of it, the stream that
+// produced them and the device; used by the frame handle (orbx_capi_frame.cu)
+int orbx_internal_results(orbx_extractor* h, int frame_index, const OrbxKp28** d_kps, const uint8_t** d_desc, cudaStream_t* st, int* device);
