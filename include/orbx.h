@@ -107,6 +107,15 @@ int orbx_extract_batch_color(orbx_extractor* h, const uint8_t* const* images, in
  * Map values must stay below 2^26 in magnitude. */
 int orbx_set_rectify_maps(orbx_extractor* h, const float* map1, const float* map2, int map_width, int map_height,
                           int map_stride, int src_width, int src_height);
+/* cv::initUndistortRectifyMap(K, D, R, P, size, CV_32F, M1, M2) itself (stereo_euroc.cc:96-97), on the device in OpenCV 4.x's
+ * double arithmetic (bit-exact against cv2 4.13): K9 / R9 row-major 3x3 doubles, D = 0, 4, 5, 8 or 12 distortion coefficients
+ * (k1, k2, p1, p2[, k3[, k4, k5, k6[, s1, s2, s3, s4]]]), P row-major with p_cols = 3 or 4 columns (only the left 3x3 block is
+ * read). orbx_init_undistort_rectify_map returns the f32 map pair (width x height each); orbx_set_rectify_camera builds the
+ * fixed-point map straight in HBM and installs it — the device-side equivalent of the two calls :96-97 + orbx_set_rectify_maps. */
+int orbx_init_undistort_rectify_map(const double* K9, const double* D, int nD, const double* R9, const double* P, int p_cols,
+                                    int width, int height, float* map1, float* map2, int device);
+int orbx_set_rectify_camera(orbx_extractor* h, const double* K9, const double* D, int nD, const double* R9, const double* P,
+                            int p_cols, int map_width, int map_height, int src_width, int src_height);
 /* size of the rectified frame (= the map's own size, which may differ from the source size): what orbx_reserve and the
  * keypoint capacity of the rectified calls are based on */
 int orbx_rectify_map_size(const orbx_extractor* h, int* map_width, int* map_height);
@@ -248,6 +257,14 @@ int orbx_stereo_extract_batch_begin(orbx_extractor* left, orbx_extractor* right,
                                     OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
                                     float* u_right, float* depth);
 int orbx_stereo_extract_batch_end(orbx_extractor* left);
+/* EuRoC-style stereo from RAW frames to mvuRight / mvDepth in one call: both extractors carry the rectification of their camera
+ * (orbx_set_rectify_camera = initUndistortRectifyMap on the device, or orbx_set_rectify_maps), cv::remap (stereo_euroc.cc:136-137)
+ * is fused into the level-0 kernels, then left / right extraction and ComputeStereoMatches as in orbx_stereo_extract_batch.
+ * Frames have the maps' source size; cap = orbx_max_keypoints() after orbx_reserve(h, map_width, map_height, ..). */
+int orbx_stereo_extract_batch_rectified(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                                        const uint8_t* const* images_right, int n, int stride, float mbf, float fx,
+                                        OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left, OrbxKeyPoint* kp_right,
+                                        uint8_t* desc_right, int32_t* n_right, int cap, float* u_right, float* depth);
 /* Device-resident, batched form: `pairs` stereo pairs whose left / right frames were the frames 0..pairs-1 of the last
  * orbx_extract_device call on `left` / `right`. Keypoints, descriptors and counts are those calls' device outputs
  * ([pairs][cap] layout). d_u_right / d_depth: [pairs][cap] floats, entries i < nl[pair] are written. Asynchronous on

@@ -160,6 +160,22 @@ def remap(img: np.ndarray, map1: np.ndarray, map2: np.ndarray) -> np.ndarray:
     return out
 
 
+def init_undistort_rectify_map(K, D, R, P, size):
+    """cv::initUndistortRectifyMap(K, D, R, P, size, CV_32FC1) -> (map1, map2); size = (width, height); P 3x3 or 3x4."""
+    import ctypes as C
+    K = np.ascontiguousarray(K, np.float64).reshape(3, 3); D = np.ascontiguousarray(D, np.float64).ravel()
+    R = np.ascontiguousarray(R, np.float64).reshape(3, 3); Ar = np.ascontiguousarray(np.asarray(P, np.float64)[:, :3])
+    w, h = size
+    m1 = np.empty((h, w), np.float32); m2 = np.empty((h, w), np.float32)
+    f64p = C.POINTER(C.c_double)
+    L = lib()
+    L.oc_init_undistort_rectify_map.argtypes = [f64p, f64p, C.c_int, f64p, f64p, C.c_int, C.c_int, f32p, f32p]
+    L.oc_init_undistort_rectify_map.restype = None
+    L.oc_init_undistort_rectify_map(K.ctypes.data_as(f64p), D.ctypes.data_as(f64p), len(D), R.ctypes.data_as(f64p), Ar.ctypes.data_as(f64p),
+                                    w, h, m1.ctypes.data_as(f32p), m2.ctypes.data_as(f32p))
+    return m1, m2
+
+
 def undistort_points(xy: np.ndarray, K4, dist) -> np.ndarray:
     xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
     K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)

@@ -1053,6 +1053,49 @@ void oc_undistort_points(const float* xy, int n, const float* K4, const float* d
     }
 }
 
+/* ------------------------------------------------------------------ cv::initUndistortRectifyMap(K, D, R, P, size, CV_32F, M1, M2)
+ * as called once per camera by Examples/Stereo/stereo_euroc.cc:96-97 (the maps cv::remap then uses at :136-137).
+ * OpenCV 4.x calib3d/undistort: everything in double; iR = (P[:, :3] * R)^-1 with cv::Matx's closed 3x3 cofactor inverse;
+ * for the pixel (j, i): (_x, _y, _w) = iR * (j, i, 1) evaluated as (i*ir[1] + ir[2]) + j*ir[0] (the per-lane positions of the
+ * vectorised loop — the scalar tail's running sum `_x += ir[0]` differs in the last bit and is NOT what cv2 4.13 returns),
+ * then the Brown-Conrady model with k1..k6, p1, p2, s1..s4 (no tilt) and the projection with K. D has 4, 5, 8 or 12 entries.
+ * Pinned bit-exact against cv2 4.13 (tests/golden/prims3_cv2.npz). K9 / R9 row-major 3x3, Ar9 = the left 3x3 block of P. */
+void oc_init_undistort_rectify_map(const double* K9, const double* D, int nD, const double* R9, const double* Ar9, int w, int h,
+                                   float* map1, float* map2)
+{
+    double k[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < nD && i < 12; i++) k[i] = D[i];
+    const double k1 = k[0], k2 = k[1], p1 = k[2], p2 = k[3], k3 = k[4], k4 = k[5], k5 = k[6], k6 = k[7], s1 = k[8], s2 = k[9], s3 = k[10], s4 = k[11];
+    const double fx = K9[0], fy = K9[4], u0 = K9[2], v0 = K9[5];
+    double a[9], ir[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int q = 0; q < 3; q++) s = s + Ar9[3 * r + q] * R9[3 * q + c];
+            a[3 * r + c] = s;
+        }
+    {
+        double d = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+        d = 1.0 / d;
+        ir[0] = (a[4] * a[8] - a[5] * a[7]) * d; ir[1] = (a[2] * a[7] - a[1] * a[8]) * d; ir[2] = (a[1] * a[5] - a[2] * a[4]) * d;
+        ir[3] = (a[5] * a[6] - a[3] * a[8]) * d; ir[4] = (a[0] * a[8] - a[2] * a[6]) * d; ir[5] = (a[2] * a[3] - a[0] * a[5]) * d;
+        ir[6] = (a[3] * a[7] - a[4] * a[6]) * d; ir[7] = (a[1] * a[6] - a[0] * a[7]) * d; ir[8] = (a[0] * a[4] - a[1] * a[3]) * d;
+    }
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++) {
+            const double _x = ((double)i * ir[1] + ir[2]) + (double)j * ir[0];
+            const double _y = ((double)i * ir[4] + ir[5]) + (double)j * ir[3];
+            const double _w = ((double)i * ir[7] + ir[8]) + (double)j * ir[6];
+            const double iw = 1.0 / _w, x = _x * iw, y = _y * iw;
+            const double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+            const double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2);
+            const double xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2) + s1 * r2 + s2 * r2 * r2;
+            const double yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy + s3 * r2 + s4 * r2 * r2;
+            map1[(size_t)i * w + j] = (float)(fx * xd + u0);
+            map2[(size_t)i * w + j] = (float)(fy * yd + v0);
+        }
+}
+
 /* ================================================================== bag of words (DBoW2)
  * Frame::ComputeBoW (Frame.cc:462-469) = mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) with
  * ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB> (include/ORBVocabulary.h). The reference vendors only

@@ -35,6 +35,8 @@ void  oc_remap_linear_8u(const uint8_t* src, int sw, int sh, int sstride, const 
                          int map_stride, int dw, int dh, uint8_t* dst, int dstride);  /* cv::remap INTER_LINEAR, BORDER_CONSTANT 0 */
 void  oc_undistort_points(const float* xy, int n, const float* K4, const float* dist, int ndist,
                           float* out_xy);                      /* cv::undistortPoints(src,dst,K,D,Mat(),K), Frame.cc:471-538 */
+void  oc_init_undistort_rectify_map(const double* K9, const double* D, int nD, const double* R9, const double* Ar9, int w, int h,
+                                    float* map1, float* map2);   /* cv::initUndistortRectifyMap(.., CV_32F, ..), stereo_euroc.cc:96-97 */
 int   oc_fast_score(const uint8_t* p, int stride);           /* cornerScore<16> with threshold floor 0 */
 int   oc_fast9_16(const uint8_t* roi, int w, int h, int stride, int threshold, int nms,
                   OcKeyPoint* out, int cap);                 /* cv::FAST(roi, kps, threshold, nms) */

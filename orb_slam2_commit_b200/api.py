@@ -273,6 +273,18 @@ class ORBextractor:
         _ck(self._L.orbx_set_rectify_maps(self._h, map1.ctypes.data_as(f32p), map2.ctypes.data_as(f32p), mw, mh, mw, sw, sh))
         self._map_size = (mw, mh)
 
+    def set_rectify_camera(self, K, D, R, P, map_size, src_size=None):
+        """initUndistortRectifyMap(K, D, R, P, map_size) built on the device and installed (stereo_euroc.cc:96-97); sizes = (w, h)."""
+        f64p = C.POINTER(C.c_double)
+        K = np.ascontiguousarray(K, np.float64).reshape(3, 3); D = np.ascontiguousarray(D, np.float64).ravel()
+        R = np.ascontiguousarray(R, np.float64).reshape(3, 3); P = np.ascontiguousarray(P, np.float64)
+        mw, mh = map_size
+        sw, sh = src_size if src_size is not None else map_size
+        self._L.orbx_set_rectify_camera.argtypes = [C.c_void_p, f64p, f64p, C.c_int, f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _ck(self._L.orbx_set_rectify_camera(self._h, K.ctypes.data_as(f64p), D.ctypes.data_as(f64p) if len(D) else None, len(D),
+                                            R.ctypes.data_as(f64p), P.ctypes.data_as(f64p), P.shape[1], mw, mh, sw, sh))
+        self._map_size = (mw, mh)
+
     def extract_rectified(self, images):
         """images: (n, h, w) or a list of UNRECTIFIED uint8 frames; cv::remap(.., INTER_LINEAR) is fused into level 0."""
         imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
@@ -546,6 +558,36 @@ def stereo_extract_host(left: ORBextractor, right: ORBextractor, images_left: np
     _ck(lib().orbx_stereo_extract_batch(left._h, right._h, pl, pr, n, w, h, w, mbf, fx, out["kl"].ctypes.data, out["dl"].ctypes.data,
                                         out["nl"].ctypes.data, out["kr"].ctypes.data, out["dr"].ctypes.data, out["nr"].ctypes.data,
                                         cap, out["u_right"].ctypes.data, out["depth"].ctypes.data))
+
+
+def stereo_extract_host_rectified(left: ORBextractor, right: ORBextractor, images_left: np.ndarray, images_right: np.ndarray, mbf: float,
+                                  fx: float, out: dict):
+    """orbx_stereo_extract_batch_rectified: UNRECTIFIED frames (n, src_h, src_w) in, both extractors carry their camera's
+    rectification (set_rectify_camera / set_rectify_maps); out as in stereo_extract_host, cap = reserve(map_w, map_h, ..)."""
+    n, h, w = images_left.shape
+    cap = out["kl"].shape[1]
+    pl = (C.c_void_p * n)(*[images_left.ctypes.data + i * h * w for i in range(n)])
+    pr = (C.c_void_p * n)(*[images_right.ctypes.data + i * h * w for i in range(n)])
+    L = lib()
+    L.orbx_stereo_extract_batch_rectified.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                                      C.c_float, C.c_float] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
+    _ck(L.orbx_stereo_extract_batch_rectified(left._h, right._h, pl, pr, n, w, mbf, fx, out["kl"].ctypes.data, out["dl"].ctypes.data,
+                                              out["nl"].ctypes.data, out["kr"].ctypes.data, out["dr"].ctypes.data, out["nr"].ctypes.data,
+                                              cap, out["u_right"].ctypes.data, out["depth"].ctypes.data))
+
+
+def init_undistort_rectify_map(K, D, R, P, size, device: int = 0):
+    """cv::initUndistortRectifyMap(K, D, R, P, size, CV_32FC1) on the device -> (map1, map2) float32 (h, w); size = (w, h)."""
+    f64p = C.POINTER(C.c_double)
+    K = np.ascontiguousarray(K, np.float64).reshape(3, 3); D = np.ascontiguousarray(D, np.float64).ravel()
+    R = np.ascontiguousarray(R, np.float64).reshape(3, 3); P = np.ascontiguousarray(P, np.float64)
+    w, h = size
+    m1 = np.empty((h, w), np.float32); m2 = np.empty((h, w), np.float32)
+    L = lib()
+    L.orbx_init_undistort_rectify_map.argtypes = [f64p, f64p, C.c_int, f64p, f64p, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_int]
+    _ck(L.orbx_init_undistort_rectify_map(K.ctypes.data_as(f64p), D.ctypes.data_as(f64p) if len(D) else None, len(D), R.ctypes.data_as(f64p),
+                                          P.ctypes.data_as(f64p), P.shape[1], w, h, m1.ctypes.data_as(f32p), m2.ctypes.data_as(f32p), device))
+    return m1, m2
 
 
 def window_top2(keypoints, descriptors, occupied, u_right, minX, minY, invW, invH, queries, query_descriptors, device: int = 0):

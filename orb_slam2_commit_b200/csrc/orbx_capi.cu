@@ -758,6 +758,73 @@ extern "C" int orbx_set_rectify_maps(orbx_extractor* h, const float* map1, const
     return ORBX_OK;
 }
 
+// host side of cv::initUndistortRectifyMap: iR = (P[:, :3] * R)^-1 with cv::Matx's product (running sum) and closed 3x3 cofactor
+// inverse, in plain doubles
+static int rectify_args(const double* K9, const double* D, int nD, const double* R9, const double* P, int p_cols, OrbxRectifyArgs* out)
+{
+    if (!K9 || !R9 || !P || (nD > 0 && !D) || (p_cols != 3 && p_cols != 4)) return fail(ORBX_ERR_INVALID, "K (3x3), R (3x3), P (3x3 or 3x4) required");
+    if (nD != 0 && nD != 4 && nD != 5 && nD != 8 && nD != 12) return fail(ORBX_ERR_UNSUPPORTED, "0, 4, 5, 8 or 12 distortion coefficients (no tilt)");
+    OrbxRectifyArgs a{};
+    for (int i = 0; i < nD; i++) a.k[i] = D[i];
+    a.fx = K9[0]; a.fy = K9[4]; a.u0 = K9[2]; a.v0 = K9[5];
+    double m[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int q = 0; q < 3; q++) s = s + P[p_cols * r + q] * R9[3 * q + c];
+            m[3 * r + c] = s;
+        }
+    double d = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    if (d == 0) return fail(ORBX_ERR_INVALID, "P * R is singular");
+    d = 1.0 / d;
+    a.ir[0] = (m[4] * m[8] - m[5] * m[7]) * d; a.ir[1] = (m[2] * m[7] - m[1] * m[8]) * d; a.ir[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+    a.ir[3] = (m[5] * m[6] - m[3] * m[8]) * d; a.ir[4] = (m[0] * m[8] - m[2] * m[6]) * d; a.ir[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+    a.ir[6] = (m[3] * m[7] - m[4] * m[6]) * d; a.ir[7] = (m[1] * m[6] - m[0] * m[7]) * d; a.ir[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+    *out = a;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_init_undistort_rectify_map(const double* K9, const double* D, int nD, const double* R9, const double* P, int p_cols,
+                                               int width, int height, float* map1, float* map2, int device)
+{
+    if (width <= 0 || height <= 0 || !map1 || !map2) return fail(ORBX_ERR_INVALID, "bad argument");
+    OrbxRectifyArgs a;
+    int rc = rectify_args(K9, D, nD, R9, P, p_cols, &a);
+    if (rc != ORBX_OK) return rc;
+    if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    float* d = nullptr;
+    const size_t n = (size_t)width * height;
+    CK(cudaMalloc(&d, 2 * n * sizeof(float)));
+    orbx_launch_rectify_map(a, width, height, d, d + n, nullptr, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(map1, d, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(map2, d + n, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_set_rectify_camera(orbx_extractor* h, const double* K9, const double* D, int nD, const double* R9, const double* P,
+                                       int p_cols, int map_width, int map_height, int src_width, int src_height)
+{
+    if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
+    if (map_width <= 0 || map_height <= 0 || src_width <= 0 || src_height <= 0) return fail(ORBX_ERR_INVALID, "bad sizes");
+    if (src_width > 32766 || src_height > 32766) return fail(ORBX_ERR_UNSUPPORTED, "source frame too large for 16-bit map coordinates");
+    OrbxRectifyArgs a;
+    int rc = rectify_args(K9, D, nD, R9, P, p_cols, &a);
+    if (rc != ORBX_OK) return rc;
+    rc = orbx_set_rectify_maps(h, nullptr, nullptr, 0, 0, 0, 0, 0);             // drains batches in flight, drops the old map and graph
+    if (rc != ORBX_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(&h->d_remap, (size_t)map_width * map_height * sizeof(uint2)));
+    orbx_launch_rectify_map(a, map_width, map_height, nullptr, nullptr, h->d_remap, 0);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    h->map_w = map_width; h->map_h = map_height; h->map_src_w = src_width; h->map_src_h = src_height;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_rectify_map_size(const orbx_extractor* h, int* map_width, int* map_height)
 {
     if (!h) return fail(ORBX_ERR_INVALID, "handle is NULL");
@@ -1083,16 +1150,22 @@ static int stereo_extract_batch_impl(orbx_extractor* left, orbx_extractor* right
                                      const uint8_t* const* images_right, int n, int width, int height, int stride,
                                      float mbf, float fx, OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left,
                                      OrbxKeyPoint* kp_right, uint8_t* desc_right, int32_t* n_right, int cap,
-                                     float* u_right, float* depth, bool begin_only)
+                                     float* u_right, float* depth, bool begin_only, bool rectify = false)
 {
     if (!left || !right || left == right) return fail(ORBX_ERR_INVALID, "two extractor instances required (Tracking.cc:120-123)");
     if (n <= 0 || !images_left || !images_right || width <= 0 || height <= 0) return ORBX_OK;
+    // with rectification (stereo_euroc.cc:136-137 fused into level 0) the frames have the maps' SOURCE size and the pyramids
+    // the maps' own size; both cameras must rectify onto the same image size
+    if (rectify && (!left->d_remap || !right->d_remap || left->map_w != right->map_w || left->map_h != right->map_h ||
+                    left->map_src_w != right->map_src_w || left->map_src_h != right->map_src_h))
+        return fail(ORBX_ERR_STATE, "both extractors need rectification maps of the same size (orbx_set_rectify_maps / orbx_set_rectify_camera)");
+    const int gw = rectify ? left->map_w : width, gh = rectify ? left->map_h : height;
     // the right handle may still serve another left handle's batch, or hold a mono batch of its own
     if (right->stereo_owner && right->stereo_owner != left) { const int rc = finish_all_pending(right); if (rc != ORBX_OK) return rc; }
     while (right->npending > 0) { const int rc = finish_oldest_pending(right); if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc; }
     // batches in flight live in `left`: a blocking call, another shape or a third batch first completes them
     while (left->npending > 0 && (!begin_only || left->npending >= 2 || left->pending[0].n != n || left->pending[0].cap != cap ||
-                                  left->pending[0].fbytes != (size_t)width * height || width != left->W || height != left->H)) {
+                                  left->pending[0].fbytes != (size_t)width * height || gw != left->W || gh != left->H)) {
         const int rc = finish_oldest_pending(left);
         if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc;
     }
@@ -1101,13 +1174,13 @@ static int stereo_extract_batch_impl(orbx_extractor* left, orbx_extractor* right
     if (left->device != right->device || left->nlevels != right->nlevels || left->scale_factor != right->scale_factor)
         return fail(ORBX_ERR_INVALID, "left and right extractors must share device and pyramid settings");
     for (orbx_extractor* h : {left, right})
-        if (width != h->W || height != h->H || h->max_batch < 1) {
-            int rc = orbx_reserve(h, width, height, std::max(1, std::min(n, std::max(h->max_batch, 64))));
+        if (gw != h->W || gh != h->H || h->max_batch < 1) {
+            int rc = orbx_reserve(h, gw, gh, std::max(1, std::min(n, std::max(h->max_batch, 64))));
             if (rc != ORBX_OK) return rc;
         }
     if (left->max_batch != right->max_batch) {
         const int B2 = std::max(left->max_batch, right->max_batch);
-        for (orbx_extractor* h : {left, right}) { int rc = orbx_reserve(h, width, height, B2); if (rc != ORBX_OK) return rc; }
+        for (orbx_extractor* h : {left, right}) { int rc = orbx_reserve(h, gw, gh, B2); if (rc != ORBX_OK) return rc; }
     }
     const int B = left->max_batch, kc = left->L.kp_cap_total;
     if (cap != kc || right->L.kp_cap_total != kc) return fail(ORBX_ERR_INVALID, "cap must equal orbx_max_keypoints() of both extractors");
@@ -1158,7 +1231,7 @@ static int stereo_extract_batch_impl(orbx_extractor* left, orbx_extractor* right
                     CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, width, sd.imgs[f0 + i], stride, width, height, cudaMemcpyHostToDevice, st));
                 }
             int rc = run_pipeline(sd.h, d_in, m, width, fbytes, sd.h->d_kps + (size_t)base * kc, sd.h->d_desc + (size_t)base * kc * 32, kc,
-                                  sd.h->d_nkp + base, st, base);
+                                  sd.h->d_nkp + base, st, base, 1, 0, rectify);
             if (rc != ORBX_OK) return rc;
         }
         OrbxStereoBatch a;
@@ -1218,6 +1291,17 @@ extern "C" int orbx_stereo_extract_batch_begin(orbx_extractor* left, orbx_extrac
 {
     return stereo_extract_batch_impl(left, right, images_left, images_right, n, width, height, stride, mbf, fx, kp_left, desc_left, n_left,
                                      kp_right, desc_right, n_right, cap, u_right, depth, true);
+}
+
+// the same with the rectification of both cameras fused into level 0: UNRECTIFIED frames in (the maps' source size)
+extern "C" int orbx_stereo_extract_batch_rectified(orbx_extractor* left, orbx_extractor* right, const uint8_t* const* images_left,
+                                                   const uint8_t* const* images_right, int n, int stride, float mbf, float fx,
+                                                   OrbxKeyPoint* kp_left, uint8_t* desc_left, int32_t* n_left, OrbxKeyPoint* kp_right,
+                                                   uint8_t* desc_right, int32_t* n_right, int cap, float* u_right, float* depth)
+{
+    if (!left || !left->d_remap) return fail(ORBX_ERR_STATE, "orbx_set_rectify_maps / orbx_set_rectify_camera has not been called on the left extractor");
+    return stereo_extract_batch_impl(left, right, images_left, images_right, n, left->map_src_w, left->map_src_h, stride, mbf, fx, kp_left,
+                                     desc_left, n_left, kp_right, desc_right, n_right, cap, u_right, depth, false, true);
 }
 
 extern "C" int orbx_stereo_extract_batch_end(orbx_extractor* left)

@@ -41,10 +41,30 @@ __global__ void hamming_init_kernel(unsigned long long* packed, int nq)
     if (i < nq) packed[i] = ht_pack(256, 256, 0xffffffffu);
 }
 
+// 256-bit Hamming distance. The popcount unit issues 16 lanes per clock per SM, a quarter of the logic pipe, and eight
+// POPC per pair made it the binding unit (0.91 of its ceiling, profiles/). A carry-save adder tree over the eight XOR
+// words (Harley-Seal) moves the work to 3-input logic ops: two full adders compress x0..x5 into two "ones" and two "twos"
+// words, a third takes the ones with x6, a fourth the three twos, so
+//   dist = popc(s3) + popc(x7) + 2 * popc(s4) + 4 * popc(c4)
+// — four POPC and eight extra LOP3 (sum = a ^ b ^ c, carry = majority(a, b, c)) instead of eight POPC.
+// (spelled as PTX so that the compiler keeps the adder tree as written: left to itself it re-associates the XORs through the
+// tree and ends up with 23 LOP3 per pair instead of 16)
+__device__ __forceinline__ unsigned ht_xor(unsigned a, unsigned b) { unsigned r; asm("xor.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ unsigned ht_xor3(unsigned a, unsigned b, unsigned c) { unsigned r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ unsigned ht_maj(unsigned a, unsigned b, unsigned c) { unsigned r; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ int ht_dist(const uint4 qa, const uint4 qb, const uint4 ta, const uint4 tb)
 {
-    return __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-           __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+    const unsigned x0 = ht_xor(qa.x, ta.x), x1 = ht_xor(qa.y, ta.y), x2 = ht_xor(qa.z, ta.z), x3 = ht_xor(qa.w, ta.w);
+    const unsigned x4 = ht_xor(qb.x, tb.x), x5 = ht_xor(qb.y, tb.y), x6 = ht_xor(qb.z, tb.z), x7 = ht_xor(qb.w, tb.w);
+#ifdef ORBX_HAMMING_PLAIN_POPC
+    return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+#else
+    const unsigned s1 = ht_xor3(x0, x1, x2), c1 = ht_maj(x0, x1, x2);
+    const unsigned s2 = ht_xor3(x3, x4, x5), c2 = ht_maj(x3, x4, x5);
+    const unsigned s3 = ht_xor3(s1, s2, x6), c3 = ht_maj(s1, s2, x6);
+    const unsigned s4 = ht_xor3(c1, c2, c3), c4 = ht_maj(c1, c2, c3);
+    return __popc(s3) + __popc(x7) + 2 * __popc(s4) + 4 * __popc(c4);
+#endif
 }
 
 __global__ void __launch_bounds__(HT_THREADS) hamming_top2_kernel(const uint4* __restrict__ q, int nq,

@@ -254,6 +254,9 @@ void orbx_launch_init_match(const OrbxInitPairDev* d_pairs, int npairs, int max_
 // cv::undistortPoints(src, dst, K, D, Mat(), K): intrinsics and (k1, k2, p1, p2, k3) widened to f64 on the host
 struct OrbxUndistortArgs { double fx, fy, cx, cy, ifx, ify, k[5]; };
 void orbx_launch_undistort(const OrbxKp28* d_in, OrbxKp28* d_out, int n, const OrbxUndistortArgs& a, cudaStream_t st);
+// cv::initUndistortRectifyMap: ir = (P[:, :3] * R)^-1 row-major, k = (k1, k2, p1, p2, k3, k4, k5, k6, s1, s2, s3, s4)
+struct OrbxRectifyArgs { double ir[9], k[12], fx, fy, u0, v0; };
+void orbx_launch_rectify_map(const OrbxRectifyArgs& a, int w, int h, float* d_map1, float* d_map2, uint2* d_fixed, cudaStream_t st);
 void orbx_launch_stereo_hamming(const OrbxKp28* kl, const uint8_t* dl, int nl, const OrbxKp28* kr, const uint8_t* dr,
                                 int nr, const int* row_start, const int* row_tab, int rows, float minD, float maxD,
                                 int* best_idx, int* best_dist, cudaStream_t st);

@@ -121,6 +121,13 @@ EUROC_LEFT = dict(
                 [0.001365741834644127, 0.9999741760894847, 0.007055629199258132],
                 [-0.008089410156878961, -0.007044357138835809, 0.9999424675829176]]),
     P=np.array([[435.2046959714599, 0, 367.4517211914062], [0, 435.2046959714599, 252.2008514404297], [0, 0, 1]]))
+EUROC_RIGHT = dict(
+    K=np.array([[457.587, 0, 379.999], [0, 456.134, 255.238], [0, 0, 1]]),
+    D=np.array([-0.28368365, 0.07451284, -0.00010473, -3.555907e-05, 0.0]),
+    R=np.array([[0.9999633526194376, -0.003625811871560086, 0.007755443660172947],
+                [0.003680398547259526, 0.9999684752771629, -0.007035845251224894],
+                [-0.007729688520722713, 0.007064130529506649, 0.999945173484644]]),
+    P=np.array([[435.2046959714599, 0, 367.4517211914062, -47.90639384423901], [0, 435.2046959714599, 252.2008514404297, 0], [0, 0, 1, 0]]))
 TUM1_K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
 TUM1_DIST = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
 

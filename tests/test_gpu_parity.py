@@ -829,3 +829,50 @@ def test_pyramid_mirror_is_the_pyramid_with_its_apron():
             flat = np.frombuffer((ctypes.c_uint8 * ((h + 38) * pitch)).from_address(addr), np.uint8)
             around = np.lib.stride_tricks.as_strided(flat, shape=(h + 38, w + 38), strides=(pitch, 1))
             assert np.array_equal(around, want), f"level {l}: apron around the mirrored payload"
+
+
+def test_init_undistort_rectify_map_on_the_device_equals_cv2(golden_dir):
+    """orbx_init_undistort_rectify_map (un-contracted f64 on the device) against the committed cv2 4.13 maps: bit for bit."""
+    from orb_slam2_commit_b200 import init_undistort_rectify_map
+    g = np.load(os.path.join(golden_dir, "prims3_cv2.npz"))
+    names = sorted({k[:-5] for k in g.files if k.endswith("_size")})
+    for n in names:
+        size = tuple(int(x) for x in g[n + "_size"])
+        m1, m2 = init_undistort_rectify_map(g[n + "_K"], g[n + "_D"], g[n + "_R"], g[n + "_P"], size)
+        assert zlib.crc32(m1.tobytes()) == int(g[n + "_crc"][0]) and zlib.crc32(m2.tobytes()) == int(g[n + "_crc"][1]), n
+        o1, o2 = ob.init_undistort_rectify_map(g[n + "_K"], g[n + "_D"], g[n + "_R"], g[n + "_P"], size)
+        assert np.array_equal(m1, o1) and np.array_equal(m2, o2)
+
+
+def test_raw_euroc_pairs_to_depth_in_one_call():
+    """orbx_set_rectify_camera (initUndistortRectifyMap on the device, both EuRoC cameras) + orbx_stereo_extract_batch_rectified:
+    unrectified pairs in, keypoints / descriptors / mvuRight / mvDepth out — against the oracle chain
+    initUndistortRectifyMap -> remap -> ORBextractor x 2 -> ComputeStereoMatches (stereo_euroc.cc:96-97,136-137; Frame.cc:80-117)."""
+    from orb_slam2_commit_b200 import api, stereo_extract_host_rectified
+    c = _cfg("euroc")
+    W, H = c["width"], c["height"]
+    cfgargs = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    exL, exR = ORBextractor(*cfgargs), ORBextractor(*cfgargs)
+    cams = (synth.EUROC_LEFT, synth.EUROC_RIGHT)
+    for ex, cam in zip((exL, exR), cams):
+        ex.set_rectify_camera(cam["K"], cam["D"], cam["R"], cam["P"], (W, H))
+    n = 3
+    pairs = [synth.synth_stereo_pair(W, H, 70 + i) for i in range(n)]
+    L = np.stack([p[0] for p in pairs]); R = np.stack([p[1] for p in pairs])
+    cap = exL.reserve(W, H, n); exR.reserve(W, H, n)
+    out = dict(kl=np.zeros((n, cap), api.KP_DTYPE), kr=np.zeros((n, cap), api.KP_DTYPE), dl=np.zeros((n, cap, 32), np.uint8),
+               dr=np.zeros((n, cap, 32), np.uint8), nl=np.zeros(n, np.int32), nr=np.zeros(n, np.int32),
+               u_right=np.zeros((n, cap), np.float32), depth=np.zeros((n, cap), np.float32))
+    stereo_extract_host_rectified(exL, exR, L, R, c["bf"], c["fx"], out)
+    maps = [ob.init_undistort_rectify_map(cam["K"], cam["D"], cam["R"], cam["P"], (W, H)) for cam in cams]
+    for i in range(n):
+        oL, oR = ob.Extractor(*cfgargs), ob.Extractor(*cfgargs)
+        k1, d1 = oL.extract(ob.remap(L[i], *maps[0])); k2, d2 = oR.extract(ob.remap(R[i], *maps[1]))
+        ur, dp = ob.stereo_match(oL, oR, k1, d1, k2, d2, c["bf"], c["fx"])
+        nl, nr = int(out["nl"][i]), int(out["nr"][i])
+        assert nl == len(k1) and nr == len(k2)
+        _check_against(out["kl"][i, :nl], out["dl"][i, :nl], k1, d1, f"left {i}")
+        _check_against(out["kr"][i, :nr], out["dr"][i, :nr], k2, d2, f"right {i}")
+        assert np.array_equal(out["u_right"][i, :nl].view(np.uint32), ur.view(np.uint32)), f"mvuRight of pair {i}"
+        assert np.array_equal(out["depth"][i, :nl].view(np.uint32), dp.view(np.uint32)), f"mvDepth of pair {i}"
+        assert (ur >= 0).sum() > 0        # (the synthetic pair is not a physical EuRoC pair: few rows still line up after rectification)

@@ -5,6 +5,8 @@
                      (resize INTER_LINEAR, copyMakeBorder REFLECT_101, GaussianBlur 7x7 s2, FAST 9-16 NMS at
                      T=20 and T=7 on whole images and cell-sized crops, fastAtan2)
   prims2_cv2.npz     cv2.remap INTER_LINEAR through initUndistortRectifyMap maps, cv2.undistortPoints
+  prims3_cv2.npz     cv2.initUndistortRectifyMap(K, D, R, P, size, CV_32FC1): EuRoC left / right cameras (map CRCs + every 8th
+                     row), twelve random cameras with 4 / 5 / 8 / 12 distortion coefficients (CRCs), one small camera in full
   ref_<cfg>.npz      keypoints (28-byte cv::KeyPoint records) + descriptors + per-level pyramid CRCs produced by
                      oracle/_ref = the UNMODIFIED /root/reference/src/ORBextractor.cc (bump-allocator build)
   sincos.json        result of the exhaustive oc_cosf/oc_sinf == glibc cosf/sinf check
@@ -105,6 +107,46 @@ def prims2():
     print("prims2_cv2.npz", os.path.getsize(os.path.join(G, "prims2_cv2.npz")))
 
 
+def rectify_cameras():
+    """The cameras of the initUndistortRectifyMap fixtures: (name, K, D, R, P, (w, h)); seeded, also used by the tests."""
+    cams = [("euroc_left", synth.EUROC_LEFT["K"], synth.EUROC_LEFT["D"], synth.EUROC_LEFT["R"], synth.EUROC_LEFT["P"], (752, 480)),
+            ("euroc_right", synth.EUROC_RIGHT["K"], synth.EUROC_RIGHT["D"], synth.EUROC_RIGHT["R"], synth.EUROC_RIGHT["P"], (752, 480))]
+    rng = np.random.default_rng(7)
+    for t in range(12):
+        W, H = [(752, 480), (640, 480), (1241, 376), (320, 240)][t % 4]
+        f = rng.uniform(300, 900)
+        K = np.array([[f, 0, W / 2 + rng.uniform(-20, 20)], [0, f * rng.uniform(0.95, 1.05), H / 2 + rng.uniform(-20, 20)], [0, 0, 1]])
+        nd = [4, 5, 8, 12][t % 4]
+        D = np.zeros(nd); D[:2] = rng.uniform(-0.3, 0.3, 2); D[2:4] = rng.uniform(-0.005, 0.005, 2)
+        if nd >= 5: D[4] = rng.uniform(-0.1, 0.1)
+        if nd >= 8: D[5:8] = rng.uniform(-0.05, 0.05, 3)
+        if nd >= 12: D[8:12] = rng.uniform(-0.002, 0.002, 4)
+        R, _ = cv2.Rodrigues(rng.uniform(-0.02, 0.02, 3))
+        fp = f * rng.uniform(0.9, 1.0)
+        P = np.array([[fp, 0, W / 2 + rng.uniform(-5, 5), 0], [0, fp, H / 2 + rng.uniform(-5, 5), 0], [0, 0, 1, 0]])
+        cams.append((f"rand{t}", K, D, R, P, (W, H)))
+    cams.append(("small", cams[2][1] * np.array([[0.25, 1, 0.25], [1, 0.25, 0.25], [1, 1, 1]]), cams[2][2], cams[2][3],
+                 cams[2][4] * np.array([[0.25, 1, 0.25, 1], [1, 0.25, 0.25, 1], [1, 1, 1, 1]]), (188, 120)))
+    return cams
+
+
+def prims3():
+    out = {"cv2_version": np.array(cv2.__version__)}
+    for name, K, D, R, P, size in rectify_cameras():
+        m1, m2 = cv2.initUndistortRectifyMap(np.asarray(K, np.float64), np.asarray(D, np.float64), np.asarray(R, np.float64),
+                                             np.asarray(P, np.float64), size, cv2.CV_32FC1)
+        for k, v in (("K", K), ("D", D), ("R", R), ("P", P)):
+            out[f"{name}_{k}"] = np.asarray(v, np.float64)
+        out[f"{name}_size"] = np.array(size)
+        out[f"{name}_crc"] = np.array([zlib.crc32(m1.tobytes()), zlib.crc32(m2.tobytes())], np.int64)
+        if name.startswith("euroc"):
+            out[f"{name}_rows8_1"] = m1[::8].copy(); out[f"{name}_rows8_2"] = m2[::8].copy()
+        if name == "small":
+            out[f"{name}_map1"] = m1; out[f"{name}_map2"] = m2
+    np.savez_compressed(os.path.join(G, "prims3_cv2.npz"), **out)
+    print("prims3_cv2.npz", os.path.getsize(os.path.join(G, "prims3_cv2.npz")))
+
+
 def ref_cases():
     assert ob.ref_available() or True
     ob.build(force=True)
@@ -138,11 +180,15 @@ def sincos():
 
 
 if __name__ == "__main__":
+    if "--prims3-only" in sys.argv:
+        prims3()
+        sys.exit(0)
     if "--prims2-only" in sys.argv:
         prims2()
         sys.exit(0)
     prims()
     prims2()
+    prims3()
     ref_cases()
     if "--sincos" in sys.argv:
         sincos()
