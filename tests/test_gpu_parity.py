@@ -194,9 +194,10 @@ def test_hamming_full_size_properties():
         idx = np.where(take, gi, idx)
         best = np.minimum(best, pd1)
     assert np.array_equal(idx, a[0]) and np.array_equal(best, a[1]) and np.array_equal(second, a[2])
-    # a spot-check of 16 queries against the oracle over the full million
-    j1, e1, e2 = ob.hamming_top2(query[:16], train, nthreads=8)
-    assert np.array_equal(i1[:16], j1) and np.array_equal(d1[:16], e1) and np.array_equal(d2[:16], e2)
+    # against the oracle over the full million: the 8 duplicated-row queries (exact ties) and 248 more spread over the set
+    sel = np.concatenate([np.arange(8), np.linspace(8, 2047, 248).astype(np.int64)])
+    j1, e1, e2 = ob.hamming_top2(query[sel], train, nthreads=os.cpu_count() or 8)
+    assert np.array_equal(i1[sel], j1) and np.array_equal(d1[sel], e1) and np.array_equal(d2[sel], e2)
 
 
 def test_stereo_hamming_matches_oracle():
@@ -876,3 +877,46 @@ def test_raw_euroc_pairs_to_depth_in_one_call():
         assert np.array_equal(out["u_right"][i, :nl].view(np.uint32), ur.view(np.uint32)), f"mvuRight of pair {i}"
         assert np.array_equal(out["depth"][i, :nl].view(np.uint32), dp.view(np.uint32)), f"mvDepth of pair {i}"
         assert (ur >= 0).sum() > 0        # (the synthetic pair is not a physical EuRoC pair: few rows still line up after rectification)
+
+
+def test_euroc_stream_of_256_pairs_matches_the_oracle():
+    """BASELINE config 3 at test size: a seeded stream of 256 EuRoC stereo pairs through the batched, chunk-pipelined host call
+    (orbx_stereo_extract_batch; pairs shard by frame, so every pair is independent) — keypoints, descriptors, mvuRight and
+    mvDepth of EVERY pair against the oracle (Frame.cc:80-84, 547-788). 32 distinct synthetic pairs, each reused with eight
+    different gains so that all 256 pairs differ; the oracle runs pair-parallel on the host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from orb_slam2_commit_b200 import api, stereo_extract_host
+    c = _cfg("euroc")
+    W, H = c["width"], c["height"]
+    cfgargs = (c["nfeatures"], c["scale"], c["nlevels"], c["ini_th"], c["min_th"])
+    base = [synth.synth_stereo_pair(W, H, 300 + i) for i in range(32)]
+    n = 256
+    L = np.empty((n, H, W), np.uint8); R = np.empty((n, H, W), np.uint8)
+    for i in range(n):
+        g = 1.0 - 0.04 * (i // 32)
+        L[i] = np.clip(base[i % 32][0].astype(np.float32) * g + (i // 32), 0, 255).astype(np.uint8)
+        R[i] = np.clip(base[i % 32][1].astype(np.float32) * g + (i // 32), 0, 255).astype(np.uint8)
+    exL, exR = ORBextractor(*cfgargs), ORBextractor(*cfgargs)
+    cap = exL.reserve(W, H, 64); exR.reserve(W, H, 64)
+    out = dict(kl=np.zeros((n, cap), api.KP_DTYPE), kr=np.zeros((n, cap), api.KP_DTYPE), dl=np.zeros((n, cap, 32), np.uint8),
+               dr=np.zeros((n, cap, 32), np.uint8), nl=np.zeros(n, np.int32), nr=np.zeros(n, np.int32),
+               u_right=np.zeros((n, cap), np.float32), depth=np.zeros((n, cap), np.float32))
+    stereo_extract_host(exL, exR, L, R, c["bf"], c["fx"], out)
+
+    def oracle_pair(i):
+        oL, oR = ob.Extractor(*cfgargs), ob.Extractor(*cfgargs)
+        k1, d1 = oL.extract(L[i]); k2, d2 = oR.extract(R[i])
+        ur, dp = ob.stereo_match(oL, oR, k1, d1, k2, d2, c["bf"], c["fx"])
+        return k1, d1, k2, d2, ur, dp
+    with ThreadPoolExecutor(os.cpu_count() or 8) as pool:
+        want = list(pool.map(oracle_pair, range(n)))
+    matched = 0
+    for i, (k1, d1, k2, d2, ur, dp) in enumerate(want):
+        nl, nr = int(out["nl"][i]), int(out["nr"][i])
+        assert nl == len(k1) and nr == len(k2), f"pair {i}"
+        _check_against(out["kl"][i, :nl], out["dl"][i, :nl], k1, d1, f"left {i}")
+        _check_against(out["kr"][i, :nr], out["dr"][i, :nr], k2, d2, f"right {i}")
+        assert np.array_equal(out["u_right"][i, :nl].view(np.uint32), ur.view(np.uint32)), f"mvuRight of pair {i}"
+        assert np.array_equal(out["depth"][i, :nl].view(np.uint32), dp.view(np.uint32)), f"mvDepth of pair {i}"
+        matched += int((ur >= 0).sum())
+    assert matched > 100 * n
