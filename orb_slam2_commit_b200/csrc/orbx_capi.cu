@@ -23,6 +23,8 @@ struct orbx_extractor {
     int max_tile_w = 0, max_tile_h = 0;
     OrbxFrameLayout L{};
     OrbxTmaps tm_fast{}, tm_desc{};               // per-level tensor maps of the raw pyramid (TMA staging of FAST tiles / describe patches)
+    OrbxTmaps tm_pyr{};                           // m[l] describes level l-1 with the source box of level l's resize tiles
+    std::vector<int> pyr_tiles; int* d_pyr_tiles = nullptr;
     // device memory
     void* d_pool = nullptr;                       // one allocation carved into the arrays of L
     OrbxLevelGeom* d_lvl = nullptr;
@@ -77,8 +79,17 @@ struct orbx_extractor {
 
 // ---- TMA descriptors (orbx_tma.cuh). cuTensorMapEncodeTiled is a driver-API symbol: fetched through the runtime so that
 // the library does not link libcuda and still loads on a machine without a driver (tests/test_abi.py).
+bool orbx_encode_level_maps_wh(OrbxTmaps* out, const OrbxLevelGeom* lvl, int nlevels, uint8_t* raw, size_t frame_raw_bytes,
+                               int frames, const int* box_w, const int* box_h, const char** err);
 bool orbx_encode_level_maps(OrbxTmaps* out, const OrbxLevelGeom* lvl, int nlevels, uint8_t* raw, size_t frame_raw_bytes,
                             int frames, int box_w, const int* box_h, const char** err)
+{
+    int bw[ORBX_MAX_LEVELS];
+    for (int l = 0; l < ORBX_MAX_LEVELS; l++) bw[l] = box_w;
+    return orbx_encode_level_maps_wh(out, lvl, nlevels, raw, frame_raw_bytes, frames, bw, box_h, err);
+}
+bool orbx_encode_level_maps_wh(OrbxTmaps* out, const OrbxLevelGeom* lvl, int nlevels, uint8_t* raw, size_t frame_raw_bytes,
+                               int frames, const int* box_w, const int* box_h, const char** err)
 {
     typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -99,7 +110,7 @@ bool orbx_encode_level_maps(OrbxTmaps* out, const OrbxLevelGeom* lvl, int nlevel
         // x = byte column of the level buffer, y = buffer row (apron included), z = frame of the working set
         const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)(g.h + 2 * ORBX_EDGE), (cuuint64_t)frames};
         const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)frame_raw_bytes};     // bytes, dims 1 and 2 (multiples of 16)
-        const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h[l], 1u};
+        const cuuint32_t box[3] = {(cuuint32_t)box_w[l], (cuuint32_t)box_h[l], 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         const CUresult r = encode(&out->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, raw + g.raw_off, dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -175,8 +186,8 @@ static void release_device(orbx_extractor* h)
     if (h->mirror) { cudaFreeHost(h->mirror); h->mirror = nullptr; h->mirror_bytes = 0; } h->mirror_frame = -1;
     cudaFree(h->stereo_scratch); h->stereo_scratch = nullptr; h->stereo_scratch_bytes = 0;
     cudaFree(h->stereo_out); h->stereo_out = nullptr; h->stereo_out_floats = 0;
-    cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps);
-    h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr;
+    cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps); cudaFree(h->d_pyr_tiles);
+    h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr; h->d_pyr_tiles = nullptr;
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
     h->d_in = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_nkp = nullptr; h->d_in_bytes = 0;
     h->W = h->H = h->max_batch = 0;
@@ -241,7 +252,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
     if (W > ORBX_MAX_DIM || H > ORBX_MAX_DIM) return fail(ORBX_ERR_UNSUPPORTED, "image larger than 4096 px");
     const int nl = h->nlevels;
     h->lvl.assign(nl, OrbxLevelGeom{});
-    h->cells.clear(); h->taps.clear();
+    h->cells.clear(); h->taps.clear(); h->pyr_tiles.clear();
     size_t raw = 0; int slot = 0, cand = 0, kpc = 0, qtcap = 0, hist_ints = 0;
     h->max_tile_w = h->max_tile_h = 8;
     for (int l = 0; l < nl; l++) {
@@ -318,6 +329,10 @@ static int build_geometry(orbx_extractor* h, int W, int H)
             build_taps(h->lvl[l - 1].w, g.w, h->taps.data() + g.xtab_off);
             g.ytab_off = g.xtab_off + g.w;
             build_taps(h->lvl[l - 1].h, g.h, h->taps.data() + g.ytab_off);
+            g.resize_fast = orbx_pyr_fast_ok(g, h->taps.data()) ? 1 : 0;
+            g.pyr_tile_off = (int)h->pyr_tiles.size();
+            orbx_pyr_tiles(g, h->taps.data(), h->pyr_tiles, &g.pyr_box_w, &g.pyr_box_h, &g.pyr_ntx, &g.pyr_nty);
+            if (g.pyr_box_w > 256 || g.pyr_box_h > 256) g.resize_fast = 0;       // TMA box limit (scale factors above ~1.7)
         } else g.ytab_off = g.xtab_off;
     }
     OrbxFrameLayout& L = h->L;
@@ -374,7 +389,9 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     CK(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice));
     if (!h->taps.empty())
         CK(cudaMemcpy(h->d_taps, h->taps.data(), h->taps.size() * sizeof(OrbxResizeTap), cudaMemcpyHostToDevice));
-    L.lvl = h->d_lvl; L.cells = h->d_cells; L.taps = h->d_taps;
+    CK(cudaMalloc(&h->d_pyr_tiles, std::max<size_t>(h->pyr_tiles.size(), 2) * sizeof(int)));
+    if (!h->pyr_tiles.empty()) CK(cudaMemcpy(h->d_pyr_tiles, h->pyr_tiles.data(), h->pyr_tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+    L.lvl = h->d_lvl; L.cells = h->d_cells; L.taps = h->d_taps; L.pyr_tiles = h->d_pyr_tiles;
     {
         int box_h[ORBX_MAX_LEVELS], box_d[ORBX_MAX_LEVELS];
         for (int l = 0; l < h->nlevels; l++) { box_h[l] = h->cells[h->lvl[l].cell0].box_h; box_d[l] = 43; }
@@ -382,6 +399,17 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
         if (!orbx_encode_level_maps(&h->tm_fast, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch,
                                     orbx_fast_tile_pitch(h->max_tile_w), box_h, &why) ||
             !orbx_encode_level_maps(&h->tm_desc, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch, 64, box_d, &why))
+            return fail(ORBX_ERR_CUDA, why ? why : "cuTensorMapEncodeTiled failed");
+        // the resize tiles of level l read level l-1: describe the source levels, shifted by one, each with its own box
+        std::vector<OrbxLevelGeom> src(h->nlevels, h->lvl[0]);
+        int pbw[ORBX_MAX_LEVELS], pbh[ORBX_MAX_LEVELS];
+        bool any = false;
+        for (int l = 0; l < h->nlevels; l++) {
+            src[l] = h->lvl[l > 0 ? l - 1 : 0];
+            const bool on = l > 0 && h->lvl[l].resize_fast;
+            pbw[l] = on ? h->lvl[l].pyr_box_w : 16; pbh[l] = on ? h->lvl[l].pyr_box_h : 1; any = any || on;
+        }
+        if (any && !orbx_encode_level_maps_wh(&h->tm_pyr, src.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch, pbw, pbh, &why))
             return fail(ORBX_ERR_CUDA, why ? why : "cuTensorMapEncodeTiled failed");
     }
     // staging for the host entry points
@@ -420,7 +448,7 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     const bool tm = h->timing;
     cudaEvent_t* ev = h->ev[h->runs % orbx_extractor::RING];
     if (tm) cudaEventRecord(ev[0], st);
-    orbx_launch_pyramid(Lb, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st, channels, rgb,
+    orbx_launch_pyramid(Lb, h->tm_pyr, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st, channels, rgb,
                         rectify ? h->d_remap : nullptr, h->map_src_w, h->map_src_h);
     if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(Lb, h->tm_fast, h->max_tile_w, h->max_tile_h, n, st);

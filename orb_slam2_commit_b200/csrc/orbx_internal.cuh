@@ -39,6 +39,8 @@ struct OrbxLevelGeom {
     int kp_cap;               // capacity of the level's keypoint list
     int qt_depth;             // quadtree fast path: depth of the count pyramid (0 = always use the sweep path)
     int xtab_off, ytab_off;   // offsets into the resize coefficient tables (elements)
+    int resize_fast;          // every group of four outputs keeps its x-taps within 8 source bytes (orbx_pyr_fast_ok)
+    int pyr_tile_off, pyr_ntx, pyr_nty, pyr_box_w, pyr_box_h;   // resize tiles of this level: table offset (ints), grid, TMA box of level l-1
 };
 
 struct OrbxCell {             // one FAST cell (ORBextractor.cc:849-914); emission rectangle in payload coords
@@ -61,6 +63,7 @@ struct OrbxFrameLayout {      // everything the kernels need, passed by value
     const OrbxLevelGeom* lvl;       // device
     const OrbxCell* cells;          // device
     const OrbxResizeTap* taps;      // device
+    const int* pyr_tiles;           // device: source boxes of the resize tiles (orbx_pyr_tiles)
     uint8_t* raw;                   // [B]
     uint32_t* slots;                // [B][slot_total]
     int* cell_count;                // [B][ncells]
@@ -94,10 +97,13 @@ static inline void orbx_need_smem(F kernel, OrbxSmemMark& mark, size_t bytes)
 }
 
 // kernel launchers (implemented in the .cu files; all asynchronous on `st`)
-void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
+struct OrbxTmaps;               // orbx_tma.cuh: one tensor map per pyramid level
+void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxTmaps& maps, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
                          int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels = 1, int rgb = 0,
                          const uint2* d_remap = nullptr, int src_w = 0, int src_h = 0);
-struct OrbxTmaps;               // orbx_tma.cuh: one tensor map per pyramid level
+bool orbx_pyr_fast_ok(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps);
+#include <vector>
+void orbx_pyr_tiles(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::vector<int>& out, int* box_w, int* box_h, int* ntx, int* nty);
 void orbx_launch_fast(const OrbxFrameLayout& L, const OrbxTmaps& maps, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
 int orbx_fast_tile_pitch(int max_tile_w);
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);

@@ -7,6 +7,9 @@
 // needs no second pass. Arithmetic is OpenCV's fixed-point bilinear (11-bit coefficients, tables built on the host
 // in OpenCV's float/double sequence): bit-exact, integer only.
 #include "orbx_internal.cuh"
+#include "orbx_tma.cuh"
+#include <algorithm>
+#include <vector>
 
 #define PYR_TX 64
 #define PYR_TY 4
@@ -20,29 +23,42 @@ __device__ __forceinline__ int reflect101(int p, int len)
 
 #define PYR_RPT 8        // buffer rows per thread
 
-// level 0: copy of the input frame (+apron)
-__global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_kernel(OrbxFrameLayout L, const uint8_t* __restrict__ img, int stride,
+// level 0: copy of the input frame (+apron). Thread = 16 adjacent bytes of PYR_L0_ROWS buffer rows, written with one 128-bit
+// store per row. Groups that lie inside the payload and whose source is 16-byte aligned (frame base, stride) read with one
+// 128-bit load; the others (apron columns: BORDER_REFLECT_101, unaligned frames) gather bytes.
+#define PYR_L0_ROWS 4
+__global__ void __launch_bounds__(256) pyr_level0_kernel(OrbxFrameLayout L, const uint8_t* __restrict__ img, int stride,
                                                          size_t frame_pitch)
 {
-    const OrbxLevelGeom g = L.lvl[0];
-    const int t = blockIdx.x * PYR_TX + threadIdx.x;        // group of 4 buffer columns starting at column 12
-    const int rb0 = (blockIdx.y * PYR_TY + threadIdx.y) * PYR_RPT;
-    const int cb = 12 + 4 * t;
-    const int rows = g.h + 2 * ORBX_EDGE;
-    if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb0 >= rows) return;
-    int xr[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) xr[k] = reflect101(cb + k - ORBX_XOFF, g.w);
+    const OrbxLevelGeom* __restrict__ gp = L.lvl;
+    const int gw = gp->w, gh = gp->h, gpitch = gp->pitch;
+    const int cb = 16 * (blockIdx.x * 32 + threadIdx.x);     // buffer column of the group (columns 13..31 hold the left apron)
+    const int rb0 = (blockIdx.y * 8 + threadIdx.y) * PYR_L0_ROWS;
+    const int rows = gh + 2 * ORBX_EDGE;
+    if (cb >= ORBX_XOFF + gw + ORBX_EDGE || rb0 >= rows) return;
     const uint8_t* fimg = img + (size_t)blockIdx.z * frame_pitch;
-    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + gp->raw_off + (size_t)rb0 * gpitch + cb;
+    const bool vec = cb >= ORBX_XOFF && cb + 16 <= ORBX_XOFF + gw && ((reinterpret_cast<uintptr_t>(fimg) | (uintptr_t)stride) & 15) == 0;
+    if (vec) {
+        const uint8_t* src = fimg + (cb - ORBX_XOFF);
 #pragma unroll
-    for (int rr = 0; rr < PYR_RPT; rr++) {
+        for (int rr = 0; rr < PYR_L0_ROWS; rr++) {
+            if (rb0 + rr >= rows) break;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(rb0 + rr - ORBX_EDGE, gh) * stride));
+            *reinterpret_cast<uint4*>(dst + (size_t)rr * gpitch) = v;
+        }
+        return;
+    }
+    int xr[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) xr[k] = reflect101(min(max(cb + k, ORBX_XOFF - ORBX_EDGE), ORBX_XOFF + gw + ORBX_EDGE - 1) - ORBX_XOFF, gw);
+    for (int rr = 0; rr < PYR_L0_ROWS; rr++) {
         if (rb0 + rr >= rows) break;
-        const uint8_t* src = fimg + (size_t)reflect101(rb0 + rr - ORBX_EDGE, g.h) * stride;
-        uint32_t out = 0;
+        const uint8_t* src = fimg + (size_t)reflect101(rb0 + rr - ORBX_EDGE, gh) * stride;
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int k = 0; k < 4; k++) out |= (uint32_t)__ldg(src + xr[k]) << (8 * k);
-        *reinterpret_cast<uint32_t*>(dst + (size_t)rr * g.pitch) = out;
+        for (int k = 0; k < 16; k++) o[k >> 2] |= (uint32_t)__ldg(src + xr[k]) << (8 * (k & 3));
+        *reinterpret_cast<uint4*>(dst + (size_t)rr * gpitch) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -124,9 +140,9 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_level0_remap_kernel(OrbxF
 }
 
 // level l > 0 from level l-1. Each thread produces 4 adjacent bytes of PYR_RPT consecutive buffer rows.
-// Generic path (threads on the apron: reflected, non-monotonic x-taps): byte loads per tap. Kept out of line so that its
-// registers do not burden the fast path below.
-__device__ __noinline__ void pyr_resize_rows_generic(const OrbxResizeTap* __restrict__ xtab, const OrbxResizeTap* __restrict__ ytab,
+// Generic path: byte loads per tap. Used (as its own kernel) for levels where some group of four outputs spreads its x-taps
+// over more than 8 source bytes (scale factors above ~1.7), which the host finds out from the tap table.
+__device__ __forceinline__ void pyr_resize_rows_generic(const OrbxResizeTap* __restrict__ xtab, const OrbxResizeTap* __restrict__ ytab,
                                                      const int gw, const int gh, const int gpitch, const int spitch,
                                                      const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dst,
                                                      const int cb, const int rb0, const int rows)
@@ -158,12 +174,136 @@ __device__ __noinline__ void pyr_resize_rows_generic(const OrbxResizeTap* __rest
     }
 }
 
-// Fast path for threads whose four columns lie in the payload (no reflection): the eight x-taps of a source row sit
-// within 8 consecutive bytes, so each source row is three aligned 32-bit loads, two funnel shifts that bring byte
-// sx[0] to the front, two byte permutes that lay the (left, right) tap pairs of two outputs side by side, and one
-// 2-way dot product per output against the packed coefficient pair — instead of eight byte loads with 64-bit
-// address arithmetic.
-__global__ void __launch_bounds__(PYR_TX * PYR_TY, 8) pyr_resize_kernel(OrbxFrameLayout L, int level)
+// Fast path (all columns whose four x-taps lie within 8 consecutive source bytes — every thread at the reference's scale
+// factors, apron included: reflected columns give the same taps in descending order). A source row costs three aligned
+// 32-bit loads, two funnel shifts that bring the first tap to byte 0, two byte permutes that lay the (left, right) tap
+// pairs of two outputs side by side and one 2-way dot product (dp2a) per output against the packed coefficient pair.
+// HORIZONTAL RESULTS ARE SHARED BETWEEN OUTPUT ROWS: at a scale of 1.2 the source rows (s, s+1) of consecutive output rows
+// overlap — the next row's s is the previous row's s+1 five times out of six — so a thread that walks PYR_RRPT output rows
+// keeps the four horizontal sums of its last source row and computes 1.2 instead of 2 source rows per output row.
+// The vertical pass takes (b * (S >> 4)) >> 16 as one multiply-high against b << 16.
+// The kernel above the generic one: a CTA produces a PYR_TW x PYR_TH tile of the level buffer (apron included). ONE bulk
+// tensor copy (TMA, orbx_tma.cuh) brings the source rectangle the tile needs — all x-taps and both y-taps of every output,
+// found per tile column / tile row on the host (orbx_pyr_tiles) — from level l-1 into shared memory; the threads then work
+// from shared memory (the global-load version of this kernel sat at 48 % long-scoreboard stalls: two dependent L2 round
+// trips per output row). Thread = 4 adjacent output bytes x PYR_RRPT rows; the four horizontal sums of a source row are
+// shared between output rows: at a scale of 1.2 the rows (s, s+1) of consecutive outputs overlap — the next output's s is the
+// previous one's s+1 five times out of six — so a thread computes about 1.2 instead of 2 source rows per output row.
+#define PYR_TW 128       // tile width in bytes (32 threads x 4)
+#define PYR_RRPT 8       // output rows per thread
+#define PYR_TH (PYR_TY2 * PYR_RRPT)
+#define PYR_TY2 8        // thread rows per CTA
+__global__ void __launch_bounds__(32 * PYR_TY2, 5) pyr_resize_kernel(OrbxFrameLayout L, int level, const __grid_constant__ OrbxTmaps maps)
+{
+    extern __shared__ __align__(128) uint8_t pyr_smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const OrbxLevelGeom* __restrict__ gp = L.lvl + level;
+    const int gw = gp->w, gh = gp->h, gpitch = gp->pitch;
+    const int bw = gp->pyr_box_w;
+    const int2 tx0 = reinterpret_cast<const int2*>(L.pyr_tiles + gp->pyr_tile_off)[blockIdx.x];                 // (source buffer column of the box, -)
+    const int2 ty0 = reinterpret_cast<const int2*>(L.pyr_tiles + gp->pyr_tile_off)[gridDim.x + blockIdx.y];     // (source buffer row of the box, -)
+    uint8_t* tile = pyr_smem + ((128u - (orbx_smem_addr(pyr_smem) & 127u)) & 127u);
+    const uint32_t bar = orbx_smem_addr(&s_bar);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) {
+        orbx_mbar_init(bar, 1);
+        orbx_mbar_expect_tx(bar, (uint32_t)(bw * gp->pyr_box_h));
+        orbx_tma_load_3d(orbx_smem_addr(tile), &maps.m[level], tx0.x, ty0.x, L.frame0 + blockIdx.z, bar);
+    }
+    __syncthreads();                                         // the barrier is initialised before anyone waits on it
+    const int cb = 12 + PYR_TW * blockIdx.x + 4 * threadIdx.x;
+    const int rb0 = PYR_TH * blockIdx.y + threadIdx.y * PYR_RRPT;
+    const int rows = gh + 2 * ORBX_EDGE;
+    const bool live = cb < ORBX_XOFF + gw + ORBX_EDGE && rb0 < rows;
+    // taps are stored as (ofs, c0, c1, pad) shorts: one 64-bit load each; c0 | c1 << 16 is bytes 2..5. On the apron the
+    // reflected columns give the same taps in descending order: the window starts at the smallest offset either way.
+    unsigned cf[4];
+    int x[4];
+    const uint2* tp = reinterpret_cast<const uint2*>(L.taps + gp->xtab_off);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint2 tk = tp[reflect101(min(cb + k, ORBX_XOFF + gw + ORBX_EDGE - 1) - ORBX_XOFF, gw)];
+        x[k] = (short)(tk.x & 0xffff);
+        cf[k] = __byte_perm(tk.x, tk.y, 0x5432);
+    }
+    const int x0 = min(min(x[0], x[1]), min(x[2], x[3]));
+    const int d0 = x[0] - x0, d1 = x[1] - x0, d2 = x[2] - x0, d3 = x[3] - x0;
+    const int s8 = (x0 & 3) * 8;
+    const unsigned sel01 = (unsigned)(d0 | ((d0 + 1) << 4) | (d1 << 8) | ((d1 + 1) << 12));
+    const unsigned sel23 = (unsigned)(d2 | ((d2 + 1) << 4) | (d3 << 8) | ((d3 + 1) << 12));
+    // payload column x0 of the source = buffer column x0 + 32; the box starts at buffer column tx0.x (a multiple of 16)
+    const uint8_t* sb = tile + ((x0 + ORBX_XOFF - tx0.x) & ~3);
+    const uint2* ytab = reinterpret_cast<const uint2*>(L.taps + gp->ytab_off);
+    uint2 ty[PYR_RRPT];
+#pragma unroll
+    for (int rr = 0; rr < PYR_RRPT; rr++) ty[rr] = ytab[reflect101(min(rb0 + rr, rows - 1) - ORBX_EDGE, gh)];
+    orbx_mbar_wait(bar, 0);
+    if (!live) return;
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + gp->raw_off + (size_t)rb0 * gpitch + cb;
+    // (S >> 4) of the four outputs for one source row: three words from the thread's aligned window, two funnel shifts that
+    // bring the first tap to byte 0, two byte permutes that lay the (left, right) tap pairs of two outputs side by side, one
+    // 2-way dot product per output against the packed coefficient pair
+    auto hrow = [&](const int sy, unsigned (&t)[4]) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(sb + (sy + ORBX_EDGE - ty0.x) * bw);
+        const uint32_t u0 = p[0], u1 = p[1], u2 = p[2];
+        const uint32_t A0 = __funnelshift_r(u0, u1, s8), A1 = __funnelshift_r(u1, u2, s8);
+        const uint32_t q01 = __byte_perm(A0, A1, sel01), q23 = __byte_perm(A0, A1, sel23);
+        t[0] = __dp2a_lo(cf[0], q01, 0u) >> 4; t[1] = __dp2a_hi(cf[1], q01, 0u) >> 4;
+        t[2] = __dp2a_lo(cf[2], q23, 0u) >> 4; t[3] = __dp2a_hi(cf[3], q23, 0u) >> 4;
+    };
+    int have = -0x7fffffff;                                  // source row whose sums `tb` holds
+    unsigned ta[4], tb[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int rr = 0; rr < PYR_RRPT; rr++) {
+        if (rb0 + rr >= rows) break;
+        // rows sy and sy+1 of the source payload (buffer rows sy + 19, sy + 20); when sy is the last row its coefficient c1
+        // is 0 and row sy+1 is the (valid) apron row, so no clamp is needed — same for columns
+        const int sy = (int)(short)(ty[rr].x & 0xffff);
+        if (have == sy) {                                    // warp-uniform: a warp's lanes share their rows
+#pragma unroll
+            for (int k = 0; k < 4; k++) ta[k] = tb[k];
+        } else hrow(sy, ta);
+        hrow(sy + 1, tb);
+        have = sy + 1;
+        // ((b0 * (S0 >> 4)) >> 16) as one multiply-high against b0 << 16
+        const unsigned b0 = ty[rr].x & 0xffff0000u, b1 = ty[rr].y << 16;
+        unsigned v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (__umulhi(b0, ta[k]) + __umulhi(b1, tb[k]) + 2u) >> 2;
+        *reinterpret_cast<uint32_t*>(dst + rr * gpitch) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+    }
+}
+
+// Host: the source boxes of the resize tiles of level `g` (from level l-1 of size sw x sh): per tile column the 16-byte aligned
+// buffer column where its box starts, per tile row the buffer row; box_w / box_h = the largest extent any tile needs (+ the
+// alignment slack and the 12-byte windows the threads read). Layout of `out`: ntx int2 entries, then nty int2 entries.
+void orbx_pyr_tiles(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::vector<int>& out, int* box_w, int* box_h, int* ntx, int* nty)
+{
+    auto refl = [](int p, int len) { p = p < 0 ? -p : p; return p >= len ? 2 * (len - 1) - p : p; };
+    const int cols = ORBX_XOFF + g.w + ORBX_EDGE, rows = g.h + 2 * ORBX_EDGE;
+    *ntx = (cols - 12 + PYR_TW - 1) / PYR_TW; *nty = (rows + PYR_TH - 1) / PYR_TH;
+    int bw = 16, bh = 2;
+    for (int bx = 0; bx < *ntx; bx++) {
+        int lo = 1 << 30, hi = -1;
+        for (int c = 12 + PYR_TW * bx; c < std::min(12 + PYR_TW * (bx + 1), cols); c++) {
+            const int o = h_taps[g.xtab_off + refl(c - ORBX_XOFF, g.w)].ofs; lo = std::min(lo, o); hi = std::max(hi, o + 1);
+        }
+        const int start = (lo + ORBX_XOFF) & ~15;
+        bw = std::max(bw, ((hi + ORBX_XOFF) & ~3) + 12 - start);          // a thread reads three words from its aligned window start
+        out.push_back(start); out.push_back(0);
+    }
+    for (int by = 0; by < *nty; by++) {
+        int lo = 1 << 30, hi = -1;
+        for (int r = PYR_TH * by; r < std::min(PYR_TH * (by + 1), rows); r++) {
+            const int o = h_taps[g.ytab_off + refl(r - ORBX_EDGE, g.h)].ofs; lo = std::min(lo, o); hi = std::max(hi, o + 1);
+        }
+        bh = std::max(bh, hi - lo + 1);
+        out.push_back(lo + ORBX_EDGE); out.push_back(0);
+    }
+    *box_w = (bw + 15) & ~15; *box_h = bh;
+}
+
+__global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_generic_kernel(OrbxFrameLayout L, int level)
 {
     const OrbxLevelGeom g = L.lvl[level];
     const OrbxLevelGeom s = L.lvl[level - 1];
@@ -174,56 +314,23 @@ __global__ void __launch_bounds__(PYR_TX * PYR_TY, 8) pyr_resize_kernel(OrbxFram
     if (cb >= ORBX_XOFF + g.w + ORBX_EDGE || rb0 >= rows) return;
     const uint8_t* sbase = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + s.raw_off + ORBX_XOFF;
     uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + g.raw_off + (size_t)rb0 * g.pitch + cb;
-    // taps are stored as (ofs, c0, c1, pad) shorts: one 64-bit load each; c0 | c1 << 16 is bytes 2..5. On the apron the
-    // reflected columns give the same taps in descending order: the window starts at the smallest offset either way.
-    unsigned cf[4];
-    int x[4];
-    const uint2* tp = reinterpret_cast<const uint2*>(L.taps + g.xtab_off);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint2 tk = tp[reflect101(cb + k - ORBX_XOFF, g.w)];
-        x[k] = (short)(tk.x & 0xffff);
-        cf[k] = __byte_perm(tk.x, tk.y, 0x5432);
-    }
-    const int x0 = min(min(x[0], x[1]), min(x[2], x[3]));
-    const int d0 = x[0] - x0, d1 = x[1] - x0, d2 = x[2] - x0, d3 = x[3] - x0;
-    const bool fast = max(max(d0, d1), max(d2, d3)) <= 6;
-    const int ab = x0 & ~3, s8 = (x0 & 3) * 8;
-    const unsigned sel01 = (unsigned)(d0 | ((d0 + 1) << 4) | (d1 << 8) | ((d1 + 1) << 12));
-    const unsigned sel23 = (unsigned)(d2 | ((d2 + 1) << 4) | (d3 << 8) | ((d3 + 1) << 12));
-    if (!fast) {
-        pyr_resize_rows_generic(L.taps + g.xtab_off, L.taps + g.ytab_off, g.w, g.h, g.pitch, s.pitch, sbase, dst, cb, rb0, rows);
-        return;
-    }
-    const uint8_t* sb = sbase + ab;
-#pragma unroll
-    for (int rr = 0; rr < PYR_RPT; rr++) {
-        if (rb0 + rr >= rows) break;
-        const OrbxResizeTap ty = L.taps[g.ytab_off + reflect101(rb0 + rr - ORBX_EDGE, g.h)];
-        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(sb + (size_t)(ty.ofs + ORBX_EDGE) * s.pitch);
-        const uint32_t* p1 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p0) + s.pitch);
-        const int b0 = ty.c0, b1 = ty.c1;
-        const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
-        const uint32_t A0 = __funnelshift_r(u0, u1, s8), A1 = __funnelshift_r(u1, u2, s8);
-        const uint32_t B0 = __funnelshift_r(v0, v1, s8), B1 = __funnelshift_r(v1, v2, s8);
-        const uint32_t qa01 = __byte_perm(A0, A1, sel01), qa23 = __byte_perm(A0, A1, sel23);
-        const uint32_t qb01 = __byte_perm(B0, B1, sel01), qb23 = __byte_perm(B0, B1, sel23);
-        int S0[4], S1[4];
-        S0[0] = (int)__dp2a_lo(cf[0], qa01, 0u); S0[1] = (int)__dp2a_hi(cf[1], qa01, 0u);
-        S0[2] = (int)__dp2a_lo(cf[2], qa23, 0u); S0[3] = (int)__dp2a_hi(cf[3], qa23, 0u);
-        S1[0] = (int)__dp2a_lo(cf[0], qb01, 0u); S1[1] = (int)__dp2a_hi(cf[1], qb01, 0u);
-        S1[2] = (int)__dp2a_lo(cf[2], qb23, 0u); S1[3] = (int)__dp2a_hi(cf[3], qb23, 0u);
-        uint32_t out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int v = (((b0 * (S0[k] >> 4)) >> 16) + ((b1 * (S1[k] >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t)(v & 0xff) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)rr * g.pitch) = out;
-    }
+    pyr_resize_rows_generic(L.taps + g.xtab_off, L.taps + g.ytab_off, g.w, g.h, g.pitch, s.pitch, sbase, dst, cb, rb0, rows);
 }
 
-void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
+// true when every group of four adjacent buffer columns of level `g` (apron included) keeps its eight x-taps within 8
+// consecutive source bytes: the condition of the fast kernel
+bool orbx_pyr_fast_ok(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps)
+{
+    auto refl = [&](int p) { p = p < 0 ? -p : p; return p >= g.w ? 2 * (g.w - 1) - p : p; };
+    for (int cb = 12; cb < ORBX_XOFF + g.w + ORBX_EDGE; cb += 4) {
+        int lo = 1 << 30, hi = -1;
+        for (int k = 0; k < 4; k++) { const int x = h_taps[g.xtab_off + refl(cb + k - ORBX_XOFF)].ofs; lo = std::min(lo, x); hi = std::max(hi, x); }
+        if (hi - lo > 6) return false;
+    }
+    return true;
+}
+
+void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxTmaps& maps, const OrbxLevelGeom* h_lvl, const uint8_t* d_img, int w, int h,
                          int stride, size_t frame_pitch, int nframes, cudaStream_t st, int channels, int rgb,
                          const uint2* d_remap, int src_w, int src_h)
 {
@@ -236,7 +343,16 @@ void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxLevelGeom* h_lvl, c
         dim3 grid((groups + PYR_TX - 1) / PYR_TX, (rows + PYR_TY * PYR_RPT - 1) / (PYR_TY * PYR_RPT), nframes);
         if (l == 0 && d_remap) pyr_level0_remap_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, d_remap, src_w, src_h);
         else if (l == 0 && channels > 1) pyr_level0_color_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, channels, rgb);
-        else if (l == 0) pyr_level0_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch);
-        else pyr_resize_kernel<<<grid, block, 0, st>>>(L, l);
+        else if (l == 0) {
+            const int g16 = (ORBX_XOFF + g.w + ORBX_EDGE + 15) / 16;
+            pyr_level0_kernel<<<dim3((g16 + 31) / 32, (rows + 8 * PYR_L0_ROWS - 1) / (8 * PYR_L0_ROWS), nframes), dim3(32, 8), 0, st>>>(L, d_img, stride, frame_pitch);
+        }
+        else if (g.resize_fast) {
+            static OrbxSmemMark mk = {};
+            const size_t smem = (size_t)g.pyr_box_w * g.pyr_box_h + 128;
+            orbx_need_smem(pyr_resize_kernel, mk, smem);
+            pyr_resize_kernel<<<dim3(g.pyr_ntx, g.pyr_nty, nframes), dim3(32, PYR_TY2), smem, st>>>(L, l, maps);
+        }
+        else pyr_resize_generic_kernel<<<grid, block, 0, st>>>(L, l);
     }
 }
