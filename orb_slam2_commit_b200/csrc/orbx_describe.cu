@@ -6,17 +6,19 @@
 // shared-memory slot (cp.async.bulk.tensor through the level's tensor map, completion on the warp's mbarrier); then
 //   * IC_Angle: lane = column u in [-15,15], integer moments, warp-shuffle reduce, cv::fastAtan2 polynomial
 //     evaluated with un-contracted f32 mul/add (bit-equal to OpenCV's scalar path);
-//   * blur on demand: the reference blurs the whole level and then reads 512 points per keypoint; here the
-//     first pass of OpenCV's fixed-point kernel [18,34,48,56,48,34,18]/256 is applied to the patch (exact in 16 bits;
-//     taken vertically, see below) and the second pass ((sum + 2^15) >> 16) only at the 16 sample points each lane
-//     needs. Border
-//     handling is the level's own REFLECT_101, which is exactly what the 19-px apron in HBM holds;
+//   * blur of the patch only: the reference blurs the whole level and then reads 512 points per keypoint; here both passes
+//     of OpenCV's fixed-point kernel [18,34,48,56,48,34,18]/256 run on the 43x43 patch in shared memory (vertical pass
+//     exact in 16 bits, horizontal pass ((sum + 2^15) >> 16) to a 37x37 byte image that overwrites the raw patch), so a
+//     sample is ONE byte load — the kernel is bound by shared-memory wavefronts, and the on-demand form of the second pass
+//     (four random 32-bit loads per sample, 64 per lane) was more than half of them. Border handling is the level's own
+//     REFLECT_101, which is exactly what the 19-px apron in HBM holds;
 //   * rBRIEF: lane i builds descriptor byte i (8 tests); sample = center + cvRound(x*b+y*a, x*a-y*b) with
 //     un-contracted f32 and round-half-even; cos/sin are the glibc 2.39 cosf/sinf polynomials in f64
 //     (bit-equal to the host libm the oracle was pinned against, tests/golden/sincos.json).
 // No blurred pyramid is ever written to HBM.
 #include "orbx_internal.cuh"
 #include "orbx_tma.cuh"
+#include <type_traits>
 
 #ifndef DESC_WARPS
 #define DESC_WARPS 4         // warps (= keypoints) per CTA
@@ -25,7 +27,9 @@
 #define PWORDS 12        // 32-bit words of a staged patch row that the kernel works on (48 bytes: 43 + up to 3 of alignment)
 #define RPW 16           // pitch of the staged rows in words: the 64-byte TMA box (its origin must be 16-byte aligned)
 #define VROWS 37         // rows of the vertically blurred patch (patch rows 3..39 centred)
-#define VPW 24           // its pitch in 32-bit words: 48 u16 per row, one per byte of the staged 48-byte patch row
+#define VPW 25           // its pitch in 32-bit words: 48 u16 per row, one per byte of the staged 48-byte patch row, + 1 word: an odd
+                         // pitch puts the 32 rows the lanes of a step read in the second pass into 32 different banks
+#define BP 40            // pitch of the blurred 37x37 byte image (8 outputs per lane and step, 5 steps per row)
 
 __device__ uint32_t g_pattern32[256];    // the 512 (x,y) int8 sample points, four bytes per word
 __constant__ int c_umax[16];
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
                                                                     int* __restrict__ nkp)
 {
     __shared__ __align__(128) uint32_t s_raw[DESC_WARPS][RAW_SLOT_WORDS];
-    __shared__ __align__(16) uint32_t s_vb[DESC_WARPS][VROWS * VPW];
+    __shared__ __align__(16) uint32_t s_vb[DESC_WARPS][VROWS * VPW + 8];   // + 8: the last row's windows over-read by up to four words
     __shared__ __align__(8) unsigned long long s_bar[DESC_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // this lane's 16 sample points (32 int8 = two 128-bit words), fetched first so the latency hides behind staging;
@@ -192,7 +196,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     uint32_t* vb = s_vb[wid];
     if (lane < 30) {
         const int col = lane % 6, strip = lane / 6;
-        const int ro0 = min(strip * 8, VROWS - 8);               // strips 0,8,16,24,29 (the last two overlap)
+        // strips start at rows 0, 7, 14, 21, 29 (eight rows each, three rows computed twice): with the 16-word pitch of the
+        // staged rows, odd and even starts sit 16 banks apart, which takes the loads from 5-way to 3-way conflicts
+        const int ro0 = strip < 4 ? strip * 7 : VROWS - 8;
         // (the window starts at a word, not at an 8-byte boundary of the box: two 32-bit loads per row)
         const uint32_t* src = raw32 + ro0 * RPW + 2 * col;
         uint32_t E[7][4];
@@ -210,8 +216,54 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
             for (int q = 0; q < 4; q++)
                 o[q] = 18u * (E[j % 7][q] + E[(j + 6) % 7][q]) + 34u * (E[(j + 1) % 7][q] + E[(j + 5) % 7][q]) +
                        48u * (E[(j + 2) % 7][q] + E[(j + 4) % 7][q]) + 56u * E[(j + 3) % 7][q];
-            *reinterpret_cast<uint4*>(vb + (ro0 + j) * VPW + col * 4) = make_uint4(o[0], o[1], o[2], o[3]);
+            uint32_t* vo = vb + (ro0 + j) * VPW + col * 4;
+            vo[0] = o[0]; vo[1] = o[1]; vo[2] = o[2]; vo[3] = o[3];
         }
+    }
+    __syncwarp();
+
+    // ---- second (horizontal) pass, dense: blur[r][c] = (sum_t w_t * vb[r][sh + c + t] + 2^15) >> 16 for c in [0, 37); a lane
+    // takes 8 adjacent outputs of one row per step (185 units = 37 rows x 5 groups over 32 lanes), i.e. 14 contiguous u16 =
+    // eight word loads, four dp2a per output with the weight pairs laid out for the parity of its first tap (the parity of
+    // sh decides between the two instances, warp-uniform). Units run column-major, so a step's lanes read 32 rows of the odd-pitch
+    // vb at one column offset: conflict-free. The byte image overwrites the raw patch, which nobody reads
+    // any more (IC_Angle and the vertical pass are done).
+    uint8_t* blur = reinterpret_cast<uint8_t*>(slot32);
+    {
+        const uint32_t* vrow = vb + (sh >> 1);
+        auto hpass = [&](auto PARC) {
+            constexpr int PAR = decltype(PARC)::value;
+            for (int u = lane; u < VROWS * 5; u += 32) {
+                const int g8 = u / VROWS, r = u - VROWS * g8;      // column-major: the lanes of a step take (mostly) 32 consecutive rows
+                const uint32_t* h = vrow + r * VPW + 4 * g8;
+                uint32_t W[8];
+#pragma unroll
+                for (int i = 0; i < 7 + PAR; i++) W[i] = h[i];
+                if (PAR == 0) W[7] = 0u;
+                uint32_t acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int m = (PAR + j) >> 1;
+                    if ((PAR + j) & 1) {
+                        unsigned a_ = __dp2a_lo(W[m], 18u << 8, 32768u);
+                        a_ = __dp2a_lo(W[m + 1], 34u | (48u << 8), a_);
+                        a_ = __dp2a_lo(W[m + 2], 56u | (48u << 8), a_);
+                        acc[j] = __dp2a_lo(W[m + 3], 34u | (18u << 8), a_);
+                    } else {
+                        unsigned a_ = __dp2a_lo(W[m], 18u | (34u << 8), 32768u);
+                        a_ = __dp2a_lo(W[m + 1], 48u | (56u << 8), a_);
+                        a_ = __dp2a_lo(W[m + 2], 48u | (34u << 8), a_);
+                        acc[j] = __dp2a_lo(W[m + 3], 18u, a_);
+                    }
+                }
+                // byte 2 of every accumulator is the blurred pixel ((sum + 2^15) >> 16 < 256)
+                const uint32_t lo = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+                const uint32_t hi = __byte_perm(__byte_perm(acc[4], acc[5], 0x0062), __byte_perm(acc[6], acc[7], 0x0062), 0x5410);
+                *reinterpret_cast<uint2*>(blur + r * BP + 8 * g8) = make_uint2(lo, hi);
+            }
+        };
+        __syncwarp();
+        if (sh & 1) hpass(std::integral_constant<int, 1>{}); else hpass(std::integral_constant<int, 0>{});
     }
     __syncwarp();
 
@@ -220,6 +272,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     float a, b;
     dev_sincosf(__fmul_rn(angle, factorPI), &b, &a);
     const uint32_t patw[8] = {pat_lo.x, pat_lo.y, pat_lo.z, pat_lo.w, pat_hi.x, pat_hi.y, pat_hi.z, pat_hi.w};
+    const uint8_t* bc = blur + 18 * BP + 18;            // blurred pixel at the keypoint
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
@@ -230,16 +283,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
             const float px = (float)(signed char)(w >> (16 * e)), py = (float)(signed char)(w >> (16 * e + 8));
             const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            // horizontal pass at the sample point: u16 entries idx .. idx+6 of row iy+18 (byte position sh + 18 + ix of
-            // the staged row is patch column 21 + ix - 3), fetched as four words; the weights follow the parity of idx
-            const int idx = (iy + 18) * (2 * VPW) + (sh + 18 + ix);
-            const uint32_t* h = vb + (idx >> 1);
-            const bool odd = idx & 1;
-            unsigned acc = __dp2a_lo(h[0], odd ? (18u << 8) : (18u | (34u << 8)), 32768u);
-            acc = __dp2a_lo(h[1], odd ? (34u | (48u << 8)) : (48u | (56u << 8)), acc);
-            acc = __dp2a_lo(h[2], odd ? (56u | (48u << 8)) : (48u | (34u << 8)), acc);
-            acc = __dp2a_lo(h[3], odd ? (34u | (18u << 8)) : 18u, acc);
-            smp[e] = (int)(acc >> 16);
+            smp[e] = bc[iy * BP + ix];
         }
         val |= (smp[0] < smp[1]) << t;
     }
