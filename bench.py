@@ -751,25 +751,37 @@ def run_matchers(args, torch, dist, rank, world, local, dev):
     emit_json_line(line)
 
 
-def h2d_ceiling_gbs(torch, dist, host_batch, dev, world, reps=8):
+def h2d_ceiling_gbs(torch, dist, host_batch, dev, world, reps=8, d2h_bytes=0):
     """What the box can feed: every rank copies its own pinned batch to its GPU at the same time, no kernels running
-    (cudaMemcpyAsync on one stream, `reps` copies back to back); aggregate GB/s = world x bytes x reps / max-over-ranks time."""
+    (cudaMemcpyAsync on one stream, `reps` copies back to back); aggregate GB/s = world x bytes x reps / max-over-ranks time.
+    With d2h_bytes > 0 a second stream copies that many bytes per rep back into pinned memory at the same time (the results of
+    a step flow back while the next frames go up): returns (h2d-only GB/s, duplex total GB/s)."""
     dst = torch.empty_like(host_batch, device=dev)
-    st = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(st):
-        dst.copy_(host_batch, non_blocking=True)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(st):
-        for _ in range(reps):
+    st = torch.cuda.Stream(device=dev); st2 = torch.cuda.Stream(device=dev)
+    back_d = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=dev)
+    back_h = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, pin_memory=True)
+
+    def run(duplex):
+        with torch.cuda.stream(st):
             dst.copy_(host_batch, non_blocking=True)
-    st.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return world * host_batch.numel() * reps / float(t.item()) / 1e9
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(st):
+                dst.copy_(host_batch, non_blocking=True)
+            if duplex:
+                with torch.cuda.stream(st2):
+                    back_h.copy_(back_d, non_blocking=True)
+        st.synchronize(); st2.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    up = world * host_batch.numel() * reps / run(False) / 1e9
+    both = world * (host_batch.numel() + d2h_bytes) * reps / run(True) / 1e9 if d2h_bytes else None
+    return up, both
 
 
 def stereo_measure(wname, P, steps, warmup, torch, dist, rank, world, local, dev, distinct=None):
@@ -1094,7 +1106,7 @@ def main():
         del ex1
 
     # ---- what the box can feed: all ranks upload their pinned batch at once, no kernels (the e2e number is read against this)
-    ceiling_gbs = h2d_ceiling_gbs(torch, dist, host_batch, dev, world)
+    ceiling_gbs, duplex_gbs = h2d_ceiling_gbs(torch, dist, host_batch, dev, world, d2h_bytes=B * (cap * 60 + 4))
 
     # ---- configs 2 and 3 ride along on the default line: KITTI and EuRoC stereo pairs (two extractors + ComputeStereoMatches,
     # Frame.cc:80-84, 547-788), pairs sharded by frame over the ranks, short runs
@@ -1239,7 +1251,10 @@ def main():
                         "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps, "api": e2e_api,
                         "synchronous_call": {"value": e2e_sync_fps, "api": ("orbx_extract_batch_rectified" if rectify else "orbx_extract_batch") + ", one blocking call per step"},
                         "h2d_ceiling_gbs": ceiling_gbs, "h2d_gbs": e2e_fps * W * H / 1e9, "frac_of_h2d_ceiling": e2e_fps * W * H / 1e9 / ceiling_gbs,
-                        "h2d_ceiling_how": "all ranks copy their pinned input batch to their GPU concurrently, no kernels running (aggregate GB/s, max time over ranks)"},
+                        "h2d_ceiling_how": "all ranks copy their pinned input batch to their GPU concurrently, no kernels running (aggregate GB/s, max time over ranks)",
+                        "duplex_ceiling_gbs": duplex_gbs, "duplex_gbs": e2e_fps * (W * H + cap * 60 + 4) / 1e9,
+                        "frac_of_duplex_ceiling": e2e_fps * (W * H + cap * 60 + 4) / 1e9 / duplex_gbs,
+                        "duplex_ceiling_how": "the same with a second stream copying the step's result bytes (keypoints + descriptors + counts) back to pinned memory at the same time; both directions counted"},
                 "latency_single_frame_ms": lat_ms, "latency_single_frame_with_pyramid_ms": lat_pyr_ms,
                 "roofline": roofline, "stages": stages,
                 "pipeline": {"keypoints_per_frame": nkp_mean, "keypoints_per_s": frames_per_s * nkp_mean,

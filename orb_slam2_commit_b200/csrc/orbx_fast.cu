@@ -32,8 +32,8 @@ struct FastSmemCfg { int list_cap, score_off, score_bytes, list_off, bar_off, pe
 // sg = +1 scores arcs of DARKER pixels (A = max_k min d), sg = -1 arcs of BRIGHTER pixels (-B = max_k min(-d)).
 // Two ring pixels ride in one register: P[k] = (e[k] + 1000) | (e[k+8] + 1000) << 16 (the bias keeps both halves
 // positive, so each P[k] is two exact multiply-adds and needs no packing step), and the sliding-window minimum
-// (log-step doubling: windows of 2, 4, then 4+4+4 overlapping = 9) runs on the packed 16-bit min/max instructions of
-// sm_100a (VIMNMX.S16x2 / VIMNMX3.S16x2). Index k+8 of a packed array is the same register with its halves swapped.
+// (windows of 3, then 3+3+3 = 9) runs on the packed 16-bit 3-input min/max instructions of sm_100a (VIMNMX3.S16x2).
+// Index k+8 of a packed array is the same register with its halves swapped.
 // NOTE: an earlier scalar version that folded the dark and the bright result into a single running accumulator was
 // mis-compiled by ptxas 12.9 for sm_100a (VIMNMX3 fusion) — tests/test_gpu_parity.py::test_stages_match_oracle pins
 // the scores.
@@ -44,38 +44,32 @@ __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ c, con
 {
     const unsigned mlo = (unsigned)(-sg), mhi = (unsigned)(-sg) << 16;
     const unsigned bias = (unsigned)(sg * v + 1000) * 0x10001u;
-    unsigned P[9], L2[10], L4[13];
+    unsigned P[10], W3[14], W9[8];
 #define ORBX_PK(j, off) P[j] = (unsigned)c[off] * mlo + ((unsigned)c[-(off)] * mhi + bias);
     ORBX_PK(0, 3 * tp) ORBX_PK(1, 3 * tp + 1) ORBX_PK(2, 2 * tp + 2) ORBX_PK(3, tp + 3)
     ORBX_PK(4, 3) ORBX_PK(5, -tp + 3) ORBX_PK(6, -2 * tp + 2) ORBX_PK(7, -3 * tp + 1)
 #undef ORBX_PK
-    P[8] = swap16(P[0]);
+    P[8] = swap16(P[0]); P[9] = swap16(P[1]);
+    // a window of nine = three windows of three: e[k..k+2], e[k+3..k+5], e[k+6..k+8] (3-input packed min, VIMNMX3.S16x2)
 #pragma unroll
-    for (int k = 0; k < 8; k++) L2[k] = __vmins2(P[k], P[k + 1]);
-    L2[8] = swap16(L2[0]); L2[9] = swap16(L2[1]);
+    for (int k = 0; k < 8; k++) W3[k] = __vimin3_s16x2(P[k], P[k + 1], P[k + 2]);
 #pragma unroll
-    for (int k = 0; k < 8; k++) L4[k] = __vmins2(L2[k], L2[k + 2]);
+    for (int k = 0; k < 6; k++) W3[8 + k] = swap16(W3[k]);
 #pragma unroll
-    for (int k = 0; k < 5; k++) L4[8 + k] = swap16(L4[k]);
-    unsigned lo9[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) lo9[k] = __vimin3_s16x2(L4[k], L4[k + 4], L4[k + 5]);   // e[k..k+3], e[k+4..k+7], e[k+5..k+8]
-    const unsigned m1 = __vimax3_s16x2(lo9[0], lo9[1], lo9[2]), m2 = __vimax3_s16x2(lo9[3], lo9[4], lo9[5]);
-    const unsigned m = __vmaxs2(__vimax3_s16x2(lo9[6], lo9[7], m1), m2);
+    for (int k = 0; k < 8; k++) W9[k] = __vimin3_s16x2(W3[k], W3[k + 3], W3[k + 6]);
+    const unsigned m1 = __vimax3_s16x2(W9[0], W9[1], W9[2]), m2 = __vimax3_s16x2(W9[3], W9[4], W9[5]);
+    const unsigned m = __vmaxs2(__vimax3_s16x2(W9[6], W9[7], m1), m2);
     int best = max((int)(m & 0xffffu), (int)(m >> 16)) - 1000;
     if (other) {
-        unsigned H2[10], H4[13], hi9[8];
+        unsigned H3[14], H9[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) H2[k] = __vmaxs2(P[k], P[k + 1]);
-        H2[8] = swap16(H2[0]); H2[9] = swap16(H2[1]);
+        for (int k = 0; k < 8; k++) H3[k] = __vimax3_s16x2(P[k], P[k + 1], P[k + 2]);
 #pragma unroll
-        for (int k = 0; k < 8; k++) H4[k] = __vmaxs2(H2[k], H2[k + 2]);
+        for (int k = 0; k < 6; k++) H3[8 + k] = swap16(H3[k]);
 #pragma unroll
-        for (int k = 0; k < 5; k++) H4[8 + k] = swap16(H4[k]);
-#pragma unroll
-        for (int k = 0; k < 8; k++) hi9[k] = __vimax3_s16x2(H4[k], H4[k + 4], H4[k + 5]);
-        const unsigned n1 = __vimin3_s16x2(hi9[0], hi9[1], hi9[2]), n2 = __vimin3_s16x2(hi9[3], hi9[4], hi9[5]);
-        const unsigned n = __vmins2(__vimin3_s16x2(hi9[6], hi9[7], n1), n2);
+        for (int k = 0; k < 8; k++) H9[k] = __vimax3_s16x2(H3[k], H3[k + 3], H3[k + 6]);
+        const unsigned n1 = __vimin3_s16x2(H9[0], H9[1], H9[2]), n2 = __vimin3_s16x2(H9[3], H9[4], H9[5]);
+        const unsigned n = __vmins2(__vimin3_s16x2(H9[6], H9[7], n1), n2);
         best = max(best, 1000 - min((int)(n & 0xffffu), (int)(n >> 16)));
     }
     return best;
@@ -274,7 +268,8 @@ void orbx_launch_fast(const OrbxFrameLayout& L, const OrbxTmaps& maps, int max_t
     int dev = 0; cudaGetDevice(&dev); dev &= 63;
     if (best_pw[dev][variant] != cfg.per_warp) {
         int bw = 0, bfw = 4;
-        for (int fw = FAST_MAX_WARPS; fw >= 2; fw--) {
+        const char* fwe = getenv("ORBX_FAST_WARPS");
+        for (int fw = fwe ? atoi(fwe) : FAST_MAX_WARPS; fw >= (fwe ? atoi(fwe) : 2); fw--) {
             const size_t sm = (size_t)cfg.per_warp * fw + 128;
             orbx_need_smem(kern, mk[variant], sm);
             int nb = 0;
