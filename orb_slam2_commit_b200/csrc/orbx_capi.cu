@@ -4,6 +4,7 @@
 // No OpenCV, no torch, no CPU fallback: without a CUDA device every compute entry point fails with ORBX_ERR_CUDA.
 #include "orbx_capi_common.cuh"
 #include "orbx_tma.cuh"
+#include <nvtx3/nvToolsExt.h>      // header-only: loads the profiler's injection library at run time, a no-op without one
 
 #include <mutex>
 
@@ -447,19 +448,28 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     }
     const bool tm = h->timing;
     cudaEvent_t* ev = h->ev[h->runs % orbx_extractor::RING];
+    // NVTX ranges around the four launch groups (ORBX_NVTX=1): they show up in Nsight Systems / ncu --nvtx timelines
+    static const bool nvtx = getenv("ORBX_NVTX") != nullptr;
+    struct Range { bool on; explicit Range(bool o, const char* n) : on(o) { if (on) nvtxRangePushA(n); } ~Range() { if (on) nvtxRangePop(); } };
+    Range r_all(nvtx, "orbx extract (ORBextractor::operator())");
     if (tm) cudaEventRecord(ev[0], st);
+    if (nvtx) nvtxRangePushA("ComputePyramid");
     orbx_launch_pyramid(Lb, h->tm_pyr, h->lvl.data(), d_img, h->W, h->H, stride, frame_pitch, n, st, channels, rgb,
                         rectify ? h->d_remap : nullptr, h->map_src_w, h->map_src_h);
+    if (nvtx) { nvtxRangePop(); nvtxRangePushA("FAST cells"); }
     if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(Lb, h->tm_fast, h->max_tile_w, h->max_tile_h, n, st);
+    if (nvtx) { nvtxRangePop(); nvtxRangePushA("DistributeOctTree"); }
     if (tm) cudaEventRecord(ev[2], st);
     // small frames: 256-thread CTAs so that several (level, frame) trees share an SM and hide each other's barriers
     // ... unless there are so few trees that every one gets an SM to itself anyway (single frames): then the wide CTA
     // finishes a tree sooner
     const bool few = n * h->nlevels <= 148;
     orbx_launch_quadtree(Lb, n, ((size_t)h->W * h->H <= (size_t)1 << 20 && !few) ? 256 : 1024, st);
+    if (nvtx) { nvtxRangePop(); nvtxRangePushA("IC_Angle + blur + rBRIEF"); }
     if (tm) cudaEventRecord(ev[3], st);
     orbx_launch_describe(Lb, h->tm_desc, n, d_kps, d_desc, cap, d_nkp, st);
+    if (nvtx) nvtxRangePop();
     if (tm) cudaEventRecord(ev[4], st);
     if (tm) h->runs++;
     CK(cudaGetLastError());
