@@ -131,11 +131,19 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     const int frame = blockIdx.y;
     const int ord = blockIdx.x * DESC_WARPS + wid;      // keypoint ordinal inside the frame (level-major)
     const int* cnt = L.lvl_kp_count + (size_t)frame * L.nlevels;
-    int level = -1, k = 0, total = 0;
-    for (int l = 0; l < L.nlevels; l++) {
-        const int c = cnt[l];
-        if (level < 0 && ord < total + c) { level = l; k = ord - total; }
-        total += c;
+    // level of the ordinal: lane l holds the count of level l, a warp scan gives the running totals (nlevels <= 16)
+    int level = -1, k = 0, total;
+    {
+        const int c = lane < L.nlevels ? cnt[lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ord < incl);
+        total = __shfl_sync(0xffffffffu, incl, ORBX_MAX_LEVELS - 1);   // the scan spans 16 lanes
+        if (m) { level = __ffs(m) - 1; k = ord - __shfl_sync(0xffffffffu, incl - c, level); }
     }
     if (ord == 0 && lane == 0) nkp[frame] = total;
     if (level < 0 || ord >= cap) return;                 // warp-uniform

@@ -25,30 +25,41 @@ __device__ __forceinline__ int reflect101(int p, int len)
 
 // level 0: copy of the input frame (+apron). Thread = 16 adjacent bytes of PYR_L0_ROWS buffer rows, written with one 128-bit
 // store per row. Groups that lie inside the payload and whose source is 16-byte aligned (frame base, stride) read with one
-// 128-bit load; the others (apron columns: BORDER_REFLECT_101, unaligned frames) gather bytes.
+// 128-bit load: they are the "interior" CTAs (blockIdx.x < nxb_in, lane = group). The other groups (apron columns:
+// BORDER_REFLECT_101, or every group of an unaligned frame) gather bytes, ~15x the instructions — they are packed densely into
+// their own CTAs (blockIdx.x == nxb_in: thread -> (row quad, edge group) by division), so that no warp of the interior runs the
+// gather path for the sake of two lanes (with lane = group across the whole row every warp did: 155 k instead of 20 k
+// warp-instructions per VGA frame).
 #define PYR_L0_ROWS 4
 __global__ void __launch_bounds__(256) pyr_level0_kernel(OrbxFrameLayout L, const uint8_t* __restrict__ img, int stride,
-                                                         size_t frame_pitch)
+                                                         size_t frame_pitch, int nxb_in, int gi1, int n_edge)
 {
     const OrbxLevelGeom* __restrict__ gp = L.lvl;
     const int gw = gp->w, gh = gp->h, gpitch = gp->pitch;
-    const int cb = 16 * (blockIdx.x * 32 + threadIdx.x);     // buffer column of the group (columns 13..31 hold the left apron)
-    const int rb0 = (blockIdx.y * 8 + threadIdx.y) * PYR_L0_ROWS;
     const int rows = gh + 2 * ORBX_EDGE;
-    if (cb >= ORBX_XOFF + gw + ORBX_EDGE || rb0 >= rows) return;
     const uint8_t* fimg = img + (size_t)blockIdx.z * frame_pitch;
-    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + gp->raw_off + (size_t)rb0 * gpitch + cb;
-    const bool vec = cb >= ORBX_XOFF && cb + 16 <= ORBX_XOFF + gw && ((reinterpret_cast<uintptr_t>(fimg) | (uintptr_t)stride) & 15) == 0;
-    if (vec) {
+    if ((int)blockIdx.x < nxb_in) {
+        const int grp = 2 + blockIdx.x * 32 + threadIdx.x;
+        const int rb0 = (blockIdx.y * 8 + threadIdx.y) * PYR_L0_ROWS;
+        if (grp >= gi1 || rb0 >= rows) return;
+        const int cb = 16 * grp;
+        uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + gp->raw_off + (size_t)rb0 * gpitch + cb;
         const uint8_t* src = fimg + (cb - ORBX_XOFF);
+        uint4 v[PYR_L0_ROWS];
 #pragma unroll
-        for (int rr = 0; rr < PYR_L0_ROWS; rr++) {
-            if (rb0 + rr >= rows) break;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(rb0 + rr - ORBX_EDGE, gh) * stride));
-            *reinterpret_cast<uint4*>(dst + (size_t)rr * gpitch) = v;
-        }
+        for (int rr = 0; rr < PYR_L0_ROWS; rr++)
+            v[rr] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(min(rb0 + rr, rows - 1) - ORBX_EDGE, gh) * stride));
+#pragma unroll
+        for (int rr = 0; rr < PYR_L0_ROWS; rr++)
+            if (rb0 + rr < rows) *reinterpret_cast<uint4*>(dst + (size_t)rr * gpitch) = v[rr];
         return;
     }
+    const int t = blockIdx.y * 256 + threadIdx.y * 32 + threadIdx.x;
+    const int rq = t / n_edge, e = t - rq * n_edge;
+    const int rb0 = rq * PYR_L0_ROWS;
+    if (rb0 >= rows) return;
+    const int cb = 16 * (e < 2 ? e : gi1 + e - 2);           // buffer column of the group (columns 13..31 hold the left apron)
+    uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + gp->raw_off + (size_t)rb0 * gpitch + cb;
     int xr[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) xr[k] = reflect101(min(max(cb + k, ORBX_XOFF - ORBX_EDGE), ORBX_XOFF + gw + ORBX_EDGE - 1) - ORBX_XOFF, gw);
@@ -344,8 +355,12 @@ void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxTmaps& maps, const 
         if (l == 0 && d_remap) pyr_level0_remap_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, d_remap, src_w, src_h);
         else if (l == 0 && channels > 1) pyr_level0_color_kernel<<<grid, block, 0, st>>>(L, d_img, stride, frame_pitch, channels, rgb);
         else if (l == 0) {
-            const int g16 = (ORBX_XOFF + g.w + ORBX_EDGE + 15) / 16;
-            pyr_level0_kernel<<<dim3((g16 + 31) / 32, (rows + 8 * PYR_L0_ROWS - 1) / (8 * PYR_L0_ROWS), nframes), dim3(32, 8), 0, st>>>(L, d_img, stride, frame_pitch);
+            const int ngroups = (ORBX_XOFF + g.w + ORBX_EDGE + 15) / 16, rq = (rows + PYR_L0_ROWS - 1) / PYR_L0_ROWS;
+            const bool aligned = ((reinterpret_cast<uintptr_t>(d_img) | (uintptr_t)stride | (uintptr_t)frame_pitch) & 15) == 0;
+            const int gi1 = aligned ? std::max((ORBX_XOFF + g.w) / 16, 2) : 2;      // interior groups: [2, gi1)
+            const int n_edge = 2 + ngroups - gi1, nxb_in = (gi1 - 2 + 31) / 32;
+            const int gy = std::max(nxb_in ? (rq + 7) / 8 : 0, (rq * n_edge + 255) / 256);
+            pyr_level0_kernel<<<dim3(nxb_in + 1, gy, nframes), dim3(32, 8), 0, st>>>(L, d_img, stride, frame_pitch, nxb_in, gi1, n_edge);
         }
         else if (g.resize_fast) {
             static OrbxSmemMark mk = {};
