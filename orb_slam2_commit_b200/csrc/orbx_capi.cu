@@ -25,6 +25,9 @@ struct orbx_extractor {
     OrbxFrameLayout L{};
     OrbxTmaps tm_fast{}, tm_desc{};               // per-level tensor maps of the raw pyramid (TMA staging of FAST tiles / describe patches)
     OrbxTmaps tm_pyr{};                           // m[l] describes level l-1 with the source box of level l's resize tiles
+    OrbxTmaps tm_blur_src{}, tm_desc_blur{};      // raw pyramid with the blur units' boxes / blurred pyramid with the descriptor's box
+    std::vector<OrbxBlurUnit> blur_units; OrbxBlurUnit* d_blur_units = nullptr;
+    int blur_rows[ORBX_MAX_LEVELS] = {};          // output rows per blur unit of a level
     std::vector<int> pyr_tiles; int* d_pyr_tiles = nullptr;
     // device memory
     void* d_pool = nullptr;                       // one allocation carved into the arrays of L
@@ -187,8 +190,8 @@ static void release_device(orbx_extractor* h)
     if (h->mirror) { cudaFreeHost(h->mirror); h->mirror = nullptr; h->mirror_bytes = 0; } h->mirror_frame = -1;
     cudaFree(h->stereo_scratch); h->stereo_scratch = nullptr; h->stereo_scratch_bytes = 0;
     cudaFree(h->stereo_out); h->stereo_out = nullptr; h->stereo_out_floats = 0;
-    cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps); cudaFree(h->d_pyr_tiles);
-    h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr; h->d_pyr_tiles = nullptr;
+    cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps); cudaFree(h->d_pyr_tiles); cudaFree(h->d_blur_units);
+    h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr; h->d_pyr_tiles = nullptr; h->d_blur_units = nullptr;
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
     h->d_in = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_nkp = nullptr; h->d_in_bytes = 0;
     h->W = h->H = h->max_batch = 0;
@@ -253,7 +256,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
     if (W > ORBX_MAX_DIM || H > ORBX_MAX_DIM) return fail(ORBX_ERR_UNSUPPORTED, "image larger than 4096 px");
     const int nl = h->nlevels;
     h->lvl.assign(nl, OrbxLevelGeom{});
-    h->cells.clear(); h->taps.clear(); h->pyr_tiles.clear();
+    h->cells.clear(); h->taps.clear(); h->pyr_tiles.clear(); h->blur_units.clear();
     size_t raw = 0; int slot = 0, cand = 0, kpc = 0, qtcap = 0, hist_ints = 0;
     h->max_tile_w = h->max_tile_h = 8;
     for (int l = 0; l < nl; l++) {
@@ -280,6 +283,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
         g.raw_off = (int)raw;
         raw += (size_t)g.pitch * (g.h + 2 * ORBX_EDGE);
         raw = (raw + 255) & ~(size_t)255;
+        orbx_blur_units(g, l, h->blur_units, &h->blur_rows[l]);
         g.cell0 = (int)h->cells.size(); g.ncols = nCols; g.nrows = nRows;
         g.cand_off = cand;
         int lvl_slots = 0;
@@ -371,6 +375,7 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
     const size_t o_raw = carve(B * L.frame_raw_bytes);
+    const size_t o_blur = carve(B * L.frame_raw_bytes);
     const size_t o_slots = carve(B * L.slot_total * sizeof(uint32_t));
     const size_t o_cc = carve(B * L.ncells * sizeof(int));
     const size_t o_cand = carve(B * L.cand_total * sizeof(uint32_t));
@@ -380,7 +385,7 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     const size_t o_lkpc = carve(B * L.nlevels * sizeof(int));
     CK(cudaMalloc(&h->d_pool, off));
     uint8_t* base = (uint8_t*)h->d_pool;
-    L.raw = base + o_raw; L.slots = (uint32_t*)(base + o_slots); L.cell_count = (int*)(base + o_cc);
+    L.raw = base + o_raw; L.blur = base + o_blur; L.slots = (uint32_t*)(base + o_slots); L.cell_count = (int*)(base + o_cc);
     L.cand = (uint32_t*)(base + o_cand); L.cand_node = (uint16_t*)(base + o_node); L.cand_count = (int*)(base + o_candc);
     L.lvl_kp = (uint32_t*)(base + o_lkp); L.lvl_kp_count = (int*)(base + o_lkpc);
     CK(cudaMalloc(&h->d_lvl, h->lvl.size() * sizeof(OrbxLevelGeom)));
@@ -392,14 +397,18 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
         CK(cudaMemcpy(h->d_taps, h->taps.data(), h->taps.size() * sizeof(OrbxResizeTap), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->d_pyr_tiles, std::max<size_t>(h->pyr_tiles.size(), 2) * sizeof(int)));
     if (!h->pyr_tiles.empty()) CK(cudaMemcpy(h->d_pyr_tiles, h->pyr_tiles.data(), h->pyr_tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_blur_units, h->blur_units.size() * sizeof(OrbxBlurUnit)));
+    CK(cudaMemcpy(h->d_blur_units, h->blur_units.data(), h->blur_units.size() * sizeof(OrbxBlurUnit), cudaMemcpyHostToDevice));
     L.lvl = h->d_lvl; L.cells = h->d_cells; L.taps = h->d_taps; L.pyr_tiles = h->d_pyr_tiles;
     {
-        int box_h[ORBX_MAX_LEVELS], box_d[ORBX_MAX_LEVELS];
-        for (int l = 0; l < h->nlevels; l++) { box_h[l] = h->cells[h->lvl[l].cell0].box_h; box_d[l] = 43; }
+        int box_h[ORBX_MAX_LEVELS], box_d[ORBX_MAX_LEVELS], box_b[ORBX_MAX_LEVELS], box_s[ORBX_MAX_LEVELS];
+        for (int l = 0; l < h->nlevels; l++) { box_h[l] = h->cells[h->lvl[l].cell0].box_h; box_d[l] = 31; box_b[l] = 37; box_s[l] = h->blur_rows[l] + 6; }
         const char* why = nullptr;
         if (!orbx_encode_level_maps(&h->tm_fast, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch,
                                     orbx_fast_tile_pitch(h->max_tile_w), box_h, &why) ||
-            !orbx_encode_level_maps(&h->tm_desc, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch, 64, box_d, &why))
+            !orbx_encode_level_maps(&h->tm_desc, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch, 48, box_d, &why) ||
+            !orbx_encode_level_maps(&h->tm_desc_blur, h->lvl.data(), h->nlevels, L.blur, L.frame_raw_bytes, max_batch, 64, box_b, &why) ||
+            !orbx_encode_level_maps(&h->tm_blur_src, h->lvl.data(), h->nlevels, L.raw, L.frame_raw_bytes, max_batch, ORBX_BLUR_BOX_W, box_s, &why))
             return fail(ORBX_ERR_CUDA, why ? why : "cuTensorMapEncodeTiled failed");
         // the resize tiles of level l read level l-1: describe the source levels, shifted by one, each with its own box
         std::vector<OrbxLevelGeom> src(h->nlevels, h->lvl[0]);
@@ -438,6 +447,7 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     Lb.frame0 = base;
     if (base) {
         Lb.raw += (size_t)base * Lb.frame_raw_bytes;
+        Lb.blur += (size_t)base * Lb.frame_raw_bytes;
         Lb.slots += (size_t)base * Lb.slot_total;
         Lb.cell_count += (size_t)base * Lb.ncells;
         Lb.cand += (size_t)base * Lb.cand_total;
@@ -468,7 +478,8 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     orbx_launch_quadtree(Lb, n, ((size_t)h->W * h->H <= (size_t)1 << 20 && !few) ? 256 : 1024, st);
     if (nvtx) { nvtxRangePop(); nvtxRangePushA("IC_Angle + blur + rBRIEF"); }
     if (tm) cudaEventRecord(ev[3], st);
-    orbx_launch_describe(Lb, h->tm_desc, n, d_kps, d_desc, cap, d_nkp, st);
+    orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, st);
+    orbx_launch_describe(Lb, h->tm_desc, h->tm_desc_blur, n, d_kps, d_desc, cap, d_nkp, st);
     if (nvtx) nvtxRangePop();
     if (tm) cudaEventRecord(ev[4], st);
     if (tm) h->runs++;

@@ -2,34 +2,28 @@
 // computeOrientation/IC_Angle ORBextractor.cc:77-105,492-499, the per-level cv::GaussianBlur :1188-1190 and
 // computeOrbDescriptor :110-152, plus the coordinate scaling / output packing of operator() :1194-1209).
 //
-// One elected lane has the TMA unit copy the 64x43-byte box around the keypoint from the HBM pyramid into the warp's
-// shared-memory slot (cp.async.bulk.tensor through the level's tensor map, completion on the warp's mbarrier); then
+// One elected lane has the TMA unit copy two boxes around the keypoint into the warp's shared-memory slots
+// (cp.async.bulk.tensor through the level's tensor maps, completion on the warp's mbarrier): 48x31 bytes of the RAW level for
+// the orientation and 64x37 bytes of the BLURRED level (orbx_blur.cu) for the tests; then
 //   * IC_Angle: lane = column u in [-15,15], integer moments, warp-shuffle reduce, cv::fastAtan2 polynomial
 //     evaluated with un-contracted f32 mul/add (bit-equal to OpenCV's scalar path);
-//   * blur of the patch only: the reference blurs the whole level and then reads 512 points per keypoint; here both passes
-//     of OpenCV's fixed-point kernel [18,34,48,56,48,34,18]/256 run on the 43x43 patch in shared memory (vertical pass
-//     exact in 16 bits, horizontal pass ((sum + 2^15) >> 16) to a 37x37 byte image that overwrites the raw patch), so a
-//     sample is ONE byte load — the kernel is bound by shared-memory wavefronts, and the on-demand form of the second pass
-//     (four random 32-bit loads per sample, 64 per lane) was more than half of them. Border handling is the level's own
-//     REFLECT_101, which is exactly what the 19-px apron in HBM holds;
 //   * rBRIEF: lane i builds descriptor byte i (8 tests); sample = center + cvRound(x*b+y*a, x*a-y*b) with
-//     un-contracted f32 and round-half-even; cos/sin are the glibc 2.39 cosf/sinf polynomials in f64
-//     (bit-equal to the host libm the oracle was pinned against, tests/golden/sincos.json).
-// No blurred pyramid is ever written to HBM.
+//     un-contracted f32 and round-half-even, one byte load from the blurred box; cos/sin are the glibc 2.39 cosf/sinf
+//     polynomials in f64 (bit-equal to the host libm the oracle was pinned against, tests/golden/sincos.json).
+// Round 1 blurred the 43x43 patch inside this kernel (no blurred pyramid in HBM): 750 of its 1500 warp-instructions per
+// keypoint; the dense blur costs a third of that per frame.
 #include "orbx_internal.cuh"
 #include "orbx_tma.cuh"
-#include <type_traits>
 
 #ifndef DESC_WARPS
 #define DESC_WARPS 4         // warps (= keypoints) per CTA
 #endif
-#define PW 43            // patch width/height
-#define PWORDS 12        // 32-bit words of a staged patch row that the kernel works on (48 bytes: 43 + up to 3 of alignment)
-#define RPW 16           // pitch of the staged rows in words: the 64-byte TMA box (its origin must be 16-byte aligned)
-#define VROWS 37         // rows of the vertically blurred patch (patch rows 3..39 centred)
-#define VPW 25           // its pitch in 32-bit words: 48 u16 per row, one per byte of the staged 48-byte patch row, + 1 word: an odd
-                         // pitch puts the 32 rows the lanes of a step read in the second pass into 32 different banks
-#define BP 40            // pitch of the blurred 37x37 byte image (8 outputs per lane and step, 5 steps per row)
+#define RAW_W 48         // raw box: columns kx-15 .. kx+15 (+ up to 15 of alignment: the box origin is 16-byte aligned), rows ky-15 .. ky+15
+#define RAW_H 31
+#define BLR_W 64         // blurred box: columns kx-18 .. kx+18 (+ alignment), rows ky-18 .. ky+18
+#define BLR_H 37
+#define RAW_SLOT 1536    // 48 x 31 = 1488, padded to a multiple of 128 bytes (TMA destination alignment)
+#define BLR_SLOT 2432    // 64 x 37 = 2368
 
 __device__ uint32_t g_pattern32[256];    // the 512 (x,y) int8 sample points, four bytes per word
 __constant__ int c_umax[16];
@@ -115,13 +109,13 @@ __device__ __forceinline__ void dev_sincosf(const float y, float* sn, float* cs)
     *sn = __double2float_rn((n & 1) ? pc : ps);
 }
 
-#define RAW_SLOT_WORDS 704   // 64 x 43 bytes = 688 words, padded to a multiple of 128 bytes (TMA destination alignment)
-__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayout L, const __grid_constant__ OrbxTmaps maps,
+__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayout L, const __grid_constant__ OrbxTmaps maps_raw,
+                                                                    const __grid_constant__ OrbxTmaps maps_blur,
                                                                     OrbxKp28* __restrict__ kps, uint8_t* __restrict__ desc, int cap,
                                                                     int* __restrict__ nkp)
 {
-    __shared__ __align__(128) uint32_t s_raw[DESC_WARPS][RAW_SLOT_WORDS];
-    __shared__ __align__(16) uint32_t s_vb[DESC_WARPS][VROWS * VPW + 8];   // + 8: the last row's windows over-read by up to four words
+    __shared__ __align__(128) uint8_t s_raw[DESC_WARPS][RAW_SLOT];
+    __shared__ __align__(128) uint8_t s_blr[DESC_WARPS][BLR_SLOT];
     __shared__ __align__(8) unsigned long long s_bar[DESC_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // this lane's 16 sample points (32 int8 = two 128-bit words), fetched first so the latency hides behind staging;
@@ -151,23 +145,19 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     const uint32_t pk = L.lvl_kp[(size_t)frame * L.kp_cap_total + L.lvl_kp_off[level] + k];
     const int kx = pk & 0xfff, ky = (pk >> 12) & 0xfff, score = pk >> 24;
 
-    // ---- stage the raw patch: rows ky-21 .. ky+21 of the 64-byte box that starts at the 16-byte aligned column at or left
-    // of kx-21; the kernel then works on the 48-byte window that starts at the WORD holding column kx-21 (byte `sh` of it)
-    uint32_t* slot32 = s_raw[wid];
-    const int x0 = kx - 21 + ORBX_XOFF;
+    // ---- stage the two boxes: each starts at the 16-byte aligned column at or left of its window
+    const int xr = kx - 15 + ORBX_XOFF, xb = kx - 18 + ORBX_XOFF;
     {
         const uint32_t bar = orbx_smem_addr(&s_bar[wid]);
         if (lane == 0) {
             orbx_mbar_init(bar, 1);
-            orbx_mbar_expect_tx(bar, PW * RPW * 4);
-            orbx_tma_load_3d(orbx_smem_addr(slot32), &maps.m[level], x0 & ~15, ky - 21 + ORBX_EDGE, L.frame0 + frame, bar);
+            orbx_mbar_expect_tx(bar, RAW_W * RAW_H + BLR_W * BLR_H);
+            orbx_tma_load_3d(orbx_smem_addr(s_raw[wid]), &maps_raw.m[level], xr & ~15, ky - 15 + ORBX_EDGE, L.frame0 + frame, bar);
+            orbx_tma_load_3d(orbx_smem_addr(s_blr[wid]), &maps_blur.m[level], xb & ~15, ky - 18 + ORBX_EDGE, L.frame0 + frame, bar);
         }
         __syncwarp();                                    // the barrier is initialised before anyone waits on it
         orbx_mbar_wait(bar, 0);
     }
-    const uint32_t* raw32 = slot32 + ((x0 & 15) >> 2);   // row r of the window = raw32 + r * RPW, 12 words
-    const int sh = x0 & 3;
-    const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32) + sh;   // raw8[r*64 + c], c in [0,43)
 
     // ---- IC_Angle on the un-blurred level
     int m10 = 0, m01 = 0;
@@ -176,12 +166,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
         constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         const int u = lane - 15;
         const int au = u < 0 ? -u : u;
-        const uint8_t* ctr = raw8 + 21 * (RPW * 4) + 21 + u;
+        const uint8_t* ctr = s_raw[wid] + (xr & 15) + 15 * RAW_W + 15 + u;
         m10 = u * ctr[0];
 #pragma unroll
         for (int v = 1; v <= 15; v++) {
             if (au <= UMAX[v]) {
-                const int vp = ctr[v * (RPW * 4)], vm = ctr[-v * (RPW * 4)];
+                const int vp = ctr[v * RAW_W], vm = ctr[-v * RAW_W];
                 m10 += u * (vp + vm);
                 m01 += v * (vp - vm);
             }
@@ -194,93 +184,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     }
     const float angle = dev_fast_atan2((float)m01, (float)m10);
 
-    // ---- first pass of the fixed-point Gaussian on the patch, taken VERTICALLY: vb[ro][b] = sum_k w_k * row(ro+k)[b]
-    // for every byte position b of the staged 48-byte rows (exact in 16 bits). OpenCV runs the horizontal pass first,
-    // but neither pass rounds before the final (sum + 2^15) >> 16, so the order does not change the result; with the
-    // vertical pass first the seven taps a sample point needs afterwards are CONTIGUOUS in shared memory: four 32-bit
-    // loads instead of seven 16-bit ones (this kernel is bound by shared-memory wavefronts: sample reads hit random banks).
-    // Lane = (8-byte column) x (strip of 8 output rows): a 7-row window of byte pairs spread into 16-bit halves slides
-    // down the column, two outputs per 32-bit op (every sum stays below 2^16).
-    uint32_t* vb = s_vb[wid];
-    if (lane < 30) {
-        const int col = lane % 6, strip = lane / 6;
-        // strips start at rows 0, 7, 14, 21, 29 (eight rows each, three rows computed twice): with the 16-word pitch of the
-        // staged rows, odd and even starts sit 16 banks apart, which takes the loads from 5-way to 3-way conflicts
-        const int ro0 = strip < 4 ? strip * 7 : VROWS - 8;
-        // (the window starts at a word, not at an 8-byte boundary of the box: two 32-bit loads per row)
-        const uint32_t* src = raw32 + ro0 * RPW + 2 * col;
-        uint32_t E[7][4];
-        auto expand = [&](uint32_t (&e)[4], const uint32_t wx, const uint32_t wy) {
-            e[0] = __byte_perm(wx, 0, 0x4140); e[1] = __byte_perm(wx, 0, 0x4342);
-            e[2] = __byte_perm(wy, 0, 0x4140); e[3] = __byte_perm(wy, 0, 0x4342);
-        };
-#pragma unroll
-        for (int i = 0; i < 6; i++) expand(E[i], src[i * RPW], src[i * RPW + 1]);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            expand(E[(j + 6) % 7], src[(j + 6) * RPW], src[(j + 6) * RPW + 1]);
-            uint32_t o[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                o[q] = 18u * (E[j % 7][q] + E[(j + 6) % 7][q]) + 34u * (E[(j + 1) % 7][q] + E[(j + 5) % 7][q]) +
-                       48u * (E[(j + 2) % 7][q] + E[(j + 4) % 7][q]) + 56u * E[(j + 3) % 7][q];
-            uint32_t* vo = vb + (ro0 + j) * VPW + col * 4;
-            vo[0] = o[0]; vo[1] = o[1]; vo[2] = o[2]; vo[3] = o[3];
-        }
-    }
-    __syncwarp();
-
-    // ---- second (horizontal) pass, dense: blur[r][c] = (sum_t w_t * vb[r][sh + c + t] + 2^15) >> 16 for c in [0, 37); a lane
-    // takes 8 adjacent outputs of one row per step (185 units = 37 rows x 5 groups over 32 lanes), i.e. 14 contiguous u16 =
-    // eight word loads, four dp2a per output with the weight pairs laid out for the parity of its first tap (the parity of
-    // sh decides between the two instances, warp-uniform). Units run column-major, so a step's lanes read 32 rows of the odd-pitch
-    // vb at one column offset: conflict-free. The byte image overwrites the raw patch, which nobody reads
-    // any more (IC_Angle and the vertical pass are done).
-    uint8_t* blur = reinterpret_cast<uint8_t*>(slot32);
-    {
-        const uint32_t* vrow = vb + (sh >> 1);
-        auto hpass = [&](auto PARC) {
-            constexpr int PAR = decltype(PARC)::value;
-            for (int u = lane; u < VROWS * 5; u += 32) {
-                const int g8 = u / VROWS, r = u - VROWS * g8;      // column-major: the lanes of a step take (mostly) 32 consecutive rows
-                const uint32_t* h = vrow + r * VPW + 4 * g8;
-                uint32_t W[8];
-#pragma unroll
-                for (int i = 0; i < 7 + PAR; i++) W[i] = h[i];
-                if (PAR == 0) W[7] = 0u;
-                uint32_t acc[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int m = (PAR + j) >> 1;
-                    if ((PAR + j) & 1) {
-                        unsigned a_ = __dp2a_lo(W[m], 18u << 8, 32768u);
-                        a_ = __dp2a_lo(W[m + 1], 34u | (48u << 8), a_);
-                        a_ = __dp2a_lo(W[m + 2], 56u | (48u << 8), a_);
-                        acc[j] = __dp2a_lo(W[m + 3], 34u | (18u << 8), a_);
-                    } else {
-                        unsigned a_ = __dp2a_lo(W[m], 18u | (34u << 8), 32768u);
-                        a_ = __dp2a_lo(W[m + 1], 48u | (56u << 8), a_);
-                        a_ = __dp2a_lo(W[m + 2], 48u | (34u << 8), a_);
-                        acc[j] = __dp2a_lo(W[m + 3], 18u, a_);
-                    }
-                }
-                // byte 2 of every accumulator is the blurred pixel ((sum + 2^15) >> 16 < 256)
-                const uint32_t lo = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
-                const uint32_t hi = __byte_perm(__byte_perm(acc[4], acc[5], 0x0062), __byte_perm(acc[6], acc[7], 0x0062), 0x5410);
-                *reinterpret_cast<uint2*>(blur + r * BP + 8 * g8) = make_uint2(lo, hi);
-            }
-        };
-        __syncwarp();
-        if (sh & 1) hpass(std::integral_constant<int, 1>{}); else hpass(std::integral_constant<int, 0>{});
-    }
-    __syncwarp();
-
     // ---- steered rBRIEF: lane i -> descriptor byte i
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
     float a, b;
     dev_sincosf(__fmul_rn(angle, factorPI), &b, &a);
     const uint32_t patw[8] = {pat_lo.x, pat_lo.y, pat_lo.z, pat_lo.w, pat_hi.x, pat_hi.y, pat_hi.z, pat_hi.w};
-    const uint8_t* bc = blur + 18 * BP + 18;            // blurred pixel at the keypoint
+    const uint8_t* bc = s_blr[wid] + (xb & 15) + 18 * BLR_W + 18;   // blurred pixel at the keypoint
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
@@ -291,7 +200,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
             const float px = (float)(signed char)(w >> (16 * e)), py = (float)(signed char)(w >> (16 * e + 8));
             const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            smp[e] = bc[iy * BP + ix];
+            smp[e] = bc[iy * BLR_W + ix];
         }
         val |= (smp[0] < smp[1]) << t;
     }
@@ -310,10 +219,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
     }
 }
 
-void orbx_launch_describe(const OrbxFrameLayout& L, const OrbxTmaps& maps, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
-                          int* d_nkp, cudaStream_t st)
+void orbx_launch_describe(const OrbxFrameLayout& L, const OrbxTmaps& maps_raw, const OrbxTmaps& maps_blur, int nframes, OrbxKp28* d_kps,
+                          uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st)
 {
     int total_cap = L.kp_cap_total;
     dim3 grid((total_cap + DESC_WARPS - 1) / DESC_WARPS, nframes);
-    describe_kernel<<<grid, DESC_WARPS * 32, 0, st>>>(L, maps, d_kps, d_desc, cap, d_nkp);
+    describe_kernel<<<grid, DESC_WARPS * 32, 0, st>>>(L, maps_raw, maps_blur, d_kps, d_desc, cap, d_nkp);
 }

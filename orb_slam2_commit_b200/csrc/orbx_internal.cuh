@@ -1,6 +1,7 @@
 // orbx_internal.cuh — shared declarations of the sm_100a ORB front-end kernels (not part of the C ABI).
 //
 // HBM layout of one extractor instance (sized by orbx_reserve for W x H frames, B frames per call):
+//   blurred pyramid: a second block of the same geometry (orbx_blur.cu)
 //   raw pyramid   [B] frames x frame_raw_bytes; level l of a frame starts at lvl[l].raw_off and is
 //                 (h+38) rows of `pitch` bytes; the payload pixel (x,y) sits at row y+19, column x+ORBX_XOFF,
 //                 so payload rows start 32-byte aligned and the 19-px REFLECT_101 apron of the reference's
@@ -51,6 +52,14 @@ struct OrbxCell {             // one FAST cell (ORBextractor.cc:849-914); emissi
     int slot_cap;
 };
 
+struct OrbxBlurUnit {         // one warp's share of the dense Gaussian blur (orbx_blur.cu): 128 columns x `rows` rows of a level
+    short level;
+    short c0, r0;             // buffer column (a multiple of 16) and buffer row of the source box; outputs start at (c0 + 4, r0 + 3)
+    short rows;               // output rows (a multiple of 8, <= ORBX_BLUR_MAX_ROWS); the box has rows + 6
+};
+#define ORBX_BLUR_BOX_W 144   // 4 + 128 + 4 columns, rounded up to the TMA unit's 16-byte granule
+#define ORBX_BLUR_MAX_ROWS 32
+
 struct OrbxResizeTap {        // cv::resize INTER_LINEAR 8U coefficients for one destination coordinate
     short ofs, c0, c1, pad;
 };
@@ -65,6 +74,7 @@ struct OrbxFrameLayout {      // everything the kernels need, passed by value
     const OrbxResizeTap* taps;      // device
     const int* pyr_tiles;           // device: source boxes of the resize tiles (orbx_pyr_tiles)
     uint8_t* raw;                   // [B]
+    uint8_t* blur;                  // [B] GaussianBlur of every level, same geometry as `raw` (read by the descriptor kernel only)
     uint32_t* slots;                // [B][slot_total]
     int* cell_count;                // [B][ncells]
     uint32_t* cand;                 // [B][cand_total]
@@ -107,8 +117,10 @@ void orbx_pyr_tiles(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::ve
 void orbx_launch_fast(const OrbxFrameLayout& L, const OrbxTmaps& maps, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
 int orbx_fast_tile_pitch(int max_tile_w);
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);
-void orbx_launch_describe(const OrbxFrameLayout& L, const OrbxTmaps& maps, int nframes, OrbxKp28* d_kps, uint8_t* d_desc, int cap,
-                          int* d_nkp, cudaStream_t st);
+void orbx_blur_units(const OrbxLevelGeom& g, int level, std::vector<OrbxBlurUnit>& out, int* rows_per_unit);
+void orbx_launch_blur(const OrbxFrameLayout& L, const OrbxTmaps& maps, const OrbxBlurUnit* d_units, int nunits, int nframes, cudaStream_t st);
+void orbx_launch_describe(const OrbxFrameLayout& L, const OrbxTmaps& maps_raw, const OrbxTmaps& maps_blur, int nframes, OrbxKp28* d_kps,
+                          uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st);
 void orbx_upload_constants();  // pattern + umax tables
 
 #define ORBX_MAX_PEERS 16
