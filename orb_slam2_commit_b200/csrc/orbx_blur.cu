@@ -12,9 +12,10 @@
 // outermost 3 apron pixels are not written and never read: samples stay within 18 px of a keypoint that is at least 16 px
 // inside the level).
 //
-// ONE WARP PER UNIT of 128 columns x R rows (R <= 32 per level, a multiple of 8), all levels and frames in one launch, no
-// block barrier. One elected lane has the TMA unit copy the unit's 144 x (R + 6) source box into the warp's shared-memory
-// slot. Lane = 4 adjacent output bytes, walked top to bottom:
+// ONE HALF-WARP PER UNIT of 64 columns x R rows (R <= 32, even), all levels and frames in one launch, no block barrier (a
+// full-warp unit of 128 columns left 17 % of the lanes beyond the right edge of the levels; half-warp units 6 %). The two
+// halves of a warp take two consecutive units of the table — any two: each half has its own 80 x (R + 6) source box, copied
+// into its shared-memory slot by the TMA unit on the warp's mbarrier. Lane = 4 adjacent output bytes, walked top to bottom:
 //   horizontal: the 7 taps of each of the 4 outputs lie in 3 consecutive words (u0 u1 u2): 6 funnel shifts line them up, two
 //               4-way byte dot products (dp4a) per output against (18,34,48,56) and (48,34,18,0)            3.5 ops / pixel
 //   vertical:   the 16-bit sums of two consecutive rows are packed per column (one byte permute per pair); an output row is
@@ -25,7 +26,7 @@
 #include "orbx_tma.cuh"
 
 #define BLUR_WARPS 4
-#define BLUR_SLOT (ORBX_BLUR_BOX_W * (ORBX_BLUR_MAX_ROWS + 6) + 32)      // 144 x 38 = 5472 -> 5504 (multiple of 128)
+#define BLUR_SLOT (ORBX_BLUR_BOX_W * (ORBX_BLUR_MAX_ROWS + 6) + 32)      // 80 x 38 = 3040 -> 3072 (multiple of 128), one per half-warp
 #define BLUR_PW (ORBX_BLUR_BOX_W / 4)                                    // box pitch in words
 
 __global__ void __launch_bounds__(BLUR_WARPS * 32) blur_units_kernel(OrbxFrameLayout L, const OrbxBlurUnit* __restrict__ units, int nunits,
@@ -33,24 +34,27 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) blur_units_kernel(OrbxFrameLa
 {
     extern __shared__ __align__(128) uint8_t blur_smem[];
     __shared__ __align__(8) unsigned long long s_bar[BLUR_WARPS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int unit = blockIdx.x * BLUR_WARPS + wid, frame = blockIdx.y;
-    if (unit >= nunits) return;                                          // whole warp
-    const OrbxBlurUnit u = units[unit];
-    uint8_t* slot = blur_smem + ((128u - (orbx_smem_addr(blur_smem) & 127u)) & 127u) + (size_t)wid * BLUR_SLOT;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+    const int unit0 = 2 * (blockIdx.x * BLUR_WARPS + wid), frame = blockIdx.y;
+    if (unit0 >= nunits) return;                                         // whole warp
+    const bool have = unit0 + half < nunits;                             // an odd table leaves the last warp's upper half idle
+    const OrbxBlurUnit u = units[have ? unit0 + half : unit0];
+    uint8_t* slot = blur_smem + ((128u - (orbx_smem_addr(blur_smem) & 127u)) & 127u) + (size_t)(2 * wid + half) * BLUR_SLOT;
     const uint32_t bar = orbx_smem_addr(&s_bar[wid]);
+    const int rows_other = __shfl_xor_sync(0xffffffffu, (int)u.rows, 16);
+    const int rows_max = max((int)u.rows, rows_other);
     if (lane == 0) {
         orbx_mbar_init(bar, 1);
-        orbx_mbar_expect_tx(bar, (uint32_t)(ORBX_BLUR_BOX_W * (u.rows + 6)));
-        orbx_tma_load_3d(orbx_smem_addr(slot), &maps.m[u.level], u.c0, u.r0, L.frame0 + frame, bar);
+        orbx_mbar_expect_tx(bar, (uint32_t)(ORBX_BLUR_BOX_W * (u.rows + 6 + (unit0 + 1 < nunits ? rows_other + 6 : 0))));
     }
+    __syncwarp();                                                        // the barrier is initialised and armed before the copies and the wait
+    if (hl == 0 && have) orbx_tma_load_3d(orbx_smem_addr(slot), &maps.m[u.level], u.c0, u.r0, L.frame0 + frame, bar);
     const OrbxLevelGeom* __restrict__ gp = L.lvl + u.level;
     const int gpitch = gp->pitch, brows = gp->h + 2 * ORBX_EDGE;
-    const int col = u.c0 + 4 + 4 * lane;                                 // buffer column of the lane's first output byte
+    const int col = u.c0 + 4 + 4 * hl;                                   // buffer column of the lane's first output byte
     uint8_t* dst = L.blur + (size_t)frame * L.frame_raw_bytes + gp->raw_off + (size_t)(u.r0 + 3) * gpitch + col;
-    const bool live = col < gpitch;
-    const uint32_t* tw = reinterpret_cast<const uint32_t*>(slot) + lane;   // (u0, u1, u2) of box row i = tw[i * BLUR_PW + 0..2]
-    __syncwarp();                                                        // the barrier is initialised before anyone waits on it
+    const bool live = have && col < gpitch;
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(slot) + hl;     // (u0, u1, u2) of box row i = tw[i * BLUR_PW + 0..2]
     orbx_mbar_wait(bar, 0);
 
     const unsigned WA = 18u | (34u << 8) | (48u << 16) | (56u << 24), WB = 48u | (34u << 8) | (18u << 16);
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) blur_units_kernel(OrbxFrameLa
     pair(0); pair(1); pair(2);
 #pragma unroll
     for (int a = 0; a < ORBX_BLUR_MAX_ROWS / 2; a++) {
-        if ((a & 3) == 0 && 2 * a >= u.rows) break;                       // warp-uniform; rows is a multiple of 8
+        if (2 * a >= rows_max) break;                                     // warp-uniform
         pair(a + 3);
         const unsigned(&p0)[4] = P[a & 3], (&p1)[4] = P[(a + 1) & 3], (&p2)[4] = P[(a + 2) & 3], (&p3)[4] = P[(a + 3) & 3];
         unsigned e[4], o[4];
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) blur_units_kernel(OrbxFrameLa
         }
         const uint32_t we = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
         const uint32_t wo = __byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410);
-        const int r = u.r0 + 3 + 2 * a;
+        const int r = 2 * a < u.rows ? u.r0 + 3 + 2 * a : brows;
         if (live && r < brows) *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * a) * gpitch) = we;
         if (live && r + 1 < brows) *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * a + 1) * gpitch) = wo;
     }
@@ -99,10 +103,10 @@ void orbx_blur_units(const OrbxLevelGeom& g, int level, std::vector<OrbxBlurUnit
     const int r_first = ORBX_EDGE - 3, r_end = ORBX_EDGE + g.h + 2;      // first output row 16
     const int need = r_end - r_first;
     const int ny = (need + ORBX_BLUR_MAX_ROWS - 1) / ORBX_BLUR_MAX_ROWS;
-    const int R = std::min(ORBX_BLUR_MAX_ROWS, (((need + ny - 1) / ny) + 7) & ~7);
+    const int R = std::min(ORBX_BLUR_MAX_ROWS, (((need + ny - 1) / ny) + 1) & ~1);
     *rows_per_unit = R;
     for (int y = 0; y < ny; y++)
-        for (int c0 = c_first; c0 + 4 < c_end; c0 += 128) {
+        for (int c0 = c_first; c0 + 4 < c_end; c0 += 64) {
             OrbxBlurUnit u;
             u.level = (short)level; u.c0 = (short)c0; u.r0 = (short)(r_first - 3 + y * R); u.rows = (short)R;
             out.push_back(u);
@@ -112,7 +116,7 @@ void orbx_blur_units(const OrbxLevelGeom& g, int level, std::vector<OrbxBlurUnit
 void orbx_launch_blur(const OrbxFrameLayout& L, const OrbxTmaps& maps, const OrbxBlurUnit* d_units, int nunits, int nframes, cudaStream_t st)
 {
     static OrbxSmemMark mk = {};
-    const size_t smem = (size_t)BLUR_SLOT * BLUR_WARPS + 128;
+    const size_t smem = (size_t)BLUR_SLOT * 2 * BLUR_WARPS + 128;
     orbx_need_smem(blur_units_kernel, mk, smem);
-    blur_units_kernel<<<dim3((nunits + BLUR_WARPS - 1) / BLUR_WARPS, nframes), BLUR_WARPS * 32, smem, st>>>(L, d_units, nunits, maps);
+    blur_units_kernel<<<dim3((nunits + 2 * BLUR_WARPS - 1) / (2 * BLUR_WARPS), nframes), BLUR_WARPS * 32, smem, st>>>(L, d_units, nunits, maps);
 }

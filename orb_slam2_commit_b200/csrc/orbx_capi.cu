@@ -335,8 +335,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
             g.ytab_off = g.xtab_off + g.w;
             build_taps(h->lvl[l - 1].h, g.h, h->taps.data() + g.ytab_off);
             g.resize_fast = orbx_pyr_fast_ok(g, h->taps.data()) ? 1 : 0;
-            g.pyr_tile_off = (int)h->pyr_tiles.size();
-            orbx_pyr_tiles(g, h->taps.data(), h->pyr_tiles, &g.pyr_box_w, &g.pyr_box_h, &g.pyr_ntx, &g.pyr_nty);
+            orbx_pyr_tiles(g, h->taps.data(), h->pyr_tiles);
             if (g.pyr_box_w > 256 || g.pyr_box_h > 256) g.resize_fast = 0;       // TMA box limit (scale factors above ~1.7)
         } else g.ytab_off = g.xtab_off;
     }
@@ -469,6 +468,15 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     if (nvtx) { nvtxRangePop(); nvtxRangePushA("FAST cells"); }
     if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(Lb, h->tm_fast, h->max_tile_w, h->max_tile_h, n, st);
+    static const int blur_overlap = getenv("ORBX_BLUR_OVERLAP") ? atoi(getenv("ORBX_BLUR_OVERLAP")) : 0;   // experiment
+    static cudaStream_t side = nullptr; static cudaEvent_t fev[16][2]; static int fring = 0;
+    cudaEvent_t* fe = nullptr;
+    if (blur_overlap) {
+        if (!side) { cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking); for (auto& e : fev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); } }
+        fe = fev[fring++ & 15];
+        cudaEventRecord(fe[0], st); cudaStreamWaitEvent(side, fe[0], 0);
+        if (blur_overlap == 1) { orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, side); cudaEventRecord(fe[1], side); }
+    }
     if (nvtx) { nvtxRangePop(); nvtxRangePushA("DistributeOctTree"); }
     if (tm) cudaEventRecord(ev[2], st);
     // small frames: 256-thread CTAs so that several (level, frame) trees share an SM and hide each other's barriers
@@ -478,7 +486,9 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     orbx_launch_quadtree(Lb, n, ((size_t)h->W * h->H <= (size_t)1 << 20 && !few) ? 256 : 1024, st);
     if (nvtx) { nvtxRangePop(); nvtxRangePushA("IC_Angle + blur + rBRIEF"); }
     if (tm) cudaEventRecord(ev[3], st);
-    orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, st);
+    if (blur_overlap == 2) { orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, side); cudaEventRecord(fe[1], side); }
+    if (blur_overlap) cudaStreamWaitEvent(st, fe[1], 0);
+    else orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, st);
     orbx_launch_describe(Lb, h->tm_desc, h->tm_desc_blur, n, d_kps, d_desc, cap, d_nkp, st);
     if (nvtx) nvtxRangePop();
     if (tm) cudaEventRecord(ev[4], st);

@@ -42,6 +42,7 @@ struct OrbxLevelGeom {
     int xtab_off, ytab_off;   // offsets into the resize coefficient tables (elements)
     int resize_fast;          // every group of four outputs keeps its x-taps within 8 source bytes (orbx_pyr_fast_ok)
     int pyr_tile_off, pyr_ntx, pyr_nty, pyr_box_w, pyr_box_h;   // resize tiles of this level: table offset (ints), grid, TMA box of level l-1
+    int pyr_xg_off, pyr_yr_off;                                 // per column group / per buffer row thread tables (ints, orbx_pyr_tiles)
 };
 
 struct OrbxCell {             // one FAST cell (ORBextractor.cc:849-914); emission rectangle in payload coords
@@ -52,12 +53,12 @@ struct OrbxCell {             // one FAST cell (ORBextractor.cc:849-914); emissi
     int slot_cap;
 };
 
-struct OrbxBlurUnit {         // one warp's share of the dense Gaussian blur (orbx_blur.cu): 128 columns x `rows` rows of a level
+struct OrbxBlurUnit {         // one half-warp's share of the dense Gaussian blur (orbx_blur.cu): 64 columns x `rows` rows of a level
     short level;
     short c0, r0;             // buffer column (a multiple of 16) and buffer row of the source box; outputs start at (c0 + 4, r0 + 3)
-    short rows;               // output rows (a multiple of 8, <= ORBX_BLUR_MAX_ROWS); the box has rows + 6
+    short rows;               // output rows (even, <= ORBX_BLUR_MAX_ROWS); the box has rows + 6
 };
-#define ORBX_BLUR_BOX_W 144   // 4 + 128 + 4 columns, rounded up to the TMA unit's 16-byte granule
+#define ORBX_BLUR_BOX_W 80    // 4 + 64 + 4 columns, rounded up to the TMA unit's 16-byte granule
 #define ORBX_BLUR_MAX_ROWS 32
 
 struct OrbxResizeTap {        // cv::resize INTER_LINEAR 8U coefficients for one destination coordinate
@@ -113,7 +114,7 @@ void orbx_launch_pyramid(const OrbxFrameLayout& L, const OrbxTmaps& maps, const 
                          const uint2* d_remap = nullptr, int src_w = 0, int src_h = 0);
 bool orbx_pyr_fast_ok(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps);
 #include <vector>
-void orbx_pyr_tiles(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::vector<int>& out, int* box_w, int* box_h, int* ntx, int* nty);
+void orbx_pyr_tiles(OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::vector<int>& out);
 void orbx_launch_fast(const OrbxFrameLayout& L, const OrbxTmaps& maps, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
 int orbx_fast_tile_pitch(int max_tile_w);
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);

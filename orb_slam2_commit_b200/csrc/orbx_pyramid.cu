@@ -201,10 +201,15 @@ __device__ __forceinline__ void pyr_resize_rows_generic(const OrbxResizeTap* __r
 // shared between output rows: at a scale of 1.2 the rows (s, s+1) of consecutive outputs overlap — the next output's s is the
 // previous one's s+1 five times out of six — so a thread computes about 1.2 instead of 2 source rows per output row.
 #define PYR_TW 128       // tile width in bytes (32 threads x 4)
-#define PYR_RRPT 8       // output rows per thread
+#define PYR_RRPT 16      // output rows per thread
 #define PYR_TH (PYR_TY2 * PYR_RRPT)
-#define PYR_TY2 8        // thread rows per CTA
-__global__ void __launch_bounds__(32 * PYR_TY2, 5) pyr_resize_kernel(OrbxFrameLayout L, int level, const __grid_constant__ OrbxTmaps maps)
+#define PYR_TY2 4        // thread rows (warps) per CTA
+// Everything a thread needs about its four columns and about each of its rows is a pure function of the level geometry, so
+// the host lays it out once (orbx_pyr_tiles): per group of four buffer columns {word-aligned source column, funnel-shift
+// amount, the two byte-permute selectors, the four packed coefficient pairs} (two 128-bit loads), per buffer row {source row
+// x box pitch, b0 << 16, b1 << 16} (one 128-bit load, the same address for the whole warp) — reflections, clamps and selector
+// arithmetic were 30 % of the kernel's instructions when every thread derived them itself.
+__global__ void __launch_bounds__(32 * PYR_TY2, 8) pyr_resize_kernel(OrbxFrameLayout L, int level, const __grid_constant__ OrbxTmaps maps)
 {
     extern __shared__ __align__(128) uint8_t pyr_smem[];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(32 * PYR_TY2, 5) pyr_resize_kernel(OrbxFrameLa
     const int gw = gp->w, gh = gp->h, gpitch = gp->pitch;
     const int bw = gp->pyr_box_w;
     const int2 tx0 = reinterpret_cast<const int2*>(L.pyr_tiles + gp->pyr_tile_off)[blockIdx.x];                 // (source buffer column of the box, -)
-    const int2 ty0 = reinterpret_cast<const int2*>(L.pyr_tiles + gp->pyr_tile_off)[gridDim.x + blockIdx.y];     // (source buffer row of the box, -)
+    const int2 ty0 = reinterpret_cast<const int2*>(L.pyr_tiles + gp->pyr_tile_off)[gridDim.x + blockIdx.y];     // (source buffer row of the box, that row x box pitch)
     uint8_t* tile = pyr_smem + ((128u - (orbx_smem_addr(pyr_smem) & 127u)) & 127u);
     const uint32_t bar = orbx_smem_addr(&s_bar);
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -222,79 +227,67 @@ __global__ void __launch_bounds__(32 * PYR_TY2, 5) pyr_resize_kernel(OrbxFrameLa
         orbx_tma_load_3d(orbx_smem_addr(tile), &maps.m[level], tx0.x, ty0.x, L.frame0 + blockIdx.z, bar);
     }
     __syncthreads();                                         // the barrier is initialised before anyone waits on it
-    const int cb = 12 + PYR_TW * blockIdx.x + 4 * threadIdx.x;
+    const int gi = 32 * blockIdx.x + threadIdx.x;            // group of four buffer columns: cb = 12 + 4 * gi
+    const int cb = 12 + 4 * gi;
     const int rb0 = PYR_TH * blockIdx.y + threadIdx.y * PYR_RRPT;
     const int rows = gh + 2 * ORBX_EDGE;
     const bool live = cb < ORBX_XOFF + gw + ORBX_EDGE && rb0 < rows;
-    // taps are stored as (ofs, c0, c1, pad) shorts: one 64-bit load each; c0 | c1 << 16 is bytes 2..5. On the apron the
-    // reflected columns give the same taps in descending order: the window starts at the smallest offset either way.
-    unsigned cf[4];
-    int x[4];
-    const uint2* tp = reinterpret_cast<const uint2*>(L.taps + gp->xtab_off);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint2 tk = tp[reflect101(min(cb + k, ORBX_XOFF + gw + ORBX_EDGE - 1) - ORBX_XOFF, gw)];
-        x[k] = (short)(tk.x & 0xffff);
-        cf[k] = __byte_perm(tk.x, tk.y, 0x5432);
-    }
-    const int x0 = min(min(x[0], x[1]), min(x[2], x[3]));
-    const int d0 = x[0] - x0, d1 = x[1] - x0, d2 = x[2] - x0, d3 = x[3] - x0;
-    const int s8 = (x0 & 3) * 8;
-    const unsigned sel01 = (unsigned)(d0 | ((d0 + 1) << 4) | (d1 << 8) | ((d1 + 1) << 12));
-    const unsigned sel23 = (unsigned)(d2 | ((d2 + 1) << 4) | (d3 << 8) | ((d3 + 1) << 12));
-    // payload column x0 of the source = buffer column x0 + 32; the box starts at buffer column tx0.x (a multiple of 16)
-    const uint8_t* sb = tile + ((x0 + ORBX_XOFF - tx0.x) & ~3);
-    const uint2* ytab = reinterpret_cast<const uint2*>(L.taps + gp->ytab_off);
-    uint2 ty[PYR_RRPT];
-#pragma unroll
-    for (int rr = 0; rr < PYR_RRPT; rr++) ty[rr] = ytab[reflect101(min(rb0 + rr, rows - 1) - ORBX_EDGE, gh)];
+    const uint4* xg = reinterpret_cast<const uint4*>(L.pyr_tiles + gp->pyr_xg_off) + 2 * gi;
+    const uint4 xa = xg[0], xc = xg[1];                     // (source column, s8, sel01, sel23), coefficient pairs
+    const uint4* __restrict__ yr = reinterpret_cast<const uint4*>(L.pyr_tiles + gp->pyr_yr_off) + rb0;
+    const unsigned s8 = xa.y, sel01 = xa.z, sel23 = xa.w;
+    const uint8_t* sb = tile + ((int)xa.x - tx0.x) - ty0.y;  // + (source buffer row x box pitch) = the thread's window in that row
     orbx_mbar_wait(bar, 0);
     if (!live) return;
     uint8_t* dst = L.raw + (size_t)blockIdx.z * L.frame_raw_bytes + gp->raw_off + (size_t)rb0 * gpitch + cb;
     // (S >> 4) of the four outputs for one source row: three words from the thread's aligned window, two funnel shifts that
     // bring the first tap to byte 0, two byte permutes that lay the (left, right) tap pairs of two outputs side by side, one
     // 2-way dot product per output against the packed coefficient pair
-    auto hrow = [&](const int sy, unsigned (&t)[4]) {
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(sb + (sy + ORBX_EDGE - ty0.x) * bw);
+    auto hrow = [&](const int off, unsigned (&t)[4]) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(sb + off);
         const uint32_t u0 = p[0], u1 = p[1], u2 = p[2];
         const uint32_t A0 = __funnelshift_r(u0, u1, s8), A1 = __funnelshift_r(u1, u2, s8);
         const uint32_t q01 = __byte_perm(A0, A1, sel01), q23 = __byte_perm(A0, A1, sel23);
-        t[0] = __dp2a_lo(cf[0], q01, 0u) >> 4; t[1] = __dp2a_hi(cf[1], q01, 0u) >> 4;
-        t[2] = __dp2a_lo(cf[2], q23, 0u) >> 4; t[3] = __dp2a_hi(cf[3], q23, 0u) >> 4;
+        t[0] = __dp2a_lo(xc.x, q01, 0u) >> 4; t[1] = __dp2a_hi(xc.y, q01, 0u) >> 4;
+        t[2] = __dp2a_lo(xc.z, q23, 0u) >> 4; t[3] = __dp2a_hi(xc.w, q23, 0u) >> 4;
     };
-    int have = -0x7fffffff;                                  // source row whose sums `tb` holds
+    int have = -0x7fffffff;                                  // source row (x box pitch) whose sums `tb` holds
     unsigned ta[4], tb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int rr = 0; rr < PYR_RRPT; rr++) {
         if (rb0 + rr >= rows) break;
         // rows sy and sy+1 of the source payload (buffer rows sy + 19, sy + 20); when sy is the last row its coefficient c1
         // is 0 and row sy+1 is the (valid) apron row, so no clamp is needed — same for columns
-        const int sy = (int)(short)(ty[rr].x & 0xffff);
-        if (have == sy) {                                    // warp-uniform: a warp's lanes share their rows
+        const uint4 y = yr[rr];                              // (source row x box pitch, b0 << 16, b1 << 16, -)
+        const int off = (int)y.x;
+        if (have == off) {                                   // warp-uniform: a warp's lanes share their rows
 #pragma unroll
             for (int k = 0; k < 4; k++) ta[k] = tb[k];
-        } else hrow(sy, ta);
-        hrow(sy + 1, tb);
-        have = sy + 1;
+        } else hrow(off, ta);
+        hrow(off + bw, tb);
+        have = off + bw;
         // ((b0 * (S0 >> 4)) >> 16) as one multiply-high against b0 << 16
-        const unsigned b0 = ty[rr].x & 0xffff0000u, b1 = ty[rr].y << 16;
         unsigned v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (__umulhi(b0, ta[k]) + __umulhi(b1, tb[k]) + 2u) >> 2;
+        for (int k = 0; k < 4; k++) v[k] = (__umulhi(y.y, ta[k]) + __umulhi(y.z, tb[k]) + 2u) >> 2;
         *reinterpret_cast<uint32_t*>(dst + rr * gpitch) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
     }
 }
 
-// Host: the source boxes of the resize tiles of level `g` (from level l-1 of size sw x sh): per tile column the 16-byte aligned
-// buffer column where its box starts, per tile row the buffer row; box_w / box_h = the largest extent any tile needs (+ the
-// alignment slack and the 12-byte windows the threads read). Layout of `out`: ntx int2 entries, then nty int2 entries.
-void orbx_pyr_tiles(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::vector<int>& out, int* box_w, int* box_h, int* ntx, int* nty)
+// Host: the tables of the resize tiles of level `g` (from level l-1): per tile column the 16-byte aligned source buffer column
+// where its box starts, per tile row the source buffer row (and that row x box pitch); box_w / box_h = the largest extent any
+// tile needs (+ the alignment slack and the 12-byte windows the threads read); then the per-column-group and per-row thread
+// tables described above the kernel. Layout of `out` from g.pyr_tile_off: ntx int2, nty int2; from g.pyr_xg_off: 8 ints per
+// column group; from g.pyr_yr_off: 4 ints per buffer row (both 16-byte aligned, padded to whole tiles).
+void orbx_pyr_tiles(OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::vector<int>& out)
 {
     auto refl = [](int p, int len) { p = p < 0 ? -p : p; return p >= len ? 2 * (len - 1) - p : p; };
     const int cols = ORBX_XOFF + g.w + ORBX_EDGE, rows = g.h + 2 * ORBX_EDGE;
-    *ntx = (cols - 12 + PYR_TW - 1) / PYR_TW; *nty = (rows + PYR_TH - 1) / PYR_TH;
+    const int ntx = (cols - 12 + PYR_TW - 1) / PYR_TW, nty = (rows + PYR_TH - 1) / PYR_TH;
+    while (out.size() & 3) out.push_back(0);
+    g.pyr_tile_off = (int)out.size(); g.pyr_ntx = ntx; g.pyr_nty = nty;
     int bw = 16, bh = 2;
-    for (int bx = 0; bx < *ntx; bx++) {
+    for (int bx = 0; bx < ntx; bx++) {
         int lo = 1 << 30, hi = -1;
         for (int c = 12 + PYR_TW * bx; c < std::min(12 + PYR_TW * (bx + 1), cols); c++) {
             const int o = h_taps[g.xtab_off + refl(c - ORBX_XOFF, g.w)].ofs; lo = std::min(lo, o); hi = std::max(hi, o + 1);
@@ -303,7 +296,8 @@ void orbx_pyr_tiles(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::ve
         bw = std::max(bw, ((hi + ORBX_XOFF) & ~3) + 12 - start);          // a thread reads three words from its aligned window start
         out.push_back(start); out.push_back(0);
     }
-    for (int by = 0; by < *nty; by++) {
+    const size_t ytiles = out.size();
+    for (int by = 0; by < nty; by++) {
         int lo = 1 << 30, hi = -1;
         for (int r = PYR_TH * by; r < std::min(PYR_TH * (by + 1), rows); r++) {
             const int o = h_taps[g.ytab_off + refl(r - ORBX_EDGE, g.h)].ofs; lo = std::min(lo, o); hi = std::max(hi, o + 1);
@@ -311,7 +305,34 @@ void orbx_pyr_tiles(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::ve
         bh = std::max(bh, hi - lo + 1);
         out.push_back(lo + ORBX_EDGE); out.push_back(0);
     }
-    *box_w = (bw + 15) & ~15; *box_h = bh;
+    bw = (bw + 15) & ~15;
+    g.pyr_box_w = bw; g.pyr_box_h = bh;
+    for (int by = 0; by < nty; by++) out[ytiles + 2 * by + 1] = out[ytiles + 2 * by] * bw;
+    while (out.size() & 3) out.push_back(0);
+    g.pyr_xg_off = (int)out.size();
+    for (int gi = 0; gi < ntx * 32; gi++) {
+        const int cb = 12 + 4 * gi;
+        int x[4]; unsigned cf[4];
+        for (int k = 0; k < 4; k++) {
+            const OrbxResizeTap& t = h_taps[g.xtab_off + refl(std::min(cb + k, cols - 1) - ORBX_XOFF, g.w)];
+            x[k] = t.ofs; cf[k] = (unsigned)(unsigned short)t.c0 | ((unsigned)(unsigned short)t.c1 << 16);
+        }
+        const int x0 = std::min(std::min(x[0], x[1]), std::min(x[2], x[3]));
+        const int d0 = x[0] - x0, d1 = x[1] - x0, d2 = x[2] - x0, d3 = x[3] - x0;
+        out.push_back((x0 + ORBX_XOFF) & ~3);
+        out.push_back((x0 & 3) * 8);
+        out.push_back(d0 | ((d0 + 1) << 4) | (d1 << 8) | ((d1 + 1) << 12));
+        out.push_back(d2 | ((d2 + 1) << 4) | (d3 << 8) | ((d3 + 1) << 12));
+        for (int k = 0; k < 4; k++) out.push_back((int)cf[k]);
+    }
+    g.pyr_yr_off = (int)out.size();
+    for (int r = 0; r < nty * PYR_TH; r++) {
+        const OrbxResizeTap& t = h_taps[g.ytab_off + refl(std::min(r, rows - 1) - ORBX_EDGE, g.h)];
+        out.push_back((t.ofs + ORBX_EDGE) * bw);
+        out.push_back((int)((unsigned)(unsigned short)t.c0 << 16));
+        out.push_back((int)((unsigned)(unsigned short)t.c1 << 16));
+        out.push_back(0);
+    }
 }
 
 __global__ void __launch_bounds__(PYR_TX * PYR_TY) pyr_resize_generic_kernel(OrbxFrameLayout L, int level)
