@@ -43,6 +43,9 @@ struct orbx_extractor {
     static constexpr int MAX_SLOTS = 8;
     cudaStream_t slot_stream[MAX_SLOTS] = {};   // host-path double buffering (copy/compute overlap)
     cudaStream_t copy_stream = nullptr;          // host batch path: all uploads of a call, in order, ahead of the kernels
+    cudaStream_t side_stream = nullptr;          // the dense blur of a pipeline run, forked next to its quadtree (run_pipeline)
+    static constexpr int FORK_RING = 32;
+    cudaEvent_t fork_ev[FORK_RING][2] = {}; unsigned fork_ring = 0;
     struct Pending { int n = 0, cap = 0, nslots = 0; size_t fbytes = 0; const int* nkp = nullptr; const int* nkp2 = nullptr; cudaEvent_t done[MAX_SLOTS] = {}; };
     Pending pending[2]; int npending = 0;        // orbx_extract_batch_begin / _end: batches in flight, oldest first
     // a stereo batch in flight is recorded on the LEFT handle but runs on the right handle's working set too: the right
@@ -210,6 +213,8 @@ extern "C" void orbx_destroy(orbx_extractor* h)
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int j = 0; j < orbx_extractor::MAX_SLOTS; j++) if (h->slot_stream[j]) cudaStreamDestroy(h->slot_stream[j]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    for (auto& e : h->fork_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
     for (auto& pd : h->pending) for (cudaEvent_t e : pd.done) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->in_ready) cudaEventDestroy(e);
     for (cudaEvent_t e : h->in_free) cudaEventDestroy(e);
@@ -363,6 +368,10 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     if (orbx_device_count() <= 0) return fail(ORBX_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
     CK(cudaSetDevice(h->device));
     if (!h->stream) CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (!h->side_stream) {
+        CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        for (auto& e : h->fork_ev) { CK(cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming)); }
+    }
     CK(cudaStreamSynchronize(h->stream));
     for (int j = 0; j < orbx_extractor::MAX_SLOTS; j++) if (h->slot_stream[j]) CK(cudaStreamSynchronize(h->slot_stream[j]));
     release_device(h);
@@ -440,7 +449,7 @@ extern "C" int orbx_max_keypoints(const orbx_extractor* h) { return (h && h->W) 
 // streams, each in its own half of the working set)
 static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stride, size_t frame_pitch,
                         OrbxKp28* d_kps, uint8_t* d_desc, int cap, int* d_nkp, cudaStream_t st, int base = 0,
-                        int channels = 1, int rgb = 0, bool rectify = false)
+                        int channels = 1, int rgb = 0, bool rectify = false, bool fork_blur = true)
 {
     OrbxFrameLayout Lb = h->L;
     Lb.frame0 = base;
@@ -468,14 +477,16 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     if (nvtx) { nvtxRangePop(); nvtxRangePushA("FAST cells"); }
     if (tm) cudaEventRecord(ev[1], st);
     orbx_launch_fast(Lb, h->tm_fast, h->max_tile_w, h->max_tile_h, n, st);
-    static const int blur_overlap = getenv("ORBX_BLUR_OVERLAP") ? atoi(getenv("ORBX_BLUR_OVERLAP")) : 0;   // experiment
-    static cudaStream_t side = nullptr; static cudaEvent_t fev[16][2]; static int fring = 0;
+    // The dense blur only needs the pyramid, the quadtree only the FAST cells: the blur runs on a side stream next to the
+    // quadtree (a latency-bound kernel that leaves issue slots idle) and joins before the descriptors. Inside a stream
+    // capture the fork / join become two parallel branches of the graph. The chunked host paths keep the blur in line: they
+    // already run up to eight pipelines side by side, which fill each other's gaps, and one side stream would chain them
+    // (measured: 165.2 k -> 162.9 k frames/s end to end with the fork, 192.5 k -> 194.6 k resident).
+    static const bool blur_serial = getenv("ORBX_BLUR_SERIAL") != nullptr;
     cudaEvent_t* fe = nullptr;
-    if (blur_overlap) {
-        if (!side) { cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking); for (auto& e : fev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); } }
-        fe = fev[fring++ & 15];
-        cudaEventRecord(fe[0], st); cudaStreamWaitEvent(side, fe[0], 0);
-        if (blur_overlap == 1) { orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, side); cudaEventRecord(fe[1], side); }
+    if (fork_blur && !blur_serial && h->side_stream) {
+        fe = h->fork_ev[h->fork_ring++ % orbx_extractor::FORK_RING];
+        cudaEventRecord(fe[0], st); cudaStreamWaitEvent(h->side_stream, fe[0], 0);
     }
     if (nvtx) { nvtxRangePop(); nvtxRangePushA("DistributeOctTree"); }
     if (tm) cudaEventRecord(ev[2], st);
@@ -486,9 +497,10 @@ static int run_pipeline(orbx_extractor* h, const uint8_t* d_img, int n, int stri
     orbx_launch_quadtree(Lb, n, ((size_t)h->W * h->H <= (size_t)1 << 20 && !few) ? 256 : 1024, st);
     if (nvtx) { nvtxRangePop(); nvtxRangePushA("IC_Angle + blur + rBRIEF"); }
     if (tm) cudaEventRecord(ev[3], st);
-    if (blur_overlap == 2) { orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, side); cudaEventRecord(fe[1], side); }
-    if (blur_overlap) cudaStreamWaitEvent(st, fe[1], 0);
-    else orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, st);
+    if (fe) {
+        orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, h->side_stream);
+        cudaEventRecord(fe[1], h->side_stream); cudaStreamWaitEvent(st, fe[1], 0);
+    } else orbx_launch_blur(Lb, h->tm_blur_src, h->d_blur_units, (int)h->blur_units.size(), n, st);
     orbx_launch_describe(Lb, h->tm_desc, h->tm_desc_blur, n, d_kps, d_desc, cap, d_nkp, st);
     if (nvtx) nvtxRangePop();
     if (tm) cudaEventRecord(ev[4], st);
@@ -712,7 +724,7 @@ static int extract_batch_impl(orbx_extractor* h, const uint8_t* const* images, i
                 h->g1_channels = channels; h->g1_rgb = rgb; h->g1_rect = (int)rectify; h->g1_stride = rowbytes; h->g1_stream = st;
                 h->g1_seen = 0;
             }
-            rc = run_pipeline(h, d_in, m, rowbytes, fbytes, d_kps, d_desc, kc, d_nkp, st, base, channels, rgb, rectify);
+            rc = run_pipeline(h, d_in, m, rowbytes, fbytes, d_kps, d_desc, kc, d_nkp, st, base, channels, rgb, rectify, n <= chunk);
             if (single) h->g1_seen++;
         }
         if (rc != ORBX_OK) return rc;
@@ -1290,7 +1302,7 @@ static int stereo_extract_batch_impl(orbx_extractor* left, orbx_extractor* right
                     CK(cudaMemcpy2DAsync(d_in + (size_t)i * fbytes, width, sd.imgs[f0 + i], stride, width, height, cudaMemcpyHostToDevice, st));
                 }
             int rc = run_pipeline(sd.h, d_in, m, width, fbytes, sd.h->d_kps + (size_t)base * kc, sd.h->d_desc + (size_t)base * kc * 32, kc,
-                                  sd.h->d_nkp + base, st, base, 1, 0, rectify);
+                                  sd.h->d_nkp + base, st, base, 1, 0, rectify, false);
             if (rc != ORBX_OK) return rc;
         }
         OrbxStereoBatch a;
