@@ -117,10 +117,11 @@ def level_geometry(c):
 
 def algorithmic_bytes(c, nkp_mean):
     """per image B = P0 + 3A + N(961+60) for the reference's data flow; per stage of THIS design
-    (DESIGN.md §kernels): pyramid P0 + A, FAST A, quadtree 8 B per candidate (in+out, ~ignored), describe N*1021."""
+    (DESIGN.md §kernels): pyramid P0 + A, FAST A, quadtree 8 B per candidate (in+out, ~ignored), describe 2A (dense blur:
+    raw read + blurred write) + N*1021."""
     P0 = c["width"] * c["height"]
     A = sum(w * h for w, h in level_geometry(c))
-    return dict(P0=P0, A=A, B_survey=P0 + 3 * A + nkp_mean * 1021, pyramid=P0 + A, fast=A, describe=nkp_mean * 1021,
+    return dict(P0=P0, A=A, B_survey=P0 + 3 * A + nkp_mean * 1021, pyramid=P0 + A, fast=A, describe=2 * A + nkp_mean * 1021,
                 quadtree=0)
 
 
@@ -414,7 +415,7 @@ def run_frame(args, torch, dist, rank, world, local, dev):
             "config": {"workload": f"{w['cfg']} frame front-end: {W}x{H}, nFeatures={c['nfeatures']}: extract + UndistortKeyPoints + ComputeBoW "
                                    f"(synthetic vocabulary k=10 L=6, {V.nwords} words) + SearchByBoW and L1 score against the previous frame",
                        "frames_per_step_per_gpu": B, "distinct_frames": len(frames)},
-            "clocks": clocks, "gpu_launches": (c["nlevels"] + 3 + 1 + 2 + 3 + 1) * args.steps,
+            "clocks": clocks, "gpu_launches": (c["nlevels"] + 4 + 1 + 2 + 3 + 1) * args.steps,
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in outs)), "steps": n_e2e,
                     "api": "orbx_extract_device + orbx_undistort_keypoints_device + orbx_bow_transform_device + orbx_search_by_bow_device + orbx_bow_score_device, pinned host buffers"},
@@ -886,7 +887,7 @@ def stereo_measure(wname, P, steps, warmup, torch, dist, rank, world, local, dev
             "data": "synthetic",
             "config": {"workload": f"{w['cfg']} stereo: {W}x{H} pairs, nFeatures={c['nfeatures']} per image, left+right extraction + ComputeStereoMatches",
                        "pairs_per_step_per_gpu": P, "distinct_pairs": len(pairs)},
-            "clocks": clocks, "gpu_launches": (2 * (c["nlevels"] + 3) + 2) * args.steps,
+            "clocks": clocks, "gpu_launches": (2 * (c["nlevels"] + 4) + 2) * args.steps,
             "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * W * H, "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in outs)), "steps": n_e2e,
                     "api": "orbx_stereo_extract_batch_begin / _end (pinned host buffers, two batches in flight)",
                     "synchronous_call": {"value": e2e_sync_v, "api": "orbx_stereo_extract_batch, one blocking call per step"}},
@@ -1234,12 +1235,12 @@ def main():
         # roofline of the contract beside it
         roofline = {"bound": "issue", "bound_detail": "instruction issue / ALU pipe (ncu smsp__issue_active ~78 %, dram throughput ~5 %); achieved, peak and frac are the HBM roofline of the same kernel",
                     "issue": issue, "kernel": {"pyramid": "pyr_level0_kernel+pyr_resize_kernel (one launch per level)", "fast": "fast_cells_kernel",
-                                              "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]],
+                                              "quadtree": "quadtree_kernel", "describe": "blur_units_kernel+describe_kernel"}[names[dom]],
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
                     "algorithmic_bytes_per_frame": ab[names[dom]], "frames_per_launch": B, "traffic": traffic,
                     "traffic_source": (f"{prof_name} (dram read+write per frame x frames per launch)" if traffic is not None else None),
                     "stage_events_averaged_over_steps": nruns}
-        launches_per_step = c["nlevels"] + 3
+        launches_per_step = c["nlevels"] + 4          # one per pyramid level, FAST, quadtree, blur, describe
         line = {"metric": "orb_frames_per_s", "value": frames_per_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",

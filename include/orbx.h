@@ -167,6 +167,9 @@ int orbx_pyramid_level_device(orbx_extractor* h, int frame, int level, const uin
  * (cell-row-major, then FAST's row-major; ORBextractor.cc:903-912), coordinates relative to minBorder. */
 int orbx_debug_candidates(orbx_extractor* h, int frame, int level, OrbxKeyPoint* out, int cap, int* n);
 int orbx_debug_level_counts(orbx_extractor* h, int frame, int32_t* counts /* nlevels */);
+/* Stage tap: the payload (w x h) of level `level` after cv::GaussianBlur(.., Size(7,7), 2, 2, BORDER_REFLECT_101) —
+ * `workingMat` of ORBextractor.cc:1188-1190, which computeDescriptors samples. */
+int orbx_debug_blurred_level(orbx_extractor* h, int frame, int level, uint8_t* dst, int dst_stride);
 
 /* ---- ORBmatcher::DescriptorDistance (ORBmatcher.h:50, ORBmatcher.cc:1844-1860) + the best / second-best search
  *      idiom around it (ORBmatcher.cc:84-126): for every query row the FIRST train index attaining the minimum

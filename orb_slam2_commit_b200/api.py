@@ -108,6 +108,7 @@ def lib():
         L.orbx_get_stage_ms.argtypes = [C.c_void_p, f32p, i32p]
         L.orbx_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
         L.orbx_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, C.c_int]
+        L.orbx_debug_blurred_level.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, C.c_int]
         L.orbx_pyramid_level_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), i32p]
         L.orbx_debug_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, i32p]
         L.orbx_debug_level_counts.argtypes = [C.c_void_p, C.c_int, i32p]
@@ -367,6 +368,13 @@ class ORBextractor:
         return [self.pyramid_level(l) for l in range(self.nlevels)]
 
     # ---- stage taps for the parity tests
+    def blurred_level(self, level: int, frame: int = 0) -> np.ndarray:
+        """The level after cv::GaussianBlur 7x7 sigma 2 (`workingMat`, ORBextractor.cc:1188-1190)."""
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        _ck(self._L.orbx_debug_blurred_level(self._h, frame, level, _u8(out), w))
+        return out
+
     def debug_candidates(self, level: int, frame: int = 0) -> np.ndarray:
         n = C.c_int32(0)
         _ck(self._L.orbx_debug_candidates(self._h, frame, level, None, 0, C.byref(n)))

@@ -1013,6 +1013,21 @@ extern "C" int orbx_pyramid_level(orbx_extractor* h, int frame, int level, uint8
     return ORBX_OK;
 }
 
+extern "C" int orbx_debug_blurred_level(orbx_extractor* h, int frame, int level, uint8_t* dst, int dst_stride)
+{
+    const uint8_t* pay; int pitch;
+    int rc = finish_all_pending(h);
+    if (rc != ORBX_OK) return rc;
+    rc = orbx_pyramid_level_device(h, frame, level, &pay, &pitch);
+    if (rc != ORBX_OK) return rc;
+    const OrbxLevelGeom& g = h->lvl[level];
+    if (!dst || dst_stride < g.w) return fail(ORBX_ERR_INVALID, "dst too small");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy2D(dst, dst_stride, h->L.blur + (pay - h->L.raw), pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
 extern "C" int orbx_debug_level_counts(orbx_extractor* h, int frame, int32_t* counts)
 {
     if (!h || !h->W || h->last_frames <= 0) return fail(ORBX_ERR_STATE, "no extract has run yet");

@@ -61,6 +61,9 @@ def test_stages_match_oracle(name, seed):
     kps_o, desc_o = orc.extract(img)
     for l in range(c["nlevels"]):
         assert np.array_equal(ex.pyramid_level(l, with_apron=True), orc.level(l)), f"pyramid level {l}"
+        bo = orc.level(l, blurred=True)              # cv::GaussianBlur of the level (None when the level has no keypoints)
+        if bo is not None:
+            assert np.array_equal(ex.blurred_level(l), bo), f"GaussianBlur of level {l}"
         co = orc.candidates(l)
         cg = ex.debug_candidates(l)
         assert len(cg) == len(co), f"level {l}: {len(cg)} vs {len(co)} FAST candidates"

@@ -10,8 +10,8 @@ for w in tum1 euroc kitti 4k kitti_stereo euroc_stereo euroc_rect tum1_frame tum
 done
 CMD="python bench.py --workload tum1 --batch 128 --steps 2 --warmup 3 --no-cpu-baseline --no-hamming"
 if $CMD > $O/${T}_plain.log 2>&1; then
-  ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 33 -c 22 --csv --log-file $O/${T}_launches_raw.csv $CMD > $O/${T}_ncu_launch.log 2>&1
-  ncu --set full --clock-control none --import-source on --launch-skip 33 -c 11 -f -o $O/${T}_full $CMD > $O/${T}_ncu_full.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 36 -c 24 --csv --log-file $O/${T}_launches_raw.csv $CMD > $O/${T}_ncu_launch.log 2>&1
+  ncu --set full --clock-control none --import-source on --launch-skip 36 -c 12 -f -o $O/${T}_full $CMD > $O/${T}_ncu_full.log 2>&1
 else
   echo "plain run failed"; tail -5 $O/${T}_plain.log
 fi
