@@ -29,6 +29,7 @@ struct orbx_extractor {
     std::vector<OrbxBlurUnit> blur_units; OrbxBlurUnit* d_blur_units = nullptr;
     int blur_rows[ORBX_MAX_LEVELS] = {};          // output rows per blur unit of a level
     std::vector<int> pyr_tiles; int* d_pyr_tiles = nullptr;
+    std::vector<uint16_t> qt_path; uint16_t* d_qt_path = nullptr;   // quadtree path-code tables (orbx_qt_path_tables)
     // device memory
     void* d_pool = nullptr;                       // one allocation carved into the arrays of L
     OrbxLevelGeom* d_lvl = nullptr;
@@ -193,8 +194,8 @@ static void release_device(orbx_extractor* h)
     if (h->mirror) { cudaFreeHost(h->mirror); h->mirror = nullptr; h->mirror_bytes = 0; } h->mirror_frame = -1;
     cudaFree(h->stereo_scratch); h->stereo_scratch = nullptr; h->stereo_scratch_bytes = 0;
     cudaFree(h->stereo_out); h->stereo_out = nullptr; h->stereo_out_floats = 0;
-    cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps); cudaFree(h->d_pyr_tiles); cudaFree(h->d_blur_units);
-    h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr; h->d_pyr_tiles = nullptr; h->d_blur_units = nullptr;
+    cudaFree(h->d_lvl); cudaFree(h->d_cells); cudaFree(h->d_taps); cudaFree(h->d_pyr_tiles); cudaFree(h->d_blur_units); cudaFree(h->d_qt_path);
+    h->d_qt_path = nullptr; h->d_lvl = nullptr; h->d_cells = nullptr; h->d_taps = nullptr; h->d_pyr_tiles = nullptr; h->d_blur_units = nullptr;
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_nkp);
     h->d_in = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_nkp = nullptr; h->d_in_bytes = 0;
     h->W = h->H = h->max_batch = 0;
@@ -261,7 +262,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
     if (W > ORBX_MAX_DIM || H > ORBX_MAX_DIM) return fail(ORBX_ERR_UNSUPPORTED, "image larger than 4096 px");
     const int nl = h->nlevels;
     h->lvl.assign(nl, OrbxLevelGeom{});
-    h->cells.clear(); h->taps.clear(); h->pyr_tiles.clear(); h->blur_units.clear();
+    h->cells.clear(); h->taps.clear(); h->pyr_tiles.clear(); h->blur_units.clear(); h->qt_path.clear();
     size_t raw = 0; int slot = 0, cand = 0, kpc = 0, qtcap = 0, hist_ints = 0;
     h->max_tile_w = h->max_tile_h = 8;
     for (int l = 0; l < nl; l++) {
@@ -327,6 +328,7 @@ static int build_geometry(orbx_extractor* h, int W, int H)
             while (d > 0 && (ints(d) > 12288 || ((long long)g.nini << (2 * d)) > 65536)) d--;
             if (getenv("ORBX_QT_SWEEP_ONLY")) d = 0;
             g.qt_depth = d;
+            orbx_qt_path_tables(g, h->qt_path);
             hist_ints = std::max(hist_ints, (int)ints(d));
         }
         qtcap = std::max(qtcap, g.kp_cap);
@@ -407,7 +409,9 @@ extern "C" int orbx_reserve(orbx_extractor* h, int width, int height, int max_ba
     if (!h->pyr_tiles.empty()) CK(cudaMemcpy(h->d_pyr_tiles, h->pyr_tiles.data(), h->pyr_tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->d_blur_units, h->blur_units.size() * sizeof(OrbxBlurUnit)));
     CK(cudaMemcpy(h->d_blur_units, h->blur_units.data(), h->blur_units.size() * sizeof(OrbxBlurUnit), cudaMemcpyHostToDevice));
-    L.lvl = h->d_lvl; L.cells = h->d_cells; L.taps = h->d_taps; L.pyr_tiles = h->d_pyr_tiles;
+    CK(cudaMalloc(&h->d_qt_path, std::max<size_t>(h->qt_path.size(), 1) * sizeof(uint16_t)));
+    if (!h->qt_path.empty()) CK(cudaMemcpy(h->d_qt_path, h->qt_path.data(), h->qt_path.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    L.lvl = h->d_lvl; L.cells = h->d_cells; L.taps = h->d_taps; L.pyr_tiles = h->d_pyr_tiles; L.qt_path = h->d_qt_path;
     {
         int box_h[ORBX_MAX_LEVELS], box_d[ORBX_MAX_LEVELS], box_b[ORBX_MAX_LEVELS], box_s[ORBX_MAX_LEVELS];
         for (int l = 0; l < h->nlevels; l++) { box_h[l] = h->cells[h->lvl[l].cell0].box_h; box_d[l] = 31; box_b[l] = 37; box_s[l] = h->blur_rows[l] + 6; }

@@ -39,6 +39,7 @@ struct OrbxLevelGeom {
     int cand_cap;
     int kp_cap;               // capacity of the level's keypoint list
     int qt_depth;             // quadtree fast path: depth of the count pyramid (0 = always use the sweep path)
+    int qt_xs_off, qt_ys_off; // per-coordinate halves of the path code (orbx_qt_path_tables), offsets into OrbxFrameLayout::qt_path
     int xtab_off, ytab_off;   // offsets into the resize coefficient tables (elements)
     int resize_fast;          // every group of four outputs keeps its x-taps within 8 source bytes (orbx_pyr_fast_ok)
     int pyr_tile_off, pyr_ntx, pyr_nty, pyr_box_w, pyr_box_h;   // resize tiles of this level: table offset (ints), grid, TMA box of level l-1
@@ -74,6 +75,7 @@ struct OrbxFrameLayout {      // everything the kernels need, passed by value
     const OrbxCell* cells;          // device
     const OrbxResizeTap* taps;      // device
     const int* pyr_tiles;           // device: source boxes of the resize tiles (orbx_pyr_tiles)
+    const uint16_t* qt_path;        // device: quadtree path-code tables of every level (orbx_qt_path_tables)
     uint8_t* raw;                   // [B]
     uint8_t* blur;                  // [B] GaussianBlur of every level, same geometry as `raw` (read by the descriptor kernel only)
     uint32_t* slots;                // [B][slot_total]
@@ -117,6 +119,7 @@ bool orbx_pyr_fast_ok(const OrbxLevelGeom& g, const OrbxResizeTap* h_taps);
 void orbx_pyr_tiles(OrbxLevelGeom& g, const OrbxResizeTap* h_taps, std::vector<int>& out);
 void orbx_launch_fast(const OrbxFrameLayout& L, const OrbxTmaps& maps, int max_tile_w, int max_tile_h, int nframes, cudaStream_t st);
 int orbx_fast_tile_pitch(int max_tile_w);
+void orbx_qt_path_tables(OrbxLevelGeom& g, std::vector<uint16_t>& out);
 void orbx_launch_quadtree(const OrbxFrameLayout& L, int nframes, int threads, cudaStream_t st);
 void orbx_blur_units(const OrbxLevelGeom& g, int level, std::vector<OrbxBlurUnit>& out, int* rows_per_unit);
 void orbx_launch_blur(const OrbxFrameLayout& L, const OrbxTmaps& maps, const OrbxBlurUnit* d_units, int nunits, int nframes, cudaStream_t st);
