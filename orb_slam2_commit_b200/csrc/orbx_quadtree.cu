@@ -411,12 +411,13 @@ __global__ void __launch_bounds__(SMALL ? 256 : QT_MAX, SMALL ? 8 : 1) quadtree_
     for (int i = tid; i < n; i += QT) {
         const uint32_t xy = cand[i];
         int idx = node[i];
-        if (fast) {                                // walk the keypoint's path down to the leaf that owns it
-            const int code = idx;
-            idx = 0;
-            for (int t = 0; t <= DEPTH; t++) {
-                const int v = H[hbase(t) + (code >> (2 * (DEPTH - t)))];
+        if (fast) {                                // walk the keypoint's path UP to the leaf that owns it: the pyramid is one level
+            int code = idx, hb = hbase(DEPTH);     // deeper than a uniform spread needs, so the leaf is a step or two away
+            idx = 0;                               // (entries below a leaf hold counts >= 0, the leaf itself -(index + 1))
+            for (int t = DEPTH; t >= 0; t--) {
+                const int v = H[hb + code];
                 if (v < 0) { idx = -v - 1; break; }
+                code >>= 2; hb = (hb - g.nini) >> 2;       // hbase(t - 1)
             }
         }
         atomicMax(&best[idx], (int)(((xy >> 24) << 23) | (0x7fffffu - (uint32_t)i)));
