@@ -92,6 +92,16 @@ __device__ __forceinline__ unsigned quick_test(const unsigned v, const unsigned 
     return ~((X4 & X12) | (X0 & X8));
 }
 
+// predicated shared-memory stores (one instruction, no branch, no dummy-slot select)
+__device__ __forceinline__ void sts_u16_if(const unsigned p, const void* addr, const unsigned v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.u16 [%1], %2; }" ::"r"(p), "r"(orbx_smem_addr(addr)), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts_u8_if(const unsigned p, const void* addr, const unsigned v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.u8 [%1], %2; }" ::"r"(p), "r"(orbx_smem_addr(addr)), "r"(v) : "memory");
+}
+
 #define FAST_DARK 0x4000u      // list entry flags (bits 14 / 15); bits 0..13 = py * TP + px
 #define FAST_BRIGHT 0x8000u
 #define FAST_QMASK 0x40004000u // the two result bits of quick_test()
@@ -152,7 +162,6 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
         int cnt = 0;
         {
             const unsigned KT = ((unsigned)(T + 0x4000) << 16) + (unsigned)(0x4000 + T);
-            unsigned short* const dummy = list + cfg.list_cap;
             if (ew <= 32) {
                 const unsigned lanemask = lane < ew ? FAST_QMASK : 0u;
                 const uint8_t* q = tile + 3 + min(lane, ew - 1);           // clamped: loads stay inside the tile; q[ty * TP] = own column
@@ -165,8 +174,7 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
                     const unsigned nY = quick_test(w3, w0, w6, q[-3], q[3], KT) & lanemask;
                     const unsigned m = __ballot_sync(0xffffffffu, nY != 0);
                     const unsigned val = (unsigned)e + ((nY | (nY >> 15)) & (FAST_DARK | FAST_BRIGHT));
-                    unsigned short* dst = list + cnt + __popc(m & lt_mask);
-                    *(nY ? dst : dummy) = (unsigned short)val;
+                    sts_u16_if(nY, list + cnt + __popc(m & lt_mask), val);
                     cnt += __popc(m);
                     w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
                     q += TP; e += TP;
@@ -181,11 +189,9 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
                     const unsigned nY0 = quick_test(q0[0], q0[-3 * TP], q0[3 * TP], q0[-3], q0[3], KT) & FAST_QMASK;
                     const unsigned nY1 = quick_test(q1[0], q1[-3 * TP], q1[3 * TP], q1[-3], q1[3], KT) & lanemask1;
                     const unsigned m0 = __ballot_sync(0xffffffffu, nY0 != 0), m1 = __ballot_sync(0xffffffffu, nY1 != 0);
-                    unsigned short* d0 = list + cnt + __popc(m0 & lt_mask);
-                    *(nY0 ? d0 : dummy) = (unsigned short)((unsigned)e + ((nY0 | (nY0 >> 15)) & (FAST_DARK | FAST_BRIGHT)));
+                    sts_u16_if(nY0, list + cnt + __popc(m0 & lt_mask), (unsigned)e + ((nY0 | (nY0 >> 15)) & (FAST_DARK | FAST_BRIGHT)));
                     cnt += __popc(m0);
-                    unsigned short* d1 = list + cnt + __popc(m1 & lt_mask);
-                    *(nY1 ? d1 : dummy) = (unsigned short)((unsigned)(e + 32) + ((nY1 | (nY1 >> 15)) & (FAST_DARK | FAST_BRIGHT)));
+                    sts_u16_if(nY1, list + cnt + __popc(m1 & lt_mask), (unsigned)(e + 32) + ((nY1 | (nY1 >> 15)) & (FAST_DARK | FAST_BRIGHT)));
                     cnt += __popc(m1);
                     q0 += TP; q1 += TP; e += TP;
                 }
@@ -208,9 +214,9 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
             const bool is_corner = k < cnt && s >= T;
             const unsigned m = __ballot_sync(0xffffffffu, is_corner);
             __syncwarp();
-            // branch-free: lanes without a corner write the dummy list slot / the spare byte behind the score map
-            *(is_corner ? list + ncorner + __popc(m & lt_mask) : list + cfg.list_cap) = (unsigned short)e;
-            score[is_corner ? e - (e / TP) * (TP - SP) + (SP + 1) : cfg.score_bytes - 1] = (uint8_t)s;    // (py, px) -> py * SP + px
+            // branch-free: predicated stores
+            sts_u16_if(is_corner, list + ncorner + __popc(m & lt_mask), (unsigned)e);
+            sts_u8_if(is_corner, score + (e - (e / TP) * (TP - SP) + (SP + 1)), (unsigned)s);                // (py, px) -> py * SP + px
             ncorner += __popc(m);
         }
         __syncwarp();
