@@ -102,6 +102,31 @@ __device__ __forceinline__ void sts_u8_if(const unsigned p, const void* addr, co
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.u8 [%1], %2; }" ::"r"(p), "r"(orbx_smem_addr(addr)), "r"(v) : "memory");
 }
 
+// One row of the quick-test append: nY = ~Y & mask (the lanes that pass, with their polarity bits), ballot, prefix count,
+// predicated 16-bit store of `base + nY + (nY >> 15)` (entry | polarity flags in bits 14 / 15) at list_addr + 2 * prefix.
+// Returns the ballot. One predicate serves the vote and the store.
+__device__ __forceinline__ unsigned fast_append_row(const unsigned Y, const unsigned mask, const unsigned lt_mask, const uint32_t list_addr,
+                                                    const unsigned base)
+{
+    unsigned m;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .b32 ny, t, a, v;\n"
+        "lop3.b32 ny, %1, %2, 0, 0x0c;\n"            // ~Y & mask
+        "setp.ne.u32 q, ny, 0;\n"
+        "vote.sync.ballot.b32 %0, q, 0xffffffff;\n"
+        "and.b32 t, %0, %3;\n"
+        "popc.b32 t, t;\n"
+        "mad.lo.u32 a, t, 2, %4;\n"
+        "shr.u32 v, ny, 15;\n"
+        "add.u32 v, v, ny;\n"
+        "add.u32 v, v, %5;\n"
+        "@q st.shared.u16 [a], v;\n"
+        "}\n" : "=r"(m) : "r"(Y), "r"(mask), "r"(lt_mask), "r"(list_addr), "r"(base) : "memory");
+    return m;
+}
+
 #define FAST_DARK 0x4000u      // list entry flags (bits 14 / 15); bits 0..13 = py * TP + px
 #define FAST_BRIGHT 0x8000u
 #define FAST_QMASK 0x40004000u // the two result bits of quick_test()
@@ -167,18 +192,18 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
                 const uint8_t* q = tile + 3 + min(lane, ew - 1);           // clamped: loads stay inside the tile; q[ty * TP] = own column
                 unsigned w0 = q[0], w1 = q[TP], w2 = q[2 * TP], w3 = q[3 * TP], w4 = q[4 * TP], w5 = q[5 * TP];   // tile rows py .. py+5
                 q += 3 * TP;                                                // q[0] = centre pixel of row py
-                int e = lane;
+                unsigned e = lane;
+                uint32_t la = orbx_smem_addr(list);                         // address of list[cnt]
 #pragma unroll 6
                 for (int py = 0; py < eh; py++) {
                     const unsigned w6 = q[3 * TP];
-                    const unsigned nY = quick_test(w3, w0, w6, q[-3], q[3], KT) & lanemask;
-                    const unsigned m = __ballot_sync(0xffffffffu, nY != 0);
-                    const unsigned val = (unsigned)e + ((nY | (nY >> 15)) & (FAST_DARK | FAST_BRIGHT));
-                    sts_u16_if(nY, list + cnt + __popc(m & lt_mask), val);
-                    cnt += __popc(m);
+                    const unsigned Y = ~quick_test(w3, w0, w6, q[-3], q[3], KT);
+                    const unsigned m = fast_append_row(Y, lanemask, lt_mask, la, e);
+                    la += 2 * __popc(m);
                     w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
                     q += TP; e += TP;
                 }
+                cnt = (int)(la - orbx_smem_addr(list)) >> 1;
             } else {                                                        // cells wider than 32 px (< 64): two column chunks per row
                 const unsigned lanemask1 = lane + 32 < ew ? FAST_QMASK : 0u;
                 const uint8_t* q0 = tile + 3 * TP + 3 + lane;
