@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(32 * PYR_TY2, 8) pyr_resize_kernel(OrbxFrameLa
 {
     extern __shared__ __align__(128) uint8_t pyr_smem[];
     __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(16) uint4 s_yr[PYR_TY2][PYR_RRPT];    // the row entries of each warp (a warp's lanes share their rows)
     const OrbxLevelGeom* __restrict__ gp = L.lvl + level;
     const int gw = gp->w, gh = gp->h, gpitch = gp->pitch;
     const int bw = gp->pyr_box_w;
@@ -234,7 +235,11 @@ __global__ void __launch_bounds__(32 * PYR_TY2, 8) pyr_resize_kernel(OrbxFrameLa
     const bool live = cb < ORBX_XOFF + gw + ORBX_EDGE && rb0 < rows;
     const uint4* xg = reinterpret_cast<const uint4*>(L.pyr_tiles + gp->pyr_xg_off) + 2 * gi;
     const uint4 xa = xg[0], xc = xg[1];                     // (source column, s8, sel01, sel23), coefficient pairs
-    const uint4* __restrict__ yr = reinterpret_cast<const uint4*>(L.pyr_tiles + gp->pyr_yr_off) + rb0;
+    // the 16 row entries go through shared memory (one coalesced load per warp while the tile is in flight): read straight
+    // from global inside the row loop they were the kernel's main stall (long scoreboard, 4-6 per issue)
+    if (threadIdx.x < PYR_RRPT) s_yr[threadIdx.y][threadIdx.x] = (reinterpret_cast<const uint4*>(L.pyr_tiles + gp->pyr_yr_off) + rb0)[threadIdx.x];
+    __syncwarp();
+    const uint4* yr = s_yr[threadIdx.y];
     const unsigned s8 = xa.y, sel01 = xa.z, sel23 = xa.w;
     const uint8_t* sb = tile + ((int)xa.x - tx0.x) - ty0.y;  // + (source buffer row x box pitch) = the thread's window in that row
     orbx_mbar_wait(bar, 0);
