@@ -127,6 +127,29 @@ __device__ __forceinline__ unsigned fast_append_row(const unsigned Y, const unsi
     return m;
 }
 
+// The corner append of the score phase in one block: predicate (k < cnt && s >= T), ballot, prefix count, predicated stores of
+// the list entry and of the score byte. The vote is also the warp-level ordering the in-place compaction needs (every lane has
+// consumed its own entry before any lane overwrites one).
+__device__ __forceinline__ unsigned fast_append_corner(const int s, const int T, const int k, const int cnt, const unsigned lt_mask,
+                                                       const uint32_t list_addr, const unsigned e, const uint32_t score_addr)
+{
+    unsigned m;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .b32 t, a;\n"
+        "setp.ge.s32 q, %1, %2;\n"
+        "setp.lt.and.s32 q, %3, %4, q;\n"
+        "vote.sync.ballot.b32 %0, q, 0xffffffff;\n"
+        "and.b32 t, %0, %5;\n"
+        "popc.b32 t, t;\n"
+        "mad.lo.u32 a, t, 2, %6;\n"
+        "@q st.shared.u16 [a], %7;\n"
+        "@q st.shared.u8 [%8], %1;\n"
+        "}\n" : "=r"(m) : "r"(s), "r"(T), "r"(k), "r"(cnt), "r"(lt_mask), "r"(list_addr), "h"((unsigned short)e), "r"(score_addr) : "memory");
+    return m;
+}
+
 #define FAST_DARK 0x4000u      // list entry flags (bits 14 / 15); bits 0..13 = py * TP + px
 #define FAST_BRIGHT 0x8000u
 #define FAST_QMASK 0x40004000u // the two result bits of quick_test()
@@ -230,35 +253,32 @@ __global__ void __launch_bounds__(288, 4) fast_cells_kernel(OrbxFrameLayout L, F
         //    A score >= T needs an arc whose nine pixels are all beyond the threshold, hence two ADJACENT compass pixels
         //    beyond it on that side: only a polarity the entry's flags name can reach T.
         int ncorner = 0;
+        uint32_t lc = orbx_smem_addr(list);                              // address of list[ncorner]
+        const uint32_t score_base = orbx_smem_addr(score) + (SP + 1);
         for (int k0 = 0; k0 < cnt; k0 += 32) {
             const int k = k0 + lane;
             const unsigned ev = k < cnt ? list[k] : FAST_DARK;           // idle lanes score tile pixel (0,0): valid memory, result dropped
             const int e = ev & 0x3fff;
             const uint8_t* cp = tile + e + (3 * TP + 3);
             const int s = fast_arc_score(cp, TP, cp[0], (ev & FAST_DARK) ? 1 : -1, (ev & (FAST_DARK | FAST_BRIGHT)) == (FAST_DARK | FAST_BRIGHT)) - 1;
-            const bool is_corner = k < cnt && s >= T;
-            const unsigned m = __ballot_sync(0xffffffffu, is_corner);
-            __syncwarp();
-            // branch-free: predicated stores
-            sts_u16_if(is_corner, list + ncorner + __popc(m & lt_mask), (unsigned)e);
-            sts_u8_if(is_corner, score + (e - (e / TP) * (TP - SP) + (SP + 1)), (unsigned)s);                // (py, px) -> py * SP + px
-            ncorner += __popc(m);
+            const unsigned m = fast_append_corner(s, T, k, cnt, lt_mask, lc, (unsigned)e,
+                                                  score_base + (unsigned)(e - (e / TP) * (TP - SP)));   // (py, px) -> py * SP + px
+            lc += 2 * __popc(m);
         }
+        ncorner = (int)(lc - orbx_smem_addr(list)) >> 1;
         __syncwarp();
         // 3. strict 3x3 NMS over the corners (row-major) + ordered write
         for (int k0 = 0; k0 < ncorner; k0 += 32) {
             const int k = k0 + lane;
-            int keep = 0, s = 0, py = 0, px = 0;
-            if (k < ncorner) {
-                const int e = list[k];
-                py = e / TP; px = e - py * TP;
-                const uint8_t* q = score + py * SP + px + (SP + 1);
-                s = q[0];
-                // branch-free: strictly greater than the largest of the eight neighbours (list entries have s >= T > 0)
-                const int nmax = max(max(max(max((int)q[-1], (int)q[1]), (int)q[-SP - 1]), max((int)q[-SP], (int)q[-SP + 1])),
-                                     max(max((int)q[SP - 1], (int)q[SP]), (int)q[SP + 1]));
-                keep = s > nmax;
-            }
+            // branch-free: lanes past the end redo the last corner and drop the result
+            const int e = list[min(k, ncorner - 1)];
+            const int py = e / TP, px = e - py * TP;
+            const uint8_t* q = score + py * SP + px + (SP + 1);
+            const int s = q[0];
+            // strictly greater than the largest of the eight neighbours (list entries have s >= T > 0)
+            const int nmax = max(max(max(max((int)q[-1], (int)q[1]), (int)q[-SP - 1]), max((int)q[-SP], (int)q[-SP + 1])),
+                                 max(max((int)q[SP - 1], (int)q[SP]), (int)q[SP + 1]));
+            const bool keep = k < ncorner && s > nmax;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int off = total + __popc(m & lt_mask);
