@@ -169,7 +169,7 @@ extern "C" int orbx_frame_search_local_points(orbx_frame* f, const OrbxTrackQuer
     fd.kps = f->kpun(); fd.desc = f->desc(); fd.u_right = f->has_stereo ? f->ur() : nullptr;
     fd.occupied = occupied ? d_up + f->u_occ : nullptr; fd.n = n;
     fd.q = (const OrbxTrackQueryDev*)(d_up + f->u_q); fd.qdesc = d_up + f->u_qd; fd.qflags = d_up + f->u_qf; fd.nq = nq;
-    fd.match = (int*)(f->d_arena + f->o_match); fd.nmatches = fd.match + f->nmax; fd.assign = (int*)(f->d_arena + f->o_assign);
+    fd.match = (int*)(f->d_arena + f->o_match); fd.nmatches = fd.match + n; fd.assign = (int*)(f->d_arena + f->o_assign);   // count right behind the n matches: one copy down
     memcpy(f->h_up + f->u_fd, &fd, sizeof fd);
     memcpy(f->h_up + f->u_sf, scale_factors, (size_t)nlevels * 4);
     if (occupied) memcpy(f->h_up + f->u_occ, occupied, (size_t)n);
@@ -181,11 +181,10 @@ extern "C" int orbx_frame_search_local_points(orbx_frame* f, const OrbxTrackQuer
     CK(cudaMemcpyAsync(d_up, f->h_up, used, cudaMemcpyHostToDevice, f->st));
     orbx_launch_local_points((const OrbxLocalFrameDev*)(d_up + f->u_fd), 1, n, bounds4, (const float*)(d_up + f->u_sf), nlevels, th, nnratio, f->st);
     CK(cudaGetLastError());
-    // match[0..n) and nmatches come down together: nmatches sits at match[nmax], so copy the two pieces into the mirror
-    CK(cudaMemcpyAsync(f->h_dn, fd.match, (size_t)n * 4, cudaMemcpyDeviceToHost, f->st));
-    CK(cudaMemcpyAsync(f->h_dn + (size_t)f->nmax * 4, fd.nmatches, 4, cudaMemcpyDeviceToHost, f->st));
+    // match[0..n) and nmatches (at match[n]) come down in one copy
+    CK(cudaMemcpyAsync(f->h_dn, fd.match, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, f->st));
     CK(cudaStreamSynchronize(f->st));
     memcpy(match, f->h_dn, (size_t)n * 4);
-    memcpy(nmatches, f->h_dn + (size_t)f->nmax * 4, 4);
+    memcpy(nmatches, f->h_dn + (size_t)n * 4, 4);
     return ORBX_OK;
 }
