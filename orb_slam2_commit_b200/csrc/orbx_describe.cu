@@ -207,22 +207,21 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(OrbxFrameLayo
         uint32_t w[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) w[k] = rw[k];
-        unsigned rs = 0;
+        unsigned rs = 0, rs2 = 0;
+        int m10b = 0;                                      // two accumulator chains each: the dot products are dependent otherwise
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const unsigned x = __funnelshift_r(w[k], w[k + 1], sh8) & disc[k];
             const int u0 = 4 * k - 15;
             const unsigned wt = (unsigned)(u0 & 0xff) | ((unsigned)((u0 + 1) & 0xff) << 8) | ((unsigned)((u0 + 2) & 0xff) << 16) | ((unsigned)((u0 + 3) & 0xff) << 24);
-            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(x), "r"(wt));
-            rs = __dp4a(x, 0x01010101u, rs);
+            if (k & 1) { asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10b) : "r"(x), "r"(wt)); rs2 = __dp4a(x, 0x01010101u, rs2); }
+            else { asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(x), "r"(wt)); rs = __dp4a(x, 0x01010101u, rs); }
         }
-        m01 = (lane - 15) * (int)rs;
+        m10 += m10b;
+        m01 = (lane - 15) * (int)(rs + rs2);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);           // redux.sync: one instruction per warp sum
+    m01 = __reduce_add_sync(0xffffffffu, m01);
     const float angle = dev_fast_atan2((float)m01, (float)m10);
 
     // ---- steered rBRIEF: lane i -> descriptor byte i
