@@ -52,6 +52,22 @@ __global__ void hamming_init_kernel(unsigned long long* packed, int nq)
 __device__ __forceinline__ unsigned ht_xor(unsigned a, unsigned b) { unsigned r; asm("xor.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ unsigned ht_xor3(unsigned a, unsigned b, unsigned c) { unsigned r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ unsigned ht_maj(unsigned a, unsigned b, unsigned c) { unsigned r; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ int ht_mad(int a, int b, int c) { int r; asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+// key = dist << HT_SHIFT | idx, with the weighted popcount sum and the shift folded into multiply-adds (FMA pipe): the logic
+// pipe is the binding one (16 LOP3 + 3 min/max per pair), every op taken off it counts
+__device__ __forceinline__ int ht_key(const uint4 qa, const uint4 qb, const uint4 ta, const uint4 tb, const int idx)
+{
+    const unsigned x0 = ht_xor(qa.x, ta.x), x1 = ht_xor(qa.y, ta.y), x2 = ht_xor(qa.z, ta.z), x3 = ht_xor(qa.w, ta.w);
+    const unsigned x4 = ht_xor(qb.x, tb.x), x5 = ht_xor(qb.y, tb.y), x6 = ht_xor(qb.z, tb.z), x7 = ht_xor(qb.w, tb.w);
+    const unsigned s1 = ht_xor3(x0, x1, x2), c1 = ht_maj(x0, x1, x2);
+    const unsigned s2 = ht_xor3(x3, x4, x5), c2 = ht_maj(x3, x4, x5);
+    const unsigned s3 = ht_xor3(s1, s2, x6), c3 = ht_maj(s1, s2, x6);
+    const unsigned s4 = ht_xor3(c1, c2, c3), c4 = ht_maj(c1, c2, c3);
+    int k = ht_mad(__popc(c4), 4 << HT_SHIFT, idx);
+    k = ht_mad(__popc(s4), 2 << HT_SHIFT, k);
+    k = ht_mad(__popc(s3), 1 << HT_SHIFT, k);
+    return ht_mad(__popc(x7), 1 << HT_SHIFT, k);
+}
 __device__ __forceinline__ int ht_dist(const uint4 qa, const uint4 qb, const uint4 ta, const uint4 tb)
 {
     const unsigned x0 = ht_xor(qa.x, ta.x), x1 = ht_xor(qa.y, ta.y), x2 = ht_xor(qa.z, ta.z), x3 = ht_xor(qa.w, ta.w);
@@ -117,7 +133,11 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_top2_kernel(const uint4* _
             const uint4 ta = s_t[buf][2 * j], tb = s_t[buf][2 * j + 1];
 #pragma unroll
             for (int k = 0; k < HT_QPT; k++) {
+#ifdef ORBX_HAMMING_PLAIN_POPC
                 const int key = (ht_dist(qa[k], qb[k], ta, tb) << HT_SHIFT) | (jbase + j);
+#else
+                const int key = ht_key(qa[k], qb[k], ta, tb, jbase + j);
+#endif
                 const int hi = max(key, best[k]);
                 best[k] = min(best[k], key);
                 second[k] = min(second[k], hi);
