@@ -16,6 +16,9 @@
 #define HT_THREADS 256
 #define HT_QPT 2                 // queries per thread
 #define HT_TILE 256              // train rows per shared-memory tile (8 KB)
+#ifndef HT_GROUP
+#define HT_GROUP 4                // train rows per top-2 update group
+#endif
 #define HT_SHIFT 22              // local train index bits inside a key (slice <= 4M rows)
 #define HT_SLICE_MAX (1 << HT_SHIFT)
 
@@ -128,8 +131,41 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_top2_kernel(const uint4* _
         }
         const int rows = min(HT_TILE, t1 - (t0 + tile * HT_TILE));
         const int jbase = tile * HT_TILE;
-#pragma unroll 4
-        for (int j = 0; j < rows; j++) {
+        // Rows go HT_GROUP at a time: the top-2 update (three min/max per pair on the binding logic pipe) only runs when some
+        // lane's group minimum beats its current second best — after the first few thousand rows that is under 1 % of the
+        // groups (a running minimum improves ~ln(n) times). A skipped update would have been a no-op for every lane
+        // (key >= second >= best leaves both unchanged), so the result is the same.
+        int j = 0;
+#ifndef ORBX_HAMMING_PLAIN_POPC
+        for (; j + HT_GROUP <= rows; j += HT_GROUP) {
+            int key[HT_GROUP][HT_QPT];
+            bool improve = false;
+#pragma unroll
+            for (int r = 0; r < HT_GROUP; r++) {
+                const uint4 ta = s_t[buf][2 * (j + r)], tb = s_t[buf][2 * (j + r) + 1];
+#pragma unroll
+                for (int k = 0; k < HT_QPT; k++) key[r][k] = ht_key(qa[k], qb[k], ta, tb, jbase + j + r);
+            }
+#pragma unroll
+            for (int k = 0; k < HT_QPT; k++) {
+                int g = key[0][k];
+#pragma unroll
+                for (int r = 1; r < HT_GROUP; r++) g = min(g, key[r][k]);
+                improve = improve || g < second[k];
+            }
+            if (__any_sync(0xffffffffu, improve)) {
+#pragma unroll
+                for (int r = 0; r < HT_GROUP; r++)
+#pragma unroll
+                    for (int k = 0; k < HT_QPT; k++) {
+                        const int hi = max(key[r][k], best[k]);
+                        best[k] = min(best[k], key[r][k]);
+                        second[k] = min(second[k], hi);
+                    }
+            }
+        }
+#endif
+        for (; j < rows; j++) {
             const uint4 ta = s_t[buf][2 * j], tb = s_t[buf][2 * j + 1];
 #pragma unroll
             for (int k = 0; k < HT_QPT; k++) {
