@@ -1205,25 +1205,28 @@ def main():
         try:
             import csv as _csv
             import glob as _glob
-            prof = sorted(_glob.glob(os.path.join(ROOT, "profiles", "r0*_ncu_full_batch128.csv")))[-1]     # the newest committed capture
+            # the newest committed capture of THIS geometry: (file suffix, frames per captured launch)
+            cap_name, cap_frames = {"tum1": ("batch128", 128), "kitti": ("kitti", 128), "euroc": ("euroc", 128), "4k": ("4k", 16)}.get(w["cfg"], (None, 0))
+            prof = sorted(_glob.glob(os.path.join(ROOT, "profiles", f"r0*_ncu_full_{cap_name}.csv")))[-1]
             prof_name = os.path.relpath(prof, ROOT)
             key = {"pyramid": "pyr_resize_kernel", "fast": "fast_cells_kernel", "quadtree": "quadtree_kernel", "describe": "describe_kernel"}[names[dom]]
             rows_ = list(_csv.reader(open(prof)))
             hdr_ = rows_[0]
             ir = [i for i, c_ in enumerate(hdr_) if c_.startswith("dram__bytes_read.sum")][0]
             iw = [i for i, c_ in enumerate(hdr_) if c_.startswith("dram__bytes_write.sum")][0]
-            mb = sum(float(r_[ir]) + float(r_[iw]) for r_ in rows_[1:] if key in r_[0])
-            # a capture of the TUM1 geometry says nothing about another workload's traffic
-            traffic = mb * 1e6 / 128.0 * B if (w["cfg"] == "tum1" and not rectify) else None
+            unit_ = lambda c_: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[c_[c_.index("[") + 1:c_.index("]")]]
+            by = sum(float(r_[ir]) * unit_(hdr_[ir]) + float(r_[iw]) * unit_(hdr_[iw]) for r_ in rows_[1:] if key in r_[0])
+            # a capture of one geometry says nothing about another workload's traffic (nor about the fused-remap level 0)
+            traffic = by / cap_frames * B if not rectify else None
         except Exception:
-            traffic = None; prof_name = None
+            traffic = None; prof_name = None; cap_frames = 0
         # the binding resource of this integer/byte pipeline is instruction issue, not HBM: warp-instructions per frame
         # (committed ncu capture, TUM1 geometry) x measured frames/s against 148 SMs x 4 issue slots x the sampled SM clock
         issue = None
         try:
             ii = [i for i, c_ in enumerate(hdr_) if c_.startswith("smsp__inst_executed.sum")][0]
-            inst_per_frame = sum(float(r_[ii]) for r_ in rows_[1:]) / 128.0
-            if w["cfg"] == "tum1" and not rectify:
+            inst_per_frame = sum(float(r_[ii]) for r_ in rows_[1:]) / cap_frames
+            if cap_frames and not rectify:
                 peak_issue = 148 * 4 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
                 issue = {"warp_instructions_per_frame": inst_per_frame, "peak_warp_instructions_per_s": peak_issue,
                          "frac": inst_per_frame * frames_per_s / world / peak_issue,
