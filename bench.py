@@ -737,6 +737,25 @@ def run_matchers(args, torch, dist, rank, world, local, dev):
                                      "all_host_threads": {"frames_per_s": frame_mt_v, "threads": nthreads_h, "handles": nthreads_h,
                                                           "note": "every thread calls on its own handle / stream; the kernels of different handles overlap on the GPU"}}},
             "pipeline": {"matches_per_frame": float(d_nm.float().mean().item())}, "others": others}
+    if world == 1:
+        # the same calls from NATIVE host threads (tools/native/bench_frame_threads.cu, built here with nvcc): the Python threads
+        # above share one interpreter lock and spend ~25 us per call in it, which caps that leg near 40 k calls/s
+        try:
+            import subprocess, tempfile
+            tmp = tempfile.mkdtemp(prefix="orbx_native_")
+            exe, scene = os.path.join(tmp, "bench_frame_threads"), os.path.join(tmp, "lp_scene.bin")
+            csrc = os.path.join(ROOT, "orb_slam2_commit_b200", "csrc")
+            subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(ROOT, "tools", "native", "bench_frame_threads.cu"),
+                            "-I" + os.path.join(ROOT, "include"), "-L" + csrc, "-lorbx", "-Xlinker", "-rpath", "-Xlinker", csrc],
+                           check=True, capture_output=True, timeout=300)
+            subprocess.run([sys.executable, os.path.join(ROOT, "tools", "native", "dump_scene.py"), scene], check=True, capture_output=True, timeout=300)
+            out_ = subprocess.run([exe, scene, str(nthreads_h), "2000"], check=True, capture_output=True, text=True, timeout=300).stdout
+            nat = json.loads(out_.strip().splitlines()[-1])
+            line["e2e"]["frame_handle"]["native_host_threads"] = {"frames_per_s": nat["all_threads_calls_per_s"], "threads": nat["threads"],
+                                                                   "one_thread_frames_per_s": nat["one_thread_calls_per_s"],
+                                                                   "how": "tools/native/bench_frame_threads.cu: std::thread callers, one handle each, no interpreter between the calls"}
+        except Exception as e:  # the tool is optional: never lose the line
+            line["e2e"]["frame_handle"]["native_host_threads"] = {"error": str(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import binding as ob
         nthreads = os.cpu_count() or 1

@@ -12,6 +12,7 @@ struct orbx_frame {
     uint8_t* d_arena = nullptr;      // device
     uint8_t* h_up = nullptr;         // pinned: the packed upload of one call (mirrors the device layout from o_up on)
     uint8_t* h_dn = nullptr;         // pinned: match[nmax] + nmatches
+    void* h_dn_dev = nullptr;        // the device's address of h_dn (the matcher kernel stores its result there)
     // device offsets
     size_t o_kp = 0, o_kpun = 0, o_desc = 0, o_ur = 0, o_match = 0, o_assign = 0, o_up = 0;
     // offsets inside the upload block
@@ -65,6 +66,7 @@ extern "C" int orbx_frame_create(int device, int max_keypoints, int max_queries,
         orbx_frame_destroy(f);
         return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
     }
+    if ((e = cudaHostGetDevicePointer(&f->h_dn_dev, f->h_dn, 0)) != cudaSuccess) { orbx_frame_destroy(f); return fail(ORBX_ERR_CUDA, cudaGetErrorString(e)); }
     orbx_keep_mempool(device);
     *out = f;
     return ORBX_OK;
@@ -169,7 +171,8 @@ extern "C" int orbx_frame_search_local_points(orbx_frame* f, const OrbxTrackQuer
     fd.kps = f->kpun(); fd.desc = f->desc(); fd.u_right = f->has_stereo ? f->ur() : nullptr;
     fd.occupied = occupied ? d_up + f->u_occ : nullptr; fd.n = n;
     fd.q = (const OrbxTrackQueryDev*)(d_up + f->u_q); fd.qdesc = d_up + f->u_qd; fd.qflags = d_up + f->u_qf; fd.nq = nq;
-    fd.match = (int*)(f->d_arena + f->o_match); fd.nmatches = fd.match + n; fd.assign = (int*)(f->d_arena + f->o_assign);   // count right behind the n matches: one copy down
+    fd.match = (int*)(f->d_arena + f->o_match); fd.nmatches = fd.match + n; fd.assign = (int*)(f->d_arena + f->o_assign);
+    fd.result_out = (int*)f->h_dn_dev;
     memcpy(f->h_up + f->u_fd, &fd, sizeof fd);
     memcpy(f->h_up + f->u_sf, scale_factors, (size_t)nlevels * 4);
     if (occupied) memcpy(f->h_up + f->u_occ, occupied, (size_t)n);
@@ -181,8 +184,8 @@ extern "C" int orbx_frame_search_local_points(orbx_frame* f, const OrbxTrackQuer
     CK(cudaMemcpyAsync(d_up, f->h_up, used, cudaMemcpyHostToDevice, f->st));
     orbx_launch_local_points((const OrbxLocalFrameDev*)(d_up + f->u_fd), 1, n, bounds4, (const float*)(d_up + f->u_sf), nlevels, th, nnratio, f->st);
     CK(cudaGetLastError());
-    // match[0..n) and nmatches (at match[n]) come down in one copy
-    CK(cudaMemcpyAsync(f->h_dn, fd.match, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, f->st));
+    // the kernel stores match[0..n) and the count straight into the pinned host mirror (result_out): the call is one upload,
+    // one launch and one synchronisation — with 16 host threads the driver's per-call lock bounds the rate, not the GPU
     CK(cudaStreamSynchronize(f->st));
     memcpy(match, f->h_dn, (size_t)n * 4);
     memcpy(nmatches, f->h_dn + (size_t)n * 4, 4);

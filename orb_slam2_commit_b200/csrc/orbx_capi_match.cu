@@ -37,7 +37,7 @@ extern "C" int orbx_search_local_points_device(const OrbxLocalPointsFrame* frame
         OrbxLocalFrameDev& d = hf[p];
         d.kps = (const OrbxKp28*)f.keypoints; d.desc = f.descriptors; d.u_right = f.u_right; d.occupied = f.occupied; d.n = f.n;
         d.q = (const OrbxTrackQueryDev*)f.queries; d.qdesc = f.query_descriptors; d.qflags = f.query_flags; d.nq = f.nq;
-        d.match = f.match; d.nmatches = f.nmatches; d.assign = d_a + off; off += (size_t)f.nq;
+        d.match = f.match; d.nmatches = f.nmatches; d.assign = d_a + off; off += (size_t)f.nq; d.result_out = nullptr;
     }
     cudaError_t e;
     do {

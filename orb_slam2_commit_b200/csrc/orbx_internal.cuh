@@ -228,6 +228,9 @@ struct OrbxLocalFrameDev {
     const OrbxTrackQueryDev* q; const uint8_t* qdesc; const uint8_t* qflags; int nq;
     int* match; int* nmatches;
     int* assign;                                  // scratch, nq entries
+    int* result_out;                              // optional (NULL): the kernel also stores match[0..n) and the count at [n] here —
+                                                  // pinned host memory the device can write (the frame handle's one-frame calls: no
+                                                  // device-to-host copy call, and the driver's per-call lock is what bounds them)
 };
 void orbx_launch_local_points(const OrbxLocalFrameDev* d_frames, int nframes, int max_n, const float* bounds4,
                               const float* d_scale_factors, int nlevels, float th, float nnratio, cudaStream_t st);

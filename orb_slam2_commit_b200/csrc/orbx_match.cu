@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(512) local_points_kernel(const OrbxLocalFrameD
     if (mine) atomicAdd(&s_success, mine);
     __syncthreads();
     if (tid == 0) *P.nmatches = s_success;
+    if (P.result_out) {                                                          // the atomics above are this CTA's own: visible after the barrier
+        for (int i = tid; i < P.n; i += blockDim.x) P.result_out[i] = P.match[i];
+        if (tid == 0) P.result_out[P.n] = s_success;
+    }
 }
 
 void orbx_launch_local_points(const OrbxLocalFrameDev* d_frames, int nframes, int max_n, const float* bounds4,
